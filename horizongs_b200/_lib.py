@@ -1,0 +1,90 @@
+"""ctypes binding of libhgs_raster.so (the C ABI declared in include/hgs_raster.h).
+
+The product path has NO fallback: if the CUDA library is missing or fails to load,
+``lib()`` raises and every operator in this package fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_C", "libhgs_raster.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "hgs_raster.h")
+
+_p, _i, _ll, _f, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes) ; order = include/hgs_raster.h
+SIGNATURES = {
+    "hgs_abi_version": (_i, []),
+    "hgs_status_string": (C.c_char_p, [_i]),
+    "hgs_project3d_fwd": (_i, [_p] * 5 + [_i] * 4 + [_f] * 4 + [_i] + [_p] * 6 + [_p]),
+    "hgs_project3d_bwd": (_i, [_p] * 5 + [_i] * 4 + [_f] * 3 + [_p] * 7 + [_p]),
+    "hgs_project2d_fwd": (_i, [_p] * 5 + [_i] * 4 + [_f] * 3 + [_i] + [_p] * 6 + [_p]),
+    "hgs_project2d_bwd": (_i, [_p] * 5 + [_i] * 4 + [_f] * 2 + [_p] * 8 + [_p]),
+    "hgs_sh_fwd": (_i, [_i, _i] + [_p] * 5 + [_i, _i, _i] + [_p] + [_p]),
+    "hgs_sh_bwd": (_i, [_i, _i] + [_p] * 7 + [_i, _i, _i] + [_p] * 3 + [_p]),
+    "hgs_isect_count": (_i, [_p, _p, _ll, _i, _i, _i, _p, _p]),
+    "hgs_scan_temp_bytes": (_sz, [_ll]),
+    "hgs_isect_prepare_temp_bytes": (_sz, [_ll]),
+    "hgs_isect_sorted_temp_bytes": (_sz, [_ll, _ll]),
+    "hgs_exclusive_scan_i32": (_i, [_p, _p, _p, _ll, _p, _sz, _p]),
+    "hgs_isect_emit": (_i, [_p] * 4 + [_i] * 5 + [_p, _p, _p]),
+    "hgs_isect_prepare": (_i, [_p, _p, _i, _i, _p, _p, _p, _p, _sz, _p]),
+    "hgs_isect_sorted": (_i, [_p] * 5 + [_i, _i, _ll, _i, _i, _i] + [_p] * 4 + [_sz, _p]),
+    "hgs_isect_offset_encode": (_i, [_p, _ll, _i, _i, _i, _p, _p]),
+    "hgs_blend3d_fwd": (_i, [_p] * 6 + [_i] * 6 + [_p, _p, _ll] + [_p] * 3 + [_p]),
+    "hgs_blend3d_bwd": (_i, [_p] * 6 + [_i] * 6 + [_p, _p, _ll] + [_p] * 10 + [_p]),
+    "hgs_blend2d_fwd": (_i, [_p] * 7 + [_i] * 6 + [_p, _p, _ll] + [_p] * 7 + [_p]),
+    "hgs_blend2d_bwd": (_i, [_p] * 7 + [_i] * 6 + [_p, _p, _ll] + [_p] * 16 + [_p]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+class HgsError(RuntimeError):
+    pass
+
+
+def declared_symbols() -> list:
+    """Function names declared in include/hgs_raster.h (used by the CPU-side ABI test)."""
+    with open(HEADER_PATH) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(hgs_[a-z0-9_]+)\s*\(", text)))
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the C-ABI library; raise if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise HgsError(
+                    f"{LIB_PATH} is missing: build it with `python -m horizongs_b200.csrc.build` "
+                    "(or __graft_entry__.build()).  There is no CPU / PyTorch fallback for this path.")
+            handle = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(handle, name)
+                fn.restype = res
+                fn.argtypes = args
+            if handle.hgs_abi_version() != 1:
+                raise HgsError("libhgs_raster.so ABI version mismatch; rebuild")
+            _lib = handle
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = lib().hgs_status_string(status).decode()
+        raise HgsError(f"{what} failed: {msg} (status {status})")
+
+
+def ptr(t):
+    """device pointer of a tensor as c_void_p (None -> NULL)"""
+    return None if t is None else C.c_void_p(t.data_ptr())

@@ -1,0 +1,606 @@
+// Stages a8-a10: tile intersection, tile|depth ordering, per-tile ranges.  Integer work, bit-exact
+// against oracle/gsplat_oracle.py::isect_tiles / isect_offset_encode (= gsplat isect_tiles(sort=True)
+// + isect_offset_encode as reached inside gsplat.rasterization*, reference render.py:40,62).
+//
+// B200-first ordering.  gsplat emits I (key,value) pairs Gaussian-major and runs a generic
+// 64-bit LSD radix sort over 32 + tile_bits + cam_bits key bits (6 passes x 24 B r/w per pair).
+// The same order is produced here with far less HBM traffic:
+//   1. depth-order the C*N Gaussians once (u32 key = depth bits, 4 stable 8-bit passes over C*N pairs,
+//      plus a camera pass when C > 1);
+//   2. emit the pairs in that order (so pairs are already depth-ordered, ties in flat-index order);
+//   3. stable-partition the I pairs by (cam, tile) only: ceil((tile_bits+cam_bits)/8) passes of 8 B pairs.
+// A stable sort on (cam, tile) of a sequence ordered by (depth, flat index) is exactly the stable sort
+// on the full cam|tile|depth key of the Gaussian-major sequence: within one tile a Gaussian appears once,
+// so ties on the full key are ties on depth between different Gaussians and both orders break them by
+// ascending flat index.
+//
+// Radix pass = 3 launches (chunk histogram, single-block scan, chunk scatter); no inter-block waiting.
+// Roofline: HBM.  Per pass 4 B (hist) + 8 B + 8 B per pair.
+#include "hgs_common.cuh"
+#include "hgs_constants.cuh"
+#include "../../include/hgs_raster.h"
+
+namespace {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 8;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 2048 pairs per block iteration
+constexpr int RADIX = 256;
+constexpr int RS_MAX_CHUNKS = 148 * 4;
+constexpr int SCAN_THREADS = 1024;
+
+struct DigitSpec {
+    int shift;
+    uint32_t mask;
+    int from_val_div;  // 0: digit from key; >0: digit from (val / from_val_div)
+};
+__device__ __forceinline__ uint32_t digit_of(const DigitSpec& ds, uint32_t key, uint32_t val) {
+    uint32_t src = ds.from_val_div > 0 ? (val / (uint32_t)ds.from_val_div) : key;
+    return (src >> ds.shift) & ds.mask;
+}
+
+struct ChunkPlan {
+    int n_chunks;
+    int tiles_per_chunk;
+};
+static ChunkPlan plan_chunks(long long n) {
+    long long tiles = (n + RS_TILE - 1) / RS_TILE;
+    ChunkPlan p;
+    p.n_chunks = (int)(tiles < RS_MAX_CHUNKS ? (tiles > 0 ? tiles : 1) : RS_MAX_CHUNKS);
+    p.tiles_per_chunk = (int)((tiles + p.n_chunks - 1) / p.n_chunks);
+    if (p.tiles_per_chunk < 1) p.tiles_per_chunk = 1;
+    return p;
+}
+
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint32_t* __restrict__ keys,
+                                                                const uint32_t* __restrict__ vals, long long n,
+                                                                DigitSpec ds, int tiles_per_chunk,
+                                                                uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s_hist[RADIX];
+    for (int i = threadIdx.x; i < RADIX; i += RS_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    const long long begin = (long long)blockIdx.x * tiles_per_chunk * RS_TILE;
+    long long end = begin + (long long)tiles_per_chunk * RS_TILE;
+    if (end > n) end = n;
+    for (long long base = begin; base < end; base += RS_THREADS) {
+        long long i = base + threadIdx.x;
+        bool valid = i < end;
+        uint32_t d = valid ? digit_of(ds, keys[i], ds.from_val_div > 0 ? vals[i] : 0u) : 0xFFFFFFFFu;
+        unsigned m = __match_any_sync(0xFFFFFFFFu, d);
+        int leader = __ffs(m) - 1;
+        if (valid && (int)(threadIdx.x & 31) == leader) atomicAdd(&s_hist[d], (uint32_t)__popc(m));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < RADIX; i += RS_THREADS) hist[(long long)i * gridDim.x + blockIdx.x] = s_hist[i];
+}
+
+// exclusive scan of `total` u32 entries in place, single block
+__global__ void __launch_bounds__(SCAN_THREADS) scan_small_kernel(uint32_t* __restrict__ data, int total) {
+    __shared__ uint32_t s_sum[SCAN_THREADS];
+    const int per = (total + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int b = threadIdx.x * per;
+    int e = b + per;
+    if (e > total) e = total;
+    uint32_t sum = 0;
+    for (int i = b; i < e; ++i) sum += data[i];
+    s_sum[threadIdx.x] = sum;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over 1024 partial sums
+    for (int off = 1; off < SCAN_THREADS; off <<= 1) {
+        uint32_t v = threadIdx.x >= off ? s_sum[threadIdx.x - off] : 0u;
+        __syncthreads();
+        s_sum[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = s_sum[threadIdx.x] - sum;
+    for (int i = b; i < e; ++i) {
+        uint32_t v = data[i];
+        data[i] = run;
+        run += v;
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(
+    const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
+    uint32_t* __restrict__ vals_out, long long n, DigitSpec ds, int tiles_per_chunk,
+    const uint32_t* __restrict__ hist_scanned) {
+    __shared__ uint32_t s_base[RADIX];
+    __shared__ uint32_t s_whist[RS_WARPS][RADIX];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int i = threadIdx.x; i < RADIX; i += RS_THREADS) s_base[i] = hist_scanned[(long long)i * gridDim.x + blockIdx.x];
+    const long long begin = (long long)blockIdx.x * tiles_per_chunk * RS_TILE;
+    long long end = begin + (long long)tiles_per_chunk * RS_TILE;
+    if (end > n) end = n;
+
+    for (long long tile = begin; tile < end; tile += RS_TILE) {
+        uint32_t key[RS_ITEMS], val[RS_ITEMS], dig[RS_ITEMS], rank[RS_ITEMS];
+        bool valid[RS_ITEMS];
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            long long idx = tile + warp * (RS_ITEMS * 32) + i * 32 + lane;
+            valid[i] = idx < end;
+            key[i] = valid[i] ? keys_in[idx] : 0xFFFFFFFFu;
+            val[i] = valid[i] ? vals_in[idx] : 0u;
+            dig[i] = valid[i] ? digit_of(ds, key[i], val[i]) : (uint32_t)(RADIX - 1);
+        }
+#pragma unroll
+        for (int i = 0; i < RADIX / 32; ++i) s_whist[warp][i * 32 + lane] = 0;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            unsigned m = __match_any_sync(0xFFFFFFFFu, dig[i]);
+            rank[i] = s_whist[warp][dig[i]] + (uint32_t)__popc(m & lt_mask);
+            __syncwarp();
+            if (lane == __ffs(m) - 1) s_whist[warp][dig[i]] += (uint32_t)__popc(m);
+            __syncwarp();
+        }
+        __syncthreads();
+        {
+            // thread d: prefix over warps for digit d, starting from the running chunk base
+            const int d = threadIdx.x;  // RS_THREADS == RADIX
+            uint32_t run = s_base[d];
+#pragma unroll
+            for (int w = 0; w < RS_WARPS; ++w) {
+                uint32_t t = s_whist[w][d];
+                s_whist[w][d] = run;
+                run += t;
+            }
+            s_base[d] = run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            if (valid[i]) {
+                uint32_t pos = s_whist[warp][dig[i]] + rank[i];
+                keys_out[pos] = key[i];
+                vals_out[pos] = val[i];
+            }
+        }
+        __syncthreads();
+    }
+}
+static_assert(RS_THREADS == RADIX, "one thread per digit in the warp-prefix step");
+
+// one stable LSD pass: (keys_in, vals_in) -> (keys_out, vals_out)
+static int radix_pass(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
+                      long long n, DigitSpec ds, uint32_t* hist, cudaStream_t st) {
+    ChunkPlan p = plan_chunks(n);
+    radix_hist_kernel<<<p.n_chunks, RS_THREADS, 0, st>>>(keys_in, vals_in, n, ds, p.tiles_per_chunk, hist);
+    HGS_LAUNCH_CHECK();
+    scan_small_kernel<<<1, SCAN_THREADS, 0, st>>>(hist, RADIX * p.n_chunks);
+    HGS_LAUNCH_CHECK();
+    radix_scatter_kernel<<<p.n_chunks, RS_THREADS, 0, st>>>(keys_in, vals_in, keys_out, vals_out, n, ds,
+                                                            p.tiles_per_chunk, hist);
+    HGS_LAUNCH_CHECK();
+    return 0;
+}
+constexpr size_t HIST_BYTES = (size_t)RADIX * RS_MAX_CHUNKS * sizeof(uint32_t);
+
+static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+static int n_bits_of(long long n) {  // floor(log2(n)) + 1 for n >= 1
+    int b = 0;
+    while (n > 0) { ++b; n >>= 1; }
+    return b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// large exclusive scan (i32 in, i32 out, i64 total): reduce / scan-of-sums / scan
+// ---------------------------------------------------------------------------------------------
+constexpr int LS_THREADS = 256;
+constexpr int LS_ITEMS = 16;
+constexpr int LS_TILE = LS_THREADS * LS_ITEMS;
+
+__device__ __forceinline__ long long block_reduce_ll(long long v, long long* s_tmp) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if ((threadIdx.x & 31) == 0) s_tmp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    long long r = 0;
+    for (int w = 0; w < LS_THREADS / 32; ++w) r += s_tmp[w];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(LS_THREADS) ls_reduce_kernel(const int32_t* __restrict__ in, long long n,
+                                                               long long* __restrict__ block_sums) {
+    __shared__ long long s_tmp[LS_THREADS / 32];
+    const long long base = (long long)blockIdx.x * LS_TILE;
+    long long sum = 0;
+#pragma unroll
+    for (int i = 0; i < LS_ITEMS; ++i) {
+        long long idx = base + i * LS_THREADS + threadIdx.x;
+        if (idx < n) sum += in[idx];
+    }
+    long long tot = block_reduce_ll(sum, s_tmp);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) ls_scan_sums_kernel(long long* __restrict__ block_sums, int nb,
+                                                                    long long* __restrict__ total) {
+    __shared__ long long s_sum[SCAN_THREADS];
+    const int per = (nb + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int b = threadIdx.x * per;
+    int e = b + per;
+    if (e > nb) e = nb;
+    long long sum = 0;
+    for (int i = b; i < e; ++i) sum += block_sums[i];
+    s_sum[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = 1; off < SCAN_THREADS; off <<= 1) {
+        long long v = threadIdx.x >= off ? s_sum[threadIdx.x - off] : 0;
+        __syncthreads();
+        s_sum[threadIdx.x] += v;
+        __syncthreads();
+    }
+    long long run = s_sum[threadIdx.x] - sum;
+    for (int i = b; i < e; ++i) {
+        long long v = block_sums[i];
+        block_sums[i] = run;
+        run += v;
+    }
+    if (threadIdx.x == SCAN_THREADS - 1) total[0] = s_sum[SCAN_THREADS - 1];
+}
+
+__global__ void __launch_bounds__(LS_THREADS) ls_scan_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out,
+                                                             long long n, const long long* __restrict__ block_sums) {
+    // thread t owns LS_ITEMS consecutive items (blocked arrangement)
+    __shared__ long long s_warp[LS_THREADS / 32];
+    const long long base = (long long)blockIdx.x * LS_TILE + (long long)threadIdx.x * LS_ITEMS;
+    int32_t v[LS_ITEMS];
+    long long sum = 0;
+#pragma unroll
+    for (int i = 0; i < LS_ITEMS; ++i) {
+        long long idx = base + i;
+        v[i] = idx < n ? in[idx] : 0;
+        sum += v[i];
+    }
+    // exclusive scan of per-thread sums across the block
+    long long incl = sum;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        long long t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    long long wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += s_warp[w];
+    long long run = block_sums[blockIdx.x] + wbase + incl - sum;
+#pragma unroll
+    for (int i = 0; i < LS_ITEMS; ++i) {
+        long long idx = base + i;
+        if (idx < n) out[idx] = (int32_t)run;
+        run += v[i];
+    }
+}
+
+static int large_scan(const int32_t* in, int32_t* out, long long* total_dev, long long n, void* temp,
+                      size_t temp_bytes, cudaStream_t st) {
+    if (n <= 0) {
+        cudaError_t e = cudaMemsetAsync(total_dev, 0, sizeof(long long), st);
+        return (int)e;
+    }
+    const int nb = hgs_ceil_div(n, LS_TILE);
+    if (temp_bytes < (size_t)nb * sizeof(long long)) return HGS_ERR_WORKSPACE;
+    long long* sums = (long long*)temp;
+    ls_reduce_kernel<<<nb, LS_THREADS, 0, st>>>(in, n, sums);
+    HGS_LAUNCH_CHECK();
+    ls_scan_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(sums, nb, total_dev);
+    HGS_LAUNCH_CHECK();
+    ls_scan_kernel<<<nb, LS_THREADS, 0, st>>>(in, out, n, sums);
+    HGS_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a8 kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void isect_count_kernel(const float* __restrict__ means2d, const int32_t* __restrict__ radii, long long CN,
+                                   int tile_size, int tile_w, int tile_h, int32_t* __restrict__ tiles_per_gauss) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= CN) return;
+    int r = radii[i];
+    int cnt = 0;
+    if (r > 0) {
+        float2 m = reinterpret_cast<const float2*>(means2d)[i];
+        int x0, y0, x1, y1;
+        hgs_tile_bbox(m.x, m.y, (float)r, (float)tile_size, tile_w, tile_h, x0, y0, x1, y1);
+        cnt = (y1 - y0) * (x1 - x0);
+    }
+    tiles_per_gauss[i] = cnt;
+}
+
+// Gaussian-major emission of full 64-bit keys (gsplat sort=False layout)
+__global__ void isect_emit_kernel(const float* __restrict__ means2d, const int32_t* __restrict__ radii,
+                                  const float* __restrict__ depths, const int32_t* __restrict__ cum, long long CN,
+                                  int N, int tile_size, int tile_w, int tile_h, int tile_bits,
+                                  long long* __restrict__ isect_ids, int32_t* __restrict__ flatten_ids) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= CN) return;
+    int r = radii[i];
+    if (r <= 0) return;
+    float2 m = reinterpret_cast<const float2*>(means2d)[i];
+    int x0, y0, x1, y1;
+    hgs_tile_bbox(m.x, m.y, (float)r, (float)tile_size, tile_w, tile_h, x0, y0, x1, y1);
+    const long long cam_enc = (i / N) << (32 + tile_bits);
+    const long long depth_enc = (long long)__float_as_int(depths[i]);
+    long long cur = cum[i];
+    for (int y = y0; y < y1; ++y)
+        for (int x = x0; x < x1; ++x) {
+            long long tile_id = (long long)y * tile_w + x;
+            isect_ids[cur] = cam_enc | (tile_id << 32) | depth_enc;
+            flatten_ids[cur] = (int32_t)i;
+            ++cur;
+        }
+}
+
+__global__ void depth_keys_kernel(const float* __restrict__ depths, const int32_t* __restrict__ tiles_per_gauss,
+                                  long long CN, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= CN) return;
+    keys[i] = tiles_per_gauss[i] > 0 ? (uint32_t)__float_as_int(depths[i]) : 0xFFFFFFFFu;
+    vals[i] = (uint32_t)i;
+}
+
+__global__ void gather_counts_kernel(const uint32_t* __restrict__ vals, const int32_t* __restrict__ tiles_per_gauss,
+                                     long long CN, int32_t* __restrict__ order, int32_t* __restrict__ cnt_sorted) {
+    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= CN) return;
+    uint32_t g = vals[j];
+    order[j] = (int32_t)g;
+    cnt_sorted[j] = tiles_per_gauss[g];
+}
+
+// depth-ordered emission of (cam|tile key, flat index); one warp per 32 consecutive sorted Gaussians,
+// lanes cooperate on Gaussians that cover many tiles
+__global__ void __launch_bounds__(256) emit_sorted_kernel(const float* __restrict__ means2d,
+                                                          const int32_t* __restrict__ radii,
+                                                          const int32_t* __restrict__ order,
+                                                          const int32_t* __restrict__ cum_sorted, long long CN, int N,
+                                                          int tile_size, int tile_w, int tile_h, int tile_bits,
+                                                          uint32_t* __restrict__ tkeys, uint32_t* __restrict__ vals) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    uint32_t g = 0;
+    uint32_t cur = 0;
+    if (j < CN) {
+        g = (uint32_t)order[j];
+        int r = radii[g];
+        if (r > 0) {
+            float2 m = reinterpret_cast<const float2*>(means2d)[g];
+            hgs_tile_bbox(m.x, m.y, (float)r, (float)tile_size, tile_w, tile_h, x0, y0, x1, y1);
+            cur = (uint32_t)cum_sorted[j];
+        }
+    }
+    const int w = x1 - x0;
+    const int cnt = (y1 - y0) * w;
+    const uint32_t cam_enc = (g / (uint32_t)N) << tile_bits;
+    constexpr int BIG = 32;
+    if (cnt > 0 && cnt < BIG) {
+        for (int k = 0; k < cnt; ++k) {
+            int y = y0 + k / w, x = x0 + k % w;
+            tkeys[cur + k] = cam_enc | (uint32_t)(y * tile_w + x);
+            vals[cur + k] = g;
+        }
+    }
+    // big ones: whole warp writes
+    unsigned big = __ballot_sync(0xFFFFFFFFu, cnt >= BIG);
+    while (big) {
+        int src = __ffs(big) - 1;
+        big &= big - 1;
+        int bx0 = __shfl_sync(0xFFFFFFFFu, x0, src), by0 = __shfl_sync(0xFFFFFFFFu, y0, src);
+        int bw = __shfl_sync(0xFFFFFFFFu, w, src), bcnt = __shfl_sync(0xFFFFFFFFu, cnt, src);
+        uint32_t bcur = __shfl_sync(0xFFFFFFFFu, cur, src), bg = __shfl_sync(0xFFFFFFFFu, g, src);
+        uint32_t bcam = __shfl_sync(0xFFFFFFFFu, cam_enc, src);
+        for (int k = lane; k < bcnt; k += 32) {
+            int y = by0 + k / bw, x = bx0 + k % bw;
+            tkeys[bcur + k] = bcam | (uint32_t)(y * tile_w + x);
+            vals[bcur + k] = bg;
+        }
+    }
+}
+
+__global__ void finalize_sorted_kernel(const uint32_t* __restrict__ tkeys, const uint32_t* __restrict__ vals,
+                                       const float* __restrict__ depths, long long n_isects, int n_tiles,
+                                       int tile_bits, int total_tiles, long long* __restrict__ isect_ids,
+                                       int32_t* __restrict__ offsets) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_isects) return;
+    const uint32_t tk = tkeys[i];
+    const uint32_t g = vals[i];
+    isect_ids[i] = ((long long)tk << 32) | (long long)__float_as_int(depths[g]);
+    const uint32_t tmask = (1u << tile_bits) - 1u;
+    const int id_curr = (int)(tk >> tile_bits) * n_tiles + (int)(tk & tmask);
+    if (i == 0)
+        for (int t = 0; t <= id_curr; ++t) offsets[t] = 0;
+    if (i == n_isects - 1)
+        for (int t = id_curr + 1; t < total_tiles; ++t) offsets[t] = (int32_t)n_isects;
+    if (i > 0) {
+        const uint32_t tp = tkeys[i - 1];
+        const int id_prev = (int)(tp >> tile_bits) * n_tiles + (int)(tp & tmask);
+        for (int t = id_prev + 1; t <= id_curr; ++t) offsets[t] = (int32_t)i;
+    }
+}
+
+__global__ void offset_encode_kernel(const long long* __restrict__ isect_ids, long long n_isects, int n_tiles,
+                                     int tile_bits, int total_tiles, int32_t* __restrict__ offsets) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_isects) return;
+    const long long tmask = (1ll << tile_bits) - 1;
+    const long long hi = isect_ids[i] >> 32;
+    const int id_curr = (int)((hi >> tile_bits) * n_tiles + (hi & tmask));
+    if (i == 0)
+        for (int t = 0; t <= id_curr; ++t) offsets[t] = 0;
+    if (i == n_isects - 1)
+        for (int t = id_curr + 1; t < total_tiles; ++t) offsets[t] = (int32_t)n_isects;
+    if (i > 0) {
+        const long long hp = isect_ids[i - 1] >> 32;
+        const int id_prev = (int)((hp >> tile_bits) * n_tiles + (hp & tmask));
+        for (int t = id_prev + 1; t <= id_curr; ++t) offsets[t] = (int32_t)i;
+    }
+}
+
+}  // namespace
+
+HGS_API int hgs_isect_count(const float* means2d, const int32_t* radii, long long CN, int tile_size, int tile_w,
+                            int tile_h, int32_t* tiles_per_gauss, void* stream) {
+    if (CN < 0 || tile_size <= 0 || tile_w <= 0 || tile_h <= 0) return HGS_ERR_INVALID_ARG;
+    if (CN == 0) return 0;
+    isect_count_kernel<<<hgs_ceil_div(CN, 256), 256, 0, (cudaStream_t)stream>>>(means2d, radii, CN, tile_size, tile_w,
+                                                                                 tile_h, tiles_per_gauss);
+    HGS_LAUNCH_CHECK();
+    return 0;
+}
+
+HGS_API size_t hgs_scan_temp_bytes(long long n) {
+    return align_up((size_t)(hgs_ceil_div(n > 0 ? n : 1, LS_TILE)) * sizeof(long long));
+}
+
+HGS_API int hgs_exclusive_scan_i32(const int32_t* in, int32_t* out, long long* total_dev, long long n, void* temp,
+                                   size_t temp_bytes, void* stream) {
+    if (n < 0) return HGS_ERR_INVALID_ARG;
+    return large_scan(in, out, total_dev, n, temp, temp_bytes, (cudaStream_t)stream);
+}
+
+HGS_API int hgs_isect_emit(const float* means2d, const int32_t* radii, const float* depths, const int32_t* cum, int C,
+                           int N, int tile_size, int tile_w, int tile_h, long long* isect_ids, int32_t* flatten_ids,
+                           void* stream) {
+    if (C <= 0 || N < 0 || tile_size <= 0) return HGS_ERR_INVALID_ARG;
+    const long long CN = (long long)C * N;
+    if (CN == 0) return 0;
+    const int tile_bits = n_bits_of((long long)tile_w * tile_h);
+    isect_emit_kernel<<<hgs_ceil_div(CN, 256), 256, 0, (cudaStream_t)stream>>>(
+        means2d, radii, depths, cum, CN, N, tile_size, tile_w, tile_h, tile_bits, isect_ids, flatten_ids);
+    HGS_LAUNCH_CHECK();
+    return 0;
+}
+
+// temp layout for prepare: keysA, valsA, keysB, valsB (CN u32 each), cnt_sorted (CN i32), hist, scan temp
+HGS_API size_t hgs_isect_prepare_temp_bytes(long long CN) {
+    size_t a = align_up((size_t)(CN > 0 ? CN : 1) * 4);
+    return 5 * a + align_up(HIST_BYTES) + hgs_scan_temp_bytes(CN);
+}
+
+HGS_API int hgs_isect_prepare(const float* depths, const int32_t* tiles_per_gauss, int C, int N, int32_t* order,
+                              int32_t* cum_sorted, long long* total_dev, void* temp, size_t temp_bytes,
+                              void* stream) {
+    if (C <= 0 || N < 0) return HGS_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long CN = (long long)C * N;
+    if (CN >= (1ll << 31)) return HGS_ERR_TOO_LARGE;
+    if (CN == 0) return (int)cudaMemsetAsync(total_dev, 0, sizeof(long long), st);
+    if (temp_bytes < hgs_isect_prepare_temp_bytes(CN)) return HGS_ERR_WORKSPACE;
+    const size_t a = align_up((size_t)CN * 4);
+    char* p = (char*)temp;
+    uint32_t* kA = (uint32_t*)p; p += a;
+    uint32_t* vA = (uint32_t*)p; p += a;
+    uint32_t* kB = (uint32_t*)p; p += a;
+    uint32_t* vB = (uint32_t*)p; p += a;
+    int32_t* cnt_sorted = (int32_t*)p; p += a;
+    uint32_t* hist = (uint32_t*)p; p += align_up(HIST_BYTES);
+    void* scan_temp = p;
+
+    const int blocks = hgs_ceil_div(CN, 256);
+    depth_keys_kernel<<<blocks, 256, 0, st>>>(depths, tiles_per_gauss, CN, kA, vA);
+    HGS_LAUNCH_CHECK();
+    uint32_t *ki = kA, *vi = vA, *ko = kB, *vo = vB;
+    for (int pass = 0; pass < 4; ++pass) {
+        DigitSpec ds{pass * 8, 0xFFu, 0};
+        int rc = radix_pass(ki, vi, ko, vo, CN, ds, hist, st);
+        if (rc) return rc;
+        uint32_t* t;
+        t = ki; ki = ko; ko = t;
+        t = vi; vi = vo; vo = t;
+    }
+    if (C > 1) {
+        const int cam_bits = n_bits_of(C);
+        for (int shift = 0; shift < cam_bits; shift += 8) {
+            int nb = cam_bits - shift < 8 ? cam_bits - shift : 8;
+            DigitSpec ds{shift, (1u << nb) - 1u, N};
+            int rc = radix_pass(ki, vi, ko, vo, CN, ds, hist, st);
+            if (rc) return rc;
+            uint32_t* t;
+            t = ki; ki = ko; ko = t;
+            t = vi; vi = vo; vo = t;
+        }
+    }
+    gather_counts_kernel<<<blocks, 256, 0, st>>>(vi, tiles_per_gauss, CN, order, cnt_sorted);
+    HGS_LAUNCH_CHECK();
+    return large_scan(cnt_sorted, cum_sorted, total_dev, CN, scan_temp, hgs_scan_temp_bytes(CN), st);
+}
+
+// temp layout for sorted: tkeyA, tkeyB, valsT (I u32 each), hist
+HGS_API size_t hgs_isect_sorted_temp_bytes(long long CN, long long n_isects) {
+    (void)CN;
+    size_t a = align_up((size_t)(n_isects > 0 ? n_isects : 1) * 4);
+    return 3 * a + align_up(HIST_BYTES);
+}
+
+HGS_API int hgs_isect_sorted(const float* means2d, const int32_t* radii, const float* depths, const int32_t* order,
+                             const int32_t* cum_sorted, int C, int N, long long n_isects, int tile_size, int tile_w,
+                             int tile_h, long long* isect_ids, int32_t* flatten_ids, int32_t* isect_offsets,
+                             void* temp, size_t temp_bytes, void* stream) {
+    if (C <= 0 || N < 0 || n_isects < 0 || tile_size <= 0 || tile_w <= 0 || tile_h <= 0) return HGS_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long CN = (long long)C * N;
+    const int n_tiles = tile_w * tile_h;
+    const long long total_tiles_ll = (long long)C * n_tiles;
+    if (n_isects >= (1ll << 31) || total_tiles_ll >= (1ll << 31)) return HGS_ERR_TOO_LARGE;
+    const int total_tiles = (int)total_tiles_ll;
+    if (n_isects == 0) return (int)cudaMemsetAsync(isect_offsets, 0, (size_t)total_tiles * sizeof(int32_t), st);
+    const int tile_bits = n_bits_of(n_tiles);
+    const int cam_bits = n_bits_of(C);
+    if (tile_bits + cam_bits > 32) return HGS_ERR_TOO_LARGE;
+    if (temp_bytes < hgs_isect_sorted_temp_bytes(CN, n_isects)) return HGS_ERR_WORKSPACE;
+    const size_t a = align_up((size_t)n_isects * 4);
+    char* p = (char*)temp;
+    uint32_t* kA = (uint32_t*)p; p += a;
+    uint32_t* kB = (uint32_t*)p; p += a;
+    uint32_t* vT = (uint32_t*)p; p += a;
+    uint32_t* hist = (uint32_t*)p;
+
+    // when C == 1 the camera bit is always 0: sort tile bits only
+    const int key_bits = (C > 1) ? tile_bits + cam_bits : tile_bits;
+    const int n_pass = (key_bits + 7) / 8;
+    // choose ping-pong start so the last pass lands the values in flatten_ids
+    uint32_t* vF = (uint32_t*)flatten_ids;
+    uint32_t *ki = kA, *ko = kB;
+    uint32_t* vi = (n_pass % 2 == 0) ? vF : vT;
+    uint32_t* vo = (n_pass % 2 == 0) ? vT : vF;
+
+    emit_sorted_kernel<<<hgs_ceil_div(CN, 256), 256, 0, st>>>(means2d, radii, order, cum_sorted, CN, N, tile_size,
+                                                              tile_w, tile_h, tile_bits, ki, vi);
+    HGS_LAUNCH_CHECK();
+    for (int pass = 0; pass < n_pass; ++pass) {
+        int shift = pass * 8;
+        int nb = key_bits - shift < 8 ? key_bits - shift : 8;
+        DigitSpec ds{shift, (1u << nb) - 1u, 0};
+        int rc = radix_pass(ki, vi, ko, vo, n_isects, ds, hist, st);
+        if (rc) return rc;
+        uint32_t* t;
+        t = ki; ki = ko; ko = t;
+        t = vi; vi = vo; vo = t;
+    }
+    // now (ki, vi) hold the result and vi == flatten_ids (values are already in their output buffer)
+    finalize_sorted_kernel<<<hgs_ceil_div(n_isects, 256), 256, 0, st>>>(ki, vi, depths, n_isects, n_tiles, tile_bits,
+                                                                        total_tiles, isect_ids, isect_offsets);
+    HGS_LAUNCH_CHECK();
+    return 0;
+}
+
+HGS_API int hgs_isect_offset_encode(const long long* isect_ids, long long n_isects, int C, int tile_w, int tile_h,
+                                    int32_t* isect_offsets, void* stream) {
+    if (C <= 0 || tile_w <= 0 || tile_h <= 0 || n_isects < 0) return HGS_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_tiles = tile_w * tile_h;
+    const int total_tiles = C * n_tiles;
+    if (n_isects == 0) return (int)cudaMemsetAsync(isect_offsets, 0, (size_t)total_tiles * sizeof(int32_t), st);
+    offset_encode_kernel<<<hgs_ceil_div(n_isects, 256), 256, 0, st>>>(isect_ids, n_isects, n_tiles,
+                                                                      n_bits_of(n_tiles), total_tiles, isect_offsets);
+    HGS_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,254 @@
+// Stage a4: fused 2D-Gaussian (surfel) projection and its backward.
+//
+// Replaces gsplat's fully_fused_projection_2dgs as reached from the reference at
+// gaussian_renderer/render.py:171-186 (prefilter_voxel, 2D branch) and inside
+// gsplat.rasterization_2dgs (render.py:56-76).  Per surfel: H = [s0*r0, s1*r1, mu] in camera
+// space, ray transform M = K H (rows M0, M1, M2), projected centre and extent from M with
+// f = (1,1,-1)/(M2.M2*), radius = ceil(3 sqrt(max(1e-4, extent))), view-facing normal.
+// Built with -fmad=false; bit-matches oracle/gsplat_oracle.py::_project2d_one.
+//
+// Roofline: HBM.  fwd 40 B in, 64 B out (+4 B tile count) per surfel; bwd 40+68 B in, 40 B out.
+#include "hgs_common.cuh"
+#include "hgs_constants.cuh"
+#include "../../include/hgs_raster.h"
+
+namespace {
+
+constexpr int PB = 256;
+
+struct Proj2dFwd {
+    float mc[3];
+    float q[3][3];
+    float qn[4];
+    float inv_norm;
+    float RQ[3][3];
+    float M0[3], M1[3], M2[3];
+    float dist, f[3];
+    float m2x, m2y;
+};
+
+__device__ __forceinline__ bool proj2d_math(const HgsCam& cam, float px, float py, float pz, float qw, float qx, float qy,
+                                            float qz, float s0, float s1, float near_plane, float far_plane,
+                                            Proj2dFwd& o) {
+    const float (*R)[3] = cam.R;
+    o.mc[2] = R[2][0] * px + R[2][1] * py + R[2][2] * pz + cam.t[2];
+    if (o.mc[2] < near_plane || o.mc[2] > far_plane) return false;
+    o.mc[0] = R[0][0] * px + R[0][1] * py + R[0][2] * pz + cam.t[0];
+    o.mc[1] = R[1][0] * px + R[1][1] * py + R[1][2] * pz + cam.t[1];
+    hgs_quat_to_rot(qw, qx, qy, qz, o.q, &o.inv_norm, o.qn);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) o.RQ[i][j] = R[i][0] * o.q[0][j] + R[i][1] * o.q[1][j] + R[i][2] * o.q[2][j];
+    float WH[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        WH[i][0] = o.RQ[i][0] * s0;
+        WH[i][1] = o.RQ[i][1] * s1;
+        WH[i][2] = o.mc[i];
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        o.M0[j] = cam.fx * WH[0][j] + cam.cx * WH[2][j];
+        o.M1[j] = cam.fy * WH[1][j] + cam.cy * WH[2][j];
+        o.M2[j] = WH[2][j];
+    }
+    o.dist = o.M2[0] * o.M2[0] + o.M2[1] * o.M2[1] - o.M2[2] * o.M2[2];
+    if (o.dist == 0.f) return false;
+    const float invd = 1.0f / o.dist;
+    o.f[0] = invd; o.f[1] = invd; o.f[2] = -invd;
+    o.m2x = o.f[0] * o.M0[0] * o.M2[0] + o.f[1] * o.M0[1] * o.M2[1] + o.f[2] * o.M0[2] * o.M2[2];
+    o.m2y = o.f[0] * o.M1[0] * o.M2[0] + o.f[1] * o.M1[1] * o.M2[1] + o.f[2] * o.M1[2] * o.M2[2];
+    return true;
+}
+
+__global__ void __launch_bounds__(PB) project2d_fwd_kernel(
+    const float* __restrict__ means, const float* __restrict__ quats, const float* __restrict__ scales,
+    const float* __restrict__ viewmats, const float* __restrict__ Ks, int N, int W, int H, float near_plane,
+    float far_plane, float radius_clip, int tile_size, int tile_w, int tile_h, int32_t* __restrict__ radii,
+    float* __restrict__ means2d, float* __restrict__ depths, float* __restrict__ ray_transforms,
+    float* __restrict__ normals, int32_t* __restrict__ tiles_per_gauss) {
+    __shared__ float s_a[PB * 3];
+    __shared__ float s_b[PB * 3];
+    const int c = blockIdx.y;
+    const long long base = (long long)blockIdx.x * PB;
+    const long long n = base + threadIdx.x;
+    block_load_rows3<PB>(means, base, N, s_a);
+    block_load_rows3<PB>(scales, base, N, s_b);
+    __syncthreads();
+    const HgsCam cam = hgs_load_cam(viewmats, Ks, c);
+    int radius_i = 0, ntiles = 0;
+    float o_m2x = 0.f, o_m2y = 0.f, o_depth = 0.f;
+    float o_rt[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float o_n[3] = {0.f, 0.f, 0.f};
+    if (n < N) {
+        const float4 qv = reinterpret_cast<const float4*>(quats)[n];
+        Proj2dFwd f;
+        bool ok = proj2d_math(cam, s_a[threadIdx.x * 3], s_a[threadIdx.x * 3 + 1], s_a[threadIdx.x * 3 + 2], qv.x, qv.y,
+                              qv.z, qv.w, s_b[threadIdx.x * 3], s_b[threadIdx.x * 3 + 1], near_plane, far_plane, f);
+        if (ok) {
+            const float tmpx = f.f[0] * f.M0[0] * f.M0[0] + f.f[1] * f.M0[1] * f.M0[1] + f.f[2] * f.M0[2] * f.M0[2];
+            const float tmpy = f.f[0] * f.M1[0] * f.M1[0] + f.f[1] * f.M1[1] * f.M1[1] + f.f[2] * f.M1[2] * f.M1[2];
+            const float hx = f.m2x * f.m2x - tmpx;
+            const float hy = f.m2y * f.m2y - tmpy;
+            const float radius = ceilf(HGS_RADIUS_SIGMA * sqrtf(fmaxf(fmaxf(hx, hy), HGS_RADIUS_FLOOR_2DGS)));
+            bool vis = !(radius <= radius_clip);
+            vis = vis && !(f.m2x + radius <= 0.f || f.m2x - radius >= (float)W || f.m2y + radius <= 0.f ||
+                           f.m2y - radius >= (float)H);
+            if (vis) {
+                radius_i = (int)radius;
+                o_m2x = f.m2x; o_m2y = f.m2y; o_depth = f.mc[2];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { o_rt[j] = f.M0[j]; o_rt[3 + j] = f.M1[j]; o_rt[6 + j] = f.M2[j]; }
+                const float dotv = -f.RQ[0][2] * f.mc[0] + -f.RQ[1][2] * f.mc[1] + -f.RQ[2][2] * f.mc[2];
+                const float sign = dotv > 0.f ? 1.0f : -1.0f;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) o_n[i] = f.RQ[i][2] * sign;
+                if (tiles_per_gauss != nullptr && radius_i > 0) {
+                    int x0, y0, x1, y1;
+                    hgs_tile_bbox(o_m2x, o_m2y, (float)radius_i, (float)tile_size, tile_w, tile_h, x0, y0, x1, y1);
+                    ntiles = (y1 - y0) * (x1 - x0);
+                }
+            }
+        }
+        const long long idx = (long long)c * N + n;
+        radii[idx] = radius_i;
+        reinterpret_cast<float2*>(means2d)[idx] = make_float2(o_m2x, o_m2y);
+        depths[idx] = o_depth;
+        if (tiles_per_gauss != nullptr) tiles_per_gauss[idx] = ntiles;
+        // 36-byte rows: each thread writes its own row (L2 merges the sectors)
+        float* rt = ray_transforms + idx * 9;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) rt[k] = o_rt[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 3; ++k) s_a[threadIdx.x * 3 + k] = o_n[k];
+    __syncthreads();
+    block_store_rows3<PB>(normals + (long long)c * N * 3, base, N, s_a);
+}
+
+__global__ void __launch_bounds__(PB) project2d_bwd_kernel(
+    const float* __restrict__ means, const float* __restrict__ quats, const float* __restrict__ scales,
+    const float* __restrict__ viewmats, const float* __restrict__ Ks, int C, int N, float near_plane, float far_plane,
+    const int32_t* __restrict__ radii, const float* __restrict__ v_means2d, const float* __restrict__ v_depths,
+    const float* __restrict__ v_ray_transforms, const float* __restrict__ v_normals, float* __restrict__ v_means,
+    float* __restrict__ v_quats, float* __restrict__ v_scales) {
+    __shared__ float s_a[PB * 3];
+    __shared__ float s_b[PB * 3];
+    const long long base = (long long)blockIdx.x * PB;
+    const long long n = base + threadIdx.x;
+    block_load_rows3<PB>(means, base, N, s_a);
+    block_load_rows3<PB>(scales, base, N, s_b);
+    __syncthreads();
+    const float px = s_a[threadIdx.x * 3], py = s_a[threadIdx.x * 3 + 1], pz = s_a[threadIdx.x * 3 + 2];
+    const float s0 = s_b[threadIdx.x * 3], s1 = s_b[threadIdx.x * 3 + 1];
+    float4 qv = make_float4(1.f, 0.f, 0.f, 0.f);
+    if (n < N) qv = reinterpret_cast<const float4*>(quats)[n];
+    float g_mean[3] = {0.f, 0.f, 0.f}, g_scale[3] = {0.f, 0.f, 0.f}, g_quat[4] = {0.f, 0.f, 0.f, 0.f};
+
+    for (int c = 0; c < C; ++c) {
+        if (n >= N) break;
+        const long long idx = (long long)c * N + n;
+        if (radii[idx] <= 0) continue;
+        const HgsCam cam = hgs_load_cam(viewmats, Ks, c);
+        Proj2dFwd f;
+        if (!proj2d_math(cam, px, py, pz, qv.x, qv.y, qv.z, qv.w, s0, s1, near_plane, far_plane, f)) continue;
+        float vM0[3] = {0.f, 0.f, 0.f}, vM1[3] = {0.f, 0.f, 0.f}, vM2[3] = {0.f, 0.f, 0.f};
+        if (v_ray_transforms != nullptr) {
+            const float* vr = v_ray_transforms + idx * 9;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { vM0[j] = vr[j]; vM1[j] = vr[3 + j]; vM2[j] = vr[6 + j]; }
+        }
+        if (v_means2d != nullptr) {
+            const float2 vm = reinterpret_cast<const float2*>(v_means2d)[idx];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                vM0[j] += vm.x * f.f[j] * f.M2[j];
+                vM1[j] += vm.y * f.f[j] * f.M2[j];
+                vM2[j] += vm.x * f.f[j] * (f.M0[j] - 2.f * f.M2[j] * f.m2x) +
+                          vm.y * f.f[j] * (f.M1[j] - 2.f * f.M2[j] * f.m2y);
+            }
+        }
+        float vWH[3][3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            vWH[0][j] = cam.fx * vM0[j];
+            vWH[1][j] = cam.fy * vM1[j];
+            vWH[2][j] = cam.cx * vM0[j] + cam.cy * vM1[j] + vM2[j];
+        }
+        float vRQ[3][3];
+        float v_mc[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            vRQ[i][0] = vWH[i][0] * s0;
+            vRQ[i][1] = vWH[i][1] * s1;
+            vRQ[i][2] = 0.f;
+            v_mc[i] = vWH[i][2];
+        }
+        g_scale[0] += f.RQ[0][0] * vWH[0][0] + f.RQ[1][0] * vWH[1][0] + f.RQ[2][0] * vWH[2][0];
+        g_scale[1] += f.RQ[0][1] * vWH[0][1] + f.RQ[1][1] * vWH[1][1] + f.RQ[2][1] * vWH[2][1];
+        if (v_depths != nullptr) v_mc[2] += v_depths[idx];
+        if (v_normals != nullptr) {
+            const float dotv = -f.RQ[0][2] * f.mc[0] + -f.RQ[1][2] * f.mc[1] + -f.RQ[2][2] * f.mc[2];
+            const float sign = dotv > 0.f ? 1.0f : -1.0f;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) vRQ[i][2] = sign * v_normals[idx * 3 + i];
+        }
+        const float (*R)[3] = cam.R;
+        float vq_mat[3][3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) vq_mat[k][j] = R[0][k] * vRQ[0][j] + R[1][k] * vRQ[1][j] + R[2][k] * vRQ[2][j];
+            g_mean[k] += R[0][k] * v_mc[0] + R[1][k] * v_mc[1] + R[2][k] * v_mc[2];
+        }
+        float vq[4];
+        hgs_quat_to_rot_vjp(f.qn, f.inv_norm, vq_mat, vq);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) g_quat[k] += vq[k];
+    }
+    if (n < N) reinterpret_cast<float4*>(v_quats)[n] = make_float4(g_quat[0], g_quat[1], g_quat[2], g_quat[3]);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        s_a[threadIdx.x * 3 + k] = g_mean[k];
+        s_b[threadIdx.x * 3 + k] = g_scale[k];
+    }
+    __syncthreads();
+    block_store_rows3<PB>(v_means, base, N, s_a);
+    block_store_rows3<PB>(v_scales, base, N, s_b);
+}
+
+}  // namespace
+
+HGS_API int hgs_project2d_fwd(const float* means, const float* quats, const float* scales, const float* viewmats,
+                              const float* Ks, int C, int N, int width, int height, float near_plane, float far_plane,
+                              float radius_clip, int tile_size, int32_t* radii, float* means2d, float* depths,
+                              float* ray_transforms, float* normals, int32_t* tiles_per_gauss, void* stream) {
+    if (C <= 0 || N < 0 || width <= 0 || height <= 0 || tile_size <= 0) return HGS_ERR_INVALID_ARG;
+    if (N == 0) return 0;
+    const int tile_w = (width + tile_size - 1) / tile_size, tile_h = (height + tile_size - 1) / tile_size;
+    dim3 grid(hgs_ceil_div(N, PB), C);
+    project2d_fwd_kernel<<<grid, PB, 0, (cudaStream_t)stream>>>(means, quats, scales, viewmats, Ks, N, width, height,
+                                                                  near_plane, far_plane, radius_clip, tile_size, tile_w,
+                                                                  tile_h, radii, means2d, depths, ray_transforms,
+                                                                  normals, tiles_per_gauss);
+    HGS_LAUNCH_CHECK();
+    return 0;
+}
+
+HGS_API int hgs_project2d_bwd(const float* means, const float* quats, const float* scales, const float* viewmats,
+                              const float* Ks, int C, int N, int width, int height, float near_plane, float far_plane,
+                              const int32_t* radii, const float* v_means2d, const float* v_depths,
+                              const float* v_ray_transforms, const float* v_normals, float* v_means, float* v_quats,
+                              float* v_scales, void* stream) {
+    (void)width; (void)height;
+    if (C <= 0 || N < 0) return HGS_ERR_INVALID_ARG;
+    if (N == 0) return 0;
+    project2d_bwd_kernel<<<hgs_ceil_div(N, PB), PB, 0, (cudaStream_t)stream>>>(
+        means, quats, scales, viewmats, Ks, C, N, near_plane, far_plane, radii, v_means2d, v_depths, v_ray_transforms,
+        v_normals, v_means, v_quats, v_scales);
+    HGS_LAUNCH_CHECK();
+    return 0;
+}

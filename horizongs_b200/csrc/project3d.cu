@@ -1,0 +1,334 @@
+// Stage a3: fused 3D-Gaussian projection (world -> camera, quat+scale -> covariance,
+// perspective Jacobian, 2D covariance + eps2d, conic, integer radius, culling) with the
+// tile-count of stage a8 folded in, and its backward.
+//
+// Replaces gsplat's fully_fused_projection as reached from the reference at
+// gaussian_renderer/render.py:149-165 (prefilter_voxel) and inside gsplat.rasterization
+// (render.py:40-54).  Built with -fmad=false: every intermediate is rounded exactly like
+// oracle/gsplat_oracle.py::_project3d_one, so radii (integers) are bit-identical to the oracle.
+//
+// Roofline: HBM.  fwd 40 B in + 28 B out (+4 B tile count) per Gaussian; bwd 40+24(+28) B in, 40 B out.
+#include "hgs_common.cuh"
+#include "hgs_constants.cuh"
+
+namespace {
+
+constexpr int PB = 256;  // threads per block
+
+struct Proj3dFwd {
+    float xc, yc, zc;
+    float q[3][3];
+    float qn[4];
+    float inv_norm;
+    float M[3][3];
+    float Sc[3][3];
+    float rz, rz2, tx, ty;
+    bool x_unclamped, y_unclamped;
+    float j00, j11, j02, j12;
+    float c00, c01, c11;  // blurred 2D covariance
+    float det, det_orig;
+    float m2x, m2y;
+};
+
+// forward math shared by fwd and bwd kernels. returns false when culled by z.
+__device__ __forceinline__ bool proj3d_math(const HgsCam& cam, float px, float py, float pz, float qw, float qx, float qy,
+                                            float qz, float s0, float s1, float s2, float W, float H, float eps2d,
+                                            float near_plane, float far_plane, Proj3dFwd& o) {
+    const float (*R)[3] = cam.R;
+    o.zc = R[2][0] * px + R[2][1] * py + R[2][2] * pz + cam.t[2];
+    if (o.zc < near_plane || o.zc > far_plane) return false;
+    o.xc = R[0][0] * px + R[0][1] * py + R[0][2] * pz + cam.t[0];
+    o.yc = R[1][0] * px + R[1][1] * py + R[1][2] * pz + cam.t[1];
+
+    hgs_quat_to_rot(qw, qx, qy, qz, o.q, &o.inv_norm, o.qn);
+    const float s[3] = {s0, s1, s2};
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) o.M[i][j] = o.q[i][j] * s[j];
+    float S[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = i; j < 3; ++j) {
+            S[i][j] = o.M[i][0] * o.M[j][0] + o.M[i][1] * o.M[j][1] + o.M[i][2] * o.M[j][2];
+            S[j][i] = S[i][j];
+        }
+    float A[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) A[i][j] = R[i][0] * S[0][j] + R[i][1] * S[1][j] + R[i][2] * S[2][j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = i; j < 3; ++j) {
+            o.Sc[i][j] = A[i][0] * R[j][0] + A[i][1] * R[j][1] + A[i][2] * R[j][2];
+            o.Sc[j][i] = o.Sc[i][j];
+        }
+
+    const float fx = cam.fx, fy = cam.fy, cx = cam.cx, cy = cam.cy;
+    float tan_fovx = 0.5f * W / fx;
+    float tan_fovy = 0.5f * H / fy;
+    float lim_x_pos = (W - cx) / fx + HGS_FOV_MARGIN * tan_fovx;
+    float lim_x_neg = cx / fx + HGS_FOV_MARGIN * tan_fovx;
+    float lim_y_pos = (H - cy) / fy + HGS_FOV_MARGIN * tan_fovy;
+    float lim_y_neg = cy / fy + HGS_FOV_MARGIN * tan_fovy;
+    o.rz = 1.0f / o.zc;
+    o.rz2 = o.rz * o.rz;
+    float xr = o.xc * o.rz, yr = o.yc * o.rz;
+    o.x_unclamped = (xr <= lim_x_pos) && (xr >= -lim_x_neg);
+    o.y_unclamped = (yr <= lim_y_pos) && (yr >= -lim_y_neg);
+    o.tx = o.zc * fminf(lim_x_pos, fmaxf(-lim_x_neg, xr));
+    o.ty = o.zc * fminf(lim_y_pos, fmaxf(-lim_y_neg, yr));
+    o.j00 = fx * o.rz;
+    o.j11 = fy * o.rz;
+    o.j02 = -(fx * o.tx * o.rz2);
+    o.j12 = -(fy * o.ty * o.rz2);
+    float B00 = o.j00 * o.Sc[0][0] + o.j02 * o.Sc[2][0];
+    float B01 = o.j00 * o.Sc[0][1] + o.j02 * o.Sc[2][1];
+    float B02 = o.j00 * o.Sc[0][2] + o.j02 * o.Sc[2][2];
+    float B11 = o.j11 * o.Sc[1][1] + o.j12 * o.Sc[2][1];
+    float B12 = o.j11 * o.Sc[1][2] + o.j12 * o.Sc[2][2];
+    float c00 = B00 * o.j00 + B02 * o.j02;
+    float c01 = B01 * o.j11 + B02 * o.j12;
+    float c11 = B11 * o.j11 + B12 * o.j12;
+    o.m2x = fx * o.xc * o.rz + cx;
+    o.m2y = fy * o.yc * o.rz + cy;
+    o.det_orig = c00 * c11 - c01 * c01;
+    c00 = c00 + eps2d;
+    c11 = c11 + eps2d;
+    o.det = c00 * c11 - c01 * c01;
+    o.c00 = c00; o.c01 = c01; o.c11 = c11;
+    return true;
+}
+
+__global__ void __launch_bounds__(PB) project3d_fwd_kernel(
+    const float* __restrict__ means, const float* __restrict__ quats, const float* __restrict__ scales,
+    const float* __restrict__ viewmats, const float* __restrict__ Ks, int N, int W, int H, float eps2d,
+    float near_plane, float far_plane, float radius_clip, int tile_size, int tile_w, int tile_h,
+    int32_t* __restrict__ radii, float* __restrict__ means2d, float* __restrict__ depths, float* __restrict__ conics,
+    float* __restrict__ compensations, int32_t* __restrict__ tiles_per_gauss) {
+    __shared__ float s_a[PB * 3];
+    __shared__ float s_b[PB * 3];
+    const int c = blockIdx.y;
+    const long long base = (long long)blockIdx.x * PB;
+    const long long n = base + threadIdx.x;
+    block_load_rows3<PB>(means, base, N, s_a);
+    block_load_rows3<PB>(scales, base, N, s_b);
+    __syncthreads();
+    const HgsCam cam = hgs_load_cam(viewmats, Ks, c);
+
+    int radius_i = 0, ntiles = 0;
+    float o_m2x = 0.f, o_m2y = 0.f, o_depth = 0.f, o_ca = 0.f, o_cb = 0.f, o_cc = 0.f, o_comp = 0.f;
+    if (n < N) {
+        const float4 qv = reinterpret_cast<const float4*>(quats)[n];
+        Proj3dFwd f;
+        bool ok = proj3d_math(cam, s_a[threadIdx.x * 3 + 0], s_a[threadIdx.x * 3 + 1], s_a[threadIdx.x * 3 + 2], qv.x,
+                              qv.y, qv.z, qv.w, s_b[threadIdx.x * 3 + 0], s_b[threadIdx.x * 3 + 1],
+                              s_b[threadIdx.x * 3 + 2], (float)W, (float)H, eps2d, near_plane, far_plane, f);
+        if (ok && f.det > 0.f) {
+            float inv_det = 1.0f / f.det;
+            float b = 0.5f * (f.c00 + f.c11);
+            float v1 = b + sqrtf(fmaxf(b * b - f.det, HGS_EIG_FLOOR));
+            float radius = ceilf(HGS_RADIUS_SIGMA * sqrtf(v1));
+            bool vis = !(radius <= radius_clip);
+            vis = vis && !(f.m2x + radius <= 0.f || f.m2x - radius >= (float)W || f.m2y + radius <= 0.f ||
+                           f.m2y - radius >= (float)H);
+            if (vis) {
+                radius_i = (int)radius;
+                o_m2x = f.m2x; o_m2y = f.m2y; o_depth = f.zc;
+                o_ca = f.c11 * inv_det;
+                o_cb = -f.c01 * inv_det;
+                o_cc = f.c00 * inv_det;
+                o_comp = sqrtf(fmaxf(f.det_orig / f.det, 0.f));
+                if (tiles_per_gauss != nullptr && radius_i > 0) {
+                    int x0, y0, x1, y1;
+                    hgs_tile_bbox(o_m2x, o_m2y, (float)radius_i, (float)tile_size, tile_w, tile_h, x0, y0, x1, y1);
+                    ntiles = (y1 - y0) * (x1 - x0);
+                }
+            }
+        }
+        const long long idx = (long long)c * N + n;
+        radii[idx] = radius_i;
+        reinterpret_cast<float2*>(means2d)[idx] = make_float2(o_m2x, o_m2y);
+        depths[idx] = o_depth;
+        if (compensations != nullptr) compensations[idx] = o_comp;
+        if (tiles_per_gauss != nullptr) tiles_per_gauss[idx] = ntiles;
+    }
+    __syncthreads();
+    s_a[threadIdx.x * 3 + 0] = o_ca;
+    s_a[threadIdx.x * 3 + 1] = o_cb;
+    s_a[threadIdx.x * 3 + 2] = o_cc;
+    __syncthreads();
+    block_store_rows3<PB>(conics + (long long)c * N * 3, base, N, s_a);
+}
+
+// One thread per Gaussian, loop over cameras: gradients w.r.t. means/quats/scales are summed
+// over the C views without atomics (deterministic).
+__global__ void __launch_bounds__(PB) project3d_bwd_kernel(
+    const float* __restrict__ means, const float* __restrict__ quats, const float* __restrict__ scales,
+    const float* __restrict__ viewmats, const float* __restrict__ Ks, int C, int N, int W, int H, float eps2d,
+    float near_plane, float far_plane, const int32_t* __restrict__ radii, const float* __restrict__ v_means2d,
+    const float* __restrict__ v_depths, const float* __restrict__ v_conics, float* __restrict__ v_means,
+    float* __restrict__ v_quats, float* __restrict__ v_scales) {
+    __shared__ float s_a[PB * 3];
+    __shared__ float s_b[PB * 3];
+    __shared__ float s_c[PB * 3];
+    const long long base = (long long)blockIdx.x * PB;
+    const long long n = base + threadIdx.x;
+    block_load_rows3<PB>(means, base, N, s_a);
+    block_load_rows3<PB>(scales, base, N, s_b);
+    __syncthreads();
+    const float px = s_a[threadIdx.x * 3 + 0], py = s_a[threadIdx.x * 3 + 1], pz = s_a[threadIdx.x * 3 + 2];
+    const float s0 = s_b[threadIdx.x * 3 + 0], s1 = s_b[threadIdx.x * 3 + 1], s2 = s_b[threadIdx.x * 3 + 2];
+    float4 qv = make_float4(1.f, 0.f, 0.f, 0.f);
+    if (n < N) qv = reinterpret_cast<const float4*>(quats)[n];
+
+    float g_mean[3] = {0.f, 0.f, 0.f};
+    float g_scale[3] = {0.f, 0.f, 0.f};
+    float g_quat[4] = {0.f, 0.f, 0.f, 0.f};
+
+    for (int c = 0; c < C; ++c) {
+        // coalesced staging of this camera's v_conics rows
+        __syncthreads();
+        block_load_rows3<PB>(v_conics + (long long)c * N * 3, base, N, s_c);
+        __syncthreads();
+        if (n >= N) continue;
+        const long long idx = (long long)c * N + n;
+        if (radii[idx] <= 0) continue;
+        const HgsCam cam = hgs_load_cam(viewmats, Ks, c);
+        Proj3dFwd f;
+        if (!proj3d_math(cam, px, py, pz, qv.x, qv.y, qv.z, qv.w, s0, s1, s2, (float)W, (float)H, eps2d, near_plane,
+                         far_plane, f))
+            continue;
+        const float2 vm = reinterpret_cast<const float2*>(v_means2d)[idx];
+        const float vd = v_depths != nullptr ? v_depths[idx] : 0.f;
+        const float va = s_c[threadIdx.x * 3 + 0], vb = 0.5f * s_c[threadIdx.x * 3 + 1], vc = s_c[threadIdx.x * 3 + 2];
+
+        // conic X = inv(Sigma2'), v_Sigma2 = -X V X
+        const float inv_det = 1.0f / f.det;
+        const float a = f.c11 * inv_det, b = -f.c01 * inv_det, cc = f.c00 * inv_det;
+        const float xv00 = a * va + b * vb, xv01 = a * vb + b * vc;
+        const float xv10 = b * va + cc * vb, xv11 = b * vb + cc * vc;
+        const float G00 = -(xv00 * a + xv01 * b);
+        const float G01 = -(xv00 * b + xv01 * cc);
+        const float G11 = -(xv10 * b + xv11 * cc);
+
+        // Sigma2 = J Sc J^T
+        const float GJ[2][3] = {{G00 * f.j00, G01 * f.j11, G00 * f.j02 + G01 * f.j12},
+                                {G01 * f.j00, G11 * f.j11, G01 * f.j02 + G11 * f.j12}};
+        float vSc[3][3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            vSc[0][j] = f.j00 * GJ[0][j];
+            vSc[1][j] = f.j11 * GJ[1][j];
+            vSc[2][j] = f.j02 * GJ[0][j] + f.j12 * GJ[1][j];
+        }
+        const float vJ00 = 2.f * (GJ[0][0] * f.Sc[0][0] + GJ[0][1] * f.Sc[1][0] + GJ[0][2] * f.Sc[2][0]);
+        const float vJ02 = 2.f * (GJ[0][0] * f.Sc[0][2] + GJ[0][1] * f.Sc[1][2] + GJ[0][2] * f.Sc[2][2]);
+        const float vJ11 = 2.f * (GJ[1][0] * f.Sc[0][1] + GJ[1][1] * f.Sc[1][1] + GJ[1][2] * f.Sc[2][1]);
+        const float vJ12 = 2.f * (GJ[1][0] * f.Sc[0][2] + GJ[1][1] * f.Sc[1][2] + GJ[1][2] * f.Sc[2][2]);
+
+        const float fx = cam.fx, fy = cam.fy;
+        const float rz3 = f.rz2 * f.rz;
+        float v_xc = fx * f.rz * vm.x;
+        float v_yc = fy * f.rz * vm.y;
+        float v_zc = -(fx * f.xc * vm.x + fy * f.yc * vm.y) * f.rz2 + vd;
+        v_zc += -fx * f.rz2 * vJ00 - fy * f.rz2 * vJ11;
+        if (f.x_unclamped) {
+            v_xc += -fx * f.rz2 * vJ02;
+            v_zc += 2.f * fx * f.tx * rz3 * vJ02;
+        } else {
+            v_zc += fx * f.tx * rz3 * vJ02;
+        }
+        if (f.y_unclamped) {
+            v_yc += -fy * f.rz2 * vJ12;
+            v_zc += 2.f * fy * f.ty * rz3 * vJ12;
+        } else {
+            v_zc += fy * f.ty * rz3 * vJ12;
+        }
+
+        const float (*R)[3] = cam.R;
+        g_mean[0] += R[0][0] * v_xc + R[1][0] * v_yc + R[2][0] * v_zc;
+        g_mean[1] += R[0][1] * v_xc + R[1][1] * v_yc + R[2][1] * v_zc;
+        g_mean[2] += R[0][2] * v_xc + R[1][2] * v_yc + R[2][2] * v_zc;
+
+        // Sc = R S R^T  ->  vS = R^T vSc R
+        float T[3][3], vS[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) T[i][j] = vSc[i][0] * R[0][j] + vSc[i][1] * R[1][j] + vSc[i][2] * R[2][j];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) vS[i][j] = R[0][i] * T[0][j] + R[1][i] * T[1][j] + R[2][i] * T[2][j];
+        // S = M M^T -> vM = (vS + vS^T) M
+        float vM[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                vM[i][j] = (vS[i][0] + vS[0][i]) * f.M[0][j] + (vS[i][1] + vS[1][i]) * f.M[1][j] +
+                           (vS[i][2] + vS[2][i]) * f.M[2][j];
+        // M = q diag(s)
+        const float s[3] = {s0, s1, s2};
+        float vq_mat[3][3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            g_scale[j] += f.q[0][j] * vM[0][j] + f.q[1][j] * vM[1][j] + f.q[2][j] * vM[2][j];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) vq_mat[i][j] = vM[i][j] * s[j];
+        }
+        float vq[4];
+        hgs_quat_to_rot_vjp(f.qn, f.inv_norm, vq_mat, vq);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) g_quat[k] += vq[k];
+    }
+
+    if (n < N) reinterpret_cast<float4*>(v_quats)[n] = make_float4(g_quat[0], g_quat[1], g_quat[2], g_quat[3]);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        s_a[threadIdx.x * 3 + k] = g_mean[k];
+        s_b[threadIdx.x * 3 + k] = g_scale[k];
+    }
+    __syncthreads();
+    block_store_rows3<PB>(v_means, base, N, s_a);
+    block_store_rows3<PB>(v_scales, base, N, s_b);
+}
+
+}  // namespace
+
+#include "../../include/hgs_raster.h"
+
+HGS_API int hgs_project3d_fwd(const float* means, const float* quats, const float* scales, const float* viewmats,
+                              const float* Ks, int C, int N, int width, int height, float eps2d, float near_plane,
+                              float far_plane, float radius_clip, int tile_size, int32_t* radii, float* means2d,
+                              float* depths, float* conics, float* compensations, int32_t* tiles_per_gauss,
+                              void* stream) {
+    if (C <= 0 || N < 0 || width <= 0 || height <= 0 || tile_size <= 0) return HGS_ERR_INVALID_ARG;
+    if (N == 0) return 0;
+    const int tile_w = (width + tile_size - 1) / tile_size, tile_h = (height + tile_size - 1) / tile_size;
+    dim3 grid(hgs_ceil_div(N, PB), C);
+    project3d_fwd_kernel<<<grid, PB, 0, (cudaStream_t)stream>>>(means, quats, scales, viewmats, Ks, N, width, height,
+                                                                  eps2d, near_plane, far_plane, radius_clip, tile_size,
+                                                                  tile_w, tile_h, radii, means2d, depths, conics,
+                                                                  compensations, tiles_per_gauss);
+    HGS_LAUNCH_CHECK();
+    return 0;
+}
+
+HGS_API int hgs_project3d_bwd(const float* means, const float* quats, const float* scales, const float* viewmats,
+                              const float* Ks, int C, int N, int width, int height, float eps2d, float near_plane,
+                              float far_plane, const int32_t* radii, const float* v_means2d, const float* v_depths,
+                              const float* v_conics, float* v_means, float* v_quats, float* v_scales, void* stream) {
+    if (C <= 0 || N < 0 || width <= 0 || height <= 0) return HGS_ERR_INVALID_ARG;
+    if (N == 0) return 0;
+    project3d_bwd_kernel<<<hgs_ceil_div(N, PB), PB, 0, (cudaStream_t)stream>>>(
+        means, quats, scales, viewmats, Ks, C, N, width, height, eps2d, near_plane, far_plane, radii, v_means2d,
+        v_depths, v_conics, v_means, v_quats, v_scales);
+    HGS_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,515 @@
+"""Operator layer: the names and call signatures of ``gsplat.cuda._wrapper`` that Horizon-GS
+imports (gaussian_renderer/render.py:14 ``from gsplat.cuda._wrapper import fully_fused_projection,
+fully_fused_projection_2dgs``) plus the other stage operators, each a torch.autograd.Function over
+the C-ABI library (include/hgs_raster.h).  PyTorch is plumbing only: it owns the tensors, the
+autograd graph and the stream; all arithmetic is in libhgs_raster.so.
+
+Only the un-packed layout is implemented (the reference passes packed=False at render.py:50,72,158,180).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from .. import _lib
+from .._lib import check, ptr
+
+_TILE_SIZES = (16,)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t: Optional[Tensor], name: str) -> Optional[Tensor]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (this path has no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise ValueError(f"{name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _n_bits(n: int) -> int:
+    return int(n).bit_length()  # floor(log2(n)) + 1 for n >= 1
+
+
+# =====================================================================================
+# a3: fully_fused_projection
+# =====================================================================================
+class _Project3D(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip,
+                calc_compensations, tile_size):
+        L = _lib.lib()
+        C, N = viewmats.shape[0], means.shape[0]
+        dev = means.device
+        radii = torch.empty((C, N), dtype=torch.int32, device=dev)
+        means2d = torch.empty((C, N, 2), dtype=torch.float32, device=dev)
+        depths = torch.empty((C, N), dtype=torch.float32, device=dev)
+        conics = torch.empty((C, N, 3), dtype=torch.float32, device=dev)
+        comps = torch.empty((C, N), dtype=torch.float32, device=dev) if calc_compensations else None
+        tiles = torch.empty((C, N), dtype=torch.int32, device=dev) if tile_size > 0 else None
+        check(L.hgs_project3d_fwd(ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), C, N, width, height,
+                                  eps2d, near_plane, far_plane, radius_clip, max(tile_size, 1), ptr(radii),
+                                  ptr(means2d), ptr(depths), ptr(conics), ptr(comps), ptr(tiles), _stream()),
+              "hgs_project3d_fwd")
+        ctx.save_for_backward(means, quats, scales, viewmats, Ks, radii)
+        ctx.cfg = (width, height, eps2d, near_plane, far_plane)
+        ctx.mark_non_differentiable(radii)
+        if tiles is not None:
+            ctx.mark_non_differentiable(tiles)
+        if comps is not None:
+            ctx.mark_non_differentiable(comps)  # TODO(antialiased): compensation gradient not implemented
+        return radii, means2d, depths, conics, comps, tiles
+
+    @staticmethod
+    def backward(ctx, _v_radii, v_means2d, v_depths, v_conics, _v_comps, _v_tiles):
+        means, quats, scales, viewmats, Ks, radii = ctx.saved_tensors
+        width, height, eps2d, near_plane, far_plane = ctx.cfg
+        L = _lib.lib()
+        C, N = radii.shape
+        v_means = torch.empty_like(means)
+        v_quats = torch.empty_like(quats)
+        v_scales = torch.empty_like(scales)
+        v_means2d = means.new_zeros((C, N, 2)) if v_means2d is None else v_means2d.contiguous()
+        v_conics = means.new_zeros((C, N, 3)) if v_conics is None else v_conics.contiguous()
+        v_depths = None if v_depths is None else v_depths.contiguous()
+        check(L.hgs_project3d_bwd(ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), C, N, width, height,
+                                  eps2d, near_plane, far_plane, ptr(radii), ptr(v_means2d), ptr(v_depths),
+                                  ptr(v_conics), ptr(v_means), ptr(v_quats), ptr(v_scales), _stream()),
+              "hgs_project3d_bwd")
+        return (v_means, v_quats, v_scales) + (None,) * 10
+
+
+def _check_proj_inputs(means, quats, scales, viewmats, Ks):
+    N = means.shape[0]
+    C = viewmats.shape[0]
+    assert means.shape == (N, 3), means.shape
+    assert quats is not None and quats.shape == (N, 4), None if quats is None else quats.shape
+    assert scales is not None and scales.shape == (N, 3), None if scales is None else scales.shape
+    assert viewmats.shape == (C, 4, 4), viewmats.shape
+    assert Ks.shape == (C, 3, 3), Ks.shape
+    return C, N
+
+
+def _project3d(means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip,
+               calc_compensations, tile_size):
+    _check_proj_inputs(means, quats, scales, viewmats, Ks)
+    means, quats, scales = _f32c(means, "means"), _f32c(quats, "quats"), _f32c(scales, "scales")
+    viewmats, Ks = _f32c(viewmats.detach(), "viewmats"), _f32c(Ks.detach(), "Ks")
+    return _Project3D.apply(means, quats, scales, viewmats, Ks, int(width), int(height), float(eps2d),
+                            float(near_plane), float(far_plane), float(radius_clip), bool(calc_compensations),
+                            int(tile_size))
+
+
+def fully_fused_projection(
+    means: Tensor, covars: Optional[Tensor], quats: Optional[Tensor], scales: Optional[Tensor], viewmats: Tensor,
+    Ks: Tensor, width: int, height: int, eps2d: float = 0.3, near_plane: float = 0.01, far_plane: float = 1e10,
+    radius_clip: float = 0.0, packed: bool = False, sparse_grad: bool = False, calc_compensations: bool = False,
+) -> Tuple[Tensor, Tensor, Tensor, Tensor, Optional[Tensor]]:
+    """Same call as gsplat.cuda._wrapper.fully_fused_projection at render.py:149-165.
+
+    -> (radii[C,N] int32, means2d[C,N,2], depths[C,N], conics[C,N,3], compensations[C,N] | None).
+    radii == 0 marks a culled Gaussian (its other outputs are zeros).
+    """
+    if covars is not None:
+        raise NotImplementedError("covars input is not supported; pass quats and scales (as render.py:151 does)")
+    if packed or sparse_grad:
+        raise NotImplementedError("packed / sparse_grad are not supported (the reference passes False)")
+    radii, means2d, depths, conics, comps, _ = _project3d(
+        means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip,
+        calc_compensations, 0)
+    return radii, means2d, depths, conics, comps
+
+
+# =====================================================================================
+# a7: spherical harmonics
+# =====================================================================================
+class _SphericalHarmonics(torch.autograd.Function):
+    """colors[C,N,3] from coeffs[N,K,3]; direction either dirs[C,N,3] or means[N,3]-campos[C,3]."""
+
+    @staticmethod
+    def forward(ctx, degree, dirs, means, campos, coeffs, radii, post):
+        L = _lib.lib()
+        N, K = coeffs.shape[0], coeffs.shape[1]
+        C = dirs.shape[0] if dirs is not None else campos.shape[0]
+        colors = torch.empty((C, N, 3), dtype=torch.float32, device=coeffs.device)
+        check(L.hgs_sh_fwd(degree, K, ptr(dirs), ptr(means), ptr(campos), ptr(coeffs), ptr(radii), C, N, int(post),
+                           ptr(colors), _stream()), "hgs_sh_fwd")
+        ctx.save_for_backward(dirs, means, campos, coeffs, radii, colors if post else None)
+        ctx.cfg = (degree, K, C, N, int(post))
+        return colors
+
+    @staticmethod
+    def backward(ctx, v_colors):
+        dirs, means, campos, coeffs, radii, colors = ctx.saved_tensors
+        degree, K, C, N, post = ctx.cfg
+        L = _lib.lib()
+        v_colors = v_colors.contiguous()
+        v_coeffs = torch.empty_like(coeffs)
+        need_dirs = dirs is not None and ctx.needs_input_grad[1]
+        need_means = means is not None and ctx.needs_input_grad[2]
+        v_dirs = torch.empty_like(dirs) if need_dirs else None
+        v_means = torch.empty_like(means) if need_means else None
+        check(L.hgs_sh_bwd(degree, K, ptr(dirs), ptr(means), ptr(campos), ptr(coeffs), ptr(radii), ptr(colors),
+                           ptr(v_colors), C, N, post, ptr(v_coeffs), ptr(v_dirs), ptr(v_means), _stream()),
+              "hgs_sh_bwd")
+        return None, v_dirs, v_means, None, v_coeffs, None, None
+
+
+def spherical_harmonics(degrees_to_use: int, dirs: Tensor, coeffs: Tensor, masks: Optional[Tensor] = None) -> Tensor:
+    """gsplat.spherical_harmonics: dirs[..., 3] (un-normalised), coeffs[..., K, 3] -> colors[..., 3].
+
+    Supported shapes: dirs [N,3] or [C,N,3] with coeffs [N,K,3] (shared over C).  masks: bool [..] like dirs[...,0].
+    """
+    assert (degrees_to_use + 1) ** 2 <= coeffs.shape[-2], coeffs.shape
+    assert dirs.shape[-1] == 3 and coeffs.shape[-1] == 3
+    if coeffs.dim() != 3:
+        raise NotImplementedError("coeffs must be [N,K,3]")
+    squeeze = dirs.dim() == 2
+    d = _f32c(dirs, "dirs")
+    d = d[None] if squeeze else d
+    assert d.dim() == 3 and d.shape[1] == coeffs.shape[0], (dirs.shape, coeffs.shape)
+    radii = None
+    if masks is not None:
+        radii = masks.reshape(d.shape[:2]).to(torch.int32).contiguous()
+    out = _SphericalHarmonics.apply(int(degrees_to_use), d, None, None, _f32c(coeffs, "coeffs"), radii, False)
+    return out[0] if squeeze else out
+
+
+def _sh_view_colors(sh_degree: int, means: Tensor, campos: Tensor, coeffs: Tensor, radii: Tensor) -> Tensor:
+    """fused path used by rasterization*: clamp_min(SH(means - campos) + 0.5, 0), masked by radii > 0."""
+    return _SphericalHarmonics.apply(int(sh_degree), None, _f32c(means, "means"), _f32c(campos, "campos"),
+                                     _f32c(coeffs, "colors"), radii, True)
+
+
+# =====================================================================================
+# a8-a10: tile intersection / sort / offsets
+# =====================================================================================
+def _isect_sorted_from_counts(means2d, radii, depths, tiles_per_gauss, C, N, tile_size, tile_width, tile_height):
+    """depth-order, scan, (one D2H read of I), emit + tile partition.  All int work in libhgs_raster."""
+    L = _lib.lib()
+    dev = means2d.device
+    CN = C * N
+    st = _stream()
+    order = torch.empty(CN, dtype=torch.int32, device=dev)
+    cum_sorted = torch.empty(CN, dtype=torch.int32, device=dev)
+    total = torch.empty(1, dtype=torch.int64, device=dev)
+    tb = L.hgs_isect_prepare_temp_bytes(CN)
+    temp = torch.empty(tb, dtype=torch.uint8, device=dev)
+    check(L.hgs_isect_prepare(ptr(depths), ptr(tiles_per_gauss), C, N, ptr(order), ptr(cum_sorted), ptr(total),
+                              ptr(temp), tb, st), "hgs_isect_prepare")
+    n_isects = int(total.item())  # the one unavoidable host read: sizes the intersection arrays
+    if n_isects >= 2 ** 31:
+        raise _lib.HgsError(f"{n_isects} tile intersections exceed the 32-bit index range")
+    isect_ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
+    flatten_ids = torch.empty(n_isects, dtype=torch.int32, device=dev)
+    offsets = torch.empty((C, tile_height, tile_width), dtype=torch.int32, device=dev)
+    tb2 = L.hgs_isect_sorted_temp_bytes(CN, n_isects)
+    temp2 = torch.empty(tb2, dtype=torch.uint8, device=dev)
+    check(L.hgs_isect_sorted(ptr(means2d), ptr(radii), ptr(depths), ptr(order), ptr(cum_sorted), C, N, n_isects,
+                             tile_size, tile_width, tile_height, ptr(isect_ids), ptr(flatten_ids), ptr(offsets),
+                             ptr(temp2), tb2, st), "hgs_isect_sorted")
+    return isect_ids, flatten_ids, offsets
+
+
+@torch.no_grad()
+def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, tile_width: int, tile_height: int,
+                sort: bool = True, packed: bool = False, n_cameras: Optional[int] = None,
+                camera_ids: Optional[Tensor] = None, gaussian_ids: Optional[Tensor] = None,
+                _with_offsets: bool = False):
+    """gsplat.isect_tiles -> (tiles_per_gauss[C,N] i32, isect_ids[I] i64, flatten_ids[I] i32)."""
+    if packed:
+        raise NotImplementedError("packed layout is not supported")
+    C, N = radii.shape
+    assert means2d.shape == (C, N, 2) and depths.shape == (C, N)
+    L = _lib.lib()
+    dev = means2d.device
+    means2d, depths = _f32c(means2d, "means2d"), _f32c(depths, "depths")
+    radii = radii.to(torch.int32).contiguous()
+    tiles = torch.empty((C, N), dtype=torch.int32, device=dev)
+    st = _stream()
+    check(L.hgs_isect_count(ptr(means2d), ptr(radii), C * N, tile_size, tile_width, tile_height, ptr(tiles), st),
+          "hgs_isect_count")
+    if sort:
+        isect_ids, flatten_ids, offsets = _isect_sorted_from_counts(
+            means2d, radii, depths, tiles, C, N, tile_size, tile_width, tile_height)
+        if _with_offsets:
+            return tiles, isect_ids, flatten_ids, offsets
+        return tiles, isect_ids, flatten_ids
+    cum = torch.empty(C * N, dtype=torch.int32, device=dev)
+    total = torch.empty(1, dtype=torch.int64, device=dev)
+    tb = L.hgs_scan_temp_bytes(C * N)
+    temp = torch.empty(tb, dtype=torch.uint8, device=dev)
+    check(L.hgs_exclusive_scan_i32(ptr(tiles), ptr(cum), ptr(total), C * N, ptr(temp), tb, st), "hgs_exclusive_scan")
+    n_isects = int(total.item())
+    isect_ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
+    flatten_ids = torch.empty(n_isects, dtype=torch.int32, device=dev)
+    check(L.hgs_isect_emit(ptr(means2d), ptr(radii), ptr(depths), ptr(cum), C, N, tile_size, tile_width, tile_height,
+                           ptr(isect_ids), ptr(flatten_ids), st), "hgs_isect_emit")
+    return tiles, isect_ids, flatten_ids
+
+
+@torch.no_grad()
+def isect_offset_encode(isect_ids: Tensor, n_cameras: int, tile_width: int, tile_height: int) -> Tensor:
+    """gsplat.isect_offset_encode -> offsets[C, tile_height, tile_width] int32."""
+    L = _lib.lib()
+    isect_ids = isect_ids.contiguous()
+    assert isect_ids.dtype == torch.int64 and isect_ids.is_cuda
+    offsets = torch.empty((n_cameras, tile_height, tile_width), dtype=torch.int32, device=isect_ids.device)
+    check(L.hgs_isect_offset_encode(ptr(isect_ids), isect_ids.numel(), n_cameras, tile_width, tile_height,
+                                    ptr(offsets), _stream()), "hgs_isect_offset_encode")
+    return offsets
+
+
+# =====================================================================================
+# a11: rasterize_to_pixels (3DGS)
+# =====================================================================================
+class _Blend3D(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means2d, conics, colors, depths, opacities, backgrounds, width, height, tile_size,
+                isect_offsets, flatten_ids, absgrad):
+        L = _lib.lib()
+        C, N = opacities.shape
+        CH = colors.shape[-1]
+        D = CH + (1 if depths is not None else 0)
+        dev = means2d.device
+        render_colors = torch.empty((C, height, width, D), dtype=torch.float32, device=dev)
+        render_alphas = torch.empty((C, height, width, 1), dtype=torch.float32, device=dev)
+        last_ids = torch.empty((C, height, width), dtype=torch.int32, device=dev)
+        check(L.hgs_blend3d_fwd(ptr(means2d), ptr(conics), ptr(colors), ptr(depths), ptr(opacities), ptr(backgrounds),
+                                C, N, CH, width, height, tile_size, ptr(isect_offsets), ptr(flatten_ids),
+                                flatten_ids.numel(), ptr(render_colors), ptr(render_alphas), ptr(last_ids), _stream()),
+              "hgs_blend3d_fwd")
+        ctx.save_for_backward(means2d, conics, colors, depths, opacities, backgrounds, isect_offsets, flatten_ids,
+                              render_alphas, last_ids)
+        ctx.cfg = (width, height, tile_size, absgrad)
+        return render_colors, render_alphas
+
+    @staticmethod
+    def backward(ctx, v_render_colors, v_render_alphas):
+        (means2d, conics, colors, depths, opacities, backgrounds, isect_offsets, flatten_ids, render_alphas,
+         last_ids) = ctx.saved_tensors
+        width, height, tile_size, absgrad = ctx.cfg
+        L = _lib.lib()
+        C, N = opacities.shape
+        CH = colors.shape[-1]
+        v_render_colors = v_render_colors.contiguous()
+        v_render_alphas = v_render_alphas.contiguous()
+        v_means2d = torch.zeros_like(means2d)
+        v_conics = torch.zeros_like(conics)
+        v_colors = torch.zeros_like(colors)
+        v_depths = torch.zeros_like(depths) if depths is not None else None
+        v_opacities = torch.zeros_like(opacities)
+        v_abs = torch.zeros_like(means2d) if absgrad else None
+        check(L.hgs_blend3d_bwd(ptr(means2d), ptr(conics), ptr(colors), ptr(depths), ptr(opacities), ptr(backgrounds),
+                                C, N, CH, width, height, tile_size, ptr(isect_offsets), ptr(flatten_ids),
+                                flatten_ids.numel(), ptr(render_alphas), ptr(last_ids), ptr(v_render_colors),
+                                ptr(v_render_alphas), ptr(v_means2d), ptr(v_abs), ptr(v_conics), ptr(v_colors),
+                                ptr(v_depths), ptr(v_opacities), _stream()), "hgs_blend3d_bwd")
+        if absgrad:
+            means2d.absgrad = v_abs
+        v_bg = None
+        if backgrounds is not None and ctx.needs_input_grad[5]:
+            v_bg = (v_render_colors * (1.0 - render_alphas)).sum(dim=(1, 2))
+        return v_means2d, v_conics, v_colors, v_depths, v_opacities, v_bg, None, None, None, None, None, None
+
+
+def _blend3d(means2d, conics, colors, depths, opacities, backgrounds, width, height, tile_size, isect_offsets,
+             flatten_ids, absgrad=False):
+    if tile_size not in _TILE_SIZES:
+        raise NotImplementedError(f"tile_size {tile_size} is not supported (supported: {_TILE_SIZES})")
+    D = colors.shape[-1] + (1 if depths is not None else 0)
+    if D > 8:
+        raise NotImplementedError(f"{D} render channels requested; at most 8 are supported")
+    return _Blend3D.apply(_f32c(means2d, "means2d"), _f32c(conics, "conics"), _f32c(colors, "colors"),
+                          _f32c(depths, "depths"), _f32c(opacities, "opacities"), _f32c(backgrounds, "backgrounds"),
+                          int(width), int(height), int(tile_size), isect_offsets.contiguous(),
+                          flatten_ids.contiguous(), bool(absgrad))
+
+
+def rasterize_to_pixels(means2d: Tensor, conics: Tensor, colors: Tensor, opacities: Tensor, image_width: int,
+                        image_height: int, tile_size: int, isect_offsets: Tensor, flatten_ids: Tensor,
+                        backgrounds: Optional[Tensor] = None, masks: Optional[Tensor] = None, packed: bool = False,
+                        absgrad: bool = False) -> Tuple[Tensor, Tensor]:
+    """gsplat.rasterize_to_pixels: means2d[C,N,2], conics[C,N,3], colors[C,N,D], opacities[C,N]
+    -> (render_colors[C,H,W,D], render_alphas[C,H,W,1])."""
+    if packed or masks is not None:
+        raise NotImplementedError("packed layout / tile masks are not supported")
+    C, N = opacities.shape
+    assert means2d.shape == (C, N, 2) and conics.shape == (C, N, 3) and colors.shape[:2] == (C, N)
+    return _blend3d(means2d, conics, colors, None, opacities, backgrounds, image_width, image_height, tile_size,
+                    isect_offsets, flatten_ids, absgrad)
+
+
+# =====================================================================================
+# a4: fully_fused_projection_2dgs
+# =====================================================================================
+class _Project2D(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means, quats, scales, viewmats, Ks, width, height, near_plane, far_plane, radius_clip,
+                tile_size):
+        L = _lib.lib()
+        C, N = viewmats.shape[0], means.shape[0]
+        dev = means.device
+        radii = torch.empty((C, N), dtype=torch.int32, device=dev)
+        means2d = torch.empty((C, N, 2), dtype=torch.float32, device=dev)
+        depths = torch.empty((C, N), dtype=torch.float32, device=dev)
+        ray_transforms = torch.empty((C, N, 3, 3), dtype=torch.float32, device=dev)
+        normals = torch.empty((C, N, 3), dtype=torch.float32, device=dev)
+        tiles = torch.empty((C, N), dtype=torch.int32, device=dev) if tile_size > 0 else None
+        check(L.hgs_project2d_fwd(ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), C, N, width, height,
+                                  near_plane, far_plane, radius_clip, max(tile_size, 1), ptr(radii), ptr(means2d),
+                                  ptr(depths), ptr(ray_transforms), ptr(normals), ptr(tiles), _stream()),
+              "hgs_project2d_fwd")
+        ctx.save_for_backward(means, quats, scales, viewmats, Ks, radii)
+        ctx.cfg = (width, height, near_plane, far_plane)
+        ctx.mark_non_differentiable(radii)
+        if tiles is not None:
+            ctx.mark_non_differentiable(tiles)
+        return radii, means2d, depths, ray_transforms, normals, tiles
+
+    @staticmethod
+    def backward(ctx, _v_radii, v_means2d, v_depths, v_ray_transforms, v_normals, _v_tiles):
+        means, quats, scales, viewmats, Ks, radii = ctx.saved_tensors
+        width, height, near_plane, far_plane = ctx.cfg
+        L = _lib.lib()
+        C, N = radii.shape
+        v_means = torch.empty_like(means)
+        v_quats = torch.empty_like(quats)
+        v_scales = torch.empty_like(scales)
+        cg = lambda t: None if t is None else t.contiguous()  # noqa: E731
+        v_means2d, v_depths, v_ray_transforms, v_normals = cg(v_means2d), cg(v_depths), cg(v_ray_transforms), cg(v_normals)
+        check(L.hgs_project2d_bwd(ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), C, N, width, height,
+                                  near_plane, far_plane, ptr(radii), ptr(v_means2d), ptr(v_depths),
+                                  ptr(v_ray_transforms), ptr(v_normals), ptr(v_means), ptr(v_quats), ptr(v_scales),
+                                  _stream()), "hgs_project2d_bwd")
+        return (v_means, v_quats, v_scales) + (None,) * 8
+
+
+def _project2d(means, quats, scales, viewmats, Ks, width, height, near_plane, far_plane, radius_clip, tile_size):
+    _check_proj_inputs(means, quats, scales, viewmats, Ks)
+    means, quats, scales = _f32c(means, "means"), _f32c(quats, "quats"), _f32c(scales, "scales")
+    viewmats, Ks = _f32c(viewmats.detach(), "viewmats"), _f32c(Ks.detach(), "Ks")
+    return _Project2D.apply(means, quats, scales, viewmats, Ks, int(width), int(height), float(near_plane),
+                            float(far_plane), float(radius_clip), int(tile_size))
+
+
+def fully_fused_projection_2dgs(
+    means: Tensor, quats: Tensor, scales: Tensor, viewmats: Tensor, densifications: Optional[Tensor], Ks: Tensor,
+    width: int, height: int, eps2d: float = 0.3, near_plane: float = 0.01, far_plane: float = 1e10,
+    radius_clip: float = 0.0, packed: bool = False, sparse_grad: bool = False,
+) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """Same call as the gsplat 2DGS fork's fully_fused_projection_2dgs at render.py:171-186
+    (``densifications`` [C,N,2] is the fork's 5th positional: a gradient slot, never read; eps2d is unused
+    by surfel projection).
+
+    -> (radii[C,N] int32, means2d[C,N,2], depths[C,N], ray_transforms[C,N,3,3], normals[C,N,3]).
+    """
+    if packed or sparse_grad:
+        raise NotImplementedError("packed / sparse_grad are not supported (the reference passes False)")
+    radii, means2d, depths, ray_transforms, normals, _ = _project2d(
+        means, quats, scales, viewmats, Ks, width, height, near_plane, far_plane, radius_clip, 0)
+    return radii, means2d, depths, ray_transforms, normals
+
+
+# =====================================================================================
+# a12: rasterize_to_pixels_2dgs
+# =====================================================================================
+class _Blend2D(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means2d, ray_transforms, colors, depths, normals, opacities, densify, backgrounds, width,
+                height, tile_size, isect_offsets, flatten_ids, distloss, box):
+        L = _lib.lib()
+        C, N = opacities.shape
+        CH = colors.shape[-1]
+        D = CH + (1 if depths is not None else 0)
+        dev = means2d.device
+        render_colors = torch.empty((C, height, width, D), dtype=torch.float32, device=dev)
+        render_alphas = torch.empty((C, height, width, 1), dtype=torch.float32, device=dev)
+        render_normals = torch.empty((C, height, width, 3), dtype=torch.float32, device=dev)
+        render_distort = torch.empty((C, height, width, 1), dtype=torch.float32, device=dev) if distloss else None
+        render_median = torch.empty((C, height, width, 1), dtype=torch.float32, device=dev)
+        last_ids = torch.empty((C, height, width), dtype=torch.int32, device=dev)
+        median_ids = torch.empty((C, height, width), dtype=torch.int32, device=dev)
+        check(L.hgs_blend2d_fwd(ptr(means2d), ptr(ray_transforms), ptr(colors), ptr(depths), ptr(normals),
+                                ptr(opacities), ptr(backgrounds), C, N, CH, width, height, tile_size,
+                                ptr(isect_offsets), ptr(flatten_ids), flatten_ids.numel(), ptr(render_colors),
+                                ptr(render_alphas), ptr(render_normals), ptr(render_distort), ptr(render_median),
+                                ptr(last_ids), ptr(median_ids), _stream()), "hgs_blend2d_fwd")
+        ctx.save_for_backward(means2d, ray_transforms, colors, depths, normals, opacities, backgrounds,
+                              isect_offsets, flatten_ids, render_colors, render_alphas, last_ids, median_ids)
+        ctx.cfg = (width, height, tile_size, distloss)
+        ctx.box = box
+        if not distloss:
+            render_distort = torch.zeros((C, height, width, 1), dtype=torch.float32, device=dev)
+            ctx.mark_non_differentiable(render_distort)
+        return render_colors, render_alphas, render_normals, render_distort, render_median
+
+    @staticmethod
+    def backward(ctx, v_render_colors, v_render_alphas, v_render_normals, v_render_distort, v_render_median):
+        (means2d, ray_transforms, colors, depths, normals, opacities, backgrounds, isect_offsets, flatten_ids,
+         render_colors, render_alphas, last_ids, median_ids) = ctx.saved_tensors
+        width, height, tile_size, distloss = ctx.cfg
+        L = _lib.lib()
+        C, N = opacities.shape
+        CH = colors.shape[-1]
+        cg = lambda t: None if t is None else t.contiguous()  # noqa: E731
+        v_render_colors = cg(v_render_colors) if v_render_colors is not None else torch.zeros_like(render_colors)
+        v_render_alphas = cg(v_render_alphas) if v_render_alphas is not None else torch.zeros_like(render_alphas)
+        v_render_normals, v_render_median = cg(v_render_normals), cg(v_render_median)
+        v_render_distort = cg(v_render_distort) if distloss else None
+        v_means2d = torch.zeros_like(means2d)
+        v_rt = torch.zeros_like(ray_transforms)
+        v_colors = torch.zeros_like(colors)
+        v_depths = torch.zeros_like(depths) if depths is not None else None
+        v_normals = torch.zeros_like(normals)
+        v_opacities = torch.zeros_like(opacities)
+        v_densify = torch.zeros_like(means2d) if (ctx.needs_input_grad[6] or ctx.box is not None) else None
+        check(L.hgs_blend2d_bwd(ptr(means2d), ptr(ray_transforms), ptr(colors), ptr(depths), ptr(normals),
+                                ptr(opacities), ptr(backgrounds), C, N, CH, width, height, tile_size,
+                                ptr(isect_offsets), ptr(flatten_ids), flatten_ids.numel(), ptr(render_colors),
+                                ptr(render_alphas), ptr(last_ids), ptr(median_ids), ptr(v_render_colors),
+                                ptr(v_render_alphas), ptr(v_render_normals), ptr(v_render_distort),
+                                ptr(v_render_median), ptr(v_means2d), ptr(v_rt), ptr(v_colors), ptr(v_depths),
+                                ptr(v_normals), ptr(v_opacities), ptr(v_densify), _stream()), "hgs_blend2d_bwd")
+        if ctx.box is not None:
+            ctx.box["densify"] = v_densify  # picked up by rendering._DensifyInject / _DensifyProbe
+        v_bg = None
+        if backgrounds is not None and ctx.needs_input_grad[7]:
+            v_bg = (v_render_colors * (1.0 - render_alphas)).sum(dim=(1, 2))
+        return (v_means2d, v_rt, v_colors, v_depths, v_normals, v_opacities,
+                v_densify if ctx.needs_input_grad[6] else None, v_bg, None, None, None, None, None, None, None)
+
+
+def _blend2d(means2d, ray_transforms, colors, depths, normals, opacities, densify, backgrounds, width, height,
+             tile_size, isect_offsets, flatten_ids, distloss=False, box=None):
+    if tile_size not in _TILE_SIZES:
+        raise NotImplementedError(f"tile_size {tile_size} is not supported (supported: {_TILE_SIZES})")
+    D = colors.shape[-1] + (1 if depths is not None else 0)
+    if D > 8:
+        raise NotImplementedError(f"{D} render channels requested; at most 8 are supported")
+    return _Blend2D.apply(_f32c(means2d, "means2d"), _f32c(ray_transforms, "ray_transforms"),
+                          _f32c(colors, "colors"), _f32c(depths, "depths"), _f32c(normals, "normals"),
+                          _f32c(opacities, "opacities"), densify, _f32c(backgrounds, "backgrounds"), int(width),
+                          int(height), int(tile_size), isect_offsets.contiguous(), flatten_ids.contiguous(),
+                          bool(distloss), box)
+
+
+def rasterize_to_pixels_2dgs(means2d: Tensor, ray_transforms: Tensor, colors: Tensor, opacities: Tensor,
+                             normals: Tensor, densify: Optional[Tensor], image_width: int, image_height: int,
+                             tile_size: int, isect_offsets: Tensor, flatten_ids: Tensor,
+                             backgrounds: Optional[Tensor] = None, masks: Optional[Tensor] = None,
+                             packed: bool = False, absgrad: bool = False, distloss: bool = False):
+    """gsplat.rasterize_to_pixels_2dgs -> (render_colors, render_alphas, render_normals, render_distort,
+    render_median).  ``densify`` [C,N,2] (zeros, requires_grad) receives the screen-space positional
+    gradient used for densification in its .grad."""
+    if packed or masks is not None or absgrad:
+        raise NotImplementedError("packed layout / tile masks / absgrad are not supported")
+    return _blend2d(means2d, ray_transforms, colors, None, normals, opacities, densify, backgrounds, image_width,
+                    image_height, tile_size, isect_offsets, flatten_ids, distloss)

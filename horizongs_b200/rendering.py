@@ -1,0 +1,241 @@
+"""The two pipelines Horizon-GS calls: ``rasterization`` (gaussian_renderer/render.py:40-54) and
+``rasterization_2dgs`` (render.py:56-76), with gsplat's Python signatures and outputs.
+
+Every stage is a hand-written sm_100a kernel behind the C ABI (include/hgs_raster.h); this file
+only sequences them and owns the tensors.  There is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from .cuda import _wrapper as W
+
+_RENDER_MODES = ("RGB", "D", "ED", "RGB+D", "RGB+ED")
+
+
+def _camera_positions(viewmats: Tensor) -> Tensor:
+    """camera centres [C,3] = -R^T t of world->camera matrices (closed form of inverse(viewmats)[:, :3, 3])."""
+    R = viewmats[:, :3, :3]
+    t = viewmats[:, :3, 3]
+    return -(R.transpose(1, 2) @ t[..., None])[..., 0]
+
+
+def _validate(means, quats, scales, opacities, colors, viewmats, Ks, render_mode, sh_degree, backgrounds):
+    N = means.shape[0]
+    C = viewmats.shape[0]
+    assert means.shape == (N, 3), means.shape
+    assert quats.shape == (N, 4), quats.shape
+    assert scales.shape == (N, 3), scales.shape
+    assert opacities.shape == (N,), opacities.shape
+    assert viewmats.shape == (C, 4, 4), viewmats.shape
+    assert Ks.shape == (C, 3, 3), Ks.shape
+    assert render_mode in _RENDER_MODES, render_mode
+    if sh_degree is None:
+        # post-activation colours [N,D] or [C,N,D]
+        assert (colors.dim() == 2 and colors.shape[0] == N) or (
+            colors.dim() == 3 and colors.shape[:2] == (C, N)), colors.shape
+    else:
+        # SH coefficients [N,K,3]
+        assert colors.dim() == 3 and colors.shape[0] == N and colors.shape[2] == 3, colors.shape
+        assert (sh_degree + 1) ** 2 <= colors.shape[1], colors.shape
+    if backgrounds is not None:
+        assert backgrounds.dim() == 2 and backgrounds.shape[0] == C, backgrounds.shape
+    if not means.is_cuda:
+        raise ValueError("horizongs_b200 runs on CUDA tensors only (no CPU fallback)")
+    return C, N
+
+
+def _per_view_features(means, colors, viewmats, radii, sh_degree, C):
+    """-> [C,N,CH] colour features for blending (CH = 3 for SH)."""
+    if sh_degree is None:
+        if colors.dim() == 2:
+            return colors[None] if C == 1 else colors[None].expand(C, -1, -1)
+        return colors
+    return W._sh_view_colors(sh_degree, means, _camera_positions(viewmats), colors, radii)
+
+
+def _mode_features(feats, depths, backgrounds, render_mode):
+    """split into (colour features or None, depth channel or None, backgrounds padded for the depth channel)"""
+    if render_mode in ("RGB+D", "RGB+ED"):
+        if backgrounds is not None:
+            backgrounds = torch.cat([backgrounds, backgrounds.new_zeros(backgrounds.shape[0], 1)], -1)
+        return feats, depths, backgrounds
+    if render_mode in ("D", "ED"):
+        if backgrounds is not None:
+            backgrounds = backgrounds.new_zeros(backgrounds.shape[0], 1)
+        return depths[..., None], None, backgrounds
+    return feats, None, backgrounds
+
+
+def rasterization(
+    means: Tensor, quats: Tensor, scales: Tensor, opacities: Tensor, colors: Tensor, viewmats: Tensor, Ks: Tensor,
+    width: int, height: int, near_plane: float = 0.01, far_plane: float = 1e10, radius_clip: float = 0.0,
+    eps2d: float = 0.3, sh_degree: Optional[int] = None, packed: bool = False, tile_size: int = 16,
+    backgrounds: Optional[Tensor] = None, render_mode: str = "RGB", sparse_grad: bool = False,
+    absgrad: bool = False, rasterize_mode: str = "classic", channel_chunk: int = 32, distributed: bool = False,
+    camera_model: str = "pinhole", covars: Optional[Tensor] = None,
+) -> Tuple[Tensor, Tensor, Dict]:
+    """3DGS rasterization with gsplat.rasterization's signature (call site render.py:40-54).
+
+    -> render_colors [C,H,W,3|4|1], render_alphas [C,H,W,1], meta.  meta["means2d"] is a non-leaf
+    tensor that accepts retain_grad() and receives pixel-unit gradients (render.py:91,101);
+    meta["radii"] is [C,N] int32 (render.py:89).
+    """
+    if packed or sparse_grad or distributed or covars is not None or camera_model != "pinhole":
+        raise NotImplementedError("packed / sparse_grad / distributed / covars / non-pinhole are not supported")
+    assert rasterize_mode in ("classic", "antialiased"), rasterize_mode
+    C, N = _validate(means, quats, scales, opacities, colors, viewmats, Ks, render_mode, sh_degree, backgrounds)
+    width, height = int(width), int(height)
+    tile_width = math.ceil(width / float(tile_size))
+    tile_height = math.ceil(height / float(tile_size))
+
+    radii, means2d, depths, conics, comps, tiles_per_gauss = W._project3d(
+        means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip,
+        rasterize_mode == "antialiased", tile_size)
+    opac = opacities[None] if C == 1 else opacities[None].expand(C, -1)
+    if comps is not None:
+        opac = opac * comps
+
+    with torch.no_grad():
+        isect_ids, flatten_ids, isect_offsets = W._isect_sorted_from_counts(
+            means2d, radii, depths, tiles_per_gauss, C, N, tile_size, tile_width, tile_height)
+
+    feats = _per_view_features(means, colors, viewmats, radii, sh_degree, C)
+    feats, depth_ch, bgs = _mode_features(feats, depths, backgrounds, render_mode)
+    render_colors, render_alphas = W._blend3d(means2d, conics, feats, depth_ch, opac, bgs, width, height, tile_size,
+                                              isect_offsets, flatten_ids, absgrad)
+    if render_mode in ("ED", "RGB+ED"):
+        render_colors = torch.cat(
+            [render_colors[..., :-1], render_colors[..., -1:] / render_alphas.clamp(min=1e-10)], dim=-1)
+
+    meta = {
+        "camera_ids": None, "gaussian_ids": None, "radii": radii, "means2d": means2d, "depths": depths,
+        "conics": conics, "opacities": opac, "tile_width": tile_width, "tile_height": tile_height,
+        "tiles_per_gauss": tiles_per_gauss, "isect_ids": isect_ids, "flatten_ids": flatten_ids,
+        "isect_offsets": isect_offsets, "width": width, "height": height, "tile_size": tile_size, "n_cameras": C,
+    }
+    return render_colors, render_alphas, meta
+
+
+class _DensifyProbe(torch.autograd.Function):
+    """Identity on means2d; together with _DensifyInject it makes ``meta["means2d"].grad`` carry the
+    densification gradient without polluting the gradient that reaches the projection.
+
+    Horizon-GS reads ``info["means2d"].grad`` for densification in BOTH modes (render.py:91,101;
+    scene/basic_model.py:131-134).  For surfels the true d(loss)/d(means2d) is almost always zero (means2d
+    only enters the rarely-taken screen-space low-pass branch), so -- like the 2DGS reference rasterizer --
+    the positional gradient of the ray transform is reported there instead.
+
+        projection -> means2d --Probe--> means2d_info (returned in meta) --Inject--> blend
+    backward:  blend stores the pseudo-gradient in ``box``; Inject adds it (so means2d_info.grad = true +
+    pseudo); Probe subtracts it again (so the projection receives the true gradient only).
+    """
+
+    @staticmethod
+    def forward(ctx, means2d, box):
+        ctx.box = box
+        return means2d.view_as(means2d)
+
+    @staticmethod
+    def backward(ctx, v):
+        extra = ctx.box.pop("densify", None)
+        return (v if extra is None else v - extra), None
+
+
+class _DensifyInject(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means2d_info, box):
+        ctx.box = box
+        return means2d_info.view_as(means2d_info)
+
+    @staticmethod
+    def backward(ctx, v):
+        extra = ctx.box.get("densify", None)
+        return (v if extra is None else v + extra), None
+
+
+def rasterization_2dgs(
+    means: Tensor, quats: Tensor, scales: Tensor, opacities: Tensor, colors: Tensor, viewmats: Tensor, Ks: Tensor,
+    width: int, height: int, near_plane: float = 0.01, far_plane: float = 1e10, radius_clip: float = 0.0,
+    eps2d: float = 0.3, sh_degree: Optional[int] = None, packed: bool = False, tile_size: int = 16,
+    backgrounds: Optional[Tensor] = None, render_mode: str = "RGB", sparse_grad: bool = False,
+    absgrad: bool = False, distloss: bool = False, depth_mode: str = "expected",
+):
+    """2DGS rasterization with the signature and NESTED return the reference unpacks at render.py:56-76:
+    ((render_colors, render_alphas, render_normals, render_normals_from_depth, render_distort,
+      render_median), meta).
+
+    render_normals [C,H,W,3] are world-space; render_normals_from_depth is [H,W,3] for C == 1 (squeezed,
+    train.py:184-185 handles both); render_distort is zeros unless distloss=True (lambda_dist is 0 in every
+    shipped config).  meta["means2d"].grad receives the densification gradient (see _DensifyProbe);
+    meta["gradient_2dgs"] carries the same quantity upstream-gsplat style.
+    """
+    if packed or sparse_grad or absgrad:
+        raise NotImplementedError("packed / sparse_grad / absgrad are not supported")
+    assert depth_mode in ("expected", "median"), depth_mode
+    C, N = _validate(means, quats, scales, opacities, colors, viewmats, Ks, render_mode, sh_degree, backgrounds)
+    width, height = int(width), int(height)
+    tile_width = math.ceil(width / float(tile_size))
+    tile_height = math.ceil(height / float(tile_size))
+
+    radii, means2d, depths, ray_transforms, normals, tiles_per_gauss = W._project2d(
+        means, quats, scales, viewmats, Ks, width, height, near_plane, far_plane, radius_clip, tile_size)
+    opac = opacities[None] if C == 1 else opacities[None].expand(C, -1)
+
+    with torch.no_grad():
+        isect_ids, flatten_ids, isect_offsets = W._isect_sorted_from_counts(
+            means2d, radii, depths, tiles_per_gauss, C, N, tile_size, tile_width, tile_height)
+
+    feats = _per_view_features(means, colors, viewmats, radii, sh_degree, C)
+    feats, depth_ch, bgs = _mode_features(feats, depths, backgrounds, render_mode)
+
+    grad_on = torch.is_grad_enabled() and means2d.requires_grad
+    box: Optional[Dict] = {} if grad_on else None
+    densify = torch.zeros_like(means2d, requires_grad=True) if grad_on else None
+    means2d_info = _DensifyProbe.apply(means2d, box) if grad_on else means2d
+    means2d_in = _DensifyInject.apply(means2d_info, box) if grad_on else means2d
+
+    render_colors, render_alphas, render_normals, render_distort, render_median = W._blend2d(
+        means2d_in, ray_transforms, feats, depth_ch, normals, opac, densify, bgs, width, height, tile_size,
+        isect_offsets, flatten_ids, distloss, box)
+
+    render_normals_from_depth = None
+    if render_mode in ("ED", "RGB+ED"):
+        render_colors = torch.cat(
+            [render_colors[..., :-1], render_colors[..., -1:] / render_alphas.clamp(min=1e-10)], dim=-1)
+    c2w = torch.linalg.inv(viewmats)
+    if render_mode in ("RGB+D", "RGB+ED"):
+        depth_for_normal = render_colors[..., -1:] if depth_mode == "expected" else render_median
+        render_normals_from_depth = depth_to_normal(depth_for_normal, c2w, Ks).squeeze(0)
+    render_normals = torch.einsum("cij,chwj->chwi", c2w[:, :3, :3], render_normals)
+
+    meta = {
+        "camera_ids": None, "gaussian_ids": None, "radii": radii, "means2d": means2d_info, "depths": depths,
+        "ray_transforms": ray_transforms, "normals": normals, "opacities": opac, "tile_width": tile_width,
+        "tile_height": tile_height, "tiles_per_gauss": tiles_per_gauss, "isect_ids": isect_ids,
+        "flatten_ids": flatten_ids, "isect_offsets": isect_offsets, "width": width, "height": height,
+        "tile_size": tile_size, "n_cameras": C, "render_distort": render_distort, "gradient_2dgs": densify,
+    }
+    return (render_colors, render_alphas, render_normals, render_normals_from_depth, render_distort,
+            render_median), meta
+
+
+def depth_to_normal(depths: Tensor, camtoworlds: Tensor, Ks: Tensor) -> Tensor:
+    """gsplat.utils.depth_to_normal: z-depth maps [C,H,W,1] -> world-space finite-difference normals
+    [C,H,W,3] (one-pixel zero border)."""
+    C, H, Wd, _ = depths.shape
+    dev, dt = depths.device, depths.dtype
+    x, y = torch.meshgrid(torch.arange(Wd, device=dev, dtype=dt), torch.arange(H, device=dev, dtype=dt), indexing="xy")
+    fx, fy = Ks[:, 0, 0][:, None, None], Ks[:, 1, 1][:, None, None]
+    cx, cy = Ks[:, 0, 2][:, None, None], Ks[:, 1, 2][:, None, None]
+    dirs_c = torch.stack([(x[None] - cx + 0.5) / fx, (y[None] - cy + 0.5) / fy, torch.ones_like(x)[None].expand(C, -1, -1)], -1)
+    dirs_w = torch.einsum("cij,chwj->chwi", camtoworlds[:, :3, :3], dirs_c)
+    pts = camtoworlds[:, None, None, :3, 3] + depths * dirs_w
+    dx = pts[:, 2:, 1:-1] - pts[:, :-2, 1:-1]
+    dy = pts[:, 1:-1, 2:] - pts[:, 1:-1, :-2]
+    n = torch.nn.functional.normalize(torch.cross(dx, dy, dim=-1), dim=-1)
+    return torch.nn.functional.pad(n, (0, 0, 1, 1, 1, 1), value=0.0)

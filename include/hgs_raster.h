@@ -1,0 +1,157 @@
+/*
+ * hgs_raster.h -- C ABI of the B200 (sm_100a) Gaussian rasterization hot path.
+ *
+ * Drop-in boundary: Horizon-GS reaches this path only through four
+ * Python callables of the third-party package gsplat,
+ *     gaussian_renderer/render.py:40-54    gsplat.rasterization
+ *     gaussian_renderer/render.py:56-76    gsplat.rasterization_2dgs
+ *     gaussian_renderer/render.py:149-165  gsplat.cuda._wrapper.fully_fused_projection
+ *     gaussian_renderer/render.py:171-186  gsplat.cuda._wrapper.fully_fused_projection_2dgs
+ * gsplat binds its CUDA stages to Python through a torch extension (gsplat/cuda/_wrapper.py ->
+ * gsplat/cuda/csrc, not vendored in the reference).  The functions below are what such a binding
+ * would call, one per stage, with plain device pointers and sizes; horizongs_b200/_lib.py binds
+ * them with ctypes and horizongs_b200/cuda/_wrapper.py mirrors gsplat's Python operator names.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; row-major, contiguous, float32
+ *     unless typed otherwise; `stream` is a cudaStream_t passed as void*.
+ *   - functions only enqueue work on `stream`: no allocation, no synchronisation, no global state;
+ *     re-entrant.  Return 0 on success, a positive cudaError_t, or a negative HGS_ERR_* code.
+ *   - C = cameras, N = Gaussians, flat Gaussian index = c*N + n, I = tile intersections,
+ *     tile grid = ceil(W/tile) x ceil(H/tile), tile id = ty*tile_w + tx.
+ *   - viewmats [C,4,4] world->camera (OpenCV axes), Ks [C,3,3], quats wxyz (normalised inside),
+ *     scales/opacities post-activation (render.py:40-54 and scene/basic_model.py:328-361).
+ */
+#ifndef HGS_RASTER_H
+#define HGS_RASTER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HGS_ABI_VERSION 1
+int hgs_abi_version(void);
+/* human-readable text for a status code returned by any function below */
+const char* hgs_status_string(int status);
+
+/* ---- a3: fully_fused_projection (render.py:149-165; inside rasterization render.py:40) ----------
+ * out: radii[C,N] i32 (0 = culled), means2d[C,N,2], depths[C,N], conics[C,N,3] (a,b,c of the inverse
+ * blurred 2D covariance), compensations[C,N] or NULL, tiles_per_gauss[C,N] i32 or NULL (stage a8's
+ * count pass fused in; needs tile_size).  Culled rows are written as zeros. */
+int hgs_project3d_fwd(const float* means, const float* quats, const float* scales, const float* viewmats,
+                      const float* Ks, int C, int N, int width, int height, float eps2d, float near_plane,
+                      float far_plane, float radius_clip, int tile_size, int32_t* radii, float* means2d,
+                      float* depths, float* conics, float* compensations, int32_t* tiles_per_gauss, void* stream);
+/* in: upstream gradients v_means2d[C,N,2], v_depths[C,N] (or NULL), v_conics[C,N,3];
+ * out (overwritten, summed over cameras): v_means[N,3], v_quats[N,4], v_scales[N,3]. */
+int hgs_project3d_bwd(const float* means, const float* quats, const float* scales, const float* viewmats,
+                      const float* Ks, int C, int N, int width, int height, float eps2d, float near_plane,
+                      float far_plane, const int32_t* radii, const float* v_means2d, const float* v_depths,
+                      const float* v_conics, float* v_means, float* v_quats, float* v_scales, void* stream);
+
+/* ---- a4: fully_fused_projection_2dgs (render.py:171-186; inside rasterization_2dgs render.py:62) --
+ * out: radii[C,N], means2d[C,N,2], depths[C,N], ray_transforms[C,N,3,3] (rows M0,M1,M2 of (K [R|t] H)),
+ * normals[C,N,3] (camera frame, facing the camera), tiles_per_gauss or NULL. */
+int hgs_project2d_fwd(const float* means, const float* quats, const float* scales, const float* viewmats,
+                      const float* Ks, int C, int N, int width, int height, float near_plane, float far_plane,
+                      float radius_clip, int tile_size, int32_t* radii, float* means2d, float* depths,
+                      float* ray_transforms, float* normals, int32_t* tiles_per_gauss, void* stream);
+int hgs_project2d_bwd(const float* means, const float* quats, const float* scales, const float* viewmats,
+                      const float* Ks, int C, int N, int width, int height, float near_plane, float far_plane,
+                      const int32_t* radii, const float* v_means2d, const float* v_depths,
+                      const float* v_ray_transforms, const float* v_normals, float* v_means, float* v_quats,
+                      float* v_scales, void* stream);
+
+/* ---- a7: spherical_harmonics (inside rasterization* when sh_degree is not None) ------------------
+ * Direction of Gaussian n for camera c is dirs[c,n,:] if dirs != NULL, else means[n,:] - campos[c,:]
+ * (normalised inside).  coeffs[N,K,3] is shared by all cameras.  radii (or NULL) masks culled rows to 0.
+ * post != 0 fuses gsplat's `clamp_min(colors + 0.5, 0)`.  out: colors[C,N,3]. */
+int hgs_sh_fwd(int degree, int K, const float* dirs, const float* means, const float* campos, const float* coeffs,
+               const int32_t* radii, int C, int N, int post, float* colors, void* stream);
+/* out (overwritten): v_coeffs[N,K,3] summed over cameras; v_dirs[C,N,3] or NULL; v_means[N,3] or NULL
+ * (direction gradient summed over cameras).  `colors` is the forward output (needed for the clamp mask
+ * when post != 0). */
+int hgs_sh_bwd(int degree, int K, const float* dirs, const float* means, const float* campos, const float* coeffs,
+               const int32_t* radii, const float* colors, const float* v_colors, int C, int N, int post,
+               float* v_coeffs, float* v_dirs, float* v_means, void* stream);
+
+/* ---- a8-a10: tile intersection, tile|depth key sort, per-tile ranges (integer, bit-exact) --------
+ * key = cam << (32 + tile_bits) | tile_id << 32 | (int64)(int32 bits of depth), value = flat index;
+ * tile_bits = floor(log2(tile_w*tile_h)) + 1.  Sorted order equals a stable ascending sort of the keys
+ * emitted Gaussian-major / tile row-major (what gsplat's isect_tiles(sort=True) returns). */
+int hgs_isect_count(const float* means2d, const int32_t* radii, long long CN, int tile_size, int tile_w, int tile_h,
+                    int32_t* tiles_per_gauss, void* stream);
+/* workspace sizes in bytes for the calls below */
+size_t hgs_scan_temp_bytes(long long n);
+size_t hgs_isect_prepare_temp_bytes(long long CN);
+size_t hgs_isect_sorted_temp_bytes(long long CN, long long n_isects);
+/* exclusive prefix sum of in[n] (i32) -> out[n] (i64 accumulate, stored i32; HGS_ERR_TOO_LARGE is
+ * reported through *total >= 2^31 being left for the caller to check); total written to total_dev[0]. */
+int hgs_exclusive_scan_i32(const int32_t* in, int32_t* out, long long* total_dev, long long n, void* temp,
+                           size_t temp_bytes, void* stream);
+/* Unsorted emission (gsplat isect_tiles(sort=False)): cum = exclusive scan of tiles_per_gauss. */
+int hgs_isect_emit(const float* means2d, const int32_t* radii, const float* depths, const int32_t* cum, int C, int N,
+                   int tile_size, int tile_w, int tile_h, long long* isect_ids, int32_t* flatten_ids, void* stream);
+/* Sorted path, phase 1 (needs no knowledge of I): depth-order the C*N Gaussians (stable LSD radix sort
+ * of the depth bits, camera-major), gather tiles_per_gauss in that order and scan it.
+ * out: order[CN] i32 (flat indices in (cam, depth, index) order), cum_sorted[CN] i32 (exclusive scan of the
+ * per-Gaussian tile counts in that order), total_dev[0] = I. */
+int hgs_isect_prepare(const float* depths, const int32_t* tiles_per_gauss, int C, int N, int32_t* order,
+                      int32_t* cum_sorted, long long* total_dev, void* temp, size_t temp_bytes, void* stream);
+/* Sorted path, phase 2: emit (tile key, flat index) pairs in depth order, stable-partition them by
+ * (cam, tile) with LSD radix passes over the tile bits only, then write the final arrays.
+ * out: isect_ids[I] i64, flatten_ids[I] i32, isect_offsets[C*tile_h*tile_w] i32. */
+int hgs_isect_sorted(const float* means2d, const int32_t* radii, const float* depths, const int32_t* order,
+                     const int32_t* cum_sorted, int C, int N, long long n_isects, int tile_size, int tile_w,
+                     int tile_h, long long* isect_ids, int32_t* flatten_ids, int32_t* isect_offsets, void* temp,
+                     size_t temp_bytes, void* stream);
+/* gsplat isect_offset_encode on already-sorted keys. */
+int hgs_isect_offset_encode(const long long* isect_ids, long long n_isects, int C, int tile_w, int tile_h,
+                            int32_t* isect_offsets, void* stream);
+
+/* ---- a11: rasterize_to_pixels (3DGS alpha blending) ----------------------------------------------
+ * colors[C,N,CH]; if depths != NULL an extra channel CH (the camera-space depth) is blended after the
+ * colours (render modes RGB+D / RGB+ED), so the output has D = CH + 1 channels, else D = CH.
+ * backgrounds[C,D] or NULL.  out: render_colors[C,H,W,D] (= sum c*alpha*T + T_final*bg),
+ * render_alphas[C,H,W,1] (= 1 - T_final), last_ids[C,H,W] i32 (index into flatten_ids of the last
+ * blended Gaussian, for the backward pass).  Supported: CH + (depths?1:0) <= 32, tile_size == 16. */
+int hgs_blend3d_fwd(const float* means2d, const float* conics, const float* colors, const float* depths,
+                    const float* opacities, const float* backgrounds, int C, int N, int CH, int width, int height,
+                    int tile_size, const int32_t* isect_offsets, const int32_t* flatten_ids, long long n_isects,
+                    float* render_colors, float* render_alphas, int32_t* last_ids, void* stream);
+/* Gradients are ACCUMULATED (+=) into v_means2d[C,N,2], v_conics[C,N,3], v_colors[C,N,CH], v_depths[C,N]
+ * (NULL iff depths == NULL), v_opacities[C,N]; the caller zero-fills them.  v_means2d_abs is NULL or
+ * receives sum |v_means2d| (gsplat absgrad). */
+int hgs_blend3d_bwd(const float* means2d, const float* conics, const float* colors, const float* depths,
+                    const float* opacities, const float* backgrounds, int C, int N, int CH, int width, int height,
+                    int tile_size, const int32_t* isect_offsets, const int32_t* flatten_ids, long long n_isects,
+                    const float* render_alphas, const int32_t* last_ids, const float* v_render_colors,
+                    const float* v_render_alphas, float* v_means2d, float* v_means2d_abs, float* v_conics,
+                    float* v_colors, float* v_depths, float* v_opacities, void* stream);
+
+/* ---- a12: rasterize_to_pixels_2dgs ----------------------------------------------------------------
+ * As a11 with ray_transforms[C,N,3,3] and normals[C,N,3]; additionally blends normals, and writes
+ * render_distort[C,H,W,1] (NULL = distortion off), render_median[C,H,W,1], median_ids[C,H,W]. */
+int hgs_blend2d_fwd(const float* means2d, const float* ray_transforms, const float* colors, const float* depths,
+                    const float* normals, const float* opacities, const float* backgrounds, int C, int N, int CH,
+                    int width, int height, int tile_size, const int32_t* isect_offsets, const int32_t* flatten_ids,
+                    long long n_isects, float* render_colors, float* render_alphas, float* render_normals,
+                    float* render_distort, float* render_median, int32_t* last_ids, int32_t* median_ids,
+                    void* stream);
+/* v_densify[C,N,2] (or NULL) receives the screen-space positional gradient used for densification. */
+int hgs_blend2d_bwd(const float* means2d, const float* ray_transforms, const float* colors, const float* depths,
+                    const float* normals, const float* opacities, const float* backgrounds, int C, int N, int CH,
+                    int width, int height, int tile_size, const int32_t* isect_offsets, const int32_t* flatten_ids,
+                    long long n_isects, const float* render_colors, const float* render_alphas,
+                    const int32_t* last_ids, const int32_t* median_ids, const float* v_render_colors,
+                    const float* v_render_alphas, const float* v_render_normals, const float* v_render_distort,
+                    const float* v_render_median, float* v_means2d, float* v_ray_transforms, float* v_colors,
+                    float* v_depths, float* v_normals, float* v_opacities, float* v_densify, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HGS_RASTER_H */
