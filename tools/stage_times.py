@@ -1,0 +1,100 @@
+"""Per-stage CUDA-event timings of the hot path on the named synthetic configs (development aid)."""
+import argparse
+import json
+import math
+import sys
+import os
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import horizongs_b200 as hgs
+from horizongs_b200 import scenes
+from horizongs_b200.cuda import _wrapper as W
+from horizongs_b200 import rendering as R
+
+
+def timed(fn, iters=10, warm=3):
+    for _ in range(warm):
+        out = fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return out, ts[len(ts) // 2]
+
+
+def run(name, sc, V, Ks, Wd, H):
+    dev = "cuda"
+    sc = sc.to(dev)
+    V, Ks = V.to(dev), Ks.to(dev)
+    C, N = V.shape[0], sc.n
+    tw, th = math.ceil(Wd / 16), math.ceil(H / 16)
+    res = {"config": name, "N": N, "C": C, "W": Wd, "H": H}
+    proj, t = timed(lambda: W._project3d(sc.means, sc.quats, sc.scales, V, Ks, Wd, H, 0.3, 0.01, 1e10, 0.0, False, 16))
+    res["project_fwd_ms"] = t
+    radii, m2, d, con, _, tiles = proj
+    res["n_visible"] = int((radii > 0).sum())
+    (ids, flat, off), t = timed(lambda: W._isect_sorted_from_counts(m2, radii, d, tiles, C, N, 16, tw, th))
+    res["isect_sort_ms"] = t
+    res["I"] = int(ids.numel())
+    res["max_tile_depth"] = int((torch.diff(torch.cat([off.flatten(), off.new_tensor([ids.numel()])]))).max())
+    if sc.sh_degree is not None:
+        campos = R._camera_positions(V)
+        cols, t = timed(lambda: W._sh_view_colors(sc.sh_degree, sc.means, campos, sc.colors, radii))
+        res["sh_fwd_ms"] = t
+    else:
+        cols = sc.colors[None]
+    op = sc.opacities[None]
+    (rc, ra), t = timed(lambda: W._blend3d(m2, con, cols, d, op, None, Wd, H, 16, off, flat))
+    res["blend_fwd_ms"] = t
+    # backward of the blend stage alone
+    ins = [x.detach().clone().requires_grad_() for x in (m2, con, cols.contiguous(), d, op)]
+    rc, ra = W._blend3d(ins[0], ins[1], ins[2], ins[3], ins[4], None, Wd, H, 16, off, flat)
+    g1, g2 = torch.rand_like(rc), torch.rand_like(ra)
+    _, t = timed(lambda: torch.autograd.grad((rc, ra), ins, (g1, g2), retain_graph=True))
+    res["blend_bwd_ms"] = t
+    # whole pipeline
+    params = [x.detach().clone().requires_grad_() for x in (sc.means, sc.quats, sc.scales, sc.opacities, sc.colors)]
+
+    def fwd():
+        return hgs.rasterization(*params, V, Ks, Wd, H, sh_degree=sc.sh_degree, render_mode="RGB+ED")
+
+    with torch.no_grad():
+        _, t = timed(fwd)
+    res["pipeline_fwd_ms"] = t
+
+    def fwdbwd():
+        rc, ra, meta = fwd()
+        (rc * g1).sum().backward()
+        for p in params:
+            p.grad = None
+
+    _, t = timed(fwdbwd)
+    res["pipeline_fwd_bwd_ms"] = t
+    print(json.dumps(res), flush=True)
+    return res
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="1a,1s,4")
+    a = ap.parse_args()
+    for c in a.configs.split(","):
+        if c == "0":
+            sc, V, Ks, Wd, H = scenes.config0()
+            run("config0", sc, V, Ks, Wd, H)
+        elif c == "1a":
+            run("config1-aerial", *scenes.config1(view="aerial"))
+        elif c == "1s":
+            run("config1-street", *scenes.config1(view="street"))
+        elif c == "4":
+            sc, V, Ks, Wd, H = scenes.config4(n_views=2)
+            run("config4-view0-aerial", sc, V[:1], Ks[:1], Wd, H)
+            run("config4-view1-street", sc, V[1:2], Ks[1:2], Wd, H)
