@@ -5,18 +5,467 @@
 // pixel centre (x+.5, y+.5); sigma = .5(a dx^2 + c dy^2) + b dx dy; alpha = min(.999, o exp(-sigma));
 // skip if sigma < 0 or alpha < 1/255; stop before the Gaussian that brings T to <= 1e-4.
 //
-// One CTA per 16x16 tile, one pixel per thread, Gaussians staged in shared memory in batches of 256.
-// Roofline: FP32 FMA / MUFU.EX2 / shared-memory broadcast (not HBM): ~26 FLOP + 1 EX2 per (pixel, Gaussian)
-// pair forward, ~80 FLOP + 1 EX2 backward plus a warp reduction and L2 atomics per (warp, Gaussian).
-#include "hgs_common.cuh"
-#include "hgs_constants.cuh"
+// B200 design (the *_fast kernels, <= 4 render channels -- every mode the reference uses):
+//   * pack: one 64-byte record per visible Gaussian (centre, conic pre-multiplied by -log2(e)/2 so that
+//     alpha = o * 2^(A dx^2 + B dx dy + C dy^2), opacity, cut-off exponent, colour, edge-optimum slopes).
+//   * one CTA per 16x16 tile, 8 warps, each warp owns an 8x4 pixel sub-tile.  Records of a batch of 128
+//     intersections are gathered into shared memory with per-thread TMA bulk copies (cp.async.bulk,
+//     mbarrier transaction counting), double buffered, so staging overlaps blending.
+//   * per-warp culling: each lane tests one Gaussian of a group of 32 against the warp's sub-tile with an
+//     exact concave-maximum-over-rectangle test (plus margin): Gaussians that cannot reach alpha >= 1/255 on
+//     any of the warp's 32 pixels are skipped for the whole warp -- result-identical to evaluating them.
+//   * backward: per-lane partials are summed over the warp with a halving butterfly (12 shuffles for 10
+//     values instead of 50), written to per-warp shared-memory slots, summed over the 8 warps per batch and
+//     added to global memory with 3 vector reductions (red.global.add.v4.f32) per (tile, Gaussian).
+//   * expected-depth normalisation (render modes ED / RGB+ED) is fused into the epilogue / prologue.
+// Roofline: FP32 FMA / MUFU.EX2 / shared-memory pipes (not HBM, no tensor cores: no dense contraction).
+// The plain kernels (one pixel per thread, gsplat-style staging) remain for 5..8 channels.
+#include "blend_common.cuh"
 #include "../../include/hgs_raster.h"
 
 namespace {
 
-constexpr int TS = HGS_TILE_SIZE;
-constexpr int BLK = TS * TS;  // 256 threads, also the batch size
+using namespace hgs;
 
+constexpr int TS = HGS_TILE_SIZE;
+constexpr int BLK = TS * TS;  // 256 threads
+
+// =====================================================================================================
+// packed per-Gaussian record
+// =====================================================================================================
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+constexpr int REC_BYTES = 64;    // global record
+constexpr int SLOT_BYTES = 80;   // shared-memory slot (stride 80 B: lane-parallel float4 reads are conflict-free)
+constexpr int FB = 128;          // batch size of the fast kernels
+constexpr float CULL_MARGIN = 0.02f;  // in log2 units; conservative (float error of the bound is ~1e-5)
+
+struct __align__(16) GRec {
+    float x, y, A, B;          // q0
+    float C, opac, p2min, _p;  // q1
+    float col[4];              // q2
+    float kx, ky, _p2, _p3;    // q3
+};
+static_assert(sizeof(GRec) == REC_BYTES, "record size");
+
+__global__ void pack3d_kernel(const float* __restrict__ means2d, const float* __restrict__ conics,
+                              const float* __restrict__ colors, const float* __restrict__ depths,
+                              const float* __restrict__ opacities, const int32_t* __restrict__ radii, long long CN,
+                              int CH, GRec* __restrict__ recs) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= CN) return;
+    if (radii != nullptr && radii[i] <= 0) return;
+    const float2 m = reinterpret_cast<const float2*>(means2d)[i];
+    const float a = conics[i * 3 + 0], b = conics[i * 3 + 1], c = conics[i * 3 + 2];
+    const float o = opacities[i];
+    GRec r;
+    r.x = m.x; r.y = m.y;
+    r.A = -0.5f * LOG2E * a;
+    r.B = -LOG2E * b;
+    r.C = -0.5f * LOG2E * c;
+    r.opac = o;
+    // contributes iff o * 2^p2 >= 1/255  <=>  p2 >= -log2(255 o); o <= 0 never contributes
+    r.p2min = (o > 0.f) ? -log2f(255.0f * o) : 1.0f;
+    r._p = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r.col[k] = (k < CH) ? colors[i * CH + k] : ((k == CH && depths != nullptr) ? depths[i] : 0.f);
+    r.kx = (r.C != 0.f) ? -r.B / (2.f * r.C) : 0.f;
+    r.ky = (r.A != 0.f) ? -r.B / (2.f * r.A) : 0.f;
+    r._p2 = 0.f; r._p3 = 0.f;
+    float4* dst = reinterpret_cast<float4*>(recs + i);
+    const float4* src = reinterpret_cast<const float4*>(&r);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dst[k] = src[k];
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// can this Gaussian reach alpha >= 1/255 (and sigma >= 0) anywhere on the pixel-centre rectangle
+// [X0,X1] x [Y0,Y1]?  Maximum of the concave quadratic p2(u,v) = A u^2 + B u v + C v^2 over the rectangle.
+__device__ __forceinline__ bool cull_keep(const float4 q0, const float4 q1, const float4 q3, float X0, float X1,
+                                          float Y0, float Y1) {
+    const float u0 = X0 - q0.x, u1 = X1 - q0.x, v0 = Y0 - q0.y, v1 = Y1 - q0.y;
+    const float A = q0.z, B = q0.w, C = q1.x;
+    const float thr = q1.z - CULL_MARGIN;
+    if (u0 <= 0.f && u1 >= 0.f && v0 <= 0.f && v1 >= 0.f) return thr <= 0.f;
+    float best;
+    {
+        float v = fminf(fmaxf(q3.x * u0, v0), v1);
+        best = (A * u0 + B * v) * u0 + C * v * v;
+        v = fminf(fmaxf(q3.x * u1, v0), v1);
+        best = fmaxf(best, (A * u1 + B * v) * u1 + C * v * v);
+        float u = fminf(fmaxf(q3.y * v0, u0), u1);
+        best = fmaxf(best, (A * u + B * v0) * u + C * v0 * v0);
+        u = fminf(fmaxf(q3.y * v1, u0), u1);
+        best = fmaxf(best, (A * u + B * v1) * u + C * v1 * v1);
+    }
+    return best >= thr;
+}
+
+__device__ __forceinline__ const float4* slot_q(const unsigned char* stage, int t) {
+    return reinterpret_cast<const float4*>(stage + t * SLOT_BYTES);
+}
+
+struct TileGeom {
+    int cam, gtile, pi, pj, warp, lane;
+    float px, py, X0, X1, Y0, Y1;
+    bool inside;
+};
+__device__ __forceinline__ TileGeom tile_geom(int tile_w, int tile_h, int W, int H) {
+    TileGeom g;
+    g.cam = blockIdx.z;
+    g.gtile = (g.cam * tile_h + blockIdx.y) * tile_w + blockIdx.x;
+    g.warp = threadIdx.x >> 5;
+    g.lane = threadIdx.x & 31;
+    const int sx = blockIdx.x * TS + (g.warp & 1) * 8, sy = blockIdx.y * TS + (g.warp >> 1) * 4;
+    g.pj = sx + (g.lane & 7);
+    g.pi = sy + (g.lane >> 3);
+    g.px = (float)g.pj + 0.5f;
+    g.py = (float)g.pi + 0.5f;
+    g.X0 = (float)sx + 0.5f; g.X1 = (float)sx + 7.5f;
+    g.Y0 = (float)sy + 0.5f; g.Y1 = (float)sy + 3.5f;
+    g.inside = (g.pi < H && g.pj < W);
+    return g;
+}
+
+// =====================================================================================================
+// fast forward
+// =====================================================================================================
+template <int D, bool NORM_DEPTH>
+__global__ void __launch_bounds__(BLK) blend3d_fwd_fast_kernel(
+    const GRec* __restrict__ recs, const float* __restrict__ backgrounds, int C, int W, int H, int tile_w, int tile_h,
+    const int32_t* __restrict__ offsets, const int32_t* __restrict__ flatten_ids, int n_isects,
+    float* __restrict__ render_colors, float* __restrict__ render_alphas, int32_t* __restrict__ last_ids) {
+    __shared__ __align__(16) unsigned char s_rec[2][FB * SLOT_BYTES];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    const TileGeom g = tile_geom(tile_w, tile_h, W, H);
+    const int tr = threadIdx.x;
+    bool done = !g.inside;
+
+    const int range_start = offsets[g.gtile];
+    const int range_end = (g.gtile == C * tile_w * tile_h - 1) ? n_isects : offsets[g.gtile + 1];
+    const int nb = (range_end - range_start + FB - 1) / FB;
+
+    if (tr == 0) {
+        mbar_init(&s_bar[0], FB);
+        mbar_init(&s_bar[1], FB);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // loader threads (tr < FB): one record per thread and batch
+    int g_next = -1;
+    if (tr < FB && nb > 0) {
+        int idx = range_start + tr;
+        const int g0 = idx < range_end ? flatten_ids[idx] : -1;
+        if (g0 >= 0) {
+            mbar_arrive_expect_tx(&s_bar[0], REC_BYTES);
+            bulk_g2s(s_rec[0] + tr * SLOT_BYTES, recs + g0, REC_BYTES, &s_bar[0]);
+        } else {
+            mbar_arrive(&s_bar[0]);
+        }
+        idx += FB;
+        g_next = idx < range_end ? flatten_ids[idx] : -1;
+    }
+
+    float T = 1.0f;
+    int cur_idx = 0;
+    float pix[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) pix[k] = 0.f;
+
+    for (int b = 0; b < nb; ++b) {
+        const int st = b & 1;
+        if (tr < FB && b + 1 < nb) {
+            const int ns = st ^ 1;
+            if (g_next >= 0) {
+                mbar_arrive_expect_tx(&s_bar[ns], REC_BYTES);
+                bulk_g2s(s_rec[ns] + tr * SLOT_BYTES, recs + g_next, REC_BYTES, &s_bar[ns]);
+            } else {
+                mbar_arrive(&s_bar[ns]);
+            }
+            const int idx = range_start + (b + 2) * FB + tr;
+            g_next = idx < range_end ? flatten_ids[idx] : -1;
+        }
+        mbar_wait(&s_bar[st], (b >> 1) & 1);
+
+        const int batch_start = range_start + b * FB;
+        const int batch_n = min(FB, range_end - batch_start);
+        const unsigned char* stage = s_rec[st];
+        if (!__all_sync(0xFFFFFFFFu, done)) {
+            for (int grp = 0; grp * 32 < batch_n; ++grp) {
+                const int t = grp * 32 + g.lane;
+                bool keep = false;
+                if (t < batch_n) {
+                    const float4* q = slot_q(stage, t);
+                    keep = cull_keep(q[0], q[1], q[3], g.X0, g.X1, g.Y0, g.Y1);
+                }
+                unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int tt = grp * 32 + j;
+                    const float4* q = slot_q(stage, tt);
+                    const float4 q0 = q[0], q1 = q[1];
+                    const float dx = q0.x - g.px, dy = q0.y - g.py;
+                    const float p2 = (q0.z * dx + q0.w * dy) * dx + (q1.x * dy) * dy;
+                    const float alpha = fminf(HGS_ALPHA_MAX, q1.y * ex2_approx(p2));
+                    if (!done && p2 <= 0.f && alpha >= HGS_ALPHA_MIN) {
+                        const float next_T = T * (1.0f - alpha);
+                        if (next_T <= HGS_T_EPS) {
+                            done = true;
+                        } else {
+                            const float vis = alpha * T;
+                            const float4 q2 = q[2];
+                            pix[0] += q2.x * vis;
+                            if (D > 1) pix[1] += q2.y * vis;
+                            if (D > 2) pix[2] += q2.z * vis;
+                            if (D > 3) pix[3] += q2.w * vis;
+                            cur_idx = batch_start + tt;
+                            T = next_T;
+                        }
+                    }
+                }
+                if (__all_sync(0xFFFFFFFFu, done)) break;
+            }
+        }
+        if (__syncthreads_count(done) >= BLK) {
+            if (b + 1 < nb) mbar_wait(&s_bar[st ^ 1], ((b + 1) >> 1) & 1);  // drain the in-flight prefetch
+            break;
+        }
+    }
+    if (g.inside) {
+        const long long pid = ((long long)g.cam * H + g.pi) * W + g.pj;
+        const float alpha_out = 1.0f - T;
+        render_alphas[pid] = alpha_out;
+        float out[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) out[k] = backgrounds == nullptr ? pix[k] : pix[k] + T * backgrounds[g.cam * D + k];
+        if (NORM_DEPTH) out[D - 1] = out[D - 1] / fmaxf(alpha_out, HGS_ED_ALPHA_FLOOR);
+        if (D == 4) {
+            reinterpret_cast<float4*>(render_colors)[pid] = make_float4(out[0], out[1], out[2], out[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < D; ++k) render_colors[pid * D + k] = out[k];
+        }
+        last_ids[pid] = cur_idx;
+    }
+}
+
+// =====================================================================================================
+// fast backward
+// =====================================================================================================
+constexpr int ACC_STRIDE = 11;  // odd: conflict-free slot writes (10 lanes) and strided flush reads
+constexpr int VP = 12;          // floats per row of the packed gradient buffer
+
+template <int D>
+struct BwdSmem {
+    unsigned char rec[2][FB * SLOT_BYTES];
+    float acc[BLK / 32][FB * ACC_STRIDE];
+    int ids[2][FB];
+    unsigned wmask[BLK / 32][FB / 32];
+    int red[BLK / 32];
+    uint64_t bar[2];
+};
+
+template <int D, bool NORM_DEPTH>
+__global__ void __launch_bounds__(BLK) blend3d_bwd_fast_kernel(
+    const GRec* __restrict__ recs, const float* __restrict__ backgrounds, int C, int W, int H, int tile_w, int tile_h,
+    const int32_t* __restrict__ offsets, const int32_t* __restrict__ flatten_ids, int n_isects,
+    const float* __restrict__ render_colors, const float* __restrict__ render_alphas,
+    const int32_t* __restrict__ last_ids, const float* __restrict__ v_render_colors,
+    const float* __restrict__ v_render_alphas, float* __restrict__ vpack) {
+    constexpr int NV = 6 + D;
+    static_assert(NV <= ACC_STRIDE, "accumulator row too small");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BwdSmem<D>& S = *reinterpret_cast<BwdSmem<D>*>(smem_raw);
+    const TileGeom g = tile_geom(tile_w, tile_h, W, H);
+    const int tr = threadIdx.x;
+
+    const int range_start = offsets[g.gtile];
+    const int range_end = (g.gtile == C * tile_w * tile_h - 1) ? n_isects : offsets[g.gtile + 1];
+    if (range_end <= range_start) return;
+
+    if (tr == 0) {
+        mbar_init(&S.bar[0], FB);
+        mbar_init(&S.bar[1], FB);
+        mbar_fence_init();
+    }
+
+    // per-pixel state
+    const long long pid = ((long long)g.cam * H + min(g.pi, H - 1)) * W + min(g.pj, W - 1);
+    const float alpha_out = render_alphas[pid];
+    const float T_final = 1.0f - alpha_out;
+    float T = T_final;
+    float buffer[D], v_c[D];
+    float v_a = g.inside ? v_render_alphas[pid] : 0.f;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        buffer[k] = 0.f;
+        v_c[k] = g.inside ? v_render_colors[pid * D + k] : 0.f;
+    }
+    if (NORM_DEPTH) {
+        // out_d = acc_d / max(alpha, eps): fold the quotient rule into v_c[D-1] and v_a
+        const float a_c = fmaxf(alpha_out, HGS_ED_ALPHA_FLOOR);
+        const float v_ed = v_c[D - 1];
+        v_c[D - 1] = v_ed / a_c;
+        if (alpha_out >= HGS_ED_ALPHA_FLOOR && g.inside) v_a += -v_ed * render_colors[pid * D + D - 1] / a_c;
+    }
+    float bg_dot = 0.f;
+    if (backgrounds != nullptr) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) bg_dot += backgrounds[g.cam * D + k] * v_c[k];
+    }
+    const int bin_final = g.inside ? last_ids[pid] : -1;
+    int warp_bin_final = bin_final;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) warp_bin_final = max(warp_bin_final, __shfl_xor_sync(0xFFFFFFFFu, warp_bin_final, o));
+    if (g.lane == 0) S.red[g.warp] = warp_bin_final;
+    __syncthreads();
+    int cta_bin_final = S.red[0];
+#pragma unroll
+    for (int w = 1; w < BLK / 32; ++w) cta_bin_final = max(cta_bin_final, S.red[w]);
+    // gsplat semantics: last_ids defaults to 0, so index 0 is always replayed by the tile that owns it
+    cta_bin_final = max(cta_bin_final, range_start);
+    if (cta_bin_final >= range_end) cta_bin_final = range_end - 1;
+
+    // batches run back to front over [range_start, cta_bin_final]
+    const int top = cta_bin_final;
+    const int nb = (top - range_start + 1 + FB - 1) / FB;
+
+    const int my_comp = halving_component<NV>(g.lane);
+    const bool is_writer = (g.lane == __ffs(__match_any_sync(0xFFFFFFFFu, my_comp)) - 1);
+
+    int g_next = -1;
+    if (tr < FB) {
+        int idx = top - tr;
+        const int g0 = idx >= range_start ? flatten_ids[idx] : -1;
+        S.ids[0][tr] = g0;
+        if (g0 >= 0) {
+            mbar_arrive_expect_tx(&S.bar[0], REC_BYTES);
+            bulk_g2s(S.rec[0] + tr * SLOT_BYTES, recs + g0, REC_BYTES, &S.bar[0]);
+        } else {
+            mbar_arrive(&S.bar[0]);
+        }
+        idx -= FB;
+        g_next = idx >= range_start ? flatten_ids[idx] : -1;
+    }
+
+    for (int b = 0; b < nb; ++b) {
+        const int st = b & 1;
+        if (tr < FB && b + 1 < nb) {
+            const int ns = st ^ 1;
+            S.ids[ns][tr] = g_next;
+            if (g_next >= 0) {
+                mbar_arrive_expect_tx(&S.bar[ns], REC_BYTES);
+                bulk_g2s(S.rec[ns] + tr * SLOT_BYTES, recs + g_next, REC_BYTES, &S.bar[ns]);
+            } else {
+                mbar_arrive(&S.bar[ns]);
+            }
+            const int idx = top - (b + 2) * FB - tr;
+            g_next = idx >= range_start ? flatten_ids[idx] : -1;
+        }
+        if (g.lane < FB / 32) S.wmask[g.warp][g.lane] = 0u;
+        mbar_wait(&S.bar[st], (b >> 1) & 1);
+        __syncwarp();
+
+        const int batch_end = top - b * FB;                       // element t <-> index batch_end - t
+        const int batch_n = min(FB, batch_end + 1 - range_start);
+        const unsigned char* stage = S.rec[st];
+        const int t_first = max(0, batch_end - warp_bin_final);
+        for (int grp = t_first >> 5; grp * 32 < batch_n; ++grp) {
+            const int t = grp * 32 + g.lane;
+            bool keep = false;
+            if (t < batch_n && t >= t_first) {
+                const float4* q = slot_q(stage, t);
+                keep = cull_keep(q[0], q[1], q[3], g.X0, g.X1, g.Y0, g.Y1);
+            }
+            unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+            unsigned written = 0u;
+            while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                const int tt = grp * 32 + j;
+                const float4* q = slot_q(stage, tt);
+                const float4 q0 = q[0], q1 = q[1];
+                const float dx = q0.x - g.px, dy = q0.y - g.py;
+                const float p2 = (q0.z * dx + q0.w * dy) * dx + (q1.x * dy) * dy;
+                const float vis = ex2_approx(p2);
+                const float opac = q1.y;
+                const float alpha = fminf(HGS_ALPHA_MAX, opac * vis);
+                const bool valid = (batch_end - tt <= bin_final) && p2 <= 0.f && alpha >= HGS_ALPHA_MIN;
+                if (!__any_sync(0xFFFFFFFFu, valid)) continue;
+                float val[NV];
+#pragma unroll
+                for (int k = 0; k < NV; ++k) val[k] = 0.f;
+                if (valid) {
+                    const float4 q2 = q[2];
+                    const float col[4] = {q2.x, q2.y, q2.z, q2.w};
+                    const float ra = 1.0f / (1.0f - alpha);
+                    T *= ra;
+                    const float fac = alpha * T;
+                    float v_alpha = 0.f;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        val[6 + k] = fac * v_c[k];
+                        v_alpha += (col[k] * T - buffer[k] * ra) * v_c[k];
+                        buffer[k] += col[k] * fac;
+                    }
+                    v_alpha += T_final * ra * v_a;
+                    if (backgrounds != nullptr) v_alpha += -T_final * ra * bg_dot;
+                    if (opac * vis <= HGS_ALPHA_MAX) {
+                        const float v_sigma = -opac * vis * v_alpha;
+                        // a dx + b dy = -ln2 (2A dx + B dy),  b dx + c dy = -ln2 (B dx + 2C dy)
+                        val[0] = v_sigma * (-LN2) * (2.f * q0.z * dx + q0.w * dy);
+                        val[1] = v_sigma * (-LN2) * (q0.w * dx + 2.f * q1.x * dy);
+                        val[2] = 0.5f * v_sigma * dx * dx;
+                        val[3] = v_sigma * dx * dy;
+                        val[4] = 0.5f * v_sigma * dy * dy;
+                        val[5] = vis * v_alpha;
+                    }
+                }
+                const float r = halving_reduce<NV>(val, g.lane);
+                if (is_writer) S.acc[g.warp][tt * ACC_STRIDE + my_comp] = r;
+                written |= 1u << j;
+            }
+            if (g.lane == 0) S.wmask[g.warp][grp] = written;
+        }
+        __syncthreads();
+        // flush: thread t sums the 8 warps' slots of Gaussian t and adds them to global memory
+        if (tr < batch_n) {
+            float sum[NV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) sum[k] = 0.f;
+            bool any = false;
+#pragma unroll
+            for (int w = 0; w < BLK / 32; ++w) {
+                if ((S.wmask[w][tr >> 5] >> (tr & 31)) & 1u) {
+                    any = true;
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) sum[k] += S.acc[w][tr * ACC_STRIDE + k];
+                }
+            }
+            if (any) {
+                float* row = vpack + (long long)S.ids[st][tr] * VP;
+                red_add_v4(row, sum[0], sum[1], sum[2], sum[3]);
+                red_add_v2(row + 4, sum[4], sum[5]);
+                if (D == 4) red_add_v4(row + 8, sum[6], sum[7], sum[8], sum[9]);
+                else if (D == 3) { red_add_v2(row + 8, sum[6], sum[7]); atomicAdd(row + 10, sum[8]); }
+                else if (D == 2) red_add_v2(row + 8, sum[6], sum[7]);
+                else atomicAdd(row + 8, sum[6]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// =====================================================================================================
+// plain kernels (any channel count up to 8)
+// =====================================================================================================
 template <int D>
 __global__ void __launch_bounds__(BLK) blend3d_fwd_kernel(
     const float* __restrict__ means2d, const float* __restrict__ conics, const float* __restrict__ colors,
@@ -31,9 +480,9 @@ __global__ void __launch_bounds__(BLK) blend3d_fwd_kernel(
     const int cam = blockIdx.z;
     const int tile_id = blockIdx.y * tile_w + blockIdx.x;
     const int gtile = cam * tile_w * tile_h + tile_id;
-    const int tr = threadIdx.y * TS + threadIdx.x;
-    const int pi = blockIdx.y * TS + threadIdx.y;
-    const int pj = blockIdx.x * TS + threadIdx.x;
+    const int tr = threadIdx.x;
+    const int pi = blockIdx.y * TS + (tr >> 4);
+    const int pj = blockIdx.x * TS + (tr & 15);
     const float px = (float)pj + 0.5f, py = (float)pi + 0.5f;
     const bool inside = (pi < H && pj < W);
     bool done = !inside;
@@ -116,10 +565,10 @@ __global__ void __launch_bounds__(BLK) blend3d_bwd_kernel(
     const int cam = blockIdx.z;
     const int tile_id = blockIdx.y * tile_w + blockIdx.x;
     const int gtile = cam * tile_w * tile_h + tile_id;
-    const int tr = threadIdx.y * TS + threadIdx.x;
+    const int tr = threadIdx.x;
     const int lane = tr & 31;
-    const int pi = blockIdx.y * TS + threadIdx.y;
-    const int pj = blockIdx.x * TS + threadIdx.x;
+    const int pi = blockIdx.y * TS + (tr >> 4);
+    const int pj = blockIdx.x * TS + (tr & 15);
     const float px = (float)pj + 0.5f, py = (float)pi + 0.5f;
     const bool inside = (pi < H && pj < W);
     const long long pid = ((long long)cam * H + min(pi, H - 1)) * W + min(pj, W - 1);
@@ -240,10 +689,10 @@ int launch_fwd(const float* means2d, const float* conics, const float* colors, c
                const float* opacities, const float* backgrounds, int C, int CH, int W, int H, int tile_w, int tile_h,
                const int32_t* offsets, const int32_t* flatten_ids, int n_isects, float* render_colors,
                float* render_alphas, int32_t* last_ids, cudaStream_t st) {
-    dim3 grid(tile_w, tile_h, C), block(TS, TS);
-    blend3d_fwd_kernel<D><<<grid, block, 0, st>>>(means2d, conics, colors, depths, opacities, backgrounds, C, CH, W, H,
-                                                   tile_w, tile_h, offsets, flatten_ids, n_isects, render_colors,
-                                                   render_alphas, last_ids);
+    dim3 grid(tile_w, tile_h, C);
+    blend3d_fwd_kernel<D><<<grid, BLK, 0, st>>>(means2d, conics, colors, depths, opacities, backgrounds, C, CH, W, H,
+                                                 tile_w, tile_h, offsets, flatten_ids, n_isects, render_colors,
+                                                 render_alphas, last_ids);
     HGS_LAUNCH_CHECK();
     return 0;
 }
@@ -255,11 +704,39 @@ int launch_bwd(const float* means2d, const float* conics, const float* colors, c
                const int32_t* last_ids, const float* v_render_colors, const float* v_render_alphas, float* v_means2d,
                float* v_means2d_abs, float* v_conics, float* v_colors, float* v_depths, float* v_opacities,
                cudaStream_t st) {
-    dim3 grid(tile_w, tile_h, C), block(TS, TS);
-    blend3d_bwd_kernel<D><<<grid, block, 0, st>>>(means2d, conics, colors, depths, opacities, backgrounds, C, CH, W, H,
-                                                   tile_w, tile_h, offsets, flatten_ids, n_isects, render_alphas,
-                                                   last_ids, v_render_colors, v_render_alphas, v_means2d,
-                                                   v_means2d_abs, v_conics, v_colors, v_depths, v_opacities);
+    dim3 grid(tile_w, tile_h, C);
+    blend3d_bwd_kernel<D><<<grid, BLK, 0, st>>>(means2d, conics, colors, depths, opacities, backgrounds, C, CH, W, H,
+                                                 tile_w, tile_h, offsets, flatten_ids, n_isects, render_alphas,
+                                                 last_ids, v_render_colors, v_render_alphas, v_means2d, v_means2d_abs,
+                                                 v_conics, v_colors, v_depths, v_opacities);
+    HGS_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int D, bool NORM>
+int launch_fwd_fast(const GRec* recs, const float* backgrounds, int C, int W, int H, int tile_w, int tile_h,
+                    const int32_t* offsets, const int32_t* flatten_ids, int n_isects, float* render_colors,
+                    float* render_alphas, int32_t* last_ids, cudaStream_t st) {
+    dim3 grid(tile_w, tile_h, C);
+    blend3d_fwd_fast_kernel<D, NORM><<<grid, BLK, 0, st>>>(recs, backgrounds, C, W, H, tile_w, tile_h, offsets,
+                                                           flatten_ids, n_isects, render_colors, render_alphas,
+                                                           last_ids);
+    HGS_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int D, bool NORM>
+int launch_bwd_fast(const GRec* recs, const float* backgrounds, int C, int W, int H, int tile_w, int tile_h,
+                    const int32_t* offsets, const int32_t* flatten_ids, int n_isects, const float* render_colors,
+                    const float* render_alphas, const int32_t* last_ids, const float* v_render_colors,
+                    const float* v_render_alphas, float* vpack, cudaStream_t st) {
+    dim3 grid(tile_w, tile_h, C);
+    const int smem = (int)sizeof(BwdSmem<D>);
+    cudaError_t e = cudaFuncSetAttribute(blend3d_bwd_fast_kernel<D, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    blend3d_bwd_fast_kernel<D, NORM><<<grid, BLK, smem, st>>>(recs, backgrounds, C, W, H, tile_w, tile_h, offsets,
+                                                             flatten_ids, n_isects, render_colors, render_alphas,
+                                                             last_ids, v_render_colors, v_render_alphas, vpack);
     HGS_LAUNCH_CHECK();
     return 0;
 }
@@ -316,5 +793,65 @@ HGS_API int hgs_blend3d_bwd(const float* means2d, const float* conics, const flo
                    isect_offsets, flatten_ids, (int)n_isects, render_alphas, last_ids, v_render_colors,              \
                    v_render_alphas, v_means2d, v_means2d_abs, v_conics, v_colors, v_depths, v_opacities, st)
     HGS_DISPATCH_D(D, CALL)
+#undef CALL
+}
+
+// ---- fast path --------------------------------------------------------------------------------------
+HGS_API size_t hgs_blend3d_pack_bytes(long long CN) { return (size_t)(CN > 0 ? CN : 1) * REC_BYTES; }
+
+HGS_API int hgs_blend3d_pack(const float* means2d, const float* conics, const float* colors, const float* depths,
+                             const float* opacities, const int32_t* radii, long long CN, int CH, void* records,
+                             void* stream) {
+    if (CN < 0 || CH < 0 || CH + (depths != nullptr ? 1 : 0) > 4) return HGS_ERR_INVALID_ARG;
+    if (CN == 0) return 0;
+    pack3d_kernel<<<hgs_ceil_div(CN, 256), 256, 0, (cudaStream_t)stream>>>(means2d, conics, colors, depths, opacities,
+                                                                            radii, CN, CH, (GRec*)records);
+    HGS_LAUNCH_CHECK();
+    return 0;
+}
+
+#define HGS_DISPATCH_FAST(D, NORM, CALL)                         \
+    switch ((D) * 2 + ((NORM) ? 1 : 0)) {                        \
+        case 2: return CALL(1, false);                           \
+        case 3: return CALL(1, true);                            \
+        case 4: return CALL(2, false);                           \
+        case 5: return CALL(2, true);                            \
+        case 6: return CALL(3, false);                           \
+        case 7: return CALL(3, true);                            \
+        case 8: return CALL(4, false);                           \
+        case 9: return CALL(4, true);                            \
+        default: return HGS_ERR_INVALID_ARG;                     \
+    }
+
+HGS_API int hgs_blend3d_fwd_packed(const void* records, const float* backgrounds, int C, int D, int normalize_depth,
+                                   int width, int height, int tile_size, const int32_t* isect_offsets,
+                                   const int32_t* flatten_ids, long long n_isects, float* render_colors,
+                                   float* render_alphas, int32_t* last_ids, void* stream) {
+    if (tile_size != TS || C <= 0 || width <= 0 || height <= 0 || D < 1 || D > 4 || n_isects < 0) return HGS_ERR_INVALID_ARG;
+    if (n_isects >= (1ll << 31)) return HGS_ERR_TOO_LARGE;
+    const int tile_w = (width + TS - 1) / TS, tile_h = (height + TS - 1) / TS;
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(DD, NN)                                                                                               \
+    launch_fwd_fast<DD, NN>((const GRec*)records, backgrounds, C, width, height, tile_w, tile_h, isect_offsets,     \
+                            flatten_ids, (int)n_isects, render_colors, render_alphas, last_ids, st)
+    HGS_DISPATCH_FAST(D, normalize_depth != 0, CALL)
+#undef CALL
+}
+
+HGS_API int hgs_blend3d_bwd_packed(const void* records, const float* backgrounds, int C, int D, int normalize_depth,
+                                   int width, int height, int tile_size, const int32_t* isect_offsets,
+                                   const int32_t* flatten_ids, long long n_isects, const float* render_colors,
+                                   const float* render_alphas, const int32_t* last_ids, const float* v_render_colors,
+                                   const float* v_render_alphas, float* vpack, void* stream) {
+    if (tile_size != TS || C <= 0 || width <= 0 || height <= 0 || D < 1 || D > 4 || n_isects < 0) return HGS_ERR_INVALID_ARG;
+    if (n_isects >= (1ll << 31)) return HGS_ERR_TOO_LARGE;
+    if (n_isects == 0) return 0;
+    const int tile_w = (width + TS - 1) / TS, tile_h = (height + TS - 1) / TS;
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(DD, NN)                                                                                               \
+    launch_bwd_fast<DD, NN>((const GRec*)records, backgrounds, C, width, height, tile_w, tile_h, isect_offsets,     \
+                            flatten_ids, (int)n_isects, render_colors, render_alphas, last_ids, v_render_colors,    \
+                            v_render_alphas, vpack, st)
+    HGS_DISPATCH_FAST(D, normalize_depth != 0, CALL)
 #undef CALL
 }

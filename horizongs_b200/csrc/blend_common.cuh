@@ -1,0 +1,105 @@
+// Building blocks shared by the blend kernels: mbarrier + cp.async.bulk (TMA bulk copy) staging,
+// halving warp reduction, vector reductions to global memory.
+#pragma once
+#include "hgs_common.cuh"
+#include "hgs_constants.cuh"
+
+namespace hgs {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier (shared::cta) ------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) __trap();
+    }
+}
+// TMA bulk copy global -> shared, completion counted in bytes on `bar`. 16-byte aligned, size % 16 == 0.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- vector reductions to global memory (sm_90+) ----------------------------------------------------
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+// ---- halving warp reduction --------------------------------------------------------------------------
+// Sums N per-lane values over the 32 lanes with ~N + log2(32) shuffles instead of 5*N: at every butterfly
+// step lanes pair up, each keeps one half of the value list and sends the other half.  Afterwards every
+// lane holds the full 32-lane sum of ONE component; halving_component() tells which.
+template <int N, int M>
+struct Halving {
+    static __device__ __forceinline__ float run(float (&v)[N], int lane) {
+        constexpr int H = N / 2, R = N - 2 * H;
+        float nv[H + R];
+        const bool up = (lane & M) != 0;
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            const float keep = up ? v[2 * i + 1] : v[2 * i];
+            const float send = up ? v[2 * i] : v[2 * i + 1];
+            nv[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, M);
+        }
+        if (R) nv[H] = v[N - 1] + __shfl_xor_sync(0xFFFFFFFFu, v[N - 1], M);
+        return Halving<H + R, M / 2>::run(nv, lane);
+    }
+    static __device__ __forceinline__ int comp(const int (&id)[N], int lane) {
+        constexpr int H = N / 2, R = N - 2 * H;
+        int nid[H + R];
+        const bool up = (lane & M) != 0;
+#pragma unroll
+        for (int i = 0; i < H; ++i) nid[i] = up ? id[2 * i + 1] : id[2 * i];
+        if (R) nid[H] = id[N - 1];
+        return Halving<H + R, M / 2>::comp(nid, lane);
+    }
+};
+template <int N>
+struct Halving<N, 0> {
+    static __device__ __forceinline__ float run(float (&v)[N], int) {
+        static_assert(N == 1, "32 lanes reduce at most 32 components");
+        return v[0];
+    }
+    static __device__ __forceinline__ int comp(const int (&id)[N], int) { return id[0]; }
+};
+template <int N>
+__device__ __forceinline__ float halving_reduce(float (&v)[N], int lane) {
+    return Halving<N, 16>::run(v, lane);
+}
+template <int N>
+__device__ __forceinline__ int halving_component(int lane) {
+    int id[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) id[i] = i;
+    return Halving<N, 16>::comp(id, lane);
+}
+
+}  // namespace hgs

@@ -14,7 +14,7 @@
 // so ties on the full key are ties on depth between different Gaussians and both orders break them by
 // ascending flat index.
 //
-// Radix pass = 3 launches (chunk histogram, single-block scan, chunk scatter); no inter-block waiting.
+// Radix pass = 3 launches (chunk histogram, per-digit row scan, chunk scatter); no inter-block waiting.
 // Roofline: HBM.  Per pass 4 B (hist) + 8 B + 8 B per pair.
 #include "hgs_common.cuh"
 #include "hgs_constants.cuh"
@@ -75,41 +75,62 @@ __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint32_t* 
     for (int i = threadIdx.x; i < RADIX; i += RS_THREADS) hist[(long long)i * gridDim.x + blockIdx.x] = s_hist[i];
 }
 
-// exclusive scan of `total` u32 entries in place, single block
-__global__ void __launch_bounds__(SCAN_THREADS) scan_small_kernel(uint32_t* __restrict__ data, int total) {
-    __shared__ uint32_t s_sum[SCAN_THREADS];
-    const int per = (total + SCAN_THREADS - 1) / SCAN_THREADS;
-    const int b = threadIdx.x * per;
-    int e = b + per;
-    if (e > total) e = total;
-    uint32_t sum = 0;
-    for (int i = b; i < e; ++i) sum += data[i];
-    s_sum[threadIdx.x] = sum;
+// block-wide exclusive scan of one value per thread (RS_THREADS threads); returns the exclusive prefix and
+// the block total
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp /*[RS_WARPS]*/, uint32_t& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    // Hillis-Steele inclusive scan over 1024 partial sums
-    for (int off = 1; off < SCAN_THREADS; off <<= 1) {
-        uint32_t v = threadIdx.x >= off ? s_sum[threadIdx.x - off] : 0u;
-        __syncthreads();
-        s_sum[threadIdx.x] += v;
-        __syncthreads();
+    uint32_t wbase = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+        const uint32_t x = s_warp[w];
+        if (w < warp) wbase += x;
+        tot += x;
     }
-    uint32_t run = s_sum[threadIdx.x] - sum;
-    for (int i = b; i < e; ++i) {
-        uint32_t v = data[i];
-        data[i] = run;
-        run += v;
+    __syncthreads();
+    total = tot;
+    return wbase + incl - v;
+}
+
+// hist is [RADIX][n_chunks]: block d turns row d into its exclusive scan (over chunks) and writes the row total
+__global__ void __launch_bounds__(RS_THREADS) radix_rowscan_kernel(uint32_t* __restrict__ hist, int n_chunks,
+                                                                   uint32_t* __restrict__ rowsum) {
+    __shared__ uint32_t s_warp[RS_WARPS];
+    uint32_t* row = hist + (long long)blockIdx.x * n_chunks;
+    uint32_t carry = 0;
+    for (int base = 0; base < n_chunks; base += RS_THREADS) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < n_chunks ? row[i] : 0u;
+        uint32_t tot;
+        const uint32_t ex = block_excl_scan(v, s_warp, tot);
+        if (i < n_chunks) row[i] = carry + ex;
+        carry += tot;
     }
+    if (threadIdx.x == 0) rowsum[blockIdx.x] = carry;
 }
 
 __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(
     const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, long long n, DigitSpec ds, int tiles_per_chunk,
-    const uint32_t* __restrict__ hist_scanned) {
+    const uint32_t* __restrict__ hist_scanned, const uint32_t* __restrict__ rowsum) {
     __shared__ uint32_t s_base[RADIX];
     __shared__ uint32_t s_whist[RS_WARPS][RADIX];
+    __shared__ uint32_t s_warp[RS_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    for (int i = threadIdx.x; i < RADIX; i += RS_THREADS) s_base[i] = hist_scanned[(long long)i * gridDim.x + blockIdx.x];
+    {
+        // global base of digit d = sum of the totals of smaller digits + this chunk's offset inside digit d
+        uint32_t tot;
+        const uint32_t digit_base = block_excl_scan(rowsum[threadIdx.x], s_warp, tot);
+        s_base[threadIdx.x] = digit_base + hist_scanned[(long long)threadIdx.x * gridDim.x + blockIdx.x];
+    }
     const long long begin = (long long)blockIdx.x * tiles_per_chunk * RS_TILE;
     long long end = begin + (long long)tiles_per_chunk * RS_TILE;
     if (end > n) end = n;
@@ -169,14 +190,15 @@ static int radix_pass(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t
     ChunkPlan p = plan_chunks(n);
     radix_hist_kernel<<<p.n_chunks, RS_THREADS, 0, st>>>(keys_in, vals_in, n, ds, p.tiles_per_chunk, hist);
     HGS_LAUNCH_CHECK();
-    scan_small_kernel<<<1, SCAN_THREADS, 0, st>>>(hist, RADIX * p.n_chunks);
+    uint32_t* rowsum = hist + (size_t)RADIX * RS_MAX_CHUNKS;
+    radix_rowscan_kernel<<<RADIX, RS_THREADS, 0, st>>>(hist, p.n_chunks, rowsum);
     HGS_LAUNCH_CHECK();
     radix_scatter_kernel<<<p.n_chunks, RS_THREADS, 0, st>>>(keys_in, vals_in, keys_out, vals_out, n, ds,
-                                                            p.tiles_per_chunk, hist);
+                                                            p.tiles_per_chunk, hist, rowsum);
     HGS_LAUNCH_CHECK();
     return 0;
 }
-constexpr size_t HIST_BYTES = (size_t)RADIX * RS_MAX_CHUNKS * sizeof(uint32_t);
+constexpr size_t HIST_BYTES = ((size_t)RADIX * RS_MAX_CHUNKS + RADIX) * sizeof(uint32_t);  // + row totals
 
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 static int n_bits_of(long long n) {  // floor(log2(n)) + 1 for n >= 1

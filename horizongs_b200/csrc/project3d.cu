@@ -170,8 +170,8 @@ __global__ void __launch_bounds__(PB) project3d_bwd_kernel(
     const float* __restrict__ means, const float* __restrict__ quats, const float* __restrict__ scales,
     const float* __restrict__ viewmats, const float* __restrict__ Ks, int C, int N, int W, int H, float eps2d,
     float near_plane, float far_plane, const int32_t* __restrict__ radii, const float* __restrict__ v_means2d,
-    const float* __restrict__ v_depths, const float* __restrict__ v_conics, float* __restrict__ v_means,
-    float* __restrict__ v_quats, float* __restrict__ v_scales) {
+    int ld_m2, const float* __restrict__ v_depths, int ld_d, const float* __restrict__ v_conics, int ld_c,
+    float* __restrict__ v_means, float* __restrict__ v_quats, float* __restrict__ v_scales) {
     __shared__ float s_a[PB * 3];
     __shared__ float s_b[PB * 3];
     __shared__ float s_c[PB * 3];
@@ -190,20 +190,25 @@ __global__ void __launch_bounds__(PB) project3d_bwd_kernel(
     float g_quat[4] = {0.f, 0.f, 0.f, 0.f};
 
     for (int c = 0; c < C; ++c) {
-        // coalesced staging of this camera's v_conics rows
+        // coalesced staging of this camera's v_conics rows (dense layout); strided rows are read directly
         __syncthreads();
-        block_load_rows3<PB>(v_conics + (long long)c * N * 3, base, N, s_c);
+        if (ld_c == 3) block_load_rows3<PB>(v_conics + (long long)c * N * 3, base, N, s_c);
         __syncthreads();
         if (n >= N) continue;
         const long long idx = (long long)c * N + n;
         if (radii[idx] <= 0) continue;
+        if (ld_c != 3) {
+            s_c[threadIdx.x * 3 + 0] = v_conics[idx * ld_c + 0];
+            s_c[threadIdx.x * 3 + 1] = v_conics[idx * ld_c + 1];
+            s_c[threadIdx.x * 3 + 2] = v_conics[idx * ld_c + 2];
+        }
         const HgsCam cam = hgs_load_cam(viewmats, Ks, c);
         Proj3dFwd f;
         if (!proj3d_math(cam, px, py, pz, qv.x, qv.y, qv.z, qv.w, s0, s1, s2, (float)W, (float)H, eps2d, near_plane,
                          far_plane, f))
             continue;
-        const float2 vm = reinterpret_cast<const float2*>(v_means2d)[idx];
-        const float vd = v_depths != nullptr ? v_depths[idx] : 0.f;
+        const float2 vm = make_float2(v_means2d[idx * ld_m2], v_means2d[idx * ld_m2 + 1]);
+        const float vd = v_depths != nullptr ? v_depths[idx * ld_d] : 0.f;
         const float va = s_c[threadIdx.x * 3 + 0], vb = 0.5f * s_c[threadIdx.x * 3 + 1], vc = s_c[threadIdx.x * 3 + 2];
 
         // conic X = inv(Sigma2'), v_Sigma2 = -X V X
@@ -322,13 +327,15 @@ HGS_API int hgs_project3d_fwd(const float* means, const float* quats, const floa
 
 HGS_API int hgs_project3d_bwd(const float* means, const float* quats, const float* scales, const float* viewmats,
                               const float* Ks, int C, int N, int width, int height, float eps2d, float near_plane,
-                              float far_plane, const int32_t* radii, const float* v_means2d, const float* v_depths,
-                              const float* v_conics, float* v_means, float* v_quats, float* v_scales, void* stream) {
-    if (C <= 0 || N < 0 || width <= 0 || height <= 0) return HGS_ERR_INVALID_ARG;
+                              float far_plane, const int32_t* radii, const float* v_means2d, int ld_means2d,
+                              const float* v_depths, int ld_depths, const float* v_conics, int ld_conics,
+                              float* v_means, float* v_quats, float* v_scales, void* stream) {
+    if (C <= 0 || N < 0 || width <= 0 || height <= 0 || ld_means2d < 2 || ld_conics < 3 || ld_depths < 1)
+        return HGS_ERR_INVALID_ARG;
     if (N == 0) return 0;
     project3d_bwd_kernel<<<hgs_ceil_div(N, PB), PB, 0, (cudaStream_t)stream>>>(
         means, quats, scales, viewmats, Ks, C, N, width, height, eps2d, near_plane, far_plane, radii, v_means2d,
-        v_depths, v_conics, v_means, v_quats, v_scales);
+        ld_means2d, v_depths, ld_depths, v_conics, ld_conics, v_means, v_quats, v_scales);
     HGS_LAUNCH_CHECK();
     return 0;
 }

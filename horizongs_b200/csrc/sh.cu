@@ -195,9 +195,9 @@ __global__ void __launch_bounds__(SB) sh_bwd_kernel(const float* __restrict__ di
                                                     const float* __restrict__ coeffs,
                                                     const int32_t* __restrict__ radii,
                                                     const float* __restrict__ colors,
-                                                    const float* __restrict__ v_colors, int C, int N, int K, int post,
-                                                    float* __restrict__ v_coeffs, float* __restrict__ v_dirs,
-                                                    float* __restrict__ v_means) {
+                                                    const float* __restrict__ v_colors, int ld_vc, int C, int N,
+                                                    int K, int post, float* __restrict__ v_coeffs,
+                                                    float* __restrict__ v_dirs, float* __restrict__ v_means) {
     extern __shared__ float smem[];
     constexpr int NB = (DEG + 1) * (DEG + 1);
     const int rs = row_stride(K);
@@ -223,7 +223,12 @@ __global__ void __launch_bounds__(SB) sh_bwd_kernel(const float* __restrict__ di
 
     for (int c = 0; c < C; ++c) {
         __syncthreads();
-        block_load_rows3<SB>(v_colors + (long long)c * N * 3, base, N, s_io);
+        if (ld_vc == 3) {
+            block_load_rows3<SB>(v_colors + (long long)c * N * 3, base, N, s_io);
+        } else if (n < N) {
+            const float* vr = v_colors + ((long long)c * N + n) * ld_vc;
+            s_io[threadIdx.x * 3] = vr[0]; s_io[threadIdx.x * 3 + 1] = vr[1]; s_io[threadIdx.x * 3 + 2] = vr[2];
+        }
         if (post) block_load_rows3<SB>(colors + (long long)c * N * 3, base, N, s_io2);
         __syncthreads();
         float v0 = s_io[threadIdx.x * 3], v1 = s_io[threadIdx.x * 3 + 1], v2 = s_io[threadIdx.x * 3 + 2];
@@ -327,9 +332,11 @@ HGS_API int hgs_sh_fwd(int degree, int K, const float* dirs, const float* means,
 }
 
 HGS_API int hgs_sh_bwd(int degree, int K, const float* dirs, const float* means, const float* campos,
-                       const float* coeffs, const int32_t* radii, const float* colors, const float* v_colors, int C,
-                       int N, int post, float* v_coeffs, float* v_dirs, float* v_means, void* stream) {
-    if (degree < 0 || degree > 4 || K < (degree + 1) * (degree + 1) || C <= 0 || N < 0) return HGS_ERR_INVALID_ARG;
+                       const float* coeffs, const int32_t* radii, const float* colors, const float* v_colors,
+                       int ld_v_colors, int C, int N, int post, float* v_coeffs, float* v_dirs, float* v_means,
+                       void* stream) {
+    if (degree < 0 || degree > 4 || K < (degree + 1) * (degree + 1) || C <= 0 || N < 0 || ld_v_colors < 3)
+        return HGS_ERR_INVALID_ARG;
     if (dirs == nullptr && (means == nullptr || campos == nullptr)) return HGS_ERR_INVALID_ARG;
     if (post && colors == nullptr) return HGS_ERR_INVALID_ARG;
     if (N == 0) return 0;
@@ -339,8 +346,8 @@ HGS_API int hgs_sh_bwd(int degree, int K, const float* dirs, const float* means,
 #define LAUNCH(DEG)                                                                                                  \
     {                                                                                                                \
         cudaFuncSetAttribute(sh_bwd_kernel<DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
-        sh_bwd_kernel<DEG><<<grid, SB, smem, st>>>(dirs, means, campos, coeffs, radii, colors, v_colors, C, N, K,    \
-                                                   post, v_coeffs, v_dirs, v_means);                                 \
+        sh_bwd_kernel<DEG><<<grid, SB, smem, st>>>(dirs, means, campos, coeffs, radii, colors, v_colors,             \
+                                                   ld_v_colors, C, N, K, post, v_coeffs, v_dirs, v_means);           \
     }
     switch (degree) {
         case 0: LAUNCH(0) break;

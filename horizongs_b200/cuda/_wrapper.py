@@ -34,6 +34,27 @@ def _f32c(t: Optional[Tensor], name: str) -> Optional[Tensor]:
     return t.contiguous()
 
 
+def _rows(t: Optional[Tensor], width: int):
+    """(tensor to take the pointer of, row stride in floats) for a [..., width] gradient.  Slices of the
+    packed blend-gradient buffer ([C,N,12] rows) are passed as they are; anything else is made dense."""
+    if t is None:
+        return None, width
+    if t.dtype == torch.float32 and t.is_cuda and t.dim() >= 2 and t.shape[-1] == width and t.numel() > 0:
+        st = t.stride()
+        ld = st[-2] if width > 1 or t.dim() >= 2 else 1
+        ok = st[-1] == 1 and ld >= width
+        # leading dims must be a plain row-major walk over rows of stride ld
+        expect = ld
+        for size, stride in zip(reversed(t.shape[:-1]), reversed(st[:-1])):
+            if size != 1 and stride != expect:
+                ok = False
+                break
+            expect *= size
+        if ok:
+            return t, int(ld)
+    return t.contiguous(), width
+
+
 def _n_bits(n: int) -> int:
     return int(n).bit_length()  # floor(log2(n)) + 1 for n >= 1
 
@@ -76,12 +97,12 @@ class _Project3D(torch.autograd.Function):
         v_means = torch.empty_like(means)
         v_quats = torch.empty_like(quats)
         v_scales = torch.empty_like(scales)
-        v_means2d = means.new_zeros((C, N, 2)) if v_means2d is None else v_means2d.contiguous()
-        v_conics = means.new_zeros((C, N, 3)) if v_conics is None else v_conics.contiguous()
-        v_depths = None if v_depths is None else v_depths.contiguous()
+        v_means2d, ld_m = _rows(means.new_zeros((C, N, 2)) if v_means2d is None else v_means2d, 2)
+        v_conics, ld_c = _rows(means.new_zeros((C, N, 3)) if v_conics is None else v_conics, 3)
+        v_depths, ld_d = _rows(None if v_depths is None else v_depths.unsqueeze(-1), 1)
         check(L.hgs_project3d_bwd(ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), C, N, width, height,
-                                  eps2d, near_plane, far_plane, ptr(radii), ptr(v_means2d), ptr(v_depths),
-                                  ptr(v_conics), ptr(v_means), ptr(v_quats), ptr(v_scales), _stream()),
+                                  eps2d, near_plane, far_plane, ptr(radii), ptr(v_means2d), ld_m, ptr(v_depths), ld_d,
+                                  ptr(v_conics), ld_c, ptr(v_means), ptr(v_quats), ptr(v_scales), _stream()),
               "hgs_project3d_bwd")
         return (v_means, v_quats, v_scales) + (None,) * 10
 
@@ -150,14 +171,14 @@ class _SphericalHarmonics(torch.autograd.Function):
         dirs, means, campos, coeffs, radii, colors = ctx.saved_tensors
         degree, K, C, N, post = ctx.cfg
         L = _lib.lib()
-        v_colors = v_colors.contiguous()
+        v_colors, ld_vc = _rows(v_colors, 3)
         v_coeffs = torch.empty_like(coeffs)
         need_dirs = dirs is not None and ctx.needs_input_grad[1]
         need_means = means is not None and ctx.needs_input_grad[2]
         v_dirs = torch.empty_like(dirs) if need_dirs else None
         v_means = torch.empty_like(means) if need_means else None
         check(L.hgs_sh_bwd(degree, K, ptr(dirs), ptr(means), ptr(campos), ptr(coeffs), ptr(radii), ptr(colors),
-                           ptr(v_colors), C, N, post, ptr(v_coeffs), ptr(v_dirs), ptr(v_means), _stream()),
+                           ptr(v_colors), ld_vc, C, N, post, ptr(v_coeffs), ptr(v_dirs), ptr(v_means), _stream()),
               "hgs_sh_bwd")
         return None, v_dirs, v_means, None, v_coeffs, None, None
 
@@ -271,9 +292,12 @@ def isect_offset_encode(isect_ids: Tensor, n_cameras: int, tile_width: int, tile
 # a11: rasterize_to_pixels (3DGS)
 # =====================================================================================
 class _Blend3D(torch.autograd.Function):
+    """rasterize_to_pixels.  <= 4 channels: packed-record fast kernels (TMA-staged, per-warp culling,
+    fused expected-depth normalisation); 5..8 channels: plain kernels."""
+
     @staticmethod
     def forward(ctx, means2d, conics, colors, depths, opacities, backgrounds, width, height, tile_size,
-                isect_offsets, flatten_ids, absgrad):
+                isect_offsets, flatten_ids, absgrad, radii, normalize_depth):
         L = _lib.lib()
         C, N = opacities.shape
         CH = colors.shape[-1]
@@ -282,25 +306,61 @@ class _Blend3D(torch.autograd.Function):
         render_colors = torch.empty((C, height, width, D), dtype=torch.float32, device=dev)
         render_alphas = torch.empty((C, height, width, 1), dtype=torch.float32, device=dev)
         last_ids = torch.empty((C, height, width), dtype=torch.int32, device=dev)
-        check(L.hgs_blend3d_fwd(ptr(means2d), ptr(conics), ptr(colors), ptr(depths), ptr(opacities), ptr(backgrounds),
-                                C, N, CH, width, height, tile_size, ptr(isect_offsets), ptr(flatten_ids),
-                                flatten_ids.numel(), ptr(render_colors), ptr(render_alphas), ptr(last_ids), _stream()),
-              "hgs_blend3d_fwd")
-        ctx.save_for_backward(means2d, conics, colors, depths, opacities, backgrounds, isect_offsets, flatten_ids,
-                              render_alphas, last_ids)
-        ctx.cfg = (width, height, tile_size, absgrad)
+        fast = D <= 4 and not absgrad
+        ctx.fast = fast
+        ctx.cfg = (width, height, tile_size, absgrad, bool(normalize_depth), CH, D)
+        st = _stream()
+        if fast:
+            records = torch.empty(L.hgs_blend3d_pack_bytes(C * N), dtype=torch.uint8, device=dev)
+            check(L.hgs_blend3d_pack(ptr(means2d), ptr(conics), ptr(colors), ptr(depths), ptr(opacities), ptr(radii),
+                                     C * N, CH, ptr(records), st), "hgs_blend3d_pack")
+            check(L.hgs_blend3d_fwd_packed(ptr(records), ptr(backgrounds), C, D, int(normalize_depth), width, height,
+                                           tile_size, ptr(isect_offsets), ptr(flatten_ids), flatten_ids.numel(),
+                                           ptr(render_colors), ptr(render_alphas), ptr(last_ids), st),
+                  "hgs_blend3d_fwd_packed")
+            ctx.save_for_backward(records, backgrounds, isect_offsets, flatten_ids, render_colors, render_alphas,
+                                  last_ids)
+            ctx.shapes = (means2d.shape, depths is not None)
+        else:
+            check(L.hgs_blend3d_fwd(ptr(means2d), ptr(conics), ptr(colors), ptr(depths), ptr(opacities),
+                                    ptr(backgrounds), C, N, CH, width, height, tile_size, ptr(isect_offsets),
+                                    ptr(flatten_ids), flatten_ids.numel(), ptr(render_colors), ptr(render_alphas),
+                                    ptr(last_ids), st), "hgs_blend3d_fwd")
+            if normalize_depth:
+                raise NotImplementedError("fused depth normalisation needs <= 4 channels")
+            ctx.save_for_backward(means2d, conics, colors, depths, opacities, backgrounds, isect_offsets, flatten_ids,
+                                  render_alphas, last_ids)
         return render_colors, render_alphas
 
     @staticmethod
     def backward(ctx, v_render_colors, v_render_alphas):
-        (means2d, conics, colors, depths, opacities, backgrounds, isect_offsets, flatten_ids, render_alphas,
-         last_ids) = ctx.saved_tensors
-        width, height, tile_size, absgrad = ctx.cfg
+        width, height, tile_size, absgrad, normalize_depth, CH, D = ctx.cfg
         L = _lib.lib()
-        C, N = opacities.shape
-        CH = colors.shape[-1]
         v_render_colors = v_render_colors.contiguous()
         v_render_alphas = v_render_alphas.contiguous()
+        tail = (None,) * 8
+        if ctx.fast:
+            records, backgrounds, isect_offsets, flatten_ids, render_colors, render_alphas, last_ids = ctx.saved_tensors
+            (C, N, _), has_depth = ctx.shapes
+            vpack = torch.zeros((C, N, 12), dtype=torch.float32, device=records.device)
+            check(L.hgs_blend3d_bwd_packed(ptr(records), ptr(backgrounds), C, D, int(normalize_depth), width, height,
+                                           tile_size, ptr(isect_offsets), ptr(flatten_ids), flatten_ids.numel(),
+                                           ptr(render_colors), ptr(render_alphas), ptr(last_ids),
+                                           ptr(v_render_colors), ptr(v_render_alphas), ptr(vpack), _stream()),
+                  "hgs_blend3d_bwd_packed")
+            v_means2d, v_conics, v_opacities = vpack[..., 0:2], vpack[..., 2:5], vpack[..., 5]
+            v_colors = vpack[..., 8:8 + CH]
+            v_depths = vpack[..., 8 + CH] if has_depth else None
+            v_bg = None
+            if backgrounds is not None and ctx.needs_input_grad[5]:
+                vrc = v_render_colors
+                if normalize_depth:
+                    vrc = torch.cat([vrc[..., :-1], vrc[..., -1:] / render_alphas.clamp(min=1e-10)], -1)
+                v_bg = (vrc * (1.0 - render_alphas)).sum(dim=(1, 2))
+            return (v_means2d, v_conics, v_colors, v_depths, v_opacities, v_bg) + tail
+        (means2d, conics, colors, depths, opacities, backgrounds, isect_offsets, flatten_ids, render_alphas,
+         last_ids) = ctx.saved_tensors
+        C, N = opacities.shape
         v_means2d = torch.zeros_like(means2d)
         v_conics = torch.zeros_like(conics)
         v_colors = torch.zeros_like(colors)
@@ -317,11 +377,11 @@ class _Blend3D(torch.autograd.Function):
         v_bg = None
         if backgrounds is not None and ctx.needs_input_grad[5]:
             v_bg = (v_render_colors * (1.0 - render_alphas)).sum(dim=(1, 2))
-        return v_means2d, v_conics, v_colors, v_depths, v_opacities, v_bg, None, None, None, None, None, None
+        return (v_means2d, v_conics, v_colors, v_depths, v_opacities, v_bg) + tail
 
 
 def _blend3d(means2d, conics, colors, depths, opacities, backgrounds, width, height, tile_size, isect_offsets,
-             flatten_ids, absgrad=False):
+             flatten_ids, absgrad=False, radii=None, normalize_depth=False):
     if tile_size not in _TILE_SIZES:
         raise NotImplementedError(f"tile_size {tile_size} is not supported (supported: {_TILE_SIZES})")
     D = colors.shape[-1] + (1 if depths is not None else 0)
@@ -330,7 +390,7 @@ def _blend3d(means2d, conics, colors, depths, opacities, backgrounds, width, hei
     return _Blend3D.apply(_f32c(means2d, "means2d"), _f32c(conics, "conics"), _f32c(colors, "colors"),
                           _f32c(depths, "depths"), _f32c(opacities, "opacities"), _f32c(backgrounds, "backgrounds"),
                           int(width), int(height), int(tile_size), isect_offsets.contiguous(),
-                          flatten_ids.contiguous(), bool(absgrad))
+                          flatten_ids.contiguous(), bool(absgrad), radii, bool(normalize_depth))
 
 
 def rasterize_to_pixels(means2d: Tensor, conics: Tensor, colors: Tensor, opacities: Tensor, image_width: int,

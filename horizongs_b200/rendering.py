@@ -106,9 +106,12 @@ def rasterization(
 
     feats = _per_view_features(means, colors, viewmats, radii, sh_degree, C)
     feats, depth_ch, bgs = _mode_features(feats, depths, backgrounds, render_mode)
+    n_ch = feats.shape[-1] + (1 if depth_ch is not None else 0)
+    fuse_norm = render_mode in ("ED", "RGB+ED") and n_ch <= 4 and not absgrad
     render_colors, render_alphas = W._blend3d(means2d, conics, feats, depth_ch, opac, bgs, width, height, tile_size,
-                                              isect_offsets, flatten_ids, absgrad)
-    if render_mode in ("ED", "RGB+ED"):
+                                              isect_offsets, flatten_ids, absgrad, radii=radii,
+                                              normalize_depth=fuse_norm)
+    if render_mode in ("ED", "RGB+ED") and not fuse_norm:
         render_colors = torch.cat(
             [render_colors[..., :-1], render_colors[..., -1:] / render_alphas.clamp(min=1e-10)], dim=-1)
 

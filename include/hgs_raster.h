@@ -45,12 +45,14 @@ int hgs_project3d_fwd(const float* means, const float* quats, const float* scale
                       const float* Ks, int C, int N, int width, int height, float eps2d, float near_plane,
                       float far_plane, float radius_clip, int tile_size, int32_t* radii, float* means2d,
                       float* depths, float* conics, float* compensations, int32_t* tiles_per_gauss, void* stream);
-/* in: upstream gradients v_means2d[C,N,2], v_depths[C,N] (or NULL), v_conics[C,N,3];
- * out (overwritten, summed over cameras): v_means[N,3], v_quats[N,4], v_scales[N,3]. */
+/* in: upstream gradients v_means2d[C,N,2], v_depths[C,N] (or NULL), v_conics[C,N,3]; each with a row
+ * stride in floats (ld_* = 2, 1, 3 when dense) so that slices of the packed blend-gradient buffer can be
+ * passed without a copy;  out (overwritten, summed over cameras): v_means[N,3], v_quats[N,4], v_scales[N,3]. */
 int hgs_project3d_bwd(const float* means, const float* quats, const float* scales, const float* viewmats,
                       const float* Ks, int C, int N, int width, int height, float eps2d, float near_plane,
-                      float far_plane, const int32_t* radii, const float* v_means2d, const float* v_depths,
-                      const float* v_conics, float* v_means, float* v_quats, float* v_scales, void* stream);
+                      float far_plane, const int32_t* radii, const float* v_means2d, int ld_means2d,
+                      const float* v_depths, int ld_depths, const float* v_conics, int ld_conics, float* v_means,
+                      float* v_quats, float* v_scales, void* stream);
 
 /* ---- a4: fully_fused_projection_2dgs (render.py:171-186; inside rasterization_2dgs render.py:62) --
  * out: radii[C,N], means2d[C,N,2], depths[C,N], ray_transforms[C,N,3,3] (rows M0,M1,M2 of (K [R|t] H)),
@@ -73,10 +75,10 @@ int hgs_sh_fwd(int degree, int K, const float* dirs, const float* means, const f
                const int32_t* radii, int C, int N, int post, float* colors, void* stream);
 /* out (overwritten): v_coeffs[N,K,3] summed over cameras; v_dirs[C,N,3] or NULL; v_means[N,3] or NULL
  * (direction gradient summed over cameras).  `colors` is the forward output (needed for the clamp mask
- * when post != 0). */
+ * when post != 0).  ld_v_colors = row stride of v_colors in floats (3 when dense). */
 int hgs_sh_bwd(int degree, int K, const float* dirs, const float* means, const float* campos, const float* coeffs,
-               const int32_t* radii, const float* colors, const float* v_colors, int C, int N, int post,
-               float* v_coeffs, float* v_dirs, float* v_means, void* stream);
+               const int32_t* radii, const float* colors, const float* v_colors, int ld_v_colors, int C, int N,
+               int post, float* v_coeffs, float* v_dirs, float* v_means, void* stream);
 
 /* ---- a8-a10: tile intersection, tile|depth key sort, per-tile ranges (integer, bit-exact) --------
  * key = cam << (32 + tile_bits) | tile_id << 32 | (int64)(int32 bits of depth), value = flat index;
@@ -131,6 +133,27 @@ int hgs_blend3d_bwd(const float* means2d, const float* conics, const float* colo
                     const float* render_alphas, const int32_t* last_ids, const float* v_render_colors,
                     const float* v_render_alphas, float* v_means2d, float* v_means2d_abs, float* v_conics,
                     float* v_colors, float* v_depths, float* v_opacities, void* stream);
+
+/* Fast path of a11 for <= 4 render channels (every mode the reference uses).
+ * hgs_blend3d_pack writes one 64-byte record per Gaussian with radii > 0 (radii may be NULL = all):
+ * centre, conic scaled by -log2(e)/2, opacity, cut-off exponent, colour (+ depth as the last channel when
+ * depths != NULL).  records: hgs_blend3d_pack_bytes(C*N) bytes, 64-byte aligned.
+ * The blend kernels gather records with TMA bulk copies.  D = channels incl. the depth channel;
+ * normalize_depth != 0 fuses expected-depth normalisation (last channel / max(alpha, 1e-10)).
+ * vpack[C*N,12] (zero-filled by the caller) accumulates per-Gaussian gradients:
+ *   [0:2] v_means2d, [2:5] v_conics, [5] v_opacities, [8:8+D] v_colors (+ v_depths in the last channel). */
+size_t hgs_blend3d_pack_bytes(long long CN);
+int hgs_blend3d_pack(const float* means2d, const float* conics, const float* colors, const float* depths,
+                     const float* opacities, const int32_t* radii, long long CN, int CH, void* records, void* stream);
+int hgs_blend3d_fwd_packed(const void* records, const float* backgrounds, int C, int D, int normalize_depth,
+                           int width, int height, int tile_size, const int32_t* isect_offsets,
+                           const int32_t* flatten_ids, long long n_isects, float* render_colors,
+                           float* render_alphas, int32_t* last_ids, void* stream);
+int hgs_blend3d_bwd_packed(const void* records, const float* backgrounds, int C, int D, int normalize_depth,
+                           int width, int height, int tile_size, const int32_t* isect_offsets,
+                           const int32_t* flatten_ids, long long n_isects, const float* render_colors,
+                           const float* render_alphas, const int32_t* last_ids, const float* v_render_colors,
+                           const float* v_render_alphas, float* vpack, void* stream);
 
 /* ---- a12: rasterize_to_pixels_2dgs ----------------------------------------------------------------
  * As a11 with ray_transforms[C,N,3,3] and normals[C,N,3]; additionally blends normals, and writes
