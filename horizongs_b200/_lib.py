@@ -19,6 +19,7 @@ _p, _i, _ll, _f, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
 # name -> (restype, argtypes) ; order = include/hgs_raster.h
 SIGNATURES = {
     "hgs_abi_version": (_i, []),
+    "hgs_debug_launch_count": (C.c_ulonglong, []),
     "hgs_status_string": (C.c_char_p, [_i]),
     "hgs_project3d_fwd": (_i, [_p] * 5 + [_i] * 4 + [_f] * 4 + [_i] + [_p] * 6 + [_p]),
     "hgs_project3d_bwd": (_i, [_p] * 5 + [_i] * 4 + [_f] * 3 + [_p, _p, _i, _p, _i, _p, _i] + [_p] * 3 + [_p]),

@@ -2,7 +2,11 @@
 #include "hgs_common.cuh"
 #include "../../include/hgs_raster.h"
 
+unsigned long long g_hgs_launches = 0;
+
 HGS_API int hgs_abi_version(void) { return HGS_ABI_VERSION; }
+
+HGS_API unsigned long long hgs_debug_launch_count(void) { return __atomic_load_n(&g_hgs_launches, __ATOMIC_RELAXED); }
 
 HGS_API const char* hgs_status_string(int status) {
     switch (status) {

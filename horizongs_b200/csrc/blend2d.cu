@@ -343,6 +343,11 @@ __global__ void __launch_bounds__(BLK) blend2d_bwd_kernel(
 
 }  // namespace
 
+static inline int hgs_count_launch(int e) {
+    if (e == 0) __atomic_fetch_add(&g_hgs_launches, 1ull, __ATOMIC_RELAXED);
+    return e;
+}
+
 #define HGS_DISPATCH_D(D, CALL)              \
     switch (D) {                             \
         case 1: return CALL(1);              \
@@ -375,7 +380,7 @@ HGS_API int hgs_blend2d_fwd(const float* means2d, const float* ray_transforms, c
                                                     flatten_ids, (int)n_isects, render_colors, render_alphas,         \
                                                     render_normals, render_distort, render_median, last_ids,          \
                                                     median_ids),                                                      \
-     (int)cudaGetLastError())
+     hgs_count_launch((int)cudaGetLastError()))
     HGS_DISPATCH_D(D, CALL)
 #undef CALL
 }
@@ -403,7 +408,7 @@ HGS_API int hgs_blend2d_bwd(const float* means2d, const float* ray_transforms, c
          tile_h, isect_offsets, flatten_ids, (int)n_isects, render_colors, render_alphas, last_ids, median_ids,       \
          v_render_colors, v_render_alphas, v_render_normals, v_render_distort, v_render_median, v_means2d,            \
          v_ray_transforms, v_colors, v_depths, v_normals, v_opacities, v_densify),                                    \
-     (int)cudaGetLastError())
+     hgs_count_launch((int)cudaGetLastError()))
     HGS_DISPATCH_D(D, CALL)
 #undef CALL
 }

@@ -10,10 +10,14 @@
 #define HGS_ERR_TOO_LARGE (-2)
 #define HGS_ERR_WORKSPACE (-3)
 
+// cumulative number of kernel launches issued by this library (diagnostics only; see hgs_debug_launch_count)
+extern unsigned long long g_hgs_launches;
+
 #define HGS_LAUNCH_CHECK()                          \
     do {                                            \
         cudaError_t e__ = cudaGetLastError();       \
         if (e__ != cudaSuccess) return (int)e__;    \
+        __atomic_fetch_add(&g_hgs_launches, 1ull, __ATOMIC_RELAXED); \
     } while (0)
 
 static inline int hgs_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

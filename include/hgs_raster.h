@@ -34,6 +34,9 @@ extern "C" {
 
 #define HGS_ABI_VERSION 1
 int hgs_abi_version(void);
+/* cumulative count of kernels this library has launched in the process (diagnostics: bench.py reports the
+ * number launched inside its timed region) */
+unsigned long long hgs_debug_launch_count(void);
 /* human-readable text for a status code returned by any function below */
 const char* hgs_status_string(int status);
 
