@@ -257,6 +257,46 @@ __global__ void __launch_bounds__(BLK) blend3d_fwd_fast_kernel(
 }
 
 // =====================================================================================================
+// pair statistics (measurement aid, never on the timed path): P_eval = (pixel, Gaussian) pairs a per-pixel
+// front-to-back loop visits before the pixel stops, P_blend = pairs that pass the alpha test and are blended
+// =====================================================================================================
+__global__ void __launch_bounds__(BLK) blend3d_stats_kernel(const GRec* __restrict__ recs, int C, int W, int H,
+                                                            int tile_w, int tile_h,
+                                                            const int32_t* __restrict__ offsets,
+                                                            const int32_t* __restrict__ flatten_ids, int n_isects,
+                                                            unsigned long long* __restrict__ counters) {
+    const TileGeom g = tile_geom(tile_w, tile_h, W, H);
+    const int range_start = offsets[g.gtile];
+    const int range_end = (g.gtile == C * tile_w * tile_h - 1) ? n_isects : offsets[g.gtile + 1];
+    unsigned long long n_eval = 0, n_blend = 0;
+    if (g.inside) {
+        float T = 1.0f;
+        for (int idx = range_start; idx < range_end; ++idx) {
+            const float4* q = reinterpret_cast<const float4*>(recs + flatten_ids[idx]);
+            const float4 q0 = q[0], q1 = q[1];
+            ++n_eval;
+            const float dx = q0.x - g.px, dy = q0.y - g.py;
+            const float p2 = (q0.z * dx + q0.w * dy) * dx + (q1.x * dy) * dy;
+            const float alpha = fminf(HGS_ALPHA_MAX, q1.y * ex2_approx(p2));
+            if (p2 > 0.f || alpha < HGS_ALPHA_MIN) continue;
+            const float next_T = T * (1.0f - alpha);
+            if (next_T <= HGS_T_EPS) break;
+            ++n_blend;
+            T = next_T;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_eval += __shfl_xor_sync(0xFFFFFFFFu, n_eval, o);
+        n_blend += __shfl_xor_sync(0xFFFFFFFFu, n_blend, o);
+    }
+    if (g.lane == 0) {
+        atomicAdd(&counters[0], n_eval);
+        atomicAdd(&counters[1], n_blend);
+    }
+}
+
+// =====================================================================================================
 // fast backward
 // =====================================================================================================
 constexpr int ACC_STRIDE = 11;  // odd: conflict-free slot writes (10 lanes) and strided flush reads
@@ -806,6 +846,19 @@ HGS_API int hgs_blend3d_pack(const float* means2d, const float* conics, const fl
     if (CN == 0) return 0;
     pack3d_kernel<<<hgs_ceil_div(CN, 256), 256, 0, (cudaStream_t)stream>>>(means2d, conics, colors, depths, opacities,
                                                                             radii, CN, CH, (GRec*)records);
+    HGS_LAUNCH_CHECK();
+    return 0;
+}
+
+HGS_API int hgs_blend3d_stats(const void* records, int C, int width, int height, int tile_size,
+                              const int32_t* isect_offsets, const int32_t* flatten_ids, long long n_isects,
+                              unsigned long long* counters, void* stream) {
+    if (tile_size != TS || C <= 0 || width <= 0 || height <= 0 || n_isects < 0 || n_isects >= (1ll << 31))
+        return HGS_ERR_INVALID_ARG;
+    const int tile_w = (width + TS - 1) / TS, tile_h = (height + TS - 1) / TS;
+    dim3 grid(tile_w, tile_h, C);
+    blend3d_stats_kernel<<<grid, BLK, 0, (cudaStream_t)stream>>>((const GRec*)records, C, width, height, tile_w, tile_h,
+                                                                 isect_offsets, flatten_ids, (int)n_isects, counters);
     HGS_LAUNCH_CHECK();
     return 0;
 }

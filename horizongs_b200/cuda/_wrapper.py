@@ -24,6 +24,21 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# Optional stage hook for measurement (bench.py): called as hook(stage_name, 0) before and hook(stage_name, 1)
+# after the kernels of a stage are enqueued.  None (the default) costs one attribute test per stage.
+_STAGE_HOOK = None
+
+
+def set_stage_hook(fn):
+    global _STAGE_HOOK
+    _STAGE_HOOK = fn
+
+
+def _mark(name: str, phase: int):
+    if _STAGE_HOOK is not None:
+        _STAGE_HOOK(name, phase)
+
+
 def _f32c(t: Optional[Tensor], name: str) -> Optional[Tensor]:
     if t is None:
         return None
@@ -75,10 +90,12 @@ class _Project3D(torch.autograd.Function):
         conics = torch.empty((C, N, 3), dtype=torch.float32, device=dev)
         comps = torch.empty((C, N), dtype=torch.float32, device=dev) if calc_compensations else None
         tiles = torch.empty((C, N), dtype=torch.int32, device=dev) if tile_size > 0 else None
+        _mark("project3d_fwd", 0)
         check(L.hgs_project3d_fwd(ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), C, N, width, height,
                                   eps2d, near_plane, far_plane, radius_clip, max(tile_size, 1), ptr(radii),
                                   ptr(means2d), ptr(depths), ptr(conics), ptr(comps), ptr(tiles), _stream()),
               "hgs_project3d_fwd")
+        _mark("project3d_fwd", 1)
         ctx.save_for_backward(means, quats, scales, viewmats, Ks, radii)
         ctx.cfg = (width, height, eps2d, near_plane, far_plane)
         ctx.mark_non_differentiable(radii)
@@ -100,10 +117,12 @@ class _Project3D(torch.autograd.Function):
         v_means2d, ld_m = _rows(means.new_zeros((C, N, 2)) if v_means2d is None else v_means2d, 2)
         v_conics, ld_c = _rows(means.new_zeros((C, N, 3)) if v_conics is None else v_conics, 3)
         v_depths, ld_d = _rows(None if v_depths is None else v_depths.unsqueeze(-1), 1)
+        _mark("project3d_bwd", 0)
         check(L.hgs_project3d_bwd(ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), C, N, width, height,
                                   eps2d, near_plane, far_plane, ptr(radii), ptr(v_means2d), ld_m, ptr(v_depths), ld_d,
                                   ptr(v_conics), ld_c, ptr(v_means), ptr(v_quats), ptr(v_scales), _stream()),
               "hgs_project3d_bwd")
+        _mark("project3d_bwd", 1)
         return (v_means, v_quats, v_scales) + (None,) * 10
 
 
@@ -160,8 +179,10 @@ class _SphericalHarmonics(torch.autograd.Function):
         N, K = coeffs.shape[0], coeffs.shape[1]
         C = dirs.shape[0] if dirs is not None else campos.shape[0]
         colors = torch.empty((C, N, 3), dtype=torch.float32, device=coeffs.device)
+        _mark("sh_fwd", 0)
         check(L.hgs_sh_fwd(degree, K, ptr(dirs), ptr(means), ptr(campos), ptr(coeffs), ptr(radii), C, N, int(post),
                            ptr(colors), _stream()), "hgs_sh_fwd")
+        _mark("sh_fwd", 1)
         ctx.save_for_backward(dirs, means, campos, coeffs, radii, colors if post else None)
         ctx.cfg = (degree, K, C, N, int(post))
         return colors
@@ -177,9 +198,11 @@ class _SphericalHarmonics(torch.autograd.Function):
         need_means = means is not None and ctx.needs_input_grad[2]
         v_dirs = torch.empty_like(dirs) if need_dirs else None
         v_means = torch.empty_like(means) if need_means else None
+        _mark("sh_bwd", 0)
         check(L.hgs_sh_bwd(degree, K, ptr(dirs), ptr(means), ptr(campos), ptr(coeffs), ptr(radii), ptr(colors),
                            ptr(v_colors), ld_vc, C, N, post, ptr(v_coeffs), ptr(v_dirs), ptr(v_means), _stream()),
               "hgs_sh_bwd")
+        _mark("sh_bwd", 1)
         return None, v_dirs, v_means, None, v_coeffs, None, None
 
 
@@ -221,11 +244,14 @@ def _isect_sorted_from_counts(means2d, radii, depths, tiles_per_gauss, C, N, til
     order = torch.empty(CN, dtype=torch.int32, device=dev)
     cum_sorted = torch.empty(CN, dtype=torch.int32, device=dev)
     total = torch.empty(1, dtype=torch.int64, device=dev)
+    _mark("isect_prepare", 0)
     tb = L.hgs_isect_prepare_temp_bytes(CN)
     temp = torch.empty(tb, dtype=torch.uint8, device=dev)
     check(L.hgs_isect_prepare(ptr(depths), ptr(tiles_per_gauss), C, N, ptr(order), ptr(cum_sorted), ptr(total),
                               ptr(temp), tb, st), "hgs_isect_prepare")
+    _mark("isect_prepare", 1)
     n_isects = int(total.item())  # the one unavoidable host read: sizes the intersection arrays
+    _mark("isect_sorted", 0)
     if n_isects >= 2 ** 31:
         raise _lib.HgsError(f"{n_isects} tile intersections exceed the 32-bit index range")
     isect_ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
@@ -236,6 +262,7 @@ def _isect_sorted_from_counts(means2d, radii, depths, tiles_per_gauss, C, N, til
     check(L.hgs_isect_sorted(ptr(means2d), ptr(radii), ptr(depths), ptr(order), ptr(cum_sorted), C, N, n_isects,
                              tile_size, tile_width, tile_height, ptr(isect_ids), ptr(flatten_ids), ptr(offsets),
                              ptr(temp2), tb2, st), "hgs_isect_sorted")
+    _mark("isect_sorted", 1)
     return isect_ids, flatten_ids, offsets
 
 
@@ -312,12 +339,16 @@ class _Blend3D(torch.autograd.Function):
         st = _stream()
         if fast:
             records = torch.empty(L.hgs_blend3d_pack_bytes(C * N), dtype=torch.uint8, device=dev)
+            _mark("blend3d_pack", 0)
             check(L.hgs_blend3d_pack(ptr(means2d), ptr(conics), ptr(colors), ptr(depths), ptr(opacities), ptr(radii),
                                      C * N, CH, ptr(records), st), "hgs_blend3d_pack")
+            _mark("blend3d_pack", 1)
+            _mark("blend3d_fwd", 0)
             check(L.hgs_blend3d_fwd_packed(ptr(records), ptr(backgrounds), C, D, int(normalize_depth), width, height,
                                            tile_size, ptr(isect_offsets), ptr(flatten_ids), flatten_ids.numel(),
                                            ptr(render_colors), ptr(render_alphas), ptr(last_ids), st),
                   "hgs_blend3d_fwd_packed")
+            _mark("blend3d_fwd", 1)
             ctx.save_for_backward(records, backgrounds, isect_offsets, flatten_ids, render_colors, render_alphas,
                                   last_ids)
             ctx.shapes = (means2d.shape, depths is not None)
@@ -343,11 +374,13 @@ class _Blend3D(torch.autograd.Function):
             records, backgrounds, isect_offsets, flatten_ids, render_colors, render_alphas, last_ids = ctx.saved_tensors
             (C, N, _), has_depth = ctx.shapes
             vpack = torch.zeros((C, N, 12), dtype=torch.float32, device=records.device)
+            _mark("blend3d_bwd", 0)
             check(L.hgs_blend3d_bwd_packed(ptr(records), ptr(backgrounds), C, D, int(normalize_depth), width, height,
                                            tile_size, ptr(isect_offsets), ptr(flatten_ids), flatten_ids.numel(),
                                            ptr(render_colors), ptr(render_alphas), ptr(last_ids),
                                            ptr(v_render_colors), ptr(v_render_alphas), ptr(vpack), _stream()),
                   "hgs_blend3d_bwd_packed")
+            _mark("blend3d_bwd", 1)
             v_means2d, v_conics, v_opacities = vpack[..., 0:2], vpack[..., 2:5], vpack[..., 5]
             v_colors = vpack[..., 8:8 + CH]
             v_depths = vpack[..., 8 + CH] if has_depth else None
@@ -573,3 +606,21 @@ def rasterize_to_pixels_2dgs(means2d: Tensor, ray_transforms: Tensor, colors: Te
         raise NotImplementedError("packed layout / tile masks / absgrad are not supported")
     return _blend2d(means2d, ray_transforms, colors, None, normals, opacities, densify, backgrounds, image_width,
                     image_height, tile_size, isect_offsets, flatten_ids, distloss)
+
+
+@torch.no_grad()
+def blend3d_pair_stats(means2d, conics, opacities, radii, width, height, tile_size, isect_offsets, flatten_ids):
+    """(P_eval, P_blend) of a view -- measurement aid for bench.py's roofline figures (not on the product path)."""
+    L = _lib.lib()
+    C, N = opacities.shape
+    dev = means2d.device
+    records = torch.empty(L.hgs_blend3d_pack_bytes(C * N), dtype=torch.uint8, device=dev)
+    dummy = torch.zeros((C, N, 1), dtype=torch.float32, device=dev)
+    st = _stream()
+    check(L.hgs_blend3d_pack(ptr(means2d.contiguous()), ptr(conics.contiguous()), ptr(dummy), None,
+                             ptr(opacities.contiguous()), ptr(radii), C * N, 1, ptr(records), st), "hgs_blend3d_pack")
+    counters = torch.zeros(2, dtype=torch.int64, device=dev)
+    check(L.hgs_blend3d_stats(ptr(records), C, int(width), int(height), int(tile_size), ptr(isect_offsets),
+                              ptr(flatten_ids), flatten_ids.numel(), ptr(counters), st), "hgs_blend3d_stats")
+    p_eval, p_blend = counters.tolist()
+    return int(p_eval), int(p_blend)

@@ -158,6 +158,13 @@ int hgs_blend3d_bwd_packed(const void* records, const float* backgrounds, int C,
                            const float* render_alphas, const int32_t* last_ids, const float* v_render_colors,
                            const float* v_render_alphas, float* vpack, void* stream);
 
+/* Measurement aid (not on the product path): counters[0] += P_eval, the (pixel, Gaussian) pairs a per-pixel
+ * front-to-back loop visits before the pixel stops; counters[1] += P_blend, the pairs actually blended.
+ * counters: two zero-initialised uint64 on the device. */
+int hgs_blend3d_stats(const void* records, int C, int width, int height, int tile_size,
+                      const int32_t* isect_offsets, const int32_t* flatten_ids, long long n_isects,
+                      unsigned long long* counters, void* stream);
+
 /* ---- a12: rasterize_to_pixels_2dgs ----------------------------------------------------------------
  * As a11 with ray_transforms[C,N,3,3] and normals[C,N,3]; additionally blends normals, and writes
  * render_distort[C,H,W,1] (NULL = distortion off), render_median[C,H,W,1], median_ids[C,H,W]. */
