@@ -215,6 +215,8 @@ def run_ours(args):
     N = sc.n
     # densification statistics (scene/basic_model.py:96-144): gradient-norm accumulator and visibility count
     stats = torch.zeros(2, N, device=dev)
+    step_stats = torch.zeros(2, N, device=dev) if world > 1 else None
+    from horizongs_b200 import distributed as D
     # pinned host copies for the end-to-end arm
     gts_pin = gts_cpu.pin_memory()
     views_pin, Ks_pin = views_cpu.pin_memory(), Ks_cpu.pin_memory()
@@ -232,16 +234,18 @@ def run_ours(args):
         meta["means2d"].retain_grad()
         loss = loss_fn(rc, ra, gt)
         loss.backward()
-        # densification statistics from the view-space gradient (pixel units -> NDC-like as basic_model.py:132-133)
-        g2 = meta["means2d"].grad[0]
-        vis = meta["radii"][0] > 0
-        local_stats = torch.stack([torch.sqrt((g2[:, 0] * (0.5 * W)) ** 2 + (g2[:, 1] * (0.5 * H)) ** 2), vis.float()])
+        # densification statistics from the view-space gradient (basic_model.py:131-144), one fused kernel;
+        # computed per view BEFORE the exchange, then summed over ranks together with the gradients
         if world > 1:
-            hs = [dist.all_reduce(p.grad, async_op=True) for p in params]
-            hs.append(dist.all_reduce(local_stats, async_op=True))
+            step_stats.zero_()
+            Wr.densification_stats_update(meta["means2d"].grad, meta["radii"], W, H, step_stats[0], step_stats[1])
+            hs = D.allreduce_gradients(params, async_op=True)
+            hs.append(dist.all_reduce(step_stats, async_op=True))
             for h in hs:
                 h.wait()
-        stats.add_(local_stats)
+            stats.add_(step_stats)
+        else:
+            Wr.densification_stats_update(meta["means2d"].grad, meta["radii"], W, H, stats[0], stats[1])
         out = loss.item() if e2e else None
         for p in params:
             p.grad = None

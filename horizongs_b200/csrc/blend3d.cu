@@ -78,6 +78,11 @@ __global__ void pack3d_kernel(const float* __restrict__ means2d, const float* __
     for (int k = 0; k < 4; ++k) dst[k] = src[k];
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -445,7 +450,7 @@ __global__ void __launch_bounds__(BLK) blend3d_bwd_fast_kernel(
                 if (valid) {
                     const float4 q2 = q[2];
                     const float col[4] = {q2.x, q2.y, q2.z, q2.w};
-                    const float ra = 1.0f / (1.0f - alpha);
+                    const float ra = rcp_approx(1.0f - alpha);  // 1 - alpha in [1e-3, 1]: 1-ulp reciprocal
                     T *= ra;
                     const float fac = alpha * T;
                     float v_alpha = 0.f;

@@ -32,6 +32,7 @@ SOURCES = {
     "isect.cu": [],
     "blend3d.cu": [],
     "blend2d.cu": [],
+    "densify.cu": [],
 }
 
 

@@ -5,9 +5,10 @@
 // B200-first ordering.  gsplat emits I (key,value) pairs Gaussian-major and runs a generic
 // 64-bit LSD radix sort over 32 + tile_bits + cam_bits key bits (6 passes x 24 B r/w per pair).
 // The same order is produced here with far less HBM traffic:
-//   1. depth-order the C*N Gaussians once (u32 key = depth bits, 4 stable 8-bit passes over C*N pairs,
-//      plus a camera pass when C > 1);
-//   2. emit the pairs in that order (so pairs are already depth-ordered, ties in flat-index order);
+//   1. compact the Gaussians that touch at least one tile (typically 10-20 % of a large scene) and
+//      depth-order them once (u32 key = depth bits, 4 stable 8-bit passes, plus a camera pass when C > 1);
+//   2. emit the pairs in that order, one thread per intersection (fully coalesced writes): pairs are already
+//      depth-ordered, ties in flat-index order;
 //   3. stable-partition the I pairs by (cam, tile) only: ceil((tile_bits+cam_bits)/8) passes of 8 B pairs.
 // A stable sort on (cam, tile) of a sequence ordered by (depth, flat index) is exactly the stable sort
 // on the full cam|tile|depth key of the Gaussian-major sequence: within one tile a Gaussian appears once,
@@ -15,6 +16,9 @@
 // ascending flat index.
 //
 // Radix pass = 3 launches (chunk histogram, per-digit row scan, chunk scatter); no inter-block waiting.
+// Element counts that are only known on the device (visible Gaussians) are read from device memory by
+// over-provisioned grids, so phase 1 needs no host round trip.  The scatter re-orders each 2048-pair tile in
+// shared memory so that global writes are contiguous runs per digit.
 // Roofline: HBM.  Per pass 4 B (hist) + 8 B + 8 B per pair.
 #include "hgs_common.cuh"
 #include "hgs_constants.cuh"
@@ -29,6 +33,7 @@ constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 2048 pairs per block iteratio
 constexpr int RADIX = 256;
 constexpr int RS_MAX_CHUNKS = 148 * 4;
 constexpr int SCAN_THREADS = 1024;
+constexpr int CP_TILE = 1024;  // elements per block in the compaction kernels
 
 struct DigitSpec {
     int shift;
@@ -40,39 +45,18 @@ __device__ __forceinline__ uint32_t digit_of(const DigitSpec& ds, uint32_t key, 
     return (src >> ds.shift) & ds.mask;
 }
 
-struct ChunkPlan {
-    int n_chunks;
-    int tiles_per_chunk;
-};
-static ChunkPlan plan_chunks(long long n) {
-    long long tiles = (n + RS_TILE - 1) / RS_TILE;
-    ChunkPlan p;
-    p.n_chunks = (int)(tiles < RS_MAX_CHUNKS ? (tiles > 0 ? tiles : 1) : RS_MAX_CHUNKS);
-    p.tiles_per_chunk = (int)((tiles + p.n_chunks - 1) / p.n_chunks);
-    if (p.tiles_per_chunk < 1) p.tiles_per_chunk = 1;
-    return p;
-}
-
-__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint32_t* __restrict__ keys,
-                                                                const uint32_t* __restrict__ vals, long long n,
-                                                                DigitSpec ds, int tiles_per_chunk,
-                                                                uint32_t* __restrict__ hist) {
-    __shared__ uint32_t s_hist[RADIX];
-    for (int i = threadIdx.x; i < RADIX; i += RS_THREADS) s_hist[i] = 0;
-    __syncthreads();
-    const long long begin = (long long)blockIdx.x * tiles_per_chunk * RS_TILE;
-    long long end = begin + (long long)tiles_per_chunk * RS_TILE;
+// chunk c of a pass over n elements with gridDim.x chunks: [begin, end)
+__device__ __forceinline__ void chunk_range(long long n, long long& begin, long long& end) {
+    const long long tiles = (n + RS_TILE - 1) / RS_TILE;
+    const long long tpc = (tiles + gridDim.x - 1) / gridDim.x;
+    begin = (long long)blockIdx.x * tpc * RS_TILE;
+    end = begin + tpc * RS_TILE;
     if (end > n) end = n;
-    for (long long base = begin; base < end; base += RS_THREADS) {
-        long long i = base + threadIdx.x;
-        bool valid = i < end;
-        uint32_t d = valid ? digit_of(ds, keys[i], ds.from_val_div > 0 ? vals[i] : 0u) : 0xFFFFFFFFu;
-        unsigned m = __match_any_sync(0xFFFFFFFFu, d);
-        int leader = __ffs(m) - 1;
-        if (valid && (int)(threadIdx.x & 31) == leader) atomicAdd(&s_hist[d], (uint32_t)__popc(m));
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < RADIX; i += RS_THREADS) hist[(long long)i * gridDim.x + blockIdx.x] = s_hist[i];
+}
+static int n_chunks_for(long long cap) {
+    long long tiles = (cap + RS_TILE - 1) / RS_TILE;
+    if (tiles < 1) tiles = 1;
+    return (int)(tiles < RS_MAX_CHUNKS ? tiles : RS_MAX_CHUNKS);
 }
 
 // block-wide exclusive scan of one value per thread (RS_THREADS threads); returns the exclusive prefix and
@@ -99,6 +83,27 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp
     return wbase + incl - v;
 }
 
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint32_t* __restrict__ keys,
+                                                                const uint32_t* __restrict__ vals,
+                                                                const long long* __restrict__ n_dev, DigitSpec ds,
+                                                                uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s_hist[RADIX];
+    for (int i = threadIdx.x; i < RADIX; i += RS_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    long long begin, end;
+    chunk_range(*n_dev, begin, end);
+    for (long long base = begin; base < end; base += RS_THREADS) {
+        long long i = base + threadIdx.x;
+        bool valid = i < end;
+        uint32_t d = valid ? digit_of(ds, keys[i], ds.from_val_div > 0 ? vals[i] : 0u) : 0xFFFFFFFFu;
+        unsigned m = __match_any_sync(0xFFFFFFFFu, d);
+        int leader = __ffs(m) - 1;
+        if (valid && (int)(threadIdx.x & 31) == leader) atomicAdd(&s_hist[d], (uint32_t)__popc(m));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < RADIX; i += RS_THREADS) hist[(long long)i * gridDim.x + blockIdx.x] = s_hist[i];
+}
+
 // hist is [RADIX][n_chunks]: block d turns row d into its exclusive scan (over chunks) and writes the row total
 __global__ void __launch_bounds__(RS_THREADS) radix_rowscan_kernel(uint32_t* __restrict__ hist, int n_chunks,
                                                                    uint32_t* __restrict__ rowsum) {
@@ -118,11 +123,15 @@ __global__ void __launch_bounds__(RS_THREADS) radix_rowscan_kernel(uint32_t* __r
 
 __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(
     const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
-    uint32_t* __restrict__ vals_out, long long n, DigitSpec ds, int tiles_per_chunk,
+    uint32_t* __restrict__ vals_out, const long long* __restrict__ n_dev, DigitSpec ds,
     const uint32_t* __restrict__ hist_scanned, const uint32_t* __restrict__ rowsum) {
-    __shared__ uint32_t s_base[RADIX];
+    __shared__ uint32_t s_base[RADIX];    // running global position of the next element of digit d (this chunk)
+    __shared__ uint32_t s_start[RADIX];   // first local sorted index of digit d inside the current tile
+    __shared__ uint32_t s_delta[RADIX];   // global position - local sorted index for digit d (mod 2^32)
     __shared__ uint32_t s_whist[RS_WARPS][RADIX];
     __shared__ uint32_t s_warp[RS_WARPS];
+    __shared__ uint32_t s_key[RS_TILE];
+    __shared__ uint32_t s_val[RS_TILE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     {
@@ -131,20 +140,19 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(
         const uint32_t digit_base = block_excl_scan(rowsum[threadIdx.x], s_warp, tot);
         s_base[threadIdx.x] = digit_base + hist_scanned[(long long)threadIdx.x * gridDim.x + blockIdx.x];
     }
-    const long long begin = (long long)blockIdx.x * tiles_per_chunk * RS_TILE;
-    long long end = begin + (long long)tiles_per_chunk * RS_TILE;
-    if (end > n) end = n;
+    long long begin, end;
+    chunk_range(*n_dev, begin, end);
 
     for (long long tile = begin; tile < end; tile += RS_TILE) {
         uint32_t key[RS_ITEMS], val[RS_ITEMS], dig[RS_ITEMS], rank[RS_ITEMS];
-        bool valid[RS_ITEMS];
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; ++i) {
             long long idx = tile + warp * (RS_ITEMS * 32) + i * 32 + lane;
-            valid[i] = idx < end;
-            key[i] = valid[i] ? keys_in[idx] : 0xFFFFFFFFu;
-            val[i] = valid[i] ? vals_in[idx] : 0u;
-            dig[i] = valid[i] ? digit_of(ds, key[i], val[i]) : (uint32_t)(RADIX - 1);
+            const bool valid = idx < end;
+            key[i] = valid ? keys_in[idx] : 0xFFFFFFFFu;
+            val[i] = valid ? vals_in[idx] : 0u;
+            // padding sorts last inside the tile (largest digit, highest index) and is never written out
+            dig[i] = valid ? digit_of(ds, key[i], val[i]) : (uint32_t)(RADIX - 1);
         }
 #pragma unroll
         for (int i = 0; i < RADIX / 32; ++i) s_whist[warp][i * 32 + lane] = 0;
@@ -158,25 +166,40 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(
             __syncwarp();
         }
         __syncthreads();
+        uint32_t cnt_d = 0;
         {
-            // thread d: prefix over warps for digit d, starting from the running chunk base
+            // thread d: exclusive prefix over warps inside digit d, and the tile's count of digit d
             const int d = threadIdx.x;  // RS_THREADS == RADIX
-            uint32_t run = s_base[d];
 #pragma unroll
             for (int w = 0; w < RS_WARPS; ++w) {
                 uint32_t t = s_whist[w][d];
-                s_whist[w][d] = run;
-                run += t;
+                s_whist[w][d] = cnt_d;
+                cnt_d += t;
             }
-            s_base[d] = run;
         }
+        uint32_t tot;
+        const uint32_t start_d = block_excl_scan(cnt_d, s_warp, tot);  // contains __syncthreads
+        s_start[threadIdx.x] = start_d;
+        s_delta[threadIdx.x] = s_base[threadIdx.x] - start_d;
+        s_base[threadIdx.x] += cnt_d;
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; ++i) {
-            if (valid[i]) {
-                uint32_t pos = s_whist[warp][dig[i]] + rank[i];
-                keys_out[pos] = key[i];
-                vals_out[pos] = val[i];
+            const uint32_t q = s_start[dig[i]] + s_whist[warp][dig[i]] + rank[i];
+            s_key[q] = key[i];
+            s_val[q] = val[i];
+        }
+        __syncthreads();
+        const long long rem = end - tile;
+        const int n_valid = (int)(rem < RS_TILE ? rem : RS_TILE);
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            const int q = i * RS_THREADS + threadIdx.x;
+            if (q < n_valid) {
+                const uint32_t k = s_key[q], v = s_val[q];
+                const uint32_t pos = s_delta[digit_of(ds, k, v)] + (uint32_t)q;
+                keys_out[pos] = k;
+                vals_out[pos] = v;
             }
         }
         __syncthreads();
@@ -184,17 +207,16 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(
 }
 static_assert(RS_THREADS == RADIX, "one thread per digit in the warp-prefix step");
 
-// one stable LSD pass: (keys_in, vals_in) -> (keys_out, vals_out)
+// one stable LSD pass: (keys_in, vals_in) -> (keys_out, vals_out); n lives on the device, cap bounds it
 static int radix_pass(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
-                      long long n, DigitSpec ds, uint32_t* hist, cudaStream_t st) {
-    ChunkPlan p = plan_chunks(n);
-    radix_hist_kernel<<<p.n_chunks, RS_THREADS, 0, st>>>(keys_in, vals_in, n, ds, p.tiles_per_chunk, hist);
+                      const long long* n_dev, long long cap, DigitSpec ds, uint32_t* hist, cudaStream_t st) {
+    const int nc = n_chunks_for(cap);
+    radix_hist_kernel<<<nc, RS_THREADS, 0, st>>>(keys_in, vals_in, n_dev, ds, hist);
     HGS_LAUNCH_CHECK();
     uint32_t* rowsum = hist + (size_t)RADIX * RS_MAX_CHUNKS;
-    radix_rowscan_kernel<<<RADIX, RS_THREADS, 0, st>>>(hist, p.n_chunks, rowsum);
+    radix_rowscan_kernel<<<RADIX, RS_THREADS, 0, st>>>(hist, nc, rowsum);
     HGS_LAUNCH_CHECK();
-    radix_scatter_kernel<<<p.n_chunks, RS_THREADS, 0, st>>>(keys_in, vals_in, keys_out, vals_out, n, ds,
-                                                            p.tiles_per_chunk, hist, rowsum);
+    radix_scatter_kernel<<<nc, RS_THREADS, 0, st>>>(keys_in, vals_in, keys_out, vals_out, n_dev, ds, hist, rowsum);
     HGS_LAUNCH_CHECK();
     return 0;
 }
@@ -208,7 +230,8 @@ static int n_bits_of(long long n) {  // floor(log2(n)) + 1 for n >= 1
 }
 
 // ---------------------------------------------------------------------------------------------
-// large exclusive scan (i32 in, i32 out, i64 total): reduce / scan-of-sums / scan
+// large exclusive scan (i32 in, i32 out, i64 total): reduce / scan-of-sums / scan.
+// n is read from device memory (n_dev) and bounded by cap (grid size).
 // ---------------------------------------------------------------------------------------------
 constexpr int LS_THREADS = 256;
 constexpr int LS_ITEMS = 16;
@@ -225,9 +248,11 @@ __device__ __forceinline__ long long block_reduce_ll(long long v, long long* s_t
     return r;
 }
 
-__global__ void __launch_bounds__(LS_THREADS) ls_reduce_kernel(const int32_t* __restrict__ in, long long n,
+__global__ void __launch_bounds__(LS_THREADS) ls_reduce_kernel(const int32_t* __restrict__ in,
+                                                               const long long* __restrict__ n_dev,
                                                                long long* __restrict__ block_sums) {
     __shared__ long long s_tmp[LS_THREADS / 32];
+    const long long n = *n_dev;
     const long long base = (long long)blockIdx.x * LS_TILE;
     long long sum = 0;
 #pragma unroll
@@ -266,9 +291,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) ls_scan_sums_kernel(long long* _
 }
 
 __global__ void __launch_bounds__(LS_THREADS) ls_scan_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out,
-                                                             long long n, const long long* __restrict__ block_sums) {
+                                                             const long long* __restrict__ n_dev,
+                                                             const long long* __restrict__ block_sums) {
     // thread t owns LS_ITEMS consecutive items (blocked arrangement)
     __shared__ long long s_warp[LS_THREADS / 32];
+    const long long n = *n_dev;
+    if ((long long)blockIdx.x * LS_TILE >= n) return;
     const long long base = (long long)blockIdx.x * LS_TILE + (long long)threadIdx.x * LS_ITEMS;
     int32_t v[LS_ITEMS];
     long long sum = 0;
@@ -278,7 +306,6 @@ __global__ void __launch_bounds__(LS_THREADS) ls_scan_kernel(const int32_t* __re
         v[i] = idx < n ? in[idx] : 0;
         sum += v[i];
     }
-    // exclusive scan of per-thread sums across the block
     long long incl = sum;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -299,23 +326,23 @@ __global__ void __launch_bounds__(LS_THREADS) ls_scan_kernel(const int32_t* __re
     }
 }
 
-static int large_scan(const int32_t* in, int32_t* out, long long* total_dev, long long n, void* temp,
-                      size_t temp_bytes, cudaStream_t st) {
-    if (n <= 0) {
-        cudaError_t e = cudaMemsetAsync(total_dev, 0, sizeof(long long), st);
-        return (int)e;
-    }
-    const int nb = hgs_ceil_div(n, LS_TILE);
+// exclusive scan of in[0..*n_dev) (n <= cap); total -> total_dev[0].  temp: ceil(cap/LS_TILE) long longs
+static int large_scan(const int32_t* in, int32_t* out, long long* total_dev, const long long* n_dev, long long cap,
+                      void* temp, size_t temp_bytes, cudaStream_t st) {
+    if (cap <= 0) return (int)cudaMemsetAsync(total_dev, 0, sizeof(long long), st);
+    const int nb = hgs_ceil_div(cap, LS_TILE);
     if (temp_bytes < (size_t)nb * sizeof(long long)) return HGS_ERR_WORKSPACE;
     long long* sums = (long long*)temp;
-    ls_reduce_kernel<<<nb, LS_THREADS, 0, st>>>(in, n, sums);
+    ls_reduce_kernel<<<nb, LS_THREADS, 0, st>>>(in, n_dev, sums);
     HGS_LAUNCH_CHECK();
     ls_scan_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(sums, nb, total_dev);
     HGS_LAUNCH_CHECK();
-    ls_scan_kernel<<<nb, LS_THREADS, 0, st>>>(in, out, n, sums);
+    ls_scan_kernel<<<nb, LS_THREADS, 0, st>>>(in, out, n_dev, sums);
     HGS_LAUNCH_CHECK();
     return 0;
 }
+
+__global__ void set_ll_kernel(long long* p, long long v) { *p = v; }
 
 // ---------------------------------------------------------------------------------------------
 // a8 kernels
@@ -359,69 +386,115 @@ __global__ void isect_emit_kernel(const float* __restrict__ means2d, const int32
         }
 }
 
-__global__ void depth_keys_kernel(const float* __restrict__ depths, const int32_t* __restrict__ tiles_per_gauss,
-                                  long long CN, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= CN) return;
-    keys[i] = tiles_per_gauss[i] > 0 ? (uint32_t)__float_as_int(depths[i]) : 0xFFFFFFFFu;
-    vals[i] = (uint32_t)i;
+// ---- compaction of the Gaussians that touch at least one tile (order-preserving) ---------------------
+__global__ void __launch_bounds__(RS_THREADS) vis_count_kernel(const int32_t* __restrict__ tiles_per_gauss,
+                                                               long long CN, long long* __restrict__ blk_count) {
+    __shared__ long long s_tmp[RS_THREADS / 32];
+    const long long base = (long long)blockIdx.x * CP_TILE;
+    long long c = 0;
+#pragma unroll
+    for (int i = 0; i < CP_TILE / RS_THREADS; ++i) {
+        const long long idx = base + i * RS_THREADS + threadIdx.x;
+        if (idx < CN && tiles_per_gauss[idx] > 0) ++c;
+    }
+    const long long tot = block_reduce_ll(c, s_tmp);
+    if (threadIdx.x == 0) blk_count[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(RS_THREADS) compact_kernel(const float* __restrict__ depths,
+                                                             const int32_t* __restrict__ tiles_per_gauss, long long CN,
+                                                             const long long* __restrict__ blk_base,
+                                                             uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    __shared__ uint32_t s_warp[RS_WARPS];
+    constexpr int PER = CP_TILE / RS_THREADS;  // 4 consecutive elements per thread (order preserving)
+    const long long first = (long long)blockIdx.x * CP_TILE + (long long)threadIdx.x * PER;
+    bool vis[PER];
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const long long idx = first + i;
+        vis[i] = idx < CN && tiles_per_gauss[idx] > 0;
+        cnt += vis[i] ? 1u : 0u;
+    }
+    uint32_t tot;
+    uint32_t pos = block_excl_scan(cnt, s_warp, tot);
+    const long long out0 = blk_base[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        if (vis[i]) {
+            const long long idx = first + i;
+            keys[out0 + pos] = (uint32_t)__float_as_int(depths[idx]);
+            vals[out0 + pos] = (uint32_t)idx;
+            ++pos;
+        }
+    }
 }
 
 __global__ void gather_counts_kernel(const uint32_t* __restrict__ vals, const int32_t* __restrict__ tiles_per_gauss,
-                                     long long CN, int32_t* __restrict__ order, int32_t* __restrict__ cnt_sorted) {
+                                     const long long* __restrict__ n_dev, int32_t* __restrict__ order,
+                                     int32_t* __restrict__ cnt_sorted) {
     long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= CN) return;
+    if (j >= *n_dev) return;
     uint32_t g = vals[j];
     order[j] = (int32_t)g;
     cnt_sorted[j] = tiles_per_gauss[g];
 }
 
-// depth-ordered emission of (cam|tile key, flat index); one warp per 32 consecutive sorted Gaussians,
-// lanes cooperate on Gaussians that cover many tiles
-__global__ void __launch_bounds__(256) emit_sorted_kernel(const float* __restrict__ means2d,
-                                                          const int32_t* __restrict__ radii,
-                                                          const int32_t* __restrict__ order,
-                                                          const int32_t* __restrict__ cum_sorted, long long CN, int N,
-                                                          int tile_size, int tile_w, int tile_h, int tile_bits,
-                                                          uint32_t* __restrict__ tkeys, uint32_t* __restrict__ vals) {
-    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-    uint32_t g = 0;
-    uint32_t cur = 0;
-    if (j < CN) {
-        g = (uint32_t)order[j];
-        int r = radii[g];
-        if (r > 0) {
-            float2 m = reinterpret_cast<const float2*>(means2d)[g];
-            hgs_tile_bbox(m.x, m.y, (float)r, (float)tile_size, tile_w, tile_h, x0, y0, x1, y1);
-            cur = (uint32_t)cum_sorted[j];
+// ---- depth-ordered emission, one thread per intersection ----------------------------------------------
+// Block b owns emissions [b*RS_TILE, (b+1)*RS_TILE): it locates the (at most RS_TILE) sorted Gaussians that
+// produce them, stages their tile boxes in shared memory and lets every thread binary-search its Gaussian.
+__global__ void __launch_bounds__(RS_THREADS) emit_sorted_kernel(
+    const float* __restrict__ means2d, const int32_t* __restrict__ radii, const int32_t* __restrict__ order,
+    const int32_t* __restrict__ cum_sorted, long long n_vis, long long n_isects, int N, int tile_size, int tile_w,
+    int tile_h, int tile_bits, uint32_t* __restrict__ tkeys, uint32_t* __restrict__ vals) {
+    __shared__ int s_cum[RS_TILE];
+    __shared__ uint32_t s_g[RS_TILE];
+    __shared__ uint32_t s_xy[RS_TILE];   // y0 << 16 | x0
+    __shared__ int s_w[RS_TILE];
+    __shared__ long long s_j[2];
+    const long long e0 = (long long)blockIdx.x * RS_TILE;
+    long long e1 = e0 + RS_TILE;
+    if (e1 > n_isects) e1 = n_isects;
+    if (threadIdx.x < 2) {
+        // last j with cum_sorted[j] <= target
+        const long long target = threadIdx.x == 0 ? e0 : e1 - 1;
+        long long lo = 0, hi = n_vis - 1;
+        while (lo < hi) {
+            const long long mid = (lo + hi + 1) >> 1;
+            if ((long long)cum_sorted[mid] <= target) lo = mid; else hi = mid - 1;
         }
+        s_j[threadIdx.x] = lo;
     }
-    const int w = x1 - x0;
-    const int cnt = (y1 - y0) * w;
-    const uint32_t cam_enc = (g / (uint32_t)N) << tile_bits;
-    constexpr int BIG = 32;
-    if (cnt > 0 && cnt < BIG) {
-        for (int k = 0; k < cnt; ++k) {
-            int y = y0 + k / w, x = x0 + k % w;
-            tkeys[cur + k] = cam_enc | (uint32_t)(y * tile_w + x);
-            vals[cur + k] = g;
-        }
+    __syncthreads();
+    const long long j0 = s_j[0];
+    const int nj = (int)(s_j[1] - j0 + 1);   // <= RS_TILE: every compacted Gaussian emits at least once
+    for (int j = threadIdx.x; j < nj; j += RS_THREADS) {
+        const uint32_t g = (uint32_t)order[j0 + j];
+        const float2 m = reinterpret_cast<const float2*>(means2d)[g];
+        int x0, y0, x1, y1;
+        hgs_tile_bbox(m.x, m.y, (float)radii[g], (float)tile_size, tile_w, tile_h, x0, y0, x1, y1);
+        s_cum[j] = cum_sorted[j0 + j];
+        s_g[j] = g;
+        s_xy[j] = ((uint32_t)y0 << 16) | (uint32_t)x0;
+        s_w[j] = x1 - x0;
     }
-    // big ones: whole warp writes
-    unsigned big = __ballot_sync(0xFFFFFFFFu, cnt >= BIG);
-    while (big) {
-        int src = __ffs(big) - 1;
-        big &= big - 1;
-        int bx0 = __shfl_sync(0xFFFFFFFFu, x0, src), by0 = __shfl_sync(0xFFFFFFFFu, y0, src);
-        int bw = __shfl_sync(0xFFFFFFFFu, w, src), bcnt = __shfl_sync(0xFFFFFFFFu, cnt, src);
-        uint32_t bcur = __shfl_sync(0xFFFFFFFFu, cur, src), bg = __shfl_sync(0xFFFFFFFFu, g, src);
-        uint32_t bcam = __shfl_sync(0xFFFFFFFFu, cam_enc, src);
-        for (int k = lane; k < bcnt; k += 32) {
-            int y = by0 + k / bw, x = bx0 + k % bw;
-            tkeys[bcur + k] = bcam | (uint32_t)(y * tile_w + x);
-            vals[bcur + k] = bg;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const long long e = e0 + i * RS_THREADS + threadIdx.x;
+        if (e < e1) {
+            int lo = 0, hi = nj - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if ((long long)s_cum[mid] <= e) lo = mid; else hi = mid - 1;
+            }
+            const int k = (int)(e - s_cum[lo]);
+            const int w = s_w[lo];
+            const uint32_t xy = s_xy[lo];
+            const int y = (int)(xy >> 16) + k / w, x = (int)(xy & 0xFFFFu) + k % w;
+            const uint32_t g = s_g[lo];
+            tkeys[e] = ((g / (uint32_t)N) << tile_bits) | (uint32_t)(y * tile_w + x);
+            vals[e] = g;
         }
     }
 }
@@ -479,13 +552,19 @@ HGS_API int hgs_isect_count(const float* means2d, const int32_t* radii, long lon
 }
 
 HGS_API size_t hgs_scan_temp_bytes(long long n) {
-    return align_up((size_t)(hgs_ceil_div(n > 0 ? n : 1, LS_TILE)) * sizeof(long long));
+    return align_up((size_t)(hgs_ceil_div(n > 0 ? n : 1, LS_TILE)) * sizeof(long long)) + 256;
 }
 
 HGS_API int hgs_exclusive_scan_i32(const int32_t* in, int32_t* out, long long* total_dev, long long n, void* temp,
                                    size_t temp_bytes, void* stream) {
     if (n < 0) return HGS_ERR_INVALID_ARG;
-    return large_scan(in, out, total_dev, n, temp, temp_bytes, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (temp_bytes < hgs_scan_temp_bytes(n)) return HGS_ERR_WORKSPACE;
+    // the element count lives in the last 256 bytes of temp
+    long long* n_dev = (long long*)((char*)temp + hgs_scan_temp_bytes(n) - 256);
+    set_ll_kernel<<<1, 1, 0, st>>>(n_dev, n);
+    HGS_LAUNCH_CHECK();
+    return large_scan(in, out, total_dev, n_dev, n, temp, temp_bytes - 256, st);
 }
 
 HGS_API int hgs_isect_emit(const float* means2d, const int32_t* radii, const float* depths, const int32_t* cum, int C,
@@ -501,22 +580,25 @@ HGS_API int hgs_isect_emit(const float* means2d, const int32_t* radii, const flo
     return 0;
 }
 
-// temp layout for prepare: keysA, valsA, keysB, valsB (CN u32 each), cnt_sorted (CN i32), hist, scan temp
+// temp layout for prepare: keysA, valsA, keysB, valsB (CN u32 each), cnt_sorted (CN i32), hist,
+// block counts/bases (ceil(CN/CP_TILE) long longs), scan temp
 HGS_API size_t hgs_isect_prepare_temp_bytes(long long CN) {
-    size_t a = align_up((size_t)(CN > 0 ? CN : 1) * 4);
-    return 5 * a + align_up(HIST_BYTES) + hgs_scan_temp_bytes(CN);
+    const size_t a = align_up((size_t)(CN > 0 ? CN : 1) * 4);
+    const size_t nb = (size_t)hgs_ceil_div(CN > 0 ? CN : 1, CP_TILE);
+    return 5 * a + align_up(HIST_BYTES) + align_up(nb * sizeof(long long)) + hgs_scan_temp_bytes(CN);
 }
 
 HGS_API int hgs_isect_prepare(const float* depths, const int32_t* tiles_per_gauss, int C, int N, int32_t* order,
-                              int32_t* cum_sorted, long long* total_dev, void* temp, size_t temp_bytes,
+                              int32_t* cum_sorted, long long* counts_dev, void* temp, size_t temp_bytes,
                               void* stream) {
     if (C <= 0 || N < 0) return HGS_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const long long CN = (long long)C * N;
     if (CN >= (1ll << 31)) return HGS_ERR_TOO_LARGE;
-    if (CN == 0) return (int)cudaMemsetAsync(total_dev, 0, sizeof(long long), st);
+    if (CN == 0) return (int)cudaMemsetAsync(counts_dev, 0, 2 * sizeof(long long), st);
     if (temp_bytes < hgs_isect_prepare_temp_bytes(CN)) return HGS_ERR_WORKSPACE;
     const size_t a = align_up((size_t)CN * 4);
+    const int nblk = hgs_ceil_div(CN, CP_TILE);
     char* p = (char*)temp;
     uint32_t* kA = (uint32_t*)p; p += a;
     uint32_t* vA = (uint32_t*)p; p += a;
@@ -524,15 +606,22 @@ HGS_API int hgs_isect_prepare(const float* depths, const int32_t* tiles_per_gaus
     uint32_t* vB = (uint32_t*)p; p += a;
     int32_t* cnt_sorted = (int32_t*)p; p += a;
     uint32_t* hist = (uint32_t*)p; p += align_up(HIST_BYTES);
+    long long* blk = (long long*)p; p += align_up((size_t)nblk * sizeof(long long));
     void* scan_temp = p;
+    long long* n_vis_dev = counts_dev;      // counts_dev[0] = visible Gaussians, counts_dev[1] = intersections
 
-    const int blocks = hgs_ceil_div(CN, 256);
-    depth_keys_kernel<<<blocks, 256, 0, st>>>(depths, tiles_per_gauss, CN, kA, vA);
+    // 1. order-preserving compaction of the Gaussians with at least one tile
+    vis_count_kernel<<<nblk, RS_THREADS, 0, st>>>(tiles_per_gauss, CN, blk);
     HGS_LAUNCH_CHECK();
+    ls_scan_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(blk, nblk, n_vis_dev);
+    HGS_LAUNCH_CHECK();
+    compact_kernel<<<nblk, RS_THREADS, 0, st>>>(depths, tiles_per_gauss, CN, blk, kA, vA);
+    HGS_LAUNCH_CHECK();
+    // 2. stable LSD sort of the depth bits (then of the camera index when C > 1)
     uint32_t *ki = kA, *vi = vA, *ko = kB, *vo = vB;
     for (int pass = 0; pass < 4; ++pass) {
         DigitSpec ds{pass * 8, 0xFFu, 0};
-        int rc = radix_pass(ki, vi, ko, vo, CN, ds, hist, st);
+        int rc = radix_pass(ki, vi, ko, vo, n_vis_dev, CN, ds, hist, st);
         if (rc) return rc;
         uint32_t* t;
         t = ki; ki = ko; ko = t;
@@ -543,37 +632,42 @@ HGS_API int hgs_isect_prepare(const float* depths, const int32_t* tiles_per_gaus
         for (int shift = 0; shift < cam_bits; shift += 8) {
             int nb = cam_bits - shift < 8 ? cam_bits - shift : 8;
             DigitSpec ds{shift, (1u << nb) - 1u, N};
-            int rc = radix_pass(ki, vi, ko, vo, CN, ds, hist, st);
+            int rc = radix_pass(ki, vi, ko, vo, n_vis_dev, CN, ds, hist, st);
             if (rc) return rc;
             uint32_t* t;
             t = ki; ki = ko; ko = t;
             t = vi; vi = vo; vo = t;
         }
     }
-    gather_counts_kernel<<<blocks, 256, 0, st>>>(vi, tiles_per_gauss, CN, order, cnt_sorted);
+    // 3. per-Gaussian tile counts in sorted order and their exclusive scan
+    gather_counts_kernel<<<hgs_ceil_div(CN, 256), 256, 0, st>>>(vi, tiles_per_gauss, n_vis_dev, order, cnt_sorted);
     HGS_LAUNCH_CHECK();
-    return large_scan(cnt_sorted, cum_sorted, total_dev, CN, scan_temp, hgs_scan_temp_bytes(CN), st);
+    return large_scan(cnt_sorted, cum_sorted, counts_dev + 1, n_vis_dev, CN, scan_temp, hgs_scan_temp_bytes(CN) - 256,
+                      st);
 }
 
-// temp layout for sorted: tkeyA, tkeyB, valsT (I u32 each), hist
+// temp layout for sorted: tkeyA, tkeyB, valsT (I u32 each), hist, element count
 HGS_API size_t hgs_isect_sorted_temp_bytes(long long CN, long long n_isects) {
     (void)CN;
     size_t a = align_up((size_t)(n_isects > 0 ? n_isects : 1) * 4);
-    return 3 * a + align_up(HIST_BYTES);
+    return 3 * a + align_up(HIST_BYTES) + 256;
 }
 
 HGS_API int hgs_isect_sorted(const float* means2d, const int32_t* radii, const float* depths, const int32_t* order,
-                             const int32_t* cum_sorted, int C, int N, long long n_isects, int tile_size, int tile_w,
-                             int tile_h, long long* isect_ids, int32_t* flatten_ids, int32_t* isect_offsets,
-                             void* temp, size_t temp_bytes, void* stream) {
-    if (C <= 0 || N < 0 || n_isects < 0 || tile_size <= 0 || tile_w <= 0 || tile_h <= 0) return HGS_ERR_INVALID_ARG;
+                             const int32_t* cum_sorted, int C, int N, long long n_visible, long long n_isects,
+                             int tile_size, int tile_w, int tile_h, long long* isect_ids, int32_t* flatten_ids,
+                             int32_t* isect_offsets, void* temp, size_t temp_bytes, void* stream) {
+    if (C <= 0 || N < 0 || n_isects < 0 || n_visible < 0 || tile_size <= 0 || tile_w <= 0 || tile_h <= 0)
+        return HGS_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const long long CN = (long long)C * N;
     const int n_tiles = tile_w * tile_h;
     const long long total_tiles_ll = (long long)C * n_tiles;
-    if (n_isects >= (1ll << 31) || total_tiles_ll >= (1ll << 31)) return HGS_ERR_TOO_LARGE;
+    if (n_isects >= (1ll << 31) || total_tiles_ll >= (1ll << 31) || tile_w >= 65536 || tile_h >= 65536)
+        return HGS_ERR_TOO_LARGE;
     const int total_tiles = (int)total_tiles_ll;
     if (n_isects == 0) return (int)cudaMemsetAsync(isect_offsets, 0, (size_t)total_tiles * sizeof(int32_t), st);
+    if (n_visible == 0) return HGS_ERR_INVALID_ARG;
     const int tile_bits = n_bits_of(n_tiles);
     const int cam_bits = n_bits_of(C);
     if (tile_bits + cam_bits > 32) return HGS_ERR_TOO_LARGE;
@@ -583,7 +677,10 @@ HGS_API int hgs_isect_sorted(const float* means2d, const int32_t* radii, const f
     uint32_t* kA = (uint32_t*)p; p += a;
     uint32_t* kB = (uint32_t*)p; p += a;
     uint32_t* vT = (uint32_t*)p; p += a;
-    uint32_t* hist = (uint32_t*)p;
+    uint32_t* hist = (uint32_t*)p; p += align_up(HIST_BYTES);
+    long long* n_dev = (long long*)p;
+    set_ll_kernel<<<1, 1, 0, st>>>(n_dev, n_isects);
+    HGS_LAUNCH_CHECK();
 
     // when C == 1 the camera bit is always 0: sort tile bits only
     const int key_bits = (C > 1) ? tile_bits + cam_bits : tile_bits;
@@ -594,14 +691,14 @@ HGS_API int hgs_isect_sorted(const float* means2d, const int32_t* radii, const f
     uint32_t* vi = (n_pass % 2 == 0) ? vF : vT;
     uint32_t* vo = (n_pass % 2 == 0) ? vT : vF;
 
-    emit_sorted_kernel<<<hgs_ceil_div(CN, 256), 256, 0, st>>>(means2d, radii, order, cum_sorted, CN, N, tile_size,
-                                                              tile_w, tile_h, tile_bits, ki, vi);
+    emit_sorted_kernel<<<hgs_ceil_div(n_isects, RS_TILE), RS_THREADS, 0, st>>>(
+        means2d, radii, order, cum_sorted, n_visible, n_isects, N, tile_size, tile_w, tile_h, tile_bits, ki, vi);
     HGS_LAUNCH_CHECK();
     for (int pass = 0; pass < n_pass; ++pass) {
         int shift = pass * 8;
         int nb = key_bits - shift < 8 ? key_bits - shift : 8;
         DigitSpec ds{shift, (1u << nb) - 1u, 0};
-        int rc = radix_pass(ki, vi, ko, vo, n_isects, ds, hist, st);
+        int rc = radix_pass(ki, vi, ko, vo, n_dev, n_isects, ds, hist, st);
         if (rc) return rc;
         uint32_t* t;
         t = ki; ki = ko; ko = t;

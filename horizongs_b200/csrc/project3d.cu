@@ -165,43 +165,33 @@ __global__ void __launch_bounds__(PB) project3d_fwd_kernel(
 }
 
 // One thread per Gaussian, loop over cameras: gradients w.r.t. means/quats/scales are summed
-// over the C views without atomics (deterministic).
+// over the C views without atomics (deterministic).  Gaussians culled in every view only write zeros:
+// their parameters and upstream gradients are never read.
 __global__ void __launch_bounds__(PB) project3d_bwd_kernel(
     const float* __restrict__ means, const float* __restrict__ quats, const float* __restrict__ scales,
     const float* __restrict__ viewmats, const float* __restrict__ Ks, int C, int N, int W, int H, float eps2d,
     float near_plane, float far_plane, const int32_t* __restrict__ radii, const float* __restrict__ v_means2d,
     int ld_m2, const float* __restrict__ v_depths, int ld_d, const float* __restrict__ v_conics, int ld_c,
     float* __restrict__ v_means, float* __restrict__ v_quats, float* __restrict__ v_scales) {
-    __shared__ float s_a[PB * 3];
-    __shared__ float s_b[PB * 3];
-    __shared__ float s_c[PB * 3];
-    const long long base = (long long)blockIdx.x * PB;
-    const long long n = base + threadIdx.x;
-    block_load_rows3<PB>(means, base, N, s_a);
-    block_load_rows3<PB>(scales, base, N, s_b);
-    __syncthreads();
-    const float px = s_a[threadIdx.x * 3 + 0], py = s_a[threadIdx.x * 3 + 1], pz = s_a[threadIdx.x * 3 + 2];
-    const float s0 = s_b[threadIdx.x * 3 + 0], s1 = s_b[threadIdx.x * 3 + 1], s2 = s_b[threadIdx.x * 3 + 2];
+    const long long n = (long long)blockIdx.x * PB + threadIdx.x;
+    if (n >= N) return;
+    bool any = false;
+    for (int c = 0; c < C; ++c) any |= radii[(long long)c * N + n] > 0;
+    float px = 0.f, py = 0.f, pz = 0.f, s0 = 1.f, s1 = 1.f, s2 = 1.f;
     float4 qv = make_float4(1.f, 0.f, 0.f, 0.f);
-    if (n < N) qv = reinterpret_cast<const float4*>(quats)[n];
+    if (any) {
+        px = means[n * 3]; py = means[n * 3 + 1]; pz = means[n * 3 + 2];
+        s0 = scales[n * 3]; s1 = scales[n * 3 + 1]; s2 = scales[n * 3 + 2];
+        qv = reinterpret_cast<const float4*>(quats)[n];
+    }
 
     float g_mean[3] = {0.f, 0.f, 0.f};
     float g_scale[3] = {0.f, 0.f, 0.f};
     float g_quat[4] = {0.f, 0.f, 0.f, 0.f};
 
-    for (int c = 0; c < C; ++c) {
-        // coalesced staging of this camera's v_conics rows (dense layout); strided rows are read directly
-        __syncthreads();
-        if (ld_c == 3) block_load_rows3<PB>(v_conics + (long long)c * N * 3, base, N, s_c);
-        __syncthreads();
-        if (n >= N) continue;
+    for (int c = 0; c < C && any; ++c) {
         const long long idx = (long long)c * N + n;
         if (radii[idx] <= 0) continue;
-        if (ld_c != 3) {
-            s_c[threadIdx.x * 3 + 0] = v_conics[idx * ld_c + 0];
-            s_c[threadIdx.x * 3 + 1] = v_conics[idx * ld_c + 1];
-            s_c[threadIdx.x * 3 + 2] = v_conics[idx * ld_c + 2];
-        }
         const HgsCam cam = hgs_load_cam(viewmats, Ks, c);
         Proj3dFwd f;
         if (!proj3d_math(cam, px, py, pz, qv.x, qv.y, qv.z, qv.w, s0, s1, s2, (float)W, (float)H, eps2d, near_plane,
@@ -209,7 +199,7 @@ __global__ void __launch_bounds__(PB) project3d_bwd_kernel(
             continue;
         const float2 vm = make_float2(v_means2d[idx * ld_m2], v_means2d[idx * ld_m2 + 1]);
         const float vd = v_depths != nullptr ? v_depths[idx * ld_d] : 0.f;
-        const float va = s_c[threadIdx.x * 3 + 0], vb = 0.5f * s_c[threadIdx.x * 3 + 1], vc = s_c[threadIdx.x * 3 + 2];
+        const float va = v_conics[idx * ld_c], vb = 0.5f * v_conics[idx * ld_c + 1], vc = v_conics[idx * ld_c + 2];
 
         // conic X = inv(Sigma2'), v_Sigma2 = -X V X
         const float inv_det = 1.0f / f.det;
@@ -292,16 +282,12 @@ __global__ void __launch_bounds__(PB) project3d_bwd_kernel(
         for (int k = 0; k < 4; ++k) g_quat[k] += vq[k];
     }
 
-    if (n < N) reinterpret_cast<float4*>(v_quats)[n] = make_float4(g_quat[0], g_quat[1], g_quat[2], g_quat[3]);
-    __syncthreads();
+    reinterpret_cast<float4*>(v_quats)[n] = make_float4(g_quat[0], g_quat[1], g_quat[2], g_quat[3]);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        s_a[threadIdx.x * 3 + k] = g_mean[k];
-        s_b[threadIdx.x * 3 + k] = g_scale[k];
+        v_means[n * 3 + k] = g_mean[k];
+        v_scales[n * 3 + k] = g_scale[k];
     }
-    __syncthreads();
-    block_store_rows3<PB>(v_means, base, N, s_a);
-    block_store_rows3<PB>(v_scales, base, N, s_b);
 }
 
 }  // namespace

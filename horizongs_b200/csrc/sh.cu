@@ -7,8 +7,9 @@
 // Fused here: direction = means - campos, normalisation, optional `clamp_min(c + 0.5, 0)`.
 //
 // One thread per Gaussian, cameras looped in-thread (coefficient gradients are summed over views
-// without atomics).  Coefficient rows are staged through shared memory so global traffic is coalesced.
-// Roofline: HBM; fwd (12 K + 12 + 12) B per Gaussian, bwd (24 K + 36) B.
+// without atomics); only Gaussians that survive culling touch their coefficient rows.
+// Roofline: HBM; fwd 12 B per Gaussian + (12 K + 12) B per visible one; bwd 12 K B (zero fill) per Gaussian
+// + (24 K + 36) B per visible one.
 #include "hgs_common.cuh"
 #include "hgs_constants.cuh"
 #include "../../include/hgs_raster.h"
@@ -112,69 +113,48 @@ __device__ __forceinline__ void sh_basis(float x, float y, float z, float* b, fl
     }
 }
 
-__device__ __forceinline__ int row_stride(int K) { return (K * 3) | 1; }  // odd -> conflict-free rows
-
-// coalesced copy of rows [base, base+SB) of a [N, K*3] array into padded shared rows (first `used` floats)
-__device__ __forceinline__ void stage_rows_in(const float* __restrict__ src, long long base, long long N, int K,
-                                              int used, float* s) {
-    const int rs = row_stride(K);
-    const int rowlen = K * 3;
-    long long rows = N - base;
-    if (rows > SB) rows = SB;
-    if (used == rowlen) {
-        const long long tot = rows * rowlen;
-        const float* p = src + base * rowlen;
-        for (long long i = threadIdx.x; i < tot; i += SB) {
-            int r = (int)(i / rowlen), c = (int)(i % rowlen);
-            s[r * rs + c] = p[i];
-        }
+// Direction of Gaussian n seen from camera c (un-normalised)
+__device__ __forceinline__ void load_dir(const float* __restrict__ dirs, const float* __restrict__ means,
+                                         const float* __restrict__ campos, long long idx, long long n, int c, float& x,
+                                         float& y, float& z) {
+    if (dirs != nullptr) {
+        x = dirs[idx * 3]; y = dirs[idx * 3 + 1]; z = dirs[idx * 3 + 2];
     } else {
-        for (long long i = threadIdx.x; i < rows * used; i += SB) {
-            int r = (int)(i / used), c = (int)(i % used);
-            s[r * rs + c] = src[(base + r) * rowlen + c];
-        }
+        x = means[n * 3] - campos[c * 3];
+        y = means[n * 3 + 1] - campos[c * 3 + 1];
+        z = means[n * 3 + 2] - campos[c * 3 + 2];
     }
 }
 
+// One thread per Gaussian.  Only Gaussians that survive culling (radii > 0) touch their coefficient row
+// (12 K bytes): in large scenes most rows are never read.  Rows are read/written by their owning thread;
+// every byte of a touched row is used, so sector efficiency stays high without shared-memory staging.
 template <int DEG>
 __global__ void __launch_bounds__(SB) sh_fwd_kernel(const float* __restrict__ dirs, const float* __restrict__ means,
                                                     const float* __restrict__ campos,
                                                     const float* __restrict__ coeffs,
                                                     const int32_t* __restrict__ radii, int C, int N, int K, int post,
                                                     float* __restrict__ colors) {
-    extern __shared__ float smem[];
     constexpr int NB = (DEG + 1) * (DEG + 1);
-    float* s_co = smem;                          // SB rows of coefficients
-    float* s_io = smem + SB * row_stride(K);     // SB*3 staging for means / dirs / colours
-    const long long base = (long long)blockIdx.x * SB;
-    const long long n = base + threadIdx.x;
-    stage_rows_in(coeffs, base, N, K, NB * 3, s_co);
-    if (dirs == nullptr) block_load_rows3<SB>(means, base, N, s_io);
-    __syncthreads();
-    float mx = 0.f, my = 0.f, mz = 0.f;
-    if (dirs == nullptr) { mx = s_io[threadIdx.x * 3]; my = s_io[threadIdx.x * 3 + 1]; mz = s_io[threadIdx.x * 3 + 2]; }
-    const float* co = s_co + threadIdx.x * row_stride(K);
+    const long long n = (long long)blockIdx.x * SB + threadIdx.x;
+    if (n >= N) return;
+    const float* co = coeffs + n * (long long)(K * 3);
     for (int c = 0; c < C; ++c) {
-        __syncthreads();
-        if (dirs != nullptr) {
-            block_load_rows3<SB>(dirs + (long long)c * N * 3, base, N, s_io);
-            __syncthreads();
-        }
+        const long long idx = (long long)c * N + n;
         float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-        if (n < N && (radii == nullptr || radii[(long long)c * N + n] > 0)) {
+        if (radii == nullptr || radii[idx] > 0) {
             float x, y, z;
-            if (dirs != nullptr) { x = s_io[threadIdx.x * 3]; y = s_io[threadIdx.x * 3 + 1]; z = s_io[threadIdx.x * 3 + 2]; }
-            else { x = mx - campos[c * 3]; y = my - campos[c * 3 + 1]; z = mz - campos[c * 3 + 2]; }
+            load_dir(dirs, means, campos, idx, n, c, x, y, z);
             const float inorm = 1.0f / sqrtf(x * x + y * y + z * z);
             x *= inorm; y *= inorm; z *= inorm;
             float b[NB];
             sh_basis<DEG, false>(x, y, z, b, nullptr, nullptr, nullptr);
-            r0 = b[0] * co[0]; r1 = b[0] * co[1]; r2 = b[0] * co[2];
+            r0 = b[0] * __ldg(co + 0); r1 = b[0] * __ldg(co + 1); r2 = b[0] * __ldg(co + 2);
 #pragma unroll
             for (int k = 1; k < NB; ++k) {
-                r0 = r0 + b[k] * co[k * 3 + 0];
-                r1 = r1 + b[k] * co[k * 3 + 1];
-                r2 = r2 + b[k] * co[k * 3 + 2];
+                r0 = r0 + b[k] * __ldg(co + k * 3 + 0);
+                r1 = r1 + b[k] * __ldg(co + k * 3 + 1);
+                r2 = r2 + b[k] * __ldg(co + k * 3 + 2);
             }
             if (post) {
                 r0 = fmaxf(r0 + HGS_SH_OFFSET, 0.f);
@@ -182,13 +162,11 @@ __global__ void __launch_bounds__(SB) sh_fwd_kernel(const float* __restrict__ di
                 r2 = fmaxf(r2 + HGS_SH_OFFSET, 0.f);
             }
         }
-        __syncthreads();
-        s_io[threadIdx.x * 3] = r0; s_io[threadIdx.x * 3 + 1] = r1; s_io[threadIdx.x * 3 + 2] = r2;
-        __syncthreads();
-        block_store_rows3<SB>(colors + (long long)c * N * 3, base, N, s_io);
+        colors[idx * 3] = r0; colors[idx * 3 + 1] = r1; colors[idx * 3 + 2] = r2;
     }
 }
 
+// v_coeffs must be zero-filled by the launcher (rows of culled Gaussians are never touched here).
 template <int DEG>
 __global__ void __launch_bounds__(SB) sh_bwd_kernel(const float* __restrict__ dirs, const float* __restrict__ means,
                                                     const float* __restrict__ campos,
@@ -198,56 +176,29 @@ __global__ void __launch_bounds__(SB) sh_bwd_kernel(const float* __restrict__ di
                                                     const float* __restrict__ v_colors, int ld_vc, int C, int N,
                                                     int K, int post, float* __restrict__ v_coeffs,
                                                     float* __restrict__ v_dirs, float* __restrict__ v_means) {
-    extern __shared__ float smem[];
     constexpr int NB = (DEG + 1) * (DEG + 1);
-    const int rs = row_stride(K);
-    float* s_co = smem;                 // coefficients in, coefficient gradients out
-    float* s_io = smem + SB * rs;       // SB*3 staging
-    float* s_io2 = s_io + SB * 3;       // SB*3 staging (forward colours for the clamp mask)
-    const long long base = (long long)blockIdx.x * SB;
-    const long long n = base + threadIdx.x;
+    const long long n = (long long)blockIdx.x * SB + threadIdx.x;
+    if (n >= N) return;
     const bool want_dir = (v_dirs != nullptr) || (v_means != nullptr);
-    stage_rows_in(coeffs, base, N, K, NB * 3, s_co);
-    if (dirs == nullptr) block_load_rows3<SB>(means, base, N, s_io);
-    __syncthreads();
-    float mx = 0.f, my = 0.f, mz = 0.f;
-    if (dirs == nullptr) { mx = s_io[threadIdx.x * 3]; my = s_io[threadIdx.x * 3 + 1]; mz = s_io[threadIdx.x * 3 + 2]; }
-    float* co = s_co + threadIdx.x * rs;
-    float coef[NB * 3];
-#pragma unroll
-    for (int k = 0; k < NB * 3; ++k) coef[k] = co[k];
+    const float* co = coeffs + n * (long long)(K * 3);
     float g_co[NB * 3];
 #pragma unroll
     for (int k = 0; k < NB * 3; ++k) g_co[k] = 0.f;
     float gm0 = 0.f, gm1 = 0.f, gm2 = 0.f;
-
+    bool any = false;
     for (int c = 0; c < C; ++c) {
-        __syncthreads();
-        if (ld_vc == 3) {
-            block_load_rows3<SB>(v_colors + (long long)c * N * 3, base, N, s_io);
-        } else if (n < N) {
-            const float* vr = v_colors + ((long long)c * N + n) * ld_vc;
-            s_io[threadIdx.x * 3] = vr[0]; s_io[threadIdx.x * 3 + 1] = vr[1]; s_io[threadIdx.x * 3 + 2] = vr[2];
-        }
-        if (post) block_load_rows3<SB>(colors + (long long)c * N * 3, base, N, s_io2);
-        __syncthreads();
-        float v0 = s_io[threadIdx.x * 3], v1 = s_io[threadIdx.x * 3 + 1], v2 = s_io[threadIdx.x * 3 + 2];
-        if (post) {
-            if (!(s_io2[threadIdx.x * 3] > 0.f)) v0 = 0.f;
-            if (!(s_io2[threadIdx.x * 3 + 1] > 0.f)) v1 = 0.f;
-            if (!(s_io2[threadIdx.x * 3 + 2] > 0.f)) v2 = 0.f;
-        }
-        float x = 0.f, y = 0.f, z = 1.f;
-        if (dirs != nullptr) {
-            __syncthreads();
-            block_load_rows3<SB>(dirs + (long long)c * N * 3, base, N, s_io);
-            __syncthreads();
-            x = s_io[threadIdx.x * 3]; y = s_io[threadIdx.x * 3 + 1]; z = s_io[threadIdx.x * 3 + 2];
-        } else if (n < N) {
-            x = mx - campos[c * 3]; y = my - campos[c * 3 + 1]; z = mz - campos[c * 3 + 2];
-        }
+        const long long idx = (long long)c * N + n;
         float gd0 = 0.f, gd1 = 0.f, gd2 = 0.f;
-        if (n < N && (radii == nullptr || radii[(long long)c * N + n] > 0)) {
+        if (radii == nullptr || radii[idx] > 0) {
+            any = true;
+            float v0 = v_colors[idx * ld_vc], v1 = v_colors[idx * ld_vc + 1], v2 = v_colors[idx * ld_vc + 2];
+            if (post) {
+                if (!(colors[idx * 3] > 0.f)) v0 = 0.f;
+                if (!(colors[idx * 3 + 1] > 0.f)) v1 = 0.f;
+                if (!(colors[idx * 3 + 2] > 0.f)) v2 = 0.f;
+            }
+            float x, y, z;
+            load_dir(dirs, means, campos, idx, n, c, x, y, z);
             const float inorm = 1.0f / sqrtf(x * x + y * y + z * z);
             x *= inorm; y *= inorm; z *= inorm;
             float b[NB], bx[NB], by[NB], bz[NB];
@@ -258,8 +209,10 @@ __global__ void __launch_bounds__(SB) sh_bwd_kernel(const float* __restrict__ di
                 g_co[k * 3 + 0] += b[k] * v0;
                 g_co[k * 3 + 1] += b[k] * v1;
                 g_co[k * 3 + 2] += b[k] * v2;
-                const float d = coef[k * 3] * v0 + coef[k * 3 + 1] * v1 + coef[k * 3 + 2] * v2;
-                vx += bx[k] * d; vy += by[k] * d; vz += bz[k] * d;
+                if (want_dir) {
+                    const float d = __ldg(co + k * 3) * v0 + __ldg(co + k * 3 + 1) * v1 + __ldg(co + k * 3 + 2) * v2;
+                    vx += bx[k] * d; vy += by[k] * d; vz += bz[k] * d;
+                }
             }
             if (want_dir) {
                 const float dd = vx * x + vy * y + vz * z;
@@ -269,39 +222,15 @@ __global__ void __launch_bounds__(SB) sh_bwd_kernel(const float* __restrict__ di
                 gm0 += gd0; gm1 += gd1; gm2 += gd2;
             }
         }
-        if (v_dirs != nullptr) {
-            __syncthreads();
-            s_io[threadIdx.x * 3] = gd0; s_io[threadIdx.x * 3 + 1] = gd1; s_io[threadIdx.x * 3 + 2] = gd2;
-            __syncthreads();
-            block_store_rows3<SB>(v_dirs + (long long)c * N * 3, base, N, s_io);
-        }
+        if (v_dirs != nullptr) { v_dirs[idx * 3] = gd0; v_dirs[idx * 3 + 1] = gd1; v_dirs[idx * 3 + 2] = gd2; }
     }
-    // coefficient gradients: padded rows -> coalesced global rows (unused degrees are zero)
-    __syncthreads();
-    {
-        const int rowlen = K * 3;
-        for (int k = NB * 3; k < rowlen; ++k) co[k] = 0.f;
+    if (any) {
+        float* out = v_coeffs + n * (long long)(K * 3);
 #pragma unroll
-        for (int k = 0; k < NB * 3; ++k) co[k] = g_co[k];
-        __syncthreads();
-        long long rows = N - base;
-        if (rows > SB) rows = SB;
-        const long long tot = rows * rowlen;
-        float* p = v_coeffs + base * rowlen;
-        for (long long i = threadIdx.x; i < tot; i += SB) {
-            int r = (int)(i / rowlen), cidx = (int)(i % rowlen);
-            p[i] = s_co[r * rs + cidx];
-        }
+        for (int k = 0; k < NB * 3; ++k) out[k] = g_co[k];
     }
-    if (v_means != nullptr) {
-        __syncthreads();
-        s_io[threadIdx.x * 3] = gm0; s_io[threadIdx.x * 3 + 1] = gm1; s_io[threadIdx.x * 3 + 2] = gm2;
-        __syncthreads();
-        block_store_rows3<SB>(v_means, base, N, s_io);
-    }
+    if (v_means != nullptr) { v_means[n * 3] = gm0; v_means[n * 3 + 1] = gm1; v_means[n * 3 + 2] = gm2; }
 }
-
-static size_t sh_smem_bytes(int K, bool bwd) { return (size_t)(SB * ((K * 3) | 1) + SB * 3 * (bwd ? 2 : 1)) * sizeof(float); }
 
 }  // namespace
 
@@ -312,13 +241,8 @@ HGS_API int hgs_sh_fwd(int degree, int K, const float* dirs, const float* means,
     if (dirs == nullptr && (means == nullptr || campos == nullptr)) return HGS_ERR_INVALID_ARG;
     if (N == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = sh_smem_bytes(K, false);
     const int grid = hgs_ceil_div(N, SB);
-#define LAUNCH(DEG)                                                                                            \
-    {                                                                                                          \
-        cudaFuncSetAttribute(sh_fwd_kernel<DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
-        sh_fwd_kernel<DEG><<<grid, SB, smem, st>>>(dirs, means, campos, coeffs, radii, C, N, K, post, colors); \
-    }
+#define LAUNCH(DEG) sh_fwd_kernel<DEG><<<grid, SB, 0, st>>>(dirs, means, campos, coeffs, radii, C, N, K, post, colors);
     switch (degree) {
         case 0: LAUNCH(0) break;
         case 1: LAUNCH(1) break;
@@ -341,14 +265,14 @@ HGS_API int hgs_sh_bwd(int degree, int K, const float* dirs, const float* means,
     if (post && colors == nullptr) return HGS_ERR_INVALID_ARG;
     if (N == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = sh_smem_bytes(K, true);
     const int grid = hgs_ceil_div(N, SB);
-#define LAUNCH(DEG)                                                                                                  \
-    {                                                                                                                \
-        cudaFuncSetAttribute(sh_bwd_kernel<DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
-        sh_bwd_kernel<DEG><<<grid, SB, smem, st>>>(dirs, means, campos, coeffs, radii, colors, v_colors,             \
-                                                   ld_v_colors, C, N, K, post, v_coeffs, v_dirs, v_means);           \
+    {
+        cudaError_t e = cudaMemsetAsync(v_coeffs, 0, (size_t)N * K * 3 * sizeof(float), st);
+        if (e != cudaSuccess) return (int)e;
     }
+#define LAUNCH(DEG)                                                                                        \
+    sh_bwd_kernel<DEG><<<grid, SB, 0, st>>>(dirs, means, campos, coeffs, radii, colors, v_colors, ld_v_colors, C, N, \
+                                            K, post, v_coeffs, v_dirs, v_means);
     switch (degree) {
         case 0: LAUNCH(0) break;
         case 1: LAUNCH(1) break;

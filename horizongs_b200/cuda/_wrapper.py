@@ -243,14 +243,14 @@ def _isect_sorted_from_counts(means2d, radii, depths, tiles_per_gauss, C, N, til
     st = _stream()
     order = torch.empty(CN, dtype=torch.int32, device=dev)
     cum_sorted = torch.empty(CN, dtype=torch.int32, device=dev)
-    total = torch.empty(1, dtype=torch.int64, device=dev)
+    counts = torch.empty(2, dtype=torch.int64, device=dev)
     _mark("isect_prepare", 0)
     tb = L.hgs_isect_prepare_temp_bytes(CN)
     temp = torch.empty(tb, dtype=torch.uint8, device=dev)
-    check(L.hgs_isect_prepare(ptr(depths), ptr(tiles_per_gauss), C, N, ptr(order), ptr(cum_sorted), ptr(total),
+    check(L.hgs_isect_prepare(ptr(depths), ptr(tiles_per_gauss), C, N, ptr(order), ptr(cum_sorted), ptr(counts),
                               ptr(temp), tb, st), "hgs_isect_prepare")
     _mark("isect_prepare", 1)
-    n_isects = int(total.item())  # the one unavoidable host read: sizes the intersection arrays
+    n_visible, n_isects = counts.tolist()  # the one unavoidable host read: sizes the intersection arrays
     _mark("isect_sorted", 0)
     if n_isects >= 2 ** 31:
         raise _lib.HgsError(f"{n_isects} tile intersections exceed the 32-bit index range")
@@ -259,8 +259,8 @@ def _isect_sorted_from_counts(means2d, radii, depths, tiles_per_gauss, C, N, til
     offsets = torch.empty((C, tile_height, tile_width), dtype=torch.int32, device=dev)
     tb2 = L.hgs_isect_sorted_temp_bytes(CN, n_isects)
     temp2 = torch.empty(tb2, dtype=torch.uint8, device=dev)
-    check(L.hgs_isect_sorted(ptr(means2d), ptr(radii), ptr(depths), ptr(order), ptr(cum_sorted), C, N, n_isects,
-                             tile_size, tile_width, tile_height, ptr(isect_ids), ptr(flatten_ids), ptr(offsets),
+    check(L.hgs_isect_sorted(ptr(means2d), ptr(radii), ptr(depths), ptr(order), ptr(cum_sorted), C, N, n_visible,
+                             n_isects, tile_size, tile_width, tile_height, ptr(isect_ids), ptr(flatten_ids), ptr(offsets),
                              ptr(temp2), tb2, st), "hgs_isect_sorted")
     _mark("isect_sorted", 1)
     return isect_ids, flatten_ids, offsets
@@ -624,3 +624,19 @@ def blend3d_pair_stats(means2d, conics, opacities, radii, width, height, tile_si
                               ptr(flatten_ids), flatten_ids.numel(), ptr(counters), st), "hgs_blend3d_stats")
     p_eval, p_blend = counters.tolist()
     return int(p_eval), int(p_blend)
+
+
+@torch.no_grad()
+def densification_stats_update(means2d_grad: Tensor, radii: Tensor, width: int, height: int, grad_accum: Tensor,
+                               denom: Tensor, max_radii: Optional[Tensor] = None, mode: str = "mean") -> None:
+    """In-place update of the densification accumulators from one rendered batch of views
+    (scene/basic_model.py:96-144): grad_accum[N] (+= or max= the scaled view-space gradient norm),
+    denom[N] (+= views that saw the Gaussian), max_radii[N] (optional)."""
+    assert mode in ("mean", "max")
+    L = _lib.lib()
+    C, N = radii.shape
+    g, ld = _rows(means2d_grad, 2)
+    assert grad_accum.is_contiguous() and denom.is_contiguous() and grad_accum.numel() == N and denom.numel() == N
+    check(L.hgs_densify_stats(ptr(g), ld, ptr(radii.contiguous()), C, N, int(width), int(height),
+                              1 if mode == "max" else 0, ptr(grad_accum), ptr(denom), ptr(max_radii), _stream()),
+          "hgs_densify_stats")

@@ -100,19 +100,20 @@ int hgs_exclusive_scan_i32(const int32_t* in, int32_t* out, long long* total_dev
 /* Unsorted emission (gsplat isect_tiles(sort=False)): cum = exclusive scan of tiles_per_gauss. */
 int hgs_isect_emit(const float* means2d, const int32_t* radii, const float* depths, const int32_t* cum, int C, int N,
                    int tile_size, int tile_w, int tile_h, long long* isect_ids, int32_t* flatten_ids, void* stream);
-/* Sorted path, phase 1 (needs no knowledge of I): depth-order the C*N Gaussians (stable LSD radix sort
- * of the depth bits, camera-major), gather tiles_per_gauss in that order and scan it.
- * out: order[CN] i32 (flat indices in (cam, depth, index) order), cum_sorted[CN] i32 (exclusive scan of the
- * per-Gaussian tile counts in that order), total_dev[0] = I. */
+/* Sorted path, phase 1 (no host round trip): compact the Gaussians with tiles_per_gauss > 0, depth-order them
+ * (stable LSD radix sort of the depth bits, camera-major), gather their tile counts in that order and scan.
+ * out: order[<= CN] i32 (flat indices of the n_vis visible Gaussians in (cam, depth, index) order),
+ * cum_sorted[<= CN] i32 (exclusive scan of their tile counts), counts_dev[0] = n_vis, counts_dev[1] = I. */
 int hgs_isect_prepare(const float* depths, const int32_t* tiles_per_gauss, int C, int N, int32_t* order,
-                      int32_t* cum_sorted, long long* total_dev, void* temp, size_t temp_bytes, void* stream);
-/* Sorted path, phase 2: emit (tile key, flat index) pairs in depth order, stable-partition them by
+                      int32_t* cum_sorted, long long* counts_dev, void* temp, size_t temp_bytes, void* stream);
+/* Sorted path, phase 2 (n_visible and n_isects read back by the caller to size the outputs): emit
+ * (tile key, flat index) pairs in depth order -- one thread per intersection -- stable-partition them by
  * (cam, tile) with LSD radix passes over the tile bits only, then write the final arrays.
  * out: isect_ids[I] i64, flatten_ids[I] i32, isect_offsets[C*tile_h*tile_w] i32. */
 int hgs_isect_sorted(const float* means2d, const int32_t* radii, const float* depths, const int32_t* order,
-                     const int32_t* cum_sorted, int C, int N, long long n_isects, int tile_size, int tile_w,
-                     int tile_h, long long* isect_ids, int32_t* flatten_ids, int32_t* isect_offsets, void* temp,
-                     size_t temp_bytes, void* stream);
+                     const int32_t* cum_sorted, int C, int N, long long n_visible, long long n_isects, int tile_size,
+                     int tile_w, int tile_h, long long* isect_ids, int32_t* flatten_ids, int32_t* isect_offsets,
+                     void* temp, size_t temp_bytes, void* stream);
 /* gsplat isect_offset_encode on already-sorted keys. */
 int hgs_isect_offset_encode(const long long* isect_ids, long long n_isects, int C, int tile_w, int tile_h,
                             int32_t* isect_offsets, void* stream);
@@ -183,6 +184,14 @@ int hgs_blend2d_bwd(const float* means2d, const float* ray_transforms, const flo
                     const float* v_render_alphas, const float* v_render_normals, const float* v_render_distort,
                     const float* v_render_median, float* v_means2d, float* v_ray_transforms, float* v_colors,
                     float* v_depths, float* v_normals, float* v_opacities, float* v_densify, void* stream);
+
+/* ---- f2 (next row of SURVEY.md section 8): densification statistics -------------------------------
+ * One pass over the view-space gradient (scene/basic_model.py:96-144, the part fed by the rasterizer): for
+ * Gaussians with radii > 0 in a view, grad_accum[n] += (mode_max ? max : sum) of ||v_means2d * (W/2, H/2)||,
+ * denom[n] += number of views that saw n, max_radii[n] = max(max_radii[n], radii) (or NULL).
+ * v_means2d[C,N,2] with row stride ld_means2d floats. */
+int hgs_densify_stats(const float* v_means2d, int ld_means2d, const int32_t* radii, int C, int N, int width,
+                      int height, int mode_max, float* grad_accum, float* denom, float* max_radii, void* stream);
 
 #ifdef __cplusplus
 }

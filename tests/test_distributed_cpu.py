@@ -1,0 +1,70 @@
+"""world_size-2 gloo tests of the view-sharded exchange step (host logic of SURVEY.md section 8e).
+The rendering itself is replaced by the CPU oracle: 2 ranks x 1 view, all-reduced, must equal single-process
+gradient accumulation over the same 2 views."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from horizongs_b200 import distributed as D
+from tests.helpers import small_scene
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _view_grads(sc, V, Ks, W, H, v):
+    from oracle import gsplat_oracle as O
+    params = [t.clone().requires_grad_() for t in (sc.means, sc.quats, sc.scales, sc.opacities, sc.colors)]
+    rc, ra, meta = O.rasterization(*params, V[v:v + 1], Ks[v:v + 1], W, H, render_mode="RGB+ED")
+    meta["means2d"].retain_grad()
+    (rc.sum() + ra.sum()).backward()
+    norm, vis = D.densification_statistics(meta["means2d"].grad, meta["radii"], W, H)
+    return params, norm, vis
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    sc, V, Ks, W, H = small_scene(n=400, C=2, width=64, height=48, scale=0.2)
+    (v,) = D.shard_views(2, rank, world, step=0)
+    params, norm, vis = _view_grads(sc, V, Ks, W, H, v)
+    D.allreduce_gradients(params)
+    D.allreduce_densification(norm, vis, mode="mean")
+    if rank == 0:
+        torch.save({"grads": [p.grad for p in params], "norm": norm, "vis": vis}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_views_partition():
+    for world in (1, 2, 4, 8):
+        for step in range(3):
+            seen = sorted(v for r in range(world) for v in D.shard_views(8, r, world, step))
+            assert seen == list(range(8))
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_allreduce_equals_single_process_accumulation(tmp_path):
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    sc, V, Ks, W, H = small_scene(n=400, C=2, width=64, height=48, scale=0.2)
+    ref_grads, ref_norm, ref_vis = None, 0, 0
+    for v in range(2):
+        params, norm, vis = _view_grads(sc, V, Ks, W, H, v)
+        ref_grads = [p.grad for p in params] if ref_grads is None else [a + p.grad for a, p in zip(ref_grads, params)]
+        ref_norm, ref_vis = ref_norm + norm, ref_vis + vis
+    for a, b in zip(got["grads"], ref_grads):
+        assert float((a - b).abs().max()) <= 1e-3 * float(b.abs().max()) + 1e-12
+    assert torch.allclose(got["norm"], ref_norm, rtol=1e-4, atol=1e-7)
+    assert torch.equal(got["vis"], ref_vis)

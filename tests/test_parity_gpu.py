@@ -297,3 +297,27 @@ def test_full_size_properties_1m_1080p():
         # idempotence
         rc3, ra3, _ = hgs.rasterization(*a, V.cuda(), Ks.cuda(), Wd, H, render_mode="RGB+ED")
         assert torch.equal(rc3, rc) and torch.equal(ra3, ra)
+
+
+# ------------------------------------------------------------------------------------ f2 densification statistics
+@pytest.mark.parametrize("mode", ["mean", "max"])
+def test_densification_stats_fused(mode):
+    from horizongs_b200 import distributed as D
+    g = torch.Generator().manual_seed(3)
+    C, N, Wd, H = 2, 5000, 640, 360
+    grad = torch.randn(C, N, 12, generator=g)[..., 0:2]            # a strided slice, like the packed buffer
+    radii = torch.randint(0, 5, (C, N), generator=g, dtype=torch.int32)
+    acc0, den0 = torch.rand(N, generator=g), torch.rand(N, generator=g).round()
+    # reference: per-view norms (scene/basic_model.py:131-144)
+    acc, den = acc0.clone(), den0.clone()
+    nrm = torch.sqrt((grad[..., 0] * 0.5 * Wd) ** 2 + (grad[..., 1] * 0.5 * H) ** 2)
+    vis = radii > 0
+    if mode == "mean":
+        acc += (nrm * vis).sum(0)
+    else:
+        acc = torch.where(vis.any(0), torch.maximum(acc, (nrm * vis).max(0).values), acc)
+    den += vis.sum(0)
+    cacc, cden, cmax = acc0.cuda(), den0.cuda(), torch.zeros(N).cuda()
+    W.densification_stats_update(grad.cuda(), radii.cuda(), Wd, H, cacc, cden, cmax, mode=mode)
+    assert torch.allclose(cacc.cpu(), acc, rtol=1e-5, atol=1e-5) and torch.equal(cden.cpu(), den)
+    assert torch.equal(cmax.cpu(), radii.max(0).values.float())
