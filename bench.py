@@ -238,14 +238,16 @@ def run_ours(args):
         # computed per view BEFORE the exchange, then summed over ranks together with the gradients
         if world > 1:
             step_stats.zero_()
-            Wr.densification_stats_update(meta["means2d"].grad, meta["radii"], W, H, step_stats[0], step_stats[1])
+            Wr.densification_stats_update(meta["means2d"].grad, meta["radii"], W, H, step_stats[0], step_stats[1],
+                                          visible_ids=meta["visible_ids"])
             hs = D.allreduce_gradients(params, async_op=True)
             hs.append(dist.all_reduce(step_stats, async_op=True))
             for h in hs:
                 h.wait()
             stats.add_(step_stats)
         else:
-            Wr.densification_stats_update(meta["means2d"].grad, meta["radii"], W, H, stats[0], stats[1])
+            Wr.densification_stats_update(meta["means2d"].grad, meta["radii"], W, H, stats[0], stats[1],
+                                          visible_ids=meta["visible_ids"])
         out = loss.item() if e2e else None
         for p in params:
             p.grad = None

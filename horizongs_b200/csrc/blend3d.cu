@@ -37,7 +37,8 @@ constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 constexpr int REC_BYTES = 64;    // global record
 constexpr int SLOT_BYTES = 80;   // shared-memory slot (stride 80 B: lane-parallel float4 reads are conflict-free)
-constexpr int FB = 128;          // batch size of the fast kernels
+constexpr int FB = 128;          // forward batch size (Gaussians staged per mbarrier phase)
+constexpr int FB_BWD = 96;       // backward batch size: 4 CTAs/SM fit in shared memory (50 KB each)
 constexpr float CULL_MARGIN = 0.02f;  // in log2 units; conservative (float error of the bound is ~1e-5)
 
 struct __align__(16) GRec {
@@ -50,11 +51,13 @@ static_assert(sizeof(GRec) == REC_BYTES, "record size");
 
 __global__ void pack3d_kernel(const float* __restrict__ means2d, const float* __restrict__ conics,
                               const float* __restrict__ colors, const float* __restrict__ depths,
-                              const float* __restrict__ opacities, const int32_t* __restrict__ radii, long long CN,
-                              int CH, GRec* __restrict__ recs) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= CN) return;
-    if (radii != nullptr && radii[i] <= 0) return;
+                              const float* __restrict__ opacities, const int32_t* __restrict__ radii,
+                              const int32_t* __restrict__ vis_ids, long long CN, int CH, GRec* __restrict__ recs) {
+    // CN = number of work items: all C*N Gaussians (vis_ids == NULL) or the visible ones listed in vis_ids
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= CN) return;
+    const long long i = vis_ids != nullptr ? (long long)vis_ids[t] : t;
+    if (vis_ids == nullptr && radii != nullptr && radii[i] <= 0) return;
     const float2 m = reinterpret_cast<const float2*>(means2d)[i];
     const float a = conics[i * 3 + 0], b = conics[i * 3 + 1], c = conics[i * 3 + 2];
     const float o = opacities[i];
@@ -307,18 +310,18 @@ __global__ void __launch_bounds__(BLK) blend3d_stats_kernel(const GRec* __restri
 constexpr int ACC_STRIDE = 11;  // odd: conflict-free slot writes (10 lanes) and strided flush reads
 constexpr int VP = 12;          // floats per row of the packed gradient buffer
 
-template <int D>
+template <int D, int FBB>
 struct BwdSmem {
-    unsigned char rec[2][FB * SLOT_BYTES];
-    float acc[BLK / 32][FB * ACC_STRIDE];
-    int ids[2][FB];
-    unsigned wmask[BLK / 32][FB / 32];
+    unsigned char rec[2][FBB * SLOT_BYTES];
+    float acc[BLK / 32][FBB * ACC_STRIDE];
+    int ids[2][FBB];
+    unsigned wmask[BLK / 32][FBB / 32];
     int red[BLK / 32];
     uint64_t bar[2];
 };
 
-template <int D, bool NORM_DEPTH>
-__global__ void __launch_bounds__(BLK) blend3d_bwd_fast_kernel(
+template <int D, bool NORM_DEPTH, int FBB>
+__global__ void __launch_bounds__(BLK, 4) blend3d_bwd_fast_kernel(
     const GRec* __restrict__ recs, const float* __restrict__ backgrounds, int C, int W, int H, int tile_w, int tile_h,
     const int32_t* __restrict__ offsets, const int32_t* __restrict__ flatten_ids, int n_isects,
     const float* __restrict__ render_colors, const float* __restrict__ render_alphas,
@@ -327,7 +330,7 @@ __global__ void __launch_bounds__(BLK) blend3d_bwd_fast_kernel(
     constexpr int NV = 6 + D;
     static_assert(NV <= ACC_STRIDE, "accumulator row too small");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    BwdSmem<D>& S = *reinterpret_cast<BwdSmem<D>*>(smem_raw);
+    BwdSmem<D, FBB>& S = *reinterpret_cast<BwdSmem<D, FBB>*>(smem_raw);
     const TileGeom g = tile_geom(tile_w, tile_h, W, H);
     const int tr = threadIdx.x;
 
@@ -336,8 +339,8 @@ __global__ void __launch_bounds__(BLK) blend3d_bwd_fast_kernel(
     if (range_end <= range_start) return;
 
     if (tr == 0) {
-        mbar_init(&S.bar[0], FB);
-        mbar_init(&S.bar[1], FB);
+        mbar_init(&S.bar[0], FBB);
+        mbar_init(&S.bar[1], FBB);
         mbar_fence_init();
     }
 
@@ -346,13 +349,10 @@ __global__ void __launch_bounds__(BLK) blend3d_bwd_fast_kernel(
     const float alpha_out = render_alphas[pid];
     const float T_final = 1.0f - alpha_out;
     float T = T_final;
-    float buffer[D], v_c[D];
+    float v_c[D];
     float v_a = g.inside ? v_render_alphas[pid] : 0.f;
 #pragma unroll
-    for (int k = 0; k < D; ++k) {
-        buffer[k] = 0.f;
-        v_c[k] = g.inside ? v_render_colors[pid * D + k] : 0.f;
-    }
+    for (int k = 0; k < D; ++k) v_c[k] = g.inside ? v_render_colors[pid * D + k] : 0.f;
     if (NORM_DEPTH) {
         // out_d = acc_d / max(alpha, eps): fold the quotient rule into v_c[D-1] and v_a
         const float a_c = fmaxf(alpha_out, HGS_ED_ALPHA_FLOOR);
@@ -365,6 +365,10 @@ __global__ void __launch_bounds__(BLK) blend3d_bwd_fast_kernel(
 #pragma unroll
         for (int k = 0; k < D; ++k) bg_dot += backgrounds[g.cam * D + k] * v_c[k];
     }
+    // d(out)/d(alpha_i) = T_i * (c_i . v_c) + (T_final (v_a - bg.v_c) - S_i) / (1 - alpha_i), where
+    // S_i = sum over the Gaussians behind i of w_j (c_j . v_c) is carried as ONE scalar (s_behind)
+    const float c0 = T_final * (v_a - bg_dot);
+    float s_behind = 0.f;
     const int bin_final = g.inside ? last_ids[pid] : -1;
     int warp_bin_final = bin_final;
 #pragma unroll
@@ -380,13 +384,13 @@ __global__ void __launch_bounds__(BLK) blend3d_bwd_fast_kernel(
 
     // batches run back to front over [range_start, cta_bin_final]
     const int top = cta_bin_final;
-    const int nb = (top - range_start + 1 + FB - 1) / FB;
+    const int nb = (top - range_start + 1 + FBB - 1) / FBB;
 
     const int my_comp = halving_component<NV>(g.lane);
     const bool is_writer = (g.lane == __ffs(__match_any_sync(0xFFFFFFFFu, my_comp)) - 1);
 
     int g_next = -1;
-    if (tr < FB) {
+    if (tr < FBB) {
         int idx = top - tr;
         const int g0 = idx >= range_start ? flatten_ids[idx] : -1;
         S.ids[0][tr] = g0;
@@ -396,13 +400,13 @@ __global__ void __launch_bounds__(BLK) blend3d_bwd_fast_kernel(
         } else {
             mbar_arrive(&S.bar[0]);
         }
-        idx -= FB;
+        idx -= FBB;
         g_next = idx >= range_start ? flatten_ids[idx] : -1;
     }
 
     for (int b = 0; b < nb; ++b) {
         const int st = b & 1;
-        if (tr < FB && b + 1 < nb) {
+        if (tr < FBB && b + 1 < nb) {
             const int ns = st ^ 1;
             S.ids[ns][tr] = g_next;
             if (g_next >= 0) {
@@ -411,15 +415,15 @@ __global__ void __launch_bounds__(BLK) blend3d_bwd_fast_kernel(
             } else {
                 mbar_arrive(&S.bar[ns]);
             }
-            const int idx = top - (b + 2) * FB - tr;
+            const int idx = top - (b + 2) * FBB - tr;
             g_next = idx >= range_start ? flatten_ids[idx] : -1;
         }
-        if (g.lane < FB / 32) S.wmask[g.warp][g.lane] = 0u;
+        if (g.lane < FBB / 32) S.wmask[g.warp][g.lane] = 0u;
         mbar_wait(&S.bar[st], (b >> 1) & 1);
         __syncwarp();
 
-        const int batch_end = top - b * FB;                       // element t <-> index batch_end - t
-        const int batch_n = min(FB, batch_end + 1 - range_start);
+        const int batch_end = top - b * FBB;                       // element t <-> index batch_end - t
+        const int batch_n = min(FBB, batch_end + 1 - range_start);
         const unsigned char* stage = S.rec[st];
         const int t_first = max(0, batch_end - warp_bin_final);
         for (int grp = t_first >> 5; grp * 32 < batch_n; ++grp) {
@@ -453,24 +457,25 @@ __global__ void __launch_bounds__(BLK) blend3d_bwd_fast_kernel(
                     const float ra = rcp_approx(1.0f - alpha);  // 1 - alpha in [1e-3, 1]: 1-ulp reciprocal
                     T *= ra;
                     const float fac = alpha * T;
-                    float v_alpha = 0.f;
+                    float cdot = 0.f;
 #pragma unroll
                     for (int k = 0; k < D; ++k) {
                         val[6 + k] = fac * v_c[k];
-                        v_alpha += (col[k] * T - buffer[k] * ra) * v_c[k];
-                        buffer[k] += col[k] * fac;
+                        cdot += col[k] * v_c[k];
                     }
-                    v_alpha += T_final * ra * v_a;
-                    if (backgrounds != nullptr) v_alpha += -T_final * ra * bg_dot;
+                    const float v_alpha = T * cdot + ra * (c0 - s_behind);
+                    s_behind += fac * cdot;
                     if (opac * vis <= HGS_ALPHA_MAX) {
-                        const float v_sigma = -opac * vis * v_alpha;
-                        // a dx + b dy = -ln2 (2A dx + B dy),  b dx + c dy = -ln2 (B dx + 2C dy)
-                        val[0] = v_sigma * (-LN2) * (2.f * q0.z * dx + q0.w * dy);
-                        val[1] = v_sigma * (-LN2) * (q0.w * dx + 2.f * q1.x * dy);
-                        val[2] = 0.5f * v_sigma * dx * dx;
-                        val[3] = v_sigma * dx * dy;
-                        val[4] = 0.5f * v_sigma * dy * dy;
-                        val[5] = vis * v_alpha;
+                        // moments of v_sigma over the pixels; the flush turns them into v_means2d / v_conics
+                        const float v_o = vis * v_alpha;
+                        const float v_sigma = -opac * v_o;
+                        const float mx = v_sigma * dx, my = v_sigma * dy;
+                        val[0] = mx;
+                        val[1] = my;
+                        val[2] = mx * dx;
+                        val[3] = mx * dy;
+                        val[4] = my * dy;
+                        val[5] = v_o;
                     }
                 }
                 const float r = halving_reduce<NV>(val, g.lane);
@@ -495,6 +500,15 @@ __global__ void __launch_bounds__(BLK) blend3d_bwd_fast_kernel(
                 }
             }
             if (any) {
+                // moments -> gradients: v_xy = (a Mx + b My, b Mx + c My) with (a, b, c) = -ln2 (2A, B, 2C);
+                // v_conic = (Mxx / 2, Mxy, Myy / 2)
+                const float4* q = slot_q(stage, tr);
+                const float4 q0 = q[0], q1 = q[1];
+                const float Mx = sum[0], My = sum[1];
+                sum[0] = -LN2 * (2.f * q0.z * Mx + q0.w * My);
+                sum[1] = -LN2 * (q0.w * Mx + 2.f * q1.x * My);
+                sum[2] *= 0.5f;
+                sum[4] *= 0.5f;
                 float* row = vpack + (long long)S.ids[st][tr] * VP;
                 red_add_v4(row, sum[0], sum[1], sum[2], sum[3]);
                 red_add_v2(row + 4, sum[4], sum[5]);
@@ -776,10 +790,11 @@ int launch_bwd_fast(const GRec* recs, const float* backgrounds, int C, int W, in
                     const float* render_alphas, const int32_t* last_ids, const float* v_render_colors,
                     const float* v_render_alphas, float* vpack, cudaStream_t st) {
     dim3 grid(tile_w, tile_h, C);
-    const int smem = (int)sizeof(BwdSmem<D>);
-    cudaError_t e = cudaFuncSetAttribute(blend3d_bwd_fast_kernel<D, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int smem = (int)sizeof(BwdSmem<D, FB_BWD>);
+    cudaError_t e = cudaFuncSetAttribute(blend3d_bwd_fast_kernel<D, NORM, FB_BWD>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
-    blend3d_bwd_fast_kernel<D, NORM><<<grid, BLK, smem, st>>>(recs, backgrounds, C, W, H, tile_w, tile_h, offsets,
+    blend3d_bwd_fast_kernel<D, NORM, FB_BWD><<<grid, BLK, smem, st>>>(recs, backgrounds, C, W, H, tile_w, tile_h, offsets,
                                                              flatten_ids, n_isects, render_colors, render_alphas,
                                                              last_ids, v_render_colors, v_render_alphas, vpack);
     HGS_LAUNCH_CHECK();
@@ -845,12 +860,13 @@ HGS_API int hgs_blend3d_bwd(const float* means2d, const float* conics, const flo
 HGS_API size_t hgs_blend3d_pack_bytes(long long CN) { return (size_t)(CN > 0 ? CN : 1) * REC_BYTES; }
 
 HGS_API int hgs_blend3d_pack(const float* means2d, const float* conics, const float* colors, const float* depths,
-                             const float* opacities, const int32_t* radii, long long CN, int CH, void* records,
-                             void* stream) {
-    if (CN < 0 || CH < 0 || CH + (depths != nullptr ? 1 : 0) > 4) return HGS_ERR_INVALID_ARG;
-    if (CN == 0) return 0;
-    pack3d_kernel<<<hgs_ceil_div(CN, 256), 256, 0, (cudaStream_t)stream>>>(means2d, conics, colors, depths, opacities,
-                                                                            radii, CN, CH, (GRec*)records);
+                             const float* opacities, const int32_t* radii, const int32_t* vis_ids, long long n_vis,
+                             long long CN, int CH, void* records, void* stream) {
+    if (CN < 0 || n_vis < 0 || CH < 0 || CH + (depths != nullptr ? 1 : 0) > 4) return HGS_ERR_INVALID_ARG;
+    const long long work = vis_ids != nullptr ? n_vis : CN;
+    if (work == 0) return 0;
+    pack3d_kernel<<<hgs_ceil_div(work, 256), 256, 0, (cudaStream_t)stream>>>(means2d, conics, colors, depths, opacities,
+                                                                              radii, vis_ids, work, CH, (GRec*)records);
     HGS_LAUNCH_CHECK();
     return 0;
 }

@@ -36,13 +36,45 @@ __global__ void densify_stats_kernel(const float* __restrict__ v_means2d, int ld
         if (max_radii != nullptr) max_radii[n] = fmaxf(max_radii[n], (float)rmax);
     }
 }
+// work-list variant: one thread per visible (camera, Gaussian) pair; several cameras -> atomics
+__global__ void densify_stats_vis_kernel(const float* __restrict__ v_means2d, int ld, const int32_t* __restrict__ radii,
+                                         const int32_t* __restrict__ vis_ids, long long n_vis, int C, int N,
+                                         float half_w, float half_h, int mode_max, float* __restrict__ grad_accum,
+                                         float* __restrict__ denom, float* __restrict__ max_radii) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_vis) return;
+    const long long idx = vis_ids[j];
+    const long long n = idx % N;
+    const float gx = v_means2d[idx * ld] * half_w, gy = v_means2d[idx * ld + 1] * half_h;
+    const float nrm = sqrtf(gx * gx + gy * gy);
+    const float r = (float)radii[idx];
+    if (C == 1) {
+        grad_accum[n] = mode_max ? fmaxf(grad_accum[n], nrm) : grad_accum[n] + nrm;
+        denom[n] += 1.f;
+        if (max_radii != nullptr) max_radii[n] = fmaxf(max_radii[n], r);
+    } else {
+        // non-negative floats order like their bit patterns
+        if (mode_max) atomicMax(reinterpret_cast<int*>(grad_accum + n), __float_as_int(nrm));
+        else atomicAdd(grad_accum + n, nrm);
+        atomicAdd(denom + n, 1.f);
+        if (max_radii != nullptr) atomicMax(reinterpret_cast<int*>(max_radii + n), __float_as_int(r));
+    }
+}
 }  // namespace
 
-HGS_API int hgs_densify_stats(const float* v_means2d, int ld_means2d, const int32_t* radii, int C, int N, int width,
-                              int height, int mode_max, float* grad_accum, float* denom, float* max_radii,
-                              void* stream) {
-    if (C <= 0 || N < 0 || ld_means2d < 2 || width <= 0 || height <= 0) return HGS_ERR_INVALID_ARG;
+HGS_API int hgs_densify_stats(const float* v_means2d, int ld_means2d, const int32_t* radii, const int32_t* vis_ids,
+                              long long n_vis, int C, int N, int width, int height, int mode_max, float* grad_accum,
+                              float* denom, float* max_radii, void* stream) {
+    if (C <= 0 || N < 0 || ld_means2d < 2 || width <= 0 || height <= 0 || n_vis < 0) return HGS_ERR_INVALID_ARG;
     if (N == 0) return 0;
+    if (vis_ids != nullptr) {
+        if (n_vis == 0) return 0;
+        densify_stats_vis_kernel<<<hgs_ceil_div(n_vis, 256), 256, 0, (cudaStream_t)stream>>>(
+            v_means2d, ld_means2d, radii, vis_ids, n_vis, C, N, 0.5f * (float)width, 0.5f * (float)height, mode_max,
+            grad_accum, denom, max_radii);
+        HGS_LAUNCH_CHECK();
+        return 0;
+    }
     densify_stats_kernel<<<hgs_ceil_div(N, 256), 256, 0, (cudaStream_t)stream>>>(
         v_means2d, ld_means2d, radii, C, N, 0.5f * (float)width, 0.5f * (float)height, mode_max, grad_accum, denom,
         max_radii);

@@ -45,6 +45,18 @@ __device__ __forceinline__ uint32_t digit_of(const DigitSpec& ds, uint32_t key, 
     return (src >> ds.shift) & ds.mask;
 }
 
+// lanes of the warp holding the same 8-bit digit (fixed cost: 8 ballots; __match_any_sync degrades to one
+// iteration per distinct value, i.e. 32 iterations on the low tile-id byte)
+__device__ __forceinline__ unsigned peers_of(uint32_t d) {
+    unsigned peers = 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const unsigned b = __ballot_sync(0xFFFFFFFFu, (d >> k) & 1u);
+        peers &= ((d >> k) & 1u) ? b : ~b;
+    }
+    return peers;
+}
+
 // chunk c of a pass over n elements with gridDim.x chunks: [begin, end)
 __device__ __forceinline__ void chunk_range(long long n, long long& begin, long long& end) {
     const long long tiles = (n + RS_TILE - 1) / RS_TILE;
@@ -95,9 +107,11 @@ __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint32_t* 
     for (long long base = begin; base < end; base += RS_THREADS) {
         long long i = base + threadIdx.x;
         bool valid = i < end;
-        uint32_t d = valid ? digit_of(ds, keys[i], ds.from_val_div > 0 ? vals[i] : 0u) : 0xFFFFFFFFu;
-        unsigned m = __match_any_sync(0xFFFFFFFFu, d);
-        int leader = __ffs(m) - 1;
+        const uint32_t d = valid ? digit_of(ds, keys[i], ds.from_val_div > 0 ? vals[i] : 0u) : 0u;
+        // invalid lanes are masked out of the peer sets
+        const unsigned vmask = __ballot_sync(0xFFFFFFFFu, valid);
+        const unsigned m = peers_of(d) & vmask;
+        const int leader = __ffs(m) - 1;
         if (valid && (int)(threadIdx.x & 31) == leader) atomicAdd(&s_hist[d], (uint32_t)__popc(m));
     }
     __syncthreads();
@@ -159,7 +173,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; ++i) {
-            unsigned m = __match_any_sync(0xFFFFFFFFu, dig[i]);
+            const unsigned m = peers_of(dig[i]);
             rank[i] = s_whist[warp][dig[i]] + (uint32_t)__popc(m & lt_mask);
             __syncwarp();
             if (lane == __ffs(m) - 1) s_whist[warp][dig[i]] += (uint32_t)__popc(m);
@@ -404,7 +418,8 @@ __global__ void __launch_bounds__(RS_THREADS) vis_count_kernel(const int32_t* __
 __global__ void __launch_bounds__(RS_THREADS) compact_kernel(const float* __restrict__ depths,
                                                              const int32_t* __restrict__ tiles_per_gauss, long long CN,
                                                              const long long* __restrict__ blk_base,
-                                                             uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                                             uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                             int32_t* __restrict__ visible_ids) {
     __shared__ uint32_t s_warp[RS_WARPS];
     constexpr int PER = CP_TILE / RS_THREADS;  // 4 consecutive elements per thread (order preserving)
     const long long first = (long long)blockIdx.x * CP_TILE + (long long)threadIdx.x * PER;
@@ -425,6 +440,7 @@ __global__ void __launch_bounds__(RS_THREADS) compact_kernel(const float* __rest
             const long long idx = first + i;
             keys[out0 + pos] = (uint32_t)__float_as_int(depths[idx]);
             vals[out0 + pos] = (uint32_t)idx;
+            if (visible_ids != nullptr) visible_ids[out0 + pos] = (int32_t)idx;
             ++pos;
         }
     }
@@ -455,15 +471,25 @@ __global__ void __launch_bounds__(RS_THREADS) emit_sorted_kernel(
     const long long e0 = (long long)blockIdx.x * RS_TILE;
     long long e1 = e0 + RS_TILE;
     if (e1 > n_isects) e1 = n_isects;
-    if (threadIdx.x < 2) {
-        // last j with cum_sorted[j] <= target
-        const long long target = threadIdx.x == 0 ? e0 : e1 - 1;
-        long long lo = 0, hi = n_vis - 1;
-        while (lo < hi) {
-            const long long mid = (lo + hi + 1) >> 1;
-            if ((long long)cum_sorted[mid] <= target) lo = mid; else hi = mid - 1;
+    if (threadIdx.x < 64) {
+        // warp 0 / warp 1: last j with cum_sorted[j] <= target, 32-ary search (cum_sorted[0] == 0 <= target)
+        const int lane = threadIdx.x & 31;
+        const long long target = threadIdx.x < 32 ? e0 : e1 - 1;
+        long long lo = 0, hi = n_vis;                       // answer in [lo, hi)
+        while (hi - lo > 32) {
+            const long long step = (hi - lo + 31) >> 5;
+            const long long idx = lo + lane * step;
+            const bool le = idx < hi && (long long)cum_sorted[idx] <= target;
+            const int p = __popc(__ballot_sync(0xFFFFFFFFu, le));   // >= 1: probes are sorted, lane 0 is true
+            const long long nlo = lo + (long long)(p - 1) * step;
+            const long long nhi = lo + (long long)p * step;
+            lo = nlo;
+            hi = nhi < hi ? nhi : hi;
         }
-        s_j[threadIdx.x] = lo;
+        const long long idx = lo + lane;
+        const bool le = idx < hi && (long long)cum_sorted[idx] <= target;
+        const int p = __popc(__ballot_sync(0xFFFFFFFFu, le));
+        if (lane == 0) s_j[threadIdx.x >> 5] = lo + p - 1;
     }
     __syncthreads();
     const long long j0 = s_j[0];
@@ -589,8 +615,8 @@ HGS_API size_t hgs_isect_prepare_temp_bytes(long long CN) {
 }
 
 HGS_API int hgs_isect_prepare(const float* depths, const int32_t* tiles_per_gauss, int C, int N, int32_t* order,
-                              int32_t* cum_sorted, long long* counts_dev, void* temp, size_t temp_bytes,
-                              void* stream) {
+                              int32_t* cum_sorted, int32_t* visible_ids, long long* counts_dev, void* temp,
+                              size_t temp_bytes, void* stream) {
     if (C <= 0 || N < 0) return HGS_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const long long CN = (long long)C * N;
@@ -615,7 +641,7 @@ HGS_API int hgs_isect_prepare(const float* depths, const int32_t* tiles_per_gaus
     HGS_LAUNCH_CHECK();
     ls_scan_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(blk, nblk, n_vis_dev);
     HGS_LAUNCH_CHECK();
-    compact_kernel<<<nblk, RS_THREADS, 0, st>>>(depths, tiles_per_gauss, CN, blk, kA, vA);
+    compact_kernel<<<nblk, RS_THREADS, 0, st>>>(depths, tiles_per_gauss, CN, blk, kA, vA, visible_ids);
     HGS_LAUNCH_CHECK();
     // 2. stable LSD sort of the depth bits (then of the camera index when C > 1)
     uint32_t *ki = kA, *vi = vA, *ko = kB, *vo = vB;

@@ -164,9 +164,106 @@ __global__ void __launch_bounds__(PB) project3d_fwd_kernel(
     block_store_rows3<PB>(conics + (long long)c * N * 3, base, N, s_a);
 }
 
-// One thread per Gaussian, loop over cameras: gradients w.r.t. means/quats/scales are summed
-// over the C views without atomics (deterministic).  Gaussians culled in every view only write zeros:
-// their parameters and upstream gradients are never read.
+// gradient of one (camera, Gaussian) pair; accumulates into g_mean / g_scale / g_quat
+__device__ __forceinline__ void proj3d_bwd_one(const HgsCam& cam, const Proj3dFwd& f, float s0, float s1, float s2,
+                                               float2 vm, float vd, float va, float vb, float vc, float g_mean[3],
+                                               float g_scale[3], float g_quat[4]) {
+    // conic X = inv(Sigma2'), v_Sigma2 = -X V X
+    const float inv_det = 1.0f / f.det;
+    const float a = f.c11 * inv_det, b = -f.c01 * inv_det, cc = f.c00 * inv_det;
+    const float xv00 = a * va + b * vb, xv01 = a * vb + b * vc;
+    const float xv10 = b * va + cc * vb, xv11 = b * vb + cc * vc;
+    const float G00 = -(xv00 * a + xv01 * b);
+    const float G01 = -(xv00 * b + xv01 * cc);
+    const float G11 = -(xv10 * b + xv11 * cc);
+
+    // Sigma2 = J Sc J^T
+    const float GJ[2][3] = {{G00 * f.j00, G01 * f.j11, G00 * f.j02 + G01 * f.j12},
+                            {G01 * f.j00, G11 * f.j11, G01 * f.j02 + G11 * f.j12}};
+    float vSc[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        vSc[0][j] = f.j00 * GJ[0][j];
+        vSc[1][j] = f.j11 * GJ[1][j];
+        vSc[2][j] = f.j02 * GJ[0][j] + f.j12 * GJ[1][j];
+    }
+    const float vJ00 = 2.f * (GJ[0][0] * f.Sc[0][0] + GJ[0][1] * f.Sc[1][0] + GJ[0][2] * f.Sc[2][0]);
+    const float vJ02 = 2.f * (GJ[0][0] * f.Sc[0][2] + GJ[0][1] * f.Sc[1][2] + GJ[0][2] * f.Sc[2][2]);
+    const float vJ11 = 2.f * (GJ[1][0] * f.Sc[0][1] + GJ[1][1] * f.Sc[1][1] + GJ[1][2] * f.Sc[2][1]);
+    const float vJ12 = 2.f * (GJ[1][0] * f.Sc[0][2] + GJ[1][1] * f.Sc[1][2] + GJ[1][2] * f.Sc[2][2]);
+
+    const float fx = cam.fx, fy = cam.fy;
+    const float rz3 = f.rz2 * f.rz;
+    float v_xc = fx * f.rz * vm.x;
+    float v_yc = fy * f.rz * vm.y;
+    float v_zc = -(fx * f.xc * vm.x + fy * f.yc * vm.y) * f.rz2 + vd;
+    v_zc += -fx * f.rz2 * vJ00 - fy * f.rz2 * vJ11;
+    if (f.x_unclamped) {
+        v_xc += -fx * f.rz2 * vJ02;
+        v_zc += 2.f * fx * f.tx * rz3 * vJ02;
+    } else {
+        v_zc += fx * f.tx * rz3 * vJ02;
+    }
+    if (f.y_unclamped) {
+        v_yc += -fy * f.rz2 * vJ12;
+        v_zc += 2.f * fy * f.ty * rz3 * vJ12;
+    } else {
+        v_zc += fy * f.ty * rz3 * vJ12;
+    }
+
+    const float (*R)[3] = cam.R;
+    g_mean[0] += R[0][0] * v_xc + R[1][0] * v_yc + R[2][0] * v_zc;
+    g_mean[1] += R[0][1] * v_xc + R[1][1] * v_yc + R[2][1] * v_zc;
+    g_mean[2] += R[0][2] * v_xc + R[1][2] * v_yc + R[2][2] * v_zc;
+
+    // Sc = R S R^T  ->  vS = R^T vSc R
+    float T[3][3], vS[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) T[i][j] = vSc[i][0] * R[0][j] + vSc[i][1] * R[1][j] + vSc[i][2] * R[2][j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) vS[i][j] = R[0][i] * T[0][j] + R[1][i] * T[1][j] + R[2][i] * T[2][j];
+    // S = M M^T -> vM = (vS + vS^T) M
+    float vM[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            vM[i][j] = (vS[i][0] + vS[0][i]) * f.M[0][j] + (vS[i][1] + vS[1][i]) * f.M[1][j] +
+                       (vS[i][2] + vS[2][i]) * f.M[2][j];
+    // M = q diag(s)
+    const float s[3] = {s0, s1, s2};
+    float vq_mat[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        g_scale[j] += f.q[0][j] * vM[0][j] + f.q[1][j] * vM[1][j] + f.q[2][j] * vM[2][j];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) vq_mat[i][j] = vM[i][j] * s[j];
+    }
+    float vq[4];
+    hgs_quat_to_rot_vjp(f.qn, f.inv_norm, vq_mat, vq);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g_quat[k] += vq[k];
+}
+
+#define PROJ3D_BWD_LOAD_AND_RUN(IDX, N_, C_)                                                                         \
+    {                                                                                                                \
+        const HgsCam cam = hgs_load_cam(viewmats, Ks, (C_));                                                         \
+        Proj3dFwd f;                                                                                                 \
+        if (proj3d_math(cam, px, py, pz, qv.x, qv.y, qv.z, qv.w, s0, s1, s2, (float)W, (float)H, eps2d, near_plane,  \
+                        far_plane, f)) {                                                                             \
+            const float2 vm = make_float2(v_means2d[(IDX) * ld_m2], v_means2d[(IDX) * ld_m2 + 1]);                   \
+            const float vd = v_depths != nullptr ? v_depths[(IDX) * ld_d] : 0.f;                                     \
+            proj3d_bwd_one(cam, f, s0, s1, s2, vm, vd, v_conics[(IDX) * ld_c], 0.5f * v_conics[(IDX) * ld_c + 1],    \
+                           v_conics[(IDX) * ld_c + 2], g_mean, g_scale, g_quat);                                     \
+        }                                                                                                            \
+    }
+
+// Dense variant: one thread per Gaussian, loop over cameras: gradients w.r.t. means/quats/scales are summed
+// over the C views without atomics (deterministic).  Gaussians culled in every view only write zeros.
 __global__ void __launch_bounds__(PB) project3d_bwd_kernel(
     const float* __restrict__ means, const float* __restrict__ quats, const float* __restrict__ scales,
     const float* __restrict__ viewmats, const float* __restrict__ Ks, int C, int N, int W, int H, float eps2d,
@@ -184,109 +281,60 @@ __global__ void __launch_bounds__(PB) project3d_bwd_kernel(
         s0 = scales[n * 3]; s1 = scales[n * 3 + 1]; s2 = scales[n * 3 + 2];
         qv = reinterpret_cast<const float4*>(quats)[n];
     }
-
     float g_mean[3] = {0.f, 0.f, 0.f};
     float g_scale[3] = {0.f, 0.f, 0.f};
     float g_quat[4] = {0.f, 0.f, 0.f, 0.f};
-
     for (int c = 0; c < C && any; ++c) {
         const long long idx = (long long)c * N + n;
         if (radii[idx] <= 0) continue;
-        const HgsCam cam = hgs_load_cam(viewmats, Ks, c);
-        Proj3dFwd f;
-        if (!proj3d_math(cam, px, py, pz, qv.x, qv.y, qv.z, qv.w, s0, s1, s2, (float)W, (float)H, eps2d, near_plane,
-                         far_plane, f))
-            continue;
-        const float2 vm = make_float2(v_means2d[idx * ld_m2], v_means2d[idx * ld_m2 + 1]);
-        const float vd = v_depths != nullptr ? v_depths[idx * ld_d] : 0.f;
-        const float va = v_conics[idx * ld_c], vb = 0.5f * v_conics[idx * ld_c + 1], vc = v_conics[idx * ld_c + 2];
-
-        // conic X = inv(Sigma2'), v_Sigma2 = -X V X
-        const float inv_det = 1.0f / f.det;
-        const float a = f.c11 * inv_det, b = -f.c01 * inv_det, cc = f.c00 * inv_det;
-        const float xv00 = a * va + b * vb, xv01 = a * vb + b * vc;
-        const float xv10 = b * va + cc * vb, xv11 = b * vb + cc * vc;
-        const float G00 = -(xv00 * a + xv01 * b);
-        const float G01 = -(xv00 * b + xv01 * cc);
-        const float G11 = -(xv10 * b + xv11 * cc);
-
-        // Sigma2 = J Sc J^T
-        const float GJ[2][3] = {{G00 * f.j00, G01 * f.j11, G00 * f.j02 + G01 * f.j12},
-                                {G01 * f.j00, G11 * f.j11, G01 * f.j02 + G11 * f.j12}};
-        float vSc[3][3];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            vSc[0][j] = f.j00 * GJ[0][j];
-            vSc[1][j] = f.j11 * GJ[1][j];
-            vSc[2][j] = f.j02 * GJ[0][j] + f.j12 * GJ[1][j];
-        }
-        const float vJ00 = 2.f * (GJ[0][0] * f.Sc[0][0] + GJ[0][1] * f.Sc[1][0] + GJ[0][2] * f.Sc[2][0]);
-        const float vJ02 = 2.f * (GJ[0][0] * f.Sc[0][2] + GJ[0][1] * f.Sc[1][2] + GJ[0][2] * f.Sc[2][2]);
-        const float vJ11 = 2.f * (GJ[1][0] * f.Sc[0][1] + GJ[1][1] * f.Sc[1][1] + GJ[1][2] * f.Sc[2][1]);
-        const float vJ12 = 2.f * (GJ[1][0] * f.Sc[0][2] + GJ[1][1] * f.Sc[1][2] + GJ[1][2] * f.Sc[2][2]);
-
-        const float fx = cam.fx, fy = cam.fy;
-        const float rz3 = f.rz2 * f.rz;
-        float v_xc = fx * f.rz * vm.x;
-        float v_yc = fy * f.rz * vm.y;
-        float v_zc = -(fx * f.xc * vm.x + fy * f.yc * vm.y) * f.rz2 + vd;
-        v_zc += -fx * f.rz2 * vJ00 - fy * f.rz2 * vJ11;
-        if (f.x_unclamped) {
-            v_xc += -fx * f.rz2 * vJ02;
-            v_zc += 2.f * fx * f.tx * rz3 * vJ02;
-        } else {
-            v_zc += fx * f.tx * rz3 * vJ02;
-        }
-        if (f.y_unclamped) {
-            v_yc += -fy * f.rz2 * vJ12;
-            v_zc += 2.f * fy * f.ty * rz3 * vJ12;
-        } else {
-            v_zc += fy * f.ty * rz3 * vJ12;
-        }
-
-        const float (*R)[3] = cam.R;
-        g_mean[0] += R[0][0] * v_xc + R[1][0] * v_yc + R[2][0] * v_zc;
-        g_mean[1] += R[0][1] * v_xc + R[1][1] * v_yc + R[2][1] * v_zc;
-        g_mean[2] += R[0][2] * v_xc + R[1][2] * v_yc + R[2][2] * v_zc;
-
-        // Sc = R S R^T  ->  vS = R^T vSc R
-        float T[3][3], vS[3][3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) T[i][j] = vSc[i][0] * R[0][j] + vSc[i][1] * R[1][j] + vSc[i][2] * R[2][j];
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) vS[i][j] = R[0][i] * T[0][j] + R[1][i] * T[1][j] + R[2][i] * T[2][j];
-        // S = M M^T -> vM = (vS + vS^T) M
-        float vM[3][3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-                vM[i][j] = (vS[i][0] + vS[0][i]) * f.M[0][j] + (vS[i][1] + vS[1][i]) * f.M[1][j] +
-                           (vS[i][2] + vS[2][i]) * f.M[2][j];
-        // M = q diag(s)
-        const float s[3] = {s0, s1, s2};
-        float vq_mat[3][3];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            g_scale[j] += f.q[0][j] * vM[0][j] + f.q[1][j] * vM[1][j] + f.q[2][j] * vM[2][j];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) vq_mat[i][j] = vM[i][j] * s[j];
-        }
-        float vq[4];
-        hgs_quat_to_rot_vjp(f.qn, f.inv_norm, vq_mat, vq);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) g_quat[k] += vq[k];
+        PROJ3D_BWD_LOAD_AND_RUN(idx, N, c)
     }
-
     reinterpret_cast<float4*>(v_quats)[n] = make_float4(g_quat[0], g_quat[1], g_quat[2], g_quat[3]);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         v_means[n * 3 + k] = g_mean[k];
         v_scales[n * 3 + k] = g_scale[k];
+    }
+}
+
+// Work-list variant: one thread per VISIBLE (camera, Gaussian) pair (vis_ids = flat indices c*N+n with
+// radii > 0, from hgs_isect_prepare), so warps are fully populated even when most Gaussians are culled.
+// Outputs are zero-filled by the launcher; with one camera every row is written once (plain stores), with
+// several cameras contributions are added atomically.
+__global__ void __launch_bounds__(PB) project3d_bwd_vis_kernel(
+    const float* __restrict__ means, const float* __restrict__ quats, const float* __restrict__ scales,
+    const float* __restrict__ viewmats, const float* __restrict__ Ks, int C, int N, int W, int H, float eps2d,
+    float near_plane, float far_plane, const int32_t* __restrict__ vis_ids, long long n_vis,
+    const float* __restrict__ v_means2d, int ld_m2, const float* __restrict__ v_depths, int ld_d,
+    const float* __restrict__ v_conics, int ld_c, float* __restrict__ v_means, float* __restrict__ v_quats,
+    float* __restrict__ v_scales) {
+    const long long j = (long long)blockIdx.x * PB + threadIdx.x;
+    if (j >= n_vis) return;
+    const long long idx = vis_ids[j];
+    const int c = (int)(idx / N);
+    const long long n = idx - (long long)c * N;
+    const float px = means[n * 3], py = means[n * 3 + 1], pz = means[n * 3 + 2];
+    const float s0 = scales[n * 3], s1 = scales[n * 3 + 1], s2 = scales[n * 3 + 2];
+    const float4 qv = reinterpret_cast<const float4*>(quats)[n];
+    float g_mean[3] = {0.f, 0.f, 0.f};
+    float g_scale[3] = {0.f, 0.f, 0.f};
+    float g_quat[4] = {0.f, 0.f, 0.f, 0.f};
+    PROJ3D_BWD_LOAD_AND_RUN(idx, N, c)
+    if (C == 1) {
+        reinterpret_cast<float4*>(v_quats)[n] = make_float4(g_quat[0], g_quat[1], g_quat[2], g_quat[3]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            v_means[n * 3 + k] = g_mean[k];
+            v_scales[n * 3 + k] = g_scale[k];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) atomicAdd(v_quats + n * 4 + k, g_quat[k]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            atomicAdd(v_means + n * 3 + k, g_mean[k]);
+            atomicAdd(v_scales + n * 3 + k, g_scale[k]);
+        }
     }
 }
 
@@ -315,10 +363,24 @@ HGS_API int hgs_project3d_bwd(const float* means, const float* quats, const floa
                               const float* Ks, int C, int N, int width, int height, float eps2d, float near_plane,
                               float far_plane, const int32_t* radii, const float* v_means2d, int ld_means2d,
                               const float* v_depths, int ld_depths, const float* v_conics, int ld_conics,
-                              float* v_means, float* v_quats, float* v_scales, void* stream) {
-    if (C <= 0 || N < 0 || width <= 0 || height <= 0 || ld_means2d < 2 || ld_conics < 3 || ld_depths < 1)
+                              const int32_t* vis_ids, long long n_vis, float* v_means, float* v_quats,
+                              float* v_scales, void* stream) {
+    if (C <= 0 || N < 0 || width <= 0 || height <= 0 || ld_means2d < 2 || ld_conics < 3 || ld_depths < 1 || n_vis < 0)
         return HGS_ERR_INVALID_ARG;
     if (N == 0) return 0;
+    if (vis_ids != nullptr) {
+        cudaStream_t st = (cudaStream_t)stream;
+        cudaError_t e;
+        if ((e = cudaMemsetAsync(v_means, 0, (size_t)N * 3 * sizeof(float), st)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemsetAsync(v_quats, 0, (size_t)N * 4 * sizeof(float), st)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemsetAsync(v_scales, 0, (size_t)N * 3 * sizeof(float), st)) != cudaSuccess) return (int)e;
+        if (n_vis == 0) return 0;
+        project3d_bwd_vis_kernel<<<hgs_ceil_div(n_vis, PB), PB, 0, st>>>(
+            means, quats, scales, viewmats, Ks, C, N, width, height, eps2d, near_plane, far_plane, vis_ids, n_vis,
+            v_means2d, ld_means2d, v_depths, ld_depths, v_conics, ld_conics, v_means, v_quats, v_scales);
+        HGS_LAUNCH_CHECK();
+        return 0;
+    }
     project3d_bwd_kernel<<<hgs_ceil_div(N, PB), PB, 0, (cudaStream_t)stream>>>(
         means, quats, scales, viewmats, Ks, C, N, width, height, eps2d, near_plane, far_plane, radii, v_means2d,
         ld_means2d, v_depths, ld_depths, v_conics, ld_conics, v_means, v_quats, v_scales);

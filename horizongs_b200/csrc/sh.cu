@@ -126,16 +126,67 @@ __device__ __forceinline__ void load_dir(const float* __restrict__ dirs, const f
     }
 }
 
-// One thread per Gaussian.  Only Gaussians that survive culling (radii > 0) touch their coefficient row
-// (12 K bytes): in large scenes most rows are never read.  Rows are read/written by their owning thread;
-// every byte of a touched row is used, so sector efficiency stays high without shared-memory staging.
+// colour of one (camera, Gaussian) pair
+template <int DEG>
+__device__ __forceinline__ void sh_eval_one(float x, float y, float z, const float* __restrict__ co, int post,
+                                            float& r0, float& r1, float& r2) {
+    constexpr int NB = (DEG + 1) * (DEG + 1);
+    const float inorm = 1.0f / sqrtf(x * x + y * y + z * z);
+    x *= inorm; y *= inorm; z *= inorm;
+    float b[NB];
+    sh_basis<DEG, false>(x, y, z, b, nullptr, nullptr, nullptr);
+    r0 = b[0] * __ldg(co + 0); r1 = b[0] * __ldg(co + 1); r2 = b[0] * __ldg(co + 2);
+#pragma unroll
+    for (int k = 1; k < NB; ++k) {
+        r0 = r0 + b[k] * __ldg(co + k * 3 + 0);
+        r1 = r1 + b[k] * __ldg(co + k * 3 + 1);
+        r2 = r2 + b[k] * __ldg(co + k * 3 + 2);
+    }
+    if (post) {
+        r0 = fmaxf(r0 + HGS_SH_OFFSET, 0.f);
+        r1 = fmaxf(r1 + HGS_SH_OFFSET, 0.f);
+        r2 = fmaxf(r2 + HGS_SH_OFFSET, 0.f);
+    }
+}
+
+// gradient of one (camera, Gaussian) pair: g_co[NB*3] += basis * v, gd = d/d(un-normalised direction)
+template <int DEG>
+__device__ __forceinline__ void sh_grad_one(float x, float y, float z, const float* __restrict__ co, float v0, float v1,
+                                            float v2, bool want_dir, float* g_co, float& gd0, float& gd1, float& gd2) {
+    constexpr int NB = (DEG + 1) * (DEG + 1);
+    const float inorm = 1.0f / sqrtf(x * x + y * y + z * z);
+    x *= inorm; y *= inorm; z *= inorm;
+    float b[NB], bx[NB], by[NB], bz[NB];
+    sh_basis<DEG, true>(x, y, z, b, bx, by, bz);
+    float vx = 0.f, vy = 0.f, vz = 0.f;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        g_co[k * 3 + 0] += b[k] * v0;
+        g_co[k * 3 + 1] += b[k] * v1;
+        g_co[k * 3 + 2] += b[k] * v2;
+        if (want_dir) {
+            const float d = __ldg(co + k * 3) * v0 + __ldg(co + k * 3 + 1) * v1 + __ldg(co + k * 3 + 2) * v2;
+            vx += bx[k] * d; vy += by[k] * d; vz += bz[k] * d;
+        }
+    }
+    gd0 = gd1 = gd2 = 0.f;
+    if (want_dir) {
+        const float dd = vx * x + vy * y + vz * z;
+        gd0 = (vx - dd * x) * inorm;
+        gd1 = (vy - dd * y) * inorm;
+        gd2 = (vz - dd * z) * inorm;
+    }
+}
+
+// Dense variant: one thread per Gaussian.  Only Gaussians that survive culling (radii > 0) touch their
+// coefficient row (12 K bytes).  Rows are read/written by their owning thread; every byte of a touched row
+// is used, so sector efficiency stays high without shared-memory staging.
 template <int DEG>
 __global__ void __launch_bounds__(SB) sh_fwd_kernel(const float* __restrict__ dirs, const float* __restrict__ means,
                                                     const float* __restrict__ campos,
                                                     const float* __restrict__ coeffs,
                                                     const int32_t* __restrict__ radii, int C, int N, int K, int post,
                                                     float* __restrict__ colors) {
-    constexpr int NB = (DEG + 1) * (DEG + 1);
     const long long n = (long long)blockIdx.x * SB + threadIdx.x;
     if (n >= N) return;
     const float* co = coeffs + n * (long long)(K * 3);
@@ -145,25 +196,28 @@ __global__ void __launch_bounds__(SB) sh_fwd_kernel(const float* __restrict__ di
         if (radii == nullptr || radii[idx] > 0) {
             float x, y, z;
             load_dir(dirs, means, campos, idx, n, c, x, y, z);
-            const float inorm = 1.0f / sqrtf(x * x + y * y + z * z);
-            x *= inorm; y *= inorm; z *= inorm;
-            float b[NB];
-            sh_basis<DEG, false>(x, y, z, b, nullptr, nullptr, nullptr);
-            r0 = b[0] * __ldg(co + 0); r1 = b[0] * __ldg(co + 1); r2 = b[0] * __ldg(co + 2);
-#pragma unroll
-            for (int k = 1; k < NB; ++k) {
-                r0 = r0 + b[k] * __ldg(co + k * 3 + 0);
-                r1 = r1 + b[k] * __ldg(co + k * 3 + 1);
-                r2 = r2 + b[k] * __ldg(co + k * 3 + 2);
-            }
-            if (post) {
-                r0 = fmaxf(r0 + HGS_SH_OFFSET, 0.f);
-                r1 = fmaxf(r1 + HGS_SH_OFFSET, 0.f);
-                r2 = fmaxf(r2 + HGS_SH_OFFSET, 0.f);
-            }
+            sh_eval_one<DEG>(x, y, z, co, post, r0, r1, r2);
         }
         colors[idx * 3] = r0; colors[idx * 3 + 1] = r1; colors[idx * 3 + 2] = r2;
     }
+}
+
+// Work-list variant: one thread per visible (camera, Gaussian) pair; colors is zero-filled by the launcher.
+template <int DEG>
+__global__ void __launch_bounds__(SB) sh_fwd_vis_kernel(const float* __restrict__ dirs, const float* __restrict__ means,
+                                                        const float* __restrict__ campos,
+                                                        const float* __restrict__ coeffs,
+                                                        const int32_t* __restrict__ vis_ids, long long n_vis, int N,
+                                                        int K, int post, float* __restrict__ colors) {
+    const long long j = (long long)blockIdx.x * SB + threadIdx.x;
+    if (j >= n_vis) return;
+    const long long idx = vis_ids[j];
+    const int c = (int)(idx / N);
+    const long long n = idx - (long long)c * N;
+    float x, y, z, r0, r1, r2;
+    load_dir(dirs, means, campos, idx, n, c, x, y, z);
+    sh_eval_one<DEG>(x, y, z, coeffs + n * (long long)(K * 3), post, r0, r1, r2);
+    colors[idx * 3] = r0; colors[idx * 3 + 1] = r1; colors[idx * 3 + 2] = r2;
 }
 
 // v_coeffs must be zero-filled by the launcher (rows of culled Gaussians are never touched here).
@@ -199,28 +253,8 @@ __global__ void __launch_bounds__(SB) sh_bwd_kernel(const float* __restrict__ di
             }
             float x, y, z;
             load_dir(dirs, means, campos, idx, n, c, x, y, z);
-            const float inorm = 1.0f / sqrtf(x * x + y * y + z * z);
-            x *= inorm; y *= inorm; z *= inorm;
-            float b[NB], bx[NB], by[NB], bz[NB];
-            sh_basis<DEG, true>(x, y, z, b, bx, by, bz);
-            float vx = 0.f, vy = 0.f, vz = 0.f;
-#pragma unroll
-            for (int k = 0; k < NB; ++k) {
-                g_co[k * 3 + 0] += b[k] * v0;
-                g_co[k * 3 + 1] += b[k] * v1;
-                g_co[k * 3 + 2] += b[k] * v2;
-                if (want_dir) {
-                    const float d = __ldg(co + k * 3) * v0 + __ldg(co + k * 3 + 1) * v1 + __ldg(co + k * 3 + 2) * v2;
-                    vx += bx[k] * d; vy += by[k] * d; vz += bz[k] * d;
-                }
-            }
-            if (want_dir) {
-                const float dd = vx * x + vy * y + vz * z;
-                gd0 = (vx - dd * x) * inorm;
-                gd1 = (vy - dd * y) * inorm;
-                gd2 = (vz - dd * z) * inorm;
-                gm0 += gd0; gm1 += gd1; gm2 += gd2;
-            }
+            sh_grad_one<DEG>(x, y, z, co, v0, v1, v2, want_dir, g_co, gd0, gd1, gd2);
+            gm0 += gd0; gm1 += gd1; gm2 += gd2;
         }
         if (v_dirs != nullptr) { v_dirs[idx * 3] = gd0; v_dirs[idx * 3 + 1] = gd1; v_dirs[idx * 3 + 2] = gd2; }
     }
@@ -232,15 +266,77 @@ __global__ void __launch_bounds__(SB) sh_bwd_kernel(const float* __restrict__ di
     if (v_means != nullptr) { v_means[n * 3] = gm0; v_means[n * 3 + 1] = gm1; v_means[n * 3 + 2] = gm2; }
 }
 
+// Work-list variant; v_coeffs / v_means / v_dirs are zero-filled by the launcher.  One camera: plain stores;
+// several cameras: a Gaussian may be seen more than once, contributions are added atomically.
+template <int DEG>
+__global__ void __launch_bounds__(SB) sh_bwd_vis_kernel(const float* __restrict__ dirs, const float* __restrict__ means,
+                                                        const float* __restrict__ campos,
+                                                        const float* __restrict__ coeffs,
+                                                        const int32_t* __restrict__ vis_ids, long long n_vis,
+                                                        const float* __restrict__ colors,
+                                                        const float* __restrict__ v_colors, int ld_vc, int C, int N,
+                                                        int K, int post, float* __restrict__ v_coeffs,
+                                                        float* __restrict__ v_dirs, float* __restrict__ v_means) {
+    constexpr int NB = (DEG + 1) * (DEG + 1);
+    const long long j = (long long)blockIdx.x * SB + threadIdx.x;
+    if (j >= n_vis) return;
+    const long long idx = vis_ids[j];
+    const int c = (int)(idx / N);
+    const long long n = idx - (long long)c * N;
+    const bool want_dir = (v_dirs != nullptr) || (v_means != nullptr);
+    float v0 = v_colors[idx * ld_vc], v1 = v_colors[idx * ld_vc + 1], v2 = v_colors[idx * ld_vc + 2];
+    if (post) {
+        if (!(colors[idx * 3] > 0.f)) v0 = 0.f;
+        if (!(colors[idx * 3 + 1] > 0.f)) v1 = 0.f;
+        if (!(colors[idx * 3 + 2] > 0.f)) v2 = 0.f;
+    }
+    float g_co[NB * 3];
+#pragma unroll
+    for (int k = 0; k < NB * 3; ++k) g_co[k] = 0.f;
+    float x, y, z, gd0, gd1, gd2;
+    load_dir(dirs, means, campos, idx, n, c, x, y, z);
+    sh_grad_one<DEG>(x, y, z, coeffs + n * (long long)(K * 3), v0, v1, v2, want_dir, g_co, gd0, gd1, gd2);
+    float* out = v_coeffs + n * (long long)(K * 3);
+    if (C == 1) {
+#pragma unroll
+        for (int k = 0; k < NB * 3; ++k) out[k] = g_co[k];
+        if (v_means != nullptr) { v_means[n * 3] = gd0; v_means[n * 3 + 1] = gd1; v_means[n * 3 + 2] = gd2; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < NB * 3; ++k) atomicAdd(out + k, g_co[k]);
+        if (v_means != nullptr) {
+            atomicAdd(v_means + n * 3, gd0); atomicAdd(v_means + n * 3 + 1, gd1); atomicAdd(v_means + n * 3 + 2, gd2);
+        }
+    }
+    if (v_dirs != nullptr) { v_dirs[idx * 3] = gd0; v_dirs[idx * 3 + 1] = gd1; v_dirs[idx * 3 + 2] = gd2; }
+}
+
 }  // namespace
 
 HGS_API int hgs_sh_fwd(int degree, int K, const float* dirs, const float* means, const float* campos,
-                       const float* coeffs, const int32_t* radii, int C, int N, int post, float* colors,
-                       void* stream) {
-    if (degree < 0 || degree > 4 || K < (degree + 1) * (degree + 1) || C <= 0 || N < 0) return HGS_ERR_INVALID_ARG;
+                       const float* coeffs, const int32_t* radii, const int32_t* vis_ids, long long n_vis, int C, int N,
+                       int post, float* colors, void* stream) {
+    if (degree < 0 || degree > 4 || K < (degree + 1) * (degree + 1) || C <= 0 || N < 0 || n_vis < 0) return HGS_ERR_INVALID_ARG;
     if (dirs == nullptr && (means == nullptr || campos == nullptr)) return HGS_ERR_INVALID_ARG;
     if (N == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    if (vis_ids != nullptr) {
+        cudaError_t e = cudaMemsetAsync(colors, 0, (size_t)C * N * 3 * sizeof(float), st);
+        if (e != cudaSuccess) return (int)e;
+        if (n_vis == 0) return 0;
+        const int grid = hgs_ceil_div(n_vis, SB);
+#define LAUNCH(DEG) sh_fwd_vis_kernel<DEG><<<grid, SB, 0, st>>>(dirs, means, campos, coeffs, vis_ids, n_vis, N, K, post, colors);
+        switch (degree) {
+            case 0: LAUNCH(0) break;
+            case 1: LAUNCH(1) break;
+            case 2: LAUNCH(2) break;
+            case 3: LAUNCH(3) break;
+            default: LAUNCH(4) break;
+        }
+#undef LAUNCH
+        HGS_LAUNCH_CHECK();
+        return 0;
+    }
     const int grid = hgs_ceil_div(N, SB);
 #define LAUNCH(DEG) sh_fwd_kernel<DEG><<<grid, SB, 0, st>>>(dirs, means, campos, coeffs, radii, C, N, K, post, colors);
     switch (degree) {
@@ -256,20 +352,39 @@ HGS_API int hgs_sh_fwd(int degree, int K, const float* dirs, const float* means,
 }
 
 HGS_API int hgs_sh_bwd(int degree, int K, const float* dirs, const float* means, const float* campos,
-                       const float* coeffs, const int32_t* radii, const float* colors, const float* v_colors,
-                       int ld_v_colors, int C, int N, int post, float* v_coeffs, float* v_dirs, float* v_means,
-                       void* stream) {
-    if (degree < 0 || degree > 4 || K < (degree + 1) * (degree + 1) || C <= 0 || N < 0 || ld_v_colors < 3)
+                       const float* coeffs, const int32_t* radii, const int32_t* vis_ids, long long n_vis,
+                       const float* colors, const float* v_colors, int ld_v_colors, int C, int N, int post,
+                       float* v_coeffs, float* v_dirs, float* v_means, void* stream) {
+    if (degree < 0 || degree > 4 || K < (degree + 1) * (degree + 1) || C <= 0 || N < 0 || ld_v_colors < 3 || n_vis < 0)
         return HGS_ERR_INVALID_ARG;
     if (dirs == nullptr && (means == nullptr || campos == nullptr)) return HGS_ERR_INVALID_ARG;
     if (post && colors == nullptr) return HGS_ERR_INVALID_ARG;
     if (N == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = hgs_ceil_div(N, SB);
-    {
-        cudaError_t e = cudaMemsetAsync(v_coeffs, 0, (size_t)N * K * 3 * sizeof(float), st);
-        if (e != cudaSuccess) return (int)e;
+    cudaError_t e = cudaMemsetAsync(v_coeffs, 0, (size_t)N * K * 3 * sizeof(float), st);
+    if (e != cudaSuccess) return (int)e;
+    if (vis_ids != nullptr) {
+        if (v_means != nullptr && (e = cudaMemsetAsync(v_means, 0, (size_t)N * 3 * sizeof(float), st)) != cudaSuccess)
+            return (int)e;
+        if (v_dirs != nullptr && (e = cudaMemsetAsync(v_dirs, 0, (size_t)C * N * 3 * sizeof(float), st)) != cudaSuccess)
+            return (int)e;
+        if (n_vis == 0) return 0;
+        const int grid = hgs_ceil_div(n_vis, SB);
+#define LAUNCH(DEG)                                                                                              \
+    sh_bwd_vis_kernel<DEG><<<grid, SB, 0, st>>>(dirs, means, campos, coeffs, vis_ids, n_vis, colors, v_colors,    \
+                                                ld_v_colors, C, N, K, post, v_coeffs, v_dirs, v_means);
+        switch (degree) {
+            case 0: LAUNCH(0) break;
+            case 1: LAUNCH(1) break;
+            case 2: LAUNCH(2) break;
+            case 3: LAUNCH(3) break;
+            default: LAUNCH(4) break;
+        }
+#undef LAUNCH
+        HGS_LAUNCH_CHECK();
+        return 0;
     }
+    const int grid = hgs_ceil_div(N, SB);
 #define LAUNCH(DEG)                                                                                        \
     sh_bwd_kernel<DEG><<<grid, SB, 0, st>>>(dirs, means, campos, coeffs, radii, colors, v_colors, ld_v_colors, C, N, \
                                             K, post, v_coeffs, v_dirs, v_means);

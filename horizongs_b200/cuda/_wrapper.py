@@ -80,8 +80,9 @@ def _n_bits(n: int) -> int:
 class _Project3D(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip,
-                calc_compensations, tile_size):
+                calc_compensations, tile_size, holder):
         L = _lib.lib()
+        ctx.holder = holder       # rendering.py drops the visible-Gaussian work list here once it is known
         C, N = viewmats.shape[0], means.shape[0]
         dev = means.device
         radii = torch.empty((C, N), dtype=torch.int32, device=dev)
@@ -117,13 +118,15 @@ class _Project3D(torch.autograd.Function):
         v_means2d, ld_m = _rows(means.new_zeros((C, N, 2)) if v_means2d is None else v_means2d, 2)
         v_conics, ld_c = _rows(means.new_zeros((C, N, 3)) if v_conics is None else v_conics, 3)
         v_depths, ld_d = _rows(None if v_depths is None else v_depths.unsqueeze(-1), 1)
+        vis = None if ctx.holder is None else ctx.holder.get("vis_ids")
         _mark("project3d_bwd", 0)
         check(L.hgs_project3d_bwd(ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), C, N, width, height,
                                   eps2d, near_plane, far_plane, ptr(radii), ptr(v_means2d), ld_m, ptr(v_depths), ld_d,
-                                  ptr(v_conics), ld_c, ptr(v_means), ptr(v_quats), ptr(v_scales), _stream()),
+                                  ptr(v_conics), ld_c, ptr(vis), 0 if vis is None else vis.numel(), ptr(v_means),
+                                  ptr(v_quats), ptr(v_scales), _stream()),
               "hgs_project3d_bwd")
         _mark("project3d_bwd", 1)
-        return (v_means, v_quats, v_scales) + (None,) * 10
+        return (v_means, v_quats, v_scales) + (None,) * 11
 
 
 def _check_proj_inputs(means, quats, scales, viewmats, Ks):
@@ -138,13 +141,13 @@ def _check_proj_inputs(means, quats, scales, viewmats, Ks):
 
 
 def _project3d(means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip,
-               calc_compensations, tile_size):
+               calc_compensations, tile_size, holder=None):
     _check_proj_inputs(means, quats, scales, viewmats, Ks)
     means, quats, scales = _f32c(means, "means"), _f32c(quats, "quats"), _f32c(scales, "scales")
     viewmats, Ks = _f32c(viewmats.detach(), "viewmats"), _f32c(Ks.detach(), "Ks")
     return _Project3D.apply(means, quats, scales, viewmats, Ks, int(width), int(height), float(eps2d),
                             float(near_plane), float(far_plane), float(radius_clip), bool(calc_compensations),
-                            int(tile_size))
+                            int(tile_size), holder)
 
 
 def fully_fused_projection(
@@ -174,15 +177,17 @@ class _SphericalHarmonics(torch.autograd.Function):
     """colors[C,N,3] from coeffs[N,K,3]; direction either dirs[C,N,3] or means[N,3]-campos[C,3]."""
 
     @staticmethod
-    def forward(ctx, degree, dirs, means, campos, coeffs, radii, post):
+    def forward(ctx, degree, dirs, means, campos, coeffs, radii, post, vis_ids=None):
         L = _lib.lib()
         N, K = coeffs.shape[0], coeffs.shape[1]
         C = dirs.shape[0] if dirs is not None else campos.shape[0]
         colors = torch.empty((C, N, 3), dtype=torch.float32, device=coeffs.device)
         _mark("sh_fwd", 0)
-        check(L.hgs_sh_fwd(degree, K, ptr(dirs), ptr(means), ptr(campos), ptr(coeffs), ptr(radii), C, N, int(post),
-                           ptr(colors), _stream()), "hgs_sh_fwd")
+        check(L.hgs_sh_fwd(degree, K, ptr(dirs), ptr(means), ptr(campos), ptr(coeffs), ptr(radii), ptr(vis_ids),
+                           0 if vis_ids is None else vis_ids.numel(), C, N, int(post), ptr(colors), _stream()),
+              "hgs_sh_fwd")
         _mark("sh_fwd", 1)
+        ctx.vis_ids = vis_ids
         ctx.save_for_backward(dirs, means, campos, coeffs, radii, colors if post else None)
         ctx.cfg = (degree, K, C, N, int(post))
         return colors
@@ -198,12 +203,14 @@ class _SphericalHarmonics(torch.autograd.Function):
         need_means = means is not None and ctx.needs_input_grad[2]
         v_dirs = torch.empty_like(dirs) if need_dirs else None
         v_means = torch.empty_like(means) if need_means else None
+        vis = ctx.vis_ids
         _mark("sh_bwd", 0)
-        check(L.hgs_sh_bwd(degree, K, ptr(dirs), ptr(means), ptr(campos), ptr(coeffs), ptr(radii), ptr(colors),
-                           ptr(v_colors), ld_vc, C, N, post, ptr(v_coeffs), ptr(v_dirs), ptr(v_means), _stream()),
+        check(L.hgs_sh_bwd(degree, K, ptr(dirs), ptr(means), ptr(campos), ptr(coeffs), ptr(radii), ptr(vis),
+                           0 if vis is None else vis.numel(), ptr(colors), ptr(v_colors), ld_vc, C, N, post,
+                           ptr(v_coeffs), ptr(v_dirs), ptr(v_means), _stream()),
               "hgs_sh_bwd")
         _mark("sh_bwd", 1)
-        return None, v_dirs, v_means, None, v_coeffs, None, None
+        return None, v_dirs, v_means, None, v_coeffs, None, None, None
 
 
 def spherical_harmonics(degrees_to_use: int, dirs: Tensor, coeffs: Tensor, masks: Optional[Tensor] = None) -> Tensor:
@@ -226,10 +233,12 @@ def spherical_harmonics(degrees_to_use: int, dirs: Tensor, coeffs: Tensor, masks
     return out[0] if squeeze else out
 
 
-def _sh_view_colors(sh_degree: int, means: Tensor, campos: Tensor, coeffs: Tensor, radii: Tensor) -> Tensor:
-    """fused path used by rasterization*: clamp_min(SH(means - campos) + 0.5, 0), masked by radii > 0."""
+def _sh_view_colors(sh_degree: int, means: Tensor, campos: Tensor, coeffs: Tensor, radii: Tensor,
+                    vis_ids: Optional[Tensor] = None) -> Tensor:
+    """fused path used by rasterization*: clamp_min(SH(means - campos) + 0.5, 0), masked by radii > 0
+    (vis_ids = the work list of visible flat indices, equivalent to the mask but without idle threads)."""
     return _SphericalHarmonics.apply(int(sh_degree), None, _f32c(means, "means"), _f32c(campos, "campos"),
-                                     _f32c(coeffs, "colors"), radii, True)
+                                     _f32c(coeffs, "colors"), radii, True, vis_ids)
 
 
 # =====================================================================================
@@ -243,12 +252,13 @@ def _isect_sorted_from_counts(means2d, radii, depths, tiles_per_gauss, C, N, til
     st = _stream()
     order = torch.empty(CN, dtype=torch.int32, device=dev)
     cum_sorted = torch.empty(CN, dtype=torch.int32, device=dev)
+    vis_ids = torch.empty(CN, dtype=torch.int32, device=dev)
     counts = torch.empty(2, dtype=torch.int64, device=dev)
     _mark("isect_prepare", 0)
     tb = L.hgs_isect_prepare_temp_bytes(CN)
     temp = torch.empty(tb, dtype=torch.uint8, device=dev)
-    check(L.hgs_isect_prepare(ptr(depths), ptr(tiles_per_gauss), C, N, ptr(order), ptr(cum_sorted), ptr(counts),
-                              ptr(temp), tb, st), "hgs_isect_prepare")
+    check(L.hgs_isect_prepare(ptr(depths), ptr(tiles_per_gauss), C, N, ptr(order), ptr(cum_sorted), ptr(vis_ids),
+                              ptr(counts), ptr(temp), tb, st), "hgs_isect_prepare")
     _mark("isect_prepare", 1)
     n_visible, n_isects = counts.tolist()  # the one unavoidable host read: sizes the intersection arrays
     _mark("isect_sorted", 0)
@@ -263,7 +273,7 @@ def _isect_sorted_from_counts(means2d, radii, depths, tiles_per_gauss, C, N, til
                              n_isects, tile_size, tile_width, tile_height, ptr(isect_ids), ptr(flatten_ids), ptr(offsets),
                              ptr(temp2), tb2, st), "hgs_isect_sorted")
     _mark("isect_sorted", 1)
-    return isect_ids, flatten_ids, offsets
+    return isect_ids, flatten_ids, offsets, vis_ids[:n_visible]
 
 
 @torch.no_grad()
@@ -285,7 +295,7 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, 
     check(L.hgs_isect_count(ptr(means2d), ptr(radii), C * N, tile_size, tile_width, tile_height, ptr(tiles), st),
           "hgs_isect_count")
     if sort:
-        isect_ids, flatten_ids, offsets = _isect_sorted_from_counts(
+        isect_ids, flatten_ids, offsets, _ = _isect_sorted_from_counts(
             means2d, radii, depths, tiles, C, N, tile_size, tile_width, tile_height)
         if _with_offsets:
             return tiles, isect_ids, flatten_ids, offsets
@@ -324,7 +334,7 @@ class _Blend3D(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means2d, conics, colors, depths, opacities, backgrounds, width, height, tile_size,
-                isect_offsets, flatten_ids, absgrad, radii, normalize_depth):
+                isect_offsets, flatten_ids, absgrad, radii, normalize_depth, vis_ids=None):
         L = _lib.lib()
         C, N = opacities.shape
         CH = colors.shape[-1]
@@ -341,7 +351,8 @@ class _Blend3D(torch.autograd.Function):
             records = torch.empty(L.hgs_blend3d_pack_bytes(C * N), dtype=torch.uint8, device=dev)
             _mark("blend3d_pack", 0)
             check(L.hgs_blend3d_pack(ptr(means2d), ptr(conics), ptr(colors), ptr(depths), ptr(opacities), ptr(radii),
-                                     C * N, CH, ptr(records), st), "hgs_blend3d_pack")
+                                     ptr(vis_ids), 0 if vis_ids is None else vis_ids.numel(), C * N, CH, ptr(records),
+                                     st), "hgs_blend3d_pack")
             _mark("blend3d_pack", 1)
             _mark("blend3d_fwd", 0)
             check(L.hgs_blend3d_fwd_packed(ptr(records), ptr(backgrounds), C, D, int(normalize_depth), width, height,
@@ -369,7 +380,7 @@ class _Blend3D(torch.autograd.Function):
         L = _lib.lib()
         v_render_colors = v_render_colors.contiguous()
         v_render_alphas = v_render_alphas.contiguous()
-        tail = (None,) * 8
+        tail = (None,) * 9
         if ctx.fast:
             records, backgrounds, isect_offsets, flatten_ids, render_colors, render_alphas, last_ids = ctx.saved_tensors
             (C, N, _), has_depth = ctx.shapes
@@ -414,7 +425,7 @@ class _Blend3D(torch.autograd.Function):
 
 
 def _blend3d(means2d, conics, colors, depths, opacities, backgrounds, width, height, tile_size, isect_offsets,
-             flatten_ids, absgrad=False, radii=None, normalize_depth=False):
+             flatten_ids, absgrad=False, radii=None, normalize_depth=False, vis_ids=None):
     if tile_size not in _TILE_SIZES:
         raise NotImplementedError(f"tile_size {tile_size} is not supported (supported: {_TILE_SIZES})")
     D = colors.shape[-1] + (1 if depths is not None else 0)
@@ -423,7 +434,7 @@ def _blend3d(means2d, conics, colors, depths, opacities, backgrounds, width, hei
     return _Blend3D.apply(_f32c(means2d, "means2d"), _f32c(conics, "conics"), _f32c(colors, "colors"),
                           _f32c(depths, "depths"), _f32c(opacities, "opacities"), _f32c(backgrounds, "backgrounds"),
                           int(width), int(height), int(tile_size), isect_offsets.contiguous(),
-                          flatten_ids.contiguous(), bool(absgrad), radii, bool(normalize_depth))
+                          flatten_ids.contiguous(), bool(absgrad), radii, bool(normalize_depth), vis_ids)
 
 
 def rasterize_to_pixels(means2d: Tensor, conics: Tensor, colors: Tensor, opacities: Tensor, image_width: int,
@@ -618,7 +629,8 @@ def blend3d_pair_stats(means2d, conics, opacities, radii, width, height, tile_si
     dummy = torch.zeros((C, N, 1), dtype=torch.float32, device=dev)
     st = _stream()
     check(L.hgs_blend3d_pack(ptr(means2d.contiguous()), ptr(conics.contiguous()), ptr(dummy), None,
-                             ptr(opacities.contiguous()), ptr(radii), C * N, 1, ptr(records), st), "hgs_blend3d_pack")
+                             ptr(opacities.contiguous()), ptr(radii), None, 0, C * N, 1, ptr(records), st),
+          "hgs_blend3d_pack")
     counters = torch.zeros(2, dtype=torch.int64, device=dev)
     check(L.hgs_blend3d_stats(ptr(records), C, int(width), int(height), int(tile_size), ptr(isect_offsets),
                               ptr(flatten_ids), flatten_ids.numel(), ptr(counters), st), "hgs_blend3d_stats")
@@ -628,15 +640,18 @@ def blend3d_pair_stats(means2d, conics, opacities, radii, width, height, tile_si
 
 @torch.no_grad()
 def densification_stats_update(means2d_grad: Tensor, radii: Tensor, width: int, height: int, grad_accum: Tensor,
-                               denom: Tensor, max_radii: Optional[Tensor] = None, mode: str = "mean") -> None:
+                               denom: Tensor, max_radii: Optional[Tensor] = None, mode: str = "mean",
+                               visible_ids: Optional[Tensor] = None) -> None:
     """In-place update of the densification accumulators from one rendered batch of views
     (scene/basic_model.py:96-144): grad_accum[N] (+= or max= the scaled view-space gradient norm),
-    denom[N] (+= views that saw the Gaussian), max_radii[N] (optional)."""
+    denom[N] (+= views that saw the Gaussian), max_radii[N] (optional).  visible_ids = meta["visible_ids"] of the
+    rasterization call (optional work list; same result, no idle threads)."""
     assert mode in ("mean", "max")
     L = _lib.lib()
     C, N = radii.shape
     g, ld = _rows(means2d_grad, 2)
     assert grad_accum.is_contiguous() and denom.is_contiguous() and grad_accum.numel() == N and denom.numel() == N
-    check(L.hgs_densify_stats(ptr(g), ld, ptr(radii.contiguous()), C, N, int(width), int(height),
+    check(L.hgs_densify_stats(ptr(g), ld, ptr(radii.contiguous()), ptr(visible_ids),
+                              0 if visible_ids is None else visible_ids.numel(), C, N, int(width), int(height),
                               1 if mode == "max" else 0, ptr(grad_accum), ptr(denom), ptr(max_radii), _stream()),
           "hgs_densify_stats")

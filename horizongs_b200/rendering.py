@@ -49,13 +49,13 @@ def _validate(means, quats, scales, opacities, colors, viewmats, Ks, render_mode
     return C, N
 
 
-def _per_view_features(means, colors, viewmats, radii, sh_degree, C):
+def _per_view_features(means, colors, viewmats, radii, sh_degree, C, vis_ids=None):
     """-> [C,N,CH] colour features for blending (CH = 3 for SH)."""
     if sh_degree is None:
         if colors.dim() == 2:
             return colors[None] if C == 1 else colors[None].expand(C, -1, -1)
         return colors
-    return W._sh_view_colors(sh_degree, means, _camera_positions(viewmats), colors, radii)
+    return W._sh_view_colors(sh_degree, means, _camera_positions(viewmats), colors, radii, vis_ids)
 
 
 def _mode_features(feats, depths, backgrounds, render_mode):
@@ -93,24 +93,26 @@ def rasterization(
     tile_width = math.ceil(width / float(tile_size))
     tile_height = math.ceil(height / float(tile_size))
 
+    holder: Dict = {}
     radii, means2d, depths, conics, comps, tiles_per_gauss = W._project3d(
         means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip,
-        rasterize_mode == "antialiased", tile_size)
+        rasterize_mode == "antialiased", tile_size, holder)
     opac = opacities[None] if C == 1 else opacities[None].expand(C, -1)
     if comps is not None:
         opac = opac * comps
 
     with torch.no_grad():
-        isect_ids, flatten_ids, isect_offsets = W._isect_sorted_from_counts(
+        isect_ids, flatten_ids, isect_offsets, vis_ids = W._isect_sorted_from_counts(
             means2d, radii, depths, tiles_per_gauss, C, N, tile_size, tile_width, tile_height)
+    holder["vis_ids"] = vis_ids          # work list for the backward of the projection
 
-    feats = _per_view_features(means, colors, viewmats, radii, sh_degree, C)
+    feats = _per_view_features(means, colors, viewmats, radii, sh_degree, C, vis_ids)
     feats, depth_ch, bgs = _mode_features(feats, depths, backgrounds, render_mode)
     n_ch = feats.shape[-1] + (1 if depth_ch is not None else 0)
     fuse_norm = render_mode in ("ED", "RGB+ED") and n_ch <= 4 and not absgrad
     render_colors, render_alphas = W._blend3d(means2d, conics, feats, depth_ch, opac, bgs, width, height, tile_size,
                                               isect_offsets, flatten_ids, absgrad, radii=radii,
-                                              normalize_depth=fuse_norm)
+                                              normalize_depth=fuse_norm, vis_ids=vis_ids)
     if render_mode in ("ED", "RGB+ED") and not fuse_norm:
         render_colors = torch.cat(
             [render_colors[..., :-1], render_colors[..., -1:] / render_alphas.clamp(min=1e-10)], dim=-1)
@@ -120,6 +122,7 @@ def rasterization(
         "conics": conics, "opacities": opac, "tile_width": tile_width, "tile_height": tile_height,
         "tiles_per_gauss": tiles_per_gauss, "isect_ids": isect_ids, "flatten_ids": flatten_ids,
         "isect_offsets": isect_offsets, "width": width, "height": height, "tile_size": tile_size, "n_cameras": C,
+        "visible_ids": vis_ids,
     }
     return render_colors, render_alphas, meta
 
@@ -190,10 +193,10 @@ def rasterization_2dgs(
     opac = opacities[None] if C == 1 else opacities[None].expand(C, -1)
 
     with torch.no_grad():
-        isect_ids, flatten_ids, isect_offsets = W._isect_sorted_from_counts(
+        isect_ids, flatten_ids, isect_offsets, vis_ids = W._isect_sorted_from_counts(
             means2d, radii, depths, tiles_per_gauss, C, N, tile_size, tile_width, tile_height)
 
-    feats = _per_view_features(means, colors, viewmats, radii, sh_degree, C)
+    feats = _per_view_features(means, colors, viewmats, radii, sh_degree, C, vis_ids)
     feats, depth_ch, bgs = _mode_features(feats, depths, backgrounds, render_mode)
 
     grad_on = torch.is_grad_enabled() and means2d.requires_grad
@@ -222,6 +225,7 @@ def rasterization_2dgs(
         "tile_height": tile_height, "tiles_per_gauss": tiles_per_gauss, "isect_ids": isect_ids,
         "flatten_ids": flatten_ids, "isect_offsets": isect_offsets, "width": width, "height": height,
         "tile_size": tile_size, "n_cameras": C, "render_distort": render_distort, "gradient_2dgs": densify,
+        "visible_ids": vis_ids,
     }
     return (render_colors, render_alphas, render_normals, render_normals_from_depth, render_distort,
             render_median), meta

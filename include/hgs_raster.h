@@ -50,12 +50,15 @@ int hgs_project3d_fwd(const float* means, const float* quats, const float* scale
                       float* depths, float* conics, float* compensations, int32_t* tiles_per_gauss, void* stream);
 /* in: upstream gradients v_means2d[C,N,2], v_depths[C,N] (or NULL), v_conics[C,N,3]; each with a row
  * stride in floats (ld_* = 2, 1, 3 when dense) so that slices of the packed blend-gradient buffer can be
- * passed without a copy;  out (overwritten, summed over cameras): v_means[N,3], v_quats[N,4], v_scales[N,3]. */
+ * passed without a copy;  out (overwritten, summed over cameras): v_means[N,3], v_quats[N,4], v_scales[N,3].
+ * vis_ids (or NULL): work list of the n_vis visible flat indices c*N+n from hgs_isect_prepare -- one thread per
+ * visible pair instead of one per Gaussian (same results; with C > 1 the sums over cameras use atomics). */
 int hgs_project3d_bwd(const float* means, const float* quats, const float* scales, const float* viewmats,
                       const float* Ks, int C, int N, int width, int height, float eps2d, float near_plane,
                       float far_plane, const int32_t* radii, const float* v_means2d, int ld_means2d,
-                      const float* v_depths, int ld_depths, const float* v_conics, int ld_conics, float* v_means,
-                      float* v_quats, float* v_scales, void* stream);
+                      const float* v_depths, int ld_depths, const float* v_conics, int ld_conics,
+                      const int32_t* vis_ids, long long n_vis, float* v_means, float* v_quats, float* v_scales,
+                      void* stream);
 
 /* ---- a4: fully_fused_projection_2dgs (render.py:171-186; inside rasterization_2dgs render.py:62) --
  * out: radii[C,N], means2d[C,N,2], depths[C,N], ray_transforms[C,N,3,3] (rows M0,M1,M2 of (K [R|t] H)),
@@ -73,15 +76,18 @@ int hgs_project2d_bwd(const float* means, const float* quats, const float* scale
 /* ---- a7: spherical_harmonics (inside rasterization* when sh_degree is not None) ------------------
  * Direction of Gaussian n for camera c is dirs[c,n,:] if dirs != NULL, else means[n,:] - campos[c,:]
  * (normalised inside).  coeffs[N,K,3] is shared by all cameras.  radii (or NULL) masks culled rows to 0.
- * post != 0 fuses gsplat's `clamp_min(colors + 0.5, 0)`.  out: colors[C,N,3]. */
+ * post != 0 fuses gsplat's `clamp_min(colors + 0.5, 0)`.  out: colors[C,N,3].
+ * vis_ids (or NULL) = work list of visible flat indices (then radii is not read). */
 int hgs_sh_fwd(int degree, int K, const float* dirs, const float* means, const float* campos, const float* coeffs,
-               const int32_t* radii, int C, int N, int post, float* colors, void* stream);
+               const int32_t* radii, const int32_t* vis_ids, long long n_vis, int C, int N, int post, float* colors,
+               void* stream);
 /* out (overwritten): v_coeffs[N,K,3] summed over cameras; v_dirs[C,N,3] or NULL; v_means[N,3] or NULL
  * (direction gradient summed over cameras).  `colors` is the forward output (needed for the clamp mask
  * when post != 0).  ld_v_colors = row stride of v_colors in floats (3 when dense). */
 int hgs_sh_bwd(int degree, int K, const float* dirs, const float* means, const float* campos, const float* coeffs,
-               const int32_t* radii, const float* colors, const float* v_colors, int ld_v_colors, int C, int N,
-               int post, float* v_coeffs, float* v_dirs, float* v_means, void* stream);
+               const int32_t* radii, const int32_t* vis_ids, long long n_vis, const float* colors,
+               const float* v_colors, int ld_v_colors, int C, int N, int post, float* v_coeffs, float* v_dirs,
+               float* v_means, void* stream);
 
 /* ---- a8-a10: tile intersection, tile|depth key sort, per-tile ranges (integer, bit-exact) --------
  * key = cam << (32 + tile_bits) | tile_id << 32 | (int64)(int32 bits of depth), value = flat index;
@@ -103,9 +109,12 @@ int hgs_isect_emit(const float* means2d, const int32_t* radii, const float* dept
 /* Sorted path, phase 1 (no host round trip): compact the Gaussians with tiles_per_gauss > 0, depth-order them
  * (stable LSD radix sort of the depth bits, camera-major), gather their tile counts in that order and scan.
  * out: order[<= CN] i32 (flat indices of the n_vis visible Gaussians in (cam, depth, index) order),
- * cum_sorted[<= CN] i32 (exclusive scan of their tile counts), counts_dev[0] = n_vis, counts_dev[1] = I. */
+ * cum_sorted[<= CN] i32 (exclusive scan of their tile counts), visible_ids[<= CN] i32 or NULL (the same
+ * flat indices in ascending order: the work list of the per-Gaussian kernels that only touch visible
+ * Gaussians), counts_dev[0] = n_vis, counts_dev[1] = I. */
 int hgs_isect_prepare(const float* depths, const int32_t* tiles_per_gauss, int C, int N, int32_t* order,
-                      int32_t* cum_sorted, long long* counts_dev, void* temp, size_t temp_bytes, void* stream);
+                      int32_t* cum_sorted, int32_t* visible_ids, long long* counts_dev, void* temp,
+                      size_t temp_bytes, void* stream);
 /* Sorted path, phase 2 (n_visible and n_isects read back by the caller to size the outputs): emit
  * (tile key, flat index) pairs in depth order -- one thread per intersection -- stable-partition them by
  * (cam, tile) with LSD radix passes over the tile bits only, then write the final arrays.
@@ -148,7 +157,8 @@ int hgs_blend3d_bwd(const float* means2d, const float* conics, const float* colo
  *   [0:2] v_means2d, [2:5] v_conics, [5] v_opacities, [8:8+D] v_colors (+ v_depths in the last channel). */
 size_t hgs_blend3d_pack_bytes(long long CN);
 int hgs_blend3d_pack(const float* means2d, const float* conics, const float* colors, const float* depths,
-                     const float* opacities, const int32_t* radii, long long CN, int CH, void* records, void* stream);
+                     const float* opacities, const int32_t* radii, const int32_t* vis_ids, long long n_vis,
+                     long long CN, int CH, void* records, void* stream);
 int hgs_blend3d_fwd_packed(const void* records, const float* backgrounds, int C, int D, int normalize_depth,
                            int width, int height, int tile_size, const int32_t* isect_offsets,
                            const int32_t* flatten_ids, long long n_isects, float* render_colors,
@@ -190,8 +200,9 @@ int hgs_blend2d_bwd(const float* means2d, const float* ray_transforms, const flo
  * Gaussians with radii > 0 in a view, grad_accum[n] += (mode_max ? max : sum) of ||v_means2d * (W/2, H/2)||,
  * denom[n] += number of views that saw n, max_radii[n] = max(max_radii[n], radii) (or NULL).
  * v_means2d[C,N,2] with row stride ld_means2d floats. */
-int hgs_densify_stats(const float* v_means2d, int ld_means2d, const int32_t* radii, int C, int N, int width,
-                      int height, int mode_max, float* grad_accum, float* denom, float* max_radii, void* stream);
+int hgs_densify_stats(const float* v_means2d, int ld_means2d, const int32_t* radii, const int32_t* vis_ids,
+                      long long n_vis, int C, int N, int width, int height, int mode_max, float* grad_accum,
+                      float* denom, float* max_radii, void* stream);
 
 #ifdef __cplusplus
 }

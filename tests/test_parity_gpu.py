@@ -321,3 +321,9 @@ def test_densification_stats_fused(mode):
     W.densification_stats_update(grad.cuda(), radii.cuda(), Wd, H, cacc, cden, cmax, mode=mode)
     assert torch.allclose(cacc.cpu(), acc, rtol=1e-5, atol=1e-5) and torch.equal(cden.cpu(), den)
     assert torch.equal(cmax.cpu(), radii.max(0).values.float())
+    # work-list variant (meta["visible_ids"]): same numbers (atomics when a Gaussian is seen by several views)
+    vis_ids = torch.nonzero(radii.flatten() > 0).flatten().int().cuda()
+    cacc2, cden2, cmax2 = acc0.cuda(), den0.cuda(), torch.zeros(N).cuda()
+    W.densification_stats_update(grad.cuda(), radii.cuda(), Wd, H, cacc2, cden2, cmax2, mode=mode, visible_ids=vis_ids)
+    assert torch.allclose(cacc2.cpu(), acc, rtol=1e-5, atol=1e-5) and torch.equal(cden2.cpu(), den)
+    assert torch.equal(cmax2, cmax)

@@ -41,7 +41,7 @@ def run(name, sc, V, Ks, Wd, H):
     res["project_fwd_ms"] = t
     radii, m2, d, con, _, tiles = proj
     res["n_visible"] = int((radii > 0).sum())
-    (ids, flat, off), t = timed(lambda: W._isect_sorted_from_counts(m2, radii, d, tiles, C, N, 16, tw, th))
+    (ids, flat, off, vis_ids), t = timed(lambda: W._isect_sorted_from_counts(m2, radii, d, tiles, C, N, 16, tw, th))
     res["isect_sort_ms"] = t
     res["I"] = int(ids.numel())
     res["max_tile_depth"] = int((torch.diff(torch.cat([off.flatten(), off.new_tensor([ids.numel()])]))).max())
