@@ -295,6 +295,13 @@ def run_ours(args):
         else:
             stage_ms.setdefault(name, []).append(opened.pop(name).elapsed_time(ev))
     stage_avg = {k: sum(v) / len(v) for k, v in stage_ms.items()}
+    # per-view split of the two blend kernels (step s of the timed loop renders view (rank + warmup + s) % 8)
+    stage_by_view = {}
+    for k in ("blend3d_fwd", "blend3d_bwd", "isect_sorted"):
+        per = {}
+        for i, t in enumerate(stage_ms.get(k, [])):
+            per.setdefault((rank + args.warmup + i) % N_VIEWS, []).append(t)
+        stage_by_view[k] = {str(v): round(sum(ts) / len(ts), 4) for v, ts in sorted(per.items())}
     # ---- e2e: host buffers, H2D of camera + ground truth and D2H of the loss inside the timed region
     for s in range(2):
         step(s, e2e=True)
@@ -400,7 +407,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "render_fps": fps,
         "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline,
-        "stage_ms": stage_avg,
+        "stage_ms": stage_avg, "stage_ms_by_view": stage_by_view,
         "counts": {"mean_n_visible": mean("n_visible"), "mean_I": mean("I"), "mean_P_eval": mean("P_eval"),
                    "mean_P_blend": mean("P_blend"), "per_view": counts},
         "frame_budget": {"ms_per_view": ms_total / n_steps, "within_33.3ms": ms_total / n_steps < 33.3,

@@ -30,6 +30,10 @@ struct Proj3dFwd {
     float m2x, m2y;
 };
 
+__device__ __forceinline__ void proj3d_cov_and_project(const HgsCam& cam, float qw, float qx, float qy, float qz,
+                                                       float s0, float s1, float s2, float W, float H, float eps2d,
+                                                       Proj3dFwd& o);
+
 // forward math shared by fwd and bwd kernels. returns false when culled by z.
 __device__ __forceinline__ bool proj3d_math(const HgsCam& cam, float px, float py, float pz, float qw, float qx, float qy,
                                             float qz, float s0, float s1, float s2, float W, float H, float eps2d,
@@ -39,7 +43,32 @@ __device__ __forceinline__ bool proj3d_math(const HgsCam& cam, float px, float p
     if (o.zc < near_plane || o.zc > far_plane) return false;
     o.xc = R[0][0] * px + R[0][1] * py + R[0][2] * pz + cam.t[0];
     o.yc = R[1][0] * px + R[1][1] * py + R[1][2] * pz + cam.t[1];
+    proj3d_cov_and_project(cam, qw, qx, qy, qz, s0, s1, s2, W, H, eps2d, o);
+    return true;
+}
 
+// Conservative early frustum test on the camera-space centre alone: an upper bound of the integer radius
+// from ||J||_F^2 * max(scale)^2 (lambda_max of J Sigma J^T <= ||J||_F^2 lambda_max(Sigma)), the tan-fov clamp
+// bounds of J, eps2d and the 0.01 eigenvalue floor.  true => the full computation would cull the Gaussian by
+// its screen-bounds test, so the covariance math (and the quaternion load) can be skipped with identical output.
+__device__ __forceinline__ bool proj3d_surely_offscreen(const HgsCam& cam, float xc, float yc, float zc, float smax,
+                                                        float W, float H, float eps2d) {
+    const float fx = cam.fx, fy = cam.fy, cx = cam.cx, cy = cam.cy;
+    const float rz = 1.0f / zc;
+    const float tan_fovx = 0.5f * W / fx, tan_fovy = 0.5f * H / fy;
+    const float Lx = fmaxf((W - cx) / fx, cx / fx) + HGS_FOV_MARGIN * tan_fovx;
+    const float Ly = fmaxf((H - cy) / fy, cy / fy) + HGS_FOV_MARGIN * tan_fovy;
+    const float jf2 = rz * rz * (fx * fx * (1.0f + Lx * Lx) + fy * fy * (1.0f + Ly * Ly));
+    const float v1_bound = jf2 * smax * smax + eps2d + 0.1f + HGS_EIG_FLOOR;
+    const float rb = (HGS_RADIUS_SIGMA * sqrtf(v1_bound) + 1.0f) * 1.001f + 0.01f;
+    const float m2x = fx * xc * rz + cx, m2y = fy * yc * rz + cy;
+    return (m2x + rb < 0.f) || (m2x - rb > W) || (m2y + rb < 0.f) || (m2y - rb > H);
+}
+
+__device__ __forceinline__ void proj3d_cov_and_project(const HgsCam& cam, float qw, float qx, float qy, float qz,
+                                                       float s0, float s1, float s2, float W, float H, float eps2d,
+                                                       Proj3dFwd& o) {
+    const float (*R)[3] = cam.R;
     hgs_quat_to_rot(qw, qx, qy, qz, o.q, &o.inv_norm, o.qn);
     const float s[3] = {s0, s1, s2};
 #pragma unroll
@@ -100,7 +129,6 @@ __device__ __forceinline__ bool proj3d_math(const HgsCam& cam, float px, float p
     c11 = c11 + eps2d;
     o.det = c00 * c11 - c01 * c01;
     o.c00 = c00; o.c01 = c01; o.c11 = c11;
-    return true;
 }
 
 __global__ void __launch_bounds__(PB) project3d_fwd_kernel(
@@ -122,11 +150,22 @@ __global__ void __launch_bounds__(PB) project3d_fwd_kernel(
     int radius_i = 0, ntiles = 0;
     float o_m2x = 0.f, o_m2y = 0.f, o_depth = 0.f, o_ca = 0.f, o_cb = 0.f, o_cc = 0.f, o_comp = 0.f;
     if (n < N) {
-        const float4 qv = reinterpret_cast<const float4*>(quats)[n];
         Proj3dFwd f;
-        bool ok = proj3d_math(cam, s_a[threadIdx.x * 3 + 0], s_a[threadIdx.x * 3 + 1], s_a[threadIdx.x * 3 + 2], qv.x,
-                              qv.y, qv.z, qv.w, s_b[threadIdx.x * 3 + 0], s_b[threadIdx.x * 3 + 1],
-                              s_b[threadIdx.x * 3 + 2], (float)W, (float)H, eps2d, near_plane, far_plane, f);
+        const float px = s_a[threadIdx.x * 3 + 0], py = s_a[threadIdx.x * 3 + 1], pz = s_a[threadIdx.x * 3 + 2];
+        const float s0 = s_b[threadIdx.x * 3 + 0], s1 = s_b[threadIdx.x * 3 + 1], s2 = s_b[threadIdx.x * 3 + 2];
+        const float (*R)[3] = cam.R;
+        f.zc = R[2][0] * px + R[2][1] * py + R[2][2] * pz + cam.t[2];
+        bool ok = !(f.zc < near_plane || f.zc > far_plane);
+        if (ok) {
+            f.xc = R[0][0] * px + R[0][1] * py + R[0][2] * pz + cam.t[0];
+            f.yc = R[1][0] * px + R[1][1] * py + R[1][2] * pz + cam.t[1];
+            ok = !proj3d_surely_offscreen(cam, f.xc, f.yc, f.zc, fmaxf(fabsf(s0), fmaxf(fabsf(s1), fabsf(s2))),
+                                          (float)W, (float)H, eps2d);
+        }
+        if (ok) {
+            const float4 qv = reinterpret_cast<const float4*>(quats)[n];
+            proj3d_cov_and_project(cam, qv.x, qv.y, qv.z, qv.w, s0, s1, s2, (float)W, (float)H, eps2d, f);
+        }
         if (ok && f.det > 0.f) {
             float inv_det = 1.0f / f.det;
             float b = 0.5f * (f.c00 + f.c11);

@@ -266,49 +266,91 @@ __global__ void __launch_bounds__(SB) sh_bwd_kernel(const float* __restrict__ di
     if (v_means != nullptr) { v_means[n * 3] = gm0; v_means[n * 3 + 1] = gm1; v_means[n * 3 + 2] = gm2; }
 }
 
-// Work-list variant; v_coeffs / v_means / v_dirs are zero-filled by the launcher.  One camera: plain stores;
-// several cameras: a Gaussian may be seen more than once, contributions are added atomically.
+// Fused dense variant used by the rasterization path (radii given): a block owns SB consecutive coefficient
+// rows and writes ALL of them with coalesced stores (zeros for culled Gaussians, so no separate memset pass);
+// the visible rows of the block are compacted first so that the gradient math runs on densely populated warps
+// even when only ~10 % of the Gaussians are visible.  Sums over cameras are taken in-thread (deterministic).
 template <int DEG>
-__global__ void __launch_bounds__(SB) sh_bwd_vis_kernel(const float* __restrict__ dirs, const float* __restrict__ means,
-                                                        const float* __restrict__ campos,
-                                                        const float* __restrict__ coeffs,
-                                                        const int32_t* __restrict__ vis_ids, long long n_vis,
-                                                        const float* __restrict__ colors,
-                                                        const float* __restrict__ v_colors, int ld_vc, int C, int N,
-                                                        int K, int post, float* __restrict__ v_coeffs,
-                                                        float* __restrict__ v_dirs, float* __restrict__ v_means) {
+__global__ void __launch_bounds__(SB) sh_bwd_fused_kernel(const float* __restrict__ means,
+                                                          const float* __restrict__ campos,
+                                                          const float* __restrict__ coeffs,
+                                                          const int32_t* __restrict__ radii,
+                                                          const float* __restrict__ colors,
+                                                          const float* __restrict__ v_colors, int ld_vc, int C, int N,
+                                                          int K, int post, float* __restrict__ v_coeffs,
+                                                          float* __restrict__ v_means) {
     constexpr int NB = (DEG + 1) * (DEG + 1);
-    const long long j = (long long)blockIdx.x * SB + threadIdx.x;
-    if (j >= n_vis) return;
-    const long long idx = vis_ids[j];
-    const int c = (int)(idx / N);
-    const long long n = idx - (long long)c * N;
-    const bool want_dir = (v_dirs != nullptr) || (v_means != nullptr);
-    float v0 = v_colors[idx * ld_vc], v1 = v_colors[idx * ld_vc + 1], v2 = v_colors[idx * ld_vc + 2];
-    if (post) {
-        if (!(colors[idx * 3] > 0.f)) v0 = 0.f;
-        if (!(colors[idx * 3 + 1] > 0.f)) v1 = 0.f;
-        if (!(colors[idx * 3 + 2] > 0.f)) v2 = 0.f;
+    constexpr int RL = NB * 3;                 // used floats per row
+    extern __shared__ float s_rows[];          // [SB][RL | 1] gradient rows of the visible Gaussians
+    __shared__ int s_list[SB];                 // compacted local row indices
+    __shared__ int s_slot[SB];                 // local row -> slot in s_rows (-1 = culled)
+    __shared__ int s_wcnt[SB / 32];
+    constexpr int RS = RL | 1;
+    const long long base = (long long)blockIdx.x * SB;
+    const long long n = base + threadIdx.x;
+    bool vis = false;
+    if (n < N)
+        for (int c = 0; c < C; ++c) vis |= radii[(long long)c * N + n] > 0;
+    // block compaction (order preserving)
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, vis);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_wcnt[warp] = __popc(bal);
+    __syncthreads();
+    int wbase = 0, n_vis = 0;
+#pragma unroll
+    for (int w = 0; w < SB / 32; ++w) {
+        if (w < warp) wbase += s_wcnt[w];
+        n_vis += s_wcnt[w];
     }
-    float g_co[NB * 3];
+    const int slot = wbase + __popc(bal & ((1u << lane) - 1u));
+    s_slot[threadIdx.x] = vis ? slot : -1;
+    if (vis) s_list[slot] = threadIdx.x;
+    __syncthreads();
+    const int rowlen = K * 3;
+    long long rows = N - base;
+    if (rows > SB) rows = SB;
+    if (n_vis > 0) {
+        // thread j < n_vis handles the j-th visible Gaussian of the block
+        float gm0 = 0.f, gm1 = 0.f, gm2 = 0.f;
+        if (threadIdx.x < n_vis) {
+            const int r = s_list[threadIdx.x];
+            const long long nn = base + r;
+            const float* co = coeffs + nn * (long long)rowlen;
+            float g_co[RL];
 #pragma unroll
-    for (int k = 0; k < NB * 3; ++k) g_co[k] = 0.f;
-    float x, y, z, gd0, gd1, gd2;
-    load_dir(dirs, means, campos, idx, n, c, x, y, z);
-    sh_grad_one<DEG>(x, y, z, coeffs + n * (long long)(K * 3), v0, v1, v2, want_dir, g_co, gd0, gd1, gd2);
-    float* out = v_coeffs + n * (long long)(K * 3);
-    if (C == 1) {
+            for (int k = 0; k < RL; ++k) g_co[k] = 0.f;
+            for (int c = 0; c < C; ++c) {
+                const long long idx = (long long)c * N + nn;
+                if (radii[idx] <= 0) continue;
+                float v0 = v_colors[idx * ld_vc], v1 = v_colors[idx * ld_vc + 1], v2 = v_colors[idx * ld_vc + 2];
+                if (post) {
+                    if (!(colors[idx * 3] > 0.f)) v0 = 0.f;
+                    if (!(colors[idx * 3 + 1] > 0.f)) v1 = 0.f;
+                    if (!(colors[idx * 3 + 2] > 0.f)) v2 = 0.f;
+                }
+                const float x = means[nn * 3] - campos[c * 3], y = means[nn * 3 + 1] - campos[c * 3 + 1],
+                            z = means[nn * 3 + 2] - campos[c * 3 + 2];
+                float gd0, gd1, gd2;
+                sh_grad_one<DEG>(x, y, z, co, v0, v1, v2, v_means != nullptr, g_co, gd0, gd1, gd2);
+                gm0 += gd0; gm1 += gd1; gm2 += gd2;
+            }
+            float* out = s_rows + threadIdx.x * RS;
 #pragma unroll
-        for (int k = 0; k < NB * 3; ++k) out[k] = g_co[k];
-        if (v_means != nullptr) { v_means[n * 3] = gd0; v_means[n * 3 + 1] = gd1; v_means[n * 3 + 2] = gd2; }
-    } else {
-#pragma unroll
-        for (int k = 0; k < NB * 3; ++k) atomicAdd(out + k, g_co[k]);
-        if (v_means != nullptr) {
-            atomicAdd(v_means + n * 3, gd0); atomicAdd(v_means + n * 3 + 1, gd1); atomicAdd(v_means + n * 3 + 2, gd2);
+            for (int k = 0; k < RL; ++k) out[k] = g_co[k];
+            if (v_means != nullptr) { v_means[nn * 3] = gm0; v_means[nn * 3 + 1] = gm1; v_means[nn * 3 + 2] = gm2; }
         }
+        __syncthreads();
     }
-    if (v_dirs != nullptr) { v_dirs[idx * 3] = gd0; v_dirs[idx * 3 + 1] = gd1; v_dirs[idx * 3 + 2] = gd2; }
+    // coalesced write of all rows of the block
+    float* dst = v_coeffs + base * rowlen;
+    const long long tot = rows * rowlen;
+    for (long long i = threadIdx.x; i < tot; i += SB) {
+        const int r = (int)(i / rowlen), c = (int)(i - (long long)r * rowlen);
+        const int sl = s_slot[r];
+        dst[i] = (sl >= 0 && c < RL) ? s_rows[sl * RS + c] : 0.f;
+    }
+    // culled Gaussians: zero direction gradient
+    if (v_means != nullptr && n < N && !vis) { v_means[n * 3] = 0.f; v_means[n * 3 + 1] = 0.f; v_means[n * 3 + 2] = 0.f; }
 }
 
 }  // namespace
@@ -361,18 +403,17 @@ HGS_API int hgs_sh_bwd(int degree, int K, const float* dirs, const float* means,
     if (post && colors == nullptr) return HGS_ERR_INVALID_ARG;
     if (N == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(v_coeffs, 0, (size_t)N * K * 3 * sizeof(float), st);
-    if (e != cudaSuccess) return (int)e;
-    if (vis_ids != nullptr) {
-        if (v_means != nullptr && (e = cudaMemsetAsync(v_means, 0, (size_t)N * 3 * sizeof(float), st)) != cudaSuccess)
-            return (int)e;
-        if (v_dirs != nullptr && (e = cudaMemsetAsync(v_dirs, 0, (size_t)C * N * 3 * sizeof(float), st)) != cudaSuccess)
-            return (int)e;
-        if (n_vis == 0) return 0;
-        const int grid = hgs_ceil_div(n_vis, SB);
-#define LAUNCH(DEG)                                                                                              \
-    sh_bwd_vis_kernel<DEG><<<grid, SB, 0, st>>>(dirs, means, campos, coeffs, vis_ids, n_vis, colors, v_colors,    \
-                                                ld_v_colors, C, N, K, post, v_coeffs, v_dirs, v_means);
+    (void)vis_ids; (void)n_vis;
+    if (radii != nullptr && dirs == nullptr && v_dirs == nullptr) {
+        // rasterization path: fused zero-fill + block-compacted gradient rows, one pass over v_coeffs
+        const int grid = hgs_ceil_div(N, SB);
+#define LAUNCH(DEG)                                                                                                \
+    {                                                                                                              \
+        const size_t smem = (size_t)SB * ((((DEG) + 1) * ((DEG) + 1) * 3) | 1) * sizeof(float);                    \
+        cudaFuncSetAttribute(sh_bwd_fused_kernel<DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        sh_bwd_fused_kernel<DEG><<<grid, SB, smem, st>>>(means, campos, coeffs, radii, colors, v_colors, ld_v_colors, \
+                                                         C, N, K, post, v_coeffs, v_means);                        \
+    }
         switch (degree) {
             case 0: LAUNCH(0) break;
             case 1: LAUNCH(1) break;
@@ -384,6 +425,8 @@ HGS_API int hgs_sh_bwd(int degree, int K, const float* dirs, const float* means,
         HGS_LAUNCH_CHECK();
         return 0;
     }
+    cudaError_t e = cudaMemsetAsync(v_coeffs, 0, (size_t)N * K * 3 * sizeof(float), st);
+    if (e != cudaSuccess) return (int)e;
     const int grid = hgs_ceil_div(N, SB);
 #define LAUNCH(DEG)                                                                                        \
     sh_bwd_kernel<DEG><<<grid, SB, 0, st>>>(dirs, means, campos, coeffs, radii, colors, v_colors, ld_v_colors, C, N, \
