@@ -104,15 +104,23 @@ __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint32_t* 
     __syncthreads();
     long long begin, end;
     chunk_range(*n_dev, begin, end);
-    for (long long base = begin; base < end; base += RS_THREADS) {
-        long long i = base + threadIdx.x;
-        bool valid = i < end;
-        const uint32_t d = valid ? digit_of(ds, keys[i], ds.from_val_div > 0 ? vals[i] : 0u) : 0u;
-        // invalid lanes are masked out of the peer sets
-        const unsigned vmask = __ballot_sync(0xFFFFFFFFu, valid);
-        const unsigned m = peers_of(d) & vmask;
-        const int leader = __ffs(m) - 1;
-        if (valid && (int)(threadIdx.x & 31) == leader) atomicAdd(&s_hist[d], (uint32_t)__popc(m));
+    for (long long base = begin; base < end; base += RS_TILE) {
+        // 8 independent loads in flight per thread, then warp-aggregated shared-memory increments
+        uint32_t d[RS_ITEMS];
+        bool valid[RS_ITEMS];
+#pragma unroll
+        for (int k = 0; k < RS_ITEMS; ++k) {
+            const long long i = base + k * RS_THREADS + threadIdx.x;
+            valid[k] = i < end;
+            d[k] = valid[k] ? digit_of(ds, keys[i], ds.from_val_div > 0 ? vals[i] : 0u) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < RS_ITEMS; ++k) {
+            const unsigned vmask = __ballot_sync(0xFFFFFFFFu, valid[k]);   // invalid lanes leave the peer sets
+            const unsigned m = peers_of(d[k]) & vmask;
+            const int leader = __ffs(m) - 1;
+            if (valid[k] && (int)(threadIdx.x & 31) == leader) atomicAdd(&s_hist[d[k]], (uint32_t)__popc(m));
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < RADIX; i += RS_THREADS) hist[(long long)i * gridDim.x + blockIdx.x] = s_hist[i];
@@ -135,7 +143,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_rowscan_kernel(uint32_t* __r
     if (threadIdx.x == 0) rowsum[blockIdx.x] = carry;
 }
 
-__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(
+__global__ void __launch_bounds__(RS_THREADS, 4) radix_scatter_kernel(
     const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, const long long* __restrict__ n_dev, DigitSpec ds,
     const uint32_t* __restrict__ hist_scanned, const uint32_t* __restrict__ rowsum) {

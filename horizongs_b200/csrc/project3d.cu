@@ -131,75 +131,116 @@ __device__ __forceinline__ void proj3d_cov_and_project(const HgsCam& cam, float 
     o.c00 = c00; o.c01 = c01; o.c11 = c11;
 }
 
+// Forward kernel in three phases so that the heavy math runs on densely populated warps even when only a
+// small, randomly scattered fraction of the Gaussians is on screen:
+//   1. every thread: camera-space centre of its Gaussian, near/far test, conservative off-screen test;
+//   2. the survivors of the block are compacted and the first n_pass threads do the covariance /
+//      Jacobian / conic / radius math, results go to shared memory;
+//   3. every thread writes its own output row (zeros for culled Gaussians), coalesced.
 __global__ void __launch_bounds__(PB) project3d_fwd_kernel(
     const float* __restrict__ means, const float* __restrict__ quats, const float* __restrict__ scales,
     const float* __restrict__ viewmats, const float* __restrict__ Ks, int N, int W, int H, float eps2d,
     float near_plane, float far_plane, float radius_clip, int tile_size, int tile_w, int tile_h,
     int32_t* __restrict__ radii, float* __restrict__ means2d, float* __restrict__ depths, float* __restrict__ conics,
     float* __restrict__ compensations, int32_t* __restrict__ tiles_per_gauss) {
-    __shared__ float s_a[PB * 3];
-    __shared__ float s_b[PB * 3];
+    __shared__ float s_a[PB * 3];        // means in, conics out
+    __shared__ float s_b[PB * 3];        // scales
+    __shared__ float s_pc[PB * 3];       // camera-space centres of the survivors
+    __shared__ float s_out[PB * 4];      // m2x, m2y, depth, compensation
+    __shared__ int s_ri[PB * 2];         // radius, tile count
+    __shared__ int s_list[PB];
+    __shared__ int s_wcnt[PB / 32];
     const int c = blockIdx.y;
     const long long base = (long long)blockIdx.x * PB;
     const long long n = base + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     block_load_rows3<PB>(means, base, N, s_a);
     block_load_rows3<PB>(scales, base, N, s_b);
+    // defaults: culled
+    s_ri[threadIdx.x * 2] = 0; s_ri[threadIdx.x * 2 + 1] = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s_out[threadIdx.x * 4 + k] = 0.f;
     __syncthreads();
     const HgsCam cam = hgs_load_cam(viewmats, Ks, c);
+    const float (*R)[3] = cam.R;
 
-    int radius_i = 0, ntiles = 0;
-    float o_m2x = 0.f, o_m2y = 0.f, o_depth = 0.f, o_ca = 0.f, o_cb = 0.f, o_cc = 0.f, o_comp = 0.f;
+    // ---- phase 1
+    bool pass = false;
     if (n < N) {
-        Proj3dFwd f;
         const float px = s_a[threadIdx.x * 3 + 0], py = s_a[threadIdx.x * 3 + 1], pz = s_a[threadIdx.x * 3 + 2];
         const float s0 = s_b[threadIdx.x * 3 + 0], s1 = s_b[threadIdx.x * 3 + 1], s2 = s_b[threadIdx.x * 3 + 2];
-        const float (*R)[3] = cam.R;
-        f.zc = R[2][0] * px + R[2][1] * py + R[2][2] * pz + cam.t[2];
-        bool ok = !(f.zc < near_plane || f.zc > far_plane);
-        if (ok) {
-            f.xc = R[0][0] * px + R[0][1] * py + R[0][2] * pz + cam.t[0];
-            f.yc = R[1][0] * px + R[1][1] * py + R[1][2] * pz + cam.t[1];
-            ok = !proj3d_surely_offscreen(cam, f.xc, f.yc, f.zc, fmaxf(fabsf(s0), fmaxf(fabsf(s1), fabsf(s2))),
-                                          (float)W, (float)H, eps2d);
+        const float zc = R[2][0] * px + R[2][1] * py + R[2][2] * pz + cam.t[2];
+        if (!(zc < near_plane || zc > far_plane)) {
+            const float xc = R[0][0] * px + R[0][1] * py + R[0][2] * pz + cam.t[0];
+            const float yc = R[1][0] * px + R[1][1] * py + R[1][2] * pz + cam.t[1];
+            pass = !proj3d_surely_offscreen(cam, xc, yc, zc, fmaxf(fabsf(s0), fmaxf(fabsf(s1), fabsf(s2))), (float)W,
+                                            (float)H, eps2d);
+            if (pass) { s_pc[threadIdx.x * 3] = xc; s_pc[threadIdx.x * 3 + 1] = yc; s_pc[threadIdx.x * 3 + 2] = zc; }
         }
-        if (ok) {
-            const float4 qv = reinterpret_cast<const float4*>(quats)[n];
-            proj3d_cov_and_project(cam, qv.x, qv.y, qv.z, qv.w, s0, s1, s2, (float)W, (float)H, eps2d, f);
-        }
-        if (ok && f.det > 0.f) {
-            float inv_det = 1.0f / f.det;
-            float b = 0.5f * (f.c00 + f.c11);
-            float v1 = b + sqrtf(fmaxf(b * b - f.det, HGS_EIG_FLOOR));
-            float radius = ceilf(HGS_RADIUS_SIGMA * sqrtf(v1));
+    }
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, pass);
+    if (lane == 0) s_wcnt[warp] = __popc(bal);
+    __syncthreads();
+    int wbase = 0, n_pass = 0;
+#pragma unroll
+    for (int w = 0; w < PB / 32; ++w) {
+        if (w < warp) wbase += s_wcnt[w];
+        n_pass += s_wcnt[w];
+    }
+    if (pass) s_list[wbase + __popc(bal & ((1u << lane) - 1u))] = threadIdx.x;
+    __syncthreads();
+
+    // ---- phase 2: dense math on the survivors
+    float o_ca = 0.f, o_cb = 0.f, o_cc = 0.f;   // conics of the row this thread PROCESSED (written to s_a below)
+    int my_row = -1;
+    if (threadIdx.x < n_pass) {
+        const int r = s_list[threadIdx.x];
+        my_row = r;
+        const float4 qv = reinterpret_cast<const float4*>(quats)[base + r];
+        Proj3dFwd f;
+        f.xc = s_pc[r * 3]; f.yc = s_pc[r * 3 + 1]; f.zc = s_pc[r * 3 + 2];
+        proj3d_cov_and_project(cam, qv.x, qv.y, qv.z, qv.w, s_b[r * 3], s_b[r * 3 + 1], s_b[r * 3 + 2], (float)W,
+                               (float)H, eps2d, f);
+        if (f.det > 0.f) {
+            const float inv_det = 1.0f / f.det;
+            const float b = 0.5f * (f.c00 + f.c11);
+            const float v1 = b + sqrtf(fmaxf(b * b - f.det, HGS_EIG_FLOOR));
+            const float radius = ceilf(HGS_RADIUS_SIGMA * sqrtf(v1));
             bool vis = !(radius <= radius_clip);
             vis = vis && !(f.m2x + radius <= 0.f || f.m2x - radius >= (float)W || f.m2y + radius <= 0.f ||
                            f.m2y - radius >= (float)H);
             if (vis) {
-                radius_i = (int)radius;
-                o_m2x = f.m2x; o_m2y = f.m2y; o_depth = f.zc;
+                const int radius_i = (int)radius;
+                int ntiles = 0;
+                if (tiles_per_gauss != nullptr && radius_i > 0) {
+                    int x0, y0, x1, y1;
+                    hgs_tile_bbox(f.m2x, f.m2y, (float)radius_i, (float)tile_size, tile_w, tile_h, x0, y0, x1, y1);
+                    ntiles = (y1 - y0) * (x1 - x0);
+                }
+                s_ri[r * 2] = radius_i; s_ri[r * 2 + 1] = ntiles;
+                s_out[r * 4] = f.m2x; s_out[r * 4 + 1] = f.m2y; s_out[r * 4 + 2] = f.zc;
+                s_out[r * 4 + 3] = sqrtf(fmaxf(f.det_orig / f.det, 0.f));
                 o_ca = f.c11 * inv_det;
                 o_cb = -f.c01 * inv_det;
                 o_cc = f.c00 * inv_det;
-                o_comp = sqrtf(fmaxf(f.det_orig / f.det, 0.f));
-                if (tiles_per_gauss != nullptr && radius_i > 0) {
-                    int x0, y0, x1, y1;
-                    hgs_tile_bbox(o_m2x, o_m2y, (float)radius_i, (float)tile_size, tile_w, tile_h, x0, y0, x1, y1);
-                    ntiles = (y1 - y0) * (x1 - x0);
-                }
             }
         }
-        const long long idx = (long long)c * N + n;
-        radii[idx] = radius_i;
-        reinterpret_cast<float2*>(means2d)[idx] = make_float2(o_m2x, o_m2y);
-        depths[idx] = o_depth;
-        if (compensations != nullptr) compensations[idx] = o_comp;
-        if (tiles_per_gauss != nullptr) tiles_per_gauss[idx] = ntiles;
     }
+    __syncthreads();   // everyone is done reading means (s_a): reuse it for the conics
+    s_a[threadIdx.x * 3 + 0] = 0.f; s_a[threadIdx.x * 3 + 1] = 0.f; s_a[threadIdx.x * 3 + 2] = 0.f;
     __syncthreads();
-    s_a[threadIdx.x * 3 + 0] = o_ca;
-    s_a[threadIdx.x * 3 + 1] = o_cb;
-    s_a[threadIdx.x * 3 + 2] = o_cc;
+    if (my_row >= 0) { s_a[my_row * 3 + 0] = o_ca; s_a[my_row * 3 + 1] = o_cb; s_a[my_row * 3 + 2] = o_cc; }
     __syncthreads();
+
+    // ---- phase 3: coalesced rows
+    if (n < N) {
+        const long long idx = (long long)c * N + n;
+        radii[idx] = s_ri[threadIdx.x * 2];
+        reinterpret_cast<float2*>(means2d)[idx] = make_float2(s_out[threadIdx.x * 4], s_out[threadIdx.x * 4 + 1]);
+        depths[idx] = s_out[threadIdx.x * 4 + 2];
+        if (compensations != nullptr) compensations[idx] = s_out[threadIdx.x * 4 + 3];
+        if (tiles_per_gauss != nullptr) tiles_per_gauss[idx] = s_ri[threadIdx.x * 2 + 1];
+    }
     block_store_rows3<PB>(conics + (long long)c * N * 3, base, N, s_a);
 }
 

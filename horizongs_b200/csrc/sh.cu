@@ -343,9 +343,10 @@ __global__ void __launch_bounds__(SB) sh_bwd_fused_kernel(const float* __restric
     }
     // coalesced write of all rows of the block
     float* dst = v_coeffs + base * rowlen;
-    const long long tot = rows * rowlen;
-    for (long long i = threadIdx.x; i < tot; i += SB) {
-        const int r = (int)(i / rowlen), c = (int)(i - (long long)r * rowlen);
+    const int tot = (int)rows * rowlen;                                   // <= 128 * 75
+    const unsigned magic = 0xFFFFFFFFu / (unsigned)rowlen + 1u;           // i / rowlen == umulhi(i, magic) here
+    for (int i = threadIdx.x; i < tot; i += SB) {
+        const int r = (int)__umulhi((unsigned)i, magic), c = i - r * rowlen;
         const int sl = s_slot[r];
         dst[i] = (sl >= 0 && c < RL) ? s_rows[sl * RS + c] : 0.f;
     }
