@@ -81,17 +81,6 @@ __global__ void pack3d_kernel(const float* __restrict__ means2d, const float* __
     for (int k = 0; k < 4; ++k) dst[k] = src[k];
 }
 
-__device__ __forceinline__ float rcp_approx(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
 // can this Gaussian reach alpha >= 1/255 (and sigma >= 0) anywhere on the pixel-centre rectangle
 // [X0,X1] x [Y0,Y1]?  Maximum of the concave quadratic p2(u,v) = A u^2 + B u v + C v^2 over the rectangle.
 __device__ __forceinline__ bool cull_keep(const float4 q0, const float4 q1, const float4 q3, float X0, float X1,
@@ -116,28 +105,6 @@ __device__ __forceinline__ bool cull_keep(const float4 q0, const float4 q1, cons
 
 __device__ __forceinline__ const float4* slot_q(const unsigned char* stage, int t) {
     return reinterpret_cast<const float4*>(stage + t * SLOT_BYTES);
-}
-
-struct TileGeom {
-    int cam, gtile, pi, pj, warp, lane;
-    float px, py, X0, X1, Y0, Y1;
-    bool inside;
-};
-__device__ __forceinline__ TileGeom tile_geom(int tile_w, int tile_h, int W, int H) {
-    TileGeom g;
-    g.cam = blockIdx.z;
-    g.gtile = (g.cam * tile_h + blockIdx.y) * tile_w + blockIdx.x;
-    g.warp = threadIdx.x >> 5;
-    g.lane = threadIdx.x & 31;
-    const int sx = blockIdx.x * TS + (g.warp & 1) * 8, sy = blockIdx.y * TS + (g.warp >> 1) * 4;
-    g.pj = sx + (g.lane & 7);
-    g.pi = sy + (g.lane >> 3);
-    g.px = (float)g.pj + 0.5f;
-    g.py = (float)g.pi + 0.5f;
-    g.X0 = (float)sx + 0.5f; g.X1 = (float)sx + 7.5f;
-    g.Y0 = (float)sy + 0.5f; g.Y1 = (float)sy + 3.5f;
-    g.inside = (g.pi < H && g.pj < W);
-    return g;
 }
 
 // =====================================================================================================

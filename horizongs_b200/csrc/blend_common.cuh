@@ -102,4 +102,43 @@ __device__ __forceinline__ int halving_component(int lane) {
     return Halving<N, 16>::comp(id, lane);
 }
 
+
+// ---- fast approximate math (MUFU) --------------------------------------------------------------------
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+
+// ---- tile / sub-tile geometry of the fast blend kernels ----------------------------------------------
+// One CTA of 256 threads per 16x16 tile; warp w owns the 8x4 pixel sub-tile ((w & 1) * 8, (w >> 1) * 4).
+struct TileGeom {
+    int cam, gtile, pi, pj, warp, lane;
+    float px, py, X0, X1, Y0, Y1;
+    bool inside;
+};
+__device__ __forceinline__ TileGeom tile_geom(int tile_w, int tile_h, int W, int H) {
+    TileGeom g;
+    g.cam = blockIdx.z;
+    g.gtile = (g.cam * tile_h + blockIdx.y) * tile_w + blockIdx.x;
+    g.warp = threadIdx.x >> 5;
+    g.lane = threadIdx.x & 31;
+    const int sx = blockIdx.x * HGS_TILE_SIZE + (g.warp & 1) * 8, sy = blockIdx.y * HGS_TILE_SIZE + (g.warp >> 1) * 4;
+    g.pj = sx + (g.lane & 7);
+    g.pi = sy + (g.lane >> 3);
+    g.px = (float)g.pj + 0.5f;
+    g.py = (float)g.pi + 0.5f;
+    g.X0 = (float)sx + 0.5f; g.X1 = (float)sx + 7.5f;
+    g.Y0 = (float)sy + 0.5f; g.Y1 = (float)sy + 3.5f;
+    g.inside = (g.pi < H && g.pj < W);
+    return g;
+}
+
+
 }  // namespace hgs

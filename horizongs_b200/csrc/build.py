@@ -32,6 +32,7 @@ SOURCES = {
     "isect.cu": [],
     "blend3d.cu": [],
     "blend2d.cu": [],
+    "blend2d_fast.cu": [],
     "densify.cu": [],
 }
 

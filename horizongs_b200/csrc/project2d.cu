@@ -128,96 +128,140 @@ __global__ void __launch_bounds__(PB) project2d_fwd_kernel(
     block_store_rows3<PB>(normals + (long long)c * N * 3, base, N, s_a);
 }
 
+// gradient of one (camera, surfel) pair; accumulates into g_mean / g_scale / g_quat
+__device__ __forceinline__ void proj2d_bwd_one(const HgsCam& cam, const Proj2dFwd& f, float s0, float s1,
+                                               const float* __restrict__ v_means2d, int ld_m2,
+                                               const float* __restrict__ v_depths, int ld_d,
+                                               const float* __restrict__ v_ray_transforms, int ld_rt,
+                                               const float* __restrict__ v_normals, int ld_n, long long idx,
+                                               float g_mean[3], float g_scale[3], float g_quat[4]) {
+    float vM0[3] = {0.f, 0.f, 0.f}, vM1[3] = {0.f, 0.f, 0.f}, vM2[3] = {0.f, 0.f, 0.f};
+    if (v_ray_transforms != nullptr) {
+        const float* vr = v_ray_transforms + idx * ld_rt;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { vM0[j] = vr[j]; vM1[j] = vr[3 + j]; vM2[j] = vr[6 + j]; }
+    }
+    if (v_means2d != nullptr) {
+        const float vmx = v_means2d[idx * ld_m2], vmy = v_means2d[idx * ld_m2 + 1];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            vM0[j] += vmx * f.f[j] * f.M2[j];
+            vM1[j] += vmy * f.f[j] * f.M2[j];
+            vM2[j] += vmx * f.f[j] * (f.M0[j] - 2.f * f.M2[j] * f.m2x) + vmy * f.f[j] * (f.M1[j] - 2.f * f.M2[j] * f.m2y);
+        }
+    }
+    float vWH[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        vWH[0][j] = cam.fx * vM0[j];
+        vWH[1][j] = cam.fy * vM1[j];
+        vWH[2][j] = cam.cx * vM0[j] + cam.cy * vM1[j] + vM2[j];
+    }
+    float vRQ[3][3];
+    float v_mc[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        vRQ[i][0] = vWH[i][0] * s0;
+        vRQ[i][1] = vWH[i][1] * s1;
+        vRQ[i][2] = 0.f;
+        v_mc[i] = vWH[i][2];
+    }
+    g_scale[0] += f.RQ[0][0] * vWH[0][0] + f.RQ[1][0] * vWH[1][0] + f.RQ[2][0] * vWH[2][0];
+    g_scale[1] += f.RQ[0][1] * vWH[0][1] + f.RQ[1][1] * vWH[1][1] + f.RQ[2][1] * vWH[2][1];
+    if (v_depths != nullptr) v_mc[2] += v_depths[idx * ld_d];
+    if (v_normals != nullptr) {
+        const float dotv = -f.RQ[0][2] * f.mc[0] + -f.RQ[1][2] * f.mc[1] + -f.RQ[2][2] * f.mc[2];
+        const float sign = dotv > 0.f ? 1.0f : -1.0f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) vRQ[i][2] = sign * v_normals[idx * ld_n + i];
+    }
+    const float (*R)[3] = cam.R;
+    float vq_mat[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) vq_mat[k][j] = R[0][k] * vRQ[0][j] + R[1][k] * vRQ[1][j] + R[2][k] * vRQ[2][j];
+        g_mean[k] += R[0][k] * v_mc[0] + R[1][k] * v_mc[1] + R[2][k] * v_mc[2];
+    }
+    float vq[4];
+    hgs_quat_to_rot_vjp(f.qn, f.inv_norm, vq_mat, vq);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g_quat[k] += vq[k];
+}
+
+// dense variant: one thread per surfel, cameras looped in-thread (deterministic)
 __global__ void __launch_bounds__(PB) project2d_bwd_kernel(
     const float* __restrict__ means, const float* __restrict__ quats, const float* __restrict__ scales,
     const float* __restrict__ viewmats, const float* __restrict__ Ks, int C, int N, float near_plane, float far_plane,
-    const int32_t* __restrict__ radii, const float* __restrict__ v_means2d, const float* __restrict__ v_depths,
-    const float* __restrict__ v_ray_transforms, const float* __restrict__ v_normals, float* __restrict__ v_means,
-    float* __restrict__ v_quats, float* __restrict__ v_scales) {
-    __shared__ float s_a[PB * 3];
-    __shared__ float s_b[PB * 3];
-    const long long base = (long long)blockIdx.x * PB;
-    const long long n = base + threadIdx.x;
-    block_load_rows3<PB>(means, base, N, s_a);
-    block_load_rows3<PB>(scales, base, N, s_b);
-    __syncthreads();
-    const float px = s_a[threadIdx.x * 3], py = s_a[threadIdx.x * 3 + 1], pz = s_a[threadIdx.x * 3 + 2];
-    const float s0 = s_b[threadIdx.x * 3], s1 = s_b[threadIdx.x * 3 + 1];
-    float4 qv = make_float4(1.f, 0.f, 0.f, 0.f);
-    if (n < N) qv = reinterpret_cast<const float4*>(quats)[n];
+    const int32_t* __restrict__ radii, const float* __restrict__ v_means2d, int ld_m2,
+    const float* __restrict__ v_depths, int ld_d, const float* __restrict__ v_ray_transforms, int ld_rt,
+    const float* __restrict__ v_normals, int ld_n, float* __restrict__ v_means, float* __restrict__ v_quats,
+    float* __restrict__ v_scales) {
+    const long long n = (long long)blockIdx.x * PB + threadIdx.x;
+    if (n >= N) return;
+    bool any = false;
+    for (int c = 0; c < C; ++c) any |= radii[(long long)c * N + n] > 0;
     float g_mean[3] = {0.f, 0.f, 0.f}, g_scale[3] = {0.f, 0.f, 0.f}, g_quat[4] = {0.f, 0.f, 0.f, 0.f};
-
-    for (int c = 0; c < C; ++c) {
-        if (n >= N) break;
-        const long long idx = (long long)c * N + n;
-        if (radii[idx] <= 0) continue;
-        const HgsCam cam = hgs_load_cam(viewmats, Ks, c);
-        Proj2dFwd f;
-        if (!proj2d_math(cam, px, py, pz, qv.x, qv.y, qv.z, qv.w, s0, s1, near_plane, far_plane, f)) continue;
-        float vM0[3] = {0.f, 0.f, 0.f}, vM1[3] = {0.f, 0.f, 0.f}, vM2[3] = {0.f, 0.f, 0.f};
-        if (v_ray_transforms != nullptr) {
-            const float* vr = v_ray_transforms + idx * 9;
-#pragma unroll
-            for (int j = 0; j < 3; ++j) { vM0[j] = vr[j]; vM1[j] = vr[3 + j]; vM2[j] = vr[6 + j]; }
+    if (any) {
+        const float px = means[n * 3], py = means[n * 3 + 1], pz = means[n * 3 + 2];
+        const float s0 = scales[n * 3], s1 = scales[n * 3 + 1];
+        const float4 qv = reinterpret_cast<const float4*>(quats)[n];
+        for (int c = 0; c < C; ++c) {
+            const long long idx = (long long)c * N + n;
+            if (radii[idx] <= 0) continue;
+            const HgsCam cam = hgs_load_cam(viewmats, Ks, c);
+            Proj2dFwd f;
+            if (!proj2d_math(cam, px, py, pz, qv.x, qv.y, qv.z, qv.w, s0, s1, near_plane, far_plane, f)) continue;
+            proj2d_bwd_one(cam, f, s0, s1, v_means2d, ld_m2, v_depths, ld_d, v_ray_transforms, ld_rt, v_normals, ld_n,
+                           idx, g_mean, g_scale, g_quat);
         }
-        if (v_means2d != nullptr) {
-            const float2 vm = reinterpret_cast<const float2*>(v_means2d)[idx];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                vM0[j] += vm.x * f.f[j] * f.M2[j];
-                vM1[j] += vm.y * f.f[j] * f.M2[j];
-                vM2[j] += vm.x * f.f[j] * (f.M0[j] - 2.f * f.M2[j] * f.m2x) +
-                          vm.y * f.f[j] * (f.M1[j] - 2.f * f.M2[j] * f.m2y);
-            }
-        }
-        float vWH[3][3];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            vWH[0][j] = cam.fx * vM0[j];
-            vWH[1][j] = cam.fy * vM1[j];
-            vWH[2][j] = cam.cx * vM0[j] + cam.cy * vM1[j] + vM2[j];
-        }
-        float vRQ[3][3];
-        float v_mc[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            vRQ[i][0] = vWH[i][0] * s0;
-            vRQ[i][1] = vWH[i][1] * s1;
-            vRQ[i][2] = 0.f;
-            v_mc[i] = vWH[i][2];
-        }
-        g_scale[0] += f.RQ[0][0] * vWH[0][0] + f.RQ[1][0] * vWH[1][0] + f.RQ[2][0] * vWH[2][0];
-        g_scale[1] += f.RQ[0][1] * vWH[0][1] + f.RQ[1][1] * vWH[1][1] + f.RQ[2][1] * vWH[2][1];
-        if (v_depths != nullptr) v_mc[2] += v_depths[idx];
-        if (v_normals != nullptr) {
-            const float dotv = -f.RQ[0][2] * f.mc[0] + -f.RQ[1][2] * f.mc[1] + -f.RQ[2][2] * f.mc[2];
-            const float sign = dotv > 0.f ? 1.0f : -1.0f;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) vRQ[i][2] = sign * v_normals[idx * 3 + i];
-        }
-        const float (*R)[3] = cam.R;
-        float vq_mat[3][3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-#pragma unroll
-            for (int j = 0; j < 3; ++j) vq_mat[k][j] = R[0][k] * vRQ[0][j] + R[1][k] * vRQ[1][j] + R[2][k] * vRQ[2][j];
-            g_mean[k] += R[0][k] * v_mc[0] + R[1][k] * v_mc[1] + R[2][k] * v_mc[2];
-        }
-        float vq[4];
-        hgs_quat_to_rot_vjp(f.qn, f.inv_norm, vq_mat, vq);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) g_quat[k] += vq[k];
     }
-    if (n < N) reinterpret_cast<float4*>(v_quats)[n] = make_float4(g_quat[0], g_quat[1], g_quat[2], g_quat[3]);
-    __syncthreads();
+    reinterpret_cast<float4*>(v_quats)[n] = make_float4(g_quat[0], g_quat[1], g_quat[2], g_quat[3]);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        s_a[threadIdx.x * 3 + k] = g_mean[k];
-        s_b[threadIdx.x * 3 + k] = g_scale[k];
+        v_means[n * 3 + k] = g_mean[k];
+        v_scales[n * 3 + k] = g_scale[k];
     }
-    __syncthreads();
-    block_store_rows3<PB>(v_means, base, N, s_a);
-    block_store_rows3<PB>(v_scales, base, N, s_b);
+}
+
+// work-list variant: one thread per visible (camera, surfel) pair; outputs zero-filled by the launcher
+__global__ void __launch_bounds__(PB) project2d_bwd_vis_kernel(
+    const float* __restrict__ means, const float* __restrict__ quats, const float* __restrict__ scales,
+    const float* __restrict__ viewmats, const float* __restrict__ Ks, int C, int N, float near_plane, float far_plane,
+    const int32_t* __restrict__ vis_ids, long long n_vis, const float* __restrict__ v_means2d, int ld_m2,
+    const float* __restrict__ v_depths, int ld_d, const float* __restrict__ v_ray_transforms, int ld_rt,
+    const float* __restrict__ v_normals, int ld_n, float* __restrict__ v_means, float* __restrict__ v_quats,
+    float* __restrict__ v_scales) {
+    const long long j = (long long)blockIdx.x * PB + threadIdx.x;
+    if (j >= n_vis) return;
+    const long long idx = vis_ids[j];
+    const int c = (int)(idx / N);
+    const long long n = idx - (long long)c * N;
+    const float px = means[n * 3], py = means[n * 3 + 1], pz = means[n * 3 + 2];
+    const float s0 = scales[n * 3], s1 = scales[n * 3 + 1];
+    const float4 qv = reinterpret_cast<const float4*>(quats)[n];
+    float g_mean[3] = {0.f, 0.f, 0.f}, g_scale[3] = {0.f, 0.f, 0.f}, g_quat[4] = {0.f, 0.f, 0.f, 0.f};
+    const HgsCam cam = hgs_load_cam(viewmats, Ks, c);
+    Proj2dFwd f;
+    if (!proj2d_math(cam, px, py, pz, qv.x, qv.y, qv.z, qv.w, s0, s1, near_plane, far_plane, f)) return;
+    proj2d_bwd_one(cam, f, s0, s1, v_means2d, ld_m2, v_depths, ld_d, v_ray_transforms, ld_rt, v_normals, ld_n, idx,
+                   g_mean, g_scale, g_quat);
+    if (C == 1) {
+        reinterpret_cast<float4*>(v_quats)[n] = make_float4(g_quat[0], g_quat[1], g_quat[2], g_quat[3]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            v_means[n * 3 + k] = g_mean[k];
+            v_scales[n * 3 + k] = g_scale[k];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) atomicAdd(v_quats + n * 4 + k, g_quat[k]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            atomicAdd(v_means + n * 3 + k, g_mean[k]);
+            atomicAdd(v_scales + n * 3 + k, g_scale[k]);
+        }
+    }
 }
 
 }  // namespace
@@ -240,15 +284,30 @@ HGS_API int hgs_project2d_fwd(const float* means, const float* quats, const floa
 
 HGS_API int hgs_project2d_bwd(const float* means, const float* quats, const float* scales, const float* viewmats,
                               const float* Ks, int C, int N, int width, int height, float near_plane, float far_plane,
-                              const int32_t* radii, const float* v_means2d, const float* v_depths,
-                              const float* v_ray_transforms, const float* v_normals, float* v_means, float* v_quats,
-                              float* v_scales, void* stream) {
+                              const int32_t* radii, const float* v_means2d, int ld_means2d, const float* v_depths,
+                              int ld_depths, const float* v_ray_transforms, int ld_ray_transforms,
+                              const float* v_normals, int ld_normals, const int32_t* vis_ids, long long n_vis,
+                              float* v_means, float* v_quats, float* v_scales, void* stream) {
     (void)width; (void)height;
-    if (C <= 0 || N < 0) return HGS_ERR_INVALID_ARG;
+    if (C <= 0 || N < 0 || n_vis < 0 || ld_means2d < 2 || ld_depths < 1 || ld_ray_transforms < 9 || ld_normals < 3)
+        return HGS_ERR_INVALID_ARG;
     if (N == 0) return 0;
-    project2d_bwd_kernel<<<hgs_ceil_div(N, PB), PB, 0, (cudaStream_t)stream>>>(
-        means, quats, scales, viewmats, Ks, C, N, near_plane, far_plane, radii, v_means2d, v_depths, v_ray_transforms,
-        v_normals, v_means, v_quats, v_scales);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (vis_ids != nullptr) {
+        cudaError_t e;
+        if ((e = cudaMemsetAsync(v_means, 0, (size_t)N * 3 * sizeof(float), st)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemsetAsync(v_quats, 0, (size_t)N * 4 * sizeof(float), st)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemsetAsync(v_scales, 0, (size_t)N * 3 * sizeof(float), st)) != cudaSuccess) return (int)e;
+        if (n_vis == 0) return 0;
+        project2d_bwd_vis_kernel<<<hgs_ceil_div(n_vis, PB), PB, 0, st>>>(
+            means, quats, scales, viewmats, Ks, C, N, near_plane, far_plane, vis_ids, n_vis, v_means2d, ld_means2d,
+            v_depths, ld_depths, v_ray_transforms, ld_ray_transforms, v_normals, ld_normals, v_means, v_quats, v_scales);
+        HGS_LAUNCH_CHECK();
+        return 0;
+    }
+    project2d_bwd_kernel<<<hgs_ceil_div(N, PB), PB, 0, st>>>(
+        means, quats, scales, viewmats, Ks, C, N, near_plane, far_plane, radii, v_means2d, ld_means2d, v_depths,
+        ld_depths, v_ray_transforms, ld_ray_transforms, v_normals, ld_normals, v_means, v_quats, v_scales);
     HGS_LAUNCH_CHECK();
     return 0;
 }

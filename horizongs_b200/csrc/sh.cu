@@ -165,7 +165,7 @@ __device__ __forceinline__ void sh_grad_one(float x, float y, float z, const flo
         g_co[k * 3 + 1] += b[k] * v1;
         g_co[k * 3 + 2] += b[k] * v2;
         if (want_dir) {
-            const float d = __ldg(co + k * 3) * v0 + __ldg(co + k * 3 + 1) * v1 + __ldg(co + k * 3 + 2) * v2;
+            const float d = co[k * 3] * v0 + co[k * 3 + 1] * v1 + co[k * 3 + 2] * v2;
             vx += bx[k] * d; vy += by[k] * d; vz += bz[k] * d;
         }
     }
@@ -310,12 +310,22 @@ __global__ void __launch_bounds__(SB) sh_bwd_fused_kernel(const float* __restric
     long long rows = N - base;
     if (rows > SB) rows = SB;
     if (n_vis > 0) {
+        // coefficient rows of the visible Gaussians -> shared memory, loaded by the whole block (each row is
+        // one contiguous 12*NB-byte segment); the slot is overwritten with the gradient row afterwards
+        if (v_means != nullptr) {
+            const unsigned magic_rl = 0xFFFFFFFFu / (unsigned)RL + 1u;
+            for (int i = threadIdx.x; i < n_vis * RL; i += SB) {
+                const int j = (int)__umulhi((unsigned)i, magic_rl), cc = i - j * RL;
+                s_rows[j * RS + cc] = coeffs[(base + s_list[j]) * (long long)rowlen + cc];
+            }
+            __syncthreads();
+        }
         // thread j < n_vis handles the j-th visible Gaussian of the block
         float gm0 = 0.f, gm1 = 0.f, gm2 = 0.f;
         if (threadIdx.x < n_vis) {
             const int r = s_list[threadIdx.x];
             const long long nn = base + r;
-            const float* co = coeffs + nn * (long long)rowlen;
+            const float* co = s_rows + threadIdx.x * RS;
             float g_co[RL];
 #pragma unroll
             for (int k = 0; k < RL; ++k) g_co[k] = 0.f;

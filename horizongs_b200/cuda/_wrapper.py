@@ -457,8 +457,9 @@ def rasterize_to_pixels(means2d: Tensor, conics: Tensor, colors: Tensor, opaciti
 class _Project2D(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means, quats, scales, viewmats, Ks, width, height, near_plane, far_plane, radius_clip,
-                tile_size):
+                tile_size, holder):
         L = _lib.lib()
+        ctx.holder = holder
         C, N = viewmats.shape[0], means.shape[0]
         dev = means.device
         radii = torch.empty((C, N), dtype=torch.int32, device=dev)
@@ -487,21 +488,27 @@ class _Project2D(torch.autograd.Function):
         v_means = torch.empty_like(means)
         v_quats = torch.empty_like(quats)
         v_scales = torch.empty_like(scales)
-        cg = lambda t: None if t is None else t.contiguous()  # noqa: E731
-        v_means2d, v_depths, v_ray_transforms, v_normals = cg(v_means2d), cg(v_depths), cg(v_ray_transforms), cg(v_normals)
+        v_means2d, ld_m = _rows(v_means2d, 2)
+        v_depths, ld_d = _rows(None if v_depths is None else v_depths.unsqueeze(-1), 1)
+        v_rt, ld_rt = _rows(None if v_ray_transforms is None else v_ray_transforms.flatten(-2), 9)
+        v_normals, ld_n = _rows(v_normals, 3)
+        vis = None if ctx.holder is None else ctx.holder.get("vis_ids")
+        _mark("project2d_bwd", 0)
         check(L.hgs_project2d_bwd(ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), C, N, width, height,
-                                  near_plane, far_plane, ptr(radii), ptr(v_means2d), ptr(v_depths),
-                                  ptr(v_ray_transforms), ptr(v_normals), ptr(v_means), ptr(v_quats), ptr(v_scales),
-                                  _stream()), "hgs_project2d_bwd")
-        return (v_means, v_quats, v_scales) + (None,) * 8
+                                  near_plane, far_plane, ptr(radii), ptr(v_means2d), ld_m, ptr(v_depths), ld_d,
+                                  ptr(v_rt), ld_rt, ptr(v_normals), ld_n, ptr(vis), 0 if vis is None else vis.numel(),
+                                  ptr(v_means), ptr(v_quats), ptr(v_scales), _stream()), "hgs_project2d_bwd")
+        _mark("project2d_bwd", 1)
+        return (v_means, v_quats, v_scales) + (None,) * 9
 
 
-def _project2d(means, quats, scales, viewmats, Ks, width, height, near_plane, far_plane, radius_clip, tile_size):
+def _project2d(means, quats, scales, viewmats, Ks, width, height, near_plane, far_plane, radius_clip, tile_size,
+               holder=None):
     _check_proj_inputs(means, quats, scales, viewmats, Ks)
     means, quats, scales = _f32c(means, "means"), _f32c(quats, "quats"), _f32c(scales, "scales")
     viewmats, Ks = _f32c(viewmats.detach(), "viewmats"), _f32c(Ks.detach(), "Ks")
     return _Project2D.apply(means, quats, scales, viewmats, Ks, int(width), int(height), float(near_plane),
-                            float(far_plane), float(radius_clip), int(tile_size))
+                            float(far_plane), float(radius_clip), int(tile_size), holder)
 
 
 def fully_fused_projection_2dgs(
@@ -526,9 +533,12 @@ def fully_fused_projection_2dgs(
 # a12: rasterize_to_pixels_2dgs
 # =====================================================================================
 class _Blend2D(torch.autograd.Function):
+    """rasterize_to_pixels_2dgs.  1 / 3 / 4 channels: packed-record fast kernels (TMA-staged, per-warp cull box,
+    fused expected-depth normalisation); otherwise the plain kernels."""
+
     @staticmethod
     def forward(ctx, means2d, ray_transforms, colors, depths, normals, opacities, densify, backgrounds, width,
-                height, tile_size, isect_offsets, flatten_ids, distloss, box):
+                height, tile_size, isect_offsets, flatten_ids, distloss, box, radii, normalize_depth, vis_ids):
         L = _lib.lib()
         C, N = opacities.shape
         CH = colors.shape[-1]
@@ -541,15 +551,39 @@ class _Blend2D(torch.autograd.Function):
         render_median = torch.empty((C, height, width, 1), dtype=torch.float32, device=dev)
         last_ids = torch.empty((C, height, width), dtype=torch.int32, device=dev)
         median_ids = torch.empty((C, height, width), dtype=torch.int32, device=dev)
-        check(L.hgs_blend2d_fwd(ptr(means2d), ptr(ray_transforms), ptr(colors), ptr(depths), ptr(normals),
-                                ptr(opacities), ptr(backgrounds), C, N, CH, width, height, tile_size,
-                                ptr(isect_offsets), ptr(flatten_ids), flatten_ids.numel(), ptr(render_colors),
-                                ptr(render_alphas), ptr(render_normals), ptr(render_distort), ptr(render_median),
-                                ptr(last_ids), ptr(median_ids), _stream()), "hgs_blend2d_fwd")
-        ctx.save_for_backward(means2d, ray_transforms, colors, depths, normals, opacities, backgrounds,
-                              isect_offsets, flatten_ids, render_colors, render_alphas, last_ids, median_ids)
-        ctx.cfg = (width, height, tile_size, distloss)
+        fast = D in (1, 3, 4)
+        ctx.fast = fast
+        ctx.cfg = (width, height, tile_size, distloss, bool(normalize_depth), CH, D)
         ctx.box = box
+        st = _stream()
+        if fast:
+            records = torch.empty(L.hgs_blend2d_pack_bytes(C * N), dtype=torch.uint8, device=dev)
+            _mark("blend2d_pack", 0)
+            check(L.hgs_blend2d_pack(ptr(means2d), ptr(ray_transforms), ptr(colors), ptr(depths), ptr(normals),
+                                     ptr(opacities), ptr(radii), ptr(vis_ids),
+                                     0 if vis_ids is None else vis_ids.numel(), C * N, CH, ptr(records), st),
+                  "hgs_blend2d_pack")
+            _mark("blend2d_pack", 1)
+            _mark("blend2d_fwd", 0)
+            check(L.hgs_blend2d_fwd_packed(ptr(records), ptr(backgrounds), C, D, int(normalize_depth), width, height,
+                                           tile_size, ptr(isect_offsets), ptr(flatten_ids), flatten_ids.numel(),
+                                           ptr(render_colors), ptr(render_alphas), ptr(render_normals),
+                                           ptr(render_distort), ptr(render_median), ptr(last_ids), ptr(median_ids),
+                                           st), "hgs_blend2d_fwd_packed")
+            _mark("blend2d_fwd", 1)
+            ctx.save_for_backward(records, backgrounds, isect_offsets, flatten_ids, render_colors, render_alphas,
+                                  last_ids, median_ids)
+            ctx.shapes = (means2d.shape, depths is not None)
+        else:
+            if normalize_depth:
+                raise NotImplementedError("fused depth normalisation needs 1, 3 or 4 channels")
+            check(L.hgs_blend2d_fwd(ptr(means2d), ptr(ray_transforms), ptr(colors), ptr(depths), ptr(normals),
+                                    ptr(opacities), ptr(backgrounds), C, N, CH, width, height, tile_size,
+                                    ptr(isect_offsets), ptr(flatten_ids), flatten_ids.numel(), ptr(render_colors),
+                                    ptr(render_alphas), ptr(render_normals), ptr(render_distort), ptr(render_median),
+                                    ptr(last_ids), ptr(median_ids), st), "hgs_blend2d_fwd")
+            ctx.save_for_backward(means2d, ray_transforms, colors, depths, normals, opacities, backgrounds,
+                                  isect_offsets, flatten_ids, render_colors, render_alphas, last_ids, median_ids)
         if not distloss:
             render_distort = torch.zeros((C, height, width, 1), dtype=torch.float32, device=dev)
             ctx.mark_non_differentiable(render_distort)
@@ -557,42 +591,69 @@ class _Blend2D(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, v_render_colors, v_render_alphas, v_render_normals, v_render_distort, v_render_median):
-        (means2d, ray_transforms, colors, depths, normals, opacities, backgrounds, isect_offsets, flatten_ids,
-         render_colors, render_alphas, last_ids, median_ids) = ctx.saved_tensors
-        width, height, tile_size, distloss = ctx.cfg
+        width, height, tile_size, distloss, normalize_depth, CH, D = ctx.cfg
         L = _lib.lib()
-        C, N = opacities.shape
-        CH = colors.shape[-1]
         cg = lambda t: None if t is None else t.contiguous()  # noqa: E731
+        tail = (None,) * 10
+        if ctx.fast:
+            (records, backgrounds, isect_offsets, flatten_ids, render_colors, render_alphas, last_ids,
+             median_ids) = ctx.saved_tensors
+            (C, N, _), has_depth = ctx.shapes
+        else:
+            (means2d, ray_transforms, colors, depths, normals, opacities, backgrounds, isect_offsets, flatten_ids,
+             render_colors, render_alphas, last_ids, median_ids) = ctx.saved_tensors
+            C, N = opacities.shape
         v_render_colors = cg(v_render_colors) if v_render_colors is not None else torch.zeros_like(render_colors)
         v_render_alphas = cg(v_render_alphas) if v_render_alphas is not None else torch.zeros_like(render_alphas)
         v_render_normals, v_render_median = cg(v_render_normals), cg(v_render_median)
         v_render_distort = cg(v_render_distort) if distloss else None
-        v_means2d = torch.zeros_like(means2d)
-        v_rt = torch.zeros_like(ray_transforms)
-        v_colors = torch.zeros_like(colors)
-        v_depths = torch.zeros_like(depths) if depths is not None else None
-        v_normals = torch.zeros_like(normals)
-        v_opacities = torch.zeros_like(opacities)
-        v_densify = torch.zeros_like(means2d) if (ctx.needs_input_grad[6] or ctx.box is not None) else None
-        check(L.hgs_blend2d_bwd(ptr(means2d), ptr(ray_transforms), ptr(colors), ptr(depths), ptr(normals),
-                                ptr(opacities), ptr(backgrounds), C, N, CH, width, height, tile_size,
-                                ptr(isect_offsets), ptr(flatten_ids), flatten_ids.numel(), ptr(render_colors),
-                                ptr(render_alphas), ptr(last_ids), ptr(median_ids), ptr(v_render_colors),
-                                ptr(v_render_alphas), ptr(v_render_normals), ptr(v_render_distort),
-                                ptr(v_render_median), ptr(v_means2d), ptr(v_rt), ptr(v_colors), ptr(v_depths),
-                                ptr(v_normals), ptr(v_opacities), ptr(v_densify), _stream()), "hgs_blend2d_bwd")
+        if ctx.fast:
+            vpack = torch.zeros((C, N, 24), dtype=torch.float32, device=records.device)
+            _mark("blend2d_bwd", 0)
+            check(L.hgs_blend2d_bwd_packed(ptr(records), ptr(backgrounds), C, D, int(normalize_depth), width, height,
+                                           tile_size, ptr(isect_offsets), ptr(flatten_ids), flatten_ids.numel(),
+                                           ptr(render_colors), ptr(render_alphas), ptr(last_ids), ptr(median_ids),
+                                           ptr(v_render_colors), ptr(v_render_alphas), ptr(v_render_normals),
+                                           ptr(v_render_distort), ptr(v_render_median), ptr(vpack), _stream()),
+                  "hgs_blend2d_bwd_packed")
+            _mark("blend2d_bwd", 1)
+            v_means2d = vpack[..., 0:2]
+            v_rt = vpack[..., 2:11].unflatten(-1, (3, 3))
+            v_normals = vpack[..., 11:14]
+            v_opacities = vpack[..., 14]
+            v_colors = vpack[..., 16:16 + CH]
+            v_depths = vpack[..., 16 + CH] if has_depth else None
+            v_densify = vpack[..., 20:22]
+        else:
+            v_means2d = torch.zeros_like(means2d)
+            v_rt = torch.zeros_like(ray_transforms)
+            v_colors = torch.zeros_like(colors)
+            v_depths = torch.zeros_like(depths) if depths is not None else None
+            v_normals = torch.zeros_like(normals)
+            v_opacities = torch.zeros_like(opacities)
+            v_densify = torch.zeros_like(means2d) if (ctx.needs_input_grad[6] or ctx.box is not None) else None
+            check(L.hgs_blend2d_bwd(ptr(means2d), ptr(ray_transforms), ptr(colors), ptr(depths), ptr(normals),
+                                    ptr(opacities), ptr(backgrounds), C, N, CH, width, height, tile_size,
+                                    ptr(isect_offsets), ptr(flatten_ids), flatten_ids.numel(), ptr(render_colors),
+                                    ptr(render_alphas), ptr(last_ids), ptr(median_ids), ptr(v_render_colors),
+                                    ptr(v_render_alphas), ptr(v_render_normals), ptr(v_render_distort),
+                                    ptr(v_render_median), ptr(v_means2d), ptr(v_rt), ptr(v_colors), ptr(v_depths),
+                                    ptr(v_normals), ptr(v_opacities), ptr(v_densify), _stream()), "hgs_blend2d_bwd")
         if ctx.box is not None:
             ctx.box["densify"] = v_densify  # picked up by rendering._DensifyInject / _DensifyProbe
         v_bg = None
         if backgrounds is not None and ctx.needs_input_grad[7]:
-            v_bg = (v_render_colors * (1.0 - render_alphas)).sum(dim=(1, 2))
+            vrc = v_render_colors
+            if normalize_depth:
+                vrc = torch.cat([vrc[..., :-1], vrc[..., -1:] / render_alphas.clamp(min=1e-10)], -1)
+            v_bg = (vrc * (1.0 - render_alphas)).sum(dim=(1, 2))
         return (v_means2d, v_rt, v_colors, v_depths, v_normals, v_opacities,
-                v_densify if ctx.needs_input_grad[6] else None, v_bg, None, None, None, None, None, None, None)
+                v_densify if ctx.needs_input_grad[6] else None, v_bg) + tail
 
 
 def _blend2d(means2d, ray_transforms, colors, depths, normals, opacities, densify, backgrounds, width, height,
-             tile_size, isect_offsets, flatten_ids, distloss=False, box=None):
+             tile_size, isect_offsets, flatten_ids, distloss=False, box=None, radii=None, normalize_depth=False,
+             vis_ids=None):
     if tile_size not in _TILE_SIZES:
         raise NotImplementedError(f"tile_size {tile_size} is not supported (supported: {_TILE_SIZES})")
     D = colors.shape[-1] + (1 if depths is not None else 0)
@@ -602,7 +663,7 @@ def _blend2d(means2d, ray_transforms, colors, depths, normals, opacities, densif
                           _f32c(colors, "colors"), _f32c(depths, "depths"), _f32c(normals, "normals"),
                           _f32c(opacities, "opacities"), densify, _f32c(backgrounds, "backgrounds"), int(width),
                           int(height), int(tile_size), isect_offsets.contiguous(), flatten_ids.contiguous(),
-                          bool(distloss), box)
+                          bool(distloss), box, radii, bool(normalize_depth), vis_ids)
 
 
 def rasterize_to_pixels_2dgs(means2d: Tensor, ray_transforms: Tensor, colors: Tensor, opacities: Tensor,

@@ -188,16 +188,20 @@ def rasterization_2dgs(
     tile_width = math.ceil(width / float(tile_size))
     tile_height = math.ceil(height / float(tile_size))
 
+    holder: Dict = {}
     radii, means2d, depths, ray_transforms, normals, tiles_per_gauss = W._project2d(
-        means, quats, scales, viewmats, Ks, width, height, near_plane, far_plane, radius_clip, tile_size)
+        means, quats, scales, viewmats, Ks, width, height, near_plane, far_plane, radius_clip, tile_size, holder)
     opac = opacities[None] if C == 1 else opacities[None].expand(C, -1)
 
     with torch.no_grad():
         isect_ids, flatten_ids, isect_offsets, vis_ids = W._isect_sorted_from_counts(
             means2d, radii, depths, tiles_per_gauss, C, N, tile_size, tile_width, tile_height)
+    holder["vis_ids"] = vis_ids
 
     feats = _per_view_features(means, colors, viewmats, radii, sh_degree, C, vis_ids)
     feats, depth_ch, bgs = _mode_features(feats, depths, backgrounds, render_mode)
+    n_ch = feats.shape[-1] + (1 if depth_ch is not None else 0)
+    fuse_norm = render_mode in ("ED", "RGB+ED") and n_ch in (1, 3, 4)
 
     grad_on = torch.is_grad_enabled() and means2d.requires_grad
     box: Optional[Dict] = {} if grad_on else None
@@ -207,10 +211,10 @@ def rasterization_2dgs(
 
     render_colors, render_alphas, render_normals, render_distort, render_median = W._blend2d(
         means2d_in, ray_transforms, feats, depth_ch, normals, opac, densify, bgs, width, height, tile_size,
-        isect_offsets, flatten_ids, distloss, box)
+        isect_offsets, flatten_ids, distloss, box, radii=radii, normalize_depth=fuse_norm, vis_ids=vis_ids)
 
     render_normals_from_depth = None
-    if render_mode in ("ED", "RGB+ED"):
+    if render_mode in ("ED", "RGB+ED") and not fuse_norm:
         render_colors = torch.cat(
             [render_colors[..., :-1], render_colors[..., -1:] / render_alphas.clamp(min=1e-10)], dim=-1)
     c2w = torch.linalg.inv(viewmats)

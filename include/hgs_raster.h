@@ -67,10 +67,13 @@ int hgs_project2d_fwd(const float* means, const float* quats, const float* scale
                       const float* Ks, int C, int N, int width, int height, float near_plane, float far_plane,
                       float radius_clip, int tile_size, int32_t* radii, float* means2d, float* depths,
                       float* ray_transforms, float* normals, int32_t* tiles_per_gauss, void* stream);
+/* upstream gradients (any may be NULL) with row strides in floats (2, 1, 9, 3 when dense); vis_ids as in
+ * hgs_project3d_bwd. */
 int hgs_project2d_bwd(const float* means, const float* quats, const float* scales, const float* viewmats,
                       const float* Ks, int C, int N, int width, int height, float near_plane, float far_plane,
-                      const int32_t* radii, const float* v_means2d, const float* v_depths,
-                      const float* v_ray_transforms, const float* v_normals, float* v_means, float* v_quats,
+                      const int32_t* radii, const float* v_means2d, int ld_means2d, const float* v_depths,
+                      int ld_depths, const float* v_ray_transforms, int ld_ray_transforms, const float* v_normals,
+                      int ld_normals, const int32_t* vis_ids, long long n_vis, float* v_means, float* v_quats,
                       float* v_scales, void* stream);
 
 /* ---- a7: spherical_harmonics (inside rasterization* when sh_degree is not None) ------------------
@@ -194,6 +197,29 @@ int hgs_blend2d_bwd(const float* means2d, const float* ray_transforms, const flo
                     const float* v_render_alphas, const float* v_render_normals, const float* v_render_distort,
                     const float* v_render_median, float* v_means2d, float* v_ray_transforms, float* v_colors,
                     float* v_depths, float* v_normals, float* v_opacities, float* v_densify, void* stream);
+
+/* Fast path of a12 (1, 3 or 4 colour channels incl. the depth channel): 96-byte surfel records (centre,
+ * opacity, ray transform, normal, colour, screen-space cull box) gathered by TMA bulk copies; per-warp culling;
+ * vpack[C*N,24] (zero-filled by the caller) accumulates the per-surfel gradients:
+ *   [0:2] v_means2d, [2:11] v_ray_transforms, [11:14] v_normals, [14] v_opacities, [16:16+D] v_colors
+ *   (+ v_depths in the last channel), [20:22] densification gradient.
+ * render_distort / v_render_distort NULL = distortion off. */
+size_t hgs_blend2d_pack_bytes(long long CN);
+int hgs_blend2d_pack(const float* means2d, const float* ray_transforms, const float* colors, const float* depths,
+                     const float* normals, const float* opacities, const int32_t* radii, const int32_t* vis_ids,
+                     long long n_vis, long long CN, int CH, void* records, void* stream);
+int hgs_blend2d_fwd_packed(const void* records, const float* backgrounds, int C, int D, int normalize_depth,
+                           int width, int height, int tile_size, const int32_t* isect_offsets,
+                           const int32_t* flatten_ids, long long n_isects, float* render_colors,
+                           float* render_alphas, float* render_normals, float* render_distort,
+                           float* render_median, int32_t* last_ids, int32_t* median_ids, void* stream);
+int hgs_blend2d_bwd_packed(const void* records, const float* backgrounds, int C, int D, int normalize_depth,
+                           int width, int height, int tile_size, const int32_t* isect_offsets,
+                           const int32_t* flatten_ids, long long n_isects, const float* render_colors,
+                           const float* render_alphas, const int32_t* last_ids, const int32_t* median_ids,
+                           const float* v_render_colors, const float* v_render_alphas,
+                           const float* v_render_normals, const float* v_render_distort,
+                           const float* v_render_median, float* vpack, void* stream);
 
 /* ---- f2 (next row of SURVEY.md section 8): densification statistics -------------------------------
  * One pass over the view-space gradient (scene/basic_model.py:96-144, the part fed by the rasterizer): for

@@ -327,3 +327,51 @@ def test_densification_stats_fused(mode):
     W.densification_stats_update(grad.cuda(), radii.cuda(), Wd, H, cacc2, cden2, cmax2, mode=mode, visible_ids=vis_ids)
     assert torch.allclose(cacc2.cpu(), acc, rtol=1e-5, atol=1e-5) and torch.equal(cden2.cpu(), den)
     assert torch.equal(cmax2, cmax)
+
+
+# ------------------------------------------------------------------------------------ plain (non-packed) kernels
+def test_blend3d_plain_kernels_five_channels():
+    """5..8 channels take the plain kernels (one pixel per thread, gsplat-style staging)."""
+    sc, V, Ks, Wd, H = small_scene(n=3000, width=128, height=96, scale=0.12)
+    m2, con, cols, op, off, flat = _stage_inputs(sc, V, Ks, Wd, H, True)
+    cols = torch.cat([cols, cols[..., :1] * 0.5], -1).contiguous()      # 5 channels
+    ins = [t.clone().requires_grad_() for t in (m2, con, cols, op)]
+    rc, ra = O.rasterize_to_pixels(*ins, Wd, H, 16, off, flat)
+    ws = [_rand_like(rc, 4), _rand_like(ra, 5)]
+    ref = _grads((rc, ra), ws, ins)
+    cins = [t.cuda().requires_grad_() for t in (m2, con, cols, op)]
+    crc, cra = hgs.rasterize_to_pixels(*cins, Wd, H, 16, off.cuda(), flat.cuda())
+    assert img_err(crc, rc) < IMG_ATOL and img_err(cra, ra) < IMG_ATOL
+    got = _grads((crc, cra), [w.cuda() for w in ws], cins)
+    for name, g, r in zip(("v_means2d", "v_conics", "v_colors", "v_opacities"), got, ref):
+        assert rel_err(g.cpu(), r) < GRAD_RTOL, (name, rel_err(g.cpu(), r))
+
+
+@pytest.mark.parametrize("D,distloss", [(3, False), (4, True), (2, True)])
+def test_blend2d_stage(D, distloss):
+    """rasterize_to_pixels_2dgs alone: D = 3/4 take the packed fast kernels, D = 2 the plain ones."""
+    sc, V, Ks, Wd, H = small_scene(n=2500, width=128, height=96, scale=0.15)
+    radii, m2, d, rt, nrm = O.fully_fused_projection_2dgs(sc.means, sc.quats, sc.scales, V, None, Ks, Wd, H)
+    tw, th = math.ceil(Wd / 16), math.ceil(H / 16)
+    _, ids, flat = O.isect_tiles(m2, radii, d, 16, tw, th)
+    off = O.isect_offset_encode(ids, 1, tw, th)
+    cols = torch.cat([sc.colors[None], d[..., None]], -1)[..., 4 - D:].contiguous()   # last channel = depth
+    op = sc.opacities[None].contiguous()
+    ins = [t.clone().requires_grad_() for t in (m2, rt, cols, op, nrm)]
+    outs = O.rasterize_to_pixels_2dgs(ins[0], ins[1], ins[2], ins[3], ins[4], Wd, H, 16, off, flat, distloss=distloss)
+    ws = [_rand_like(o, 30 + i) for i, o in enumerate(outs)]
+    ref = _grads(outs, ws, ins)
+    cins = [t.cuda().requires_grad_() for t in (m2, rt, cols, op, nrm)]
+    couts = hgs.rasterize_to_pixels_2dgs(cins[0], cins[1], cins[2], cins[3], cins[4], None, Wd, H, 16, off.cuda(),
+                                         flat.cuda(), distloss=distloss)
+    for name, c, r in zip(("colors", "alphas", "normals", "distort", "median"), couts, outs):
+        err = ((c.detach().cpu() - r.detach()).abs() / r.detach().abs().clamp(min=1.0))
+        if name == "median":
+            assert float((err > 2e-3).float().mean()) < 2e-3, name
+        else:
+            assert float(err.max()) < IMG_ATOL, (name, float(err.max()))
+    got = _grads(couts, [w.cuda() for w in ws], cins)
+    for name, g, r in zip(("v_means2d", "v_ray_transforms", "v_colors", "v_opacities", "v_normals"), got, ref):
+        if r is None:
+            continue
+        assert rel_err(g.cpu(), r) < 5 * GRAD_RTOL, (name, rel_err(g.cpu(), r))
