@@ -217,6 +217,7 @@ def run_ours(args):
     stats = torch.zeros(2, N, device=dev)
     step_stats = torch.zeros(2, N, device=dev) if world > 1 else None
     from horizongs_b200 import distributed as D
+    exchange = D.GradientExchange(params)       # no-op on one GPU
     # pinned host copies for the end-to-end arm
     gts_pin = gts_cpu.pin_memory()
     views_pin, Ks_pin = views_cpu.pin_memory(), Ks_cpu.pin_memory()
@@ -240,10 +241,9 @@ def run_ours(args):
             step_stats.zero_()
             Wr.densification_stats_update(meta["means2d"].grad, meta["radii"], W, H, step_stats[0], step_stats[1],
                                           visible_ids=meta["visible_ids"])
-            hs = D.allreduce_gradients(params, async_op=True)
-            hs.append(dist.all_reduce(step_stats, async_op=True))
-            for h in hs:
-                h.wait()
+            h = dist.all_reduce(step_stats, async_op=True)
+            exchange.wait()                      # gradient all-reduces were started inside backward()
+            h.wait()
             stats.add_(step_stats)
         else:
             Wr.densification_stats_update(meta["means2d"].grad, meta["radii"], W, H, stats[0], stats[1],

@@ -21,24 +21,32 @@ def _free_port():
     return p
 
 
-def _view_grads(sc, V, Ks, W, H, v):
+def _view_grads(sc, V, Ks, W, H, v, exchange=False):
     from oracle import gsplat_oracle as O
     params = [t.clone().requires_grad_() for t in (sc.means, sc.quats, sc.scales, sc.opacities, sc.colors)]
+    ex = D.GradientExchange(params) if exchange else None
     rc, ra, meta = O.rasterization(*params, V[v:v + 1], Ks[v:v + 1], W, H, render_mode="RGB+ED")
     meta["means2d"].retain_grad()
     (rc.sum() + ra.sum()).backward()
+    if ex is not None:
+        ex.wait()
+        ex.close()
     norm, vis = D.densification_statistics(meta["means2d"].grad, meta["radii"], W, H)
     return params, norm, vis
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, overlapped):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(2)
     sc, V, Ks, W, H = small_scene(n=400, C=2, width=64, height=48, scale=0.2)
     (v,) = D.shard_views(2, rank, world, step=0)
-    params, norm, vis = _view_grads(sc, V, Ks, W, H, v)
-    D.allreduce_gradients(params)
+    if overlapped:
+        # all-reduces start from post-accumulate hooks inside backward() (same order on every rank)
+        params, norm, vis = _view_grads(sc, V, Ks, W, H, v, exchange=True)
+    else:
+        params, norm, vis = _view_grads(sc, V, Ks, W, H, v)
+        D.allreduce_gradients(params)
     D.allreduce_densification(norm, vis, mode="mean")
     if rank == 0:
         torch.save({"grads": [p.grad for p in params], "norm": norm, "vis": vis}, out)
@@ -54,9 +62,10 @@ def test_shard_views_partition():
 
 
 @pytest.mark.timeout(300)
-def test_two_rank_allreduce_equals_single_process_accumulation(tmp_path):
+@pytest.mark.parametrize("overlapped", [False, True])
+def test_two_rank_allreduce_equals_single_process_accumulation(tmp_path, overlapped):
     out = str(tmp_path / "r0.pt")
-    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), out, overlapped), nprocs=2, join=True)
     got = torch.load(out)
     sc, V, Ks, W, H = small_scene(n=400, C=2, width=64, height=48, scale=0.2)
     ref_grads, ref_norm, ref_vis = None, 0, 0

@@ -82,6 +82,39 @@ def run(name, sc, V, Ks, Wd, H):
     return res
 
 
+def run2d(name, sc, V, Ks, Wd, H, distloss):
+    """config 2: 2DGS pipeline (rasterization_2dgs), forward and forward+backward."""
+    dev = "cuda"
+    sc = sc.to(dev)
+    V, Ks = V.to(dev), Ks.to(dev)
+    params = [x.detach().clone().requires_grad_() for x in (sc.means, sc.quats, sc.scales, sc.opacities, sc.colors)]
+    res = {"config": name, "N": sc.n, "W": Wd, "H": H, "distloss": distloss}
+
+    def fwd():
+        return hgs.rasterization_2dgs(*params, V, Ks, Wd, H, sh_degree=sc.sh_degree, render_mode="RGB+ED",
+                                      distloss=distloss)
+
+    with torch.no_grad():
+        (outs, meta), t = timed(fwd)
+    res["pipeline_fwd_ms"] = t
+    res["I"] = int(meta["flatten_ids"].numel())
+    res["n_visible"] = int((meta["radii"] > 0).sum())
+    g = [torch.rand_like(o) for o in outs[:3]]
+
+    def fwdbwd():
+        (rc, ra, rn, rnd, rd, rm), meta = fwd()
+        loss = (rc * g[0]).sum() + (ra * g[1]).sum() + 0.05 * (rn * g[2]).sum() + 0.05 * (1 - (rn * rnd).sum(-1)).mean()
+        if distloss:
+            loss = loss + 0.01 * rd.mean()
+        loss.backward()
+        for p in params:
+            p.grad = None
+
+    _, t = timed(fwdbwd)
+    res["pipeline_fwd_bwd_ms"] = t
+    print(json.dumps(res), flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="1a,1s,4")
@@ -94,6 +127,10 @@ if __name__ == "__main__":
             run("config1-aerial", *scenes.config1(view="aerial"))
         elif c == "1s":
             run("config1-street", *scenes.config1(view="street"))
+        elif c == "2":
+            for view in ("aerial", "street"):
+                for dl in (False, True):
+                    run2d(f"config2-2dgs-{view}", *scenes.config1(view=view), dl)
         elif c == "4":
             sc, V, Ks, Wd, H = scenes.config4(n_views=2)
             run("config4-view0-aerial", sc, V[:1], Ks[:1], Wd, H)
