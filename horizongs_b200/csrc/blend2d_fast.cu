@@ -6,10 +6,13 @@
 // gaussian_renderer/render.py:56-76).
 //
 // Cull test: a pixel can only be touched if its ray hits the surfel inside the disc u^2 + v^2 <= 2 tau
-// (tau = ln(255 o)), i.e. inside the projection of that disc -- whose exact screen-space bounding box follows
-// from the ray transform (same tangent-plane formula the projection uses for its radius, at level rho^2 = 2 tau)
-// -- or if it lies within sqrt(tau) pixels of the projected centre (screen-space low-pass term).  The union of
-// the two boxes (plus margin) is stored in the record; a warp skips a surfel whose box misses its 8x4 pixels.
+// (tau = ln(255 o)) or if it lies within sqrt(tau) pixels of the projected centre (screen-space low-pass term).
+// The pixel -> (u, v) map is the homography (u', v', w') = x (M1 x M2) + y (M2 x M0) + (M0 x M1), so the first
+// region is the conic u'^2 + v'^2 - 2 tau w'^2 <= 0 in pixel coordinates.  When it is an ellipse the pack
+// kernel (in double precision) stores its centre and normalised quadratic form; a warp evaluates the exact
+// minimum of that form over its 8x4 pixel rectangle, exactly like the 3DGS kernels -- important for surfels
+// seen at grazing angles, whose bounding boxes are huge but whose footprints are thin slivers.  Degenerate or
+// unbounded conics are never culled.
 #include "blend_common.cuh"
 #include "../../include/hgs_raster.h"
 
@@ -19,7 +22,7 @@ using namespace hgs;
 
 constexpr int TS = HGS_TILE_SIZE;
 constexpr int BLK = TS * TS;
-constexpr int REC2_BYTES = 96;
+constexpr int REC2_BYTES = 112;
 constexpr int SLOT2_BYTES = 112;   // 7 x 16 B: lane-parallel float4 reads are conflict-free
 constexpr int FB2 = 64;            // surfels per batch
 constexpr int VP2 = 24;            // floats per row of the packed gradient buffer
@@ -30,7 +33,8 @@ struct __align__(16) SRec {
     float v[3], ny;         // q2: M1, normal.y
     float w[3], nz;         // q3: M2, normal.z
     float col[4];           // q4
-    float bx, by, hx, hy;   // q5: cull box centre / half extents
+    float ex, ey, QA, QB;   // q5: ellipse centre, normalised form F(d) = QA dx^2 + QB dx dy + QC dy^2 (footprint F <= 1)
+    float QC, lp2, kx, ky;  // q6: ..., squared low-pass radius (< 0: never visible), edge-optimum slopes
 };
 static_assert(sizeof(SRec) == REC2_BYTES, "record size");
 
@@ -52,34 +56,46 @@ __global__ void pack2d_kernel(const float* __restrict__ means2d, const float* __
     r.nx = normals[i * 3]; r.ny = normals[i * 3 + 1]; r.nz = normals[i * 3 + 2];
 #pragma unroll
     for (int k = 0; k < 4; ++k) r.col[k] = (k < CH) ? colors[i * CH + k] : ((k == CH && depths != nullptr) ? depths[i] : 0.f);
-    // cull box
-    float bx = m.x, by = m.y, hx = -1.f, hy = -1.f;             // negative extent: never touched
+    // cull data
+    float ex = m.x, ey = m.y, QA = 0.f, QB = 0.f, QC = 0.f, lp2 = -1.f;   // QA = QB = QC = 0: never culled
     const float o = r.opac;
     if (o * 255.0f >= 1.0f) {
-        const float tau = logf(255.0f * o);
-        const float rd = sqrtf(tau);                              // low-pass disc radius
-        float lox = m.x - rd, hix = m.x + rd, loy = m.y - rd, hiy = m.y + rd;
-        const float rho2 = 2.0f * tau;
-        const float dist = rho2 * (r.w[0] * r.w[0] + r.w[1] * r.w[1]) - r.w[2] * r.w[2];
-        if (dist < 0.f) {
-            const float inv = 1.0f / dist;
-            const float f0 = rho2 * inv, f1 = rho2 * inv, f2 = -inv;
-            const float cx = f0 * r.u[0] * r.w[0] + f1 * r.u[1] * r.w[1] + f2 * r.u[2] * r.w[2];
-            const float cy = f0 * r.v[0] * r.w[0] + f1 * r.v[1] * r.w[1] + f2 * r.v[2] * r.w[2];
-            const float tx = f0 * r.u[0] * r.u[0] + f1 * r.u[1] * r.u[1] + f2 * r.u[2] * r.u[2];
-            const float ty = f0 * r.v[0] * r.v[0] + f1 * r.v[1] * r.v[1] + f2 * r.v[2] * r.v[2];
-            const float ex = sqrtf(fmaxf(cx * cx - tx, 0.f)), ey = sqrtf(fmaxf(cy * cy - ty, 0.f));
-            lox = fminf(lox, cx - ex); hix = fmaxf(hix, cx + ex);
-            loy = fminf(loy, cy - ey); hiy = fmaxf(hiy, cy + ey);
-            bx = 0.5f * (lox + hix); by = 0.5f * (loy + hiy);
-            hx = 0.5f * (hix - lox) * 1.01f + 0.1f;
-            hy = 0.5f * (hiy - loy) * 1.01f + 0.1f;
-        } else {
-            hx = 1e30f; hy = 1e30f;                               // disc crosses the camera plane: unbounded
+        const double tau = log(255.0 * (double)o);
+        lp2 = (float)tau * 1.02f + 0.05f;
+        const double rho2 = 2.0 * tau;
+        const double u[3] = {r.u[0], r.u[1], r.u[2]}, v[3] = {r.v[0], r.v[1], r.v[2]}, w[3] = {r.w[0], r.w[1], r.w[2]};
+        // (u', v', w') = x a + y b + c
+        const double a[3] = {v[1] * w[2] - v[2] * w[1], v[2] * w[0] - v[0] * w[2], v[0] * w[1] - v[1] * w[0]};
+        const double b[3] = {w[1] * u[2] - w[2] * u[1], w[2] * u[0] - w[0] * u[2], w[0] * u[1] - w[1] * u[0]};
+        const double c[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+        const double sg[3] = {1.0, 1.0, -rho2};
+        double qxx = 0, qxy = 0, qyy = 0, qx = 0, qy = 0, q0 = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            qxx += sg[k] * a[k] * a[k]; qxy += sg[k] * a[k] * b[k]; qyy += sg[k] * b[k] * b[k];
+            qx += sg[k] * a[k] * c[k];  qy += sg[k] * b[k] * c[k];  q0 += sg[k] * c[k] * c[k];
         }
-        if (!(hx == hx) || !(hy == hy) || !(bx == bx) || !(by == by)) { bx = m.x; by = m.y; hx = 1e30f; hy = 1e30f; }
+        const double det2 = qxx * qyy - qxy * qxy;
+        if (qxx > 0.0 && qyy > 0.0 && det2 > 1e-9 * qxx * qyy) {
+            const double cx = -(qyy * qx - qxy * qy) / det2, cy = -(qxx * qy - qxy * qx) / det2;
+            const double kappa = -(q0 + qx * cx + qy * cy);
+            if (kappa > 0.0) {
+                const double sc = 1.0 / (kappa * 1.02);            // 2 % margin on the footprint
+                ex = (float)cx; ey = (float)cy;
+                QA = (float)(qxx * sc); QB = (float)(2.0 * qxy * sc); QC = (float)(qyy * sc);
+                if (!(QA == QA) || !(QB == QB) || !(QC == QC) || !(ex == ex) || !(ey == ey) || isinf(QA) || isinf(QC)) {
+                    ex = m.x; ey = m.y; QA = 0.f; QB = 0.f; QC = 0.f;
+                }
+            }
+        }
+    } else {
+        QA = 1e30f; QC = 1e30f;                                   // opacity below 1/255: never visible
+        ex = -1e30f; ey = -1e30f;
     }
-    r.bx = bx; r.by = by; r.hx = hx; r.hy = hy;
+    r.ex = ex; r.ey = ey; r.QA = QA; r.QB = QB;
+    r.QC = QC; r.lp2 = lp2;
+    r.kx = (QC != 0.f) ? -QB / (2.f * QC) : 0.f;
+    r.ky = (QA != 0.f) ? -QB / (2.f * QA) : 0.f;
     float4* dst = reinterpret_cast<float4*>(recs + i);
     const float4* src = reinterpret_cast<const float4*>(&r);
 #pragma unroll
@@ -89,8 +105,28 @@ __global__ void pack2d_kernel(const float* __restrict__ means2d, const float* __
 __device__ __forceinline__ const float4* slot2(const unsigned char* stage, int t) {
     return reinterpret_cast<const float4*>(stage + t * SLOT2_BYTES);
 }
-__device__ __forceinline__ bool cull2_keep(const float4 q5, float X0, float X1, float Y0, float Y1) {
-    return !(q5.x + q5.z < X0 || q5.x - q5.z > X1 || q5.y + q5.w < Y0 || q5.y - q5.w > Y1);
+// keep the surfel if the rectangle of pixel centres [X0,X1]x[Y0,Y1] meets its footprint ellipse
+// (minimum of the convex form over the rectangle <= 1) or comes within the low-pass radius of its centre
+__device__ __forceinline__ bool cull2_keep(const float4 q0, const float4 q5, const float4 q6, float X0, float X1,
+                                           float Y0, float Y1) {
+    if (q6.y < 0.f) return false;
+    // low-pass disc around the projected centre
+    const float ddx = fmaxf(fmaxf(X0 - q0.x, q0.x - X1), 0.f), ddy = fmaxf(fmaxf(Y0 - q0.y, q0.y - Y1), 0.f);
+    if (ddx * ddx + ddy * ddy <= q6.y) return true;
+    const float u0 = X0 - q5.x, u1 = X1 - q5.x, v0 = Y0 - q5.y, v1 = Y1 - q5.y;
+    if (u0 <= 0.f && u1 >= 0.f && v0 <= 0.f && v1 >= 0.f) return true;
+    const float A = q5.z, B = q5.w, C = q6.x;
+    // value of the form minus a bound of its float32 rounding error (thin, long ellipses cancel heavily)
+    auto lower = [&](float u, float v) {
+        const float val = (A * u + B * v) * u + C * v * v;
+        const float mag = (fabsf(A * u) + fabsf(B * v)) * fabsf(u) + fabsf(C) * v * v;
+        return val - 4e-6f * mag;
+    };
+    float best = lower(u0, fminf(fmaxf(q6.z * u0, v0), v1));
+    best = fminf(best, lower(u1, fminf(fmaxf(q6.z * u1, v0), v1)));
+    best = fminf(best, lower(fminf(fmaxf(q6.w * v0, u0), u1), v0));
+    best = fminf(best, lower(fminf(fmaxf(q6.w * v1, u0), u1), v1));
+    return best <= 1.0f;
 }
 
 struct Eval2 {
@@ -186,7 +222,10 @@ __global__ void __launch_bounds__(BLK) blend2d_fwd_fast_kernel(
             for (int grp = 0; grp * 32 < batch_n; ++grp) {
                 const int t = grp * 32 + g.lane;
                 bool keep = false;
-                if (t < batch_n) keep = cull2_keep(slot2(stage, t)[5], g.X0, g.X1, g.Y0, g.Y1);
+                if (t < batch_n) {
+                    const float4* q = slot2(stage, t);
+                    keep = cull2_keep(q[0], q[5], q[6], g.X0, g.X1, g.Y0, g.Y1);
+                }
                 unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
                 while (m) {
                     const int j = __ffs(m) - 1;
@@ -378,7 +417,10 @@ __global__ void __launch_bounds__(BLK) blend2d_bwd_fast_kernel(
         for (int grp = t_first >> 5; grp * 32 < batch_n; ++grp) {
             const int t = grp * 32 + g.lane;
             bool keep = false;
-            if (t < batch_n && t >= t_first) keep = cull2_keep(slot2(stage, t)[5], g.X0, g.X1, g.Y0, g.Y1);
+            if (t < batch_n && t >= t_first) {
+                const float4* q = slot2(stage, t);
+                keep = cull2_keep(q[0], q[5], q[6], g.X0, g.X1, g.Y0, g.Y1);
+            }
             unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
             unsigned written = 0u;
             while (m) {

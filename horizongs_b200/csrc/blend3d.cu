@@ -89,17 +89,16 @@ __device__ __forceinline__ bool cull_keep(const float4 q0, const float4 q1, cons
     const float A = q0.z, B = q0.w, C = q1.x;
     const float thr = q1.z - CULL_MARGIN;
     if (u0 <= 0.f && u1 >= 0.f && v0 <= 0.f && v1 >= 0.f) return thr <= 0.f;
-    float best;
-    {
-        float v = fminf(fmaxf(q3.x * u0, v0), v1);
-        best = (A * u0 + B * v) * u0 + C * v * v;
-        v = fminf(fmaxf(q3.x * u1, v0), v1);
-        best = fmaxf(best, (A * u1 + B * v) * u1 + C * v * v);
-        float u = fminf(fmaxf(q3.y * v0, u0), u1);
-        best = fmaxf(best, (A * u + B * v0) * u + C * v0 * v0);
-        u = fminf(fmaxf(q3.y * v1, u0), u1);
-        best = fmaxf(best, (A * u + B * v1) * u + C * v1 * v1);
-    }
+    // value of the exponent plus a bound of its float32 rounding error (long thin Gaussians cancel heavily)
+    auto upper = [&](float u, float v) {
+        const float val = (A * u + B * v) * u + C * v * v;
+        const float mag = (fabsf(A * u) + fabsf(B * v)) * fabsf(u) + fabsf(C) * v * v;
+        return val + 4e-6f * mag;
+    };
+    float best = upper(u0, fminf(fmaxf(q3.x * u0, v0), v1));
+    best = fmaxf(best, upper(u1, fminf(fmaxf(q3.x * u1, v0), v1)));
+    best = fmaxf(best, upper(fminf(fmaxf(q3.y * v0, u0), u1), v0));
+    best = fmaxf(best, upper(fminf(fmaxf(q3.y * v1, u0), u1), v1));
     return best >= thr;
 }
 

@@ -51,14 +51,19 @@ __device__ __forceinline__ bool proj3d_math(const HgsCam& cam, float px, float p
 // from ||J||_F^2 * max(scale)^2 (lambda_max of J Sigma J^T <= ||J||_F^2 lambda_max(Sigma)), the tan-fov clamp
 // bounds of J, eps2d and the 0.01 eigenvalue floor.  true => the full computation would cull the Gaussian by
 // its screen-bounds test, so the covariance math (and the quaternion load) can be skipped with identical output.
-__device__ __forceinline__ bool proj3d_surely_offscreen(const HgsCam& cam, float xc, float yc, float zc, float smax,
-                                                        float W, float H, float eps2d) {
+// per-camera constant of the bound: fx^2 (1 + Lx^2) + fy^2 (1 + Ly^2), L = largest clamped |x/z|
+__device__ __forceinline__ float proj3d_jf_coeff(const HgsCam& cam, float W, float H) {
     const float fx = cam.fx, fy = cam.fy, cx = cam.cx, cy = cam.cy;
-    const float rz = 1.0f / zc;
     const float tan_fovx = 0.5f * W / fx, tan_fovy = 0.5f * H / fy;
     const float Lx = fmaxf((W - cx) / fx, cx / fx) + HGS_FOV_MARGIN * tan_fovx;
     const float Ly = fmaxf((H - cy) / fy, cy / fy) + HGS_FOV_MARGIN * tan_fovy;
-    const float jf2 = rz * rz * (fx * fx * (1.0f + Lx * Lx) + fy * fy * (1.0f + Ly * Ly));
+    return fx * fx * (1.0f + Lx * Lx) + fy * fy * (1.0f + Ly * Ly);
+}
+__device__ __forceinline__ bool proj3d_surely_offscreen(const HgsCam& cam, float jf_coeff, float xc, float yc, float zc,
+                                                        float smax, float W, float H, float eps2d) {
+    const float fx = cam.fx, fy = cam.fy, cx = cam.cx, cy = cam.cy;
+    const float rz = 1.0f / zc;
+    const float jf2 = rz * rz * jf_coeff;
     const float v1_bound = jf2 * smax * smax + eps2d + 0.1f + HGS_EIG_FLOOR;
     const float rb = (HGS_RADIUS_SIGMA * sqrtf(v1_bound) + 1.0f) * 1.001f + 0.01f;
     const float m2x = fx * xc * rz + cx, m2y = fy * yc * rz + cy;
@@ -150,6 +155,7 @@ __global__ void __launch_bounds__(PB) project3d_fwd_kernel(
     __shared__ int s_ri[PB * 2];         // radius, tile count
     __shared__ int s_list[PB];
     __shared__ int s_wcnt[PB / 32];
+    __shared__ float s_cam[26];          // viewmat (16), K (9), bound coefficient
     const int c = blockIdx.y;
     const long long base = (long long)blockIdx.x * PB;
     const long long n = base + threadIdx.x;
@@ -160,8 +166,21 @@ __global__ void __launch_bounds__(PB) project3d_fwd_kernel(
     s_ri[threadIdx.x * 2] = 0; s_ri[threadIdx.x * 2 + 1] = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) s_out[threadIdx.x * 4 + k] = 0.f;
+    // camera: loaded once per block, the derived bound coefficient computed by one thread
+    if (threadIdx.x < 16) s_cam[threadIdx.x] = viewmats[c * 16 + threadIdx.x];
+    else if (threadIdx.x < 25) s_cam[threadIdx.x] = Ks[c * 9 + threadIdx.x - 16];
     __syncthreads();
-    const HgsCam cam = hgs_load_cam(viewmats, Ks, c);
+    HgsCam cam;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) cam.R[i][j] = s_cam[i * 4 + j];
+        cam.t[i] = s_cam[i * 4 + 3];
+    }
+    cam.fx = s_cam[16]; cam.fy = s_cam[20]; cam.cx = s_cam[18]; cam.cy = s_cam[21];
+    if (threadIdx.x == 0) s_cam[25] = proj3d_jf_coeff(cam, (float)W, (float)H);
+    __syncthreads();
+    const float jf_coeff = s_cam[25];
     const float (*R)[3] = cam.R;
 
     // ---- phase 1
@@ -173,8 +192,8 @@ __global__ void __launch_bounds__(PB) project3d_fwd_kernel(
         if (!(zc < near_plane || zc > far_plane)) {
             const float xc = R[0][0] * px + R[0][1] * py + R[0][2] * pz + cam.t[0];
             const float yc = R[1][0] * px + R[1][1] * py + R[1][2] * pz + cam.t[1];
-            pass = !proj3d_surely_offscreen(cam, xc, yc, zc, fmaxf(fabsf(s0), fmaxf(fabsf(s1), fabsf(s2))), (float)W,
-                                            (float)H, eps2d);
+            pass = !proj3d_surely_offscreen(cam, jf_coeff, xc, yc, zc, fmaxf(fabsf(s0), fmaxf(fabsf(s1), fabsf(s2))),
+                                            (float)W, (float)H, eps2d);
             if (pass) { s_pc[threadIdx.x * 3] = xc; s_pc[threadIdx.x * 3 + 1] = yc; s_pc[threadIdx.x * 3 + 2] = zc; }
         }
     }

@@ -351,11 +351,30 @@ __global__ void __launch_bounds__(SB) sh_bwd_fused_kernel(const float* __restric
         }
         __syncthreads();
     }
-    // coalesced write of all rows of the block
-    float* dst = v_coeffs + base * rowlen;
+    // coalesced write of all rows of the block: 16-byte stores; a float4 whose (at most two) rows are both
+    // culled -- the common case -- is a plain zero store
     const int tot = (int)rows * rowlen;                                   // <= 128 * 75
     const unsigned magic = 0xFFFFFFFFu / (unsigned)rowlen + 1u;           // i / rowlen == umulhi(i, magic) here
-    for (int i = threadIdx.x; i < tot; i += SB) {
+    float* dst = v_coeffs + base * rowlen;                                // 16-byte aligned: SB * rowlen * 4 % 16 == 0
+    const int tot4 = tot >> 2;
+    for (int v4 = threadIdx.x; v4 < tot4; v4 += SB) {
+        const int i0 = v4 << 2;
+        const int r0 = (int)__umulhi((unsigned)i0, magic), r1 = (int)__umulhi((unsigned)(i0 + 3), magic);
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s_slot[r0] >= 0 || s_slot[r1] >= 0) {
+            float e[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = i0 + k;
+                const int r = (int)__umulhi((unsigned)i, magic), c = i - r * rowlen;
+                const int sl = s_slot[r];
+                e[k] = (sl >= 0 && c < RL) ? s_rows[sl * RS + c] : 0.f;
+            }
+            o = make_float4(e[0], e[1], e[2], e[3]);
+        }
+        reinterpret_cast<float4*>(dst)[v4] = o;
+    }
+    for (int i = (tot4 << 2) + threadIdx.x; i < tot; i += SB) {          // tail of a partial last block
         const int r = (int)__umulhi((unsigned)i, magic), c = i - r * rowlen;
         const int sl = s_slot[r];
         dst[i] = (sl >= 0 && c < RL) ? s_rows[sl * RS + c] : 0.f;

@@ -198,8 +198,8 @@ int hgs_blend2d_bwd(const float* means2d, const float* ray_transforms, const flo
                     const float* v_render_median, float* v_means2d, float* v_ray_transforms, float* v_colors,
                     float* v_depths, float* v_normals, float* v_opacities, float* v_densify, void* stream);
 
-/* Fast path of a12 (1, 3 or 4 colour channels incl. the depth channel): 96-byte surfel records (centre,
- * opacity, ray transform, normal, colour, screen-space cull box) gathered by TMA bulk copies; per-warp culling;
+/* Fast path of a12 (1, 3 or 4 colour channels incl. the depth channel): 112-byte surfel records (centre,
+ * opacity, ray transform, normal, colour, footprint ellipse) gathered by TMA bulk copies; per-warp culling;
  * vpack[C*N,24] (zero-filled by the caller) accumulates the per-surfel gradients:
  *   [0:2] v_means2d, [2:11] v_ray_transforms, [11:14] v_normals, [14] v_opacities, [16:16+D] v_colors
  *   (+ v_depths in the last channel), [20:22] densification gradient.
