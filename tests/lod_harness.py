@@ -1,0 +1,103 @@
+"""A miniature of Horizon-GS's LOD anchor model + render() for BASELINE.json configs[3] (test harness only).
+
+It mirrors the *call pattern* of the reference adapter (gaussian_renderer/render.py:16-118 render(),
+:120-197 prefilter_voxel()) and of the anchor decode (scene/basic_model.py:297-371
+generate_neural_gaussians; scene/lod_model.py:286-290 set_anchor_mask) with a backend switch: the same
+Python runs on the CPU oracle and on the CUDA operators.  The decode stays in PyTorch, as in the reference.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+
+class TinyAnchorModel(nn.Module):
+    def __init__(self, n_anchors=600, n_offsets=10, feat_dim=32, levels=3, extent=3.0, seed=0):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.n_offsets, self.levels = n_offsets, levels
+        self.standard_dist, self.fork = 8.0, 2
+        anchor = (torch.rand(n_anchors, 3, generator=g) * 2 - 1) * extent
+        anchor[:, 2] = anchor[:, 2].abs() * 0.3
+        self.anchor = nn.Parameter(anchor)
+        self.level = torch.randint(0, levels, (n_anchors,), generator=g)
+        voxel = 0.4 / (2.0 ** self.level.float())
+        self.offset = nn.Parameter(torch.randn(n_anchors, n_offsets, 3, generator=g) * 0.3)
+        self.anchor_feat = nn.Parameter(torch.randn(n_anchors, feat_dim, generator=g) * 0.5)
+        self.scaling = nn.Parameter(torch.log(voxel)[:, None].expand(-1, 6).contiguous())   # exp() activation
+        rot = torch.zeros(n_anchors, 4)
+        rot[:, 0] = 1.0
+        self.rotation = rot                                                   # identity wxyz (lod_model.py:269-270)
+        torch.manual_seed(seed)
+        mlp = lambda out: nn.Sequential(nn.Linear(feat_dim + 3, feat_dim), nn.ReLU(True), nn.Linear(feat_dim, out))  # noqa: E731
+        self.mlp_opacity = nn.Sequential(mlp(n_offsets), nn.Tanh())
+        self.mlp_cov = mlp(7 * n_offsets)
+        self.mlp_color = nn.Sequential(mlp(3 * n_offsets), nn.Sigmoid())
+
+    def anchor_mask(self, cam_center):
+        """scene/lod_model.py:286-290 + basic_model.py:192-210: level <= int level of the view distance"""
+        dist = (self.anchor.detach() - cam_center).norm(dim=1)
+        lvl = torch.log2(self.standard_dist / dist) / math.log2(self.fork)
+        int_level = lvl.floor().clamp(0, self.levels - 1).long()
+        return self.level.to(self.anchor.device) <= int_level
+
+    def decode(self, cam_center, visible_mask):
+        """scene/basic_model.py:297-371 with color_attr == 'RGB', view_dim 3, appearance_dim 0"""
+        anchor = self.anchor[visible_mask]
+        feat = self.anchor_feat[visible_mask]
+        offsets = self.offset[visible_mask]
+        scaling = torch.exp(self.scaling[visible_mask])
+        view = anchor - cam_center
+        view = view / view.norm(dim=1, keepdim=True)
+        x = torch.cat([feat, view], 1)
+        k = self.n_offsets
+        opacity = self.mlp_opacity(x).reshape(-1, 1)
+        mask = (opacity > 0).view(-1)
+        color = self.mlp_color(x).reshape(-1, 3)
+        scale_rot = self.mlp_cov(x).reshape(-1, 7)
+        rep = torch.cat([scaling, anchor], -1).repeat_interleave(k, 0)
+        allv = torch.cat([rep, color, scale_rot, offsets.reshape(-1, 3)], -1)[mask]
+        s_rep, a_rep, color, scale_rot, off = allv.split([6, 3, 3, 7, 3], -1)
+        scales = s_rep[:, 3:] * torch.sigmoid(scale_rot[:, :3])
+        quats = torch.nn.functional.normalize(scale_rot[:, 3:7])
+        xyz = a_rep + off * s_rep[:, :3]
+        return xyz, color, opacity[mask], scales, quats
+
+
+def render(model, viewmat, K, width, height, bg, backend, two_d=False):
+    """the reference adapter's control flow; `backend` is a module-like object exposing the gsplat names"""
+    dev = model.anchor.device
+    cam_center = torch.linalg.inv(viewmat)[:3, 3]
+    amask = model.anchor_mask(cam_center)
+    # prefilter_voxel(): project the anchors as Gaussians, keep radii > 0 (render.py:120-197)
+    means = model.anchor.detach()[amask]
+    scales = torch.exp(model.scaling.detach()[amask])[:, :3]
+    quats = model.rotation.to(dev)[amask]
+    with torch.no_grad():
+        if two_d:
+            dens = torch.zeros((1, means.shape[0], 2), device=dev)
+            proj = backend.fully_fused_projection_2dgs(means, quats, scales, viewmat[None], dens, K[None], int(width),
+                                                       int(height), eps2d=0.3, packed=False, near_plane=0.01,
+                                                       far_plane=1e10, radius_clip=0.0, sparse_grad=False)
+        else:
+            proj = backend.fully_fused_projection(means, None, quats, scales, viewmat[None], K[None], int(width),
+                                                  int(height), eps2d=0.3, packed=False, near_plane=0.01,
+                                                  far_plane=1e10, radius_clip=0.0, sparse_grad=False,
+                                                  calc_compensations=False)
+    visible = amask.clone()
+    visible[amask] = proj[0].squeeze(0) > 0
+    xyz, color, opacity, scaling, rot = model.decode(cam_center, visible)
+    kw = dict(means=xyz, quats=rot, scales=scaling, opacities=opacity.squeeze(-1), colors=color,
+              viewmats=viewmat[None], Ks=K[None], backgrounds=bg[None], width=int(width), height=int(height),
+              packed=False, sh_degree=None, render_mode="RGB+ED")
+    if two_d:
+        (rc, ra, rn, rnd, rd, rm), info = backend.rasterization_2dgs(**kw)
+    else:
+        rc, ra, info = backend.rasterization(**kw)
+    info["means2d"].retain_grad()
+    out = {"render": rc[0, ..., :3].permute(2, 0, 1), "render_depth": rc[0, ..., 3:4].permute(2, 0, 1),
+           "render_alphas": ra[0].permute(2, 0, 1), "viewspace_points": info["means2d"],
+           "radii": info["radii"].squeeze(0), "visible_mask": visible, "n_gaussians": xyz.shape[0]}
+    if two_d:
+        out.update(render_normals=rn, render_normals_from_depth=rnd)
+    return out
