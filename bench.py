@@ -146,6 +146,23 @@ def oracle_full_frame_estimate(sc, view, K, win, threads):
     return t_gauss + t_pix * scale, t_step, n_isect
 
 
+def centre_window(w, h):
+    return (WIDTH // 2 - w // 2, HEIGHT // 2 - h // 2, w, h)
+
+
+def pick_window(sc, view, K, threads):
+    """the bounded sample: a centre window sized so that one oracle step is roughly 10-30 s of CPU work on this host
+    (192x128 first; a fast host re-runs with 4x / 16x the pixels).  -> (estimate, seconds, isects, window)"""
+    win = centre_window(192, 128)
+    est, t_step, n_isect = oracle_full_frame_estimate(sc, view, K, win, threads)
+    for w, h in ((384, 256), (768, 512)):
+        if t_step >= 5.0:
+            break
+        win = centre_window(w, h)
+        est, t_step, n_isect = oracle_full_frame_estimate(sc, view, K, win, threads)
+    return est, t_step, n_isect, win
+
+
 def run_reference(args):
     """--impl reference: the CPU oracle port on a bounded sample, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -154,10 +171,10 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     steps, warm = args.steps, args.warmup
     sc, views, Ks, W, H, _ = make_workload(args.gaussians)
-    # window sized so that (steps + warmup) samples end within a few minutes
-    win = (W // 2 - 96, H // 2 - 64, 192, 128)
-    ests = []
+    # window sized so that one sample is 10-30 s of CPU work and (steps + warmup) samples end within a few minutes
     t_all = time.time()
+    _, _, _, win = pick_window(sc, views[0], Ks[0], threads)
+    ests = []
     for s in range(warm + steps):
         v = s % N_VIEWS
         est, t_step, n_isect = oracle_full_frame_estimate(sc, views[v], Ks[v], win, threads)
@@ -217,7 +234,27 @@ def run_ours(args):
     stats = torch.zeros(2, N, device=dev)
     step_stats = torch.zeros(2, N, device=dev) if world > 1 else None
     from horizongs_b200 import distributed as D
-    exchange = D.GradientExchange(params)       # no-op on one GPU
+    # gradient exchange (N > 1): sparse all-reduce over NVLink peer memory (csrc/exchange.cu); the dense NCCL
+    # all-reduce stays available (--exchange nccl) and is the fallback if peer memory cannot be mapped
+    peer, exchange, exchange_name = None, None, "none (1 GPU)"
+    if world > 1 and args.exchange == "peer":
+        try:
+            peer = D.PeerGradientExchange((3, 4, 3, 1, 27, 1, 1), N, cap_rows=N // 4, device=dev)
+            exchange_name = ("sparse all-reduce over NVLink peer memory (own kernels, csrc/exchange.cu): each rank stores "
+                             "the 40-float records (38 gradients + 2 densification statistics) of its visible Gaussians "
+                             "into every peer's mailbox, then merges all ranks' records in rank order")
+        except Exception as e:  # noqa: BLE001
+            log(f"[bench] rank {rank}: peer-memory exchange unavailable ({e}); using the NCCL all-reduce")
+            peer = None
+        ok = torch.tensor([1 if peer is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0 and peer is not None:
+            peer = None
+    if world > 1 and peer is None:
+        exchange = D.GradientExchange(params)
+        exchange_name = ("NCCL all-reduce of 38 floats/Gaussian gradients + 2 floats/Gaussian densification statistics "
+                         "per step")
+    copy_stream = torch.cuda.Stream(device=dev)
     # pinned host copies for the end-to-end arm
     gts_pin = gts_cpu.pin_memory()
     views_pin, Ks_pin = views_cpu.pin_memory(), Ks_cpu.pin_memory()
@@ -225,14 +262,22 @@ def run_ours(args):
     def step(s, e2e=False):
         v = (rank + s) % N_VIEWS
         if e2e:
+            # camera first (the forward needs it at once); the 25 MB ground-truth image is copied on a second
+            # stream while the forward runs and joined just before the loss
             view = views_pin[v:v + 1].to(dev, non_blocking=True)
             Km = Ks_pin[v:v + 1].to(dev, non_blocking=True)
-            gt = gts_pin[v:v + 1].to(dev, non_blocking=True)
+            main = torch.cuda.current_stream()
+            copy_stream.wait_stream(main)
+            with torch.cuda.stream(copy_stream):
+                gt = gts_pin[v:v + 1].to(dev, non_blocking=True)
+            gt.record_stream(main)
         else:
             view, Km, gt = views[v:v + 1], Ks[v:v + 1], gts[v:v + 1]
         rc, ra, meta = hgs.rasterization(params[0], params[1], params[2], params[3], params[4], view, Km, W, H,
                                          sh_degree=2, render_mode="RGB+ED", backgrounds=bg, packed=False)
         meta["means2d"].retain_grad()
+        if e2e:
+            torch.cuda.current_stream().wait_stream(copy_stream)
         loss = loss_fn(rc, ra, gt)
         loss.backward()
         # densification statistics from the view-space gradient (basic_model.py:131-144), one fused kernel;
@@ -241,9 +286,12 @@ def run_ours(args):
             step_stats.zero_()
             Wr.densification_stats_update(meta["means2d"].grad, meta["radii"], W, H, step_stats[0], step_stats[1],
                                           visible_ids=meta["visible_ids"])
-            h = dist.all_reduce(step_stats, async_op=True)
-            exchange.wait()                      # gradient all-reduces were started inside backward()
-            h.wait()
+            if peer is not None:
+                peer.exchange([p.grad for p in params] + [step_stats[0], step_stats[1]], meta["visible_ids"])
+            else:
+                h = dist.all_reduce(step_stats, async_op=True)
+                exchange.wait()                  # gradient all-reduces were started inside backward()
+                h.wait()
             stats.add_(step_stats)
         else:
             Wr.densification_stats_update(meta["means2d"].grad, meta["radii"], W, H, stats[0], stats[1],
@@ -306,6 +354,8 @@ def run_ours(args):
     for s in range(2):
         step(s, e2e=True)
     ms_e2e, _ = timed(args.steps, args.warmup, e2e=True)
+    if peer is not None:
+        peer.check_status()
     clk = clocks.stop() if rank == 0 else None
 
     # ---- forward-only render FPS (reference method: torch.no_grad around render(), render.py:79-83,177)
@@ -319,6 +369,8 @@ def run_ours(args):
         torch.cuda.synchronize()
         fps = args.steps / (time.perf_counter() - t0)
 
+    if peer is not None:
+        peer.close()
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -382,9 +434,8 @@ def run_ours(args):
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        win = (W // 2 - 96, H // 2 - 64, 192, 128)
         t0 = time.time()
-        est, t_step, _ = oracle_full_frame_estimate(sc_cpu, views_cpu[0], Ks_cpu[0], win, threads)
+        est, t_step, _, win = pick_window(sc_cpu, views_cpu[0], Ks_cpu[0], threads)
         cpu_baseline = {"value": 1.0 / est, "unit": "iters/s", "cores": threads, "kind": "port",
                         "sample": f"view 0, {win[2]}x{win[3]} centre window of the 1920x1080 frame with all {N} Gaussians "
                                   f"projected ({t_step:.1f}s measured); per-pixel cost scaled to the full frame, "
@@ -399,8 +450,7 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(N), "views": N_VIEWS, "render_mode": "RGB+ED", "sh_degree": 2,
                    "tile_size": 16, "l2": "inputs larger than L2 (912 MB of Gaussian parameters per step; no flush)",
-                   "collective": "NCCL all-reduce of 38 floats/Gaussian gradients + 2 floats/Gaussian densification "
-                                 "statistics per step" if world > 1 else "none (1 GPU)"},
+                   "collective": exchange_name},
         "clocks": clk,
         "e2e": {"value": world * n_steps / (ms_e2e * 1e-3), "unit": "iters/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / n_steps},
@@ -427,6 +477,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gaussians", type=int, default=6_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: sparse all-reduce over NVLink peer memory (default) or the dense NCCL all-reduce")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     if args.impl == "reference":

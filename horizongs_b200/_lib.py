@@ -48,6 +48,15 @@ SIGNATURES = {
     "hgs_blend2d_fwd_packed": (_i, [_p, _p] + [_i] * 6 + [_p, _p, _ll] + [_p] * 7 + [_p]),
     "hgs_blend2d_bwd_packed": (_i, [_p, _p] + [_i] * 6 + [_p, _p, _ll] + [_p] * 10 + [_p]),
     "hgs_densify_stats": (_i, [_p, _i, _p, _p, _ll, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "hgs_exchange_row_floats": (_i, [_p, _i]),
+    "hgs_exchange_mailbox_bytes": (_sz, [_i, _ll, _ll, _i]),
+    "hgs_exchange_push": (_i, [_p, _p, _i, _ll, _p, _ll, _ll, _p, _i, _i, C.c_ulonglong, _p]),
+    "hgs_exchange_reduce": (_i, [_p, _p, _i, _ll, _ll, _p, _i, _i, C.c_ulonglong, _p, _p]),
+    "hgs_peer_alloc": (_i, [_sz, C.POINTER(C.c_void_p)]),
+    "hgs_peer_free": (_i, [_p]),
+    "hgs_peer_export": (_i, [_p, _p]),
+    "hgs_peer_import": (_i, [_p, C.POINTER(C.c_void_p)]),
+    "hgs_peer_close": (_i, [_p]),
     "hgs_blend2d_fwd": (_i, [_p] * 7 + [_i] * 6 + [_p, _p, _ll] + [_p] * 7 + [_p]),
     "hgs_blend2d_bwd": (_i, [_p] * 7 + [_i] * 6 + [_p, _p, _ll] + [_p] * 16 + [_p]),
 }

@@ -102,3 +102,115 @@ def allreduce_densification(grad_norm: torch.Tensor, visible: torch.Tensor, max_
     if max_radii is not None:
         dist.all_reduce(max_radii, op=dist.ReduceOp.MAX, group=group)
     return grad_norm, visible, max_radii
+
+
+class PeerGradientExchange:
+    """Sparse SUM all-reduce of view-sharded gradients over NVLink peer memory (csrc/exchange.cu).
+
+    With one view per GPU only the rows of the Gaussians that view sees are non-zero, so instead of the dense
+    NCCL all-reduce every rank stores its visible rows (one record = id + the rows of all tensors) straight
+    into a mailbox in every peer's memory and then adds the W sources' records into its dense tensors in rank
+    order -- all replicas end with bit-identical sums.  torch.distributed is used once, at construction, to
+    trade the CUDA IPC handles of the mailboxes; the per-step exchange is two C-ABI calls and no collective.
+
+    widths: row widths of the tensors exchanged together, e.g. (3, 4, 3, 1, 27, 1, 1) for the gradients of
+    means / quats / scales / opacities / SH coefficients and the two densification statistics.
+    n_rows_total: N, the number of rows of every tensor; cap_rows: the largest number of rows one rank may
+    contribute per step (its visible Gaussians).
+    """
+
+    def __init__(self, widths: Sequence[int], n_rows_total: int, cap_rows: int, group=None,
+                 device: Optional[torch.device] = None):
+        import ctypes as C
+        from . import _lib
+        assert dist.is_available() and dist.is_initialized(), "PeerGradientExchange needs an initialised process group"
+        self._C, self._lib, self._check = C, _lib.lib(), _lib.check
+        L = self._lib
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.widths = [int(w) for w in widths]
+        self._widths_c = (C.c_int * len(self.widths))(*self.widths)
+        self.row = L.hgs_exchange_row_floats(self._widths_c, len(self.widths))
+        if self.row <= 0:
+            raise _lib.HgsError(f"unsupported tensor widths {self.widths}")
+        self.cap_rows = (int(cap_rows) + 31) // 32 * 32
+        self.n_ids = int(n_rows_total)
+        self.nbytes = L.hgs_exchange_mailbox_bytes(self.world, self.n_ids, self.cap_rows, self.row)
+        if self.nbytes == 0:
+            raise _lib.HgsError(f"unsupported exchange geometry: world {self.world}, N {self.n_ids}, cap {self.cap_rows}")
+        self.step = 0
+        self._local = C.c_void_p()
+        self._check(L.hgs_peer_alloc(self.nbytes, C.byref(self._local)), "hgs_peer_alloc")
+        handle = (C.c_ubyte * 64)()
+        self._check(L.hgs_peer_export(self._local, handle), "hgs_peer_export")
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+        gathered = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(gathered, mine, group=group)
+        self._peers = []
+        for r, h in enumerate(gathered):
+            if r == self.rank:
+                self._peers.append(self._local.value)
+                continue
+            buf = (C.c_ubyte * 64)(*h.cpu().tolist())
+            p = C.c_void_p()
+            self._check(L.hgs_peer_import(buf, C.byref(p)), f"hgs_peer_import(rank {r})")
+            self._peers.append(p.value)
+        self._peers_c = (C.c_void_p * self.world)(*self._peers)
+        self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        dist.barrier(group=group)          # every mailbox is mapped everywhere before the first push
+
+    def _tensor_ptrs(self, tensors):
+        assert len(tensors) == len(self.widths)
+        for t, w in zip(tensors, self.widths):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), "dense float32 CUDA tensors only"
+            assert t.shape[0] == self.n_ids and t.numel() == self.n_ids * w, (t.shape, w)
+        return (self._C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+    def push(self, tensors: Sequence[torch.Tensor], ids: torch.Tensor) -> None:
+        """first half of exchange(): store this rank's records into every peer's mailbox and raise its flag"""
+        C, L = self._C, self._lib
+        assert ids.dtype == torch.int32 and ids.is_contiguous()
+        n = int(ids.numel())
+        if n > self.cap_rows:
+            raise self._lib_error(f"{n} rows exceed the mailbox capacity {self.cap_rows}")
+        self._check(L.hgs_exchange_push(self._tensor_ptrs(tensors), self._widths_c, len(tensors), self.n_ids,
+                                        C.c_void_p(ids.data_ptr()) if n > 0 else None, n, self.cap_rows,
+                                        self._peers_c, self.world, self.rank, self.step,
+                                        torch.cuda.current_stream().cuda_stream), "hgs_exchange_push")
+
+    def reduce(self, tensors: Sequence[torch.Tensor]) -> None:
+        """second half: merge all ranks' records of this step into the dense tensors; ends the step"""
+        C, L = self._C, self._lib
+        self._check(L.hgs_exchange_reduce(self._tensor_ptrs(tensors), self._widths_c, len(tensors),
+                                          self.n_ids, self.cap_rows, self._local, self.world, self.rank,
+                                          self.step, C.c_void_p(self._status.data_ptr()),
+                                          torch.cuda.current_stream().cuda_stream), "hgs_exchange_reduce")
+        self.step += 1
+
+    def exchange(self, tensors: Sequence[torch.Tensor], ids: torch.Tensor) -> None:
+        """In place: tensors[k] ([N, widths[k]] float32, dense) become the SUM over ranks.  `ids` (int32, unique,
+        ASCENDING) lists the rows of THIS rank that are non-zero (meta["visible_ids"] of a one-camera
+        rasterization); rows a rank does not list must be zero on that rank."""
+        self.push(tensors, ids)
+        self.reduce(tensors)
+
+    def _lib_error(self, msg):
+        from . import _lib
+        return _lib.HgsError(msg)
+
+    def check_status(self) -> None:
+        """raise if a peer's records did not arrive in time in any exchange so far (one host read)"""
+        if int(self._status.item()) != 0:
+            raise self._lib_error("peer gradient exchange timed out waiting for a peer")
+
+    def close(self) -> None:
+        if self._local is None:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)     # nobody unmaps while a peer may still push
+        for r, p in enumerate(self._peers):
+            if r != self.rank:
+                self._lib.hgs_peer_close(self._C.c_void_p(p))
+        self._lib.hgs_peer_free(self._local)
+        self._local = None

@@ -230,6 +230,44 @@ int hgs_densify_stats(const float* v_means2d, int ld_means2d, const int32_t* rad
                       long long n_vis, int C, int N, int width, int height, int mode_max, float* grad_accum,
                       float* denom, float* max_radii, void* stream);
 
+/* ---- e: exchange of view-sharded gradients over NVLink peer memory -----------
+ * New behaviour (the reference trains one view per iteration in one process; gaussian_renderer/render.py has no
+ * collective): with one view per GPU only the Gaussians a view sees have non-zero gradient rows, so the SUM over
+ * ranks is done as a sparse all-reduce.  `tensors_host` / `widths_host` are HOST arrays describing up to
+ * HGS_EXCHANGE_MAX_TENSORS dense row-major float32 device tensors [N, widths[k]] (the parameter gradients and the
+ * densification statistics); a record is one id plus the concatenated rows (padded to a multiple of 4 floats).
+ * Each rank owns a mailbox of hgs_exchange_mailbox_bytes() in its own memory, mapped into every peer.
+ *   push   : records of the n_rows Gaussians listed in ids[] (unique, ASCENDING: the rank's visible set as written
+ *            by hgs_isect_prepare; n_rows <= cap_rows, a multiple of 32) are gathered, staged in shared memory and
+ *            stored with TMA bulk copies into slot (step & 1, rank) of EVERY mailbox in mailboxes_host[world] (peer
+ *            pointers; [rank] is the local one), then flag `rank` of every mailbox is raised to step + 1 (release,
+ *            system scope).  n_ids = N, the number of rows of each tensor.
+ *   reduce : for every block of consecutive Gaussian ids (n_ids = N rows in each tensor) waits (acquire) for flag
+ *            src = 0..world-1 of the local mailbox, merges the sources' records in that order (ids[] must be
+ *            ASCENDING, as hgs_isect_prepare's visible_ids are) and overwrites the touched rows of the tensors --
+ *            the same order on every rank, so all replicas end with bit-identical sums; rows no rank listed are
+ *            left as they are (zero).  *status_dev (device int, zero-initialised) is set to 1 if a peer's flag
+ *            does not arrive within 20 s.
+ * `step` must increase by 1 per exchange on all ranks; both calls only enqueue kernels on `stream`. */
+#define HGS_EXCHANGE_MAX_TENSORS 8
+#define HGS_EXCHANGE_MAX_RANKS 16
+#define HGS_PEER_HANDLE_BYTES 64
+int hgs_exchange_row_floats(const int* widths_host, int n_tensors);
+size_t hgs_exchange_mailbox_bytes(int world, long long n_ids, long long cap_rows, int row_floats);
+int hgs_exchange_push(float* const* tensors_host, const int* widths_host, int n_tensors, long long n_ids,
+                      const int32_t* ids, long long n_rows, long long cap_rows, void* const* mailboxes_host, int world,
+                      int rank, unsigned long long step, void* stream);
+int hgs_exchange_reduce(float* const* tensors_host, const int* widths_host, int n_tensors, long long n_ids,
+                        long long cap_rows, const void* mailbox, int world, int rank, unsigned long long step,
+                        int* status_dev, void* stream);
+/* Peer memory management (these allocate / synchronise, unlike the stage functions): a zero-filled device
+ * allocation, its 64-byte CUDA IPC handle (host buffer) and the mapping of a peer's handle into this process. */
+int hgs_peer_alloc(size_t bytes, void** out);
+int hgs_peer_free(void* ptr);
+int hgs_peer_export(void* ptr, unsigned char* handle64_host);
+int hgs_peer_import(const unsigned char* handle64_host, void** out);
+int hgs_peer_close(void* ptr);
+
 #ifdef __cplusplus
 }
 #endif
