@@ -236,21 +236,28 @@ def run_ours(args):
     from horizongs_b200 import distributed as D
     # gradient exchange (N > 1): sparse all-reduce over NVLink peer memory (csrc/exchange.cu); the dense NCCL
     # all-reduce stays available (--exchange nccl) and is the fallback if peer memory cannot be mapped
-    peer, exchange, exchange_name = None, None, "none (1 GPU)"
-    if world > 1 and args.exchange == "peer":
+    peer, fused, exchange, exchange_name = None, None, None, "none (1 GPU)"
+    if world > 1 and args.exchange in ("peer", "fused"):
         try:
-            peer = D.PeerGradientExchange((3, 4, 3, 1, 27, 1, 1), N, cap_rows=N // 4, device=dev)
-            exchange_name = ("sparse all-reduce over NVLink peer memory (own kernels, csrc/exchange.cu): each rank stores "
-                             "the 40-float records (38 gradients + 2 densification statistics) of its visible Gaussians "
-                             "into every peer's mailbox, then merges all ranks' records in rank order")
+            if args.exchange == "fused":
+                fused = D.FusedBackwardExchange(N, cap_rows=N // 4, device=dev)
+                exchange_name = ("SH / projection backward fused with the exchange over NVLink peer memory (own kernels, "
+                                 "csrc/exchange_vjp.cu): each rank stores the 12-float blend-gradient rows of its visible "
+                                 "Gaussians into every peer's mailbox; every rank then runs the per-Gaussian backward of "
+                                 "all views' rows, summing in rank order, and updates the densification statistics")
+            else:
+                peer = D.PeerGradientExchange((3, 4, 3, 1, 27, 1, 1), N, cap_rows=N // 4, device=dev)
+                exchange_name = ("sparse all-reduce over NVLink peer memory (own kernels, csrc/exchange.cu): each rank "
+                                 "stores the 40-float records (38 gradients + 2 densification statistics) of its visible "
+                                 "Gaussians into every peer's mailbox, then merges all ranks' records in rank order")
         except Exception as e:  # noqa: BLE001
             log(f"[bench] rank {rank}: peer-memory exchange unavailable ({e}); using the NCCL all-reduce")
-            peer = None
-        ok = torch.tensor([1 if peer is not None else 0], device=dev)
+            peer = fused = None
+        ok = torch.tensor([1 if (peer is not None or fused is not None) else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok.item()) == 0 and peer is not None:
-            peer = None
-    if world > 1 and peer is None:
+        if int(ok.item()) == 0:
+            peer = fused = None
+    if world > 1 and peer is None and fused is None:
         exchange = D.GradientExchange(params)
         exchange_name = ("NCCL all-reduce of 38 floats/Gaussian gradients + 2 floats/Gaussian densification statistics "
                          "per step")
@@ -273,6 +280,21 @@ def run_ours(args):
             gt.record_stream(main)
         else:
             view, Km, gt = views[v:v + 1], Ks[v:v + 1], gts[v:v + 1]
+        if fused is not None:
+            # N > 1, fused: backward() stops after the blend backward; the SH / projection backward of all ranks'
+            # views, the densification statistics and the exchange are one push + one reduce kernel
+            with fused.deferred():
+                rc, ra, meta = hgs.rasterization(params[0], params[1], params[2], params[3], params[4], view, Km, W, H,
+                                                 sh_degree=2, render_mode="RGB+ED", backgrounds=bg, packed=False)
+                if e2e:
+                    torch.cuda.current_stream().wait_stream(copy_stream)
+                loss = loss_fn(rc, ra, gt)
+                loss.backward()
+            fused.finish(*params, grad_accum=stats[0], denom=stats[1])
+            out = loss.item() if e2e else None
+            for p in params:
+                p.grad = None
+            return out
         rc, ra, meta = hgs.rasterization(params[0], params[1], params[2], params[3], params[4], view, Km, W, H,
                                          sh_degree=2, render_mode="RGB+ED", backgrounds=bg, packed=False)
         meta["means2d"].retain_grad()
@@ -356,6 +378,8 @@ def run_ours(args):
     ms_e2e, _ = timed(args.steps, args.warmup, e2e=True)
     if peer is not None:
         peer.check_status()
+    if fused is not None:
+        fused.check_status()
     clk = clocks.stop() if rank == 0 else None
 
     # ---- forward-only render FPS (reference method: torch.no_grad around render(), render.py:79-83,177)
@@ -371,6 +395,8 @@ def run_ours(args):
 
     if peer is not None:
         peer.close()
+    if fused is not None:
+        fused.close()
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -477,8 +503,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gaussians", type=int, default=6_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: sparse all-reduce over NVLink peer memory (default) or the dense NCCL all-reduce")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "peer", "nccl"],
+                    help="N > 1: per-Gaussian backward fused with the exchange over NVLink peer memory (default), "
+                         "sparse all-reduce of the parameter gradients over peer memory, or the dense NCCL all-reduce")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     if args.impl == "reference":

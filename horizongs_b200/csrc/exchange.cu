@@ -22,21 +22,11 @@
 // Roofline: NVLink inbound bandwidth for push, HBM for reduce.
 #include <string.h>
 
-#include "hgs_common.cuh"
-#include "../../include/hgs_raster.h"
+#include "exchange_common.cuh"
 
 namespace {
 
 constexpr int EX_MAX_T = HGS_EXCHANGE_MAX_TENSORS;
-constexpr int EX_MAX_W = HGS_EXCHANGE_MAX_RANKS;
-constexpr int EX_MAX_ROW = 128;        // floats per record (all tensors' widths, padded to a multiple of 4)
-constexpr int EX_FLAG_STRIDE = 128;    // bytes between the per-source flags
-constexpr int EX_COUNTER_OFF = EX_MAX_W * EX_FLAG_STRIDE;   // push-completion counter (local use)
-constexpr int EX_CTRL_BYTES = 4096;
-constexpr int EX_HDR_BYTES = 128;      // slot header: row count
-constexpr int EX_THREADS = 256;
-constexpr int EX_IDS = 256;            // Gaussian ids per merge CTA (and per entry of a slot's block index)
-constexpr int EX_CHUNK = 64;           // records staged per TMA bulk store
 
 struct ExTensors {
     float* p[EX_MAX_T];
@@ -44,33 +34,6 @@ struct ExTensors {
     int n;      // tensors
     int row;    // floats per record
 };
-struct ExPeers {
-    unsigned char* base[EX_MAX_W];
-    int world, rank;
-};
-// slot = [header 128 B][block entries: one per block of EX_IDS consecutive ids = {first record, 256-bit presence
-//         bitmap}, 48 B each][records: cap x row floats]; mailbox = [control 4 KB][2 parities x world slots].
-// The ids themselves never travel: the bitmaps list them, in record order.
-constexpr int EX_ENTRY_WORDS = 12;     // lo, bits[8], pad[3]
-struct ExLayout {
-    long long cap, n_ids;
-    int row, world, n_blocks;
-    size_t ent_off, rows_off, slot_bytes;
-};
-__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-inline ExLayout make_layout(int world, long long n_ids, long long cap, int row) {
-    ExLayout L;
-    L.cap = cap; L.n_ids = n_ids; L.row = row; L.world = world;
-    L.n_blocks = (int)((n_ids + EX_IDS - 1) / EX_IDS);
-    L.ent_off = EX_HDR_BYTES;
-    L.rows_off = L.ent_off + align_up((size_t)L.n_blocks * EX_ENTRY_WORDS * 4, 128);
-    L.slot_bytes = L.rows_off + (size_t)cap * row * 4;
-    return L;
-}
-__device__ __forceinline__ size_t slot_offset(const ExLayout& L, int parity, int src) {
-    return EX_CTRL_BYTES + (size_t)(parity * L.world + src) * L.slot_bytes;
-}
-
 // column -> (pointer to that column of row 0, row stride, position in the merge kernel's staging tile)
 struct ColTable {
     float* ptr[EX_MAX_ROW];
@@ -99,41 +62,6 @@ __device__ __forceinline__ void build_table(const ExTensors& T, ColTable& tab) {
     __syncthreads();
 }
 
-__device__ __forceinline__ void st_release_sys(unsigned long long* addr, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* addr) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-// TMA bulk copy shared -> global (the destination may be peer memory), tracked by the thread's bulk group
-__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, unsigned bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
-                 "r"((unsigned)__cvta_generic_to_shared(src_smem)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
-
-__device__ __forceinline__ int lower_bound_ids(const int32_t* __restrict__ ids, int n, long long key) {
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if ((long long)ids[mid] < key) lo = mid + 1;
-        else hi = mid;
-    }
-    return lo;
-}
-
 // Gather the records of the rows listed in ids[] (ascending) from the dense tensors, stage them in shared memory
 // and store each staged chunk with one TMA bulk copy per peer into slot (parity, rank) of that peer's mailbox
 // (double buffered: the gather of chunk k+1 overlaps the stores of chunk k); also the slot's block entries.
@@ -147,25 +75,7 @@ __global__ void __launch_bounds__(EX_THREADS) exchange_push_kernel(ExTensors T, 
     float4* const stage_rows[2] = {reinterpret_cast<float4*>(ex_smem + sizeof(ColTable)),
                                    reinterpret_cast<float4*>(ex_smem + sizeof(ColTable)) + EX_CHUNK * r4};
     const size_t soff = slot_offset(L, parity, P.rank);
-    // block entries: first record with id >= b * EX_IDS and the presence bitmap of the block's ids
-    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < L.n_blocks; b += gridDim.x * blockDim.x) {
-        const long long id0 = (long long)b * EX_IDS;
-        const int lo = lower_bound_ids(ids, n_rows, id0);
-        unsigned bits[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-        for (int j = lo; j < n_rows; ++j) {
-            const long long l = (long long)ids[j] - id0;
-            if (l >= EX_IDS) break;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) bits[w] |= ((int)(l >> 5) == w) ? (1u << (l & 31)) : 0u;
-        }
-        const uint4 e0 = make_uint4((unsigned)lo, bits[0], bits[1], bits[2]);
-        const uint4 e1 = make_uint4(bits[3], bits[4], bits[5], bits[6]);
-        const uint4 e2 = make_uint4(bits[7], 0u, 0u, 0u);
-        for (int q = 0; q < P.world; ++q) {
-            uint4* e = reinterpret_cast<uint4*>(P.base[q] + soff + L.ent_off) + (size_t)b * 3;
-            e[0] = e0; e[1] = e1; e[2] = e2;
-        }
-    }
+    write_block_entries(P, L, soff, ids, n_rows);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         for (int q = 0; q < P.world; ++q) *reinterpret_cast<long long*>(P.base[q] + soff) = n_rows;
     }
@@ -198,41 +108,7 @@ __global__ void __launch_bounds__(EX_THREADS) exchange_push_kernel(ExTensors T, 
             bulk_commit();
         }
     }
-    // publish: complete the bulk stores, fence everything system-wide; the last block to finish raises the flags
-    if (threadIdx.x < P.world) {
-        bulk_wait_all();
-        fence_proxy_async();
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned int* counter = reinterpret_cast<unsigned int*>(P.base[P.rank] + EX_COUNTER_OFF);
-        const unsigned int prev = atomicAdd(counter, 1u);
-        if (prev == gridDim.x - 1) {
-            *counter = 0u;
-            __threadfence_system();
-            for (int q = 0; q < P.world; ++q)
-                st_release_sys(reinterpret_cast<unsigned long long*>(P.base[q] + (size_t)P.rank * EX_FLAG_STRIDE), flag_value);
-        }
-    }
-}
-
-// Wait (acquire, system scope) until every source has raised its flag for this step; bounded: a dead peer
-// fails the step (*status = 1) instead of hanging the GPU.  The merge kernel follows in stream order.
-__global__ void exchange_wait_kernel(const unsigned char* mailbox, int world, unsigned long long want,
-                                     int* __restrict__ status) {
-    const int src = threadIdx.x;
-    if (src >= world) return;
-    const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(mailbox + (size_t)src * EX_FLAG_STRIDE);
-    if (ld_acquire_sys(flag) >= want) return;
-    const unsigned long long t0 = global_timer_ns();
-    while (ld_acquire_sys(flag) < want) {
-        if (global_timer_ns() - t0 > 20000000000ull) {
-            atomicExch(status, 1);
-            return;
-        }
-        __nanosleep(100);
-    }
+    publish_push(P, flag_value);
 }
 
 // Merge of all sources, one CTA per block of EX_IDS consecutive Gaussian ids.  Every source lists its ids in
@@ -244,9 +120,7 @@ __global__ void exchange_wait_kernel(const unsigned char* mailbox, int world, un
 // there are no partial-sector writes and no read-modify-write of the dense tensors.
 struct MergeSmem {      // followed by float stage[EX_IDS * row]
     ColTable tab;
-    unsigned bits[EX_MAX_W][8];
-    int pre[EX_MAX_W][8];       // records of the block before bitmap word w
-    int lo[EX_MAX_W];
+    BlockEntries ent;
     unsigned short present[EX_IDS];
     unsigned short touched[EX_IDS];
     int n_touched;
@@ -263,30 +137,18 @@ __global__ void __launch_bounds__(EX_THREADS) exchange_merge_kernel(ExTensors T,
     const int world = L.world;
     const int tid = threadIdx.x;
     if (__ldcg(status) != 0) return;     // a peer never arrived: leave the tensors alone, the host raises
-    // block entries of all sources -> shared memory (one round trip)
-    if (tid < world * 9) {
-        const int src = tid / 9, w = tid - src * 9;
-        const unsigned* e = reinterpret_cast<const unsigned*>(mailbox + slot_offset(L, parity, src) + L.ent_off) +
-                            (size_t)blockIdx.x * EX_ENTRY_WORDS;
-        const unsigned v = __ldcg(e + w);
-        if (w == 0) S.lo[src] = (int)v;
-        else S.bits[src][w - 1] = v;
-    }
+    load_block_entries(S.ent, L, mailbox, parity, blockIdx.x);    // one round trip
     if (tid == 0) S.n_touched = 0;
     {
         float4* z = reinterpret_cast<float4*>(stage);
         for (int i = tid; i < EX_IDS * r4; i += EX_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     build_table(T, S.tab);    // ends with __syncthreads()
-    if (tid < world) {
-        int acc = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) { S.pre[tid][w] = acc; acc += __popc(S.bits[tid][w]); }
-    }
+    prefix_block_entries(S.ent, world);
     {
         // EX_IDS == EX_THREADS: thread l owns local id l
         unsigned m = 0;
-        for (int s = 0; s < world; ++s) m |= ((S.bits[s][tid >> 5] >> (tid & 31)) & 1u) << s;
+        for (int s = 0; s < world; ++s) m |= ((S.ent.bits[s][tid >> 5] >> (tid & 31)) & 1u) << s;
         S.present[tid] = (unsigned short)m;
         const unsigned ball = __ballot_sync(0xFFFFFFFFu, m != 0);
         int base = 0;
@@ -307,7 +169,7 @@ __global__ void __launch_bounds__(EX_THREADS) exchange_merge_kernel(ExTensors T,
         while (m) {                        // ascending source rank = the addition order on every replica
             const int s = __ffs(m) - 1;
             m &= m - 1;
-            const int p = S.lo[s] + S.pre[s][l >> 5] + __popc(S.bits[s][l >> 5] & ((1u << (l & 31)) - 1u));
+            const int p = record_index(S.ent, s, l);
             const float4* rows = reinterpret_cast<const float4*>(mailbox + slot_offset(L, parity, s) + L.rows_off);
             const float4 v = __ldcg(rows + (size_t)p * r4 + c);
             a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
@@ -356,11 +218,6 @@ int fill_tensors(ExTensors& T, float* const* tensors, const int* widths, int n_t
     return T.row <= EX_MAX_ROW ? 0 : HGS_ERR_INVALID_ARG;
 }
 
-bool bad_geometry(int world, int rank, long long n_ids, long long cap_rows) {
-    return world < 1 || world > EX_MAX_W || rank < 0 || rank >= world || n_ids < 1 || n_ids >= (1ll << 31) ||
-           cap_rows < 1 || cap_rows % 32 != 0 || cap_rows * 32 >= (1ll << 31);
-}
-
 }  // namespace
 
 HGS_API int hgs_exchange_row_floats(const int* widths_host, int n_tensors) {
@@ -375,7 +232,7 @@ HGS_API int hgs_exchange_row_floats(const int* widths_host, int n_tensors) {
 }
 
 HGS_API size_t hgs_exchange_mailbox_bytes(int world, long long n_ids, long long cap_rows, int row_floats) {
-    if (bad_geometry(world, 0, n_ids, cap_rows) || row_floats < 4 || row_floats > EX_MAX_ROW || row_floats % 4) return 0;
+    if (ex_bad_geometry(world, 0, n_ids, cap_rows) || row_floats < 4 || row_floats > EX_MAX_ROW || row_floats % 4) return 0;
     return EX_CTRL_BYTES + (size_t)2 * world * make_layout(world, n_ids, cap_rows, row_floats).slot_bytes;
 }
 
@@ -384,21 +241,13 @@ HGS_API int hgs_exchange_push(float* const* tensors_host, const int* widths_host
                               int world, int rank, unsigned long long step, void* stream) {
     ExTensors T;
     if (int e = fill_tensors(T, tensors_host, widths_host, n_tensors)) return e;
-    if (bad_geometry(world, rank, n_ids, cap_rows) || n_rows < 0) return HGS_ERR_INVALID_ARG;
+    if (ex_bad_geometry(world, rank, n_ids, cap_rows) || n_rows < 0) return HGS_ERR_INVALID_ARG;
     if (n_rows > cap_rows) return HGS_ERR_WORKSPACE;
     if (n_rows > 0 && ids == nullptr) return HGS_ERR_INVALID_ARG;
     ExPeers P;
-    for (int q = 0; q < EX_MAX_W; ++q) P.base[q] = q < world ? (unsigned char*)mailboxes_host[q] : nullptr;
-    for (int q = 0; q < world; ++q)
-        if (P.base[q] == nullptr) return HGS_ERR_INVALID_ARG;
-    P.world = world;
-    P.rank = rank;
+    if (int e = ex_fill_peers(P, mailboxes_host, world, rank)) return e;
     const ExLayout L = make_layout(world, n_ids, cap_rows, T.row);
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long chunks = (n_rows + EX_CHUNK - 1) / EX_CHUNK;
-    const int grid = (int)(chunks < 1 ? 1 : (chunks > (long long)sms * 8 ? (long long)sms * 8 : chunks));
+    const int grid = ex_push_grid(n_rows);
     const int smem = (int)(sizeof(ColTable) + (size_t)2 * EX_CHUNK * T.row * 4);
     cudaError_t e = cudaFuncSetAttribute(exchange_push_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
@@ -413,7 +262,7 @@ HGS_API int hgs_exchange_reduce(float* const* tensors_host, const int* widths_ho
                                 int* status_dev, void* stream) {
     ExTensors T;
     if (int e = fill_tensors(T, tensors_host, widths_host, n_tensors)) return e;
-    if (bad_geometry(world, rank, n_ids, cap_rows) || mailbox == nullptr || status_dev == nullptr) return HGS_ERR_INVALID_ARG;
+    if (ex_bad_geometry(world, rank, n_ids, cap_rows) || mailbox == nullptr || status_dev == nullptr) return HGS_ERR_INVALID_ARG;
     const ExLayout L = make_layout(world, n_ids, cap_rows, T.row);
     cudaStream_t st = (cudaStream_t)stream;
     exchange_wait_kernel<<<1, 32, 0, st>>>((const unsigned char*)mailbox, world, step + 1ull, status_dev);

@@ -39,6 +39,32 @@ def _mark(name: str, phase: int):
         _STAGE_HOOK(name, phase)
 
 
+# Deferred per-Gaussian backward (multi-GPU, horizongs_b200.distributed.FusedBackwardExchange): inside
+# `with deferred_backward(sink):` a rasterization() call records what the SH / projection backward would need in
+# `sink`, and loss.backward() stops after the blend backward -- the SH / projection backward of ALL ranks' views
+# then runs fused with the gradient exchange (csrc/exchange_vjp.cu).
+_DEFER_SINK = None
+
+
+class deferred_backward:
+    def __init__(self, sink: dict):
+        self.sink = sink
+
+    def __enter__(self):
+        global _DEFER_SINK
+        self._prev, _DEFER_SINK = _DEFER_SINK, self.sink
+        return self.sink
+
+    def __exit__(self, *exc):
+        global _DEFER_SINK
+        _DEFER_SINK = self._prev
+        return False
+
+
+def current_deferred_sink():
+    return _DEFER_SINK
+
+
 def _f32c(t: Optional[Tensor], name: str) -> Optional[Tensor]:
     if t is None:
         return None
@@ -108,6 +134,8 @@ class _Project3D(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, _v_radii, v_means2d, v_depths, v_conics, _v_comps, _v_tiles):
+        if ctx.holder is not None and ctx.holder.get("defer") is not None:
+            return (None,) * 14           # runs later, fused with the exchange (FusedBackwardExchange.finish)
         means, quats, scales, viewmats, Ks, radii = ctx.saved_tensors
         width, height, eps2d, near_plane, far_plane = ctx.cfg
         L = _lib.lib()
@@ -177,7 +205,8 @@ class _SphericalHarmonics(torch.autograd.Function):
     """colors[C,N,3] from coeffs[N,K,3]; direction either dirs[C,N,3] or means[N,3]-campos[C,3]."""
 
     @staticmethod
-    def forward(ctx, degree, dirs, means, campos, coeffs, radii, post, vis_ids=None):
+    def forward(ctx, degree, dirs, means, campos, coeffs, radii, post, vis_ids=None, defer=None):
+        ctx.defer = defer
         L = _lib.lib()
         N, K = coeffs.shape[0], coeffs.shape[1]
         C = dirs.shape[0] if dirs is not None else campos.shape[0]
@@ -196,6 +225,9 @@ class _SphericalHarmonics(torch.autograd.Function):
     def backward(ctx, v_colors):
         dirs, means, campos, coeffs, radii, colors = ctx.saved_tensors
         degree, K, C, N, post = ctx.cfg
+        if ctx.defer is not None:
+            ctx.defer["colors_fwd"] = colors      # the clamp mask of `post`; the gradient itself comes from vpack
+            return (None,) * 9
         L = _lib.lib()
         v_colors, ld_vc = _rows(v_colors, 3)
         v_coeffs = torch.empty_like(coeffs)
@@ -210,7 +242,7 @@ class _SphericalHarmonics(torch.autograd.Function):
                            ptr(v_coeffs), ptr(v_dirs), ptr(v_means), _stream()),
               "hgs_sh_bwd")
         _mark("sh_bwd", 1)
-        return None, v_dirs, v_means, None, v_coeffs, None, None, None
+        return None, v_dirs, v_means, None, v_coeffs, None, None, None, None
 
 
 def spherical_harmonics(degrees_to_use: int, dirs: Tensor, coeffs: Tensor, masks: Optional[Tensor] = None) -> Tensor:
@@ -234,11 +266,11 @@ def spherical_harmonics(degrees_to_use: int, dirs: Tensor, coeffs: Tensor, masks
 
 
 def _sh_view_colors(sh_degree: int, means: Tensor, campos: Tensor, coeffs: Tensor, radii: Tensor,
-                    vis_ids: Optional[Tensor] = None) -> Tensor:
+                    vis_ids: Optional[Tensor] = None, defer: Optional[dict] = None) -> Tensor:
     """fused path used by rasterization*: clamp_min(SH(means - campos) + 0.5, 0), masked by radii > 0
     (vis_ids = the work list of visible flat indices, equivalent to the mask but without idle threads)."""
     return _SphericalHarmonics.apply(int(sh_degree), None, _f32c(means, "means"), _f32c(campos, "campos"),
-                                     _f32c(coeffs, "colors"), radii, True, vis_ids)
+                                     _f32c(coeffs, "colors"), radii, True, vis_ids, defer)
 
 
 # =====================================================================================
@@ -334,8 +366,9 @@ class _Blend3D(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means2d, conics, colors, depths, opacities, backgrounds, width, height, tile_size,
-                isect_offsets, flatten_ids, absgrad, radii, normalize_depth, vis_ids=None):
+                isect_offsets, flatten_ids, absgrad, radii, normalize_depth, vis_ids=None, defer=None):
         L = _lib.lib()
+        ctx.defer = defer
         C, N = opacities.shape
         CH = colors.shape[-1]
         D = CH + (1 if depths is not None else 0)
@@ -380,7 +413,7 @@ class _Blend3D(torch.autograd.Function):
         L = _lib.lib()
         v_render_colors = v_render_colors.contiguous()
         v_render_alphas = v_render_alphas.contiguous()
-        tail = (None,) * 9
+        tail = (None,) * 10
         if ctx.fast:
             records, backgrounds, isect_offsets, flatten_ids, render_colors, render_alphas, last_ids = ctx.saved_tensors
             (C, N, _), has_depth = ctx.shapes
@@ -392,6 +425,8 @@ class _Blend3D(torch.autograd.Function):
                                            ptr(v_render_colors), ptr(v_render_alphas), ptr(vpack), _stream()),
                   "hgs_blend3d_bwd_packed")
             _mark("blend3d_bwd", 1)
+            if ctx.defer is not None:
+                ctx.defer["vpack"] = vpack
             v_means2d, v_conics, v_opacities = vpack[..., 0:2], vpack[..., 2:5], vpack[..., 5]
             v_colors = vpack[..., 8:8 + CH]
             v_depths = vpack[..., 8 + CH] if has_depth else None
@@ -425,7 +460,7 @@ class _Blend3D(torch.autograd.Function):
 
 
 def _blend3d(means2d, conics, colors, depths, opacities, backgrounds, width, height, tile_size, isect_offsets,
-             flatten_ids, absgrad=False, radii=None, normalize_depth=False, vis_ids=None):
+             flatten_ids, absgrad=False, radii=None, normalize_depth=False, vis_ids=None, defer=None):
     if tile_size not in _TILE_SIZES:
         raise NotImplementedError(f"tile_size {tile_size} is not supported (supported: {_TILE_SIZES})")
     D = colors.shape[-1] + (1 if depths is not None else 0)
@@ -434,7 +469,7 @@ def _blend3d(means2d, conics, colors, depths, opacities, backgrounds, width, hei
     return _Blend3D.apply(_f32c(means2d, "means2d"), _f32c(conics, "conics"), _f32c(colors, "colors"),
                           _f32c(depths, "depths"), _f32c(opacities, "opacities"), _f32c(backgrounds, "backgrounds"),
                           int(width), int(height), int(tile_size), isect_offsets.contiguous(),
-                          flatten_ids.contiguous(), bool(absgrad), radii, bool(normalize_depth), vis_ids)
+                          flatten_ids.contiguous(), bool(absgrad), radii, bool(normalize_depth), vis_ids, defer)
 
 
 def rasterize_to_pixels(means2d: Tensor, conics: Tensor, colors: Tensor, opacities: Tensor, image_width: int,

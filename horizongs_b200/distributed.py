@@ -104,14 +104,70 @@ def allreduce_densification(grad_norm: torch.Tensor, visible: torch.Tensor, max_
     return grad_norm, visible, max_radii
 
 
+class _PeerMailbox:
+    """A zero-filled device allocation of `nbytes` on every rank, mapped into every peer through CUDA IPC handles
+    traded once over torch.distributed (hgs_peer_* of the C ABI).  ptrs[r] is rank r's mailbox as seen from here."""
+
+    def __init__(self, nbytes: int, group=None, device: Optional[torch.device] = None):
+        import ctypes as C
+        from . import _lib
+        assert dist.is_available() and dist.is_initialized(), "peer-memory exchange needs an initialised process group"
+        self._C, self._lib, self._check = C, _lib.lib(), _lib.check
+        L = self._lib
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.nbytes = int(nbytes)
+        self._local = C.c_void_p()
+        self._check(L.hgs_peer_alloc(self.nbytes, C.byref(self._local)), "hgs_peer_alloc")
+        handle = (C.c_ubyte * 64)()
+        self._check(L.hgs_peer_export(self._local, handle), "hgs_peer_export")
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+        gathered = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(gathered, mine, group=group)
+        self.ptrs = []
+        for r, h in enumerate(gathered):
+            if r == self.rank:
+                self.ptrs.append(self._local.value)
+                continue
+            buf = (C.c_ubyte * 64)(*h.cpu().tolist())
+            p = C.c_void_p()
+            self._check(L.hgs_peer_import(buf, C.byref(p)), f"hgs_peer_import(rank {r})")
+            self.ptrs.append(p.value)
+        self.ptrs_c = (C.c_void_p * self.world)(*self.ptrs)
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        dist.barrier(group=group)          # every mailbox is mapped everywhere before the first push
+
+    @property
+    def local(self):
+        return self._local
+
+    def check_status(self) -> None:
+        """raise if a peer's records did not arrive in time in any exchange so far (one host read)"""
+        from . import _lib
+        if int(self.status.item()) != 0:
+            raise _lib.HgsError("peer gradient exchange timed out waiting for a peer")
+
+    def close(self) -> None:
+        if self._local is None:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)     # nobody unmaps while a peer may still push
+        for r, p in enumerate(self.ptrs):
+            if r != self.rank:
+                self._lib.hgs_peer_close(self._C.c_void_p(p))
+        self._lib.hgs_peer_free(self._local)
+        self._local = None
+
+
 class PeerGradientExchange:
     """Sparse SUM all-reduce of view-sharded gradients over NVLink peer memory (csrc/exchange.cu).
 
     With one view per GPU only the rows of the Gaussians that view sees are non-zero, so instead of the dense
-    NCCL all-reduce every rank stores its visible rows (one record = id + the rows of all tensors) straight
-    into a mailbox in every peer's memory and then adds the W sources' records into its dense tensors in rank
-    order -- all replicas end with bit-identical sums.  torch.distributed is used once, at construction, to
-    trade the CUDA IPC handles of the mailboxes; the per-step exchange is two C-ABI calls and no collective.
+    NCCL all-reduce every rank stores its visible rows (one record = the rows of all tensors) straight into a
+    mailbox in every peer's memory and then adds the W sources' records into its dense tensors in rank order --
+    all replicas end with bit-identical sums.  torch.distributed is used once, at construction, to trade the
+    CUDA IPC handles of the mailboxes; the per-step exchange is two C-ABI calls and no collective.
 
     widths: row widths of the tensors exchanged together, e.g. (3, 4, 3, 1, 27, 1, 1) for the gradients of
     means / quats / scales / opacities / SH coefficients and the two densification statistics.
@@ -123,12 +179,8 @@ class PeerGradientExchange:
                  device: Optional[torch.device] = None):
         import ctypes as C
         from . import _lib
-        assert dist.is_available() and dist.is_initialized(), "PeerGradientExchange needs an initialised process group"
-        self._C, self._lib, self._check = C, _lib.lib(), _lib.check
-        L = self._lib
-        self.group = group
-        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        L = _lib.lib()
+        self._C, self._lib, self._check = C, L, _lib.check
         self.widths = [int(w) for w in widths]
         self._widths_c = (C.c_int * len(self.widths))(*self.widths)
         self.row = L.hgs_exchange_row_floats(self._widths_c, len(self.widths))
@@ -136,29 +188,13 @@ class PeerGradientExchange:
             raise _lib.HgsError(f"unsupported tensor widths {self.widths}")
         self.cap_rows = (int(cap_rows) + 31) // 32 * 32
         self.n_ids = int(n_rows_total)
-        self.nbytes = L.hgs_exchange_mailbox_bytes(self.world, self.n_ids, self.cap_rows, self.row)
-        if self.nbytes == 0:
-            raise _lib.HgsError(f"unsupported exchange geometry: world {self.world}, N {self.n_ids}, cap {self.cap_rows}")
+        world = dist.get_world_size(group)
+        nbytes = L.hgs_exchange_mailbox_bytes(world, self.n_ids, self.cap_rows, self.row)
+        if nbytes == 0:
+            raise _lib.HgsError(f"unsupported exchange geometry: world {world}, N {self.n_ids}, cap {self.cap_rows}")
+        self.box = _PeerMailbox(nbytes, group, device)
+        self.world, self.rank = self.box.world, self.box.rank
         self.step = 0
-        self._local = C.c_void_p()
-        self._check(L.hgs_peer_alloc(self.nbytes, C.byref(self._local)), "hgs_peer_alloc")
-        handle = (C.c_ubyte * 64)()
-        self._check(L.hgs_peer_export(self._local, handle), "hgs_peer_export")
-        mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
-        gathered = [torch.empty_like(mine) for _ in range(self.world)]
-        dist.all_gather(gathered, mine, group=group)
-        self._peers = []
-        for r, h in enumerate(gathered):
-            if r == self.rank:
-                self._peers.append(self._local.value)
-                continue
-            buf = (C.c_ubyte * 64)(*h.cpu().tolist())
-            p = C.c_void_p()
-            self._check(L.hgs_peer_import(buf, C.byref(p)), f"hgs_peer_import(rank {r})")
-            self._peers.append(p.value)
-        self._peers_c = (C.c_void_p * self.world)(*self._peers)
-        self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
-        dist.barrier(group=group)          # every mailbox is mapped everywhere before the first push
 
     def _tensor_ptrs(self, tensors):
         assert len(tensors) == len(self.widths)
@@ -176,15 +212,15 @@ class PeerGradientExchange:
             raise self._lib_error(f"{n} rows exceed the mailbox capacity {self.cap_rows}")
         self._check(L.hgs_exchange_push(self._tensor_ptrs(tensors), self._widths_c, len(tensors), self.n_ids,
                                         C.c_void_p(ids.data_ptr()) if n > 0 else None, n, self.cap_rows,
-                                        self._peers_c, self.world, self.rank, self.step,
+                                        self.box.ptrs_c, self.world, self.rank, self.step,
                                         torch.cuda.current_stream().cuda_stream), "hgs_exchange_push")
 
     def reduce(self, tensors: Sequence[torch.Tensor]) -> None:
         """second half: merge all ranks' records of this step into the dense tensors; ends the step"""
         C, L = self._C, self._lib
         self._check(L.hgs_exchange_reduce(self._tensor_ptrs(tensors), self._widths_c, len(tensors),
-                                          self.n_ids, self.cap_rows, self._local, self.world, self.rank,
-                                          self.step, C.c_void_p(self._status.data_ptr()),
+                                          self.n_ids, self.cap_rows, self.box.local, self.world, self.rank,
+                                          self.step, C.c_void_p(self.box.status.data_ptr()),
                                           torch.cuda.current_stream().cuda_stream), "hgs_exchange_reduce")
         self.step += 1
 
@@ -200,17 +236,94 @@ class PeerGradientExchange:
         return _lib.HgsError(msg)
 
     def check_status(self) -> None:
-        """raise if a peer's records did not arrive in time in any exchange so far (one host read)"""
-        if int(self._status.item()) != 0:
-            raise self._lib_error("peer gradient exchange timed out waiting for a peer")
+        self.box.check_status()
 
     def close(self) -> None:
-        if self._local is None:
-            return
-        torch.cuda.synchronize(self.device)
-        dist.barrier(group=self.group)     # nobody unmaps while a peer may still push
-        for r, p in enumerate(self._peers):
-            if r != self.rank:
-                self._lib.hgs_peer_close(self._C.c_void_p(p))
-        self._lib.hgs_peer_free(self._local)
-        self._local = None
+        self.box.close()
+
+
+class FusedBackwardExchange:
+    """The SH / projection backward of all ranks' views fused with the gradient exchange (csrc/exchange_vjp.cu).
+
+    With replicated parameters the gradient of a view w.r.t. means / quats / scales / colours is a function of the
+    12-float row the blend backward left for each visible Gaussian, the Gaussian's parameters (every rank has
+    them) and the view's camera.  So the ranks trade those 48-byte rows (3.3x less NVLink traffic than the 38
+    parameter gradients) and every rank runs the per-Gaussian backward of ALL views itself, summing in rank
+    order: bit-identical gradients everywhere, and sh_bwd + project3d_bwd + densify_stats + the all-reduce of a
+    step collapse into one push and one reduce kernel.  One camera per rank and step.
+
+        ex = FusedBackwardExchange(N, cap_rows=N // 4)
+        with ex.deferred():                       # backward stops after the blend backward
+            rc, ra, meta = rasterization(means, quats, scales, opacities, colors, viewmat[None], K[None], W, H, ...)
+            loss(rc, ra).backward()
+        ex.finish(means, quats, scales, opacities, colors, grad_accum, denom)   # sets .grad of the five tensors
+    """
+
+    def __init__(self, n_gaussians: int, cap_rows: int, group=None, device: Optional[torch.device] = None):
+        import ctypes as C
+        from . import _lib
+        L = _lib.lib()
+        self._C, self._lib, self._check = C, L, _lib.check
+        self.n_ids = int(n_gaussians)
+        self.cap_rows = (int(cap_rows) + 31) // 32 * 32
+        world = dist.get_world_size(group)
+        nbytes = L.hgs_exchange_vjp_mailbox_bytes(world, self.n_ids, self.cap_rows)
+        if nbytes == 0:
+            raise _lib.HgsError(f"unsupported exchange geometry: world {world}, N {self.n_ids}, cap {self.cap_rows}")
+        self.box = _PeerMailbox(nbytes, group, device)
+        self.world, self.rank = self.box.world, self.box.rank
+        self.step = 0
+        self.sink: dict = {}
+
+    def deferred(self):
+        from .cuda import _wrapper as W
+        return W.deferred_backward(self.sink)
+
+    def finish(self, means, quats, scales, opacities, colors, grad_accum: Optional[torch.Tensor] = None,
+               denom: Optional[torch.Tensor] = None) -> None:
+        """push this rank's blend-gradient rows, then compute the summed gradients of all ranks' views and store
+        them in .grad of the five parameter tensors; grad_accum / denom ([N] float32, optional) receive += the
+        densification statistics (scene/basic_model.py:131-144) of all views."""
+        from . import _lib
+        C, L, sk = self._C, self._lib, self.sink
+        if "vpack" not in sk:
+            raise _lib.HgsError("finish(): no deferred backward recorded (run rasterization + backward inside deferred())")
+        N = self.n_ids
+        vpack, ids = sk["vpack"], sk["vis_ids"]
+        assert vpack.shape == (1, N, 12) and vpack.is_contiguous() and sk["n"] == N
+        n = int(ids.numel())
+        if n > self.cap_rows:
+            raise _lib.HgsError(f"{n} visible Gaussians exceed the mailbox capacity {self.cap_rows}")
+        sh_degree = sk["sh_degree"]
+        cf = sk.get("colors_fwd")
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
+        for t in (means, quats, scales, opacities, colors):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape[0] == N
+        K = 1 if sh_degree is None else int(colors.shape[1])
+        st = torch.cuda.current_stream().cuda_stream
+        from .cuda import _wrapper as W
+        W._mark("exchange_vjp_push", 0)
+        self._check(L.hgs_exchange_vjp_push(p(vpack), p(cf), p(sk["viewmats"]), p(sk["Ks"]), p(sk["campos"]), N,
+                                            p(ids) if n > 0 else None, n, self.cap_rows, self.box.ptrs_c, self.world,
+                                            self.rank, self.step, st), "hgs_exchange_vjp_push")
+        W._mark("exchange_vjp_push", 1)
+        outs = [torch.empty_like(t) for t in (means, quats, scales, opacities, colors)]
+        W._mark("exchange_vjp_reduce", 0)
+        self._check(L.hgs_exchange_vjp_reduce(-1 if sh_degree is None else int(sh_degree), K, p(means.detach()),
+                                              p(quats.detach()), p(scales.detach()), p(colors.detach()),
+                                              int(sk["width"]), int(sk["height"]), float(sk["eps2d"]),
+                                              float(sk["near_plane"]), float(sk["far_plane"]), N, self.cap_rows,
+                                              self.box.local, self.world, self.rank, self.step, p(outs[0]), p(outs[1]),
+                                              p(outs[2]), p(outs[3]), p(outs[4]), p(grad_accum), p(denom),
+                                              p(self.box.status), st), "hgs_exchange_vjp_reduce")
+        W._mark("exchange_vjp_reduce", 1)
+        self.step += 1
+        for t, g in zip((means, quats, scales, opacities, colors), outs):
+            t.grad = g
+        sk.clear()
+
+    def check_status(self) -> None:
+        self.box.check_status()
+
+    def close(self) -> None:
+        self.box.close()

@@ -49,13 +49,13 @@ def _validate(means, quats, scales, opacities, colors, viewmats, Ks, render_mode
     return C, N
 
 
-def _per_view_features(means, colors, viewmats, radii, sh_degree, C, vis_ids=None):
+def _per_view_features(means, colors, viewmats, radii, sh_degree, C, vis_ids=None, defer=None):
     """-> [C,N,CH] colour features for blending (CH = 3 for SH)."""
     if sh_degree is None:
         if colors.dim() == 2:
             return colors[None] if C == 1 else colors[None].expand(C, -1, -1)
         return colors
-    return W._sh_view_colors(sh_degree, means, _camera_positions(viewmats), colors, radii, vis_ids)
+    return W._sh_view_colors(sh_degree, means, _camera_positions(viewmats), colors, radii, vis_ids, defer)
 
 
 def _mode_features(feats, depths, backgrounds, render_mode):
@@ -106,13 +106,27 @@ def rasterization(
             means2d, radii, depths, tiles_per_gauss, C, N, tile_size, tile_width, tile_height)
     holder["vis_ids"] = vis_ids          # work list for the backward of the projection
 
-    feats = _per_view_features(means, colors, viewmats, radii, sh_degree, C, vis_ids)
+    # multi-GPU: the SH / projection backward is deferred and runs fused with the gradient exchange
+    defer = W.current_deferred_sink() if torch.is_grad_enabled() else None
+    if defer is not None:
+        if C != 1 or render_mode not in ("RGB", "RGB+D", "RGB+ED") or absgrad or comps is not None:
+            raise NotImplementedError("deferred backward needs one camera per rank, an RGB(+depth) render mode, "
+                                      "no absgrad and rasterize_mode='classic'")
+        if sh_degree is None and (colors.dim() != 2 or colors.shape[-1] != 3):
+            raise NotImplementedError("deferred backward needs [N,3] colours or SH coefficients")
+        holder["defer"] = defer
+        defer.clear()
+        defer.update(vis_ids=vis_ids, viewmats=viewmats.detach().contiguous(), Ks=Ks.detach().contiguous(),
+                     campos=_camera_positions(viewmats.detach()).contiguous(), width=width, height=height, eps2d=eps2d,
+                     near_plane=near_plane, far_plane=far_plane, sh_degree=sh_degree, n=N)
+
+    feats = _per_view_features(means, colors, viewmats, radii, sh_degree, C, vis_ids, defer)
     feats, depth_ch, bgs = _mode_features(feats, depths, backgrounds, render_mode)
     n_ch = feats.shape[-1] + (1 if depth_ch is not None else 0)
     fuse_norm = render_mode in ("ED", "RGB+ED") and n_ch <= 4 and not absgrad
     render_colors, render_alphas = W._blend3d(means2d, conics, feats, depth_ch, opac, bgs, width, height, tile_size,
                                               isect_offsets, flatten_ids, absgrad, radii=radii,
-                                              normalize_depth=fuse_norm, vis_ids=vis_ids)
+                                              normalize_depth=fuse_norm, vis_ids=vis_ids, defer=defer)
     if render_mode in ("ED", "RGB+ED") and not fuse_norm:
         render_colors = torch.cat(
             [render_colors[..., :-1], render_colors[..., -1:] / render_alphas.clamp(min=1e-10)], dim=-1)

@@ -77,3 +77,84 @@ def test_peer_exchange_equals_dense_allreduce(tmp_path):
         got = torch.load(os.path.join(str(tmp_path), f"r{r}.pt"))
         assert got["ok"], f"rank {r}: replicas are not bit-identical"
         assert got["worst"] < 1e-5, f"rank {r}: differs from the dense all-reduce by {got['worst']}"
+
+
+def _fused_worker(rank, world, port, out_dir, sh_degree, steps):
+    import math
+    import torch.distributed as dist
+    import horizongs_b200 as hgs
+    from horizongs_b200 import distributed as D, scenes
+    from horizongs_b200.cuda import _wrapper as Wr
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    N, Wd, H = 6000, 208, 144
+    sc = scenes.make_scene(N, 3.0, 1.0, 0.08, 0.5, sh_degree=sh_degree, seed=3).to(dev)
+    params = [t.requires_grad_() for t in (sc.means, sc.quats, sc.scales, sc.opacities, sc.colors)]
+    Km = scenes.intrinsics(Wd, H, 70.0).to(dev)
+    ex = D.FusedBackwardExchange(N, cap_rows=N, device=dev)
+    wimg = torch.rand(1, H, Wd, 4, generator=torch.Generator().manual_seed(5)).to(dev)
+    ok, worst = True, 0.0
+    acc_ref, den_ref = torch.zeros(N, device=dev), torch.zeros(N, device=dev)
+    acc, den = torch.zeros(N, device=dev), torch.zeros(N, device=dev)
+    for s in range(steps):
+        a = 2 * math.pi * (rank + s * world) / (world * steps)
+        # step 2: rank 1 looks away from the scene (sees nothing)
+        eye = (5.0 * math.cos(a), 5.0 * math.sin(a), 2.0 + 0.3 * rank)
+        target = (0.0, 0.0, 0.2) if not (s == 2 and rank == 1) else (20.0 * math.cos(a), 20.0 * math.sin(a), 2.0)
+        V = scenes.look_at(eye, target).to(dev)
+
+        def run():
+            rc, ra, meta = hgs.rasterization(*params, V[None], Km[None], Wd, H, sh_degree=sh_degree,
+                                             render_mode="RGB+ED", backgrounds=torch.full((1, 3), 0.2, device=dev))
+            meta["means2d"].retain_grad()
+            ((rc * wimg).sum() + ra.sum()).backward()
+            return meta
+        # reference: every rank's own autograd gradients, dense NCCL all-reduce
+        for p in params:
+            p.grad = None
+        meta = run()
+        ref = [p.grad.clone().contiguous() for p in params]
+        st = torch.zeros(2, N, device=dev)
+        Wr.densification_stats_update(meta["means2d"].grad, meta["radii"], Wd, H, st[0], st[1],
+                                      visible_ids=meta["visible_ids"])
+        for t in ref + [st]:
+            dist.all_reduce(t)
+        acc_ref += st[0]
+        den_ref += st[1]
+        # fused: backward stops after the blend backward; SH / projection backward of all views + exchange in one
+        for p in params:
+            p.grad = None
+        with ex.deferred():
+            run()
+        ex.finish(*params, grad_accum=acc, denom=den)
+        torch.cuda.synchronize()
+        ex.check_status()
+        for p, r in zip(params, ref):
+            worst = max(worst, float((p.grad - r).abs().max()) / (float(r.abs().max()) + 1e-12))
+            g0 = p.grad.clone()
+            dist.broadcast(g0, 0)
+            ok = ok and bool(torch.equal(g0, p.grad))
+    worst = max(worst, float((acc - acc_ref).abs().max()) / (float(acc_ref.abs().max()) + 1e-12))
+    ok = ok and bool(torch.equal(den, den_ref))
+    torch.save({"ok": ok, "worst": worst}, os.path.join(out_dir, f"f{rank}.pt"))
+    ex.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("sh_degree", [2, None])
+def test_fused_backward_exchange_equals_allreduced_autograd(tmp_path, sh_degree):
+    """SH / projection backward fused with the exchange == dense all-reduce of every rank's autograd gradients
+    (gradient tolerance of north_star: 1e-3 rel), bit-identical on all ranks, densification statistics included."""
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    mp.spawn(_fused_worker, args=(world, _free_port(), str(tmp_path), sh_degree, 4), nprocs=world, join=True)
+    for r in range(world):
+        got = torch.load(os.path.join(str(tmp_path), f"f{r}.pt"))
+        assert got["ok"], f"rank {r}: replicas are not bit-identical (or visibility counts differ)"
+        assert got["worst"] < 1e-4, f"rank {r}: differs from the all-reduced autograd gradients by {got['worst']}"
