@@ -230,6 +230,17 @@ int hgs_densify_stats(const float* v_means2d, int ld_means2d, const int32_t* rad
                       long long n_vis, int C, int N, int width, int height, int mode_max, float* grad_accum,
                       float* denom, float* max_radii, void* stream);
 
+/* ---- f3, first part (next row of SURVEY.md section 8): fused photometric L1 loss -------------------------
+ * L = mean_{p,c<3} |render_colors[p,c] - gt[p,c]| + w_depth * mean_p render_colors[p,3] (D == 4 only)
+ *     + w_alpha * mean_p render_alphas[p] (render_alphas may be NULL)          utils/loss_utils.py:17-18, train.py:158
+ * P = pixels (C*H*W), D = 3 or 4 channels.  fwd: partials[hgs_l1_loss_partials()] scratch, loss[1] out (device).
+ * bwd: v_loss[1] = upstream gradient (device); v_render_colors[P,D], v_render_alphas[P] (or NULL) overwritten. */
+int hgs_l1_loss_partials(void);
+int hgs_l1_loss_fwd(const float* render_colors, const float* render_alphas, const float* gt, long long P, int D,
+                    float w_depth, float w_alpha, float* partials, float* loss, void* stream);
+int hgs_l1_loss_bwd(const float* render_colors, const float* gt, const float* v_loss, long long P, int D,
+                    float w_depth, float w_alpha, float* v_render_colors, float* v_render_alphas, void* stream);
+
 /* ---- e: exchange of view-sharded gradients over NVLink peer memory -----------
  * New behaviour (the reference trains one view per iteration in one process; gaussian_renderer/render.py has no
  * collective): with one view per GPU only the Gaussians a view sees have non-zero gradient rows, so the SUM over

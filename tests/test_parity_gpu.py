@@ -409,3 +409,25 @@ def test_lod_anchor_model_render_through_adapter_control_flow(two_d):
         assert pr.grad is not None and pg.grad is not None, name
         assert rel_err(pg.grad.cpu(), pr.grad) < 5 * GRAD_RTOL, (name, rel_err(pg.grad.cpu(), pr.grad))
     assert go["viewspace_points"].grad is not None
+
+
+# ------------------------------------------------------------------------------------ f3: fused photometric L1 loss
+@pytest.mark.parametrize("D", [3, 4])
+def test_fused_l1_loss_matches_torch(D):
+    """csrc/loss.cu against the reference's expression (utils/loss_utils.py:17-18) written in torch ops"""
+    from horizongs_b200 import losses
+    g = torch.Generator().manual_seed(11)
+    H, Wd = 67, 131
+    rc = torch.rand(2, H, Wd, D, generator=g).cuda().requires_grad_()
+    ra = torch.rand(2, H, Wd, 1, generator=g).cuda().requires_grad_()
+    gt = torch.rand(2, H, Wd, 3, generator=g).cuda()
+    loss = losses.photometric_l1_loss(rc, gt, ra, w_depth=0.01, w_alpha=0.02)
+    (3.0 * loss).backward()
+    rc2, ra2 = rc.detach().clone().requires_grad_(), ra.detach().clone().requires_grad_()
+    ref = (rc2[..., :3] - gt).abs().mean() + 0.02 * ra2.mean()
+    if D == 4:
+        ref = ref + 0.01 * rc2[..., 3].mean()
+    (3.0 * ref).backward()
+    assert abs(float(loss) - float(ref)) < 1e-6 * max(1.0, abs(float(ref)))
+    assert torch.allclose(rc.grad, rc2.grad, rtol=1e-6, atol=1e-12)
+    assert torch.allclose(ra.grad, ra2.grad, rtol=1e-6, atol=1e-12)
