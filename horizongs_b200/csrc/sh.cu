@@ -237,6 +237,98 @@ __global__ void __launch_bounds__(SB) sh_bwd_fused_kernel(const float* __restric
     if (v_means != nullptr && n < N && !vis) { v_means[n * 3] = 0.f; v_means[n * 3 + 1] = 0.f; v_means[n * 3 + 2] = 0.f; }
 }
 
+// Work-list variant for one camera (vis_ids = ascending ids of the visible Gaussians, from hgs_isect_prepare):
+// AUTONOMOUS WARPS, no CTA barrier.  Round k = visible Gaussians [32k, 32k+32) belongs to one warp: lane j owns
+// Gaussian vis_ids[32k + j], so the gradient math runs on dense warps however few Gaussians are visible.  A round
+//   1. zero-fills every output row of the id range it covers -- from its first visible id up to the next round's
+//      first -- with streaming 16-byte stores (culled Gaussians get their zero rows here, no memset pass),
+//   2. stages its 32 coefficient rows in the warp's shared-memory tile, all loads in flight together (coalesced),
+//   3. runs sh_grad_one per lane, leaves the coefficient-gradient row in the tile, writes the direction gradient,
+//   4. writes the 32 coefficient-gradient rows with coalesced stores.
+constexpr int SHW = 8;   // warps per CTA
+template <int DEG>
+__global__ void __launch_bounds__(SHW * 32) sh_bwd_rounds_kernel(const float* __restrict__ means,
+                                                                const float* __restrict__ campos,
+                                                                const float* __restrict__ coeffs,
+                                                                const int32_t* __restrict__ vis_ids, int n_vis,
+                                                                const float* __restrict__ colors,
+                                                                const float* __restrict__ v_colors, int ld_vc, int N,
+                                                                int K, int post, float* __restrict__ v_coeffs,
+                                                                float* __restrict__ v_means) {
+    constexpr int NB = (DEG + 1) * (DEG + 1);
+    constexpr int RL = NB * 3;
+    constexpr int RS = RL | 1;
+    extern __shared__ float s_tiles[];         // [SHW][32][RS]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* rows = s_tiles + warp * 32 * RS;
+    const int n_rounds = max(1, (n_vis + 31) >> 5);
+    const int rnd = blockIdx.x * SHW + warp;
+    if (rnd >= n_rounds) return;
+    const int rowlen = K * 3;
+    const int j0 = rnd << 5;
+    const int nj = min(32, n_vis - j0);        // <= 0 only when nothing is visible
+    const bool mine = lane < nj;
+    const long long n = mine ? vis_ids[j0 + lane] : 0;
+    const long long lo = rnd == 0 ? 0 : vis_ids[j0];
+    const long long hi = rnd == n_rounds - 1 ? N : vis_ids[j0 + 32];
+    // loads of this lane's Gaussian first, so that they are in flight during the zero fill
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f, x = 0.f, y = 0.f, z = 1.f;
+    if (mine) {
+        v0 = v_colors[n * ld_vc]; v1 = v_colors[n * ld_vc + 1]; v2 = v_colors[n * ld_vc + 2];
+        if (post) {
+            if (!(colors[n * 3] > 0.f)) v0 = 0.f;
+            if (!(colors[n * 3 + 1] > 0.f)) v1 = 0.f;
+            if (!(colors[n * 3 + 2] > 0.f)) v2 = 0.f;
+        }
+        x = means[n * 3] - campos[0]; y = means[n * 3 + 1] - campos[1]; z = means[n * 3 + 2] - campos[2];
+    }
+    {
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (v_means != nullptr)
+            for (long long e = lo * 3 + lane; e < hi * 3; e += 32) v_means[e] = 0.f;
+        const long long e_lo = lo * rowlen, e_hi = hi * rowlen;
+        const long long a_lo = min((e_lo + 3) & ~3ll, e_hi), a_hi = max(e_hi & ~3ll, a_lo);
+        for (long long e = e_lo + lane; e < a_lo; e += 32) v_coeffs[e] = 0.f;
+        for (long long e = a_lo + 4 * lane; e < a_hi; e += 128) *reinterpret_cast<float4*>(v_coeffs + e) = z4;
+        for (long long e = a_hi + lane; e < e_hi; e += 32) v_coeffs[e] = 0.f;
+    }
+    const unsigned magic_rl = 0xFFFFFFFFu / (unsigned)RL + 1u;
+    if (v_means != nullptr && DEG >= 1) {
+        float tmp[RL];
+#pragma unroll
+        for (int k = 0; k < RL; ++k) {
+            const int i = lane + 32 * k;
+            const int j = (int)__umulhi((unsigned)i, magic_rl), cc = i - j * RL;
+            tmp[k] = j < nj ? coeffs[(long long)vis_ids[j0 + j] * rowlen + cc] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < RL; ++k) {
+            const int i = lane + 32 * k;
+            const int j = (int)__umulhi((unsigned)i, magic_rl), cc = i - j * RL;
+            rows[j * RS + cc] = tmp[k];
+        }
+    }
+    __syncwarp();          // tile staged; the zero fill is ordered before the row / direction-gradient stores below
+    if (mine) {
+        float g_co[RL];
+#pragma unroll
+        for (int k = 0; k < RL; ++k) g_co[k] = 0.f;
+        float gd0, gd1, gd2;
+        sh_grad_one<DEG>(x, y, z, rows + lane * RS, v0, v1, v2, v_means != nullptr && DEG >= 1, g_co, gd0, gd1, gd2);
+        float* out = rows + lane * RS;
+#pragma unroll
+        for (int k = 0; k < RL; ++k) out[k] = g_co[k];
+        if (v_means != nullptr) { v_means[n * 3] = gd0; v_means[n * 3 + 1] = gd1; v_means[n * 3 + 2] = gd2; }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < RL; ++k) {
+        const int i = lane + 32 * k;
+        const int j = (int)__umulhi((unsigned)i, magic_rl), cc = i - j * RL;
+        if (j < nj) v_coeffs[(long long)vis_ids[j0 + j] * rowlen + cc] = rows[j * RS + cc];
+    }
+}
+
 }  // namespace
 
 HGS_API int hgs_sh_fwd(int degree, int K, const float* dirs, const float* means, const float* campos,
@@ -287,7 +379,28 @@ HGS_API int hgs_sh_bwd(int degree, int K, const float* dirs, const float* means,
     if (post && colors == nullptr) return HGS_ERR_INVALID_ARG;
     if (N == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    (void)vis_ids; (void)n_vis;
+    if (vis_ids != nullptr && C == 1 && dirs == nullptr && v_dirs == nullptr && n_vis < (1ll << 31)) {
+        // rasterization path, one camera: dense-warp rounds over the visible work list (zero fill included)
+        const int n_rounds = (int)((n_vis + 31) / 32 < 1 ? 1 : (n_vis + 31) / 32);
+        const int grid = hgs_ceil_div(n_rounds, SHW);
+#define LAUNCH(DEG)                                                                                                \
+    {                                                                                                              \
+        const size_t smem = (size_t)SHW * 32 * ((((DEG) + 1) * ((DEG) + 1) * 3) | 1) * sizeof(float);              \
+        cudaFuncSetAttribute(sh_bwd_rounds_kernel<DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+        sh_bwd_rounds_kernel<DEG><<<grid, SHW * 32, smem, st>>>(means, campos, coeffs, vis_ids, (int)n_vis, colors, \
+                                                               v_colors, ld_v_colors, N, K, post, v_coeffs, v_means); \
+    }
+        switch (degree) {
+            case 0: LAUNCH(0) break;
+            case 1: LAUNCH(1) break;
+            case 2: LAUNCH(2) break;
+            case 3: LAUNCH(3) break;
+            default: LAUNCH(4) break;
+        }
+#undef LAUNCH
+        HGS_LAUNCH_CHECK();
+        return 0;
+    }
     if (radii != nullptr && dirs == nullptr && v_dirs == nullptr) {
         // rasterization path: fused zero-fill + block-compacted gradient rows, one pass over v_coeffs
         const int grid = hgs_ceil_div(N, SB);
