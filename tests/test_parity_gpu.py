@@ -428,6 +428,6 @@ def test_fused_l1_loss_matches_torch(D):
     if D == 4:
         ref = ref + 0.01 * rc2[..., 3].mean()
     (3.0 * ref).backward()
-    assert abs(float(loss) - float(ref)) < 1e-6 * max(1.0, abs(float(ref)))
+    assert abs(float(loss.detach()) - float(ref.detach())) < 1e-6 * max(1.0, abs(float(ref.detach())))
     assert torch.allclose(rc.grad, rc2.grad, rtol=1e-6, atol=1e-12)
     assert torch.allclose(ra.grad, ra2.grad, rtol=1e-6, atol=1e-12)
