@@ -1,24 +1,25 @@
 // Stage e, fused form: the backward of the per-Gaussian stages (a7 spherical harmonics,
 // a3 projection) FUSED with the exchange of the view-sharded gradients over NVLink peer memory.
 //
-// With replicated Gaussian parameters the gradient of view v w.r.t. means / quats / scales / SH coefficients is a
-// function of (a) the 12-float row the blend backward produced for that Gaussian (v_means2d, v_conics,
-// v_opacities, v_colors, v_depths: one row of the packed gradient buffer `vpack`), (b) the Gaussian's parameters,
-// which EVERY rank holds, and (c) view v's camera.  So the ranks do not exchange the 38 parameter gradients of
-// their visible Gaussians (160 B per record, csrc/exchange.cu) but the 48-byte blend-gradient rows, 3.3x less
-// NVLink traffic, and every rank then runs the SH / projection backward of ALL views' rows itself:
-//   push   : each rank stores the vpack rows of its visible Gaussians (SH clamp mask applied) and its camera
-//            into a mailbox slot in every peer's memory (TMA bulk stores, release flag; exchange_common.cuh);
-//   reduce : one CTA per block of 256 consecutive Gaussian ids; the thread that owns a touched Gaussian loops
-//            over the sources that saw it IN RANK ORDER, runs sh_grad_one / proj3d_bwd_one (the same device
-//            functions as the single-GPU backward kernels, sh_math.cuh / project3d_math.cuh) with that
-//            source's camera and accumulates in registers; the dense gradient tensors are written once
-//            (v_coeffs with coalesced 16-byte stores, zeros for untouched rows) and the densification
-//            statistics (scene/basic_model.py:131-144) are updated in the same pass.
-// This replaces, per step and rank: sh_bwd + project3d_bwd + densify_stats + the gradient all-reduce.
+// A view's gradient w.r.t. the 38 floats of a Gaussian has 27 floats of SH-coefficient gradient, and that part is
+// RANK ONE: v_coeffs[k][c] = basis_k(direction) * v_colour[c], where the direction is (mean - camera position)
+// and every rank holds the means.  So the ranks do not exchange 38 gradients per visible Gaussian (160 B,
+// csrc/exchange.cu) but a 64-byte record:
+//   push   : one thread per visible Gaussian runs the camera-specific backward -- projection VJP (means, quats,
+//            scales), SH direction gradient (into means), densification norm -- from the row the blend backward
+//            left in `vpack`, and the record {v_means 3, v_opacity, v_quats 4, v_scales 3, norm, v_colour 3} is
+//            staged in shared memory and stored with TMA bulk copies into a mailbox slot in EVERY peer's memory
+//            (release flag; exchange_common.cuh).  The heavy math runs once per (Gaussian, view) pair, on the
+//            rank that rendered the view, on dense warps.
+//   reduce : on every rank, one lane per (Gaussian, view) pair expands the rank-one SH part (basis of that
+//            view's direction x v_colour) and the pairs of a Gaussian are summed IN RANK ORDER; the dense
+//            gradient tensors are written once (zeros for untouched rows) and the densification statistics
+//            (scene/basic_model.py:131-144) are updated in the same pass.
+// This replaces, per step and rank: sh_bwd + project3d_bwd + densify_stats + the gradient all-reduce, with
+// 2.5x less NVLink traffic than the sparse all-reduce and 25x less than the dense one.
 // All replicas add the same numbers in the same order: bit-identical gradients on every rank.
-// (Built with fused multiply-add: the backward needs no bit-equality with the oracle, and it is 25 % fewer
-// instructions; the single-GPU backward kernels use the same source with -fmad=false.)
+// (Built with fused multiply-add: the backward needs no bit-equality with the oracle; the single-GPU backward
+// kernels use the same device functions with -fmad=false.)
 #include <stdlib.h>
 
 #include "exchange_common.cuh"
@@ -28,63 +29,10 @@
 
 namespace {
 
-constexpr int VJ_ROW = 12;        // floats per record = one vpack row
+constexpr int VJ_ROW = 16;        // floats per record: v_means 3, v_opacity | v_quats 4 | v_scales 3, norm | v_colour 3, -
 constexpr int VJ_R4 = VJ_ROW / 4;
 constexpr int VJ_CAM = 28;        // viewmat 16, K 9, camera position 3 (slot header, after the row count)
-
-__global__ void __launch_bounds__(EX_THREADS) vjp_push_kernel(ExPeers P, ExLayout L, const float4* __restrict__ vpack,
-                                                             const float* __restrict__ colors_fwd,
-                                                             const float* __restrict__ viewmat,
-                                                             const float* __restrict__ Kmat,
-                                                             const float* __restrict__ campos,
-                                                             const int32_t* __restrict__ ids, int n_rows, int parity,
-                                                             unsigned long long flag_value) {
-    __shared__ __align__(128) float4 stage[2][EX_CHUNK * VJ_R4];
-    const size_t soff = slot_offset(L, parity, P.rank);
-    write_block_entries(P, L, soff, ids, n_rows);
-    if (blockIdx.x == 0 && threadIdx.x <= VJ_CAM) {
-        const int t = threadIdx.x;
-        for (int q = 0; q < P.world; ++q) {
-            unsigned char* hdr = P.base[q] + soff;
-            if (t == 0) {
-                *reinterpret_cast<long long*>(hdr) = n_rows;
-            } else {
-                const int k = t - 1;
-                reinterpret_cast<float*>(hdr + 8)[k] = k < 16 ? viewmat[k] : (k < 25 ? Kmat[k - 16] : campos[k - 25]);
-            }
-        }
-    }
-    const int n_chunks = (n_rows + EX_CHUNK - 1) / EX_CHUNK;
-    int it = 0;
-    for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, ++it) {
-        const int st = it & 1;
-        const int r0 = chunk * EX_CHUNK;
-        const int nr = min(EX_CHUNK, n_rows - r0);
-        if (threadIdx.x < P.world) bulk_wait_read<1>();   // stage `st` was last read by the stores of iteration it - 2
-        __syncthreads();
-        for (int f = threadIdx.x; f < nr * VJ_R4; f += EX_THREADS) {
-            const int r = f / VJ_R4;
-            const int c = f - r * VJ_R4;
-            const long long id = ids[r0 + r];
-            float4 v = vpack[id * VJ_R4 + c];
-            if (c == 2 && colors_fwd != nullptr) {
-                // gsplat's clamp_min(colour + 0.5, 0): no gradient through a clamped channel
-                if (!(colors_fwd[id * 3 + 0] > 0.f)) v.x = 0.f;
-                if (!(colors_fwd[id * 3 + 1] > 0.f)) v.y = 0.f;
-                if (!(colors_fwd[id * 3 + 2] > 0.f)) v.z = 0.f;
-            }
-            stage[st][f] = v;
-        }
-        fence_proxy_async();
-        __syncthreads();
-        if (threadIdx.x < P.world) {
-            bulk_s2g(P.base[threadIdx.x] + soff + L.rows_off + (size_t)r0 * VJ_ROW * 4, stage[st],
-                     (unsigned)(nr * VJ_ROW * 4));
-            bulk_commit();
-        }
-    }
-    publish_push(P, flag_value);
-}
+constexpr int VJ_PUSH = 256;      // records computed and staged per iteration of a push CTA (one per thread)
 
 __device__ __forceinline__ HgsCam cam_from(const float* c) {
     HgsCam cam;
@@ -101,6 +49,85 @@ __device__ __forceinline__ HgsCam cam_from(const float* c) {
     return cam;
 }
 
+// The push kernel: thread t of a CTA computes the record of one visible Gaussian (the camera-specific backward),
+// the CTA stages 256 records in shared memory and stores them with one TMA bulk copy per peer (double buffered).
+template <int DEG>
+__global__ void __launch_bounds__(VJ_PUSH) vjp_push_kernel(
+    ExPeers P, ExLayout L, const float4* __restrict__ vpack, const float* __restrict__ colors_fwd,
+    const float* __restrict__ viewmat, const float* __restrict__ Kmat, const float* __restrict__ campos,
+    const float* __restrict__ means, const float* __restrict__ quats, const float* __restrict__ scales,
+    const float* __restrict__ coeffs, int K, float Wf, float Hf, float eps2d, float near_plane, float far_plane,
+    const int32_t* __restrict__ ids, int n_rows, int parity, unsigned long long flag_value) {
+    __shared__ __align__(128) float4 stage[2][VJ_PUSH * VJ_R4];
+    const size_t soff = slot_offset(L, parity, P.rank);
+    write_block_entries(P, L, soff, ids, n_rows);
+    if (blockIdx.x == 0 && threadIdx.x <= VJ_CAM) {
+        const int t = threadIdx.x;
+        for (int q = 0; q < P.world; ++q) {
+            unsigned char* hdr = P.base[q] + soff;
+            if (t == 0) {
+                *reinterpret_cast<long long*>(hdr) = n_rows;
+            } else {
+                const int k = t - 1;
+                reinterpret_cast<float*>(hdr + 8)[k] = k < 16 ? viewmat[k] : (k < 25 ? Kmat[k - 16] : campos[k - 25]);
+            }
+        }
+    }
+    float camf[VJ_CAM];
+#pragma unroll
+    for (int k = 0; k < VJ_CAM; ++k) camf[k] = k < 16 ? viewmat[k] : (k < 25 ? Kmat[k - 16] : campos[k - 25]);
+    const HgsCam cam = cam_from(camf);
+    const int rowlen = K * 3;
+    const int n_chunks = (n_rows + VJ_PUSH - 1) / VJ_PUSH;
+    int it = 0;
+    for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, ++it) {
+        const int st = it & 1;
+        const int r0 = chunk * VJ_PUSH;
+        const int nr = min(VJ_PUSH, n_rows - r0);
+        if (threadIdx.x < P.world) bulk_wait_read<1>();   // stage `st` was last read by the stores of iteration it - 2
+        __syncthreads();
+        if (threadIdx.x < nr) {
+            const long long n = ids[r0 + threadIdx.x];
+            const float4 q0 = vpack[n * 3], q1 = vpack[n * 3 + 1];     // v_means2d, v_conics a b | c, v_opacity
+            float4 q2 = vpack[n * 3 + 2];                              // v_colour, v_depth
+            if (colors_fwd != nullptr) {
+                // gsplat's clamp_min(colour + 0.5, 0): no gradient through a clamped channel
+                if (!(colors_fwd[n * 3 + 0] > 0.f)) q2.x = 0.f;
+                if (!(colors_fwd[n * 3 + 1] > 0.f)) q2.y = 0.f;
+                if (!(colors_fwd[n * 3 + 2] > 0.f)) q2.z = 0.f;
+            }
+            const float px = means[n * 3], py = means[n * 3 + 1], pz = means[n * 3 + 2];
+            const float s0 = scales[n * 3], s1 = scales[n * 3 + 1], s2 = scales[n * 3 + 2];
+            const float4 qv = reinterpret_cast<const float4*>(quats)[n];
+            float g_mean[3] = {0.f, 0.f, 0.f}, g_scale[3] = {0.f, 0.f, 0.f}, g_quat[4] = {0.f, 0.f, 0.f, 0.f};
+            if (DEG >= 1) {
+                float gd0, gd1, gd2;
+                sh_dirgrad_one<(DEG >= 1 ? DEG : 1)>(px - camf[25], py - camf[26], pz - camf[27], coeffs + n * rowlen, q2.x,
+                                                     q2.y, q2.z, gd0, gd1, gd2);
+                g_mean[0] = gd0; g_mean[1] = gd1; g_mean[2] = gd2;
+            }
+            Proj3dFwd f;
+            if (proj3d_math(cam, px, py, pz, qv.x, qv.y, qv.z, qv.w, s0, s1, s2, Wf, Hf, eps2d, near_plane, far_plane, f))
+                proj3d_bwd_one(cam, f, s0, s1, s2, make_float2(q0.x, q0.y), q2.w, q0.z, 0.5f * q0.w, q1.x, g_mean, g_scale,
+                               g_quat);
+            const float gx = q0.x * (0.5f * Wf), gy = q0.y * (0.5f * Hf);
+            float4* rec = stage[st] + threadIdx.x * VJ_R4;
+            rec[0] = make_float4(g_mean[0], g_mean[1], g_mean[2], q1.y);
+            rec[1] = make_float4(g_quat[0], g_quat[1], g_quat[2], g_quat[3]);
+            rec[2] = make_float4(g_scale[0], g_scale[1], g_scale[2], sqrtf(gx * gx + gy * gy));
+            rec[3] = make_float4(q2.x, q2.y, q2.z, 0.f);
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (threadIdx.x < P.world) {
+            bulk_s2g(P.base[threadIdx.x] + soff + L.rows_off + (size_t)r0 * VJ_ROW * 4, stage[st],
+                     (unsigned)(nr * VJ_ROW * 4));
+            bulk_commit();
+        }
+    }
+    publish_push(P, flag_value);
+}
+
 // The reduce kernel.  One CTA of 8 warps owns RANGE consecutive Gaussian ids (RANGE / 256 block entries per
 // source).  Set-up (one round trip, a few barriers): the sources' presence bitmaps of the range, their union, the
 // ordered list of touched ids and the prefix sum of their (Gaussian, source) PAIR counts go to shared memory.
@@ -108,9 +135,9 @@ __device__ __forceinline__ HgsCam cam_from(const float* c) {
 // three serial iterations of one lane.  The touched list is cut into rounds of whole Gaussians holding at most 32
 // pairs (a new round starts whenever the running pair count passes a multiple of T = 33 - world), round k
 // belongs to warp k % 8, and from there the warps are AUTONOMOUS (no CTA barrier).  A round
-//   1. stages the coefficient rows of its Gaussians in the warp's shared-memory tile (coalesced, all loads in
-//      flight together) while every lane loads its pair's 48-byte record and its Gaussian's parameters,
-//   2. every lane runs the SH and the projection backward of its pair with that source's camera,
+//   1. every lane loads its pair's 64-byte record and its Gaussian's mean; meanwhile the id range the round
+//      covers is zero-filled with streaming 16-byte stores,
+//   2. every lane expands the rank-one SH part of its pair: basis(mean - that view's camera position) x v_colour,
 //   3. the pairs of one Gaussian are summed IN RANK ORDER by the lane of its first pair (through a
 //      shared-memory tile; single-source Gaussians -- the majority -- skip it), which writes the per-Gaussian
 //      rows and leaves the coefficient-gradient row in the tile,
@@ -122,7 +149,7 @@ __device__ __forceinline__ HgsCam cam_from(const float* c) {
 constexpr int VJ_WARPS = 8;
 constexpr int VJ_RANGE = 2048;                 // Gaussian ids per CTA
 constexpr int VJ_NW = VJ_RANGE / 32;           // bitmap words per CTA
-constexpr int VJ_OUT = 16;                     // per-pair outputs besides the coefficient gradients
+constexpr int VJ_OUT = 13;                     // per-pair outputs besides the coefficient gradients
 struct VjSmem {      // followed by unsigned bits[world][NW], int first[world][NW], then the per-warp tiles
     float cam[EX_MAX_W][VJ_CAM];
     unsigned uni[VJ_NW];                // union of the sources' bitmaps
@@ -139,11 +166,9 @@ static_assert(sizeof(VjSmem) % 16 == 0, "tile alignment");
 template <int DEG>
 __global__ void __launch_bounds__(VJ_WARPS * 32, 2) vjp_reduce_kernel(
     ExLayout L, const unsigned char* mailbox, int parity, const int* __restrict__ status,
-    const float* __restrict__ means, const float* __restrict__ quats, const float* __restrict__ scales,
-    const float* __restrict__ coeffs, int K, float Wf, float Hf, float eps2d, float near_plane, float far_plane,
-    float* __restrict__ v_means, float* __restrict__ v_quats, float* __restrict__ v_scales,
-    float* __restrict__ v_opac, float* __restrict__ v_coeffs, float* __restrict__ grad_accum,
-    float* __restrict__ denom) {
+    const float* __restrict__ means, int K, float* __restrict__ v_means, float* __restrict__ v_quats,
+    float* __restrict__ v_scales, float* __restrict__ v_opac, float* __restrict__ v_coeffs,
+    float* __restrict__ grad_accum, float* __restrict__ denom) {
     constexpr int NB = DEG >= 0 ? (DEG + 1) * (DEG + 1) : 1;
     constexpr int RL = NB * 3;
     constexpr int RS = RL | 1;
@@ -298,17 +323,15 @@ __global__ void __launch_bounds__(VJ_WARPS * 32, 2) vjp_reduce_kernel(
             for (int k = lane - seg_off; k > 0; --k) m &= m - 1;    // (lane - seg_off)-th source that saw it
             src = __ffs(m) - 1;
         }
-        // (1) loads: the pair's record and the Gaussian's parameters, then the coefficient rows -> tile
-        float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0, qv = make_float4(1.f, 0.f, 0.f, 0.f);
-        float px = 0.f, py = 0.f, pz = 0.f, s0 = 1.f, s1 = 1.f, s2 = 1.f;
+        // (1) loads: the pair's record and the Gaussian's mean
+        float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0, q3 = q0;
+        float px = 0.f, py = 0.f, pz = 1.f;
         if (mine) {
             const int rec_i = s_first[src * NW + (l >> 5)] + __popc(s_bits[src * NW + (l >> 5)] & ((1u << (l & 31)) - 1u));
             const float4* rec = reinterpret_cast<const float4*>(mailbox + slot_offset(L, parity, src) + L.rows_off) +
                                 (size_t)rec_i * VJ_R4;
-            q0 = __ldcg(rec); q1 = __ldcg(rec + 1); q2 = __ldcg(rec + 2);
-            px = means[n * 3]; py = means[n * 3 + 1]; pz = means[n * 3 + 2];
-            s0 = scales[n * 3]; s1 = scales[n * 3 + 1]; s2 = scales[n * 3 + 2];
-            qv = reinterpret_cast<const float4*>(quats)[n];
+            q0 = __ldcg(rec); q1 = __ldcg(rec + 1); q2 = __ldcg(rec + 2); q3 = __ldcg(rec + 3);
+            if (DEG >= 1) { px = means[n * 3]; py = means[n * 3 + 1]; pz = means[n * 3 + 2]; }
         }
         // the id range this round covers: [its first touched id (or the CTA's first id), the next round's first).
         // All of its output rows are zeroed first (plain streaming stores, issued while the loads above are in
@@ -331,47 +354,30 @@ __global__ void __launch_bounds__(VJ_WARPS * 32, 2) vjp_reduce_kernel(
             for (long long e = a_lo + 4 * lane; e < a_hi; e += 128) *reinterpret_cast<float4*>(v_coeffs + e) = z4;
             for (long long e = a_hi + lane; e < e_hi; e += 32) v_coeffs[e] = 0.f;
         }
-        if (DEG >= 1) {
-            const unsigned magic_rl = 0xFFFFFFFFu / (unsigned)RL + 1u;
-            float tmp[RL];
-#pragma unroll
-            for (int k = 0; k < RL; ++k) {
-                const int i = lane + 32 * k;
-                const int j = (int)__umulhi((unsigned)i, magic_rl), cc = i - j * RL;
-                tmp[k] = j < nG ? coeffs[(id0 + S.list[j0 + j]) * (long long)rowlen + cc] : 0.f;
-            }
-#pragma unroll
-            for (int k = 0; k < RL; ++k) {
-                const int i = lane + 32 * k;
-                const int j = (int)__umulhi((unsigned)i, magic_rl), cc = i - j * RL;
-                rows[j * RS + cc] = tmp[k];
-            }
-            __syncwarp();
-        }
-        // (2) the pair's backward
+        // (2) the pair's contribution: the rank-one SH part expanded, the rest as the pusher computed it
         float g_co[RL];
-        float o[VJ_OUT];     // gm 0..2 | g_mean 3..5 | g_scale 6..8 | g_quat 9..12 | opacity 13 | norm 14 | count 15
+        float o[VJ_OUT];     // v_means 0..2 | v_quats 3..6 | v_scales 7..9 | opacity 10 | norm 11 | count 12
 #pragma unroll
         for (int k = 0; k < RL; ++k) g_co[k] = 0.f;
 #pragma unroll
         for (int k = 0; k < VJ_OUT; ++k) o[k] = 0.f;
         if (mine) {
             if (DEG >= 0) {
-                const float x = px - S.cam[src][25], y = py - S.cam[src][26], z = pz - S.cam[src][27];
-                sh_grad_one<(DEG >= 0 ? DEG : 0)>(x, y, z, rows + g * RS, q2.x, q2.y, q2.z, DEG >= 1, g_co, o[0], o[1], o[2]);
+                float b[NB];
+                if (DEG >= 1) sh_basis_of<(DEG >= 0 ? DEG : 0)>(px - S.cam[src][25], py - S.cam[src][26], pz - S.cam[src][27], b);
+                else b[0] = 0.2820947917738781f;
+#pragma unroll
+                for (int k = 0; k < NB; ++k) {
+                    g_co[k * 3] = b[k] * q3.x; g_co[k * 3 + 1] = b[k] * q3.y; g_co[k * 3 + 2] = b[k] * q3.z;
+                }
             } else {
-                g_co[0] = q2.x; g_co[1] = q2.y; g_co[2] = q2.z;
+                g_co[0] = q3.x; g_co[1] = q3.y; g_co[2] = q3.z;
             }
-            const HgsCam cam = cam_from(S.cam[src]);
-            Proj3dFwd f;
-            if (proj3d_math(cam, px, py, pz, qv.x, qv.y, qv.z, qv.w, s0, s1, s2, Wf, Hf, eps2d, near_plane, far_plane, f))
-                proj3d_bwd_one(cam, f, s0, s1, s2, make_float2(q0.x, q0.y), q2.w, q0.z, 0.5f * q0.w, q1.x, o + 3, o + 6, o + 9);
-            o[13] = q1.y;
-            const float gx = q0.x * (0.5f * Wf), gy = q0.y * (0.5f * Hf);
-            o[14] = sqrtf(gx * gx + gy * gy);
-            o[15] = 1.f;
+            o[0] = q0.x; o[1] = q0.y; o[2] = q0.z; o[10] = q0.w;
+            o[3] = q1.x; o[4] = q1.y; o[5] = q1.z; o[6] = q1.w;
+            o[7] = q2.x; o[8] = q2.y; o[9] = q2.z; o[11] = q2.w;
+            o[12] = 1.f;
         }
-        __syncwarp();      // every lane is done reading the coefficient rows
         // (3) sum a Gaussian's pairs in rank order at its first pair's lane
         const bool head = mine && lane == seg_off;
         if (mine && !head) {
@@ -396,16 +402,16 @@ __global__ void __launch_bounds__(VJ_WARPS * 32, 2) vjp_reduce_kernel(
             float* out = rows + g * RS;
 #pragma unroll
             for (int k = 0; k < RL; ++k) out[k] = g_co[k];
-            v_means[n * 3] = o[0] + o[3];
-            v_means[n * 3 + 1] = o[1] + o[4];
-            v_means[n * 3 + 2] = o[2] + o[5];
-            v_scales[n * 3] = o[6];
-            v_scales[n * 3 + 1] = o[7];
-            v_scales[n * 3 + 2] = o[8];
-            reinterpret_cast<float4*>(v_quats)[n] = make_float4(o[9], o[10], o[11], o[12]);
-            v_opac[n] = o[13];
-            if (grad_accum != nullptr) grad_accum[n] += o[14];
-            if (denom != nullptr) denom[n] += o[15];
+            v_means[n * 3] = o[0];
+            v_means[n * 3 + 1] = o[1];
+            v_means[n * 3 + 2] = o[2];
+            reinterpret_cast<float4*>(v_quats)[n] = make_float4(o[3], o[4], o[5], o[6]);
+            v_scales[n * 3] = o[7];
+            v_scales[n * 3 + 1] = o[8];
+            v_scales[n * 3 + 2] = o[9];
+            v_opac[n] = o[10];
+            if (grad_accum != nullptr) grad_accum[n] += o[11];
+            if (denom != nullptr) denom[n] += o[12];
         }
         __syncwarp();
         // (4) the round's coefficient-gradient rows, coalesced: consecutive lanes write consecutive floats of a row
@@ -424,9 +430,8 @@ __global__ void __launch_bounds__(VJ_WARPS * 32, 2) vjp_reduce_kernel(
 
 template <int DEG>
 int launch_reduce(const ExLayout& L, const unsigned char* mailbox, int parity, const int* status, const float* means,
-                  const float* quats, const float* scales, const float* coeffs, int K, int width, int height,
-                  float eps2d, float near_plane, float far_plane, float* v_means, float* v_quats, float* v_scales,
-                  float* v_opac, float* v_coeffs, float* grad_accum, float* denom, cudaStream_t st) {
+                  int K, float* v_means, float* v_quats, float* v_scales, float* v_opac, float* v_coeffs,
+                  float* grad_accum, float* denom, cudaStream_t st) {
     constexpr int NB = DEG >= 0 ? (DEG + 1) * (DEG + 1) : 1;
     constexpr int RL = NB * 3;
     const int smem = (int)(sizeof(VjSmem) + (size_t)L.world * VJ_NW * 8 +
@@ -434,9 +439,25 @@ int launch_reduce(const ExLayout& L, const unsigned char* mailbox, int parity, c
     cudaError_t e = cudaFuncSetAttribute(vjp_reduce_kernel<DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     const int grid = (int)((L.n_ids + VJ_RANGE - 1) / VJ_RANGE);
-    vjp_reduce_kernel<DEG><<<grid, VJ_WARPS * 32, smem, st>>>(
-        L, mailbox, parity, status, means, quats, scales, coeffs, K, (float)width, (float)height, eps2d, near_plane,
-        far_plane, v_means, v_quats, v_scales, v_opac, v_coeffs, grad_accum, denom);
+    vjp_reduce_kernel<DEG><<<grid, VJ_WARPS * 32, smem, st>>>(L, mailbox, parity, status, means, K, v_means, v_quats,
+                                                             v_scales, v_opac, v_coeffs, grad_accum, denom);
+    HGS_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int DEG>
+int launch_push(const ExPeers& P, const ExLayout& L, const float* vpack, const float* colors_fwd, const float* viewmat,
+                const float* Kmat, const float* campos, const float* means, const float* quats, const float* scales,
+                const float* coeffs, int K, int width, int height, float eps2d, float near_plane, float far_plane,
+                const int32_t* ids, int n_rows, int parity, unsigned long long flag_value, cudaStream_t st) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int chunks = (n_rows + VJ_PUSH - 1) / VJ_PUSH;
+    const int grid = chunks < 1 ? 1 : (chunks > sms * 4 ? sms * 4 : chunks);
+    vjp_push_kernel<DEG><<<grid, VJ_PUSH, 0, st>>>(P, L, reinterpret_cast<const float4*>(vpack), colors_fwd, viewmat, Kmat,
+                                                   campos, means, quats, scales, coeffs, K, (float)width, (float)height,
+                                                   eps2d, near_plane, far_plane, ids, n_rows, parity, flag_value);
     HGS_LAUNCH_CHECK();
     return 0;
 }
@@ -448,41 +469,50 @@ HGS_API size_t hgs_exchange_vjp_mailbox_bytes(int world, long long n_ids, long l
     return EX_CTRL_BYTES + (size_t)2 * world * make_layout(world, n_ids, cap_rows, VJ_ROW).slot_bytes;
 }
 
-HGS_API int hgs_exchange_vjp_push(const float* vpack, const float* colors_fwd, const float* viewmat, const float* K,
-                                  const float* campos, long long n_ids, const int32_t* ids, long long n_rows,
-                                  long long cap_rows, void* const* mailboxes_host, int world, int rank,
+HGS_API int hgs_exchange_vjp_push(int sh_degree, int K, const float* vpack, const float* colors_fwd, const float* viewmat,
+                                  const float* Kmat, const float* campos, const float* means, const float* quats,
+                                  const float* scales, const float* coeffs, int width, int height, float eps2d,
+                                  float near_plane, float far_plane, long long n_ids, const int32_t* ids,
+                                  long long n_rows, long long cap_rows, void* const* mailboxes_host, int world, int rank,
                                   unsigned long long step, void* stream) {
     if (ex_bad_geometry(world, rank, n_ids, cap_rows) || n_rows < 0 || vpack == nullptr || viewmat == nullptr ||
-        K == nullptr || campos == nullptr || (reinterpret_cast<size_t>(vpack) & 15))
+        Kmat == nullptr || campos == nullptr || means == nullptr || quats == nullptr || scales == nullptr ||
+        (reinterpret_cast<size_t>(vpack) & 15) || (reinterpret_cast<size_t>(quats) & 15) || sh_degree < -1 ||
+        sh_degree > 4 || width <= 0 || height <= 0)
         return HGS_ERR_INVALID_ARG;
+    if (sh_degree >= 0 ? K < (sh_degree + 1) * (sh_degree + 1) : K != 1) return HGS_ERR_INVALID_ARG;
+    if (sh_degree >= 1 && coeffs == nullptr) return HGS_ERR_INVALID_ARG;
     if (n_rows > cap_rows) return HGS_ERR_WORKSPACE;
     if (n_rows > 0 && ids == nullptr) return HGS_ERR_INVALID_ARG;
     ExPeers P;
     if (int e = ex_fill_peers(P, mailboxes_host, world, rank)) return e;
     const ExLayout L = make_layout(world, n_ids, cap_rows, VJ_ROW);
-    vjp_push_kernel<<<ex_push_grid(n_rows), EX_THREADS, 0, (cudaStream_t)stream>>>(
-        P, L, reinterpret_cast<const float4*>(vpack), colors_fwd, viewmat, K, campos, ids, (int)n_rows, (int)(step & 1ull),
-        step + 1ull);
-    HGS_LAUNCH_CHECK();
-    return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(DEG)                                                                                                       \
+    launch_push<DEG>(P, L, vpack, colors_fwd, viewmat, Kmat, campos, means, quats, scales, coeffs, K, width, height, eps2d, \
+                     near_plane, far_plane, ids, (int)n_rows, (int)(step & 1ull), step + 1ull, st)
+    switch (sh_degree) {
+        case 1: return CALL(1);
+        case 2: return CALL(2);
+        case 3: return CALL(3);
+        case 4: return CALL(4);
+        default: return CALL(0);     // degree 0 and plain colours: no direction gradient
+    }
+#undef CALL
 }
 
-HGS_API int hgs_exchange_vjp_reduce(int sh_degree, int K, const float* means, const float* quats, const float* scales,
-                                    const float* coeffs, int width, int height, float eps2d, float near_plane,
-                                    float far_plane, long long n_ids, long long cap_rows, const void* mailbox, int world,
-                                    int rank, unsigned long long step, float* v_means, float* v_quats, float* v_scales,
-                                    float* v_opacities, float* v_coeffs, float* grad_accum, float* denom,
-                                    int* status_dev, void* stream) {
+HGS_API int hgs_exchange_vjp_reduce(int sh_degree, int K, const float* means, long long n_ids, long long cap_rows,
+                                    const void* mailbox, int world, int rank, unsigned long long step, float* v_means,
+                                    float* v_quats, float* v_scales, float* v_opacities, float* v_coeffs,
+                                    float* grad_accum, float* denom, int* status_dev, void* stream) {
     if (ex_bad_geometry(world, rank, n_ids, cap_rows) || mailbox == nullptr || status_dev == nullptr || sh_degree < -1 ||
-        sh_degree > 4 || width <= 0 || height <= 0)
+        sh_degree > 4)
         return HGS_ERR_INVALID_ARG;
     if (sh_degree >= 0 ? K < (sh_degree + 1) * (sh_degree + 1) : K != 1) return HGS_ERR_INVALID_ARG;
-    if (means == nullptr || quats == nullptr || scales == nullptr || (sh_degree >= 1 && coeffs == nullptr) ||
-        v_means == nullptr || v_quats == nullptr || v_scales == nullptr || v_opacities == nullptr || v_coeffs == nullptr)
+    if (means == nullptr || v_means == nullptr || v_quats == nullptr || v_scales == nullptr || v_opacities == nullptr ||
+        v_coeffs == nullptr)
         return HGS_ERR_INVALID_ARG;
-    if ((reinterpret_cast<size_t>(quats) & 15) || (reinterpret_cast<size_t>(v_quats) & 15) ||
-        (reinterpret_cast<size_t>(v_coeffs) & 15))
-        return HGS_ERR_INVALID_ARG;
+    if ((reinterpret_cast<size_t>(v_quats) & 15) || (reinterpret_cast<size_t>(v_coeffs) & 15)) return HGS_ERR_INVALID_ARG;
     const ExLayout L = make_layout(world, n_ids, cap_rows, VJ_ROW);
     cudaStream_t st = (cudaStream_t)stream;
     exchange_wait_kernel<<<1, 32, 0, st>>>((const unsigned char*)mailbox, world, step + 1ull, status_dev);
@@ -490,8 +520,8 @@ HGS_API int hgs_exchange_vjp_reduce(int sh_degree, int K, const float* means, co
     const unsigned char* mb = (const unsigned char*)mailbox;
     const int parity = (int)(step & 1ull);
 #define CALL(DEG)                                                                                                      \
-    launch_reduce<DEG>(L, mb, parity, status_dev, means, quats, scales, coeffs, K, width, height, eps2d, near_plane,    \
-                       far_plane, v_means, v_quats, v_scales, v_opacities, v_coeffs, grad_accum, denom, st)
+    launch_reduce<DEG>(L, mb, parity, status_dev, means, K, v_means, v_quats, v_scales, v_opacities, v_coeffs, grad_accum, \
+                       denom, st)
     switch (sh_degree) {
         case -1: return CALL(-1);
         case 0: return CALL(0);

@@ -155,4 +155,32 @@ __device__ __forceinline__ void sh_grad_one(float x, float y, float z, const flo
     }
 }
 
+// direction gradient only (no coefficient gradients): gd = d/d(un-normalised direction) of sum_c v_c * colour_c
+template <int DEG>
+__device__ __forceinline__ void sh_dirgrad_one(float x, float y, float z, const float* __restrict__ co, float v0, float v1,
+                                               float v2, float& gd0, float& gd1, float& gd2) {
+    constexpr int NB = (DEG + 1) * (DEG + 1);
+    const float inorm = 1.0f / sqrtf(x * x + y * y + z * z);
+    x *= inorm; y *= inorm; z *= inorm;
+    float b[NB], bx[NB], by[NB], bz[NB];
+    sh_basis<DEG, true>(x, y, z, b, bx, by, bz);
+    float vx = 0.f, vy = 0.f, vz = 0.f;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        const float d = co[k * 3] * v0 + co[k * 3 + 1] * v1 + co[k * 3 + 2] * v2;
+        vx += bx[k] * d; vy += by[k] * d; vz += bz[k] * d;
+    }
+    const float dd = vx * x + vy * y + vz * z;
+    gd0 = (vx - dd * x) * inorm;
+    gd1 = (vy - dd * y) * inorm;
+    gd2 = (vz - dd * z) * inorm;
+}
+
+// basis values of the normalised direction (x, y, z un-normalised on input)
+template <int DEG>
+__device__ __forceinline__ void sh_basis_of(float x, float y, float z, float* b) {
+    const float inorm = 1.0f / sqrtf(x * x + y * y + z * z);
+    sh_basis<DEG, false>(x * inorm, y * inorm, z * inorm, b, nullptr, nullptr, nullptr);
+}
+
 }  // namespace

@@ -245,12 +245,13 @@ class PeerGradientExchange:
 class FusedBackwardExchange:
     """The SH / projection backward of all ranks' views fused with the gradient exchange (csrc/exchange_vjp.cu).
 
-    With replicated parameters the gradient of a view w.r.t. means / quats / scales / colours is a function of the
-    12-float row the blend backward left for each visible Gaussian, the Gaussian's parameters (every rank has
-    them) and the view's camera.  So the ranks trade those 48-byte rows (3.3x less NVLink traffic than the 38
-    parameter gradients) and every rank runs the per-Gaussian backward of ALL views itself, summing in rank
-    order: bit-identical gradients everywhere, and sh_bwd + project3d_bwd + densify_stats + the all-reduce of a
-    step collapse into one push and one reduce kernel.  One camera per rank and step.
+    27 of the 38 gradient floats of a Gaussian are SH-coefficient gradients, and that part is rank one:
+    basis(mean - camera position) x v_colour.  Every rank holds the means, so a rank runs the camera-specific
+    backward of its own view (projection VJP, SH direction gradient, densification norm) inside the push kernel and
+    trades one 64-byte record per visible Gaussian (2.5x less NVLink traffic than the 38 gradients); the reduce
+    kernel expands the SH part and sums the pairs of every Gaussian in rank order: bit-identical gradients
+    everywhere, and sh_bwd + project3d_bwd + densify_stats + the all-reduce of a step collapse into one push and
+    one reduce kernel.  One camera per rank and step.
 
         ex = FusedBackwardExchange(N, cap_rows=N // 4)
         with ex.deferred():                       # backward stops after the blend backward
@@ -303,19 +304,20 @@ class FusedBackwardExchange:
         st = torch.cuda.current_stream().cuda_stream
         from .cuda import _wrapper as W
         W._mark("exchange_vjp_push", 0)
-        self._check(L.hgs_exchange_vjp_push(p(vpack), p(cf), p(sk["viewmats"]), p(sk["Ks"]), p(sk["campos"]), N,
+        deg = -1 if sh_degree is None else int(sh_degree)
+        dm, dq, ds, dc = means.detach(), quats.detach(), scales.detach(), colors.detach()
+        self._check(L.hgs_exchange_vjp_push(deg, K, p(vpack), p(cf), p(sk["viewmats"]), p(sk["Ks"]), p(sk["campos"]),
+                                            p(dm), p(dq), p(ds), p(dc), int(sk["width"]), int(sk["height"]),
+                                            float(sk["eps2d"]), float(sk["near_plane"]), float(sk["far_plane"]), N,
                                             p(ids) if n > 0 else None, n, self.cap_rows, self.box.ptrs_c, self.world,
                                             self.rank, self.step, st), "hgs_exchange_vjp_push")
         W._mark("exchange_vjp_push", 1)
         outs = [torch.empty_like(t) for t in (means, quats, scales, opacities, colors)]
         W._mark("exchange_vjp_reduce", 0)
-        self._check(L.hgs_exchange_vjp_reduce(-1 if sh_degree is None else int(sh_degree), K, p(means.detach()),
-                                              p(quats.detach()), p(scales.detach()), p(colors.detach()),
-                                              int(sk["width"]), int(sk["height"]), float(sk["eps2d"]),
-                                              float(sk["near_plane"]), float(sk["far_plane"]), N, self.cap_rows,
-                                              self.box.local, self.world, self.rank, self.step, p(outs[0]), p(outs[1]),
-                                              p(outs[2]), p(outs[3]), p(outs[4]), p(grad_accum), p(denom),
-                                              p(self.box.status), st), "hgs_exchange_vjp_reduce")
+        self._check(L.hgs_exchange_vjp_reduce(deg, K, p(dm), N, self.cap_rows, self.box.local, self.world, self.rank,
+                                              self.step, p(outs[0]), p(outs[1]), p(outs[2]), p(outs[3]), p(outs[4]),
+                                              p(grad_accum), p(denom), p(self.box.status), st),
+                    "hgs_exchange_vjp_reduce")
         W._mark("exchange_vjp_reduce", 1)
         self.step += 1
         for t, g in zip((means, quats, scales, opacities, colors), outs):

@@ -272,31 +272,32 @@ int hgs_exchange_reduce(float* const* tensors_host, const int* widths_host, int 
                         long long cap_rows, const void* mailbox, int world, int rank, unsigned long long step,
                         int* status_dev, void* stream);
 /* ---- e, fused form: SH / projection backward fused with the exchange (csrc/exchange_vjp.cu) -----------------
- * With replicated parameters, a view's gradient w.r.t. means / quats / scales / SH coefficients is a function of
- * the 12-float row the blend backward produced for the Gaussian (one row of `vpack`, see hgs_blend3d_bwd_packed),
- * the Gaussian's parameters and the view's camera.  The ranks therefore exchange the 48-byte vpack rows of their
- * visible Gaussians (one camera per rank) instead of 38 parameter gradients, and every rank runs the SH and
- * projection backward of ALL views' rows -- replacing hgs_sh_bwd + hgs_project3d_bwd + hgs_densify_stats + the
- * gradient all-reduce of a step.
- *   push   : vpack[N,12] rows of ids[n_rows] (ascending) with the SH clamp mask applied (colors_fwd[N,3] = the
- *            forward colours, or NULL), plus this rank's camera (DEVICE pointers viewmat[16], K[9], campos[3]),
- *            into slot (step & 1, rank) of every mailbox; then the rank's flag is raised (release).
- *   reduce : waits for all flags, then for every Gaussian sums over the sources that listed it, in rank order,
- *            the gradients w.r.t. means[N,3], quats[N,4], scales[N,3], opacities[N] and coefficients
- *            (sh_degree 0..4: coeffs[N,K,3]; sh_degree -1: plain colours, K == 1) and OVERWRITES the five output
- *            tensors (zeros for Gaussians nobody saw); grad_accum[N] / denom[N] (or NULL) receive += the
- *            densification statistics of all views.  Bit-identical on every rank. */
+ * The SH-coefficient part of a view's gradient is rank one -- v_coeffs[k][c] = basis_k(mean - camera position) *
+ * v_colour[c] -- and every rank holds the means, so the ranks exchange one 64-byte record per visible Gaussian
+ * {v_means 3, v_opacity, v_quats 4, v_scales 3, densification norm, v_colour 3} instead of 38 gradients, replacing
+ * hgs_sh_bwd + hgs_project3d_bwd + hgs_densify_stats + the gradient all-reduce of a step (one camera per rank).
+ *   push   : one thread per row of ids[n_rows] (ascending) runs the camera-specific backward from the row the
+ *            blend backward left in vpack[N,12] (see hgs_blend3d_bwd_packed): projection VJP, SH direction
+ *            gradient (sh_degree >= 1: coeffs[N,K,3]; 0 or -1: none), SH clamp mask (colors_fwd[N,3] = the
+ *            forward colours, or NULL), densification norm; the records and this rank's camera (DEVICE pointers
+ *            viewmat[16], Kmat[9], campos[3]) go into slot (step & 1, rank) of every mailbox, then the rank's
+ *            flag is raised (release).
+ *   reduce : waits for all flags, then for every Gaussian sums the records of the sources that listed it, in rank
+ *            order, expanding the SH part with that source's direction, and OVERWRITES v_means[N,3], v_quats[N,4],
+ *            v_scales[N,3], v_opacities[N], v_coeffs[N,K,3] (sh_degree -1: plain colours, K == 1) -- zeros for
+ *            Gaussians nobody saw; grad_accum[N] / denom[N] (or NULL) receive += the densification statistics of
+ *            all views.  Bit-identical on every rank. */
 size_t hgs_exchange_vjp_mailbox_bytes(int world, long long n_ids, long long cap_rows);
-int hgs_exchange_vjp_push(const float* vpack, const float* colors_fwd, const float* viewmat, const float* K,
-                          const float* campos, long long n_ids, const int32_t* ids, long long n_rows,
+int hgs_exchange_vjp_push(int sh_degree, int K, const float* vpack, const float* colors_fwd, const float* viewmat,
+                          const float* Kmat, const float* campos, const float* means, const float* quats,
+                          const float* scales, const float* coeffs, int width, int height, float eps2d,
+                          float near_plane, float far_plane, long long n_ids, const int32_t* ids, long long n_rows,
                           long long cap_rows, void* const* mailboxes_host, int world, int rank,
                           unsigned long long step, void* stream);
-int hgs_exchange_vjp_reduce(int sh_degree, int K, const float* means, const float* quats, const float* scales,
-                            const float* coeffs, int width, int height, float eps2d, float near_plane,
-                            float far_plane, long long n_ids, long long cap_rows, const void* mailbox, int world,
-                            int rank, unsigned long long step, float* v_means, float* v_quats, float* v_scales,
-                            float* v_opacities, float* v_coeffs, float* grad_accum, float* denom, int* status_dev,
-                            void* stream);
+int hgs_exchange_vjp_reduce(int sh_degree, int K, const float* means, long long n_ids, long long cap_rows,
+                            const void* mailbox, int world, int rank, unsigned long long step, float* v_means,
+                            float* v_quats, float* v_scales, float* v_opacities, float* v_coeffs, float* grad_accum,
+                            float* denom, int* status_dev, void* stream);
 /* Peer memory management (these allocate / synchronise, unlike the stage functions): a zero-filled device
  * allocation, its 64-byte CUDA IPC handle (host buffer) and the mapping of a peer's handle into this process. */
 int hgs_peer_alloc(size_t bytes, void** out);
