@@ -35,6 +35,7 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 METRIC = "fwd+bwd iters/s, 6M Gaussians @1920x1080"
+LOSS_MODE = "l1"
 N_VIEWS = 8
 WIDTH, HEIGHT = 1920, 1080
 
@@ -59,6 +60,8 @@ def loss_fn(rc, ra, gt):
     same expression is one fused forward and one fused backward kernel (horizongs_b200.losses, csrc/loss.cu)."""
     if rc.is_cuda:
         from horizongs_b200 import losses
+        if LOSS_MODE == "l1ssim":       # the reference's full photometric loss (train.py:158-160), fused
+            return losses.photometric_loss(rc, gt, 0.2, ra, w_depth=0.01, w_alpha=0.01)
         return losses.photometric_l1_loss(rc, gt, ra, w_depth=0.01, w_alpha=0.01)
     return (rc[..., :3] - gt).abs().mean() + 0.01 * rc[..., 3].mean() + 0.01 * ra.mean()
 
@@ -510,7 +513,12 @@ def main():
     ap.add_argument("--exchange", default="fused", choices=["fused", "peer", "nccl"],
                     help="N > 1: per-Gaussian backward fused with the exchange over NVLink peer memory (default), "
                          "sparse all-reduce of the parameter gradients over peer memory, or the dense NCCL all-reduce")
+    ap.add_argument("--loss", default="l1", choices=["l1", "l1ssim"],
+                    help="loss inside the step: fused L1 (+ depth / alpha means; default) or the reference's "
+                         "0.8 L1 + 0.2 (1 - SSIM), fused (csrc/loss.cu)")
     args = ap.parse_args()
+    global LOSS_MODE
+    LOSS_MODE = args.loss
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     if args.impl == "reference":
         run_reference(args)

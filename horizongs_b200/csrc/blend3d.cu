@@ -264,9 +264,31 @@ __global__ void __launch_bounds__(BLK) blend3d_stats_kernel(const GRec* __restri
         n_eval += __shfl_xor_sync(0xFFFFFFFFu, n_eval, o);
         n_blend += __shfl_xor_sync(0xFFFFFFFFu, n_blend, o);
     }
+    // culling statistics (whole tile range, no early termination): (warp, Gaussian) pairs surviving the 8x4 cull,
+    // and the iteration counts two independent half-warps would need with 4x4 / 8x2 half rectangles
+    unsigned long long n_full = 0, n_h44 = 0, n_h82 = 0;
+    for (int base = range_start; base < range_end; base += 32) {
+        const int idx = base + g.lane;
+        bool k0 = false, ka = false, kb = false, kc = false, kd = false;
+        if (idx < range_end) {
+            const float4* q = reinterpret_cast<const float4*>(recs + flatten_ids[idx]);
+            const float4 q0 = q[0], q1 = q[1], q3 = q[3];
+            k0 = cull_keep(q0, q1, q3, g.X0, g.X1, g.Y0, g.Y1);
+            ka = cull_keep(q0, q1, q3, g.X0, g.X0 + 3.f, g.Y0, g.Y1);
+            kb = cull_keep(q0, q1, q3, g.X0 + 4.f, g.X1, g.Y0, g.Y1);
+            kc = cull_keep(q0, q1, q3, g.X0, g.X1, g.Y0, g.Y0 + 1.f);
+            kd = cull_keep(q0, q1, q3, g.X0, g.X1, g.Y0 + 2.f, g.Y1);
+        }
+        n_full += __popc(__ballot_sync(0xFFFFFFFFu, k0));
+        n_h44 += max(__popc(__ballot_sync(0xFFFFFFFFu, ka)), __popc(__ballot_sync(0xFFFFFFFFu, kb)));
+        n_h82 += max(__popc(__ballot_sync(0xFFFFFFFFu, kc)), __popc(__ballot_sync(0xFFFFFFFFu, kd)));
+    }
     if (g.lane == 0) {
         atomicAdd(&counters[0], n_eval);
         atomicAdd(&counters[1], n_blend);
+        atomicAdd(&counters[2], n_full);
+        atomicAdd(&counters[3], n_h44);
+        atomicAdd(&counters[4], n_h82);
     }
 }
 

@@ -727,11 +727,13 @@ def blend3d_pair_stats(means2d, conics, opacities, radii, width, height, tile_si
     check(L.hgs_blend3d_pack(ptr(means2d.contiguous()), ptr(conics.contiguous()), ptr(dummy), None,
                              ptr(opacities.contiguous()), ptr(radii), None, 0, C * N, 1, ptr(records), st),
           "hgs_blend3d_pack")
-    counters = torch.zeros(2, dtype=torch.int64, device=dev)
+    counters = torch.zeros(8, dtype=torch.int64, device=dev)
     check(L.hgs_blend3d_stats(ptr(records), C, int(width), int(height), int(tile_size), ptr(isect_offsets),
                               ptr(flatten_ids), flatten_ids.numel(), ptr(counters), st), "hgs_blend3d_stats")
-    p_eval, p_blend = counters.tolist()
-    return int(p_eval), int(p_blend)
+    vals = counters.tolist()
+    blend3d_pair_stats.last_cull = {"warp_pairs_8x4": int(vals[2]), "half_iters_4x4": int(vals[3]),
+                                    "half_iters_8x2": int(vals[4])}
+    return int(vals[0]), int(vals[1])
 
 
 @torch.no_grad()

@@ -174,7 +174,7 @@ int hgs_blend3d_bwd_packed(const void* records, const float* backgrounds, int C,
 
 /* Measurement aid (not on the product path): counters[0] += P_eval, the (pixel, Gaussian) pairs a per-pixel
  * front-to-back loop visits before the pixel stops; counters[1] += P_blend, the pairs actually blended.
- * counters: two zero-initialised uint64 on the device. */
+ * counters: eight zero-initialised uint64 on the device ([2..4]: culling statistics). */
 int hgs_blend3d_stats(const void* records, int C, int width, int height, int tile_size,
                       const int32_t* isect_offsets, const int32_t* flatten_ids, long long n_isects,
                       unsigned long long* counters, void* stream);
@@ -240,6 +240,18 @@ int hgs_l1_loss_fwd(const float* render_colors, const float* render_alphas, cons
                     float w_depth, float w_alpha, float* partials, float* loss, void* stream);
 int hgs_l1_loss_bwd(const float* render_colors, const float* gt, const float* v_loss, long long P, int D,
                     float w_depth, float w_alpha, float* v_render_colors, float* v_render_alphas, void* stream);
+
+/* ---- f3, second part: fused SSIM (utils/loss_utils.py:20-60, train.py:159) -----------------------------------
+ * mean SSIM between channels 0..2 of render_colors[C,H,W,D] (channels-last, D >= 3) and gt[C,H,W,3], 11x11
+ * Gaussian window (sigma 1.5), zero padding, C1 = 0.01^2, C2 = 0.03^2 -- the reference's ssim(img1, img2).
+ * fwd: dmaps[3][C*H*W*3] receives d ssim / d{mu1, E[x^2], E[xy]} per pixel (kept for bwd), partials[hgs_ssim_partials]
+ * scratch, ssim_mean[1] out (device).  bwd: v_ssim[1] = d loss / d ssim_mean (device); the gradient w.r.t.
+ * render_colors[..., 0:3] is ADDED to v_render_colors[C,H,W,D]. */
+long long hgs_ssim_partials(int C, int H, int W);
+int hgs_ssim_fwd(const float* render_colors, const float* gt, int C, int H, int W, int D, float* dmaps, float* partials,
+                 float* ssim_mean, void* stream);
+int hgs_ssim_bwd(const float* render_colors, const float* gt, const float* dmaps, const float* v_ssim, int C, int H,
+                 int W, int D, float* v_render_colors, void* stream);
 
 /* ---- e: exchange of view-sharded gradients over NVLink peer memory -----------
  * New behaviour (the reference trains one view per iteration in one process; gaussian_renderer/render.py has no

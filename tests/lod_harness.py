@@ -12,16 +12,17 @@ import torch.nn as nn
 
 
 class TinyAnchorModel(nn.Module):
-    def __init__(self, n_anchors=600, n_offsets=10, feat_dim=32, levels=3, extent=3.0, seed=0):
+    def __init__(self, n_anchors=600, n_offsets=10, feat_dim=32, levels=3, extent=3.0, seed=0, voxel0=0.4,
+                 standard_dist=8.0):
         super().__init__()
         g = torch.Generator().manual_seed(seed)
         self.n_offsets, self.levels = n_offsets, levels
-        self.standard_dist, self.fork = 8.0, 2
+        self.standard_dist, self.fork = standard_dist, 2
         anchor = (torch.rand(n_anchors, 3, generator=g) * 2 - 1) * extent
         anchor[:, 2] = anchor[:, 2].abs() * 0.3
         self.anchor = nn.Parameter(anchor)
         self.level = torch.randint(0, levels, (n_anchors,), generator=g)
-        voxel = 0.4 / (2.0 ** self.level.float())
+        voxel = voxel0 / (2.0 ** self.level.float())
         self.offset = nn.Parameter(torch.randn(n_anchors, n_offsets, 3, generator=g) * 0.3)
         self.anchor_feat = nn.Parameter(torch.randn(n_anchors, feat_dim, generator=g) * 0.5)
         self.scaling = nn.Parameter(torch.log(voxel)[:, None].expand(-1, 6).contiguous())   # exp() activation
@@ -94,7 +95,10 @@ def render(model, viewmat, K, width, height, bg, backend, two_d=False):
         (rc, ra, rn, rnd, rd, rm), info = backend.rasterization_2dgs(**kw)
     else:
         rc, ra, info = backend.rasterization(**kw)
-    info["means2d"].retain_grad()
+    try:                                   # render.py:90-93 (no graph under torch.no_grad())
+        info["means2d"].retain_grad()
+    except RuntimeError:
+        pass
     out = {"render": rc[0, ..., :3].permute(2, 0, 1), "render_depth": rc[0, ..., 3:4].permute(2, 0, 1),
            "render_alphas": ra[0].permute(2, 0, 1), "viewspace_points": info["means2d"],
            "radii": info["radii"].squeeze(0), "visible_mask": visible, "n_gaussians": xyz.shape[0]}

@@ -231,3 +231,16 @@ def test_gsplat_shim_import_surface():
             "assert callable(gsplat.rasterization) and callable(gsplat.rasterization_2dgs)") % (
         root, os.path.join(root, "shim"))
     subprocess.run([sys.executable, "-c", code], check=True)
+
+
+def test_reference_loss_fixtures_are_consistent():
+    """tests/golden/reference_losses.npz (generated from the reference's utils/loss_utils.py by
+    tests/golden/make_golden_losses.py): loss = (1 - lambda) * l1 + lambda * (1 - ssim), train.py:158-160; the GPU
+    test test_fused_l1_ssim_loss_matches_reference_golden checks csrc/loss.cu against these values."""
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_losses.npz"))
+    for case in ("a", "b", "c"):
+        lam = float(G[f"{case}_lambda"])
+        assert abs(float(G[f"{case}_loss"]) - ((1 - lam) * float(G[f"{case}_l1"]) + lam * (1 - float(G[f"{case}_ssim"])))) < 1e-12
+        assert G[f"{case}_grad"].shape == G[f"{case}_img"].shape
+        l1 = np.abs(G[f"{case}_img"].astype(np.float64) - G[f"{case}_gt"].astype(np.float64)).mean()
+        assert abs(l1 - float(G[f"{case}_l1"])) < 1e-12

@@ -431,3 +431,33 @@ def test_fused_l1_loss_matches_torch(D):
     assert abs(float(loss.detach()) - float(ref.detach())) < 1e-6 * max(1.0, abs(float(ref.detach())))
     assert torch.allclose(rc.grad, rc2.grad, rtol=1e-6, atol=1e-12)
     assert torch.allclose(ra.grad, ra2.grad, rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_fused_l1_ssim_loss_matches_reference_golden(case):
+    """csrc/loss.cu (fused L1 + SSIM, forward and backward) against values and gradients produced by the REFERENCE's
+    own utils/loss_utils.py (l1_loss, ssim) combined as train.py:158-160 -- fixtures tests/golden/reference_losses.npz,
+    generated by tests/golden/make_golden_losses.py.  This row of the path IS pinned to reference code."""
+    import os
+    import numpy as np
+    from horizongs_b200 import losses
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_losses.npz"))
+    img = torch.from_numpy(G[f"{case}_img"]).permute(1, 2, 0)[None].contiguous().cuda()      # CHW -> [1,H,W,3]
+    gt = torch.from_numpy(G[f"{case}_gt"]).permute(1, 2, 0)[None].contiguous().cuda()
+    lam = float(G[f"{case}_lambda"])
+    for D in (3, 4):
+        rc = img if D == 3 else torch.cat([img, torch.rand_like(img[..., :1])], -1)
+        rc = rc.clone().requires_grad_()
+        loss = losses.photometric_loss(rc, gt, lambda_dssim=lam)
+        loss.backward()
+        assert abs(float(loss.detach()) - float(G[f"{case}_loss"])) < 2e-6, (float(loss.detach()), float(G[f"{case}_loss"]))
+        ref_grad = torch.from_numpy(G[f"{case}_grad"]).permute(1, 2, 0)[None].float()
+        got = rc.grad[..., :3].cpu()
+        assert float((got - ref_grad).abs().max()) < 2e-4 * float(ref_grad.abs().max())
+        if D == 4:
+            assert float(rc.grad[..., 3].abs().max()) == 0.0
+    # the two terms on their own
+    l1 = losses.photometric_loss(img, gt, lambda_dssim=0.0)
+    assert abs(float(l1) - float(G[f"{case}_l1"])) < 1e-6
+    ss = losses.photometric_loss(img, gt, lambda_dssim=1.0)
+    assert abs((1.0 - float(ss)) - float(G[f"{case}_ssim"])) < 2e-6

@@ -115,6 +115,56 @@ def run2d(name, sc, V, Ks, Wd, H, distloss):
     print(json.dumps(res), flush=True)
 
 
+def run_lod(n_anchors=500_000):
+    """config 3: LOD anchor model through the reference adapter's control flow (tests/lod_harness.py): anchor
+    mask + prefilter (fully_fused_projection) + MLP decode (PyTorch, as in the reference) + rasterization."""
+    from tests import lod_harness as LH
+    dev = "cuda"
+    Wd, H = 1920, 1080
+    model = LH.TinyAnchorModel(n_anchors=n_anchors, levels=4, extent=25.0, voxel0=0.12, standard_dist=26.686).to(dev)
+    model.level = model.level.to(dev)
+    V = scenes.aerial_camera(12.0, 45.0, 30.0, (2.0, -3.0)).to(dev)
+    Km = scenes.intrinsics(Wd, H).to(dev)
+    bg = torch.zeros(3, device=dev)
+    res = {"config": "config3-lod-aerial", "anchors": n_anchors, "W": Wd, "H": H}
+    marks = []
+    W.set_stage_hook(lambda name, ph: marks.append((name, ph, _ev())))
+
+    def _ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def fwd():
+        return LH.render(model, V, Km, Wd, H, bg, hgs)
+
+    with torch.no_grad():
+        o, t = timed(fwd)
+    res["render_fwd_ms"] = t
+    res["n_gaussians"] = int(o["n_gaussians"])
+    res["n_visible_anchors"] = int(o["visible_mask"].sum())
+
+    def fwdbwd():
+        o = fwd()
+        (o["render"].mean() + 0.1 * o["render_depth"].mean()).backward()
+        model.zero_grad(set_to_none=True)
+
+    marks.clear()
+    _, t = timed(fwdbwd, iters=5, warm=2)
+    res["render_fwd_bwd_ms"] = t
+    W.set_stage_hook(None)
+    torch.cuda.synchronize()
+    open_, agg = {}, {}
+    for name, ph, ev in marks:
+        if ph == 0:
+            open_[name] = ev
+        elif name in open_:
+            agg.setdefault(name, []).append(open_.pop(name).elapsed_time(ev))
+    res["rasterizer_stage_ms"] = {k: round(sum(v) / len(v), 4) for k, v in agg.items()}
+    res["rasterizer_total_ms"] = round(sum(res["rasterizer_stage_ms"].values()), 4)
+    print(json.dumps(res), flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="1a,1s,4")
@@ -131,6 +181,8 @@ if __name__ == "__main__":
             for view in ("aerial", "street"):
                 for dl in (False, True):
                     run2d(f"config2-2dgs-{view}", *scenes.config1(view=view), dl)
+        elif c == "3":
+            run_lod()
         elif c == "4":
             sc, V, Ks, Wd, H = scenes.config4(n_views=2)
             run("config4-view0-aerial", sc, V[:1], Ks[:1], Wd, H)
