@@ -269,6 +269,17 @@ def run_ours(args):
         exchange_name = ("NCCL all-reduce of 38 floats/Gaussian gradients + 2 floats/Gaussian densification statistics "
                          "per step")
     copy_stream = torch.cuda.Stream(device=dev)
+    loss_ready = torch.cuda.Event()
+    loss_host = torch.zeros(1).pin_memory()
+
+    def read_loss(loss):
+        """device -> host read of the step's loss, every step: the 4-byte copy runs on the copy stream as soon as the
+        forward has produced the loss (the backward is already enqueued behind it), and the host waits for the value"""
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(loss_ready)
+            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        copy_stream.synchronize()
+        return float(loss_host[0])
     # pinned host copies for the end-to-end arm
     gts_pin = gts_cpu.pin_memory()
     views_pin, Ks_pin = views_cpu.pin_memory(), Ks_cpu.pin_memory()
@@ -296,9 +307,11 @@ def run_ours(args):
                 if e2e:
                     torch.cuda.current_stream().wait_stream(copy_stream)
                 loss = loss_fn(rc, ra, gt)
+                if e2e:
+                    loss_ready.record()
                 loss.backward()
             fused.finish(*params, grad_accum=stats[0], denom=stats[1])
-            out = loss.item() if e2e else None
+            out = read_loss(loss) if e2e else None
             for p in params:
                 p.grad = None
             return out
@@ -308,6 +321,8 @@ def run_ours(args):
         if e2e:
             torch.cuda.current_stream().wait_stream(copy_stream)
         loss = loss_fn(rc, ra, gt)
+        if e2e:
+            loss_ready.record()
         loss.backward()
         # densification statistics from the view-space gradient (basic_model.py:131-144), one fused kernel;
         # computed per view BEFORE the exchange, then summed over ranks together with the gradients
@@ -325,7 +340,7 @@ def run_ours(args):
         else:
             Wr.densification_stats_update(meta["means2d"].grad, meta["radii"], W, H, stats[0], stats[1],
                                           visible_ids=meta["visible_ids"])
-        out = loss.item() if e2e else None
+        out = read_loss(loss) if e2e else None
         for p in params:
             p.grad = None
         return out
