@@ -52,10 +52,12 @@ static_assert(sizeof(GRec) == REC_BYTES, "record size");
 __global__ void pack3d_kernel(const float* __restrict__ means2d, const float* __restrict__ conics,
                               const float* __restrict__ colors, const float* __restrict__ depths,
                               const float* __restrict__ opacities, const int32_t* __restrict__ radii,
-                              const int32_t* __restrict__ vis_ids, long long CN, int CH, GRec* __restrict__ recs) {
+                              const int32_t* __restrict__ vis_ids, long long CN,
+                              const long long* __restrict__ n_dev, int CH, GRec* __restrict__ recs) {
     // CN = number of work items: all C*N Gaussians (vis_ids == NULL) or the visible ones listed in vis_ids
+    // (n_dev != NULL: the count lives on the device and CN is only a bound)
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= CN) return;
+    if (t >= (n_dev != nullptr ? *n_dev : CN)) return;
     const long long i = vis_ids != nullptr ? (long long)vis_ids[t] : t;
     if (vis_ids == nullptr && radii != nullptr && radii[i] <= 0) return;
     const float2 m = reinterpret_cast<const float2*>(means2d)[i];
@@ -849,12 +851,13 @@ HGS_API size_t hgs_blend3d_pack_bytes(long long CN) { return (size_t)(CN > 0 ? C
 
 HGS_API int hgs_blend3d_pack(const float* means2d, const float* conics, const float* colors, const float* depths,
                              const float* opacities, const int32_t* radii, const int32_t* vis_ids, long long n_vis,
-                             long long CN, int CH, void* records, void* stream) {
+                             const long long* n_vis_dev, long long CN, int CH, void* records, void* stream) {
     if (CN < 0 || n_vis < 0 || CH < 0 || CH + (depths != nullptr ? 1 : 0) > 4) return HGS_ERR_INVALID_ARG;
     const long long work = vis_ids != nullptr ? n_vis : CN;
     if (work == 0) return 0;
-    pack3d_kernel<<<hgs_ceil_div(work, 256), 256, 0, (cudaStream_t)stream>>>(means2d, conics, colors, depths, opacities,
-                                                                              radii, vis_ids, work, CH, (GRec*)records);
+    pack3d_kernel<<<hgs_ceil_div(work, 256), 256, 0, (cudaStream_t)stream>>>(
+        means2d, conics, colors, depths, opacities, radii, vis_ids, work, vis_ids != nullptr ? n_vis_dev : nullptr, CH,
+        (GRec*)records);
     HGS_LAUNCH_CHECK();
     return 0;
 }

@@ -61,10 +61,11 @@ template <int DEG>
 __global__ void __launch_bounds__(SB) sh_fwd_vis_kernel(const float* __restrict__ dirs, const float* __restrict__ means,
                                                         const float* __restrict__ campos,
                                                         const float* __restrict__ coeffs,
-                                                        const int32_t* __restrict__ vis_ids, long long n_vis, int N,
+                                                        const int32_t* __restrict__ vis_ids, long long n_vis,
+                                                        const long long* __restrict__ n_vis_dev, int N,
                                                         int K, int post, float* __restrict__ colors) {
     const long long j = (long long)blockIdx.x * SB + threadIdx.x;
-    if (j >= n_vis) return;
+    if (j >= (n_vis_dev != nullptr ? *n_vis_dev : n_vis)) return;   // device-side count: n_vis is only a bound
     const long long idx = vis_ids[j];
     const int c = (int)(idx / N);
     const long long n = idx - (long long)c * N;
@@ -332,8 +333,8 @@ __global__ void __launch_bounds__(SHW * 32) sh_bwd_rounds_kernel(const float* __
 }  // namespace
 
 HGS_API int hgs_sh_fwd(int degree, int K, const float* dirs, const float* means, const float* campos,
-                       const float* coeffs, const int32_t* radii, const int32_t* vis_ids, long long n_vis, int C, int N,
-                       int post, float* colors, void* stream) {
+                       const float* coeffs, const int32_t* radii, const int32_t* vis_ids, long long n_vis,
+                       const long long* n_vis_dev, int C, int N, int post, float* colors, void* stream) {
     if (degree < 0 || degree > 4 || K < (degree + 1) * (degree + 1) || C <= 0 || N < 0 || n_vis < 0) return HGS_ERR_INVALID_ARG;
     if (dirs == nullptr && (means == nullptr || campos == nullptr)) return HGS_ERR_INVALID_ARG;
     if (N == 0) return 0;
@@ -343,7 +344,7 @@ HGS_API int hgs_sh_fwd(int degree, int K, const float* dirs, const float* means,
         if (e != cudaSuccess) return (int)e;
         if (n_vis == 0) return 0;
         const int grid = hgs_ceil_div(n_vis, SB);
-#define LAUNCH(DEG) sh_fwd_vis_kernel<DEG><<<grid, SB, 0, st>>>(dirs, means, campos, coeffs, vis_ids, n_vis, N, K, post, colors);
+#define LAUNCH(DEG) sh_fwd_vis_kernel<DEG><<<grid, SB, 0, st>>>(dirs, means, campos, coeffs, vis_ids, n_vis, n_vis_dev, N, K, post, colors);
         switch (degree) {
             case 0: LAUNCH(0) break;
             case 1: LAUNCH(1) break;

@@ -205,16 +205,18 @@ class _SphericalHarmonics(torch.autograd.Function):
     """colors[C,N,3] from coeffs[N,K,3]; direction either dirs[C,N,3] or means[N,3]-campos[C,3]."""
 
     @staticmethod
-    def forward(ctx, degree, dirs, means, campos, coeffs, radii, post, vis_ids=None, defer=None):
+    def forward(ctx, degree, dirs, means, campos, coeffs, radii, post, vis_ids=None, defer=None, n_vis_dev=None,
+                holder=None):
         ctx.defer = defer
+        ctx.holder = holder     # rendering.py drops the exact work list here once the host knows its length
         L = _lib.lib()
         N, K = coeffs.shape[0], coeffs.shape[1]
         C = dirs.shape[0] if dirs is not None else campos.shape[0]
         colors = torch.empty((C, N, 3), dtype=torch.float32, device=coeffs.device)
         _mark("sh_fwd", 0)
         check(L.hgs_sh_fwd(degree, K, ptr(dirs), ptr(means), ptr(campos), ptr(coeffs), ptr(radii), ptr(vis_ids),
-                           0 if vis_ids is None else vis_ids.numel(), C, N, int(post), ptr(colors), _stream()),
-              "hgs_sh_fwd")
+                           0 if vis_ids is None else vis_ids.numel(), ptr(n_vis_dev), C, N, int(post), ptr(colors),
+                           _stream()), "hgs_sh_fwd")
         _mark("sh_fwd", 1)
         ctx.vis_ids = vis_ids
         ctx.save_for_backward(dirs, means, campos, coeffs, radii, colors if post else None)
@@ -227,7 +229,7 @@ class _SphericalHarmonics(torch.autograd.Function):
         degree, K, C, N, post = ctx.cfg
         if ctx.defer is not None:
             ctx.defer["colors_fwd"] = colors      # the clamp mask of `post`; the gradient itself comes from vpack
-            return (None,) * 9
+            return (None,) * 11
         L = _lib.lib()
         v_colors, ld_vc = _rows(v_colors, 3)
         v_coeffs = torch.empty_like(coeffs)
@@ -235,14 +237,14 @@ class _SphericalHarmonics(torch.autograd.Function):
         need_means = means is not None and ctx.needs_input_grad[2]
         v_dirs = torch.empty_like(dirs) if need_dirs else None
         v_means = torch.empty_like(means) if need_means else None
-        vis = ctx.vis_ids
+        vis = ctx.vis_ids if ctx.holder is None else ctx.holder.get("vis_ids", ctx.vis_ids)
         _mark("sh_bwd", 0)
         check(L.hgs_sh_bwd(degree, K, ptr(dirs), ptr(means), ptr(campos), ptr(coeffs), ptr(radii), ptr(vis),
                            0 if vis is None else vis.numel(), ptr(colors), ptr(v_colors), ld_vc, C, N, post,
                            ptr(v_coeffs), ptr(v_dirs), ptr(v_means), _stream()),
               "hgs_sh_bwd")
         _mark("sh_bwd", 1)
-        return None, v_dirs, v_means, None, v_coeffs, None, None, None, None
+        return None, v_dirs, v_means, None, v_coeffs, None, None, None, None, None, None
 
 
 def spherical_harmonics(degrees_to_use: int, dirs: Tensor, coeffs: Tensor, masks: Optional[Tensor] = None) -> Tensor:
@@ -266,20 +268,26 @@ def spherical_harmonics(degrees_to_use: int, dirs: Tensor, coeffs: Tensor, masks
 
 
 def _sh_view_colors(sh_degree: int, means: Tensor, campos: Tensor, coeffs: Tensor, radii: Tensor,
-                    vis_ids: Optional[Tensor] = None, defer: Optional[dict] = None) -> Tensor:
+                    vis_ids: Optional[Tensor] = None, defer: Optional[dict] = None, n_vis_dev: Optional[Tensor] = None,
+                    holder: Optional[dict] = None) -> Tensor:
     """fused path used by rasterization*: clamp_min(SH(means - campos) + 0.5, 0), masked by radii > 0
     (vis_ids = the work list of visible flat indices, equivalent to the mask but without idle threads)."""
     return _SphericalHarmonics.apply(int(sh_degree), None, _f32c(means, "means"), _f32c(campos, "campos"),
-                                     _f32c(coeffs, "colors"), radii, True, vis_ids, defer)
+                                     _f32c(coeffs, "colors"), radii, True, vis_ids, defer, n_vis_dev, holder)
 
 
 # =====================================================================================
 # a8-a10: tile intersection / sort / offsets
 # =====================================================================================
-def _isect_sorted_from_counts(means2d, radii, depths, tiles_per_gauss, C, N, tile_size, tile_width, tile_height):
-    """depth-order, scan, (one D2H read of I), emit + tile partition.  All int work in libhgs_raster."""
+_PINNED_COUNTS = {}
+
+
+def _isect_prepare_async(depths, tiles_per_gauss, C, N):
+    """phase 1 of the sorted path: compact + depth-order + scan on the device, and an ASYNCHRONOUS copy of
+    (n_visible, n_isects) into pinned host memory.  Work that only needs the device-side count (SH colours, record
+    packing) can be enqueued before _isect_finish() makes the host wait for the two numbers."""
     L = _lib.lib()
-    dev = means2d.device
+    dev = depths.device
     CN = C * N
     st = _stream()
     order = torch.empty(CN, dtype=torch.int32, device=dev)
@@ -292,7 +300,24 @@ def _isect_sorted_from_counts(means2d, radii, depths, tiles_per_gauss, C, N, til
     check(L.hgs_isect_prepare(ptr(depths), ptr(tiles_per_gauss), C, N, ptr(order), ptr(cum_sorted), ptr(vis_ids),
                               ptr(counts), ptr(temp), tb, st), "hgs_isect_prepare")
     _mark("isect_prepare", 1)
-    n_visible, n_isects = counts.tolist()  # the one unavoidable host read: sizes the intersection arrays
+    host = _PINNED_COUNTS.get(dev)
+    if host is None:
+        host = _PINNED_COUNTS[dev] = torch.empty(2, dtype=torch.int64).pin_memory()
+    host.copy_(counts, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    return {"order": order, "cum_sorted": cum_sorted, "vis_full": vis_ids, "counts": counts, "host": host, "event": ev,
+            "temp": temp}
+
+
+def _isect_finish(prep, means2d, radii, depths, C, N, tile_size, tile_width, tile_height):
+    """phase 2: the one host read (sizes the intersection arrays), then emit + tile partition."""
+    L = _lib.lib()
+    dev = means2d.device
+    CN = C * N
+    st = _stream()
+    prep["event"].synchronize()
+    n_visible, n_isects = prep["host"].tolist()
     _mark("isect_sorted", 0)
     if n_isects >= 2 ** 31:
         raise _lib.HgsError(f"{n_isects} tile intersections exceed the 32-bit index range")
@@ -301,11 +326,17 @@ def _isect_sorted_from_counts(means2d, radii, depths, tiles_per_gauss, C, N, til
     offsets = torch.empty((C, tile_height, tile_width), dtype=torch.int32, device=dev)
     tb2 = L.hgs_isect_sorted_temp_bytes(CN, n_isects)
     temp2 = torch.empty(tb2, dtype=torch.uint8, device=dev)
-    check(L.hgs_isect_sorted(ptr(means2d), ptr(radii), ptr(depths), ptr(order), ptr(cum_sorted), C, N, n_visible,
-                             n_isects, tile_size, tile_width, tile_height, ptr(isect_ids), ptr(flatten_ids), ptr(offsets),
-                             ptr(temp2), tb2, st), "hgs_isect_sorted")
+    check(L.hgs_isect_sorted(ptr(means2d), ptr(radii), ptr(depths), ptr(prep["order"]), ptr(prep["cum_sorted"]), C, N,
+                             n_visible, n_isects, tile_size, tile_width, tile_height, ptr(isect_ids), ptr(flatten_ids),
+                             ptr(offsets), ptr(temp2), tb2, st), "hgs_isect_sorted")
     _mark("isect_sorted", 1)
-    return isect_ids, flatten_ids, offsets, vis_ids[:n_visible]
+    return isect_ids, flatten_ids, offsets, prep["vis_full"][:n_visible]
+
+
+def _isect_sorted_from_counts(means2d, radii, depths, tiles_per_gauss, C, N, tile_size, tile_width, tile_height):
+    """depth-order, scan, (one D2H read of I), emit + tile partition.  All int work in libhgs_raster."""
+    prep = _isect_prepare_async(depths, tiles_per_gauss, C, N)
+    return _isect_finish(prep, means2d, radii, depths, C, N, tile_size, tile_width, tile_height)
 
 
 @torch.no_grad()
@@ -366,7 +397,7 @@ class _Blend3D(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means2d, conics, colors, depths, opacities, backgrounds, width, height, tile_size,
-                isect_offsets, flatten_ids, absgrad, radii, normalize_depth, vis_ids=None, defer=None):
+                isect_offsets, flatten_ids, absgrad, radii, normalize_depth, vis_ids=None, defer=None, records=None):
         L = _lib.lib()
         ctx.defer = defer
         C, N = opacities.shape
@@ -381,12 +412,8 @@ class _Blend3D(torch.autograd.Function):
         ctx.cfg = (width, height, tile_size, absgrad, bool(normalize_depth), CH, D)
         st = _stream()
         if fast:
-            records = torch.empty(L.hgs_blend3d_pack_bytes(C * N), dtype=torch.uint8, device=dev)
-            _mark("blend3d_pack", 0)
-            check(L.hgs_blend3d_pack(ptr(means2d), ptr(conics), ptr(colors), ptr(depths), ptr(opacities), ptr(radii),
-                                     ptr(vis_ids), 0 if vis_ids is None else vis_ids.numel(), C * N, CH, ptr(records),
-                                     st), "hgs_blend3d_pack")
-            _mark("blend3d_pack", 1)
+            if records is None:
+                records = _pack3d(means2d, conics, colors, depths, opacities, radii, vis_ids, None)
             _mark("blend3d_fwd", 0)
             check(L.hgs_blend3d_fwd_packed(ptr(records), ptr(backgrounds), C, D, int(normalize_depth), width, height,
                                            tile_size, ptr(isect_offsets), ptr(flatten_ids), flatten_ids.numel(),
@@ -413,7 +440,7 @@ class _Blend3D(torch.autograd.Function):
         L = _lib.lib()
         v_render_colors = v_render_colors.contiguous()
         v_render_alphas = v_render_alphas.contiguous()
-        tail = (None,) * 10
+        tail = (None,) * 11
         if ctx.fast:
             records, backgrounds, isect_offsets, flatten_ids, render_colors, render_alphas, last_ids = ctx.saved_tensors
             (C, N, _), has_depth = ctx.shapes
@@ -459,8 +486,24 @@ class _Blend3D(torch.autograd.Function):
         return (v_means2d, v_conics, v_colors, v_depths, v_opacities, v_bg) + tail
 
 
+@torch.no_grad()
+def _pack3d(means2d, conics, colors, depths, opacities, radii, vis_ids, n_vis_dev):
+    """64-byte blend records of the visible Gaussians (hgs_blend3d_pack).  With n_vis_dev (device-side length of the
+    work list) the call can be enqueued before the host knows how many Gaussians are visible."""
+    L = _lib.lib()
+    C, N = opacities.shape
+    CH = colors.shape[-1]
+    records = torch.empty(L.hgs_blend3d_pack_bytes(C * N), dtype=torch.uint8, device=means2d.device)
+    _mark("blend3d_pack", 0)
+    check(L.hgs_blend3d_pack(ptr(means2d), ptr(conics), ptr(colors), ptr(depths), ptr(opacities), ptr(radii),
+                             ptr(vis_ids), 0 if vis_ids is None else vis_ids.numel(), ptr(n_vis_dev), C * N, CH,
+                             ptr(records), _stream()), "hgs_blend3d_pack")
+    _mark("blend3d_pack", 1)
+    return records
+
+
 def _blend3d(means2d, conics, colors, depths, opacities, backgrounds, width, height, tile_size, isect_offsets,
-             flatten_ids, absgrad=False, radii=None, normalize_depth=False, vis_ids=None, defer=None):
+             flatten_ids, absgrad=False, radii=None, normalize_depth=False, vis_ids=None, defer=None, records=None):
     if tile_size not in _TILE_SIZES:
         raise NotImplementedError(f"tile_size {tile_size} is not supported (supported: {_TILE_SIZES})")
     D = colors.shape[-1] + (1 if depths is not None else 0)
@@ -469,7 +512,7 @@ def _blend3d(means2d, conics, colors, depths, opacities, backgrounds, width, hei
     return _Blend3D.apply(_f32c(means2d, "means2d"), _f32c(conics, "conics"), _f32c(colors, "colors"),
                           _f32c(depths, "depths"), _f32c(opacities, "opacities"), _f32c(backgrounds, "backgrounds"),
                           int(width), int(height), int(tile_size), isect_offsets.contiguous(),
-                          flatten_ids.contiguous(), bool(absgrad), radii, bool(normalize_depth), vis_ids, defer)
+                          flatten_ids.contiguous(), bool(absgrad), radii, bool(normalize_depth), vis_ids, defer, records)
 
 
 def rasterize_to_pixels(means2d: Tensor, conics: Tensor, colors: Tensor, opacities: Tensor, image_width: int,
@@ -725,7 +768,7 @@ def blend3d_pair_stats(means2d, conics, opacities, radii, width, height, tile_si
     dummy = torch.zeros((C, N, 1), dtype=torch.float32, device=dev)
     st = _stream()
     check(L.hgs_blend3d_pack(ptr(means2d.contiguous()), ptr(conics.contiguous()), ptr(dummy), None,
-                             ptr(opacities.contiguous()), ptr(radii), None, 0, C * N, 1, ptr(records), st),
+                             ptr(opacities.contiguous()), ptr(radii), None, 0, None, C * N, 1, ptr(records), st),
           "hgs_blend3d_pack")
     counters = torch.zeros(8, dtype=torch.int64, device=dev)
     check(L.hgs_blend3d_stats(ptr(records), C, int(width), int(height), int(tile_size), ptr(isect_offsets),

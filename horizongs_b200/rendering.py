@@ -49,13 +49,15 @@ def _validate(means, quats, scales, opacities, colors, viewmats, Ks, render_mode
     return C, N
 
 
-def _per_view_features(means, colors, viewmats, radii, sh_degree, C, vis_ids=None, defer=None):
+def _per_view_features(means, colors, viewmats, radii, sh_degree, C, vis_ids=None, defer=None, n_vis_dev=None,
+                       holder=None):
     """-> [C,N,CH] colour features for blending (CH = 3 for SH)."""
     if sh_degree is None:
         if colors.dim() == 2:
             return colors[None] if C == 1 else colors[None].expand(C, -1, -1)
         return colors
-    return W._sh_view_colors(sh_degree, means, _camera_positions(viewmats), colors, radii, vis_ids, defer)
+    return W._sh_view_colors(sh_degree, means, _camera_positions(viewmats), colors, radii, vis_ids, defer, n_vis_dev,
+                             holder)
 
 
 def _mode_features(feats, depths, backgrounds, render_mode):
@@ -101,10 +103,12 @@ def rasterization(
     if comps is not None:
         opac = opac * comps
 
+    # phase 1 of the ordering: everything up to the one host read of (n_visible, n_isects) -- the copy is
+    # asynchronous, and the stages that only need the device-side count (SH colours, record packing) are enqueued
+    # BEFORE the host waits for it, so the GPU is busy while the host reads the two numbers
     with torch.no_grad():
-        isect_ids, flatten_ids, isect_offsets, vis_ids = W._isect_sorted_from_counts(
-            means2d, radii, depths, tiles_per_gauss, C, N, tile_size, tile_width, tile_height)
-    holder["vis_ids"] = vis_ids          # work list for the backward of the projection
+        prep = W._isect_prepare_async(depths, tiles_per_gauss, C, N)
+    vis_full, n_vis_dev = prep["vis_full"], prep["counts"]
 
     # multi-GPU: the SH / projection backward is deferred and runs fused with the gradient exchange
     defer = W.current_deferred_sink() if torch.is_grad_enabled() else None
@@ -116,17 +120,30 @@ def rasterization(
             raise NotImplementedError("deferred backward needs [N,3] colours or SH coefficients")
         holder["defer"] = defer
         defer.clear()
-        defer.update(vis_ids=vis_ids, viewmats=viewmats.detach().contiguous(), Ks=Ks.detach().contiguous(),
+        defer.update(viewmats=viewmats.detach().contiguous(), Ks=Ks.detach().contiguous(),
                      campos=_camera_positions(viewmats.detach()).contiguous(), width=width, height=height, eps2d=eps2d,
                      near_plane=near_plane, far_plane=far_plane, sh_degree=sh_degree, n=N)
 
-    feats = _per_view_features(means, colors, viewmats, radii, sh_degree, C, vis_ids, defer)
+    feats = _per_view_features(means, colors, viewmats, radii, sh_degree, C, vis_full, defer, n_vis_dev, holder)
     feats, depth_ch, bgs = _mode_features(feats, depths, backgrounds, render_mode)
     n_ch = feats.shape[-1] + (1 if depth_ch is not None else 0)
     fuse_norm = render_mode in ("ED", "RGB+ED") and n_ch <= 4 and not absgrad
+    records = None
+    if n_ch <= 4 and not absgrad:
+        records = W._pack3d(W._f32c(means2d, "means2d"), W._f32c(conics, "conics"), W._f32c(feats, "colors"),
+                            W._f32c(depth_ch, "depths"), W._f32c(opac, "opacities"), radii, vis_full, n_vis_dev)
+
+    # phase 2: the host read, then emit + tile partition
+    with torch.no_grad():
+        isect_ids, flatten_ids, isect_offsets, vis_ids = W._isect_finish(
+            prep, means2d, radii, depths, C, N, tile_size, tile_width, tile_height)
+    holder["vis_ids"] = vis_ids          # work list for the backward of the projection and of the SH stage
+    if defer is not None:
+        defer["vis_ids"] = vis_ids
+
     render_colors, render_alphas = W._blend3d(means2d, conics, feats, depth_ch, opac, bgs, width, height, tile_size,
                                               isect_offsets, flatten_ids, absgrad, radii=radii,
-                                              normalize_depth=fuse_norm, vis_ids=vis_ids, defer=defer)
+                                              normalize_depth=fuse_norm, vis_ids=vis_ids, defer=defer, records=records)
     if render_mode in ("ED", "RGB+ED") and not fuse_norm:
         render_colors = torch.cat(
             [render_colors[..., :-1], render_colors[..., -1:] / render_alphas.clamp(min=1e-10)], dim=-1)

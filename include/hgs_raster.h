@@ -80,10 +80,12 @@ int hgs_project2d_bwd(const float* means, const float* quats, const float* scale
  * Direction of Gaussian n for camera c is dirs[c,n,:] if dirs != NULL, else means[n,:] - campos[c,:]
  * (normalised inside).  coeffs[N,K,3] is shared by all cameras.  radii (or NULL) masks culled rows to 0.
  * post != 0 fuses gsplat's `clamp_min(colors + 0.5, 0)`.  out: colors[C,N,3].
- * vis_ids (or NULL) = work list of visible flat indices (then radii is not read). */
+ * vis_ids (or NULL) = work list of visible flat indices (then radii is not read).  n_vis_dev (or NULL): the length
+ * of the work list as a DEVICE value (counts_dev[0] of hgs_isect_prepare); n_vis is then only an upper bound, so the
+ * call can be enqueued before the host has read the count. */
 int hgs_sh_fwd(int degree, int K, const float* dirs, const float* means, const float* campos, const float* coeffs,
-               const int32_t* radii, const int32_t* vis_ids, long long n_vis, int C, int N, int post, float* colors,
-               void* stream);
+               const int32_t* radii, const int32_t* vis_ids, long long n_vis, const long long* n_vis_dev, int C, int N,
+               int post, float* colors, void* stream);
 /* out (overwritten): v_coeffs[N,K,3] summed over cameras; v_dirs[C,N,3] or NULL; v_means[N,3] or NULL
  * (direction gradient summed over cameras).  `colors` is the forward output (needed for the clamp mask
  * when post != 0).  ld_v_colors = row stride of v_colors in floats (3 when dense). */
@@ -154,6 +156,7 @@ int hgs_blend3d_bwd(const float* means2d, const float* conics, const float* colo
  * hgs_blend3d_pack writes one 64-byte record per Gaussian with radii > 0 (radii may be NULL = all):
  * centre, conic scaled by -log2(e)/2, opacity, cut-off exponent, colour (+ depth as the last channel when
  * depths != NULL).  records: hgs_blend3d_pack_bytes(C*N) bytes, 64-byte aligned.
+ * n_vis_dev (or NULL): device-side length of vis_ids (n_vis is then an upper bound), as in hgs_sh_fwd.
  * The blend kernels gather records with TMA bulk copies.  D = channels incl. the depth channel;
  * normalize_depth != 0 fuses expected-depth normalisation (last channel / max(alpha, 1e-10)).
  * vpack[C*N,12] (zero-filled by the caller) accumulates per-Gaussian gradients:
@@ -161,7 +164,7 @@ int hgs_blend3d_bwd(const float* means2d, const float* conics, const float* colo
 size_t hgs_blend3d_pack_bytes(long long CN);
 int hgs_blend3d_pack(const float* means2d, const float* conics, const float* colors, const float* depths,
                      const float* opacities, const int32_t* radii, const int32_t* vis_ids, long long n_vis,
-                     long long CN, int CH, void* records, void* stream);
+                     const long long* n_vis_dev, long long CN, int CH, void* records, void* stream);
 int hgs_blend3d_fwd_packed(const void* records, const float* backgrounds, int C, int D, int normalize_depth,
                            int width, int height, int tile_size, const int32_t* isect_offsets,
                            const int32_t* flatten_ids, long long n_isects, float* render_colors,
