@@ -158,3 +158,20 @@ def test_fused_backward_exchange_equals_allreduced_autograd(tmp_path, sh_degree)
         got = torch.load(os.path.join(str(tmp_path), f"f{r}.pt"))
         assert got["ok"], f"rank {r}: replicas are not bit-identical (or visibility counts differ)"
         assert got["worst"] < 1e-4, f"rank {r}: differs from the all-reduced autograd gradients by {got['worst']}"
+
+
+@pytest.mark.timeout(600)
+def test_exchanges_on_one_gpu_equal_local_autograd(tmp_path):
+    """world of ONE rank (runs on the single-GPU test box): the peer-memory exchanges degenerate to "push to my own
+    mailbox, reduce from it", so the push / wait / merge / reduce kernels all run and their result must equal the
+    plain autograd gradients (FusedBackwardExchange) resp. leave the tensors unchanged (PeerGradientExchange)."""
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 1:
+        pytest.skip("needs a GPU")
+    port = _free_port()
+    mp.spawn(_fused_worker, args=(1, port, str(tmp_path), 2, 3), nprocs=1, join=True)
+    got = torch.load(os.path.join(str(tmp_path), "f0.pt"))
+    assert got["ok"] and got["worst"] < 1e-4, got
+    mp.spawn(_worker, args=(1, _free_port(), str(tmp_path), 20011, 4), nprocs=1, join=True)
+    got = torch.load(os.path.join(str(tmp_path), "r0.pt"))
+    assert got["ok"] and got["worst"] < 1e-6, got
