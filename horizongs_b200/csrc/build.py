@@ -35,6 +35,7 @@ SOURCES = {
     "blend2d_fast.cu": [],
     "densify.cu": [],
     "loss.cu": [],
+    "decode.cu": [],
     "exchange.cu": [],
     "exchange_vjp.cu": [],
 }

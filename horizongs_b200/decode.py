@@ -1,0 +1,108 @@
+"""Fused anchor -> neural-Gaussian decode of the LOD model (csrc/decode.cu).
+
+``generate_neural_gaussians`` mirrors scene/basic_model.py:297-371 for the configuration Horizon-GS ships
+(view_dim 3, appearance_dim 0, colour_dim 3, feat_dim 32, n_offsets <= 16): three MLPs on cat(anchor_feat, unit view
+direction), the opacity > 0 mask, the compaction and the post-processing are three kernels (count / forward /
+backward) with the MLP weights in shared memory, and the kept Gaussians are written straight into the tensors
+``rasterization()`` consumes.  Differentiable w.r.t. anchor, anchor_feat, offset, the (post-activation) grid scaling
+and all MLP parameters.  CUDA only (no fallback)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Tuple
+
+import torch
+from torch import Tensor, nn
+
+from . import _lib
+from ._lib import check, ptr
+
+
+def _mlp_tensors(mlp: nn.Sequential):
+    lin = [m for m in mlp.modules() if isinstance(m, nn.Linear)]
+    if len(lin) != 2:
+        raise NotImplementedError("expected Linear -> ReLU -> Linear [-> activation] (scene/lod_model.py:67-84)")
+    return [lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias]
+
+
+class _AnchorDecode(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, feat, offset, scaling, cam_center, vis, color_sigmoid, *mlp):
+        L = _lib.lib()
+        dev = anchor.device
+        V, k, F = int(vis.numel()), int(offset.shape[1]), int(feat.shape[1])
+        st = torch.cuda.current_stream().cuda_stream
+        mlp = [t.contiguous() for t in mlp]
+        mp = (C.c_void_p * 12)(*[t.data_ptr() for t in mlp])
+        opac_all = torch.empty((V, k), dtype=torch.float32, device=dev)
+        bits = torch.empty(V, dtype=torch.int32, device=dev)
+        cnt = torch.empty(V, dtype=torch.int32, device=dev)
+        check(L.hgs_decode_count(mp, ptr(anchor), ptr(feat), ptr(cam_center), ptr(vis), V, F, k, ptr(opac_all), ptr(bits),
+                                 ptr(cnt), st), "hgs_decode_count")
+        incl = torch.cumsum(cnt, 0, dtype=torch.int64)
+        row0 = (incl - cnt).contiguous()
+        M = int(incl[-1].item()) if V > 0 else 0            # the one host read (the reference's boolean gather has one too)
+        xyz = torch.empty((M, 3), dtype=torch.float32, device=dev)
+        color = torch.empty((M, 3), dtype=torch.float32, device=dev)
+        opacity = torch.empty((M,), dtype=torch.float32, device=dev)
+        scales = torch.empty((M, 3), dtype=torch.float32, device=dev)
+        quats = torch.empty((M, 4), dtype=torch.float32, device=dev)
+        check(L.hgs_decode_fwd(mp, ptr(anchor), ptr(feat), ptr(offset), ptr(scaling), ptr(cam_center), ptr(vis), V, F, k,
+                               int(color_sigmoid), ptr(opac_all), ptr(bits), ptr(row0), ptr(xyz), ptr(color), ptr(opacity),
+                               ptr(scales), ptr(quats), st), "hgs_decode_fwd")
+        mask = ((bits[:, None] >> torch.arange(k, device=dev, dtype=torch.int32)[None]) & 1).bool().reshape(-1)
+        ctx.save_for_backward(anchor, feat, offset, scaling, cam_center, vis, opac_all, bits, row0, *mlp)
+        ctx.cfg = (V, k, F, int(color_sigmoid))
+        ctx.mark_non_differentiable(mask)
+        return xyz, color, opacity, scales, quats, mask
+
+    @staticmethod
+    def backward(ctx, v_xyz, v_color, v_opacity, v_scales, v_quats, _v_mask):
+        anchor, feat, offset, scaling, cam_center, vis, opac_all, bits, row0, *mlp = ctx.saved_tensors
+        V, k, F, color_sigmoid = ctx.cfg
+        L = _lib.lib()
+        dev = anchor.device
+        rows = next((t.shape[0] for t in (v_xyz, v_color, v_opacity, v_scales, v_quats) if t is not None), 0)
+
+        def dense(t, shape):
+            return torch.zeros(shape, dtype=torch.float32, device=dev) if t is None else t.contiguous()
+        v_xyz, v_color = dense(v_xyz, (rows, 3)), dense(v_color, (rows, 3))
+        v_opacity, v_scales, v_quats = dense(v_opacity, (rows,)), dense(v_scales, (rows, 3)), dense(v_quats, (rows, 4))
+        g_anchor, g_feat = torch.zeros_like(anchor), torch.zeros_like(feat)
+        g_offset, g_scaling = torch.zeros_like(offset), torch.zeros_like(scaling)
+        g_mlp = [torch.zeros_like(t) for t in mlp]
+        mp = (C.c_void_p * 12)(*[t.data_ptr() for t in mlp])
+        gp = (C.c_void_p * 12)(*[t.data_ptr() for t in g_mlp])
+        check(L.hgs_decode_bwd(mp, gp, ptr(anchor), ptr(feat), ptr(offset), ptr(scaling), ptr(cam_center), ptr(vis), V, F, k,
+                               color_sigmoid, ptr(opac_all), ptr(bits), ptr(row0), ptr(v_xyz), ptr(v_color), ptr(v_opacity),
+                               ptr(v_scales), ptr(v_quats), ptr(g_anchor), ptr(g_feat), ptr(g_offset), ptr(g_scaling),
+                               torch.cuda.current_stream().cuda_stream), "hgs_decode_bwd")
+        return (g_anchor, g_feat, g_offset, g_scaling, None, None, None, *g_mlp)
+
+
+def generate_neural_gaussians(anchor: Tensor, anchor_feat: Tensor, offset: Tensor, scaling: Tensor, cam_center: Tensor,
+                              visible_mask: Tensor, mlp_opacity: nn.Sequential, mlp_cov: nn.Sequential,
+                              mlp_color: nn.Sequential) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """-> (xyz [M,3], color [M,3], opacity [M,1], scaling [M,3], rot [M,4], mask [V*k] bool), the tensors
+    scene/basic_model.py:297-371 returns (without the pass-through `offsets` / `active_sh_degree`).
+
+    anchor [A,3], anchor_feat [A,32], offset [A,k,3], scaling [A,6] POST-activation (get_scaling = exp(_scaling),
+    lod_model.py:182-183), cam_center [3], visible_mask [A] bool; the MLPs are the nn.Sequential modules of
+    scene/lod_model.py:67-84 (a trailing nn.Sigmoid on the colour MLP is honoured)."""
+    if not anchor.is_cuda:
+        raise ValueError("generate_neural_gaussians runs on CUDA tensors only (no CPU fallback)")
+    A, k = anchor.shape[0], offset.shape[1]
+    assert anchor_feat.shape == (A, 32), "feat_dim 32 (one lane per hidden unit)"
+    assert offset.shape == (A, k, 3) and 1 <= k <= 16 and scaling.shape == (A, 6) and visible_mask.shape == (A,)
+    last = lambda seq: [m for m in seq.modules() if not isinstance(m, nn.Sequential)][-1]  # noqa: E731
+    if not isinstance(last(mlp_opacity), nn.Tanh):
+        raise NotImplementedError("the opacity MLP must end in Tanh (scene/lod_model.py:67-72)")
+    mlp = _mlp_tensors(mlp_opacity) + _mlp_tensors(mlp_cov) + _mlp_tensors(mlp_color)
+    if mlp[0].shape != (32, 35) or mlp[2].shape != (k, 32) or mlp[6].shape != (7 * k, 32) or mlp[10].shape != (3 * k, 32):
+        raise NotImplementedError("supported: view_dim 3, appearance_dim 0, colour_dim 3, feat_dim 32")
+    color_sigmoid = isinstance(last(mlp_color), nn.Sigmoid)
+    vis = torch.nonzero(visible_mask).flatten().contiguous()                      # int64 work list (one host read)
+    xyz, color, opacity, scales, quats, mask = _AnchorDecode.apply(
+        anchor.contiguous(), anchor_feat.contiguous(), offset.contiguous(), scaling.contiguous(),
+        cam_center.detach().to(torch.float32).contiguous(), vis, color_sigmoid, *mlp)
+    return xyz, color, opacity[:, None], scales, quats, mask

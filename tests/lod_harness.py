@@ -65,8 +65,9 @@ class TinyAnchorModel(nn.Module):
         return xyz, color, opacity[mask], scales, quats
 
 
-def render(model, viewmat, K, width, height, bg, backend, two_d=False):
-    """the reference adapter's control flow; `backend` is a module-like object exposing the gsplat names"""
+def render(model, viewmat, K, width, height, bg, backend, two_d=False, fused_decode=False):
+    """the reference adapter's control flow; `backend` is a module-like object exposing the gsplat names.
+    fused_decode: use horizongs_b200.decode.generate_neural_gaussians (csrc/decode.cu) instead of model.decode()."""
     dev = model.anchor.device
     cam_center = torch.linalg.inv(viewmat)[:3, 3]
     amask = model.anchor_mask(cam_center)
@@ -87,7 +88,13 @@ def render(model, viewmat, K, width, height, bg, backend, two_d=False):
                                                   calc_compensations=False)
     visible = amask.clone()
     visible[amask] = proj[0].squeeze(0) > 0
-    xyz, color, opacity, scaling, rot = model.decode(cam_center, visible)
+    if fused_decode:
+        from horizongs_b200 import decode as DEC
+        xyz, color, opacity, scaling, rot, _ = DEC.generate_neural_gaussians(
+            model.anchor, model.anchor_feat, model.offset, torch.exp(model.scaling), cam_center, visible,
+            model.mlp_opacity, model.mlp_cov, model.mlp_color)
+    else:
+        xyz, color, opacity, scaling, rot = model.decode(cam_center, visible)
     kw = dict(means=xyz, quats=rot, scales=scaling, opacities=opacity.squeeze(-1), colors=color,
               viewmats=viewmat[None], Ks=K[None], backgrounds=bg[None], width=int(width), height=int(height),
               packed=False, sh_degree=None, render_mode="RGB+ED")

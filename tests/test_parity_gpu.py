@@ -461,3 +461,37 @@ def test_fused_l1_ssim_loss_matches_reference_golden(case):
     assert abs(float(l1) - float(G[f"{case}_l1"])) < 1e-6
     ss = losses.photometric_loss(img, gt, lambda_dssim=1.0)
     assert abs((1.0 - float(ss)) - float(G[f"{case}_ssim"])) < 2e-6
+
+
+# ------------------------------------------------------------------------------------ f1: fused anchor decode
+@pytest.mark.parametrize("color_sigmoid", [True, False])
+def test_fused_anchor_decode_matches_pytorch_decode(color_sigmoid):
+    """csrc/decode.cu against the PyTorch statement of scene/basic_model.py:297-371 (tests/lod_harness.py decode):
+    same rows in the same order, and the same gradients w.r.t. anchors, offsets, features, scaling and all MLP
+    parameters."""
+    import copy
+    import torch.nn as nn
+    from tests import lod_harness as LH
+    from horizongs_b200 import decode as DEC
+    ref = LH.TinyAnchorModel(n_anchors=3000, seed=3)
+    if not color_sigmoid:
+        ref.mlp_color = nn.Sequential(*list(ref.mlp_color)[:-1])          # scene/lod_model.py:80-84: no activation
+    ref = ref.cuda()
+    ref.level = ref.level.cuda()
+    fus = copy.deepcopy(ref)
+    g = torch.Generator().manual_seed(5)
+    cam = torch.tensor([0.3, -4.0, 2.0], device="cuda")
+    vis = (torch.rand(3000, generator=g) < 0.6).cuda()
+    xyz_r, col_r, op_r, sc_r, rot_r = ref.decode(cam, vis)
+    xyz, col, op, sc, rot, mask = DEC.generate_neural_gaussians(
+        fus.anchor, fus.anchor_feat, fus.offset, torch.exp(fus.scaling), cam, vis, fus.mlp_opacity, fus.mlp_cov, fus.mlp_color)
+    assert xyz.shape == xyz_r.shape and op.shape == op_r.shape and int(mask.sum()) == xyz.shape[0]
+    for a, b in ((xyz, xyz_r), (col, col_r), (op, op_r), (sc, sc_r), (rot, rot_r)):
+        assert float((a - b).detach().abs().max()) < 2e-5 * max(1.0, float(b.detach().abs().max()))
+    ws = [torch.randn(t.shape, generator=g).cuda() for t in (xyz_r, col_r, op_r, sc_r, rot_r)]
+    sum((t * w).sum() for t, w in zip((xyz_r, col_r, op_r, sc_r, rot_r), ws)).backward()
+    sum((t * w).sum() for t, w in zip((xyz, col, op, sc, rot), ws)).backward()
+    for (name, pr), (_, pf) in zip(ref.named_parameters(), fus.named_parameters()):
+        assert pr.grad is not None and pf.grad is not None, name
+        err = float((pf.grad - pr.grad).abs().max()) / (float(pr.grad.abs().max()) + 1e-12)
+        assert err < 2e-4, (name, err)

@@ -115,18 +115,19 @@ def run2d(name, sc, V, Ks, Wd, H, distloss):
     print(json.dumps(res), flush=True)
 
 
-def run_lod(n_anchors=500_000):
+def run_lod(n_anchors=500_000, fused_decode=False, standard_dist=26.686):
     """config 3: LOD anchor model through the reference adapter's control flow (tests/lod_harness.py): anchor
     mask + prefilter (fully_fused_projection) + MLP decode (PyTorch, as in the reference) + rasterization."""
     from tests import lod_harness as LH
     dev = "cuda"
     Wd, H = 1920, 1080
-    model = LH.TinyAnchorModel(n_anchors=n_anchors, levels=4, extent=25.0, voxel0=0.12, standard_dist=26.686).to(dev)
+    model = LH.TinyAnchorModel(n_anchors=n_anchors, levels=4, extent=25.0, voxel0=0.12, standard_dist=standard_dist).to(dev)
     model.level = model.level.to(dev)
     V = scenes.aerial_camera(12.0, 45.0, 30.0, (2.0, -3.0)).to(dev)
     Km = scenes.intrinsics(Wd, H).to(dev)
     bg = torch.zeros(3, device=dev)
-    res = {"config": "config3-lod-aerial", "anchors": n_anchors, "W": Wd, "H": H}
+    res = {"config": "config3-lod-aerial", "anchors": n_anchors, "W": Wd, "H": H, "fused_decode": fused_decode,
+           "standard_dist": standard_dist}
     marks = []
     W.set_stage_hook(lambda name, ph: marks.append((name, ph, _ev())))
 
@@ -136,7 +137,7 @@ def run_lod(n_anchors=500_000):
         return e
 
     def fwd():
-        return LH.render(model, V, Km, Wd, H, bg, hgs)
+        return LH.render(model, V, Km, Wd, H, bg, hgs, fused_decode=fused_decode)
 
     with torch.no_grad():
         o, t = timed(fwd)
@@ -182,7 +183,9 @@ if __name__ == "__main__":
                 for dl in (False, True):
                     run2d(f"config2-2dgs-{view}", *scenes.config1(view=view), dl)
         elif c == "3":
-            run_lod()
+            for sd in (26.686, 200.0):          # the reference's standard_dist, and one that keeps most anchors
+                run_lod(fused_decode=False, standard_dist=sd)
+                run_lod(fused_decode=True, standard_dist=sd)
         elif c == "4":
             sc, V, Ks, Wd, H = scenes.config4(n_views=2)
             run("config4-view0-aerial", sc, V[:1], Ks[:1], Wd, H)
