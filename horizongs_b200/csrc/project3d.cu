@@ -231,6 +231,53 @@ __global__ void __launch_bounds__(PB) project3d_bwd_vis_kernel(
     }
 }
 
+// SURVEY.md section 8(f1), first half: LOD level test (scene/lod_model.py:286-290 set_anchor_mask with
+// basic_model.py:192-203 map_to_int_level) fused with the anchor prefilter (gaussian_renderer/render.py:120-197:
+// project the anchors as Gaussians with scales = scaling[:, :3], keep radii > 0) -- one pass over the anchors
+// instead of ~6 elementwise kernels, a boolean gather, a projection launch whose other outputs are thrown away and
+// a boolean scatter.  The projection arithmetic is project3d_fwd_kernel's (same device functions, same -fmad=false).
+// level_mode: 0 floor, 1 round, 2 ceil.  visible[a] = 1 iff level[a] <= int_level(a) and the anchor's radius > 0.
+__global__ void __launch_bounds__(PB) anchor_filter_kernel(
+    const float* __restrict__ anchor, const int32_t* __restrict__ level, const float* __restrict__ extra_level,
+    const float* __restrict__ scaling, int ld_scaling, const float* __restrict__ rotation,
+    const float* __restrict__ cam_center, float resolution_scale, float standard_dist, float inv_log2_fork, int max_level,
+    int level_mode, const float* __restrict__ viewmat, const float* __restrict__ Kmat, int N, int W, int H, float eps2d,
+    float near_plane, float far_plane, float radius_clip, uint8_t* __restrict__ visible) {
+    const long long n = (long long)blockIdx.x * PB + threadIdx.x;
+    if (n >= N) return;
+    const float px = anchor[n * 3], py = anchor[n * 3 + 1], pz = anchor[n * 3 + 2];
+    bool vis = true;
+    if (level != nullptr) {
+        const float dx = px - cam_center[0], dy = py - cam_center[1], dz = pz - cam_center[2];
+        const float dist = sqrtf(dx * dx + dy * dy + dz * dz) * resolution_scale;
+        const float pred = log2f(standard_dist / dist) * inv_log2_fork + (extra_level != nullptr ? extra_level[n] : 0.f);
+        const float q = level_mode == 0 ? floorf(pred) : (level_mode == 1 ? nearbyintf(pred) : ceilf(pred));
+        const int il = (int)fminf(fmaxf(q, 0.f), (float)max_level);
+        vis = level[n] <= il;
+    }
+    if (vis) {
+        const HgsCam cam = hgs_load_cam(viewmat, Kmat, 0);
+        const float s0 = scaling[n * ld_scaling], s1 = scaling[n * ld_scaling + 1], s2 = scaling[n * ld_scaling + 2];
+        const float4 qv = reinterpret_cast<const float4*>(rotation)[n];
+        Proj3dFwd f;
+        vis = proj3d_math(cam, px, py, pz, qv.x, qv.y, qv.z, qv.w, s0, s1, s2, (float)W, (float)H, eps2d, near_plane,
+                          far_plane, f);
+        if (vis) {
+            vis = false;
+            if (f.det > 0.f) {
+                const float b = 0.5f * (f.c00 + f.c11);
+                const float v1 = b + sqrtf(fmaxf(b * b - f.det, HGS_EIG_FLOOR));
+                const float radius = ceilf(HGS_RADIUS_SIGMA * sqrtf(v1));
+                vis = !(radius <= radius_clip) &&
+                      !(f.m2x + radius <= 0.f || f.m2x - radius >= (float)W || f.m2y + radius <= 0.f ||
+                        f.m2y - radius >= (float)H) &&
+                      (int)radius > 0;
+            }
+        }
+    }
+    visible[n] = vis ? 1 : 0;
+}
+
 }  // namespace
 
 #include "../../include/hgs_raster.h"
@@ -277,6 +324,25 @@ HGS_API int hgs_project3d_bwd(const float* means, const float* quats, const floa
     project3d_bwd_kernel<<<hgs_ceil_div(N, PB), PB, 0, (cudaStream_t)stream>>>(
         means, quats, scales, viewmats, Ks, C, N, width, height, eps2d, near_plane, far_plane, radii, v_means2d,
         ld_means2d, v_depths, ld_depths, v_conics, ld_conics, v_means, v_quats, v_scales);
+    HGS_LAUNCH_CHECK();
+    return 0;
+}
+
+HGS_API int hgs_anchor_filter(const float* anchor, const int32_t* level, const float* extra_level, const float* scaling,
+                              int ld_scaling, const float* rotation, const float* cam_center, float resolution_scale,
+                              float standard_dist, float fork, int max_level, int level_mode, const float* viewmat,
+                              const float* Kmat, int N, int width, int height, float eps2d, float near_plane,
+                              float far_plane, float radius_clip, uint8_t* visible, void* stream) {
+    if (N < 0 || width <= 0 || height <= 0 || ld_scaling < 3 || anchor == nullptr || scaling == nullptr ||
+        rotation == nullptr || viewmat == nullptr || Kmat == nullptr || visible == nullptr || level_mode < 0 ||
+        level_mode > 2 || (level != nullptr && (cam_center == nullptr || !(fork > 1.f) || max_level < 0)) ||
+        (reinterpret_cast<size_t>(rotation) & 15))
+        return HGS_ERR_INVALID_ARG;
+    if (N == 0) return 0;
+    anchor_filter_kernel<<<hgs_ceil_div(N, PB), PB, 0, (cudaStream_t)stream>>>(
+        anchor, level, extra_level, scaling, ld_scaling, rotation, cam_center, resolution_scale, standard_dist,
+        level != nullptr ? 1.0f / log2f(fork) : 0.f, max_level, level_mode, viewmat, Kmat, N, width, height, eps2d,
+        near_plane, far_plane, radius_clip, visible);
     HGS_LAUNCH_CHECK();
     return 0;
 }

@@ -106,3 +106,39 @@ def generate_neural_gaussians(anchor: Tensor, anchor_feat: Tensor, offset: Tenso
         anchor.contiguous(), anchor_feat.contiguous(), offset.contiguous(), scaling.contiguous(),
         cam_center.detach().to(torch.float32).contiguous(), vis, color_sigmoid, *mlp)
     return xyz, color, opacity[:, None], scales, quats, mask
+
+
+@torch.no_grad()
+def anchor_visibility(anchor: Tensor, scaling: Tensor, rotation: Tensor, viewmat: Tensor, K: Tensor, width: int,
+                      height: int, level: Tensor = None, extra_level: Tensor = None, cam_center: Tensor = None,
+                      standard_dist: float = 1.0, fork: float = 2.0, max_level: int = 0, resolution_scale: float = 1.0,
+                      dist2level: str = "floor", eps2d: float = 0.3, near_plane: float = 0.01, far_plane: float = 1e10,
+                      radius_clip: float = 0.0) -> Tensor:
+    """bool [A]: the anchors that pass the LOD level test (scene/lod_model.py:286-290, basic_model.py:192-203;
+    skipped when `level` is None) AND the prefilter of gaussian_renderer/render.py:120-197 (projected as Gaussians
+    with scales = scaling[:, :3], quats = rotation, radii > 0) -- one kernel (hgs_anchor_filter) instead of the
+    elementwise chain, the boolean gather, the projection call and the boolean scatter.
+    anchor [A,3], scaling [A,>=3] post-activation, rotation [A,4] (wxyz), viewmat [4,4], K [3,3]."""
+    if not anchor.is_cuda:
+        raise ValueError("anchor_visibility runs on CUDA tensors only (no CPU fallback)")
+    L = _lib.lib()
+    A = anchor.shape[0]
+    mode = {"floor": 0, "round": 1, "ceil": 2}.get(dist2level)
+    if mode is None:
+        raise NotImplementedError(f"dist2level '{dist2level}' is not supported (floor / round / ceil)")
+    dev = anchor.device
+    f32 = lambda t: None if t is None else t.detach().to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
+    anchor, rotation, viewmat, K = f32(anchor), f32(rotation), f32(viewmat), f32(K)
+    scaling = scaling.detach()
+    if scaling.stride(-1) != 1 or scaling.dtype != torch.float32 or scaling.device != dev:
+        scaling = scaling.to(device=dev, dtype=torch.float32).contiguous()
+    lvl = None if level is None else level.reshape(A).to(device=dev, dtype=torch.int32).contiguous()
+    if lvl is not None and cam_center is None:
+        cam_center = torch.linalg.inv(viewmat)[:3, 3]
+    out = torch.empty(A, dtype=torch.uint8, device=anchor.device)
+    check(L.hgs_anchor_filter(ptr(anchor), ptr(lvl), ptr(f32(extra_level)), ptr(scaling), int(scaling.stride(0)),
+                              ptr(rotation), ptr(f32(cam_center)), float(resolution_scale), float(standard_dist),
+                              float(fork), int(max_level), mode, ptr(viewmat), ptr(K), A, int(width), int(height),
+                              float(eps2d), float(near_plane), float(far_plane), float(radius_clip), ptr(out),
+                              torch.cuda.current_stream().cuda_stream), "hgs_anchor_filter")
+    return out.bool()

@@ -281,6 +281,18 @@ int hgs_decode_bwd(const float* const* mlp_host, float* const* mlp_grad_host, co
                    const float* v_scales, const float* v_quats, float* g_anchor, float* g_feat, float* g_offset,
                    float* g_scaling, void* stream);
 
+/* LOD level test + anchor prefilter in one pass (scene/lod_model.py:286-290 set_anchor_mask with
+ * basic_model.py:192-203 map_to_int_level; gaussian_renderer/render.py:120-197 prefilter_voxel): visible[a] = 1 iff
+ * level[a] <= clamp(f(log2(standard_dist / (|anchor - cam_center| * resolution_scale)) / log2(fork) + extra_level[a]),
+ * 0, max_level) (f = floor / round / ceil for level_mode 0 / 1 / 2; level == NULL skips the test) AND projecting
+ * the anchor as a Gaussian with scales = scaling[a, 0:3] (row stride ld_scaling), quats = rotation[a] gives
+ * radii > 0 -- the arithmetic of hgs_project3d_fwd.  viewmat[16], Kmat[9], cam_center[3]: device pointers. */
+int hgs_anchor_filter(const float* anchor, const int32_t* level, const float* extra_level, const float* scaling,
+                      int ld_scaling, const float* rotation, const float* cam_center, float resolution_scale,
+                      float standard_dist, float fork, int max_level, int level_mode, const float* viewmat,
+                      const float* Kmat, int N, int width, int height, float eps2d, float near_plane, float far_plane,
+                      float radius_clip, uint8_t* visible, void* stream);
+
 /* ---- e: exchange of view-sharded gradients over NVLink peer memory -----------
  * New behaviour (the reference trains one view per iteration in one process; gaussian_renderer/render.py has no
  * collective): with one view per GPU only the Gaussians a view sees have non-zero gradient rows, so the SUM over

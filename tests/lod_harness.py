@@ -70,24 +70,31 @@ def render(model, viewmat, K, width, height, bg, backend, two_d=False, fused_dec
     fused_decode: use horizongs_b200.decode.generate_neural_gaussians (csrc/decode.cu) instead of model.decode()."""
     dev = model.anchor.device
     cam_center = torch.linalg.inv(viewmat)[:3, 3]
-    amask = model.anchor_mask(cam_center)
-    # prefilter_voxel(): project the anchors as Gaussians, keep radii > 0 (render.py:120-197)
-    means = model.anchor.detach()[amask]
-    scales = torch.exp(model.scaling.detach()[amask])[:, :3]
-    quats = model.rotation.to(dev)[amask]
-    with torch.no_grad():
-        if two_d:
-            dens = torch.zeros((1, means.shape[0], 2), device=dev)
-            proj = backend.fully_fused_projection_2dgs(means, quats, scales, viewmat[None], dens, K[None], int(width),
-                                                       int(height), eps2d=0.3, packed=False, near_plane=0.01,
-                                                       far_plane=1e10, radius_clip=0.0, sparse_grad=False)
-        else:
-            proj = backend.fully_fused_projection(means, None, quats, scales, viewmat[None], K[None], int(width),
-                                                  int(height), eps2d=0.3, packed=False, near_plane=0.01,
-                                                  far_plane=1e10, radius_clip=0.0, sparse_grad=False,
-                                                  calc_compensations=False)
-    visible = amask.clone()
-    visible[amask] = proj[0].squeeze(0) > 0
+    if fused_decode:
+        # LOD level test + prefilter in one kernel (csrc/project3d.cu anchor_filter_kernel)
+        from horizongs_b200 import decode as DEC
+        visible = DEC.anchor_visibility(model.anchor, torch.exp(model.scaling.detach()), model.rotation.to(dev), viewmat, K,
+                                        int(width), int(height), level=model.level, cam_center=cam_center,
+                                        standard_dist=model.standard_dist, fork=model.fork, max_level=model.levels - 1)
+    else:
+        amask = model.anchor_mask(cam_center)
+        # prefilter_voxel(): project the anchors as Gaussians, keep radii > 0 (render.py:120-197)
+        means = model.anchor.detach()[amask]
+        scales = torch.exp(model.scaling.detach()[amask])[:, :3]
+        quats = model.rotation.to(dev)[amask]
+        with torch.no_grad():
+            if two_d:
+                dens = torch.zeros((1, means.shape[0], 2), device=dev)
+                proj = backend.fully_fused_projection_2dgs(means, quats, scales, viewmat[None], dens, K[None], int(width),
+                                                           int(height), eps2d=0.3, packed=False, near_plane=0.01,
+                                                           far_plane=1e10, radius_clip=0.0, sparse_grad=False)
+            else:
+                proj = backend.fully_fused_projection(means, None, quats, scales, viewmat[None], K[None], int(width),
+                                                      int(height), eps2d=0.3, packed=False, near_plane=0.01,
+                                                      far_plane=1e10, radius_clip=0.0, sparse_grad=False,
+                                                      calc_compensations=False)
+        visible = amask.clone()
+        visible[amask] = proj[0].squeeze(0) > 0
     if fused_decode:
         from horizongs_b200 import decode as DEC
         xyz, color, opacity, scaling, rot, _ = DEC.generate_neural_gaussians(

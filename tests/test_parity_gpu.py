@@ -378,11 +378,12 @@ def test_blend2d_stage(D, distloss):
 
 
 # ------------------------------------------------------------------------------------ configs[3]: LOD anchor model
-@pytest.mark.parametrize("two_d", [False, True])
-def test_lod_anchor_model_render_through_adapter_control_flow(two_d):
+@pytest.mark.parametrize("two_d,fused", [(False, False), (True, False), (False, True)])
+def test_lod_anchor_model_render_through_adapter_control_flow(two_d, fused):
     """BASELINE.json configs[3] in miniature: anchor LOD mask -> prefilter (fully_fused_projection[_2dgs]) ->
     MLP decode in PyTorch -> rasterization[_2dgs], forward + backward to anchors / offsets / features / MLPs,
-    CUDA operators against the oracle under the same adapter code (tests/lod_harness.py)."""
+    CUDA operators against the oracle under the same adapter code (tests/lod_harness.py).  fused: the GPU side
+    uses the fused LOD mask + prefilter and the fused decode (row f1) instead of the PyTorch ops."""
     import copy
     import oracle
     from tests import lod_harness as LH
@@ -396,7 +397,8 @@ def test_lod_anchor_model_render_through_adapter_control_flow(two_d):
     w = _rand_like(torch.empty(3, H, Wd), 41)
     outs = []
     for model, backend, dev in ((ref_model, oracle, "cpu"), (gpu_model, hgs, "cuda")):
-        o = LH.render(model, V.to(dev), Km.to(dev), Wd, H, bg.to(dev), backend, two_d=two_d)
+        o = LH.render(model, V.to(dev), Km.to(dev), Wd, H, bg.to(dev), backend, two_d=two_d,
+                      fused_decode=fused and dev == "cuda")
         loss = (o["render"] * w.to(dev)).sum() + o["render_alphas"].sum() + 0.1 * o["render_depth"].sum()
         loss.backward()
         outs.append(o)
@@ -495,3 +497,36 @@ def test_fused_anchor_decode_matches_pytorch_decode(color_sigmoid):
         assert pr.grad is not None and pf.grad is not None, name
         err = float((pf.grad - pr.grad).abs().max()) / (float(pr.grad.abs().max()) + 1e-12)
         assert err < 2e-4, (name, err)
+
+
+def test_fused_anchor_visibility_matches_mask_plus_prefilter():
+    """hgs_anchor_filter == set_anchor_mask (lod_model.py:286-290) followed by prefilter_voxel (render.py:120-197),
+    except for anchors whose predicted level sits within 1e-5 of an integer (float32 rounding of log2)."""
+    import math
+    from tests import lod_harness as LH
+    from horizongs_b200 import decode as DEC, scenes
+    model = LH.TinyAnchorModel(n_anchors=20000, levels=4, extent=12.0, voxel0=0.2, standard_dist=20.0, seed=4).cuda()
+    model.level = model.level.cuda()
+    Wd, H = 320, 200
+    V = scenes.look_at((2.0, -9.0, 4.0), (0.0, 0.0, 0.3)).cuda()
+    Km = scenes.intrinsics(Wd, H, 65.0).cuda()
+    cam = torch.linalg.inv(V)[:3, 3]
+    amask = model.anchor_mask(cam)
+    radii = hgs.fully_fused_projection(model.anchor.detach()[amask], None, model.rotation.cuda()[amask],
+                                       torch.exp(model.scaling.detach()[amask])[:, :3], V[None], Km[None], Wd, H)[0]
+    ref = amask.clone()
+    ref[amask] = radii.squeeze(0) > 0
+    got = DEC.anchor_visibility(model.anchor, torch.exp(model.scaling.detach()), model.rotation.cuda(), V, Km, Wd, H,
+                                level=model.level, cam_center=cam, standard_dist=model.standard_dist, fork=model.fork,
+                                max_level=model.levels - 1)
+    assert 100 < int(ref.sum()) < 20000
+    bad = torch.nonzero(got != ref).flatten()
+    if bad.numel():
+        d = (model.anchor.detach()[bad].double() - cam.double()).norm(dim=1)
+        pred = torch.log2(model.standard_dist / d) / math.log2(model.fork)
+        assert float((pred - pred.round()).abs().max()) < 1e-5, "mismatch away from a level boundary"
+    # without the level test it is exactly the prefilter
+    r_all = hgs.fully_fused_projection(model.anchor.detach(), None, model.rotation.cuda(),
+                                       torch.exp(model.scaling.detach())[:, :3], V[None], Km[None], Wd, H)[0].squeeze(0) > 0
+    assert torch.equal(DEC.anchor_visibility(model.anchor, torch.exp(model.scaling.detach()), model.rotation.cuda(), V, Km,
+                                             Wd, H), r_all)
