@@ -42,6 +42,7 @@ SIGNATURES = {
     "hgs_blend3d_pack": (_i, [_p] * 7 + [_ll, _p, _ll, _i, _p, _p]),
     "hgs_blend3d_fwd_packed": (_i, [_p, _p] + [_i] * 6 + [_p, _p, _ll] + [_p] * 3 + [_p]),
     "hgs_blend3d_bwd_packed": (_i, [_p, _p] + [_i] * 6 + [_p, _p, _ll] + [_p] * 6 + [_p]),
+    "hgs_blend3d_unpack": (_i, [_p, _p, _ll, _ll, _p, _p, _p]),
     "hgs_blend3d_stats": (_i, [_p, _i, _i, _i, _i, _p, _p, _ll, _p, _p]),
     "hgs_blend2d_pack_bytes": (_sz, [_ll]),
     "hgs_blend2d_pack": (_i, [_p] * 8 + [_ll, _ll, _i, _p, _p]),

@@ -791,6 +791,21 @@ int launch_bwd_fast(const GRec* recs, const float* backgrounds, int C, int W, in
     return 0;
 }
 
+// The view-space mean gradient and the opacity gradient are consumed as dense tensors by autograd (retain_grad() of
+// meta["means2d"] clones the gradient; the opacity gradient is accumulated into a leaf): reading them as strided
+// views of the 48-byte vpack rows touches every sector of vpack (288 MB at 6 M Gaussians).  This copies the two
+// columns of the VISIBLE rows into dense, zero-filled tensors instead (zero fill by the launcher).
+__global__ void unpack_vpack_kernel(const float* __restrict__ vpack, const int32_t* __restrict__ vis_ids, long long n_vis,
+                                    float* __restrict__ v_means2d, float* __restrict__ v_opacities) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_vis) return;
+    const long long i = vis_ids[t];
+    const float4 q0 = reinterpret_cast<const float4*>(vpack + i * VP)[0];
+    const float2 q1 = reinterpret_cast<const float2*>(vpack + i * VP + 4)[0];
+    reinterpret_cast<float2*>(v_means2d)[i] = make_float2(q0.x, q0.y);
+    v_opacities[i] = q1.y;
+}
+
 }  // namespace
 
 #define HGS_DISPATCH_D(D, CALL)                     \
@@ -919,4 +934,19 @@ HGS_API int hgs_blend3d_bwd_packed(const void* records, const float* backgrounds
                             v_render_alphas, vpack, st)
     HGS_DISPATCH_FAST(D, normalize_depth != 0, CALL)
 #undef CALL
+}
+
+HGS_API int hgs_blend3d_unpack(const float* vpack, const int32_t* vis_ids, long long n_vis, long long CN, float* v_means2d,
+                               float* v_opacities, void* stream) {
+    if (vpack == nullptr || v_means2d == nullptr || v_opacities == nullptr || n_vis < 0 || CN < 0 ||
+        (n_vis > 0 && vis_ids == nullptr))
+        return HGS_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(v_means2d, 0, (size_t)CN * 2 * sizeof(float), st)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemsetAsync(v_opacities, 0, (size_t)CN * sizeof(float), st)) != cudaSuccess) return (int)e;
+    if (n_vis == 0) return 0;
+    unpack_vpack_kernel<<<hgs_ceil_div(n_vis, 256), 256, 0, st>>>(vpack, vis_ids, n_vis, v_means2d, v_opacities);
+    HGS_LAUNCH_CHECK();
+    return 0;
 }

@@ -400,6 +400,7 @@ class _Blend3D(torch.autograd.Function):
                 isect_offsets, flatten_ids, absgrad, radii, normalize_depth, vis_ids=None, defer=None, records=None):
         L = _lib.lib()
         ctx.defer = defer
+        ctx.vis_ids = vis_ids
         C, N = opacities.shape
         CH = colors.shape[-1]
         D = CH + (1 if depths is not None else 0)
@@ -455,6 +456,13 @@ class _Blend3D(torch.autograd.Function):
             if ctx.defer is not None:
                 ctx.defer["vpack"] = vpack
             v_means2d, v_conics, v_opacities = vpack[..., 0:2], vpack[..., 2:5], vpack[..., 5]
+            if ctx.vis_ids is not None and ctx.defer is None:
+                # autograd consumes these two as dense tensors (retain_grad clone, leaf accumulation): copy the visible
+                # rows into dense zero-filled tensors instead of handing out strided views of the 48-byte rows
+                v_means2d = torch.empty((C, N, 2), dtype=torch.float32, device=records.device)
+                v_opacities = torch.empty((C, N), dtype=torch.float32, device=records.device)
+                check(L.hgs_blend3d_unpack(ptr(vpack), ptr(ctx.vis_ids), ctx.vis_ids.numel(), C * N, ptr(v_means2d),
+                                           ptr(v_opacities), _stream()), "hgs_blend3d_unpack")
             v_colors = vpack[..., 8:8 + CH]
             v_depths = vpack[..., 8 + CH] if has_depth else None
             v_bg = None

@@ -175,6 +175,11 @@ int hgs_blend3d_bwd_packed(const void* records, const float* backgrounds, int C,
                            const float* render_alphas, const int32_t* last_ids, const float* v_render_colors,
                            const float* v_render_alphas, float* vpack, void* stream);
 
+/* Dense copies of two columns of vpack for the rows listed in vis_ids (the others are zero-filled): v_means2d[CN,2]
+ * and v_opacities[CN] -- what autograd consumes as dense tensors (retain_grad of meta["means2d"], the opacity leaf). */
+int hgs_blend3d_unpack(const float* vpack, const int32_t* vis_ids, long long n_vis, long long CN, float* v_means2d,
+                       float* v_opacities, void* stream);
+
 /* Measurement aid (not on the product path): counters[0] += P_eval, the (pixel, Gaussian) pairs a per-pixel
  * front-to-back loop visits before the pixel stops; counters[1] += P_blend, the pairs actually blended.
  * counters: eight zero-initialised uint64 on the device ([2..4]: culling statistics). */
