@@ -530,3 +530,37 @@ def test_fused_anchor_visibility_matches_mask_plus_prefilter():
                                        torch.exp(model.scaling.detach())[:, :3], V[None], Km[None], Wd, H)[0].squeeze(0) > 0
     assert torch.equal(DEC.anchor_visibility(model.anchor, torch.exp(model.scaling.detach()), model.rotation.cuda(), V, Km,
                                              Wd, H), r_all)
+
+
+@pytest.mark.parametrize("mode", ["floor", "round", "ceil"])
+def test_fused_anchor_visibility_level_modes_extra_level_and_resolution_scale(mode):
+    """the level test of hgs_anchor_filter against the reference expressions (scene/lod_model.py:286-290,
+    basic_model.py:192-203) with extra_level, resolution_scale and the three dist2level modes; the prefilter half is
+    switched off by a camera that sees everything (huge image), so only the level test decides."""
+    import math
+    from horizongs_b200 import decode as DEC, scenes
+    g = torch.Generator().manual_seed(9)
+    A = 50000
+    anchor = ((torch.rand(A, 3, generator=g) * 2 - 1) * 6).cuda()
+    anchor[:, 2] = anchor[:, 2].abs() * 0.2
+    level = torch.randint(0, 6, (A,), generator=g).cuda()
+    extra = (torch.rand(A, generator=g) * 0.8 - 0.4).cuda()
+    scaling = torch.full((A, 6), 0.05).cuda()
+    rot = torch.zeros(A, 4).cuda()
+    rot[:, 0] = 1.0
+    V = scenes.look_at((0.0, -30.0, 12.0), (0.0, 0.0, 0.0)).cuda()
+    Km = scenes.intrinsics(4000, 4000, 60.0).cuda()
+    cam = torch.linalg.inv(V)[:3, 3]
+    sd, fork, rs, max_level = 40.0, 2.0, 1.3, 4
+    dist = torch.sqrt(torch.sum((anchor - cam) ** 2, dim=1)) * rs
+    pred = torch.log2(sd / dist) / math.log2(fork) + extra
+    q = {"floor": torch.floor, "round": torch.round, "ceil": torch.ceil}[mode](pred)
+    ref = level <= torch.clamp(q.int(), min=0, max=max_level)
+    got = DEC.anchor_visibility(anchor, scaling, rot, V, Km, 4000, 4000, level=level, extra_level=extra, cam_center=cam,
+                                standard_dist=sd, fork=fork, max_level=max_level, resolution_scale=rs, dist2level=mode)
+    assert 0.05 * A < int(ref.sum()) < 0.95 * A
+    bad = torch.nonzero(got != ref).flatten()
+    if bad.numel():
+        p64 = pred[bad].double()
+        edge = (p64 - p64.round()).abs() if mode != "round" else ((p64 - p64.floor()) - 0.5).abs()
+        assert float(edge.max()) < 1e-5 and bad.numel() < 10, (bad.numel(), float(edge.max()))
