@@ -24,6 +24,7 @@
 
 #include "exchange_common.cuh"
 #include "hgs_constants.cuh"
+#include "project2d_math.cuh"
 #include "project3d_math.cuh"
 #include "sh_math.cuh"
 
@@ -116,6 +117,88 @@ __global__ void __launch_bounds__(VJ_PUSH) vjp_push_kernel(
             rec[1] = make_float4(g_quat[0], g_quat[1], g_quat[2], g_quat[3]);
             rec[2] = make_float4(g_scale[0], g_scale[1], g_scale[2], sqrtf(gx * gx + gy * gy));
             rec[3] = make_float4(q2.x, q2.y, q2.z, 0.f);
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (threadIdx.x < P.world) {
+            bulk_s2g(P.base[threadIdx.x] + soff + L.rows_off + (size_t)r0 * VJ_ROW * 4, stage[st],
+                     (unsigned)(nr * VJ_ROW * 4));
+            bulk_commit();
+        }
+    }
+    publish_push(P, flag_value);
+}
+
+// The 2DGS push kernel: the same record, computed from the 24-float row the surfel blend backward leaves in its
+// vpack ([0:2] v_means2d, [2:11] v_ray_transforms, [11:14] v_normals, [14] v_opacity, [16:16+3] v_colour,
+// [19] v_depth when the depth channel is rendered, [20:22] densification gradient; see hgs_blend2d_bwd_packed)
+// with the surfel projection VJP (project2d_math.cuh).  The densification norm uses v_means2d + the densification
+// gradient, as meta["means2d"].grad does on one GPU (rendering.py _DensifyProbe / _DensifyInject).
+constexpr int VJ_ROW2D = 24;
+template <int DEG>
+__global__ void __launch_bounds__(VJ_PUSH) vjp_push2d_kernel(
+    ExPeers P, ExLayout L, const float* __restrict__ vpack, int has_depth, const float* __restrict__ colors_fwd,
+    const float* __restrict__ viewmat, const float* __restrict__ Kmat, const float* __restrict__ campos,
+    const float* __restrict__ means, const float* __restrict__ quats, const float* __restrict__ scales,
+    const float* __restrict__ coeffs, int K, float Wf, float Hf, float near_plane, float far_plane,
+    const int32_t* __restrict__ ids, int n_rows, int parity, unsigned long long flag_value) {
+    __shared__ __align__(128) float4 stage[2][VJ_PUSH * VJ_R4];
+    const size_t soff = slot_offset(L, parity, P.rank);
+    write_block_entries(P, L, soff, ids, n_rows);
+    if (blockIdx.x == 0 && threadIdx.x <= VJ_CAM) {
+        const int t = threadIdx.x;
+        for (int q = 0; q < P.world; ++q) {
+            unsigned char* hdr = P.base[q] + soff;
+            if (t == 0) {
+                *reinterpret_cast<long long*>(hdr) = n_rows;
+            } else {
+                const int k = t - 1;
+                reinterpret_cast<float*>(hdr + 8)[k] = k < 16 ? viewmat[k] : (k < 25 ? Kmat[k - 16] : campos[k - 25]);
+            }
+        }
+    }
+    float camf[VJ_CAM];
+#pragma unroll
+    for (int k = 0; k < VJ_CAM; ++k) camf[k] = k < 16 ? viewmat[k] : (k < 25 ? Kmat[k - 16] : campos[k - 25]);
+    const HgsCam cam = cam_from(camf);
+    const int rowlen = K * 3;
+    const int n_chunks = (n_rows + VJ_PUSH - 1) / VJ_PUSH;
+    int it = 0;
+    for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, ++it) {
+        const int st = it & 1;
+        const int r0 = chunk * VJ_PUSH;
+        const int nr = min(VJ_PUSH, n_rows - r0);
+        if (threadIdx.x < P.world) bulk_wait_read<1>();
+        __syncthreads();
+        if (threadIdx.x < nr) {
+            const long long n = ids[r0 + threadIdx.x];
+            const float* row = vpack + n * VJ_ROW2D;
+            float v0 = row[16], v1 = row[17], v2 = row[18];
+            if (colors_fwd != nullptr) {
+                if (!(colors_fwd[n * 3 + 0] > 0.f)) v0 = 0.f;
+                if (!(colors_fwd[n * 3 + 1] > 0.f)) v1 = 0.f;
+                if (!(colors_fwd[n * 3 + 2] > 0.f)) v2 = 0.f;
+            }
+            const float px = means[n * 3], py = means[n * 3 + 1], pz = means[n * 3 + 2];
+            const float s0 = scales[n * 3], s1 = scales[n * 3 + 1];
+            const float4 qv = reinterpret_cast<const float4*>(quats)[n];
+            float g_mean[3] = {0.f, 0.f, 0.f}, g_scale[3] = {0.f, 0.f, 0.f}, g_quat[4] = {0.f, 0.f, 0.f, 0.f};
+            if (DEG >= 1) {
+                float gd0, gd1, gd2;
+                sh_dirgrad_one<(DEG >= 1 ? DEG : 1)>(px - camf[25], py - camf[26], pz - camf[27], coeffs + n * rowlen, v0, v1,
+                                                     v2, gd0, gd1, gd2);
+                g_mean[0] = gd0; g_mean[1] = gd1; g_mean[2] = gd2;
+            }
+            Proj2dFwd f;
+            if (proj2d_math(cam, px, py, pz, qv.x, qv.y, qv.z, qv.w, s0, s1, near_plane, far_plane, f))
+                proj2d_bwd_one(cam, f, s0, s1, vpack, VJ_ROW2D, has_depth ? vpack + 19 : nullptr, VJ_ROW2D, vpack + 2, VJ_ROW2D,
+                               vpack + 11, VJ_ROW2D, n, g_mean, g_scale, g_quat);
+            const float gx = (row[0] + row[20]) * (0.5f * Wf), gy = (row[1] + row[21]) * (0.5f * Hf);
+            float4* rec = stage[st] + threadIdx.x * VJ_R4;
+            rec[0] = make_float4(g_mean[0], g_mean[1], g_mean[2], row[14]);
+            rec[1] = make_float4(g_quat[0], g_quat[1], g_quat[2], g_quat[3]);
+            rec[2] = make_float4(g_scale[0], g_scale[1], g_scale[2], sqrtf(gx * gx + gy * gy));
+            rec[3] = make_float4(v0, v1, v2, 0.f);
         }
         fence_proxy_async();
         __syncthreads();
@@ -462,6 +545,23 @@ int launch_push(const ExPeers& P, const ExLayout& L, const float* vpack, const f
     return 0;
 }
 
+template <int DEG>
+int launch_push2d(const ExPeers& P, const ExLayout& L, const float* vpack, int has_depth, const float* colors_fwd,
+                  const float* viewmat, const float* Kmat, const float* campos, const float* means, const float* quats,
+                  const float* scales, const float* coeffs, int K, int width, int height, float near_plane, float far_plane,
+                  const int32_t* ids, int n_rows, int parity, unsigned long long flag_value, cudaStream_t st) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int chunks = (n_rows + VJ_PUSH - 1) / VJ_PUSH;
+    const int grid = chunks < 1 ? 1 : (chunks > sms * 4 ? sms * 4 : chunks);
+    vjp_push2d_kernel<DEG><<<grid, VJ_PUSH, 0, st>>>(P, L, vpack, has_depth, colors_fwd, viewmat, Kmat, campos, means, quats,
+                                                     scales, coeffs, K, (float)width, (float)height, near_plane, far_plane, ids,
+                                                     n_rows, parity, flag_value);
+    HGS_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace
 
 HGS_API size_t hgs_exchange_vjp_mailbox_bytes(int world, long long n_ids, long long cap_rows) {
@@ -529,6 +629,37 @@ HGS_API int hgs_exchange_vjp_reduce(int sh_degree, int K, const float* means, lo
         case 2: return CALL(2);
         case 3: return CALL(3);
         default: return CALL(4);
+    }
+#undef CALL
+}
+
+HGS_API int hgs_exchange_vjp_push_2dgs(int sh_degree, int K, const float* vpack24, int has_depth, const float* colors_fwd,
+                                       const float* viewmat, const float* Kmat, const float* campos, const float* means,
+                                       const float* quats, const float* scales, const float* coeffs, int width, int height,
+                                       float near_plane, float far_plane, long long n_ids, const int32_t* ids,
+                                       long long n_rows, long long cap_rows, void* const* mailboxes_host, int world,
+                                       int rank, unsigned long long step, void* stream) {
+    if (ex_bad_geometry(world, rank, n_ids, cap_rows) || n_rows < 0 || vpack24 == nullptr || viewmat == nullptr ||
+        Kmat == nullptr || campos == nullptr || means == nullptr || quats == nullptr || scales == nullptr ||
+        (reinterpret_cast<size_t>(quats) & 15) || sh_degree < -1 || sh_degree > 4 || width <= 0 || height <= 0)
+        return HGS_ERR_INVALID_ARG;
+    if (sh_degree >= 0 ? K < (sh_degree + 1) * (sh_degree + 1) : K != 1) return HGS_ERR_INVALID_ARG;
+    if (sh_degree >= 1 && coeffs == nullptr) return HGS_ERR_INVALID_ARG;
+    if (n_rows > cap_rows) return HGS_ERR_WORKSPACE;
+    if (n_rows > 0 && ids == nullptr) return HGS_ERR_INVALID_ARG;
+    ExPeers P;
+    if (int e = ex_fill_peers(P, mailboxes_host, world, rank)) return e;
+    const ExLayout L = make_layout(world, n_ids, cap_rows, VJ_ROW);
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(DEG)                                                                                                       \
+    launch_push2d<DEG>(P, L, vpack24, has_depth, colors_fwd, viewmat, Kmat, campos, means, quats, scales, coeffs, K, width, \
+                       height, near_plane, far_plane, ids, (int)n_rows, (int)(step & 1ull), step + 1ull, st)
+    switch (sh_degree) {
+        case 1: return CALL(1);
+        case 2: return CALL(2);
+        case 3: return CALL(3);
+        case 4: return CALL(4);
+        default: return CALL(0);
     }
 #undef CALL
 }

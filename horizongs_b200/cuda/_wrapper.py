@@ -567,6 +567,8 @@ class _Project2D(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, _v_radii, v_means2d, v_depths, v_ray_transforms, v_normals, _v_tiles):
+        if ctx.holder is not None and ctx.holder.get("defer") is not None:
+            return (None,) * 12           # runs later, fused with the exchange (FusedBackwardExchange.finish)
         means, quats, scales, viewmats, Ks, radii = ctx.saved_tensors
         width, height, near_plane, far_plane = ctx.cfg
         L = _lib.lib()
@@ -624,8 +626,10 @@ class _Blend2D(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means2d, ray_transforms, colors, depths, normals, opacities, densify, backgrounds, width,
-                height, tile_size, isect_offsets, flatten_ids, distloss, box, radii, normalize_depth, vis_ids):
+                height, tile_size, isect_offsets, flatten_ids, distloss, box, radii, normalize_depth, vis_ids,
+                defer=None):
         L = _lib.lib()
+        ctx.defer = defer
         C, N = opacities.shape
         CH = colors.shape[-1]
         D = CH + (1 if depths is not None else 0)
@@ -680,7 +684,7 @@ class _Blend2D(torch.autograd.Function):
         width, height, tile_size, distloss, normalize_depth, CH, D = ctx.cfg
         L = _lib.lib()
         cg = lambda t: None if t is None else t.contiguous()  # noqa: E731
-        tail = (None,) * 10
+        tail = (None,) * 11
         if ctx.fast:
             (records, backgrounds, isect_offsets, flatten_ids, render_colors, render_alphas, last_ids,
              median_ids) = ctx.saved_tensors
@@ -703,6 +707,8 @@ class _Blend2D(torch.autograd.Function):
                                            ptr(v_render_distort), ptr(v_render_median), ptr(vpack), _stream()),
                   "hgs_blend2d_bwd_packed")
             _mark("blend2d_bwd", 1)
+            if ctx.defer is not None:
+                ctx.defer.update(vpack=vpack, surfel=True, has_depth=bool(has_depth))
             v_means2d = vpack[..., 0:2]
             v_rt = vpack[..., 2:11].unflatten(-1, (3, 3))
             v_normals = vpack[..., 11:14]
@@ -739,7 +745,7 @@ class _Blend2D(torch.autograd.Function):
 
 def _blend2d(means2d, ray_transforms, colors, depths, normals, opacities, densify, backgrounds, width, height,
              tile_size, isect_offsets, flatten_ids, distloss=False, box=None, radii=None, normalize_depth=False,
-             vis_ids=None):
+             vis_ids=None, defer=None):
     if tile_size not in _TILE_SIZES:
         raise NotImplementedError(f"tile_size {tile_size} is not supported (supported: {_TILE_SIZES})")
     D = colors.shape[-1] + (1 if depths is not None else 0)
@@ -749,7 +755,7 @@ def _blend2d(means2d, ray_transforms, colors, depths, normals, opacities, densif
                           _f32c(colors, "colors"), _f32c(depths, "depths"), _f32c(normals, "normals"),
                           _f32c(opacities, "opacities"), densify, _f32c(backgrounds, "backgrounds"), int(width),
                           int(height), int(tile_size), isect_offsets.contiguous(), flatten_ids.contiguous(),
-                          bool(distloss), box, radii, bool(normalize_depth), vis_ids)
+                          bool(distloss), box, radii, bool(normalize_depth), vis_ids, defer)
 
 
 def rasterize_to_pixels_2dgs(means2d: Tensor, ray_transforms: Tensor, colors: Tensor, opacities: Tensor,

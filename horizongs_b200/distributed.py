@@ -291,7 +291,8 @@ class FusedBackwardExchange:
             raise _lib.HgsError("finish(): no deferred backward recorded (run rasterization + backward inside deferred())")
         N = self.n_ids
         vpack, ids = sk["vpack"], sk["vis_ids"]
-        assert vpack.shape == (1, N, 12) and vpack.is_contiguous() and sk["n"] == N
+        surfel = bool(sk.get("surfel", False))          # rasterization_2dgs: 24-float rows, surfel projection VJP
+        assert vpack.shape == (1, N, 24 if surfel else 12) and vpack.is_contiguous() and sk["n"] == N
         n = int(ids.numel())
         if n > self.cap_rows:
             raise _lib.HgsError(f"{n} visible Gaussians exceed the mailbox capacity {self.cap_rows}")
@@ -306,11 +307,19 @@ class FusedBackwardExchange:
         W._mark("exchange_vjp_push", 0)
         deg = -1 if sh_degree is None else int(sh_degree)
         dm, dq, ds, dc = means.detach(), quats.detach(), scales.detach(), colors.detach()
-        self._check(L.hgs_exchange_vjp_push(deg, K, p(vpack), p(cf), p(sk["viewmats"]), p(sk["Ks"]), p(sk["campos"]),
-                                            p(dm), p(dq), p(ds), p(dc), int(sk["width"]), int(sk["height"]),
-                                            float(sk["eps2d"]), float(sk["near_plane"]), float(sk["far_plane"]), N,
-                                            p(ids) if n > 0 else None, n, self.cap_rows, self.box.ptrs_c, self.world,
-                                            self.rank, self.step, st), "hgs_exchange_vjp_push")
+        if surfel:
+            self._check(L.hgs_exchange_vjp_push_2dgs(deg, K, p(vpack), int(sk["has_depth"]), p(cf), p(sk["viewmats"]),
+                                                     p(sk["Ks"]), p(sk["campos"]), p(dm), p(dq), p(ds), p(dc),
+                                                     int(sk["width"]), int(sk["height"]), float(sk["near_plane"]),
+                                                     float(sk["far_plane"]), N, p(ids) if n > 0 else None, n,
+                                                     self.cap_rows, self.box.ptrs_c, self.world, self.rank, self.step, st),
+                        "hgs_exchange_vjp_push_2dgs")
+        else:
+            self._check(L.hgs_exchange_vjp_push(deg, K, p(vpack), p(cf), p(sk["viewmats"]), p(sk["Ks"]), p(sk["campos"]),
+                                                p(dm), p(dq), p(ds), p(dc), int(sk["width"]), int(sk["height"]),
+                                                float(sk["eps2d"]), float(sk["near_plane"]), float(sk["far_plane"]), N,
+                                                p(ids) if n > 0 else None, n, self.cap_rows, self.box.ptrs_c, self.world,
+                                                self.rank, self.step, st), "hgs_exchange_vjp_push")
         W._mark("exchange_vjp_push", 1)
         outs = [torch.empty_like(t) for t in (means, quats, scales, opacities, colors)]
         W._mark("exchange_vjp_reduce", 0)

@@ -229,7 +229,20 @@ def rasterization_2dgs(
             means2d, radii, depths, tiles_per_gauss, C, N, tile_size, tile_width, tile_height)
     holder["vis_ids"] = vis_ids
 
-    feats = _per_view_features(means, colors, viewmats, radii, sh_degree, C, vis_ids)
+    # multi-GPU: the SH / surfel-projection backward is deferred and runs fused with the gradient exchange
+    defer = W.current_deferred_sink() if torch.is_grad_enabled() else None
+    if defer is not None:
+        if C != 1 or render_mode not in ("RGB", "RGB+D", "RGB+ED"):
+            raise NotImplementedError("deferred backward needs one camera per rank and an RGB(+depth) render mode")
+        if sh_degree is None and (colors.dim() != 2 or colors.shape[-1] != 3):
+            raise NotImplementedError("deferred backward needs [N,3] colours or SH coefficients")
+        holder["defer"] = defer
+        defer.clear()
+        defer.update(vis_ids=vis_ids, viewmats=viewmats.detach().contiguous(), Ks=Ks.detach().contiguous(),
+                     campos=_camera_positions(viewmats.detach()).contiguous(), width=width, height=height, eps2d=eps2d,
+                     near_plane=near_plane, far_plane=far_plane, sh_degree=sh_degree, n=N)
+
+    feats = _per_view_features(means, colors, viewmats, radii, sh_degree, C, vis_ids, defer)
     feats, depth_ch, bgs = _mode_features(feats, depths, backgrounds, render_mode)
     n_ch = feats.shape[-1] + (1 if depth_ch is not None else 0)
     fuse_norm = render_mode in ("ED", "RGB+ED") and n_ch in (1, 3, 4)
@@ -242,7 +255,7 @@ def rasterization_2dgs(
 
     render_colors, render_alphas, render_normals, render_distort, render_median = W._blend2d(
         means2d_in, ray_transforms, feats, depth_ch, normals, opac, densify, bgs, width, height, tile_size,
-        isect_offsets, flatten_ids, distloss, box, radii=radii, normalize_depth=fuse_norm, vis_ids=vis_ids)
+        isect_offsets, flatten_ids, distloss, box, radii=radii, normalize_depth=fuse_norm, vis_ids=vis_ids, defer=defer)
 
     render_normals_from_depth = None
     if render_mode in ("ED", "RGB+ED") and not fuse_norm:

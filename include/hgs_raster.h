@@ -351,6 +351,15 @@ int hgs_exchange_vjp_push(int sh_degree, int K, const float* vpack, const float*
                           float near_plane, float far_plane, long long n_ids, const int32_t* ids, long long n_rows,
                           long long cap_rows, void* const* mailboxes_host, int world, int rank,
                           unsigned long long step, void* stream);
+/* the same push for rasterization_2dgs: vpack24[N,24] is the row layout of hgs_blend2d_bwd_packed (has_depth: the
+ * depth channel was rendered, its gradient sits in column 19); the surfel projection VJP replaces the 3DGS one and
+ * the densification norm uses v_means2d + the densification gradient (columns 20:22).  The reduce is shared. */
+int hgs_exchange_vjp_push_2dgs(int sh_degree, int K, const float* vpack24, int has_depth, const float* colors_fwd,
+                               const float* viewmat, const float* Kmat, const float* campos, const float* means,
+                               const float* quats, const float* scales, const float* coeffs, int width, int height,
+                               float near_plane, float far_plane, long long n_ids, const int32_t* ids, long long n_rows,
+                               long long cap_rows, void* const* mailboxes_host, int world, int rank,
+                               unsigned long long step, void* stream);
 int hgs_exchange_vjp_reduce(int sh_degree, int K, const float* means, long long n_ids, long long cap_rows,
                             const void* mailbox, int world, int rank, unsigned long long step, float* v_means,
                             float* v_quats, float* v_scales, float* v_opacities, float* v_coeffs, float* grad_accum,

@@ -79,7 +79,7 @@ def test_peer_exchange_equals_dense_allreduce(tmp_path):
         assert got["worst"] < 1e-5, f"rank {r}: differs from the dense all-reduce by {got['worst']}"
 
 
-def _fused_worker(rank, world, port, out_dir, sh_degree, steps):
+def _fused_worker(rank, world, port, out_dir, sh_degree, steps, two_d=False):
     import math
     import torch.distributed as dist
     import horizongs_b200 as hgs
@@ -106,10 +106,17 @@ def _fused_worker(rank, world, port, out_dir, sh_degree, steps):
         V = scenes.look_at(eye, target).to(dev)
 
         def run():
-            rc, ra, meta = hgs.rasterization(*params, V[None], Km[None], Wd, H, sh_degree=sh_degree,
-                                             render_mode="RGB+ED", backgrounds=torch.full((1, 3), 0.2, device=dev))
+            bgs = torch.full((1, 3), 0.2, device=dev)
+            if two_d:
+                (rc, ra, rn, rnd, rd, rm), meta = hgs.rasterization_2dgs(*params, V[None], Km[None], Wd, H, sh_degree=sh_degree,
+                                                                      render_mode="RGB+ED", backgrounds=bgs)
+                extra = 0.05 * (rn * wimg[..., :3]).sum() + 0.05 * (1 - (rn * rnd).sum(-1)).mean()
+            else:
+                rc, ra, meta = hgs.rasterization(*params, V[None], Km[None], Wd, H, sh_degree=sh_degree,
+                                                 render_mode="RGB+ED", backgrounds=bgs)
+                extra = 0.0
             meta["means2d"].retain_grad()
-            ((rc * wimg).sum() + ra.sum()).backward()
+            ((rc * wimg).sum() + ra.sum() + extra).backward()
             return meta
         # reference: every rank's own autograd gradients, dense NCCL all-reduce
         for p in params:
@@ -145,15 +152,15 @@ def _fused_worker(rank, world, port, out_dir, sh_degree, steps):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("sh_degree", [2, None])
-def test_fused_backward_exchange_equals_allreduced_autograd(tmp_path, sh_degree):
+@pytest.mark.parametrize("sh_degree,two_d", [(2, False), (None, False), (2, True)])
+def test_fused_backward_exchange_equals_allreduced_autograd(tmp_path, sh_degree, two_d):
     """SH / projection backward fused with the exchange == dense all-reduce of every rank's autograd gradients
     (gradient tolerance of north_star: 1e-3 rel), bit-identical on all ranks, densification statistics included."""
     import torch.multiprocessing as mp
     world = min(torch.cuda.device_count(), 8)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
-    mp.spawn(_fused_worker, args=(world, _free_port(), str(tmp_path), sh_degree, 4), nprocs=world, join=True)
+    mp.spawn(_fused_worker, args=(world, _free_port(), str(tmp_path), sh_degree, 4, two_d), nprocs=world, join=True)
     for r in range(world):
         got = torch.load(os.path.join(str(tmp_path), f"f{r}.pt"))
         assert got["ok"], f"rank {r}: replicas are not bit-identical (or visibility counts differ)"
@@ -169,9 +176,10 @@ def test_exchanges_on_one_gpu_equal_local_autograd(tmp_path):
     if torch.cuda.device_count() < 1:
         pytest.skip("needs a GPU")
     port = _free_port()
-    mp.spawn(_fused_worker, args=(1, port, str(tmp_path), 2, 3), nprocs=1, join=True)
-    got = torch.load(os.path.join(str(tmp_path), "f0.pt"))
-    assert got["ok"] and got["worst"] < 1e-4, got
+    for two_d in (False, True):
+        mp.spawn(_fused_worker, args=(1, port + (1 if two_d else 0), str(tmp_path), 2, 3, two_d), nprocs=1, join=True)
+        got = torch.load(os.path.join(str(tmp_path), "f0.pt"))
+        assert got["ok"] and got["worst"] < 1e-4, (two_d, got)
     mp.spawn(_worker, args=(1, _free_port(), str(tmp_path), 20011, 4), nprocs=1, join=True)
     got = torch.load(os.path.join(str(tmp_path), "r0.pt"))
     assert got["ok"] and got["worst"] < 1e-6, got
