@@ -244,3 +244,32 @@ def test_reference_loss_fixtures_are_consistent():
         assert G[f"{case}_grad"].shape == G[f"{case}_img"].shape
         l1 = np.abs(G[f"{case}_img"].astype(np.float64) - G[f"{case}_gt"].astype(np.float64)).mean()
         assert abs(l1 - float(G[f"{case}_l1"])) < 1e-12
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """every function declared in include/hgs_raster.h is bound in horizongs_b200/_lib.py with the same number of
+    parameters and compatible kinds (pointer / integer / float), so the ctypes layer cannot drift from the C ABI"""
+    import ctypes as C
+    from horizongs_b200 import _lib
+    text = open(_lib.HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = re.findall(r"\b(?:int|size_t|long long|unsigned long long|const char\*)\s+(hgs_[a-z0-9_]+)\s*\((.*?)\)\s*;", text,
+                        flags=re.S)
+    assert len(protos) >= 50
+    seen = set()
+    for name, params in protos:
+        seen.add(name)
+        assert name in _lib.SIGNATURES, f"{name} is declared in the header but not bound in _lib.SIGNATURES"
+        params = " ".join(params.split())
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        argtypes = _lib.SIGNATURES[name][1]
+        assert len(plist) == len(argtypes), (name, len(plist), len(argtypes))
+        for p, t in zip(plist, argtypes):
+            is_ptr = "*" in p
+            if is_ptr:
+                assert t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents") or issubclass(t, C._Pointer), (name, p, t)
+            elif re.match(r"(const )?float\b", p):
+                assert t is C.c_float, (name, p, t)
+            else:
+                assert t in (C.c_int, C.c_longlong, C.c_size_t, C.c_ulonglong), (name, p, t)
+    assert seen == set(_lib.SIGNATURES), sorted(set(_lib.SIGNATURES) ^ seen)
