@@ -1,21 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- fwd+bwd iterations/s of the rasterization hot path on BASELINE.json's headline workload.
+"""bench.py -- fwd+bwd iterations/s of the rasterization hot path on BASELINE.json's workloads.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 0|1|2|3|4]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
 
-Workload (config.workload): BASELINE.json configs[4] = the configuration its metric is quoted on -- 6M explicit
-SH2 Gaussians, 1920x1080, render_mode RGB+ED, 8 seeded cameras (aerial / street alternating).  One "step" =
-one view per GPU: rasterization forward, an L1-style loss, backward to the 38 floats of every Gaussian, and
-for N > 1 the NCCL all-reduce of those gradients and of the densification statistics.  Rank r renders view
-(r + step) mod 8, so every rank sees every view ("weak" scaling: per-GPU work fixed).
+Default workload (config.workload): BASELINE.json configs[4] = the configuration its metric is quoted on -- 6M
+explicit SH2 Gaussians, 1920x1080, render_mode RGB+ED, 8 seeded cameras (aerial / street alternating).  One "step"
+= one view per GPU: rasterization forward, an L1-style loss, backward to the 38 floats of every Gaussian, the
+densification statistics, and for N > 1 the gradient exchange (default: the per-Gaussian backward fused with the
+exchange over NVLink peer memory, csrc/exchange_vjp.cu; `--exchange nccl` = dense NCCL all-reduce).  Rank r renders
+view (r + step) mod 8, so every rank sees every view ("weak" scaling: per-GPU work fixed).
+`--config 0..3` time the other named configurations (parity-test cases of the contract, measured for completeness):
+0 = 100k / 256x256 (the CPU-runnable case, full frame on both arms), 1 = 1M 3DGS 1080p aerial + street, 2 = 1M 2DGS
+surfels with the normal-consistency loss, 3 = LOD anchor model (500k anchors x 10) through the adapter control flow.
 
 One JSON line on stdout (rank 0).  `value` = views/s with everything resident in HBM; `e2e` = the same through
 the public API with the step's camera and ground-truth image copied from pinned host memory and the loss read
-back, inside the timed region.  `roofline` describes the dominant kernel (blend backward, FP32-pipe bound),
-`roofline_hbm` the dominant HBM-bound stage; `cpu_baseline` is the CPU oracle on a bounded sample.
-`--impl reference` times the CPU oracle port (the reference's own rasterizer, gsplat, is not installable
-here: see DESIGN.md) on a bounded sample of the same workload, rank 0 only.
+back, inside the timed region.  `roofline` describes the dominant kernel (blend backward, FP32-issue bound),
+`roofline_hbm` the dominant HBM-bound stage; `cpu_baseline` is the CPU oracle on a bounded, FIXED sample (384x256
+centre window of views 0 and 7; measured seconds and the full-frame extrapolation are separate fields);
+`parity_check` compares the CUDA path with the oracle on those same windows of the benchmarked scene (integer stages
+bit-exact, image 1e-4, gradients 1e-3) and, for N > 1, `exchange_parity` compares the fused exchange with the dense
+all-reduce of every rank's autograd gradients.
+`--impl reference` times the CPU oracle port (the reference's own rasterizer, gsplat, is not installable here: see
+DESIGN.md) on the same bounded sample, rank 0 only.
 """
 from __future__ import annotations
 
@@ -34,36 +42,97 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-METRIC = "fwd+bwd iters/s, 6M Gaussians @1920x1080"
 LOSS_MODE = "l1"
-N_VIEWS = 8
-WIDTH, HEIGHT = 1920, 1080
+SAMPLE_WINDOW = (384, 256)          # the bounded CPU sample: centre window of the 1080p frame, fixed
+SAMPLE_VIEWS = {4: (0, 7), 1: (0, 1), 2: (0, 1)}   # one aerial and one street view (view 7 of configs[4] has the deepest tiles)
+LAMBDA_NORMAL = 0.05                # config/our_2d: lambda_normal (train.py:180-188)
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-# ------------------------------------------------------------------------------------------------- workload
-def make_workload(n_gauss: int):
-    from horizongs_b200 import scenes
-    t0 = time.time()
-    sc, views, Ks, W, H = scenes.config4(n=n_gauss, n_views=N_VIEWS, width=WIDTH, height=HEIGHT)
-    g = torch.Generator().manual_seed(7)
-    gts = torch.rand(N_VIEWS, H, W, 3, generator=g)             # synthetic ground-truth images
-    log(f"[bench] scene {n_gauss} Gaussians generated in {time.time() - t0:.1f}s")
-    return sc, views, Ks, W, H, gts
+# ------------------------------------------------------------------------------------------------- workloads
+class Workload:
+    """scene + cameras + ground truth of one BASELINE.json config (CPU tensors; callers move them)"""
+
+    def __init__(self, config: int, n_gauss: int | None):
+        from horizongs_b200 import scenes
+        t0 = time.time()
+        self.config = config
+        self.kind = "2dgs" if config == 2 else ("lod" if config == 3 else "3dgs")
+        if config == 4:
+            n = n_gauss or 6_000_000
+            self.sc, self.views, self.Ks, self.W, self.H = scenes.config4(n=n, n_views=8)
+            self.name = (f"configs[4]: {n / 1e6:g}M explicit SH2 3DGS Gaussians, {self.W}x{self.H}, RGB+ED, "
+                         "1 view per GPU per step")
+            self.metric = f"fwd+bwd iters/s, {n / 1e6:g}M Gaussians @{self.W}x{self.H}"
+        elif config in (1, 2):
+            n = n_gauss or 1_000_000
+            sc, va, Ks, self.W, self.H = scenes.config1(n=n, view="aerial")
+            _, vs, _, _, _ = scenes.config1(n=16, view="street")
+            self.sc, self.views, self.Ks = sc, torch.cat([va, vs], 0), Ks.expand(2, -1, -1).contiguous()
+            what = "3DGS Gaussians" if config == 1 else "2DGS surfels (normal-consistency loss, distortion off)"
+            self.name = (f"configs[{config}]: {n / 1e6:g}M {what}, {self.W}x{self.H}, RGB+ED, aerial + street views "
+                         "alternating, 1 view per GPU per step")
+            self.metric = f"fwd+bwd iters/s, {n / 1e6:g}M {'Gaussians' if config == 1 else 'surfels'} @{self.W}x{self.H}"
+        elif config == 0:
+            n = n_gauss or 100_000
+            self.sc, self.views, self.Ks, self.W, self.H = scenes.config0(n=n)
+            self.name = f"configs[0]: {n / 1e3:g}k 3DGS Gaussians, one {self.W}x{self.H} camera, RGB+ED (full frame on both arms)"
+            self.metric = f"fwd+bwd iters/s, {n / 1e3:g}k Gaussians @{self.W}x{self.H}"
+        elif config == 3:
+            from tests import lod_harness as LH
+            n = n_gauss or 500_000
+            self.W, self.H = 1920, 1080
+            self.model = LH.TinyAnchorModel(n_anchors=n, levels=4, extent=25.0, voxel0=0.12, standard_dist=26.686)
+            self.views = torch.stack([scenes.aerial_camera(12.0, 45.0, 30.0, (2.0, -3.0)),
+                                      scenes.street_camera(0.3, 40.0, (1.0, 2.0))], 0)
+            self.Ks = scenes.intrinsics(self.W, self.H)[None].expand(2, -1, -1).contiguous()
+            self.sc = None
+            self.name = (f"configs[3]: LOD anchor model, {n / 1e3:g}k anchors x 10 neural Gaussians, {self.W}x{self.H}, "
+                         "level mask + prefilter + fused decode + rasterization through the adapter control flow")
+            self.metric = f"fwd+bwd iters/s, {n / 1e3:g}k anchors x10 @{self.W}x{self.H}"
+        else:
+            raise ValueError(config)
+        self.n_views = self.views.shape[0]
+        g = torch.Generator().manual_seed(7)
+        self.gts = torch.rand(self.n_views, self.H, self.W, 3, generator=g)        # synthetic ground-truth images
+        self.sh_degree = None if self.sc is None else self.sc.sh_degree
+        log(f"[bench] workload {self.name!r} generated in {time.time() - t0:.1f}s")
+
+    @property
+    def n(self):
+        return self.sc.n if self.sc is not None else self.model.anchor.shape[0]
 
 
-def loss_fn(rc, ra, gt):
+def loss_fn(rc, ra, gt, extra=None):
     """L1 photometric term + small depth / alpha terms (every output channel gets a gradient).  On the GPU the
-    same expression is one fused forward and one fused backward kernel (horizongs_b200.losses, csrc/loss.cu)."""
+    same expression is one fused forward and one fused backward kernel (horizongs_b200.losses, csrc/loss.cu).
+    extra = (render_normals, normals_from_depth) of a 2DGS render: + the normal-consistency term of train.py:180-188."""
     if rc.is_cuda:
         from horizongs_b200 import losses
         if LOSS_MODE == "l1ssim":       # the reference's full photometric loss (train.py:158-160), fused
-            return losses.photometric_loss(rc, gt, 0.2, ra, w_depth=0.01, w_alpha=0.01)
-        return losses.photometric_l1_loss(rc, gt, ra, w_depth=0.01, w_alpha=0.01)
-    return (rc[..., :3] - gt).abs().mean() + 0.01 * rc[..., 3].mean() + 0.01 * ra.mean()
+            loss = losses.photometric_loss(rc, gt, 0.2, ra, w_depth=0.01, w_alpha=0.01)
+        else:
+            loss = losses.photometric_l1_loss(rc, gt, ra, w_depth=0.01, w_alpha=0.01)
+    else:
+        loss = (rc[..., :3] - gt).abs().mean() + 0.01 * rc[..., 3].mean() + 0.01 * ra.mean()
+    if extra is not None:
+        rn, rnd = extra
+        nfd = rnd.reshape(rn.shape) * ra.detach()
+        loss = loss + LAMBDA_NORMAL * (1.0 - (rn * nfd).sum(-1)).mean()
+    return loss
+
+
+def render_explicit(backend, kind, params, view, Km, W, H, sh_degree, bg):
+    """-> (render_colors, render_alphas, meta, extra) through the gsplat-named pipeline of `backend`"""
+    kw = dict(sh_degree=sh_degree, render_mode="RGB+ED", backgrounds=bg, packed=False)
+    if kind == "2dgs":
+        (rc, ra, rn, rnd, _, _), meta = backend.rasterization_2dgs(*params, view, Km, W, H, **kw)
+        return rc, ra, meta, (rn, rnd)
+    rc, ra, meta = backend.rasterization(*params, view, Km, W, H, **kw)
+    return rc, ra, meta, None
 
 
 # ------------------------------------------------------------------------------------------------- clocks
@@ -120,97 +189,216 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- CPU oracle arm
-def oracle_window_step(sc, view, K, win, threads):
-    """fwd+bwd of the CPU oracle on a window (x0,y0,w,h) of the full frame (a sub-frustum: same Gaussians, same
-    camera, principal point shifted).  Returns (seconds for the window step, seconds of its projection/SH part)."""
+def centre_window(wl: Workload):
+    if wl.W <= SAMPLE_WINDOW[0] or wl.H <= SAMPLE_WINDOW[1]:
+        return (0, 0, wl.W, wl.H)                                   # configs[0]: the full frame, nothing extrapolated
+    w, h = SAMPLE_WINDOW
+    return (wl.W // 2 - w // 2, wl.H // 2 - h // 2, w, h)
+
+
+def window_K(K, win):
+    K2 = K.clone()
+    K2[0, 2] -= win[0]
+    K2[1, 2] -= win[1]
+    return K2
+
+
+def window_gt(win):
+    return torch.rand(1, win[3], win[2], 3, generator=torch.Generator().manual_seed(3))
+
+
+def oracle_window_step(wl: Workload, v: int, win, threads, keep=False):
+    """fwd+bwd of the CPU oracle on the window (x0,y0,w,h) of view v (a sub-frustum: same Gaussians, same camera,
+    principal point shifted).  -> dict(seconds of the step, seconds of its per-Gaussian part, isects, and -- keep --
+    the outputs / meta / gradients for the parity check)"""
     from oracle import gsplat_oracle as O
     torch.set_num_threads(threads)
-    x0, y0, w, h = win
-    K2 = K.clone()
-    K2[0, 2] -= x0
-    K2[1, 2] -= y0
-    params = [t.clone().requires_grad_() for t in (sc.means, sc.quats, sc.scales, sc.opacities, sc.colors)]
-    gt = torch.rand(1, h, w, 3, generator=torch.Generator().manual_seed(3))
+    sc = wl.sc
+    K2 = window_K(wl.Ks[v], win)
+    w, h = win[2], win[3]
+    src = (sc.means, sc.quats, sc.scales, sc.opacities, sc.colors)
+    params = [t.clone().requires_grad_() for t in src]
+    gt = window_gt(win)
+    bg = torch.zeros(1, 3)
     t0 = time.perf_counter()
-    rc, ra, meta = O.rasterization(*params, view[None], K2[None], w, h, sh_degree=sc.sh_degree, render_mode="RGB+ED",
-                                   backgrounds=torch.zeros(1, 3))
-    loss_fn(rc, ra, gt).backward()
+    rc, ra, meta, extra = render_explicit(O, wl.kind, params, wl.views[v][None], K2[None], w, h, sc.sh_degree, bg)
+    if keep:
+        meta["means2d"].retain_grad()
+    loss = loss_fn(rc, ra, gt, extra)
+    loss.backward()
     t_step = time.perf_counter() - t0
+    out = {"t_step": t_step, "n_isects": int(meta["flatten_ids"].numel())}
+    if keep:
+        out.update(rc=rc.detach(), ra=ra.detach(), meta=meta, grads=[p.grad for p in params],
+                   extra=None if extra is None else [e.detach() for e in extra], loss=float(loss.detach()))
     # the per-Gaussian part (projection + SH, fwd+bwd) does not shrink with the window: time it alone
-    params = [t.clone().requires_grad_() for t in (sc.means, sc.quats, sc.scales, sc.opacities, sc.colors)]
+    params = [t.clone().requires_grad_() for t in src]
     t0 = time.perf_counter()
-    radii, m2, d, con, _ = O.fully_fused_projection(params[0], None, params[1], params[2], view[None], K2[None], w, h)
-    cols = O._view_colors(params[0], params[4], view[None], radii, sc.sh_degree)
-    (m2.sum() + d.sum() + con.sum() + cols.sum()).backward()
-    t_gauss = time.perf_counter() - t0
-    return t_step, t_gauss, int(meta["flatten_ids"].numel())
+    if wl.kind == "2dgs":
+        radii, m2, d, rt, nrm = O.fully_fused_projection_2dgs(params[0], params[1], params[2], wl.views[v][None], None,
+                                                              K2[None], w, h)
+        geo = rt.sum() + nrm.sum()
+    else:
+        radii, m2, d, con, _ = O.fully_fused_projection(params[0], None, params[1], params[2], wl.views[v][None],
+                                                        K2[None], w, h)
+        geo = con.sum()
+    cols = O._view_colors(params[0], params[4], wl.views[v][None], radii, sc.sh_degree)
+    (m2.sum() + d.sum() + geo + cols.sum()).backward()
+    out["t_gauss"] = time.perf_counter() - t0
+    scale = (wl.W * wl.H) / float(w * h)
+    out["t_full_est"] = out["t_gauss"] + max(t_step - out["t_gauss"], 1e-6) * scale
+    out["scale"] = scale
+    return out
 
 
-def oracle_full_frame_estimate(sc, view, K, win, threads):
-    t_step, t_gauss, n_isect = oracle_window_step(sc, view, K, win, threads)
-    scale = (WIDTH * HEIGHT) / float(win[2] * win[3])
-    t_pix = max(t_step - t_gauss, 1e-6)
-    return t_gauss + t_pix * scale, t_step, n_isect
-
-
-def centre_window(w, h):
-    return (WIDTH // 2 - w // 2, HEIGHT // 2 - h // 2, w, h)
-
-
-def pick_window(sc, view, K, threads):
-    """the bounded sample: a centre window sized so that one oracle step is roughly 10-30 s of CPU work on this host
-    (192x128 first; a fast host re-runs with 4x / 16x the pixels).  -> (estimate, seconds, isects, window)"""
-    win = centre_window(192, 128)
-    est, t_step, n_isect = oracle_full_frame_estimate(sc, view, K, win, threads)
-    for w, h in ((384, 256), (768, 512)):
-        if t_step >= 5.0:
-            break
-        win = centre_window(w, h)
-        est, t_step, n_isect = oracle_full_frame_estimate(sc, view, K, win, threads)
-    return est, t_step, n_isect, win
+def cpu_sample_description(wl, win, views, threads):
+    if win[2] == wl.W and win[3] == wl.H:
+        return f"the full {wl.W}x{wl.H} frame of view(s) {list(views)}, nothing extrapolated"
+    return (f"{win[2]}x{win[3]} centre window (fixed) of the {wl.W}x{wl.H} frame of views {list(views)}, all {wl.n} "
+            f"Gaussians projected; full-frame estimate = per-Gaussian seconds + per-pixel seconds x "
+            f"{wl.W * wl.H / (win[2] * win[3]):.2f}; measured and estimated seconds are separate fields")
 
 
 def run_reference(args):
-    """--impl reference: the CPU oracle port on a bounded sample, rank 0 only."""
+    """--impl reference: the CPU oracle port on the bounded sample, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    steps, warm = args.steps, args.warmup
-    sc, views, Ks, W, H, _ = make_workload(args.gaussians)
-    # window sized so that one sample is 10-30 s of CPU work and (steps + warmup) samples end within a few minutes
+    wl = Workload(args.config, args.gaussians)
+    if wl.kind == "lod":
+        print(json.dumps({"impl": "reference", "unavailable": "configs[3] has no CPU arm (the decode stays PyTorch; "
+                          "its rasterizer part is covered by configs[1])"}), flush=True)
+        return
+    win = centre_window(wl)
+    views = SAMPLE_VIEWS.get(args.config, (0,))
     t_all = time.time()
-    _, _, _, win = pick_window(sc, views[0], Ks[0], threads)
-    ests = []
-    for s in range(warm + steps):
-        v = s % N_VIEWS
-        est, t_step, n_isect = oracle_full_frame_estimate(sc, views[v], Ks[v], win, threads)
-        if s >= warm:
-            ests.append(est)
-        log(f"[reference] step {s}: window {t_step:.2f}s -> full-frame estimate {est:.1f}s ({n_isect} isects)")
-        if time.time() - t_all > 240 and len(ests) >= 1:
+    rows = []
+    budget = 200.0
+    for s in range(args.warmup + args.steps):
+        v = views[s % len(views)]
+        r = oracle_window_step(wl, v, win, threads)
+        log(f"[reference] step {s}: view {v} window {r['t_step']:.2f}s (per-Gaussian part {r['t_gauss']:.2f}s) -> "
+            f"full-frame estimate {r['t_full_est']:.1f}s ({r['n_isects']} isects)")
+        if s >= args.warmup:
+            rows.append((v, r))
+        if time.time() - t_all > budget and len({v for v, _ in rows}) >= len(views):
             log("[reference] time budget reached; stopping early")
             break
-    ms = 1e3 * sum(ests) / len(ests)
-    value = 1e3 / ms
-    sample = (f"{win[2]}x{win[3]} centre window of the 1920x1080 frame, all {sc.n} Gaussians projected; per-pixel cost "
-              f"scaled by {WIDTH * HEIGHT / (win[2] * win[3]):.0f}x, per-Gaussian cost unscaled; mean of {len(ests)} views")
+    # mean over the sample views (each view's repetitions averaged first, so an odd count does not skew it)
+    per_view = {}
+    for v, r in rows:
+        per_view.setdefault(v, []).append(r)
+    est = sum(sum(x["t_full_est"] for x in rs) / len(rs) for rs in per_view.values()) / len(per_view)
+    meas = sum(sum(x["t_step"] for x in rs) / len(rs) for rs in per_view.values()) / len(per_view)
+    value = 1.0 / est
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": args.gpus,
-        "steps": len(ests), "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.gaussians), "views": N_VIEWS, "render_mode": "RGB+ED",
-                   "sh_degree": 2, "note": "gsplat (the reference's rasterizer) is not installable here; this is the "
-                   "repo's CPU oracle port of it (torch, float32)"},
-        "cpu_baseline": {"value": value, "unit": "iters/s", "cores": threads, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": wl.metric, "value": value, "unit": "iters/s", "n_gpus": args.gpus,
+        "steps": len(rows), "warmup": args.warmup, "ms_per_step": 1e3 * est, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl.name, "views": wl.n_views, "render_mode": "RGB+ED", "sh_degree": wl.sh_degree,
+                   "note": "gsplat (the reference's rasterizer) is not installable here; this is the repo's CPU oracle "
+                           "port of it (torch, float32).  value / ms_per_step are the FULL-FRAME estimate; "
+                           "measured_s_per_sample_step is what one timed step actually took"},
+        "cpu_baseline": {"value": value, "unit": "iters/s", "cores": threads, "kind": "port",
+                         "sample": cpu_sample_description(wl, win, views, threads),
+                         "measured_s_per_sample_step": meas, "estimated_s_per_full_frame": est,
+                         "extrapolation_factor_pixels": rows[0][1]["scale"],
+                         "per_view": {str(v): {"measured_s": sum(x["t_step"] for x in rs) / len(rs),
+                                               "per_gaussian_s": sum(x["t_gauss"] for x in rs) / len(rs),
+                                               "estimated_full_frame_s": sum(x["t_full_est"] for x in rs) / len(rs)}
+                                      for v, rs in per_view.items()}},
         "e2e": {"value": value, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_name(n):
-    return f"configs[4]: {n / 1e6:g}M explicit SH2 3DGS Gaussians, {WIDTH}x{HEIGHT}, RGB+ED, 1 view per GPU per step"
+# ------------------------------------------------------------------------------------------------- parity
+def _rel(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def parity_check_explicit(wl: Workload, params, dev, threads):
+    """CUDA path vs the CPU oracle on the fixed sample windows of the BENCHMARKED scene: integer stages bit-exact,
+    image 1e-4 abs (depth channel relative to max(1, |ref|)), the five parameter gradients 1e-3 relative to the
+    tensor's max (north_star tolerances).  Returns (parity dict, the oracle timings for cpu_baseline)."""
+    import horizongs_b200 as hgs
+    win = centre_window(wl)
+    views = SAMPLE_VIEWS.get(wl.config, (0,))
+    res = {"window": list(win), "views": list(views), "tol": {"image_abs": 1e-4, "grad_rel": 1e-3}, "per_view": {}}
+    timings = {}
+    ok_all = True
+    for v in views:
+        o = oracle_window_step(wl, v, win, threads, keep=True)
+        timings[v] = {k: o[k] for k in ("t_step", "t_gauss", "t_full_est", "scale", "n_isects")}
+        K2 = window_K(wl.Ks[v], win).to(dev)
+        for p in params:
+            p.grad = None
+        rc, ra, meta, extra = render_explicit(hgs, wl.kind, params, wl.views[v][None].to(dev), K2[None], win[2], win[3],
+                                              wl.sh_degree, torch.zeros(1, 3, device=dev))
+        meta["means2d"].retain_grad()
+        loss_fn(rc, ra, window_gt(win).to(dev), extra).backward()
+        torch.cuda.synchronize()
+        ints = {k: bool(torch.equal(meta[k].cpu(), o["meta"][k]))
+                for k in ("radii", "tiles_per_gauss", "isect_ids", "flatten_ids", "isect_offsets")}
+        ref_rc = o["rc"]
+        img = float(((rc.detach().cpu() - ref_rc).abs() / ref_rc.abs().clamp(min=1.0)).max())
+        alp = float((ra.detach().cpu() - o["ra"]).abs().max())
+        grads = {n: _rel(p.grad.cpu(), g) for n, p, g in zip(("means", "quats", "scales", "opacities", "colors"),
+                                                             params, o["grads"])}
+        grads["means2d"] = _rel(meta["means2d"].grad.cpu(), o["meta"]["means2d"].grad) if wl.kind != "2dgs" else None
+        row = {"n_isects": o["n_isects"], "n_visible": int((o["meta"]["radii"] > 0).sum()),
+               "max_tile_depth": int(torch.diff(torch.cat([o["meta"]["isect_offsets"].flatten(),
+                                                           torch.tensor([o["n_isects"]])])).max()),
+               "integer_stages_bit_exact": ints, "image_max_err": img, "alpha_max_err": alp, "grad_max_rel": grads}
+        if extra is not None:
+            row["normals_max_err"] = float((extra[0].detach().cpu() - o["extra"][0]).abs().max())
+        ok = all(ints.values()) and img < 1e-4 and alp < 1e-4 and all(g is None or g < 1e-3 for g in grads.values())
+        row["ok"] = ok
+        ok_all = ok_all and ok
+        res["per_view"][str(v)] = row
+        for p in params:
+            p.grad = None
+        del o
+    res["ok"] = ok_all
+    return res, timings
+
+
+def exchange_parity_check(fused, step_plain, step_fused, params, stats, world, dev):
+    """N > 1: one extra step both ways -- the fused backward + exchange against the dense all-reduce of every rank's
+    autograd gradients (and densification statistics); bit-identity of the fused result across ranks."""
+    import torch.distributed as dist
+    N = params[0].shape[0]
+    s = 10_000                                          # a step index outside the timed range; same views both ways
+    # dense reference
+    st_ref = torch.zeros(2, N, device=dev)
+    step_plain(s, st_ref)
+    ref = [p.grad.clone().contiguous() for p in params]
+    for t in ref + [st_ref]:
+        dist.all_reduce(t)
+    for p in params:
+        p.grad = None
+    st_f = torch.zeros(2, N, device=dev)
+    step_fused(s, st_f)
+    torch.cuda.synchronize()
+    worst = 0.0
+    same = True
+    for p, r in zip(params, ref):
+        worst = max(worst, _rel(p.grad, r))
+        g0 = p.grad.clone()
+        dist.broadcast(g0, 0)
+        same = same and bool(torch.equal(g0, p.grad))
+    worst = max(worst, _rel(st_f[0], st_ref[0]))
+    same_den = bool(torch.equal(st_f[1], st_ref[1]))
+    t = torch.tensor([worst, 0.0 if same else 1.0, 0.0 if same_den else 1.0], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    for p in params:
+        p.grad = None
+    return {"max_rel": float(t[0]), "bit_identical": bool(t[1] == 0), "visibility_counts_equal": bool(t[2] == 0),
+            "tol": 1e-3, "ok": bool(t[0] < 1e-3 and t[1] == 0 and t[2] == 0),
+            "what": "fused SH/projection backward + peer-memory exchange vs dense NCCL all-reduce of every rank's autograd "
+                    "gradients and densification statistics, one extra step after the timed region"}
 
 
 # ------------------------------------------------------------------------------------------------- our arm
@@ -230,28 +418,38 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()                                   # fails loudly if the CUDA library is missing
 
-    sc_cpu, views_cpu, Ks_cpu, W, H, gts_cpu = make_workload(args.gaussians)
-    sc = sc_cpu.to(dev)
-    views, Ks = views_cpu.to(dev), Ks_cpu.to(dev)
-    gts = gts_cpu.to(dev)
+    wl = Workload(args.config, args.gaussians)
+    W, H, NV = wl.W, wl.H, wl.n_views
+    views, Ks, gts = wl.views.to(dev), wl.Ks.to(dev), wl.gts.to(dev)
     bg = torch.zeros(1, 3, device=dev)
-    params = [t.requires_grad_() for t in (sc.means, sc.quats, sc.scales, sc.opacities, sc.colors)]
-    N = sc.n
+    if wl.kind == "lod":
+        from tests import lod_harness as LH
+        model = wl.model.to(dev)
+        model.level = model.level.to(dev)
+        params = list(model.parameters())
+        N = wl.n * model.n_offsets
+    else:
+        sc = wl.sc.to(dev)
+        params = [t.requires_grad_() for t in (sc.means, sc.quats, sc.scales, sc.opacities, sc.colors)]
+        N = sc.n
     # densification statistics (scene/basic_model.py:96-144): gradient-norm accumulator and visibility count
     stats = torch.zeros(2, N, device=dev)
     step_stats = torch.zeros(2, N, device=dev) if world > 1 else None
     from horizongs_b200 import distributed as D
-    # gradient exchange (N > 1): sparse all-reduce over NVLink peer memory (csrc/exchange.cu); the dense NCCL
-    # all-reduce stays available (--exchange nccl) and is the fallback if peer memory cannot be mapped
+    # gradient exchange (N > 1): backward fused with the exchange over NVLink peer memory (csrc/exchange_vjp.cu); the
+    # sparse all-reduce (csrc/exchange.cu) and the dense NCCL all-reduce stay available (--exchange peer | nccl)
     peer, fused, exchange, exchange_name = None, None, None, "none (1 GPU)"
+    if world > 1 and wl.kind == "lod":
+        raise SystemExit("configs[3] is a single-GPU bench line")
     if world > 1 and args.exchange in ("peer", "fused"):
         try:
             if args.exchange == "fused":
                 fused = D.FusedBackwardExchange(N, cap_rows=N // 4, device=dev)
-                exchange_name = ("SH / projection backward fused with the exchange over NVLink peer memory (own kernels, "
-                                 "csrc/exchange_vjp.cu): each rank stores the 12-float blend-gradient rows of its visible "
-                                 "Gaussians into every peer's mailbox; every rank then runs the per-Gaussian backward of "
-                                 "all views' rows, summing in rank order, and updates the densification statistics")
+                exchange_name = ("per-Gaussian backward fused with the exchange over NVLink peer memory (own kernels, "
+                                 "csrc/exchange_vjp.cu): each rank runs the camera-specific SH / projection VJP of its own "
+                                 "view and stores one 64-byte record per visible Gaussian into every peer's mailbox; every "
+                                 "rank then expands the rank-one SH part, sums all views' records in rank order "
+                                 "(bit-identical replicas) and updates the densification statistics")
             else:
                 peer = D.PeerGradientExchange((3, 4, 3, 1, 27, 1, 1), N, cap_rows=N // 4, device=dev)
                 exchange_name = ("sparse all-reduce over NVLink peer memory (own kernels, csrc/exchange.cu): each rank "
@@ -281,65 +479,80 @@ def run_ours(args):
         copy_stream.synchronize()
         return float(loss_host[0])
     # pinned host copies for the end-to-end arm
-    gts_pin = gts_cpu.pin_memory()
-    views_pin, Ks_pin = views_cpu.pin_memory(), Ks_cpu.pin_memory()
+    gts_pin = wl.gts.pin_memory()
+    views_pin, Ks_pin = wl.views.pin_memory(), wl.Ks.pin_memory()
 
-    def step(s, e2e=False):
-        v = (rank + s) % N_VIEWS
-        if e2e:
-            # camera first (the forward needs it at once); the 25 MB ground-truth image is copied on a second
-            # stream while the forward runs and joined just before the loss
-            view = views_pin[v:v + 1].to(dev, non_blocking=True)
-            Km = Ks_pin[v:v + 1].to(dev, non_blocking=True)
-            main = torch.cuda.current_stream()
-            copy_stream.wait_stream(main)
-            with torch.cuda.stream(copy_stream):
-                gt = gts_pin[v:v + 1].to(dev, non_blocking=True)
-            gt.record_stream(main)
+    def inputs(s, e2e):
+        v = (rank + s) % NV
+        if not e2e:
+            return views[v:v + 1], Ks[v:v + 1], gts[v:v + 1]
+        # camera first (the forward needs it at once); the ground-truth image is copied on a second stream while the
+        # forward runs and joined just before the loss
+        view = views_pin[v:v + 1].to(dev, non_blocking=True)
+        Km = Ks_pin[v:v + 1].to(dev, non_blocking=True)
+        main = torch.cuda.current_stream()
+        copy_stream.wait_stream(main)
+        with torch.cuda.stream(copy_stream):
+            gt = gts_pin[v:v + 1].to(dev, non_blocking=True)
+        gt.record_stream(main)
+        return view, Km, gt
+
+    def fwd_loss(view, Km, gt, e2e):
+        if wl.kind == "lod":
+            o = LH.render(model, view[0], Km[0], W, H, bg[0], hgs, fused_decode=True)
+            rc = torch.cat([o["render"], o["render_depth"]], 0).permute(1, 2, 0)[None]
+            ra = o["render_alphas"].permute(1, 2, 0)[None]
+            meta, extra = {"means2d": o["viewspace_points"], "radii": o["radii"][None], "visible_ids": None}, None
         else:
-            view, Km, gt = views[v:v + 1], Ks[v:v + 1], gts[v:v + 1]
-        if fused is not None:
-            # N > 1, fused: backward() stops after the blend backward; the SH / projection backward of all ranks'
-            # views, the densification statistics and the exchange are one push + one reduce kernel
-            with fused.deferred():
-                rc, ra, meta = hgs.rasterization(params[0], params[1], params[2], params[3], params[4], view, Km, W, H,
-                                                 sh_degree=2, render_mode="RGB+ED", backgrounds=bg, packed=False)
-                if e2e:
-                    torch.cuda.current_stream().wait_stream(copy_stream)
-                loss = loss_fn(rc, ra, gt)
-                if e2e:
-                    loss_ready.record()
-                loss.backward()
-            fused.finish(*params, grad_accum=stats[0], denom=stats[1])
-            out = read_loss(loss) if e2e else None
-            for p in params:
-                p.grad = None
-            return out
-        rc, ra, meta = hgs.rasterization(params[0], params[1], params[2], params[3], params[4], view, Km, W, H,
-                                         sh_degree=2, render_mode="RGB+ED", backgrounds=bg, packed=False)
-        meta["means2d"].retain_grad()
+            rc, ra, meta, extra = render_explicit(hgs, wl.kind, params, view, Km, W, H, wl.sh_degree, bg)
         if e2e:
             torch.cuda.current_stream().wait_stream(copy_stream)
-        loss = loss_fn(rc, ra, gt)
+        loss = loss_fn(rc, ra, gt, extra)
         if e2e:
             loss_ready.record()
+        return loss, meta
+
+    meta_vis = [None]
+
+    def step_fused(s, st, e2e=False):
+        # N > 1, fused: backward() stops after the blend backward; the SH / projection backward of all ranks' views, the
+        # densification statistics and the exchange are one push + one reduce kernel
+        view, Km, gt = inputs(s, e2e)
+        with fused.deferred():
+            loss, _ = fwd_loss(view, Km, gt, e2e)
+            loss.backward()
+        fused.finish(*params, grad_accum=st[0], denom=st[1])
+        return loss
+
+    def step_plain(s, st, e2e=False):
+        view, Km, gt = inputs(s, e2e)
+        loss, meta = fwd_loss(view, Km, gt, e2e)
+        if wl.kind != "lod":
+            meta["means2d"].retain_grad()
         loss.backward()
-        # densification statistics from the view-space gradient (basic_model.py:131-144), one fused kernel;
-        # computed per view BEFORE the exchange, then summed over ranks together with the gradients
-        if world > 1:
-            step_stats.zero_()
-            Wr.densification_stats_update(meta["means2d"].grad, meta["radii"], W, H, step_stats[0], step_stats[1],
+        # densification statistics from the view-space gradient (basic_model.py:131-144), one fused kernel
+        if wl.kind != "lod":
+            Wr.densification_stats_update(meta["means2d"].grad, meta["radii"], W, H, st[0], st[1],
                                           visible_ids=meta["visible_ids"])
+        meta_vis[0] = meta["visible_ids"]          # work list of the step (the sparse all-reduce needs it)
+        return loss
+
+    def step(s, e2e=False):
+        if fused is not None:
+            loss = step_fused(s, stats, e2e)
+        elif world > 1:
+            # statistics per view BEFORE the exchange, then summed over ranks together with the gradients
+            step_stats.zero_()
+            loss = step_plain(s, step_stats, e2e)
             if peer is not None:
-                peer.exchange([p.grad for p in params] + [step_stats[0], step_stats[1]], meta["visible_ids"])
+                peer.exchange([p.grad for p in params] + [step_stats[0], step_stats[1]], meta_vis[0])
             else:
                 h = dist.all_reduce(step_stats, async_op=True)
                 exchange.wait()                  # gradient all-reduces were started inside backward()
                 h.wait()
             stats.add_(step_stats)
         else:
-            Wr.densification_stats_update(meta["means2d"].grad, meta["radii"], W, H, stats[0], stats[1],
-                                          visible_ids=meta["visible_ids"])
+            loss = step_plain(s, stats, e2e)
         out = read_loss(loss) if e2e else None
         for p in params:
             p.grad = None
@@ -387,12 +600,14 @@ def run_ours(args):
         else:
             stage_ms.setdefault(name, []).append(opened.pop(name).elapsed_time(ev))
     stage_avg = {k: sum(v) / len(v) for k, v in stage_ms.items()}
-    # per-view split of the two blend kernels (step s of the timed loop renders view (rank + warmup + s) % 8)
+    blend_b = "blend2d_bwd" if wl.kind == "2dgs" else "blend3d_bwd"
+    blend_f = "blend2d_fwd" if wl.kind == "2dgs" else "blend3d_fwd"
+    # per-view split of the blend kernels (step s of the timed loop renders view (rank + warmup + s) % n_views)
     stage_by_view = {}
-    for k in ("blend3d_fwd", "blend3d_bwd", "isect_sorted"):
+    for k in (blend_f, blend_b, "isect_sorted"):
         per = {}
         for i, t in enumerate(stage_ms.get(k, [])):
-            per.setdefault((rank + args.warmup + i) % N_VIEWS, []).append(t)
+            per.setdefault((rank + args.warmup + i) % NV, []).append(t)
         stage_by_view[k] = {str(v): round(sum(ts) / len(ts), 4) for v, ts in sorted(per.items())}
     # ---- e2e: host buffers, H2D of camera + ground truth and D2H of the loss inside the timed region
     for s in range(2):
@@ -404,14 +619,28 @@ def run_ours(args):
         fused.check_status()
     clk = clocks.stop() if rank == 0 else None
 
+    # ---- per-rank stage times (N > 1): what the step waits on
+    stage_ranks = None
+    if world > 1:
+        allst = [None] * world
+        dist.all_gather_object(allst, {k: round(v, 4) for k, v in stage_avg.items()})
+        keys = sorted({k for d in allst for k in d})
+        stage_ranks = {k: {"min": min(d.get(k, 0.0) for d in allst), "max": max(d.get(k, 0.0) for d in allst)}
+                       for k in keys}
+
+    # ---- N > 1: parity of the exchange (fused vs dense all-reduce of autograd gradients), outside the timed region
+    exchange_parity = None
+    if fused is not None:
+        exchange_parity = exchange_parity_check(fused, step_plain, step_fused, params, stats, world, dev)
+        fused.check_status()
+
     # ---- forward-only render FPS (reference method: torch.no_grad around render(), render.py:79-83,177)
     with torch.no_grad():
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for s in range(args.steps):
-            v = (rank + s) % N_VIEWS
-            hgs.rasterization(params[0], params[1], params[2], params[3], params[4], views[v:v + 1], Ks[v:v + 1], W, H,
-                              sh_degree=2, render_mode="RGB+ED", backgrounds=bg)
+            view, Km, gt = inputs(s, False)
+            fwd_loss(view, Km, gt, False)
         torch.cuda.synchronize()
         fps = args.steps / (time.perf_counter() - t0)
 
@@ -427,17 +656,20 @@ def run_ours(args):
 
     # ---- data-dependent counts per view (outside any timed region)
     counts = []
-    with torch.no_grad():
-        for v in range(N_VIEWS):
-            rc, ra, meta = hgs.rasterization(params[0], params[1], params[2], params[3], params[4], views[v:v + 1],
-                                             Ks[v:v + 1], W, H, sh_degree=2, render_mode="RGB+ED")
-            pe, pb = Wr.blend3d_pair_stats(meta["means2d"], meta["conics"], meta["opacities"].contiguous(),
-                                           meta["radii"], W, H, 16, meta["isect_offsets"], meta["flatten_ids"])
-            off = meta["isect_offsets"].flatten()
-            depth = torch.diff(torch.cat([off, off.new_tensor([meta["flatten_ids"].numel()])]))
-            counts.append({"view": v, "n_visible": int((meta["radii"] > 0).sum()), "I": int(meta["flatten_ids"].numel()),
-                           "P_eval": pe, "P_blend": pb, "max_tile_depth": int(depth.max())})
-    mean = lambda k: sum(c[k] for c in counts) / len(counts)  # noqa: E731
+    if wl.kind != "lod":
+        with torch.no_grad():
+            for v in range(NV):
+                rc, ra, meta, _ = render_explicit(hgs, wl.kind, params, views[v:v + 1], Ks[v:v + 1], W, H, wl.sh_degree, bg)
+                off = meta["isect_offsets"].flatten()
+                depth = torch.diff(torch.cat([off, off.new_tensor([meta["flatten_ids"].numel()])]))
+                row = {"view": v, "n_visible": int((meta["radii"] > 0).sum()), "I": int(meta["flatten_ids"].numel()),
+                       "max_tile_depth": int(depth.max())}
+                if wl.kind == "3dgs":
+                    pe, pb = Wr.blend3d_pair_stats(meta["means2d"], meta["conics"], meta["opacities"].contiguous(),
+                                                   meta["radii"], W, H, 16, meta["isect_offsets"], meta["flatten_ids"])
+                    row.update(P_eval=pe, P_blend=pb)
+                counts.append(row)
+    mean = lambda k: sum(c[k] for c in counts) / max(1, len(counts))  # noqa: E731
 
     # ---- roofline of the dominant kernel (blend backward): FP32 pipe
     peaks = {}
@@ -457,47 +689,73 @@ def run_ours(args):
             traffic = json.load(open(tpath))
         except Exception:
             traffic = None
-    dom = max((k for k in stage_avg if k.startswith("blend3d")), key=lambda k: stage_avg[k], default=None)
+    dom = max((k for k in stage_avg if k.startswith("blend") and k.endswith(("_fwd", "_bwd"))),
+              key=lambda k: stage_avg[k], default=None)
     roofline = None
-    if dom is not None:
+    if dom is not None and wl.kind == "3dgs" and counts:
         # algorithmic work: sigma/alpha/tests 14 FLOP per evaluated pair; forward blend 12 FLOP and
-        # backward 66 FLOP per blended pair
-        flops = (14 * mean("P_eval") + (66 if dom == "blend3d_bwd" else 12) * mean("P_blend"))
+        # backward 66 FLOP per blended pair.  frac_blended_only counts ONLY pairs that are actually blended at
+        # SURVEY 8(d)'s 80 (bwd) / 26 (fwd) FLOP per pair -- the per-warp cull skips most evaluated pairs
+        bwd = dom == "blend3d_bwd"
+        flops = (14 * mean("P_eval") + (66 if bwd else 12) * mean("P_blend"))
         ach = flops / (stage_avg[dom] * 1e-3) / 1e12
+        ach2 = (80 if bwd else 26) * mean("P_blend") / (stage_avg[dom] * 1e-3) / 1e12
         roofline = {"kernel": dom, "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
-                    "frac": ach / fp32_peak, "traffic": (traffic or {}).get(dom),
+                    "frac": ach / fp32_peak, "frac_blended_pairs_only": ach2 / fp32_peak,
+                    "traffic": (traffic or {}).get(dom),
                     "peak_source": f"2 FLOP x 128 lanes x {n_sm} SMs x {sm_max:.0f} MHz (non-tensor FP32 FMA peak; "
                                    "the path is not a dense contraction, no tensor-core roofline applies)",
                     "avg_launch_ms": stage_avg[dom]}
+    elif dom is not None:
+        roofline = {"kernel": dom, "bound": "fp32", "achieved": None, "peak": fp32_peak, "unit": "TFLOP/s", "frac": None,
+                    "traffic": (traffic or {}).get(dom), "avg_launch_ms": stage_avg[dom],
+                    "note": "pair counts are only instrumented for the 3DGS blend; see profiles/ for the ncu pipe utilisation"}
     roofline_hbm = None
-    if "isect_sorted" in stage_avg:
-        # emit 8 B + 2 tile-bit passes x (4 + 8 + 8) B + finalize (8 + 8 + 4) B per intersection
-        bytes_i = (8 + 2 * 20 + 20) * mean("I")
-        ach = bytes_i / (stage_avg["isect_sorted"] * 1e-3) / 1e9
-        roofline_hbm = {"kernel": "isect_sorted (emit + tile partition + finalize)", "bound": "hbm", "achieved": ach,
-                        "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "peak_source": hbm_src,
-                        "traffic": (traffic or {}).get("isect_sorted"), "avg_launch_ms": stage_avg["isect_sorted"]}
+    if "isect_sorted" in stage_avg and counts:
+        # the ordering stages as a whole (isect_prepare + isect_sorted): algorithmic bytes of gsplat's formulation of the
+        # same result are far larger (152 B x I); ours: depth sort 4 passes x 20 B per visible Gaussian + emit 8 B +
+        # 2 tile-bit passes x 20 B + finalize 20 B per intersection
+        t_ord = stage_avg["isect_sorted"] + stage_avg.get("isect_prepare", 0.0)
+        bytes_i = (8 + 2 * 20 + 20) * mean("I") + 4 * 20 * mean("n_visible") + 8 * N
+        ach = bytes_i / (t_ord * 1e-3) / 1e9
+        roofline_hbm = {"kernel": "ordering stages (isect_prepare + isect_sorted: depth sort, emit, tile partition, "
+                                  "ranges)", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": ach / hbm_peak, "peak_source": hbm_src, "traffic": (traffic or {}).get("isect_sorted"),
+                        "avg_launch_ms": t_ord}
 
-    # ---- CPU baseline on a bounded sample (rank 0, N == 1 only)
-    cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+    # ---- parity on the benchmarked scene + CPU baseline on the same bounded sample (rank 0)
+    parity, cpu_baseline = None, None
+    threads = os.cpu_count() or 1
+    if wl.kind != "lod" and not args.no_cpu_baseline and (world == 1 or args.parity_at_scale):
         t0 = time.time()
-        est, t_step, _, win = pick_window(sc_cpu, views_cpu[0], Ks_cpu[0], threads)
-        cpu_baseline = {"value": 1.0 / est, "unit": "iters/s", "cores": threads, "kind": "port",
-                        "sample": f"view 0, {win[2]}x{win[3]} centre window of the 1920x1080 frame with all {N} Gaussians "
-                                  f"projected ({t_step:.1f}s measured); per-pixel cost scaled to the full frame, "
-                                  f"per-Gaussian cost unscaled; CPU oracle (torch float32), {time.time() - t0:.0f}s of CPU work"}
+        parity, tim = parity_check_explicit(wl, params, dev, threads)
+        win = centre_window(wl)
+        vs = list(tim)
+        est = sum(tim[v]["t_full_est"] for v in vs) / len(vs)
+        meas = sum(tim[v]["t_step"] for v in vs) / len(vs)
+        if world == 1:
+            cpu_baseline = {"value": 1.0 / est, "unit": "iters/s", "cores": threads, "kind": "port",
+                            "sample": cpu_sample_description(wl, win, vs, threads),
+                            "measured_s_per_sample_step": meas, "estimated_s_per_full_frame": est,
+                            "extrapolation_factor_pixels": tim[vs[0]]["scale"],
+                            "per_view": {str(v): {"measured_s": tim[v]["t_step"], "per_gaussian_s": tim[v]["t_gauss"],
+                                                  "estimated_full_frame_s": tim[v]["t_full_est"]} for v in vs},
+                            "cpu_seconds_spent": round(time.time() - t0, 1)}
 
     n_steps = args.steps
     value = world * n_steps / (ms_total * 1e-3)
     h2d = int(gts_pin[0:1].numel() * 4 + 16 * 4 + 9 * 4)
+    sum_stage = sum(stage_avg.values())
     line = {
-        "metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": n_steps, "warmup": args.warmup,
+        "metric": wl.metric, "value": value, "unit": "iters/s", "n_gpus": world, "steps": n_steps, "warmup": args.warmup,
         "ms_per_step": ms_total / n_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(N), "views": N_VIEWS, "render_mode": "RGB+ED", "sh_degree": 2,
-                   "tile_size": 16, "l2": "inputs larger than L2 (912 MB of Gaussian parameters per step; no flush)",
+        "config": {"workload": wl.name, "views": NV, "render_mode": "RGB+ED", "sh_degree": wl.sh_degree,
+                   "tile_size": 16, "loss": LOSS_MODE,
+                   "l2": (f"inputs larger than L2 ({N * 38 * 4 / 1e6:.0f} MB of Gaussian parameters per step; no flush)"
+                          if N * 38 * 4 > 126e6 else
+                          "the view (and with it the set of visible Gaussians and every intermediate) changes every step; "
+                          "parameters + gradients + intermediates of a step exceed L2"),
                    "collective": exchange_name},
         "clocks": clk,
         "e2e": {"value": world * n_steps / (ms_e2e * 1e-3), "unit": "iters/s", "h2d_bytes_per_step": h2d,
@@ -505,9 +763,13 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "render_fps": fps,
         "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline,
-        "stage_ms": stage_avg, "stage_ms_by_view": stage_by_view,
-        "counts": {"mean_n_visible": mean("n_visible"), "mean_I": mean("I"), "mean_P_eval": mean("P_eval"),
-                   "mean_P_blend": mean("P_blend"), "per_view": counts},
+        "parity_check": parity, "exchange_parity": exchange_parity,
+        "stage_ms": stage_avg, "stage_ms_sum": sum_stage, "outside_stage_ms": ms_total / n_steps - sum_stage,
+        "stage_ms_by_view": stage_by_view, "stage_ms_over_ranks": stage_ranks,
+        "counts": ({"mean_n_visible": mean("n_visible"), "mean_I": mean("I"),
+                    "mean_P_eval": mean("P_eval") if wl.kind == "3dgs" else None,
+                    "mean_P_blend": mean("P_blend") if wl.kind == "3dgs" else None, "per_view": counts}
+                   if counts else None),
         "frame_budget": {"ms_per_view": ms_total / n_steps, "within_33.3ms": ms_total / n_steps < 33.3,
                          "within_16.7ms": ms_total / n_steps < 16.7},
     }
@@ -523,8 +785,11 @@ def main():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--gaussians", type=int, default=6_000_000)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=4, choices=[0, 1, 2, 3, 4],
+                    help="index into BASELINE.json configs (default 4: the configuration the metric is quoted on)")
+    ap.add_argument("--gaussians", type=int, default=None, help="override the Gaussian / anchor count of the config")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle legs (parity_check, cpu_baseline)")
+    ap.add_argument("--parity-at-scale", action="store_true", help="N > 1: also run rank 0's oracle parity check")
     ap.add_argument("--exchange", default="fused", choices=["fused", "peer", "nccl"],
                     help="N > 1: per-Gaussian backward fused with the exchange over NVLink peer memory (default), "
                          "sparse all-reduce of the parameter gradients over peer memory, or the dense NCCL all-reduce")

@@ -269,7 +269,7 @@ def test_rasterization_2dgs_pipeline(distloss):
         else:
             assert float(err.max()) < IMG_ATOL, (name, float(err.max()), float((err > IMG_ATOL).float().mean()))
     for name, g, r in zip(("means", "quats", "scales", "opacities", "colors"), cins, ins):
-        assert rel_err(g.grad.cpu(), r.grad) < 5 * GRAD_RTOL, (name, rel_err(g.grad.cpu(), r.grad))
+        assert rel_err(g.grad.cpu(), r.grad) < GRAD_RTOL, (name, rel_err(g.grad.cpu(), r.grad))
     assert cmeta["means2d"].grad is not None and float(cmeta["means2d"].grad.abs().sum()) > 0
 
 
@@ -297,6 +297,36 @@ def test_full_size_properties_1m_1080p():
         # idempotence
         rc3, ra3, _ = hgs.rasterization(*a, V.cuda(), Ks.cuda(), Wd, H, render_mode="RGB+ED")
         assert torch.equal(rc3, rc) and torch.equal(ra3, ra)
+
+
+@pytest.mark.parametrize("view", ["aerial", "street"])
+def test_config1_1m_1080p_window_against_oracle(view):
+    """BASELINE config 1 at FULL size (1M Gaussians, 1920x1080 camera) against the oracle on a 384x256 centre window of
+    the frame (a sub-frustum: same Gaussians, same camera, principal point shifted -- what bench.py's parity_check
+    does on the 6M scene): integer stages bit-exact, image 1e-4, all five parameter gradients and means2d.grad 1e-3."""
+    from horizongs_b200 import scenes
+    sc, V, Ks, Wd, H = scenes.config1(n=1_000_000, view=view)
+    w, h = 384, 256
+    K2 = Ks.clone()
+    K2[0, 0, 2] -= Wd // 2 - w // 2
+    K2[0, 1, 2] -= H // 2 - h // 2
+    wts = [_rand_like(torch.empty(1, h, w, 4), 51), _rand_like(torch.empty(1, h, w, 1), 52)]
+    ins = [t.clone().requires_grad_() for t in (sc.means, sc.quats, sc.scales, sc.opacities, sc.colors)]
+    rc, ra, meta = O.rasterization(*ins, V, K2, w, h, render_mode="RGB+ED")
+    meta["means2d"].retain_grad()
+    ((rc * wts[0]).mean() + (ra * wts[1]).mean()).backward()
+    cins = [t.cuda().requires_grad_() for t in (sc.means, sc.quats, sc.scales, sc.opacities, sc.colors)]
+    crc, cra, cmeta = hgs.rasterization(*cins, V.cuda(), K2.cuda(), w, h, render_mode="RGB+ED")
+    cmeta["means2d"].retain_grad()
+    ((crc * wts[0].cuda()).mean() + (cra * wts[1].cuda()).mean()).backward()
+    assert meta["flatten_ids"].numel() > 50_000
+    for k in ("radii", "tiles_per_gauss", "isect_ids", "flatten_ids", "isect_offsets"):
+        assert torch.equal(cmeta[k].cpu(), meta[k]), k
+    assert img_err(crc, rc) < IMG_ATOL, img_err(crc, rc)
+    assert img_err(cra, ra) < IMG_ATOL, img_err(cra, ra)
+    for name, g, r in zip(("means", "quats", "scales", "opacities", "colors"), cins, ins):
+        assert rel_err(g.grad.cpu(), r.grad) < GRAD_RTOL, (name, rel_err(g.grad.cpu(), r.grad))
+    assert rel_err(cmeta["means2d"].grad.cpu(), meta["means2d"].grad) < GRAD_RTOL
 
 
 # ------------------------------------------------------------------------------------ f2 densification statistics
@@ -374,7 +404,7 @@ def test_blend2d_stage(D, distloss):
     for name, g, r in zip(("v_means2d", "v_ray_transforms", "v_colors", "v_opacities", "v_normals"), got, ref):
         if r is None:
             continue
-        assert rel_err(g.cpu(), r) < 5 * GRAD_RTOL, (name, rel_err(g.cpu(), r))
+        assert rel_err(g.cpu(), r) < GRAD_RTOL, (name, rel_err(g.cpu(), r))
 
 
 # ------------------------------------------------------------------------------------ configs[3]: LOD anchor model
@@ -409,7 +439,7 @@ def test_lod_anchor_model_render_through_adapter_control_flow(two_d, fused):
     assert img_err(go["render_depth"], ro["render_depth"]) < IMG_ATOL
     for (name, pr), (_, pg) in zip(ref_model.named_parameters(), gpu_model.named_parameters()):
         assert pr.grad is not None and pg.grad is not None, name
-        assert rel_err(pg.grad.cpu(), pr.grad) < 5 * GRAD_RTOL, (name, rel_err(pg.grad.cpu(), pr.grad))
+        assert rel_err(pg.grad.cpu(), pr.grad) < GRAD_RTOL, (name, rel_err(pg.grad.cpu(), pr.grad))
     assert go["viewspace_points"].grad is not None
 
 
