@@ -29,12 +29,12 @@ SIGNATURES = {
     "hgs_sh_bwd": (_i, [_i, _i] + [_p] * 6 + [_ll, _p, _p, _i, _i, _i, _i] + [_p] * 3 + [_p]),
     "hgs_isect_count": (_i, [_p, _p, _ll, _i, _i, _i, _p, _p]),
     "hgs_scan_temp_bytes": (_sz, [_ll]),
-    "hgs_isect_prepare_temp_bytes": (_sz, [_ll]),
-    "hgs_isect_sorted_temp_bytes": (_sz, [_ll, _ll]),
+    "hgs_isect_bin_temp_bytes": (_sz, [_ll, _i, _i, _i]),
+    "hgs_isect_bin_bucket_bytes": (_sz, [_ll]),
     "hgs_exclusive_scan_i32": (_i, [_p, _p, _p, _ll, _p, _sz, _p]),
     "hgs_isect_emit": (_i, [_p] * 4 + [_i] * 5 + [_p, _p, _p]),
-    "hgs_isect_prepare": (_i, [_p, _p, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
-    "hgs_isect_sorted": (_i, [_p] * 5 + [_i, _i, _ll, _ll, _i, _i, _i] + [_p] * 4 + [_sz, _p]),
+    "hgs_isect_bin_prepare": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
+    "hgs_isect_bin_sorted": (_i, [_p, _i, _i, _ll, _ll, _ll, _i, _i, _i] + [_p] * 4 + [_sz, _p, _sz, _p]),
     "hgs_isect_offset_encode": (_i, [_p, _ll, _i, _i, _i, _p, _p]),
     "hgs_blend3d_fwd": (_i, [_p] * 6 + [_i] * 6 + [_p, _p, _ll] + [_p] * 3 + [_p]),
     "hgs_blend3d_bwd": (_i, [_p] * 6 + [_i] * 6 + [_p, _p, _ll] + [_p] * 10 + [_p]),
@@ -110,7 +110,7 @@ def lib() -> C.CDLL:
                 fn = getattr(handle, name)
                 fn.restype = res
                 fn.argtypes = args
-            if handle.hgs_abi_version() != 1:
+            if handle.hgs_abi_version() != 2:
                 raise HgsError("libhgs_raster.so ABI version mismatch; rebuild")
             _lib = handle
     return _lib

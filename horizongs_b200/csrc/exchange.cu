@@ -242,8 +242,8 @@ HGS_API int hgs_exchange_push(float* const* tensors_host, const int* widths_host
     ExTensors T;
     if (int e = fill_tensors(T, tensors_host, widths_host, n_tensors)) return e;
     if (ex_bad_geometry(world, rank, n_ids, cap_rows) || n_rows < 0) return HGS_ERR_INVALID_ARG;
-    if (n_rows > cap_rows) return HGS_ERR_WORKSPACE;
     if (n_rows > 0 && ids == nullptr) return HGS_ERR_INVALID_ARG;
+    if (n_rows > cap_rows) n_rows = -1;   // overflow: push no records and a negative row count (see exchange_wait_kernel)
     ExPeers P;
     if (int e = ex_fill_peers(P, mailboxes_host, world, rank)) return e;
     const ExLayout L = make_layout(world, n_ids, cap_rows, T.row);
@@ -265,7 +265,7 @@ HGS_API int hgs_exchange_reduce(float* const* tensors_host, const int* widths_ho
     if (ex_bad_geometry(world, rank, n_ids, cap_rows) || mailbox == nullptr || status_dev == nullptr) return HGS_ERR_INVALID_ARG;
     const ExLayout L = make_layout(world, n_ids, cap_rows, T.row);
     cudaStream_t st = (cudaStream_t)stream;
-    exchange_wait_kernel<<<1, 32, 0, st>>>((const unsigned char*)mailbox, world, step + 1ull, status_dev);
+    exchange_wait_kernel<<<1, 32, 0, st>>>((const unsigned char*)mailbox, L, (int)(step & 1ull), step + 1ull, status_dev);
     HGS_LAUNCH_CHECK();
     const int smem = (int)(sizeof(MergeSmem) + (size_t)EX_IDS * T.row * 4);
     cudaError_t e = cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

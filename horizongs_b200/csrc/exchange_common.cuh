@@ -154,21 +154,28 @@ __device__ __forceinline__ void prefix_block_entries(BlockEntries& E, int world)
 }
 
 // Wait (acquire, system scope) until every source has raised its flag for this step; bounded: a dead peer
-// fails the step (*status = 1) instead of hanging the GPU.  The merge kernel follows in stream order.
-__global__ void exchange_wait_kernel(const unsigned char* mailbox, int world, unsigned long long want,
+// fails the step (*status = 1) instead of hanging the GPU.  A source whose contribution did not fit its slot
+// pushed nothing and a negative row count: *status = 2 on EVERY rank (overflow is a collective outcome, the step
+// counters stay in lock-step).  The merge / reduce kernel follows in stream order.
+#define HGS_EX_TIMEOUT 1
+#define HGS_EX_OVERFLOW 2
+__global__ void exchange_wait_kernel(const unsigned char* mailbox, ExLayout L, int parity, unsigned long long want,
                                      int* __restrict__ status) {
     const int src = threadIdx.x;
-    if (src >= world) return;
+    if (src >= L.world) return;
     const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(mailbox + (size_t)src * EX_FLAG_STRIDE);
-    if (ld_acquire_sys(flag) >= want) return;
-    const unsigned long long t0 = global_timer_ns();
-    while (ld_acquire_sys(flag) < want) {
-        if (global_timer_ns() - t0 > 20000000000ull) {
-            atomicExch(status, 1);
-            return;
+    if (ld_acquire_sys(flag) < want) {
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(flag) < want) {
+            if (global_timer_ns() - t0 > 20000000000ull) {
+                atomicMax(status, HGS_EX_TIMEOUT);
+                return;
+            }
+            __nanosleep(100);
         }
-        __nanosleep(100);
     }
+    const long long rows = __ldcg(reinterpret_cast<const long long*>(mailbox + slot_offset(L, parity, src)));
+    if (rows < 0) atomicMax(status, HGS_EX_OVERFLOW);
 }
 
 

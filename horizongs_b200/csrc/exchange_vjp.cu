@@ -266,7 +266,9 @@ __global__ void __launch_bounds__(VJ_WARPS * 32, 2) vjp_reduce_kernel(
     int* s_first = reinterpret_cast<int*>(s_bits + world * NW);                            // [world][NW]
     float* s_tiles = reinterpret_cast<float*>(s_first + world * NW);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (__ldcg(status) != 0) return;     // a peer never arrived: the host raises
+    // a peer never arrived, or a contribution overflowed its slot: behave as if nobody had pushed anything (all
+    // gradients of this step become zero, the statistics stay) -- the host raises when it reads the status
+    const bool dead = __ldcg(status) != 0;
     const long long id0 = (long long)blockIdx.x * RANGE;
     const int ent0 = blockIdx.x * (RANGE / EX_IDS);
     // ---- set-up: bitmaps (and first-record indices) of the range from every source, cameras
@@ -275,7 +277,7 @@ __global__ void __launch_bounds__(VJ_WARPS * 32, 2) vjp_reduce_kernel(
         const int ent = ent0 + (w >> 3), ww = w & 7;
         unsigned bits = 0u;
         int first = 0;
-        if (ent < L.n_blocks) {
+        if (ent < L.n_blocks && !dead) {
             const unsigned* e = reinterpret_cast<const unsigned*>(mailbox + slot_offset(L, parity, s) + L.ent_off) +
                                 (size_t)ent * EX_ENTRY_WORDS;
             first = (int)__ldcg(e);
@@ -582,8 +584,8 @@ HGS_API int hgs_exchange_vjp_push(int sh_degree, int K, const float* vpack, cons
         return HGS_ERR_INVALID_ARG;
     if (sh_degree >= 0 ? K < (sh_degree + 1) * (sh_degree + 1) : K != 1) return HGS_ERR_INVALID_ARG;
     if (sh_degree >= 1 && coeffs == nullptr) return HGS_ERR_INVALID_ARG;
-    if (n_rows > cap_rows) return HGS_ERR_WORKSPACE;
     if (n_rows > 0 && ids == nullptr) return HGS_ERR_INVALID_ARG;
+    if (n_rows > cap_rows) n_rows = -1;   // overflow: push no records and a negative row count (see exchange_wait_kernel)
     ExPeers P;
     if (int e = ex_fill_peers(P, mailboxes_host, world, rank)) return e;
     const ExLayout L = make_layout(world, n_ids, cap_rows, VJ_ROW);
@@ -615,7 +617,7 @@ HGS_API int hgs_exchange_vjp_reduce(int sh_degree, int K, const float* means, lo
     if ((reinterpret_cast<size_t>(v_quats) & 15) || (reinterpret_cast<size_t>(v_coeffs) & 15)) return HGS_ERR_INVALID_ARG;
     const ExLayout L = make_layout(world, n_ids, cap_rows, VJ_ROW);
     cudaStream_t st = (cudaStream_t)stream;
-    exchange_wait_kernel<<<1, 32, 0, st>>>((const unsigned char*)mailbox, world, step + 1ull, status_dev);
+    exchange_wait_kernel<<<1, 32, 0, st>>>((const unsigned char*)mailbox, L, (int)(step & 1ull), step + 1ull, status_dev);
     HGS_LAUNCH_CHECK();
     const unsigned char* mb = (const unsigned char*)mailbox;
     const int parity = (int)(step & 1ull);
@@ -645,8 +647,8 @@ HGS_API int hgs_exchange_vjp_push_2dgs(int sh_degree, int K, const float* vpack2
         return HGS_ERR_INVALID_ARG;
     if (sh_degree >= 0 ? K < (sh_degree + 1) * (sh_degree + 1) : K != 1) return HGS_ERR_INVALID_ARG;
     if (sh_degree >= 1 && coeffs == nullptr) return HGS_ERR_INVALID_ARG;
-    if (n_rows > cap_rows) return HGS_ERR_WORKSPACE;
     if (n_rows > 0 && ids == nullptr) return HGS_ERR_INVALID_ARG;
+    if (n_rows > cap_rows) n_rows = -1;   // overflow: push no records and a negative row count (see exchange_wait_kernel)
     ExPeers P;
     if (int e = ex_fill_peers(P, mailboxes_host, world, rank)) return e;
     const ExLayout L = make_layout(world, n_ids, cap_rows, VJ_ROW);

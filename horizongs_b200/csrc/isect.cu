@@ -2,24 +2,23 @@
 // against oracle/gsplat_oracle.py::isect_tiles / isect_offset_encode (= gsplat isect_tiles(sort=True)
 // + isect_offset_encode as reached inside gsplat.rasterization*, reference render.py:40,62).
 //
-// B200-first ordering.  gsplat emits I (key,value) pairs Gaussian-major and runs a generic
-// 64-bit LSD radix sort over 32 + tile_bits + cam_bits key bits (6 passes x 24 B r/w per pair).
-// The same order is produced here with far less HBM traffic:
-//   1. compact the Gaussians that touch at least one tile (typically 10-20 % of a large scene) and
-//      depth-order them once (u32 key = depth bits, 4 stable 8-bit passes, plus a camera pass when C > 1);
-//   2. emit the pairs in that order, one thread per intersection (fully coalesced writes): pairs are already
-//      depth-ordered, ties in flat-index order;
-//   3. stable-partition the I pairs by (cam, tile) only: ceil((tile_bits+cam_bits)/8) passes of 8 B pairs.
-// A stable sort on (cam, tile) of a sequence ordered by (depth, flat index) is exactly the stable sort
-// on the full cam|tile|depth key of the Gaussian-major sequence: within one tile a Gaussian appears once,
-// so ties on the full key are ties on depth between different Gaussians and both orders break them by
-// ascending flat index.
-//
-// Radix pass = 3 launches (chunk histogram, per-digit row scan, chunk scatter); no inter-block waiting.
-// Element counts that are only known on the device (visible Gaussians) are read from device memory by
-// over-provisioned grids, so phase 1 needs no host round trip.  The scatter re-orders each 2048-pair tile in
-// shared memory so that global writes are contiguous runs per digit.
-// Roofline: HBM.  Per pass 4 B (hist) + 8 B + 8 B per pair.
+// B200-first ordering.  gsplat emits I (key,value) pairs Gaussian-major and runs a generic 64-bit LSD radix
+// sort over 32 + tile_bits + cam_bits key bits (6 passes x 24 B r/w per pair through HBM).  The same order is
+// produced here by BINNING, with every pair crossing memory twice and the sort itself on the SM:
+//   1. bin_count:   one pass over tiles_per_gauss: ordered compaction of the Gaussians that touch a tile
+//                   (single-pass scan, decoupled look-back) + histogram of the (camera, tile) bins;
+//   2. tile_scan:   exclusive scan of the histogram = the per-tile ranges (isect_offsets, the a10 output);
+//   3. bin_scatter: every visible Gaussian drops (depth bits << 32 | flat index) into its tiles' ranges
+//                   (slot by atomic cursor: arrival order is arbitrary);
+//   4. tile_sort:   one CTA per (camera, tile) sorts its range by the 64-bit (depth, flat index) key -- a
+//                   bitonic network held in registers (blocked, 1..16 keys per thread), exchanged by warp
+//                   shuffles and, for the widest strides only, through shared memory -- and writes
+//                   isect_ids / flatten_ids.  Ranges longer than 4096 are sorted in 4096-key chunks and merged
+//                   by the same network with the widest strides through (L2-resident) global memory.
+// Within a tile the keys (depth bits, flat index) are unique, so the sorted order does not depend on the
+// arrival order: it is the stable ascending sort of gsplat's cam|tile|depth keys over the Gaussian-major
+// emission (ties on depth are broken by ascending flat index in both).
+// Roofline: HBM for steps 1-3 (16 B per Gaussian + 8 B per pair), shuffle / issue for step 4.
 #include "hgs_common.cuh"
 #include "hgs_constants.cuh"
 #include "../../include/hgs_raster.h"
@@ -28,47 +27,14 @@ namespace {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 8;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 2048 pairs per block iteration
-constexpr int RADIX = 256;
-constexpr int RS_MAX_CHUNKS = 148 * 4;
 constexpr int SCAN_THREADS = 1024;
-constexpr int CP_TILE = 1024;  // elements per block in the compaction kernels
+constexpr int CP_TILE = 1024;  // elements per block in the compaction kernel
 
-struct DigitSpec {
-    int shift;
-    uint32_t mask;
-    int from_val_div;  // 0: digit from key; >0: digit from (val / from_val_div)
-};
-__device__ __forceinline__ uint32_t digit_of(const DigitSpec& ds, uint32_t key, uint32_t val) {
-    uint32_t src = ds.from_val_div > 0 ? (val / (uint32_t)ds.from_val_div) : key;
-    return (src >> ds.shift) & ds.mask;
-}
-
-// lanes of the warp holding the same 8-bit digit (fixed cost: 8 ballots; __match_any_sync degrades to one
-// iteration per distinct value, i.e. 32 iterations on the low tile-id byte)
-__device__ __forceinline__ unsigned peers_of(uint32_t d) {
-    unsigned peers = 0xFFFFFFFFu;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const unsigned b = __ballot_sync(0xFFFFFFFFu, (d >> k) & 1u);
-        peers &= ((d >> k) & 1u) ? b : ~b;
-    }
-    return peers;
-}
-
-// chunk c of a pass over n elements with gridDim.x chunks: [begin, end)
-__device__ __forceinline__ void chunk_range(long long n, long long& begin, long long& end) {
-    const long long tiles = (n + RS_TILE - 1) / RS_TILE;
-    const long long tpc = (tiles + gridDim.x - 1) / gridDim.x;
-    begin = (long long)blockIdx.x * tpc * RS_TILE;
-    end = begin + tpc * RS_TILE;
-    if (end > n) end = n;
-}
-static int n_chunks_for(long long cap) {
-    long long tiles = (cap + RS_TILE - 1) / RS_TILE;
-    if (tiles < 1) tiles = 1;
-    return (int)(tiles < RS_MAX_CHUNKS ? tiles : RS_MAX_CHUNKS);
+static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+static int n_bits_of(long long n) {  // floor(log2(n)) + 1 for n >= 1
+    int b = 0;
+    while (n > 0) { ++b; n >>= 1; }
+    return b;
 }
 
 // block-wide exclusive scan of one value per thread (RS_THREADS threads); returns the exclusive prefix and
@@ -93,162 +59,6 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp
     __syncthreads();
     total = tot;
     return wbase + incl - v;
-}
-
-__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint32_t* __restrict__ keys,
-                                                                const uint32_t* __restrict__ vals,
-                                                                const long long* __restrict__ n_dev, DigitSpec ds,
-                                                                uint32_t* __restrict__ hist) {
-    __shared__ uint32_t s_hist[RADIX];
-    for (int i = threadIdx.x; i < RADIX; i += RS_THREADS) s_hist[i] = 0;
-    __syncthreads();
-    long long begin, end;
-    chunk_range(*n_dev, begin, end);
-    for (long long base = begin; base < end; base += RS_TILE) {
-        // 8 independent loads in flight per thread, then warp-aggregated shared-memory increments
-        uint32_t d[RS_ITEMS];
-        bool valid[RS_ITEMS];
-#pragma unroll
-        for (int k = 0; k < RS_ITEMS; ++k) {
-            const long long i = base + k * RS_THREADS + threadIdx.x;
-            valid[k] = i < end;
-            d[k] = valid[k] ? digit_of(ds, keys[i], ds.from_val_div > 0 ? vals[i] : 0u) : 0u;
-        }
-#pragma unroll
-        for (int k = 0; k < RS_ITEMS; ++k) {
-            const unsigned vmask = __ballot_sync(0xFFFFFFFFu, valid[k]);   // invalid lanes leave the peer sets
-            const unsigned m = peers_of(d[k]) & vmask;
-            const int leader = __ffs(m) - 1;
-            if (valid[k] && (int)(threadIdx.x & 31) == leader) atomicAdd(&s_hist[d[k]], (uint32_t)__popc(m));
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < RADIX; i += RS_THREADS) hist[(long long)i * gridDim.x + blockIdx.x] = s_hist[i];
-}
-
-// hist is [RADIX][n_chunks]: block d turns row d into its exclusive scan (over chunks) and writes the row total
-__global__ void __launch_bounds__(RS_THREADS) radix_rowscan_kernel(uint32_t* __restrict__ hist, int n_chunks,
-                                                                   uint32_t* __restrict__ rowsum) {
-    __shared__ uint32_t s_warp[RS_WARPS];
-    uint32_t* row = hist + (long long)blockIdx.x * n_chunks;
-    uint32_t carry = 0;
-    for (int base = 0; base < n_chunks; base += RS_THREADS) {
-        const int i = base + threadIdx.x;
-        const uint32_t v = i < n_chunks ? row[i] : 0u;
-        uint32_t tot;
-        const uint32_t ex = block_excl_scan(v, s_warp, tot);
-        if (i < n_chunks) row[i] = carry + ex;
-        carry += tot;
-    }
-    if (threadIdx.x == 0) rowsum[blockIdx.x] = carry;
-}
-
-__global__ void __launch_bounds__(RS_THREADS, 4) radix_scatter_kernel(
-    const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
-    uint32_t* __restrict__ vals_out, const long long* __restrict__ n_dev, DigitSpec ds,
-    const uint32_t* __restrict__ hist_scanned, const uint32_t* __restrict__ rowsum) {
-    __shared__ uint32_t s_base[RADIX];    // running global position of the next element of digit d (this chunk)
-    __shared__ uint32_t s_start[RADIX];   // first local sorted index of digit d inside the current tile
-    __shared__ uint32_t s_delta[RADIX];   // global position - local sorted index for digit d (mod 2^32)
-    __shared__ uint32_t s_whist[RS_WARPS][RADIX];
-    __shared__ uint32_t s_warp[RS_WARPS];
-    __shared__ uint32_t s_key[RS_TILE];
-    __shared__ uint32_t s_val[RS_TILE];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    {
-        // global base of digit d = sum of the totals of smaller digits + this chunk's offset inside digit d
-        uint32_t tot;
-        const uint32_t digit_base = block_excl_scan(rowsum[threadIdx.x], s_warp, tot);
-        s_base[threadIdx.x] = digit_base + hist_scanned[(long long)threadIdx.x * gridDim.x + blockIdx.x];
-    }
-    long long begin, end;
-    chunk_range(*n_dev, begin, end);
-
-    for (long long tile = begin; tile < end; tile += RS_TILE) {
-        uint32_t key[RS_ITEMS], val[RS_ITEMS], dig[RS_ITEMS], rank[RS_ITEMS];
-#pragma unroll
-        for (int i = 0; i < RS_ITEMS; ++i) {
-            long long idx = tile + warp * (RS_ITEMS * 32) + i * 32 + lane;
-            const bool valid = idx < end;
-            key[i] = valid ? keys_in[idx] : 0xFFFFFFFFu;
-            val[i] = valid ? vals_in[idx] : 0u;
-            // padding sorts last inside the tile (largest digit, highest index) and is never written out
-            dig[i] = valid ? digit_of(ds, key[i], val[i]) : (uint32_t)(RADIX - 1);
-        }
-#pragma unroll
-        for (int i = 0; i < RADIX / 32; ++i) s_whist[warp][i * 32 + lane] = 0;
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < RS_ITEMS; ++i) {
-            const unsigned m = peers_of(dig[i]);
-            rank[i] = s_whist[warp][dig[i]] + (uint32_t)__popc(m & lt_mask);
-            __syncwarp();
-            if (lane == __ffs(m) - 1) s_whist[warp][dig[i]] += (uint32_t)__popc(m);
-            __syncwarp();
-        }
-        __syncthreads();
-        uint32_t cnt_d = 0;
-        {
-            // thread d: exclusive prefix over warps inside digit d, and the tile's count of digit d
-            const int d = threadIdx.x;  // RS_THREADS == RADIX
-#pragma unroll
-            for (int w = 0; w < RS_WARPS; ++w) {
-                uint32_t t = s_whist[w][d];
-                s_whist[w][d] = cnt_d;
-                cnt_d += t;
-            }
-        }
-        uint32_t tot;
-        const uint32_t start_d = block_excl_scan(cnt_d, s_warp, tot);  // contains __syncthreads
-        s_start[threadIdx.x] = start_d;
-        s_delta[threadIdx.x] = s_base[threadIdx.x] - start_d;
-        s_base[threadIdx.x] += cnt_d;
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < RS_ITEMS; ++i) {
-            const uint32_t q = s_start[dig[i]] + s_whist[warp][dig[i]] + rank[i];
-            s_key[q] = key[i];
-            s_val[q] = val[i];
-        }
-        __syncthreads();
-        const long long rem = end - tile;
-        const int n_valid = (int)(rem < RS_TILE ? rem : RS_TILE);
-#pragma unroll
-        for (int i = 0; i < RS_ITEMS; ++i) {
-            const int q = i * RS_THREADS + threadIdx.x;
-            if (q < n_valid) {
-                const uint32_t k = s_key[q], v = s_val[q];
-                const uint32_t pos = s_delta[digit_of(ds, k, v)] + (uint32_t)q;
-                keys_out[pos] = k;
-                vals_out[pos] = v;
-            }
-        }
-        __syncthreads();
-    }
-}
-static_assert(RS_THREADS == RADIX, "one thread per digit in the warp-prefix step");
-
-// one stable LSD pass: (keys_in, vals_in) -> (keys_out, vals_out); n lives on the device, cap bounds it
-static int radix_pass(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
-                      const long long* n_dev, long long cap, DigitSpec ds, uint32_t* hist, cudaStream_t st) {
-    const int nc = n_chunks_for(cap);
-    radix_hist_kernel<<<nc, RS_THREADS, 0, st>>>(keys_in, vals_in, n_dev, ds, hist);
-    HGS_LAUNCH_CHECK();
-    uint32_t* rowsum = hist + (size_t)RADIX * RS_MAX_CHUNKS;
-    radix_rowscan_kernel<<<RADIX, RS_THREADS, 0, st>>>(hist, nc, rowsum);
-    HGS_LAUNCH_CHECK();
-    radix_scatter_kernel<<<nc, RS_THREADS, 0, st>>>(keys_in, vals_in, keys_out, vals_out, n_dev, ds, hist, rowsum);
-    HGS_LAUNCH_CHECK();
-    return 0;
-}
-constexpr size_t HIST_BYTES = ((size_t)RADIX * RS_MAX_CHUNKS + RADIX) * sizeof(uint32_t);  // + row totals
-
-static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
-static int n_bits_of(long long n) {  // floor(log2(n)) + 1 for n >= 1
-    int b = 0;
-    while (n > 0) { ++b; n >>= 1; }
-    return b;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -408,150 +218,573 @@ __global__ void isect_emit_kernel(const float* __restrict__ means2d, const int32
         }
 }
 
-// ---- compaction of the Gaussians that touch at least one tile (order-preserving) ---------------------
-__global__ void __launch_bounds__(RS_THREADS) vis_count_kernel(const int32_t* __restrict__ tiles_per_gauss,
-                                                               long long CN, long long* __restrict__ blk_count) {
-    __shared__ long long s_tmp[RS_THREADS / 32];
-    const long long base = (long long)blockIdx.x * CP_TILE;
-    long long c = 0;
-#pragma unroll
-    for (int i = 0; i < CP_TILE / RS_THREADS; ++i) {
-        const long long idx = base + i * RS_THREADS + threadIdx.x;
-        if (idx < CN && tiles_per_gauss[idx] > 0) ++c;
+// =============================================================================================
+// sorted path by binning (see the header comment)
+// =============================================================================================
+constexpr int ST = 2;                            // tiles per side of a super-tile (the binning / sorting unit)
+constexpr int ST2 = ST * ST;
+constexpr int SUB = 4;                           // sub-bins per super-tile (by flat index): spreads the atomics
+constexpr int PAD = 32;                          // u32 slots per atomic counter: one 128-byte line each (the L2 serialises
+                                                 // atomics per line, not per address)
+constexpr int BIG_AREA = 16;                     // Gaussians covering more tiles are spread over the whole CTA
+#define LB_AGG (1ull << 62)      // look-back flag: block aggregate published
+#define LB_PREFIX (2ull << 62)   // look-back flag: inclusive prefix published
+#define LB_MASK ((1ull << 62) - 1)
+#define KEY_INF (~0ull)
+constexpr int SORT_CHUNK = 2048;                 // keys one CTA sorts in registers (8 per thread)
+constexpr int ID_BITS = 28;                      // sort key = depth bits << 32 | flat index << 4 | tile mask
+static_assert(ST2 <= 4, "the tile mask of a key is 4 bits");
+
+// what the later kernels need to know about a visible Gaussian (written once, in work-list order)
+struct __align__(16) VisRec {
+    uint32_t g, depth_bits;
+    uint32_t xy0, xy1;       // tile box: x0 | y0 << 16,  x1 | y1 << 16
+};
+
+struct BinGeom {
+    int N, tile_w, tile_h, stw, sth;             // stw x sth super-tiles per camera
+    float tile_size, inv_tile_size;              // inv_tile_size > 0: tile_size is a power of two (x / ts == x * inv)
+};
+
+// tile box [x0, x1) x [y0, y1) of a visible Gaussian: hgs_tile_bbox's arithmetic (a power-of-two tile size
+// divides exactly by multiplication)
+__device__ __forceinline__ void tile_box(const BinGeom& G, const float* __restrict__ means2d,
+                                         const int32_t* __restrict__ radii, long long g, int& x0, int& y0, int& x1,
+                                         int& y1) {
+    const float2 m = reinterpret_cast<const float2*>(means2d)[g];
+    const float r = (float)radii[g];
+    if (G.inv_tile_size > 0.f) {
+        const float tr = r * G.inv_tile_size, tx = m.x * G.inv_tile_size, ty = m.y * G.inv_tile_size;
+        x0 = (int)fminf(fmaxf(floorf(tx - tr), 0.f), (float)G.tile_w);
+        y0 = (int)fminf(fmaxf(floorf(ty - tr), 0.f), (float)G.tile_h);
+        x1 = (int)fminf(fmaxf(ceilf(tx + tr), 0.f), (float)G.tile_w);
+        y1 = (int)fminf(fmaxf(ceilf(ty + tr), 0.f), (float)G.tile_h);
+    } else {
+        hgs_tile_bbox(m.x, m.y, r, G.tile_size, G.tile_w, G.tile_h, x0, y0, x1, y1);
     }
-    const long long tot = block_reduce_ll(c, s_tmp);
-    if (threadIdx.x == 0) blk_count[blockIdx.x] = tot;
 }
 
-__global__ void __launch_bounds__(RS_THREADS) compact_kernel(const float* __restrict__ depths,
-                                                             const int32_t* __restrict__ tiles_per_gauss, long long CN,
-                                                             const long long* __restrict__ blk_base,
-                                                             uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                                                             int32_t* __restrict__ visible_ids) {
+// ---- phase 1a: ordered compaction of the Gaussians with tiles + super-tile histogram --------------------
+__global__ void __launch_bounds__(RS_THREADS) bin_count_kernel(
+    const float* __restrict__ means2d, const int32_t* __restrict__ radii, const float* __restrict__ depths,
+    const int32_t* __restrict__ tiles_per_gauss, long long CN, BinGeom G, int nblk,
+    unsigned long long* __restrict__ flags, uint32_t* __restrict__ ticket, uint32_t* __restrict__ super_count,
+    int32_t* __restrict__ visible_ids, VisRec* __restrict__ vrec, long long* __restrict__ counts_dev) {
     __shared__ uint32_t s_warp[RS_WARPS];
+    __shared__ uint32_t s_bid, s_nbig;
+    __shared__ unsigned long long s_excl, s_isect;
+    __shared__ uint32_t s_list[CP_TILE];
+    __shared__ uint2 s_box[CP_TILE];
+    __shared__ uint32_t s_big[CP_TILE];
+    if (threadIdx.x == 0) {
+        s_bid = atomicAdd(ticket, 1u);   // logical block id = start order: every predecessor is already running
+        s_nbig = 0;
+        s_isect = 0;
+    }
+    __syncthreads();
+    const uint32_t bid = s_bid;
     constexpr int PER = CP_TILE / RS_THREADS;  // 4 consecutive elements per thread (order preserving)
-    const long long first = (long long)blockIdx.x * CP_TILE + (long long)threadIdx.x * PER;
-    bool vis[PER];
+    const long long first = (long long)bid * CP_TILE + (long long)threadIdx.x * PER;
+    int tcount[PER];
+    if (first + PER <= CN && (reinterpret_cast<uintptr_t>(tiles_per_gauss) & 15) == 0) {
+        const int4 q = *reinterpret_cast<const int4*>(tiles_per_gauss + first);
+        tcount[0] = q.x; tcount[1] = q.y; tcount[2] = q.z; tcount[3] = q.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < PER; ++i) tcount[i] = first + i < CN ? tiles_per_gauss[first + i] : 0;
+    }
     uint32_t cnt = 0;
+    unsigned long long isects = 0;
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
-        const long long idx = first + i;
-        vis[i] = idx < CN && tiles_per_gauss[idx] > 0;
-        cnt += vis[i] ? 1u : 0u;
+        cnt += tcount[i] > 0 ? 1u : 0u;
+        isects += tcount[i] > 0 ? (unsigned long long)tcount[i] : 0ull;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) isects += __shfl_xor_sync(0xFFFFFFFFu, isects, o);
+    if ((threadIdx.x & 31) == 0 && isects) atomicAdd(&s_isect, isects);
     uint32_t tot;
     uint32_t pos = block_excl_scan(cnt, s_warp, tot);
-    const long long out0 = blk_base[blockIdx.x];
 #pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        if (vis[i]) {
-            const long long idx = first + i;
-            keys[out0 + pos] = (uint32_t)__float_as_int(depths[idx]);
-            vals[out0 + pos] = (uint32_t)idx;
-            if (visible_ids != nullptr) visible_ids[out0 + pos] = (int32_t)idx;
-            ++pos;
-        }
-    }
-}
-
-__global__ void gather_counts_kernel(const uint32_t* __restrict__ vals, const int32_t* __restrict__ tiles_per_gauss,
-                                     const long long* __restrict__ n_dev, int32_t* __restrict__ order,
-                                     int32_t* __restrict__ cnt_sorted) {
-    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= *n_dev) return;
-    uint32_t g = vals[j];
-    order[j] = (int32_t)g;
-    cnt_sorted[j] = tiles_per_gauss[g];
-}
-
-// ---- depth-ordered emission, one thread per intersection ----------------------------------------------
-// Block b owns emissions [b*RS_TILE, (b+1)*RS_TILE): it locates the (at most RS_TILE) sorted Gaussians that
-// produce them, stages their tile boxes in shared memory and lets every thread binary-search its Gaussian.
-__global__ void __launch_bounds__(RS_THREADS) emit_sorted_kernel(
-    const float* __restrict__ means2d, const int32_t* __restrict__ radii, const int32_t* __restrict__ order,
-    const int32_t* __restrict__ cum_sorted, long long n_vis, long long n_isects, int N, int tile_size, int tile_w,
-    int tile_h, int tile_bits, uint32_t* __restrict__ tkeys, uint32_t* __restrict__ vals) {
-    __shared__ int s_cum[RS_TILE];
-    __shared__ uint32_t s_g[RS_TILE];
-    __shared__ uint32_t s_xy[RS_TILE];   // y0 << 16 | x0
-    __shared__ int s_w[RS_TILE];
-    __shared__ long long s_j[2];
-    const long long e0 = (long long)blockIdx.x * RS_TILE;
-    long long e1 = e0 + RS_TILE;
-    if (e1 > n_isects) e1 = n_isects;
-    if (threadIdx.x < 64) {
-        // warp 0 / warp 1: last j with cum_sorted[j] <= target, 32-ary search (cum_sorted[0] == 0 <= target)
-        const int lane = threadIdx.x & 31;
-        const long long target = threadIdx.x < 32 ? e0 : e1 - 1;
-        long long lo = 0, hi = n_vis;                       // answer in [lo, hi)
-        while (hi - lo > 32) {
-            const long long step = (hi - lo + 31) >> 5;
-            const long long idx = lo + lane * step;
-            const bool le = idx < hi && (long long)cum_sorted[idx] <= target;
-            const int p = __popc(__ballot_sync(0xFFFFFFFFu, le));   // >= 1: probes are sorted, lane 0 is true
-            const long long nlo = lo + (long long)(p - 1) * step;
-            const long long nhi = lo + (long long)p * step;
-            lo = nlo;
-            hi = nhi < hi ? nhi : hi;
-        }
-        const long long idx = lo + lane;
-        const bool le = idx < hi && (long long)cum_sorted[idx] <= target;
-        const int p = __popc(__ballot_sync(0xFFFFFFFFu, le));
-        if (lane == 0) s_j[threadIdx.x >> 5] = lo + p - 1;
+    for (int i = 0; i < PER; ++i)
+        if (tcount[i] > 0) s_list[pos++] = (uint32_t)(first + i);
+    // publish the block total at once; the prefix of the earlier blocks is only needed for the final writes
+    if (threadIdx.x == 0) {
+        volatile unsigned long long* vf = flags;
+        vf[bid] = (bid == 0 ? LB_PREFIX : LB_AGG) | (unsigned long long)tot;
     }
     __syncthreads();
-    const long long j0 = s_j[0];
-    const int nj = (int)(s_j[1] - j0 + 1);   // <= RS_TILE: every compacted Gaussian emits at least once
-    for (int j = threadIdx.x; j < nj; j += RS_THREADS) {
-        const uint32_t g = (uint32_t)order[j0 + j];
-        const float2 m = reinterpret_cast<const float2*>(means2d)[g];
+    // the block's visible Gaussians: tile boxes, histogram of the super-tiles they touch
+    const int n_super = G.stw * G.sth;
+    for (uint32_t i = threadIdx.x; i < tot; i += RS_THREADS) {
+        const uint32_t g = s_list[i];
         int x0, y0, x1, y1;
-        hgs_tile_bbox(m.x, m.y, (float)radii[g], (float)tile_size, tile_w, tile_h, x0, y0, x1, y1);
-        s_cum[j] = cum_sorted[j0 + j];
-        s_g[j] = g;
-        s_xy[j] = ((uint32_t)y0 << 16) | (uint32_t)x0;
-        s_w[j] = x1 - x0;
+        tile_box(G, means2d, radii, g, x0, y0, x1, y1);
+        s_box[i] = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));
+        const int sx0 = x0 / ST, sy0 = y0 / ST, sx1 = (x1 - 1) / ST, sy1 = (y1 - 1) / ST;
+        if ((sx1 - sx0 + 1) * (sy1 - sy0 + 1) > BIG_AREA) {
+            s_big[atomicAdd(&s_nbig, 1u)] = i;
+            continue;
+        }
+        uint32_t* srow = super_count + (((long long)(g / (uint32_t)G.N) * n_super) * SUB + (g % SUB)) * PAD;
+        for (int y = sy0; y <= sy1; ++y)
+            for (int x = sx0; x <= sx1; ++x) atomicAdd(srow + (long long)(y * G.stw + x) * (SUB * PAD), 1u);
     }
     __syncthreads();
+    const uint32_t nbig = s_nbig;
+    for (uint32_t b = 0; b < nbig; ++b) {
+        const uint32_t i = s_big[b], g = s_list[i];
+        const uint2 bx = s_box[i];
+        const int sx0 = (int)(bx.x & 0xFFFFu) / ST, sy0 = (int)(bx.x >> 16) / ST;
+        const int sw = ((int)(bx.y & 0xFFFFu) - 1) / ST - sx0 + 1, sarea = sw * (((int)(bx.y >> 16) - 1) / ST - sy0 + 1);
+        uint32_t* srow = super_count + (((long long)(g / (uint32_t)G.N) * n_super) * SUB + (g % SUB)) * PAD;
+        for (int k = threadIdx.x; k < sarea; k += RS_THREADS)
+            atomicAdd(srow + (long long)((sy0 + k / sw) * G.stw + sx0 + k % sw) * (SUB * PAD), 1u);
+    }
+    if (threadIdx.x < 32) {
+        // decoupled look-back (warp 0): exclusive prefix of the block totals of all earlier blocks
+        const int lane = threadIdx.x;
+        volatile unsigned long long* vf = flags;
+        unsigned long long excl = 0;
+        if (bid > 0) {
+            long long j = (long long)bid - 1;
+            while (true) {
+                const long long idx = j - lane;
+                unsigned long long v;
+                do {
+                    v = idx >= 0 ? vf[idx] : LB_PREFIX;
+                } while (__any_sync(0xFFFFFFFFu, (v >> 62) == 0));
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2);
+                const int stop = m ? __ffs(m) - 1 : 31;      // nearest predecessor that already knows its prefix
+                unsigned long long c = lane <= stop ? (v & LB_MASK) : 0ull;
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
-        const long long e = e0 + i * RS_THREADS + threadIdx.x;
-        if (e < e1) {
-            int lo = 0, hi = nj - 1;
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                if ((long long)s_cum[mid] <= e) lo = mid; else hi = mid - 1;
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+                excl += c;
+                if (m) break;
+                j -= 32;
             }
-            const int k = (int)(e - s_cum[lo]);
-            const int w = s_w[lo];
-            const uint32_t xy = s_xy[lo];
-            const int y = (int)(xy >> 16) + k / w, x = (int)(xy & 0xFFFFu) + k % w;
-            const uint32_t g = s_g[lo];
-            tkeys[e] = ((g / (uint32_t)N) << tile_bits) | (uint32_t)(y * tile_w + x);
-            vals[e] = g;
+            if (lane == 0) vf[bid] = LB_PREFIX | (excl + tot);
+        }
+        if (lane == 0) {
+            s_excl = excl;
+            if ((int)bid == nblk - 1) counts_dev[0] = (long long)(excl + tot);
+            if (s_isect) atomicAdd(reinterpret_cast<unsigned long long*>(counts_dev + 1), s_isect);
+        }
+    }
+    __syncthreads();
+    const long long out0 = (long long)s_excl;
+    for (uint32_t i = threadIdx.x; i < tot; i += RS_THREADS) {
+        const uint32_t g = s_list[i];
+        visible_ids[out0 + i] = (int32_t)g;
+        const uint2 bx = s_box[i];
+        VisRec r;
+        r.g = g; r.depth_bits = __float_as_uint(depths[g]); r.xy0 = bx.x; r.xy1 = bx.y;
+        vrec[out0 + i] = r;
+    }
+}
+
+
+// ---- phase 1b: exclusive scan of the (padded) sub-bin counters, one CTA: soff[i], total -> counts_dev[2] ----
+__global__ void __launch_bounds__(SCAN_THREADS) hist_scan_kernel(const uint32_t* __restrict__ hist_padded, int n,
+                                                                 int32_t* __restrict__ soff,
+                                                                 long long* __restrict__ counts_dev) {
+    __shared__ long long s_warp[SCAN_THREADS / 32];
+    // gather the counters into soff (independent strided loads, many in flight), then scan in place
+#pragma unroll 8
+    for (int i = threadIdx.x; i < n; i += SCAN_THREADS) soff[i] = (int32_t)__ldcg(hist_padded + (long long)i * PAD);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per = (n + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int b = min(threadIdx.x * per, n), e = min(b + per, n);
+    long long sum = 0;
+    for (int i = b; i < e; ++i) sum += (uint32_t)soff[i];
+    long long incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const long long w = s_warp[lane];
+        long long wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        s_warp[lane] = wi - w;      // exclusive prefix of the warp totals
+        if (lane == 31) counts_dev[2] = wi;
+    }
+    __syncthreads();
+    long long run = s_warp[warp] + incl - sum;
+    for (int i = b; i < e; ++i) {
+        const uint32_t c = (uint32_t)soff[i];
+        soff[i] = (int32_t)run;     // totals >= 2^31 are rejected by the caller before the ranges are used
+        run += c;
+    }
+}
+static_assert(SCAN_THREADS == 1024, "hist_scan_kernel scans 32 warp totals with one warp");
+
+// ---- phase 2a: every visible Gaussian drops one key per super-tile it touches into that super-tile's range:
+// key = depth bits << 32 | flat index << 4 | mask of the super-tile's ST x ST tiles it touches (bit ly * ST + lx)
+__device__ __forceinline__ unsigned long long make_key(const VisRec& r, int sx, int sy) {
+    const int x0 = (int)(r.xy0 & 0xFFFFu), y0 = (int)(r.xy0 >> 16), x1 = (int)(r.xy1 & 0xFFFFu), y1 = (int)(r.xy1 >> 16);
+    const int lx0 = max(x0 - sx * ST, 0), lx1 = min(x1 - sx * ST, ST);
+    const int ly0 = max(y0 - sy * ST, 0), ly1 = min(y1 - sy * ST, ST);
+    const uint32_t cols = ((1u << lx1) - 1u) & ~((1u << lx0) - 1u);
+    uint32_t mask = 0;
+    for (int ly = ly0; ly < ly1; ++ly) mask |= cols << (ly * ST);
+    return ((unsigned long long)r.depth_bits << 32) | ((unsigned long long)r.g << (32 - ID_BITS)) | mask;
+}
+
+__global__ void __launch_bounds__(RS_THREADS) bin_scatter_kernel(
+    const VisRec* __restrict__ vrec, const long long* __restrict__ counts_dev, BinGeom G,
+    const int32_t* __restrict__ soff, uint32_t* __restrict__ cursor, unsigned long long* __restrict__ bucket) {
+    __shared__ uint32_t s_nbig;
+    __shared__ uint32_t s_big[RS_THREADS];
+    const long long n_vis = counts_dev[0];
+    if ((long long)blockIdx.x * RS_THREADS >= n_vis) return;
+    if (threadIdx.x == 0) s_nbig = 0;
+    __syncthreads();
+    const long long j = (long long)blockIdx.x * RS_THREADS + threadIdx.x;
+    const int n_super = G.stw * G.sth;
+    if (j < n_vis) {
+        const VisRec r = vrec[j];
+        const int sx0 = (int)(r.xy0 & 0xFFFFu) / ST, sy0 = (int)(r.xy0 >> 16) / ST;
+        const int sx1 = ((int)(r.xy1 & 0xFFFFu) - 1) / ST, sy1 = ((int)(r.xy1 >> 16) - 1) / ST;
+        if ((sx1 - sx0 + 1) * (sy1 - sy0 + 1) > BIG_AREA) {
+            s_big[atomicAdd(&s_nbig, 1u)] = threadIdx.x;
+        } else {
+            const long long base = ((long long)(r.g / (uint32_t)G.N) * n_super) * SUB + (r.g % SUB);
+            for (int y = sy0; y <= sy1; ++y)
+                for (int x = sx0; x <= sx1; ++x) {
+                    const long long t = base + (long long)(y * G.stw + x) * SUB;
+                    const uint32_t slot = atomicAdd(&cursor[t * PAD], 1u);
+                    bucket[(long long)soff[t] + slot] = make_key(r, x, y);
+                }
+        }
+    }
+    __syncthreads();
+    const uint32_t nbig = s_nbig;
+    for (uint32_t b = 0; b < nbig; ++b) {
+        const VisRec r = vrec[(long long)blockIdx.x * RS_THREADS + s_big[b]];
+        const int sx0 = (int)(r.xy0 & 0xFFFFu) / ST, sy0 = (int)(r.xy0 >> 16) / ST;
+        const int sw = ((int)(r.xy1 & 0xFFFFu) - 1) / ST - sx0 + 1, sarea = sw * (((int)(r.xy1 >> 16) - 1) / ST - sy0 + 1);
+        const long long base = ((long long)(r.g / (uint32_t)G.N) * n_super) * SUB + (r.g % SUB);
+        for (int k = threadIdx.x; k < sarea; k += RS_THREADS) {
+            const int x = sx0 + k % sw, y = sy0 + k / sw;
+            const long long t = base + (long long)(y * G.stw + x) * SUB;
+            const uint32_t slot = atomicAdd(&cursor[t * PAD], 1u);
+            bucket[(long long)soff[t] + slot] = make_key(r, x, y);
         }
     }
 }
 
-__global__ void finalize_sorted_kernel(const uint32_t* __restrict__ tkeys, const uint32_t* __restrict__ vals,
-                                       const float* __restrict__ depths, long long n_isects, int n_tiles,
-                                       int tile_bits, int total_tiles, long long* __restrict__ isect_ids,
-                                       int32_t* __restrict__ offsets) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_isects) return;
-    const uint32_t tk = tkeys[i];
-    const uint32_t g = vals[i];
-    isect_ids[i] = ((long long)tk << 32) | (long long)__float_as_int(depths[g]);
-    const uint32_t tmask = (1u << tile_bits) - 1u;
-    const int id_curr = (int)(tk >> tile_bits) * n_tiles + (int)(tk & tmask);
-    if (i == 0)
-        for (int t = 0; t <= id_curr; ++t) offsets[t] = 0;
-    if (i == n_isects - 1)
-        for (int t = id_curr + 1; t < total_tiles; ++t) offsets[t] = (int32_t)n_isects;
-    if (i > 0) {
-        const uint32_t tp = tkeys[i - 1];
-        const int id_prev = (int)(tp >> tile_bits) * n_tiles + (int)(tp & tmask);
-        for (int t = id_prev + 1; t <= id_curr; ++t) offsets[t] = (int32_t)i;
+// ---- phase 2b: per-super-tile sort ------------------------------------------------------------------
+// Ascending bitonic network in its uniform-direction form (first stage of every merge pairs i with
+// i ^ (k - 1), the others i with i ^ j; every exchange puts the minimum at the lower index, so +inf padding at
+// the top never moves).  Blocked layout: thread t holds keys [t * IPT, (t + 1) * IPT).
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
+    const unsigned lo = __shfl_xor_sync(0xFFFFFFFFu, (unsigned)v, m);
+    const unsigned hi = __shfl_xor_sync(0xFFFFFFFFu, (unsigned)(v >> 32), m);
+    return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ void cmp_exch(unsigned long long& a, unsigned long long& b) {
+    const bool sw = b < a;
+    const unsigned long long lo = sw ? b : a, hi = sw ? a : b;
+    a = lo;
+    b = hi;
+}
+__device__ __forceinline__ unsigned long long pick(bool lower, unsigned long long mine, unsigned long long other) {
+    const bool take = lower ? (other < mine) : (mine < other);
+    return take ? other : mine;
+}
+
+// stages j = j_hi, j_hi / 2, ..., 1 (plain i ^ j exchanges); s_buf: RS_THREADS * IPT keys
+// `active`: the warp holds at least one real key (a warp of +inf padding never changes: it only takes part in the
+// shared-memory stages, where its partners read it)
+template <int IPT>
+__device__ __forceinline__ void merge_xor_stages(unsigned long long (&v)[IPT], int j_hi, unsigned long long* s_buf,
+                                                 bool active = true) {
+    const int t = threadIdx.x;
+    int j = j_hi;
+    for (; j >= 32 * IPT; j >>= 1) {          // partner in another warp: through shared memory ([a][t] layout)
+        const int m = j / IPT;
+#pragma unroll
+        for (int a = 0; a < IPT; ++a) s_buf[a * RS_THREADS + t] = v[a];
+        __syncthreads();
+        const bool lower = (t & m) == 0;
+#pragma unroll
+        for (int a = 0; a < IPT; ++a) v[a] = pick(lower, v[a], s_buf[a * RS_THREADS + (t ^ m)]);
+        __syncthreads();
+    }
+    if (!active) return;
+    for (; j >= IPT; j >>= 1) {               // partner in this warp: shuffles
+        const int m = j / IPT;
+        const bool lower = (t & m) == 0;
+#pragma unroll
+        for (int a = 0; a < IPT; ++a) v[a] = pick(lower, v[a], shfl_xor_u64(v[a], m));
+    }
+#pragma unroll
+    for (int jj = IPT / 2; jj > 0; jj >>= 1) {  // partner in this thread
+        if (jj <= j) {
+#pragma unroll
+            for (int a = 0; a < IPT; ++a)
+                if ((a & jj) == 0) cmp_exch(v[a], v[a | jj]);
+        }
+    }
+}
+
+// full sort of the CTA's RS_THREADS * IPT keys; k_max = smallest power of two >= the number of real keys
+// (the +inf padding above it is already in place)
+template <int IPT>
+__device__ __forceinline__ void cta_sort(unsigned long long (&v)[IPT], int k_max, unsigned long long* s_buf,
+                                         bool active = true) {
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int k = 2; k <= IPT; k <<= 1) {      // merges inside the thread
+        if (!active) break;
+#pragma unroll
+        for (int a = 0; a < IPT; ++a)
+            if ((a & (k >> 1)) == 0) cmp_exch(v[a], v[a ^ (k - 1)]);
+#pragma unroll
+        for (int jj = k >> 2; jj > 0; jj >>= 1) {
+#pragma unroll
+            for (int a = 0; a < IPT; ++a)
+                if ((a & jj) == 0) cmp_exch(v[a], v[a | jj]);
+        }
+    }
+    for (int k = 2 * IPT; k <= k_max; k <<= 1) {
+        // mirror stage: key (t, a) meets key (t ^ (k / IPT - 1), IPT - 1 - a)
+        const int m = k / IPT - 1;
+        const bool lower = (t & (k / IPT / 2)) == 0;
+        unsigned long long o[IPT];
+        if (m >= 32) {
+#pragma unroll
+            for (int a = 0; a < IPT; ++a) s_buf[a * RS_THREADS + t] = v[a];
+            __syncthreads();
+#pragma unroll
+            for (int a = 0; a < IPT; ++a) o[a] = s_buf[(IPT - 1 - a) * RS_THREADS + (t ^ m)];
+            __syncthreads();
+#pragma unroll
+            for (int a = 0; a < IPT; ++a) v[a] = pick(lower, v[a], o[a]);
+        } else if (active) {
+#pragma unroll
+            for (int a = 0; a < IPT; ++a) o[a] = shfl_xor_u64(v[IPT - 1 - a], m);
+#pragma unroll
+            for (int a = 0; a < IPT; ++a) v[a] = pick(lower, v[a], o[a]);
+        }
+        merge_xor_stages<IPT>(v, k >> 2, s_buf, active);
+    }
+}
+
+// keys [0, n) of buf -> registers (blocked), coalesced through shared memory; padding = +inf
+template <int IPT>
+__device__ __forceinline__ void load_blocked(unsigned long long (&v)[IPT], const unsigned long long* buf, int n,
+                                             unsigned long long* s_buf) {
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int a = 0; a < IPT; ++a) {
+        const int i = a * RS_THREADS + t;
+        s_buf[i] = i < n ? buf[i] : KEY_INF;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < IPT; ++a) v[a] = s_buf[t * IPT + a];
+    __syncthreads();
+}
+template <int IPT>
+__device__ __forceinline__ void stage_blocked(const unsigned long long (&v)[IPT], unsigned long long* s_buf) {
+#pragma unroll
+    for (int a = 0; a < IPT; ++a) s_buf[threadIdx.x * IPT + a] = v[a];
+    __syncthreads();
+}
+
+// sort n <= RS_THREADS * IPT keys of `bucket`; the sorted keys end up in s_buf[0, n)
+template <int IPT>
+__device__ __forceinline__ void sort_small(const unsigned long long* bucket, int n, unsigned long long* s_buf) {
+    unsigned long long v[IPT];
+    load_blocked<IPT>(v, bucket, n, s_buf);
+    int k_max = 2;
+    while (k_max < n) k_max <<= 1;
+    cta_sort<IPT>(v, k_max, s_buf, (threadIdx.x & ~31) * IPT < n);
+    stage_blocked<IPT>(v, s_buf);
+}
+
+// one global-memory exchange stage of the big merge: pairs (i, p) with bit `h` of i clear,
+// p = mirror ? i ^ (2h - 1) : i | h
+__device__ __forceinline__ void global_stage(unsigned long long* buf, int n, int h, bool mirror) {
+    for (int q = threadIdx.x;; q += RS_THREADS) {
+        const int i = ((q & ~(h - 1)) << 1) | (q & (h - 1));
+        if (i >= n) break;
+        const int p = mirror ? (i ^ (2 * h - 1)) : (i | h);
+        if (p < n) {
+            unsigned long long a = buf[i], b = buf[p];
+            if (b < a) {
+                buf[i] = b;
+                buf[p] = a;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// ranges longer than SORT_CHUNK: chunk sorts + merges whose wide strides go through (L2-resident) global
+// memory; sorted in place
+__device__ void sort_big(unsigned long long* bucket, int n, unsigned long long* s_buf) {
+    constexpr int IPT = SORT_CHUNK / RS_THREADS;
+    const int n_chunks = (n + SORT_CHUNK - 1) / SORT_CHUNK;
+    unsigned long long v[IPT];
+    for (int c = 0; c < n_chunks; ++c) {
+        unsigned long long* cb = bucket + (long long)c * SORT_CHUNK;
+        const int cn = min(SORT_CHUNK, n - c * SORT_CHUNK);
+        load_blocked<IPT>(v, cb, cn, s_buf);
+        cta_sort<IPT>(v, SORT_CHUNK, s_buf);
+        stage_blocked<IPT>(v, s_buf);
+        for (int i = threadIdx.x; i < cn; i += RS_THREADS) cb[i] = s_buf[i];
+        __syncthreads();
+    }
+    int P = SORT_CHUNK;
+    while (P < n) P <<= 1;
+    for (int k = 2 * SORT_CHUNK; k <= P; k <<= 1) {
+        global_stage(bucket, n, k >> 1, true);
+        for (int j = k >> 2; j >= SORT_CHUNK; j >>= 1) global_stage(bucket, n, j, false);
+        for (int c = 0; c < n_chunks; ++c) {
+            unsigned long long* cb = bucket + (long long)c * SORT_CHUNK;
+            const int cn = min(SORT_CHUNK, n - c * SORT_CHUNK);
+            load_blocked<IPT>(v, cb, cn, s_buf);
+            merge_xor_stages<IPT>(v, SORT_CHUNK >> 1, s_buf);
+            stage_blocked<IPT>(v, s_buf);
+            for (int i = threadIdx.x; i < cn; i += RS_THREADS) cb[i] = s_buf[i];
+            __syncthreads();
+        }
+    }
+}
+
+// One CTA per (camera, super-tile): sorts the super-tile's keys by (depth bits, flat index) in place and counts
+// the keys of each of its tiles (= the tile histogram) from the masks the keys carry.
+__global__ void __launch_bounds__(RS_THREADS) super_sort_kernel(
+    BinGeom G, int total_super, const int32_t* __restrict__ soff, const long long* __restrict__ counts_dev,
+    unsigned long long* bucket, uint32_t* __restrict__ tile_count) {
+    __shared__ __align__(16) unsigned long long s_buf[SORT_CHUNK];
+    __shared__ uint32_t s_cnt[ST2];
+    const int s = blockIdx.x;
+    const int n_super = G.stw * G.sth, n_tiles = G.tile_w * G.tile_h;
+    const int cam = s / n_super, sy = (s % n_super) / G.stw, sx = s % G.stw;
+    const long long begin = soff[(long long)s * SUB];
+    const long long end = s + 1 < total_super ? (long long)soff[(long long)(s + 1) * SUB] : counts_dev[2];
+    const int n = (int)(end - begin);
+    if (threadIdx.x < ST2) s_cnt[threadIdx.x] = 0;
+    uint32_t cnt[ST2];
+#pragma unroll
+    for (int k = 0; k < ST2; ++k) cnt[k] = 0;
+    if (n > 0) {
+        unsigned long long* bk = bucket + begin;
+        const bool big = n > SORT_CHUNK;
+        if (n <= RS_THREADS) sort_small<1>(bk, n, s_buf);
+        else if (n <= 2 * RS_THREADS) sort_small<2>(bk, n, s_buf);
+        else if (n <= 4 * RS_THREADS) sort_small<4>(bk, n, s_buf);
+        else if (!big) sort_small<8>(bk, n, s_buf);
+        else sort_big(bk, n, s_buf);
+        for (int i = threadIdx.x; i < n; i += RS_THREADS) {
+            const unsigned long long key = big ? bk[i] : s_buf[i];
+            if (!big) bk[i] = key;
+            const uint32_t mask = (uint32_t)key & ((1u << ST2) - 1u);
+#pragma unroll
+            for (int k = 0; k < ST2; ++k) cnt[k] += (mask >> k) & 1u;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < ST2; ++k) {
+        uint32_t c = cnt[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+        if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt[k], c);
+    }
+    __syncthreads();
+    if (threadIdx.x < ST2) {
+        const int tx = sx * ST + (threadIdx.x % ST), ty = sy * ST + (threadIdx.x / ST);
+        if (tx < G.tile_w && ty < G.tile_h) tile_count[(long long)cam * n_tiles + ty * G.tile_w + tx] = s_cnt[threadIdx.x];
+    }
+}
+static_assert(ST2 <= 8 && ST2 <= RS_WARPS, "one warp per tile of the super-tile, masks are 8 bits");
+static_assert(SORT_CHUNK == 8 * RS_THREADS, "largest in-register sort class");
+
+__device__ __forceinline__ long long block_sum_u32(const uint32_t* __restrict__ a, long long lo, long long hi,
+                                                   long long* s_red) {
+    long long v = 0;
+    for (long long i = lo + threadIdx.x; i < hi; i += RS_THREADS) v += a[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    long long r = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) r += s_red[w];
+    return r;
+}
+
+// One CTA per (camera, super-tile): the start of each of its tiles' ranges is the sum of the tile histogram before
+// that tile (summed here, no scan launch; also written out as isect_offsets), and every tile's range is the
+// ORDER-PRESERVING selection of the super-tile's sorted keys by the tile's mask bit: warp w serves tile w.
+__global__ void __launch_bounds__(RS_THREADS) super_expand_kernel(
+    BinGeom G, int total_super, int tile_bits, const int32_t* __restrict__ soff, const long long* __restrict__ counts_dev,
+    const unsigned long long* __restrict__ bucket, const uint32_t* __restrict__ tile_count,
+    int32_t* __restrict__ offsets, long long* __restrict__ isect_ids, int32_t* __restrict__ flatten_ids) {
+    constexpr int CH = 1024;
+    __shared__ __align__(16) unsigned long long s_key[CH];
+    __shared__ long long s_red[RS_WARPS];
+    const int s = blockIdx.x;
+    const int n_super = G.stw * G.sth, n_tiles = G.tile_w * G.tile_h;
+    const int cam = s / n_super, sy = (s % n_super) / G.stw, sx = s % G.stw;
+    // tile rows ty0 (and ty0 + 1): first tile index of the super-tile in each
+    const int tx0 = sx * ST, ty0 = sy * ST;
+    const long long A = (long long)cam * n_tiles + (long long)ty0 * G.tile_w + tx0;
+    long long row_start[ST];
+    row_start[0] = block_sum_u32(tile_count, 0, A, s_red);
+#pragma unroll
+    for (int r = 1; r < ST; ++r)
+        row_start[r] = ty0 + r < G.tile_h ? row_start[r - 1] + block_sum_u32(tile_count, A + (long long)(r - 1) * G.tile_w,
+                                                                             A + (long long)r * G.tile_w, s_red)
+                                          : 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lx = warp % ST, ly = warp / ST;
+    const bool live = warp < ST2 && tx0 + lx < G.tile_w && ty0 + ly < G.tile_h;
+    long long wpos = 0;
+    unsigned long long tkey_hi = 0;
+    if (live) {
+        const long long t_idx = A + (long long)ly * G.tile_w + lx;
+        wpos = row_start[ly];
+        for (int x = 0; x < lx; ++x) wpos += tile_count[t_idx - lx + x];
+        if (lane == 0) offsets[t_idx] = (int32_t)wpos;
+        tkey_hi = (((unsigned long long)cam << tile_bits) | (unsigned long long)((ty0 + ly) * G.tile_w + tx0 + lx)) << 32;
+    }
+    const long long begin = soff[(long long)s * SUB];
+    const long long end = s + 1 < total_super ? (long long)soff[(long long)(s + 1) * SUB] : counts_dev[2];
+    const int n = (int)(end - begin);
+    const unsigned lt = (1u << lane) - 1u;
+    for (int c0 = 0; c0 < n; c0 += CH) {
+        const int cn = min(CH, n - c0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cn; i += RS_THREADS) s_key[i] = bucket[begin + c0 + i];
+        __syncthreads();
+        if (!live) continue;
+        for (int i0 = 0; i0 < cn; i0 += 32) {
+            const int i = i0 + lane;
+            const unsigned long long key = i < cn ? s_key[i] : 0ull;
+            const bool in = ((uint32_t)key >> warp) & 1u;
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, in);
+            if (in) {
+                const long long p = wpos + __popc(m & lt);
+                isect_ids[p] = (long long)(tkey_hi | (key >> 32));
+                flatten_ids[p] = (int32_t)(((uint32_t)key) >> (32 - ID_BITS));
+            }
+            wpos += __popc(m);
+        }
     }
 }
 
@@ -614,133 +847,108 @@ HGS_API int hgs_isect_emit(const float* means2d, const int32_t* radii, const flo
     return 0;
 }
 
-// temp layout for prepare: keysA, valsA, keysB, valsB (CN u32 each), cnt_sorted (CN i32), hist,
-// block counts/bases (ceil(CN/CP_TILE) long longs), scan temp
-HGS_API size_t hgs_isect_prepare_temp_bytes(long long CN) {
-    const size_t a = align_up((size_t)(CN > 0 ? CN : 1) * 4);
-    const size_t nb = (size_t)hgs_ceil_div(CN > 0 ? CN : 1, CP_TILE);
-    return 5 * a + align_up(HIST_BYTES) + align_up(nb * sizeof(long long)) + hgs_scan_temp_bytes(CN);
+// temp layout of the sorted path (zero-filled by phase 1 up to zero_bytes; shared by both phases):
+// look-back flags [ceil(CN / CP_TILE)] u64 | tile histogram [C*T] u32 | super-tile sub-bin histogram [S*SUB] u32 |
+// sub-bin cursors [S*SUB] u32 | ticket || sub-bin offsets [S*SUB] i32 | visible-Gaussian records [CN] x 16 B
+static BinGeom make_geom(int N, int tile_size, int tile_w, int tile_h) {
+    BinGeom G;
+    G.N = N; G.tile_w = tile_w; G.tile_h = tile_h;
+    G.stw = (tile_w + ST - 1) / ST;
+    G.sth = (tile_h + ST - 1) / ST;
+    G.tile_size = (float)tile_size;
+    G.inv_tile_size = (tile_size & (tile_size - 1)) == 0 ? 1.0f / (float)tile_size : 0.f;
+    return G;
+}
+struct BinTemp {
+    unsigned long long* flags;
+    uint32_t *tile_count, *super_count, *cursor, *ticket;
+    int32_t* soff;
+    VisRec* vrec;
+    size_t zero_bytes, bytes;
+};
+static BinTemp bin_temp(void* temp, long long CN, long long total_super, long long total_tiles) {
+    BinTemp T;
+    const size_t nblk = (size_t)hgs_ceil_div(CN > 0 ? CN : 1, CP_TILE);
+    const size_t S = (size_t)(total_super > 0 ? total_super : 1) * SUB, TT = (size_t)(total_tiles > 0 ? total_tiles : 1);
+    char* p = (char*)temp;
+    T.flags = (unsigned long long*)p; p += align_up(nblk * sizeof(unsigned long long));
+    T.tile_count = (uint32_t*)p; p += align_up(TT * sizeof(uint32_t));
+    T.super_count = (uint32_t*)p; p += align_up(S * PAD * sizeof(uint32_t));
+    T.cursor = (uint32_t*)p; p += align_up(S * PAD * sizeof(uint32_t));
+    T.ticket = (uint32_t*)p; p += 256;
+    T.zero_bytes = (size_t)(p - (char*)temp);
+    T.soff = (int32_t*)p; p += align_up(S * sizeof(int32_t));
+    T.vrec = (VisRec*)p; p += align_up((size_t)(CN > 0 ? CN : 1) * sizeof(VisRec));
+    T.bytes = (size_t)(p - (char*)temp);
+    return T;
 }
 
-HGS_API int hgs_isect_prepare(const float* depths, const int32_t* tiles_per_gauss, int C, int N, int32_t* order,
-                              int32_t* cum_sorted, int32_t* visible_ids, long long* counts_dev, void* temp,
-                              size_t temp_bytes, void* stream) {
-    if (C <= 0 || N < 0) return HGS_ERR_INVALID_ARG;
+HGS_API size_t hgs_isect_bin_temp_bytes(long long CN, int C, int tile_w, int tile_h) {
+    const BinGeom G = make_geom(1, 16, tile_w > 0 ? tile_w : 1, tile_h > 0 ? tile_h : 1);
+    return bin_temp(nullptr, CN, (long long)C * G.stw * G.sth, (long long)C * tile_w * tile_h).bytes;
+}
+
+HGS_API size_t hgs_isect_bin_bucket_bytes(long long n_super_isects) {
+    // one 8-byte sort key per (Gaussian, super-tile) pair
+    return align_up((size_t)(n_super_isects > 0 ? n_super_isects : 1) * sizeof(unsigned long long));
+}
+
+HGS_API int hgs_isect_bin_prepare(const float* means2d, const int32_t* radii, const float* depths,
+                                  const int32_t* tiles_per_gauss, int C, int N, int tile_size, int tile_w, int tile_h, int32_t* visible_ids,
+                                  long long* counts_dev, void* temp, size_t temp_bytes, void* stream) {
+    if (C <= 0 || N < 0 || tile_size <= 0 || tile_w <= 0 || tile_h <= 0) return HGS_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const long long CN = (long long)C * N;
-    if (CN >= (1ll << 31)) return HGS_ERR_TOO_LARGE;
-    if (CN == 0) return (int)cudaMemsetAsync(counts_dev, 0, 2 * sizeof(long long), st);
-    if (temp_bytes < hgs_isect_prepare_temp_bytes(CN)) return HGS_ERR_WORKSPACE;
-    const size_t a = align_up((size_t)CN * 4);
+    const long long tt_ll = (long long)C * tile_w * tile_h;
+    // flat indices travel in ID_BITS bits of the sort keys
+    if (CN >= (1ll << ID_BITS) || tt_ll >= (1ll << 29) || tile_w >= 65536 || tile_h >= 65536) return HGS_ERR_TOO_LARGE;
+    if (n_bits_of((long long)tile_w * tile_h) + n_bits_of(C) > 32) return HGS_ERR_TOO_LARGE;
+    if (CN == 0) return (int)cudaMemsetAsync(counts_dev, 0, 3 * sizeof(long long), st);
+    const BinGeom G = make_geom(N, tile_size, tile_w, tile_h);
+    const int total_super = C * G.stw * G.sth;
+    const BinTemp T = bin_temp(temp, CN, total_super, tt_ll);
+    if (temp_bytes < T.bytes) return HGS_ERR_WORKSPACE;
     const int nblk = hgs_ceil_div(CN, CP_TILE);
-    char* p = (char*)temp;
-    uint32_t* kA = (uint32_t*)p; p += a;
-    uint32_t* vA = (uint32_t*)p; p += a;
-    uint32_t* kB = (uint32_t*)p; p += a;
-    uint32_t* vB = (uint32_t*)p; p += a;
-    int32_t* cnt_sorted = (int32_t*)p; p += a;
-    uint32_t* hist = (uint32_t*)p; p += align_up(HIST_BYTES);
-    long long* blk = (long long*)p; p += align_up((size_t)nblk * sizeof(long long));
-    void* scan_temp = p;
-    long long* n_vis_dev = counts_dev;      // counts_dev[0] = visible Gaussians, counts_dev[1] = intersections
-
-    // 1. order-preserving compaction of the Gaussians with at least one tile
-    vis_count_kernel<<<nblk, RS_THREADS, 0, st>>>(tiles_per_gauss, CN, blk);
+    cudaError_t e = cudaMemsetAsync(temp, 0, T.zero_bytes, st);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(counts_dev, 0, 3 * sizeof(long long), st);
+    if (e != cudaSuccess) return (int)e;
+    bin_count_kernel<<<nblk, RS_THREADS, 0, st>>>(means2d, radii, depths, tiles_per_gauss, CN, G, nblk, T.flags, T.ticket,
+                                                  T.super_count, visible_ids, T.vrec, counts_dev);
     HGS_LAUNCH_CHECK();
-    ls_scan_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(blk, nblk, n_vis_dev);
+    hist_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(T.super_count, total_super * SUB, T.soff, counts_dev);
     HGS_LAUNCH_CHECK();
-    compact_kernel<<<nblk, RS_THREADS, 0, st>>>(depths, tiles_per_gauss, CN, blk, kA, vA, visible_ids);
-    HGS_LAUNCH_CHECK();
-    // 2. stable LSD sort of the depth bits (then of the camera index when C > 1)
-    uint32_t *ki = kA, *vi = vA, *ko = kB, *vo = vB;
-    for (int pass = 0; pass < 4; ++pass) {
-        DigitSpec ds{pass * 8, 0xFFu, 0};
-        int rc = radix_pass(ki, vi, ko, vo, n_vis_dev, CN, ds, hist, st);
-        if (rc) return rc;
-        uint32_t* t;
-        t = ki; ki = ko; ko = t;
-        t = vi; vi = vo; vo = t;
-    }
-    if (C > 1) {
-        const int cam_bits = n_bits_of(C);
-        for (int shift = 0; shift < cam_bits; shift += 8) {
-            int nb = cam_bits - shift < 8 ? cam_bits - shift : 8;
-            DigitSpec ds{shift, (1u << nb) - 1u, N};
-            int rc = radix_pass(ki, vi, ko, vo, n_vis_dev, CN, ds, hist, st);
-            if (rc) return rc;
-            uint32_t* t;
-            t = ki; ki = ko; ko = t;
-            t = vi; vi = vo; vo = t;
-        }
-    }
-    // 3. per-Gaussian tile counts in sorted order and their exclusive scan
-    gather_counts_kernel<<<hgs_ceil_div(CN, 256), 256, 0, st>>>(vi, tiles_per_gauss, n_vis_dev, order, cnt_sorted);
-    HGS_LAUNCH_CHECK();
-    return large_scan(cnt_sorted, cum_sorted, counts_dev + 1, n_vis_dev, CN, scan_temp, hgs_scan_temp_bytes(CN) - 256,
-                      st);
+    return 0;
 }
 
-// temp layout for sorted: tkeyA, tkeyB, valsT (I u32 each), hist, element count
-HGS_API size_t hgs_isect_sorted_temp_bytes(long long CN, long long n_isects) {
-    (void)CN;
-    size_t a = align_up((size_t)(n_isects > 0 ? n_isects : 1) * 4);
-    return 3 * a + align_up(HIST_BYTES) + 256;
-}
-
-HGS_API int hgs_isect_sorted(const float* means2d, const int32_t* radii, const float* depths, const int32_t* order,
-                             const int32_t* cum_sorted, int C, int N, long long n_visible, long long n_isects,
-                             int tile_size, int tile_w, int tile_h, long long* isect_ids, int32_t* flatten_ids,
-                             int32_t* isect_offsets, void* temp, size_t temp_bytes, void* stream) {
-    if (C <= 0 || N < 0 || n_isects < 0 || n_visible < 0 || tile_size <= 0 || tile_w <= 0 || tile_h <= 0)
+HGS_API int hgs_isect_bin_sorted(const long long* counts_dev, int C, int N,
+                                 long long n_visible_bound, long long n_isects, long long n_super_isects, int tile_size,
+                                 int tile_w, int tile_h, int32_t* isect_offsets, long long* isect_ids,
+                                 int32_t* flatten_ids, void* temp, size_t temp_bytes, void* bucket, size_t bucket_bytes,
+                                 void* stream) {
+    if (C <= 0 || N < 0 || n_isects < 0 || n_visible_bound < 0 || n_super_isects < 0 || tile_size <= 0 || tile_w <= 0 ||
+        tile_h <= 0)
         return HGS_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const long long CN = (long long)C * N;
     const int n_tiles = tile_w * tile_h;
-    const long long total_tiles_ll = (long long)C * n_tiles;
-    if (n_isects >= (1ll << 31) || total_tiles_ll >= (1ll << 31) || tile_w >= 65536 || tile_h >= 65536)
-        return HGS_ERR_TOO_LARGE;
-    const int total_tiles = (int)total_tiles_ll;
-    if (n_isects == 0) return (int)cudaMemsetAsync(isect_offsets, 0, (size_t)total_tiles * sizeof(int32_t), st);
-    if (n_visible == 0) return HGS_ERR_INVALID_ARG;
-    const int tile_bits = n_bits_of(n_tiles);
-    const int cam_bits = n_bits_of(C);
-    if (tile_bits + cam_bits > 32) return HGS_ERR_TOO_LARGE;
-    if (temp_bytes < hgs_isect_sorted_temp_bytes(CN, n_isects)) return HGS_ERR_WORKSPACE;
-    const size_t a = align_up((size_t)n_isects * 4);
-    char* p = (char*)temp;
-    uint32_t* kA = (uint32_t*)p; p += a;
-    uint32_t* kB = (uint32_t*)p; p += a;
-    uint32_t* vT = (uint32_t*)p; p += a;
-    uint32_t* hist = (uint32_t*)p; p += align_up(HIST_BYTES);
-    long long* n_dev = (long long*)p;
-    set_ll_kernel<<<1, 1, 0, st>>>(n_dev, n_isects);
+    const long long tt_ll = (long long)C * n_tiles;
+    if (n_isects >= (1ll << 31) || tt_ll >= (1ll << 29)) return HGS_ERR_TOO_LARGE;
+    if (n_isects == 0 || n_visible_bound == 0)
+        return (int)cudaMemsetAsync(isect_offsets, 0, (size_t)tt_ll * sizeof(int32_t), st);
+    const BinGeom G = make_geom(N, tile_size, tile_w, tile_h);
+    const int total_super = C * G.stw * G.sth;
+    const BinTemp T = bin_temp(temp, CN, total_super, tt_ll);
+    if (temp_bytes < T.bytes) return HGS_ERR_WORKSPACE;
+    if (bucket_bytes < hgs_isect_bin_bucket_bytes(n_super_isects)) return HGS_ERR_WORKSPACE;
+    unsigned long long* keys = (unsigned long long*)bucket;
+    bin_scatter_kernel<<<hgs_ceil_div(n_visible_bound, RS_THREADS), RS_THREADS, 0, st>>>(T.vrec, counts_dev, G, T.soff,
+                                                                                         T.cursor, keys);
     HGS_LAUNCH_CHECK();
-
-    // when C == 1 the camera bit is always 0: sort tile bits only
-    const int key_bits = (C > 1) ? tile_bits + cam_bits : tile_bits;
-    const int n_pass = (key_bits + 7) / 8;
-    // choose ping-pong start so the last pass lands the values in flatten_ids
-    uint32_t* vF = (uint32_t*)flatten_ids;
-    uint32_t *ki = kA, *ko = kB;
-    uint32_t* vi = (n_pass % 2 == 0) ? vF : vT;
-    uint32_t* vo = (n_pass % 2 == 0) ? vT : vF;
-
-    emit_sorted_kernel<<<hgs_ceil_div(n_isects, RS_TILE), RS_THREADS, 0, st>>>(
-        means2d, radii, order, cum_sorted, n_visible, n_isects, N, tile_size, tile_w, tile_h, tile_bits, ki, vi);
+    super_sort_kernel<<<total_super, RS_THREADS, 0, st>>>(G, total_super, T.soff, counts_dev, keys, T.tile_count);
     HGS_LAUNCH_CHECK();
-    for (int pass = 0; pass < n_pass; ++pass) {
-        int shift = pass * 8;
-        int nb = key_bits - shift < 8 ? key_bits - shift : 8;
-        DigitSpec ds{shift, (1u << nb) - 1u, 0};
-        int rc = radix_pass(ki, vi, ko, vo, n_dev, n_isects, ds, hist, st);
-        if (rc) return rc;
-        uint32_t* t;
-        t = ki; ki = ko; ko = t;
-        t = vi; vi = vo; vo = t;
-    }
-    // now (ki, vi) hold the result and vi == flatten_ids (values are already in their output buffer)
-    finalize_sorted_kernel<<<hgs_ceil_div(n_isects, 256), 256, 0, st>>>(ki, vi, depths, n_isects, n_tiles, tile_bits,
-                                                                        total_tiles, isect_ids, isect_offsets);
+    super_expand_kernel<<<total_super, RS_THREADS, 0, st>>>(G, total_super, n_bits_of(n_tiles), T.soff, counts_dev, keys,
+                                                            T.tile_count, isect_offsets, isect_ids, flatten_ids);
     HGS_LAUNCH_CHECK();
     return 0;
 }

@@ -279,63 +279,73 @@ def _sh_view_colors(sh_degree: int, means: Tensor, campos: Tensor, coeffs: Tenso
 # =====================================================================================
 # a8-a10: tile intersection / sort / offsets
 # =====================================================================================
-_PINNED_COUNTS = {}
+_PINNED_RING = {}          # device -> (list of pinned [2] int64 buffers, next slot): one buffer per call in flight
+_PINNED_SLOTS = 16
 
 
-def _isect_prepare_async(depths, tiles_per_gauss, C, N):
-    """phase 1 of the sorted path: compact + depth-order + scan on the device, and an ASYNCHRONOUS copy of
-    (n_visible, n_isects) into pinned host memory.  Work that only needs the device-side count (SH colours, record
-    packing) can be enqueued before _isect_finish() makes the host wait for the two numbers."""
-    L = _lib.lib()
-    dev = depths.device
-    CN = C * N
-    st = _stream()
-    order = torch.empty(CN, dtype=torch.int32, device=dev)
-    cum_sorted = torch.empty(CN, dtype=torch.int32, device=dev)
-    vis_ids = torch.empty(CN, dtype=torch.int32, device=dev)
-    counts = torch.empty(2, dtype=torch.int64, device=dev)
-    _mark("isect_prepare", 0)
-    tb = L.hgs_isect_prepare_temp_bytes(CN)
-    temp = torch.empty(tb, dtype=torch.uint8, device=dev)
-    check(L.hgs_isect_prepare(ptr(depths), ptr(tiles_per_gauss), C, N, ptr(order), ptr(cum_sorted), ptr(vis_ids),
-                              ptr(counts), ptr(temp), tb, st), "hgs_isect_prepare")
-    _mark("isect_prepare", 1)
-    host = _PINNED_COUNTS.get(dev)
-    if host is None:
-        host = _PINNED_COUNTS[dev] = torch.empty(2, dtype=torch.int64).pin_memory()
-    host.copy_(counts, non_blocking=True)
-    ev = torch.cuda.Event()
-    ev.record()
-    return {"order": order, "cum_sorted": cum_sorted, "vis_full": vis_ids, "counts": counts, "host": host, "event": ev,
-            "temp": temp}
+def _pinned_counts(dev):
+    """a pinned 16-byte host buffer for this call's (n_visible, n_isects); rotating ring per device, so that several
+    rasterizations in flight (other streams / threads) never share one"""
+    ring = _PINNED_RING.get(dev)
+    if ring is None:
+        ring = _PINNED_RING[dev] = [[torch.empty(3, dtype=torch.int64).pin_memory() for _ in range(_PINNED_SLOTS)], 0]
+    buf = ring[0][ring[1] % _PINNED_SLOTS]
+    ring[1] += 1
+    return buf
 
 
-def _isect_finish(prep, means2d, radii, depths, C, N, tile_size, tile_width, tile_height):
-    """phase 2: the one host read (sizes the intersection arrays), then emit + tile partition."""
+def _isect_prepare_async(means2d, radii, depths, tiles_per_gauss, C, N, tile_size, tile_width, tile_height):
+    """phase 1 of the sorted path: ordered compaction of the visible Gaussians + (camera, tile) histogram + its scan
+    (= the per-tile ranges) on the device, and an ASYNCHRONOUS copy of (n_visible, n_isects) into pinned host memory.
+    Work that only needs the device-side count (SH colours, record packing) can be enqueued before _isect_finish()
+    makes the host wait for the two numbers."""
     L = _lib.lib()
     dev = means2d.device
     CN = C * N
     st = _stream()
+    vis_ids = torch.empty(CN, dtype=torch.int32, device=dev)
+    counts = torch.empty(3, dtype=torch.int64, device=dev)
+    _mark("isect_prepare", 0)
+    tb = L.hgs_isect_bin_temp_bytes(CN, C, tile_width, tile_height)
+    temp = torch.empty(tb, dtype=torch.uint8, device=dev)
+    check(L.hgs_isect_bin_prepare(ptr(means2d), ptr(radii), ptr(depths), ptr(tiles_per_gauss), C, N, tile_size, tile_width,
+                                  tile_height, ptr(vis_ids), ptr(counts), ptr(temp), tb, st),
+          "hgs_isect_bin_prepare")
+    _mark("isect_prepare", 1)
+    host = _pinned_counts(dev)
+    host.copy_(counts, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    return {"vis_full": vis_ids, "counts": counts, "host": host, "event": ev, "temp": temp}
+
+
+def _isect_finish(prep, means2d, radii, depths, C, N, tile_size, tile_width, tile_height):
+    """phase 2: the one host read (sizes the intersection arrays), then scatter into the tile ranges + per-tile sort."""
+    L = _lib.lib()
+    dev = means2d.device
+    st = _stream()
     prep["event"].synchronize()
-    n_visible, n_isects = prep["host"].tolist()
+    n_visible, n_isects, n_super = prep["host"].tolist()
     _mark("isect_sorted", 0)
     if n_isects >= 2 ** 31:
         raise _lib.HgsError(f"{n_isects} tile intersections exceed the 32-bit index range")
     isect_ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
     flatten_ids = torch.empty(n_isects, dtype=torch.int32, device=dev)
     offsets = torch.empty((C, tile_height, tile_width), dtype=torch.int32, device=dev)
-    tb2 = L.hgs_isect_sorted_temp_bytes(CN, n_isects)
-    temp2 = torch.empty(tb2, dtype=torch.uint8, device=dev)
-    check(L.hgs_isect_sorted(ptr(means2d), ptr(radii), ptr(depths), ptr(prep["order"]), ptr(prep["cum_sorted"]), C, N,
-                             n_visible, n_isects, tile_size, tile_width, tile_height, ptr(isect_ids), ptr(flatten_ids),
-                             ptr(offsets), ptr(temp2), tb2, st), "hgs_isect_sorted")
+    temp = prep["temp"]
+    bb = L.hgs_isect_bin_bucket_bytes(n_super)
+    bucket = torch.empty(bb, dtype=torch.uint8, device=dev)
+    check(L.hgs_isect_bin_sorted(ptr(prep["counts"]), C, N, n_visible, n_isects, n_super, tile_size, tile_width, tile_height, ptr(offsets),
+                                 ptr(isect_ids), ptr(flatten_ids), ptr(temp), temp.numel(), ptr(bucket), bb, st),
+          "hgs_isect_bin_sorted")
     _mark("isect_sorted", 1)
     return isect_ids, flatten_ids, offsets, prep["vis_full"][:n_visible]
 
 
 def _isect_sorted_from_counts(means2d, radii, depths, tiles_per_gauss, C, N, tile_size, tile_width, tile_height):
-    """depth-order, scan, (one D2H read of I), emit + tile partition.  All int work in libhgs_raster."""
-    prep = _isect_prepare_async(depths, tiles_per_gauss, C, N)
+    """compaction + tile histogram + ranges, (one D2H read of I), scatter + per-tile sort.  All int work in
+    libhgs_raster."""
+    prep = _isect_prepare_async(means2d, radii, depths, tiles_per_gauss, C, N, tile_size, tile_width, tile_height)
     return _isect_finish(prep, means2d, radii, depths, C, N, tile_size, tile_width, tile_height)
 
 

@@ -136,17 +136,43 @@ class _PeerMailbox:
             self.ptrs.append(p.value)
         self.ptrs_c = (C.c_void_p * self.world)(*self.ptrs)
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._status_event = None
         dist.barrier(group=group)          # every mailbox is mapped everywhere before the first push
 
     @property
     def local(self):
         return self._local
 
-    def check_status(self) -> None:
-        """raise if a peer's records did not arrive in time in any exchange so far (one host read)"""
+    _STATUS_TEXT = {1: "timed out waiting for a peer's records",
+                    2: "a rank's contribution exceeded the mailbox capacity (cap_rows); every rank skipped that step's "
+                       "gradients -- construct the exchange with a larger cap_rows"}
+
+    def _raise(self, code: int) -> None:
         from . import _lib
-        if int(self.status.item()) != 0:
-            raise _lib.HgsError("peer gradient exchange timed out waiting for a peer")
+        raise _lib.HgsError("peer gradient exchange failed: " + self._STATUS_TEXT.get(code, f"status {code}"))
+
+    def record_status(self) -> None:
+        """enqueue an asynchronous copy of the sticky device status (after a reduce); poll_status() reads it later"""
+        self._status_host.copy_(self.status, non_blocking=True)
+        self._status_event = torch.cuda.Event()
+        self._status_event.record()
+
+    def poll_status(self) -> None:
+        """raise if an EARLIER exchange failed on this or any other rank (timeout / overflow are outcomes every rank
+        observes for the same step); never blocks: only a status copy that has already landed is looked at"""
+        ev = self._status_event
+        if ev is not None and ev.query():
+            self._status_event = None
+            code = int(self._status_host[0])
+            if code != 0:
+                self._raise(code)
+
+    def check_status(self) -> None:
+        """raise if any exchange so far failed (one blocking host read)"""
+        code = int(self.status.item())
+        if code != 0:
+            self._raise(code)
 
     def close(self) -> None:
         if self._local is None:
@@ -208,8 +234,9 @@ class PeerGradientExchange:
         C, L = self._C, self._lib
         assert ids.dtype == torch.int32 and ids.is_contiguous()
         n = int(ids.numel())
-        if n > self.cap_rows:
-            raise self._lib_error(f"{n} rows exceed the mailbox capacity {self.cap_rows}")
+        # n > cap_rows is NOT raised here: the rank pushes an overflow marker instead, so that every rank fails the
+        # same step (status 2, surfaced by poll_status / check_status) and the step counters stay in lock-step
+        self.box.poll_status()
         self._check(L.hgs_exchange_push(self._tensor_ptrs(tensors), self._widths_c, len(tensors), self.n_ids,
                                         C.c_void_p(ids.data_ptr()) if n > 0 else None, n, self.cap_rows,
                                         self.box.ptrs_c, self.world, self.rank, self.step,
@@ -223,6 +250,7 @@ class PeerGradientExchange:
                                           self.step, C.c_void_p(self.box.status.data_ptr()),
                                           torch.cuda.current_stream().cuda_stream), "hgs_exchange_reduce")
         self.step += 1
+        self.box.record_status()
 
     def exchange(self, tensors: Sequence[torch.Tensor], ids: torch.Tensor) -> None:
         """In place: tensors[k] ([N, widths[k]] float32, dense) become the SUM over ranks.  `ids` (int32, unique,
@@ -294,8 +322,9 @@ class FusedBackwardExchange:
         surfel = bool(sk.get("surfel", False))          # rasterization_2dgs: 24-float rows, surfel projection VJP
         assert vpack.shape == (1, N, 24 if surfel else 12) and vpack.is_contiguous() and sk["n"] == N
         n = int(ids.numel())
-        if n > self.cap_rows:
-            raise _lib.HgsError(f"{n} visible Gaussians exceed the mailbox capacity {self.cap_rows}")
+        # n > cap_rows is NOT raised here: the rank pushes an overflow marker, every rank's reduce then yields zero
+        # gradients for this step and status 2 (surfaced one step later by poll_status, or by check_status)
+        self.box.poll_status()
         sh_degree = sk["sh_degree"]
         cf = sk.get("colors_fwd")
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
@@ -329,6 +358,7 @@ class FusedBackwardExchange:
                     "hgs_exchange_vjp_reduce")
         W._mark("exchange_vjp_reduce", 1)
         self.step += 1
+        self.box.record_status()
         for t, g in zip((means, quats, scales, opacities, colors), outs):
             t.grad = g
         sk.clear()

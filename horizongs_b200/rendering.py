@@ -107,7 +107,7 @@ def rasterization(
     # asynchronous, and the stages that only need the device-side count (SH colours, record packing) are enqueued
     # BEFORE the host waits for it, so the GPU is busy while the host reads the two numbers
     with torch.no_grad():
-        prep = W._isect_prepare_async(depths, tiles_per_gauss, C, N)
+        prep = W._isect_prepare_async(means2d, radii, depths, tiles_per_gauss, C, N, tile_size, tile_width, tile_height)
     vis_full, n_vis_dev = prep["vis_full"], prep["counts"]
 
     # multi-GPU: the SH / projection backward is deferred and runs fused with the gradient exchange

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define HGS_ABI_VERSION 1
+#define HGS_ABI_VERSION 2
 int hgs_abi_version(void);
 /* cumulative count of kernels this library has launched in the process (diagnostics: bench.py reports the
  * number launched inside its timed region) */
@@ -51,7 +51,7 @@ int hgs_project3d_fwd(const float* means, const float* quats, const float* scale
 /* in: upstream gradients v_means2d[C,N,2], v_depths[C,N] (or NULL), v_conics[C,N,3]; each with a row
  * stride in floats (ld_* = 2, 1, 3 when dense) so that slices of the packed blend-gradient buffer can be
  * passed without a copy;  out (overwritten, summed over cameras): v_means[N,3], v_quats[N,4], v_scales[N,3].
- * vis_ids (or NULL): work list of the n_vis visible flat indices c*N+n from hgs_isect_prepare -- one thread per
+ * vis_ids (or NULL): work list of the n_vis visible flat indices c*N+n from hgs_isect_bin_prepare -- one thread per
  * visible pair instead of one per Gaussian (same results; with C > 1 the sums over cameras use atomics). */
 int hgs_project3d_bwd(const float* means, const float* quats, const float* scales, const float* viewmats,
                       const float* Ks, int C, int N, int width, int height, float eps2d, float near_plane,
@@ -81,7 +81,7 @@ int hgs_project2d_bwd(const float* means, const float* quats, const float* scale
  * (normalised inside).  coeffs[N,K,3] is shared by all cameras.  radii (or NULL) masks culled rows to 0.
  * post != 0 fuses gsplat's `clamp_min(colors + 0.5, 0)`.  out: colors[C,N,3].
  * vis_ids (or NULL) = work list of visible flat indices (then radii is not read).  n_vis_dev (or NULL): the length
- * of the work list as a DEVICE value (counts_dev[0] of hgs_isect_prepare); n_vis is then only an upper bound, so the
+ * of the work list as a DEVICE value (counts_dev[0] of hgs_isect_bin_prepare); n_vis is then only an upper bound, so the
  * call can be enqueued before the host has read the count. */
 int hgs_sh_fwd(int degree, int K, const float* dirs, const float* means, const float* campos, const float* coeffs,
                const int32_t* radii, const int32_t* vis_ids, long long n_vis, const long long* n_vis_dev, int C, int N,
@@ -102,8 +102,8 @@ int hgs_isect_count(const float* means2d, const int32_t* radii, long long CN, in
                     int32_t* tiles_per_gauss, void* stream);
 /* workspace sizes in bytes for the calls below */
 size_t hgs_scan_temp_bytes(long long n);
-size_t hgs_isect_prepare_temp_bytes(long long CN);
-size_t hgs_isect_sorted_temp_bytes(long long CN, long long n_isects);
+size_t hgs_isect_bin_temp_bytes(long long CN, int C, int tile_w, int tile_h);
+size_t hgs_isect_bin_bucket_bytes(long long n_super_isects);
 /* exclusive prefix sum of in[n] (i32) -> out[n] (i64 accumulate, stored i32; HGS_ERR_TOO_LARGE is
  * reported through *total >= 2^31 being left for the caller to check); total written to total_dev[0]. */
 int hgs_exclusive_scan_i32(const int32_t* in, int32_t* out, long long* total_dev, long long n, void* temp,
@@ -111,23 +111,32 @@ int hgs_exclusive_scan_i32(const int32_t* in, int32_t* out, long long* total_dev
 /* Unsorted emission (gsplat isect_tiles(sort=False)): cum = exclusive scan of tiles_per_gauss. */
 int hgs_isect_emit(const float* means2d, const int32_t* radii, const float* depths, const int32_t* cum, int C, int N,
                    int tile_size, int tile_w, int tile_h, long long* isect_ids, int32_t* flatten_ids, void* stream);
-/* Sorted path, phase 1 (no host round trip): compact the Gaussians with tiles_per_gauss > 0, depth-order them
- * (stable LSD radix sort of the depth bits, camera-major), gather their tile counts in that order and scan.
- * out: order[<= CN] i32 (flat indices of the n_vis visible Gaussians in (cam, depth, index) order),
- * cum_sorted[<= CN] i32 (exclusive scan of their tile counts), visible_ids[<= CN] i32 or NULL (the same
- * flat indices in ascending order: the work list of the per-Gaussian kernels that only touch visible
- * Gaussians), counts_dev[0] = n_vis, counts_dev[1] = I. */
-int hgs_isect_prepare(const float* depths, const int32_t* tiles_per_gauss, int C, int N, int32_t* order,
-                      int32_t* cum_sorted, int32_t* visible_ids, long long* counts_dev, void* temp,
-                      size_t temp_bytes, void* stream);
-/* Sorted path, phase 2 (n_visible and n_isects read back by the caller to size the outputs): emit
- * (tile key, flat index) pairs in depth order -- one thread per intersection -- stable-partition them by
- * (cam, tile) with LSD radix passes over the tile bits only, then write the final arrays.
+/* Sorted path by BINNING (replaces gsplat's emit + 64-bit CUB radix sort + isect_offset_encode; same results).
+ * The binning / sorting unit is a SUPER-TILE of 2x2 tiles: a Gaussian touches ~2.5x fewer of them than tiles, so
+ * that many fewer keys are scattered and sorted; every tile's range is an order-preserving selection of its
+ * super-tile's sorted keys.
+ * Phase 1 (no host round trip): one pass over tiles_per_gauss compacts the Gaussians with at least one tile, in
+ * ascending flat-index order (single-pass scan, decoupled look-back), and histograms the (camera, super-tile)
+ * bins; one more launch scans the histogram.
+ * out: visible_ids[<= CN] i32 (ascending: the work list of the per-Gaussian kernels that only touch visible
+ * Gaussians), counts_dev[0] = n_vis, counts_dev[1] = I,
+ * counts_dev[2] = number of (Gaussian, super-tile) pairs.
+ * temp (hgs_isect_bin_temp_bytes) must be passed unchanged to phase 2. */
+int hgs_isect_bin_prepare(const float* means2d, const int32_t* radii, const float* depths,
+                          const int32_t* tiles_per_gauss, int C, int N, int tile_size, int tile_w, int tile_h,
+                          int32_t* visible_ids, long long* counts_dev, void* temp, size_t temp_bytes, void* stream);
+/* Phase 2 (counts read back by the caller to size the outputs; n_visible_bound >= counts_dev[0] sizes the grid,
+ * the exact counts are read on the device): every visible Gaussian drops a key (depth bits << 32 | flat index << 4
+ * | mask of the super-tile's tiles it touches; C*N < 2^28) into the ranges of the super-tiles it touches; one CTA per (camera, super-tile) sorts its range on the SM (bitonic network
+ * in registers / shuffles / shared memory; ranges > 2048 keys in chunks merged through L2) and counts the keys of
+ * each of its tiles; a last kernel sums those counts into the per-tile range starts and selects every tile's keys,
+ * in order, from its super-tile's sorted range.
+ * in: counts_dev, temp of phase 1 (it holds the tile boxes and depth bits of the visible Gaussians); bucket: hgs_isect_bin_bucket_bytes(counts[2]) bytes of scratch.
  * out: isect_ids[I] i64, flatten_ids[I] i32, isect_offsets[C*tile_h*tile_w] i32. */
-int hgs_isect_sorted(const float* means2d, const int32_t* radii, const float* depths, const int32_t* order,
-                     const int32_t* cum_sorted, int C, int N, long long n_visible, long long n_isects, int tile_size,
-                     int tile_w, int tile_h, long long* isect_ids, int32_t* flatten_ids, int32_t* isect_offsets,
-                     void* temp, size_t temp_bytes, void* stream);
+int hgs_isect_bin_sorted(const long long* counts_dev, int C, int N, long long n_visible_bound, long long n_isects,
+                         long long n_super_isects, int tile_size, int tile_w, int tile_h, int32_t* isect_offsets,
+                         long long* isect_ids, int32_t* flatten_ids, void* temp, size_t temp_bytes, void* bucket,
+                         size_t bucket_bytes, void* stream);
 /* gsplat isect_offset_encode on already-sorted keys. */
 int hgs_isect_offset_encode(const long long* isect_ids, long long n_isects, int C, int tile_w, int tile_h,
                             int32_t* isect_offsets, void* stream);
@@ -306,13 +315,13 @@ int hgs_anchor_filter(const float* anchor, const int32_t* level, const float* ex
  * densification statistics); a record is one id plus the concatenated rows (padded to a multiple of 4 floats).
  * Each rank owns a mailbox of hgs_exchange_mailbox_bytes() in its own memory, mapped into every peer.
  *   push   : records of the n_rows Gaussians listed in ids[] (unique, ASCENDING: the rank's visible set as written
- *            by hgs_isect_prepare; n_rows <= cap_rows, a multiple of 32) are gathered, staged in shared memory and
+ *            by hgs_isect_bin_prepare; n_rows <= cap_rows, a multiple of 32) are gathered, staged in shared memory and
  *            stored with TMA bulk copies into slot (step & 1, rank) of EVERY mailbox in mailboxes_host[world] (peer
  *            pointers; [rank] is the local one), then flag `rank` of every mailbox is raised to step + 1 (release,
  *            system scope).  n_ids = N, the number of rows of each tensor.
  *   reduce : for every block of consecutive Gaussian ids (n_ids = N rows in each tensor) waits (acquire) for flag
  *            src = 0..world-1 of the local mailbox, merges the sources' records in that order (ids[] must be
- *            ASCENDING, as hgs_isect_prepare's visible_ids are) and overwrites the touched rows of the tensors --
+ *            ASCENDING, as hgs_isect_bin_prepare's visible_ids are) and overwrites the touched rows of the tensors --
  *            the same order on every rank, so all replicas end with bit-identical sums; rows no rank listed are
  *            left as they are (zero).  *status_dev (device int, zero-initialised) is set to 1 if a peer's flag
  *            does not arrive within 20 s.

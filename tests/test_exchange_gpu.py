@@ -183,3 +183,55 @@ def test_exchanges_on_one_gpu_equal_local_autograd(tmp_path):
     mp.spawn(_worker, args=(1, _free_port(), str(tmp_path), 20011, 4), nprocs=1, join=True)
     got = torch.load(os.path.join(str(tmp_path), "r0.pt"))
     assert got["ok"] and got["worst"] < 1e-6, got
+
+
+def _overflow_worker(rank, world, port, out_dir):
+    """a rank whose visible set does not fit cap_rows: nobody hangs, EVERY rank gets zero gradients for that step and
+    the same sticky status, and every rank's next finish() raises (the status copy of the failed step has landed)"""
+    import torch.distributed as dist
+    import horizongs_b200 as hgs
+    from horizongs_b200 import _lib, distributed as D, scenes
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    N, Wd, H = 4000, 160, 112
+    sc = scenes.make_scene(N, 3.0, 1.0, 0.08, 0.5, sh_degree=1, seed=3).to(dev)
+    params = [t.requires_grad_() for t in (sc.means, sc.quats, sc.scales, sc.opacities, sc.colors)]
+    Km = scenes.intrinsics(Wd, H, 70.0).to(dev)
+    ex = D.FusedBackwardExchange(N, cap_rows=64, device=dev)       # far too small for the full view
+    near = scenes.look_at((0.0, -5.0, 2.0), (0.0, 0.0, 0.2)).to(dev)
+    away = scenes.look_at((0.0, -5.0, 2.0), (0.0, -50.0, 2.0)).to(dev)        # sees nothing: fits
+
+    def run(V):
+        with ex.deferred():
+            rc, ra, meta = hgs.rasterization(*params, V[None], Km[None], Wd, H, sh_degree=1, render_mode="RGB+ED")
+            (rc.sum() + ra.sum()).backward()
+        return int(meta["visible_ids"].numel())
+
+    res = {"n_vis": run(near if rank == world - 1 else away)}
+    ex.finish(*params)                      # must not raise and must not hang
+    torch.cuda.synchronize()
+    res["zero"] = all(float(p.grad.abs().max()) == 0.0 for p in params)
+    res["status"] = int(ex.box.status.item())
+    run(away)
+    try:
+        ex.finish(*params)
+        res["raised"] = ""
+    except _lib.HgsError as e:
+        res["raised"] = str(e)
+    torch.save(res, os.path.join(out_dir, f"o{rank}.pt"))
+    ex.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_exchange_overflow_is_a_collective_outcome(tmp_path):
+    import torch.multiprocessing as mp
+    world = min(max(torch.cuda.device_count(), 1), 8)
+    mp.spawn(_overflow_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        got = torch.load(os.path.join(str(tmp_path), f"o{r}.pt"))
+        assert got["status"] == 2 and got["zero"] and "capacity" in got["raised"], (r, got)
+    assert torch.load(os.path.join(str(tmp_path), f"o{world - 1}.pt"))["n_vis"] > 64

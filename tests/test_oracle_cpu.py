@@ -205,7 +205,7 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol(built_lib):
     for name in declared:
         assert hasattr(built_lib, name), f"{name} declared in include/hgs_raster.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
-    assert built_lib.hgs_abi_version() == 1
+    assert built_lib.hgs_abi_version() == 2
     assert built_lib.hgs_status_string(-1).decode().startswith("hgs:")
 
 

@@ -135,6 +135,24 @@ def test_isect_ties_and_huge_gaussians():
     assert torch.equal(ct.cpu(), tiles) and torch.equal(ci.cpu(), ids) and torch.equal(cf.cpu(), flat)
 
 
+@pytest.mark.parametrize("n", [200, 300, 700, 1500, 3000, 4096, 4097, 9000, 12289, 40000])
+def test_isect_deep_tiles_every_sort_class(n):
+    """per-tile ranges of every size class of the tile sort (1..16 keys per thread in registers, and the chunked
+    merge for ranges > 4096), with many exact depth ties: n Gaussians piled onto a 3x2-tile image"""
+    g = torch.Generator().manual_seed(n)
+    m2 = torch.rand(1, n, 2, generator=g) * torch.tensor([48.0, 32.0])
+    radii = torch.randint(1, 20, (1, n), generator=g, dtype=torch.int32)
+    radii[0, ::7] = 0
+    depths = torch.randint(1, max(2, n // 3), (1, n), generator=g).float() * 0.125
+    tiles, ids, flat = O.isect_tiles(m2, radii, depths, 16, 3, 2)
+    off = O.isect_offset_encode(ids, 1, 3, 2)
+    ct, ci, cf, co = hgs.isect_tiles(m2.cuda(), radii.cuda(), depths.cuda(), 16, 3, 2, _with_offsets=True)
+    assert int(torch.diff(torch.cat([off.flatten(), torch.tensor([ids.numel()])])).max()) > 0.3 * n
+    assert torch.equal(ct.cpu(), tiles) and torch.equal(co.cpu(), off)
+    assert torch.equal(ci.cpu(), ids), f"{int((ci.cpu() != ids).sum())} of {ids.numel()} keys differ"
+    assert torch.equal(cf.cpu(), flat), f"{int((cf.cpu() != flat).sum())} of {flat.numel()} values differ"
+
+
 def test_isect_empty():
     m2 = torch.zeros(1, 10, 2).cuda()
     radii = torch.zeros(1, 10, dtype=torch.int32).cuda()
