@@ -806,6 +806,14 @@ __global__ void unpack_vpack_kernel(const float* __restrict__ vpack, const int32
     v_opacities[i] = q1.y;
 }
 
+// rows[ids[j]] := 0 (16-byte stores; R4 float4 per row)
+__global__ void zero_rows_kernel(float4* __restrict__ rows, int R4, const int32_t* __restrict__ ids, long long n_ids) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_ids * R4) return;
+    const long long j = t / R4;
+    rows[(long long)ids[j] * R4 + (t - j * R4)] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 }  // namespace
 
 #define HGS_DISPATCH_D(D, CALL)                     \
@@ -947,6 +955,18 @@ HGS_API int hgs_blend3d_unpack(const float* vpack, const int32_t* vis_ids, long 
     if ((e = cudaMemsetAsync(v_opacities, 0, (size_t)CN * sizeof(float), st)) != cudaSuccess) return (int)e;
     if (n_vis == 0) return 0;
     unpack_vpack_kernel<<<hgs_ceil_div(n_vis, 256), 256, 0, st>>>(vpack, vis_ids, n_vis, v_means2d, v_opacities);
+    HGS_LAUNCH_CHECK();
+    return 0;
+}
+
+HGS_API int hgs_zero_rows(float* rows, int row_floats, const int32_t* ids, long long n_ids, void* stream) {
+    if (rows == nullptr || row_floats <= 0 || row_floats % 4 != 0 || n_ids < 0 || (reinterpret_cast<size_t>(rows) & 15))
+        return HGS_ERR_INVALID_ARG;
+    if (n_ids == 0) return 0;
+    if (ids == nullptr) return HGS_ERR_INVALID_ARG;
+    const int R4 = row_floats / 4;
+    zero_rows_kernel<<<hgs_ceil_div(n_ids * R4, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(rows), R4,
+                                                                                      ids, n_ids);
     HGS_LAUNCH_CHECK();
     return 0;
 }

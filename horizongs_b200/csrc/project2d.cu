@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(PB) project2d_bwd_kernel(
     const int32_t* __restrict__ radii, const float* __restrict__ v_means2d, int ld_m2,
     const float* __restrict__ v_depths, int ld_d, const float* __restrict__ v_ray_transforms, int ld_rt,
     const float* __restrict__ v_normals, int ld_n, float* __restrict__ v_means, float* __restrict__ v_quats,
-    float* __restrict__ v_scales) {
+    float* __restrict__ v_scales, int acc) {
     const long long n = (long long)blockIdx.x * PB + threadIdx.x;
     if (n >= N) return;
     bool any = false;
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(PB) project2d_bwd_kernel(
     reinterpret_cast<float4*>(v_quats)[n] = make_float4(g_quat[0], g_quat[1], g_quat[2], g_quat[3]);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        v_means[n * 3 + k] = g_mean[k];
+        v_means[n * 3 + k] = acc ? v_means[n * 3 + k] + g_mean[k] : g_mean[k];
         v_scales[n * 3 + k] = g_scale[k];
     }
 }
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(PB) project2d_bwd_vis_kernel(
     const int32_t* __restrict__ vis_ids, long long n_vis, const float* __restrict__ v_means2d, int ld_m2,
     const float* __restrict__ v_depths, int ld_d, const float* __restrict__ v_ray_transforms, int ld_rt,
     const float* __restrict__ v_normals, int ld_n, float* __restrict__ v_means, float* __restrict__ v_quats,
-    float* __restrict__ v_scales) {
+    float* __restrict__ v_scales, int acc) {
     const long long j = (long long)blockIdx.x * PB + threadIdx.x;
     if (j >= n_vis) return;
     const long long idx = vis_ids[j];
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(PB) project2d_bwd_vis_kernel(
         reinterpret_cast<float4*>(v_quats)[n] = make_float4(g_quat[0], g_quat[1], g_quat[2], g_quat[3]);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            v_means[n * 3 + k] = g_mean[k];
+            v_means[n * 3 + k] = acc ? v_means[n * 3 + k] + g_mean[k] : g_mean[k];
             v_scales[n * 3 + k] = g_scale[k];
         }
     } else {
@@ -181,7 +181,7 @@ HGS_API int hgs_project2d_bwd(const float* means, const float* quats, const floa
                               const int32_t* radii, const float* v_means2d, int ld_means2d, const float* v_depths,
                               int ld_depths, const float* v_ray_transforms, int ld_ray_transforms,
                               const float* v_normals, int ld_normals, const int32_t* vis_ids, long long n_vis,
-                              float* v_means, float* v_quats, float* v_scales, void* stream) {
+                              float* v_means, float* v_quats, float* v_scales, int accumulate_means, void* stream) {
     (void)width; (void)height;
     if (C <= 0 || N < 0 || n_vis < 0 || ld_means2d < 2 || ld_depths < 1 || ld_ray_transforms < 9 || ld_normals < 3)
         return HGS_ERR_INVALID_ARG;
@@ -189,19 +189,20 @@ HGS_API int hgs_project2d_bwd(const float* means, const float* quats, const floa
     cudaStream_t st = (cudaStream_t)stream;
     if (vis_ids != nullptr) {
         cudaError_t e;
-        if ((e = cudaMemsetAsync(v_means, 0, (size_t)N * 3 * sizeof(float), st)) != cudaSuccess) return (int)e;
+        if (!accumulate_means && (e = cudaMemsetAsync(v_means, 0, (size_t)N * 3 * sizeof(float), st)) != cudaSuccess)
+            return (int)e;
         if ((e = cudaMemsetAsync(v_quats, 0, (size_t)N * 4 * sizeof(float), st)) != cudaSuccess) return (int)e;
         if ((e = cudaMemsetAsync(v_scales, 0, (size_t)N * 3 * sizeof(float), st)) != cudaSuccess) return (int)e;
         if (n_vis == 0) return 0;
         project2d_bwd_vis_kernel<<<hgs_ceil_div(n_vis, PB), PB, 0, st>>>(
             means, quats, scales, viewmats, Ks, C, N, near_plane, far_plane, vis_ids, n_vis, v_means2d, ld_means2d,
-            v_depths, ld_depths, v_ray_transforms, ld_ray_transforms, v_normals, ld_normals, v_means, v_quats, v_scales);
+            v_depths, ld_depths, v_ray_transforms, ld_ray_transforms, v_normals, ld_normals, v_means, v_quats, v_scales, accumulate_means);
         HGS_LAUNCH_CHECK();
         return 0;
     }
     project2d_bwd_kernel<<<hgs_ceil_div(N, PB), PB, 0, st>>>(
         means, quats, scales, viewmats, Ks, C, N, near_plane, far_plane, radii, v_means2d, ld_means2d, v_depths,
-        ld_depths, v_ray_transforms, ld_ray_transforms, v_normals, ld_normals, v_means, v_quats, v_scales);
+        ld_depths, v_ray_transforms, ld_ray_transforms, v_normals, ld_normals, v_means, v_quats, v_scales, accumulate_means);
     HGS_LAUNCH_CHECK();
     return 0;
 }

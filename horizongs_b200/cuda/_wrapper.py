@@ -109,6 +109,7 @@ class _Project3D(torch.autograd.Function):
                 calc_compensations, tile_size, holder):
         L = _lib.lib()
         ctx.holder = holder       # rendering.py drops the visible-Gaussian work list here once it is known
+        ctx.set_materialize_grads(False)      # no zero tensors for the gradients of the integer outputs
         C, N = viewmats.shape[0], means.shape[0]
         dev = means.device
         radii = torch.empty((C, N), dtype=torch.int32, device=dev)
@@ -140,7 +141,12 @@ class _Project3D(torch.autograd.Function):
         width, height, eps2d, near_plane, far_plane = ctx.cfg
         L = _lib.lib()
         C, N = radii.shape
-        v_means = torch.empty_like(means)
+        # the SH stage ran its backward first and left its direction gradient for the means here: add to it
+        # instead of letting autograd sum two dense [N,3] tensors
+        v_means = _take_sh_means_grad(ctx.holder, means)
+        acc = v_means is not None
+        if not acc:
+            v_means = torch.empty_like(means)
         v_quats = torch.empty_like(quats)
         v_scales = torch.empty_like(scales)
         v_means2d, ld_m = _rows(means.new_zeros((C, N, 2)) if v_means2d is None else v_means2d, 2)
@@ -151,10 +157,21 @@ class _Project3D(torch.autograd.Function):
         check(L.hgs_project3d_bwd(ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), C, N, width, height,
                                   eps2d, near_plane, far_plane, ptr(radii), ptr(v_means2d), ld_m, ptr(v_depths), ld_d,
                                   ptr(v_conics), ld_c, ptr(vis), 0 if vis is None else vis.numel(), ptr(v_means),
-                                  ptr(v_quats), ptr(v_scales), _stream()),
+                                  ptr(v_quats), ptr(v_scales), int(acc), _stream()),
               "hgs_project3d_bwd")
         _mark("project3d_bwd", 1)
         return (v_means, v_quats, v_scales) + (None,) * 11
+
+
+def _take_sh_means_grad(holder, means):
+    """the [N,3] direction gradient the SH backward of the same rasterization call parked in `holder` (or None)"""
+    if holder is None:
+        return None
+    holder["proj_bwd_done"] = True
+    g = holder.pop("v_means_sh", None)
+    if g is not None and (g.shape != means.shape or not g.is_contiguous()):
+        raise _lib.HgsError("internal: parked SH gradient has the wrong layout")
+    return g
 
 
 def _check_proj_inputs(means, quats, scales, viewmats, Ks):
@@ -244,6 +261,12 @@ class _SphericalHarmonics(torch.autograd.Function):
                            ptr(v_coeffs), ptr(v_dirs), ptr(v_means), _stream()),
               "hgs_sh_bwd")
         _mark("sh_bwd", 1)
+        if v_means is not None and ctx.holder is not None and ctx.holder.get("park_means_grad") and \
+                not ctx.holder.get("proj_bwd_done"):
+            # the projection backward of this call has not run yet: it will ADD its gradient into this tensor
+            # (hgs_project3d_bwd accumulate_means) -- saves autograd's dense [N,3] + [N,3] addition
+            ctx.holder["v_means_sh"] = v_means
+            v_means = None
         return None, v_dirs, v_means, None, v_coeffs, None, None, None, None, None, None
 
 
@@ -407,10 +430,12 @@ class _Blend3D(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means2d, conics, colors, depths, opacities, backgrounds, width, height, tile_size,
-                isect_offsets, flatten_ids, absgrad, radii, normalize_depth, vis_ids=None, defer=None, records=None):
+                isect_offsets, flatten_ids, absgrad, radii, normalize_depth, vis_ids=None, defer=None, records=None,
+                aux=None):
         L = _lib.lib()
         ctx.defer = defer
         ctx.vis_ids = vis_ids
+        ctx.aux = aux           # weak references to the per-Gaussian inputs (does anybody retain their gradient?)
         C, N = opacities.shape
         CH = colors.shape[-1]
         D = CH + (1 if depths is not None else 0)
@@ -451,11 +476,11 @@ class _Blend3D(torch.autograd.Function):
         L = _lib.lib()
         v_render_colors = v_render_colors.contiguous()
         v_render_alphas = v_render_alphas.contiguous()
-        tail = (None,) * 11
+        tail = (None,) * 12
         if ctx.fast:
             records, backgrounds, isect_offsets, flatten_ids, render_colors, render_alphas, last_ids = ctx.saved_tensors
             (C, N, _), has_depth = ctx.shapes
-            vpack = torch.zeros((C, N, 12), dtype=torch.float32, device=records.device)
+            vpack = _vpack_alloc(C, N, 12, ctx.vis_ids, ctx.aux, records.device)
             _mark("blend3d_bwd", 0)
             check(L.hgs_blend3d_bwd_packed(ptr(records), ptr(backgrounds), C, D, int(normalize_depth), width, height,
                                            tile_size, ptr(isect_offsets), ptr(flatten_ids), flatten_ids.numel(),
@@ -520,8 +545,22 @@ def _pack3d(means2d, conics, colors, depths, opacities, radii, vis_ids, n_vis_de
     return records
 
 
+def _vpack_alloc(C, N, width, vis_ids, aux, dev):
+    """the packed gradient accumulator of a blend backward.  Every consumer of its rows (projection / SH backward,
+    the dense unpack, the fused exchange) goes through the work list of visible Gaussians, so only those rows are
+    zeroed (hgs_zero_rows) -- unless there is no work list, or somebody retains the gradient of one of the
+    per-Gaussian blend inputs and could look at the rows of culled Gaussians: then the whole buffer is zero-filled."""
+    dense = vis_ids is None or aux is None or any(r() is None or r().retains_grad for r in aux)
+    if dense:
+        return torch.zeros((C, N, width), dtype=torch.float32, device=dev)
+    vpack = torch.empty((C, N, width), dtype=torch.float32, device=dev)
+    check(_lib.lib().hgs_zero_rows(ptr(vpack), width, ptr(vis_ids), vis_ids.numel(), _stream()), "hgs_zero_rows")
+    return vpack
+
+
 def _blend3d(means2d, conics, colors, depths, opacities, backgrounds, width, height, tile_size, isect_offsets,
-             flatten_ids, absgrad=False, radii=None, normalize_depth=False, vis_ids=None, defer=None, records=None):
+             flatten_ids, absgrad=False, radii=None, normalize_depth=False, vis_ids=None, defer=None, records=None,
+             aux=None):
     if tile_size not in _TILE_SIZES:
         raise NotImplementedError(f"tile_size {tile_size} is not supported (supported: {_TILE_SIZES})")
     D = colors.shape[-1] + (1 if depths is not None else 0)
@@ -530,7 +569,8 @@ def _blend3d(means2d, conics, colors, depths, opacities, backgrounds, width, hei
     return _Blend3D.apply(_f32c(means2d, "means2d"), _f32c(conics, "conics"), _f32c(colors, "colors"),
                           _f32c(depths, "depths"), _f32c(opacities, "opacities"), _f32c(backgrounds, "backgrounds"),
                           int(width), int(height), int(tile_size), isect_offsets.contiguous(),
-                          flatten_ids.contiguous(), bool(absgrad), radii, bool(normalize_depth), vis_ids, defer, records)
+                          flatten_ids.contiguous(), bool(absgrad), radii, bool(normalize_depth), vis_ids, defer, records,
+                          aux)
 
 
 def rasterize_to_pixels(means2d: Tensor, conics: Tensor, colors: Tensor, opacities: Tensor, image_width: int,
@@ -556,6 +596,7 @@ class _Project2D(torch.autograd.Function):
                 tile_size, holder):
         L = _lib.lib()
         ctx.holder = holder
+        ctx.set_materialize_grads(False)
         C, N = viewmats.shape[0], means.shape[0]
         dev = means.device
         radii = torch.empty((C, N), dtype=torch.int32, device=dev)
@@ -583,7 +624,10 @@ class _Project2D(torch.autograd.Function):
         width, height, near_plane, far_plane = ctx.cfg
         L = _lib.lib()
         C, N = radii.shape
-        v_means = torch.empty_like(means)
+        v_means = _take_sh_means_grad(ctx.holder, means)
+        acc = v_means is not None
+        if not acc:
+            v_means = torch.empty_like(means)
         v_quats = torch.empty_like(quats)
         v_scales = torch.empty_like(scales)
         v_means2d, ld_m = _rows(v_means2d, 2)
@@ -595,7 +639,7 @@ class _Project2D(torch.autograd.Function):
         check(L.hgs_project2d_bwd(ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), C, N, width, height,
                                   near_plane, far_plane, ptr(radii), ptr(v_means2d), ld_m, ptr(v_depths), ld_d,
                                   ptr(v_rt), ld_rt, ptr(v_normals), ld_n, ptr(vis), 0 if vis is None else vis.numel(),
-                                  ptr(v_means), ptr(v_quats), ptr(v_scales), _stream()), "hgs_project2d_bwd")
+                                  ptr(v_means), ptr(v_quats), ptr(v_scales), int(acc), _stream()), "hgs_project2d_bwd")
         _mark("project2d_bwd", 1)
         return (v_means, v_quats, v_scales) + (None,) * 9
 

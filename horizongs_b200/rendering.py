@@ -7,6 +7,7 @@ only sequences them and owns the tensors.  There is no CPU or PyTorch fallback.
 from __future__ import annotations
 
 import math
+import weakref
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -95,7 +96,7 @@ def rasterization(
     tile_width = math.ceil(width / float(tile_size))
     tile_height = math.ceil(height / float(tile_size))
 
-    holder: Dict = {}
+    holder: Dict = {"park_means_grad": sh_degree is not None}
     radii, means2d, depths, conics, comps, tiles_per_gauss = W._project3d(
         means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip,
         rasterize_mode == "antialiased", tile_size, holder)
@@ -143,7 +144,8 @@ def rasterization(
 
     render_colors, render_alphas = W._blend3d(means2d, conics, feats, depth_ch, opac, bgs, width, height, tile_size,
                                               isect_offsets, flatten_ids, absgrad, radii=radii,
-                                              normalize_depth=fuse_norm, vis_ids=vis_ids, defer=defer, records=records)
+                                              normalize_depth=fuse_norm, vis_ids=vis_ids, defer=defer, records=records,
+                                              aux=[weakref.ref(t) for t in (conics, feats, depth_ch) if t is not None])
     if render_mode in ("ED", "RGB+ED") and not fuse_norm:
         render_colors = torch.cat(
             [render_colors[..., :-1], render_colors[..., -1:] / render_alphas.clamp(min=1e-10)], dim=-1)
@@ -219,7 +221,7 @@ def rasterization_2dgs(
     tile_width = math.ceil(width / float(tile_size))
     tile_height = math.ceil(height / float(tile_size))
 
-    holder: Dict = {}
+    holder: Dict = {"park_means_grad": sh_degree is not None}
     radii, means2d, depths, ray_transforms, normals, tiles_per_gauss = W._project2d(
         means, quats, scales, viewmats, Ks, width, height, near_plane, far_plane, radius_clip, tile_size, holder)
     opac = opacities[None] if C == 1 else opacities[None].expand(C, -1)
@@ -242,7 +244,7 @@ def rasterization_2dgs(
                      campos=_camera_positions(viewmats.detach()).contiguous(), width=width, height=height, eps2d=eps2d,
                      near_plane=near_plane, far_plane=far_plane, sh_degree=sh_degree, n=N)
 
-    feats = _per_view_features(means, colors, viewmats, radii, sh_degree, C, vis_ids, defer)
+    feats = _per_view_features(means, colors, viewmats, radii, sh_degree, C, vis_ids, defer, holder=holder)
     feats, depth_ch, bgs = _mode_features(feats, depths, backgrounds, render_mode)
     n_ch = feats.shape[-1] + (1 if depth_ch is not None else 0)
     fuse_norm = render_mode in ("ED", "RGB+ED") and n_ch in (1, 3, 4)

@@ -52,13 +52,15 @@ int hgs_project3d_fwd(const float* means, const float* quats, const float* scale
  * stride in floats (ld_* = 2, 1, 3 when dense) so that slices of the packed blend-gradient buffer can be
  * passed without a copy;  out (overwritten, summed over cameras): v_means[N,3], v_quats[N,4], v_scales[N,3].
  * vis_ids (or NULL): work list of the n_vis visible flat indices c*N+n from hgs_isect_bin_prepare -- one thread per
- * visible pair instead of one per Gaussian (same results; with C > 1 the sums over cameras use atomics). */
+ * visible pair instead of one per Gaussian (same results; with C > 1 the sums over cameras use atomics).
+ * accumulate_means != 0: v_means already holds a gradient (the SH direction gradient of hgs_sh_bwd, zero in the rows of
+ * culled Gaussians) and the projection gradient is ADDED to it instead of overwriting it. */
 int hgs_project3d_bwd(const float* means, const float* quats, const float* scales, const float* viewmats,
                       const float* Ks, int C, int N, int width, int height, float eps2d, float near_plane,
                       float far_plane, const int32_t* radii, const float* v_means2d, int ld_means2d,
                       const float* v_depths, int ld_depths, const float* v_conics, int ld_conics,
                       const int32_t* vis_ids, long long n_vis, float* v_means, float* v_quats, float* v_scales,
-                      void* stream);
+                      int accumulate_means, void* stream);
 
 /* ---- a4: fully_fused_projection_2dgs (render.py:171-186; inside rasterization_2dgs render.py:62) --
  * out: radii[C,N], means2d[C,N,2], depths[C,N], ray_transforms[C,N,3,3] (rows M0,M1,M2 of (K [R|t] H)),
@@ -74,7 +76,7 @@ int hgs_project2d_bwd(const float* means, const float* quats, const float* scale
                       const int32_t* radii, const float* v_means2d, int ld_means2d, const float* v_depths,
                       int ld_depths, const float* v_ray_transforms, int ld_ray_transforms, const float* v_normals,
                       int ld_normals, const int32_t* vis_ids, long long n_vis, float* v_means, float* v_quats,
-                      float* v_scales, void* stream);
+                      float* v_scales, int accumulate_means, void* stream);
 
 /* ---- a7: spherical_harmonics (inside rasterization* when sh_degree is not None) ------------------
  * Direction of Gaussian n for camera c is dirs[c,n,:] if dirs != NULL, else means[n,:] - campos[c,:]
@@ -188,6 +190,9 @@ int hgs_blend3d_bwd_packed(const void* records, const float* backgrounds, int C,
  * and v_opacities[CN] -- what autograd consumes as dense tensors (retain_grad of meta["means2d"], the opacity leaf). */
 int hgs_blend3d_unpack(const float* vpack, const int32_t* vis_ids, long long n_vis, long long CN, float* v_means2d,
                        float* v_opacities, void* stream);
+/* rows[ids[j]] of an [*, row_floats] float buffer (row_floats % 4 == 0, 16-byte aligned) := 0 for j < n_ids: zeroes the
+ * accumulator rows of the visible Gaussians only, where every reader of the buffer goes through the same work list. */
+int hgs_zero_rows(float* rows, int row_floats, const int32_t* ids, long long n_ids, void* stream);
 
 /* Measurement aid (not on the product path): counters[0] += P_eval, the (pixel, Gaussian) pairs a per-pixel
  * front-to-back loop visits before the pixel stops; counters[1] += P_blend, the pairs actually blended.
