@@ -26,7 +26,7 @@ SIGNATURES = {
     "hgs_project2d_fwd": (_i, [_p] * 5 + [_i] * 4 + [_f] * 3 + [_i] + [_p] * 6 + [_p]),
     "hgs_project2d_bwd": (_i, [_p] * 5 + [_i] * 4 + [_f] * 2 + [_p, _p, _i, _p, _i, _p, _i, _p, _i, _p, _ll] + [_p] * 3 + [_i, _p]),
     "hgs_sh_fwd": (_i, [_i, _i] + [_p] * 6 + [_ll, _p, _i, _i, _i] + [_p] + [_p]),
-    "hgs_sh_bwd": (_i, [_i, _i] + [_p] * 6 + [_ll, _p, _p, _i, _i, _i, _i] + [_p] * 3 + [_p]),
+    "hgs_sh_bwd": (_i, [_i, _i] + [_p] * 6 + [_ll, _p, _p, _i, _i, _i, _i] + [_p] * 3 + [_i, _p]),
     "hgs_isect_count": (_i, [_p, _p, _ll, _i, _i, _i, _p, _p]),
     "hgs_scan_temp_bytes": (_sz, [_ll]),
     "hgs_isect_bin_temp_bytes": (_sz, [_ll, _i, _i, _i]),
@@ -42,7 +42,7 @@ SIGNATURES = {
     "hgs_blend3d_pack": (_i, [_p] * 7 + [_ll, _p, _ll, _i, _p, _p]),
     "hgs_blend3d_fwd_packed": (_i, [_p, _p] + [_i] * 6 + [_p, _p, _ll] + [_p] * 3 + [_p]),
     "hgs_blend3d_bwd_packed": (_i, [_p, _p] + [_i] * 6 + [_p, _p, _ll] + [_p] * 6 + [_p]),
-    "hgs_blend3d_unpack": (_i, [_p, _p, _ll, _ll, _p, _p, _p]),
+    "hgs_blend3d_unpack": (_i, [_p, _p, _ll, _ll, _p, _p, _i, _p]),
     "hgs_zero_rows": (_i, [_p, _i, _p, _ll, _p]),
     "hgs_blend3d_stats": (_i, [_p, _i, _i, _i, _i, _p, _p, _ll, _p, _p]),
     "hgs_blend2d_pack_bytes": (_sz, [_ll]),

@@ -945,14 +945,16 @@ HGS_API int hgs_blend3d_bwd_packed(const void* records, const float* backgrounds
 }
 
 HGS_API int hgs_blend3d_unpack(const float* vpack, const int32_t* vis_ids, long long n_vis, long long CN, float* v_means2d,
-                               float* v_opacities, void* stream) {
+                               float* v_opacities, int outputs_zeroed, void* stream) {
     if (vpack == nullptr || v_means2d == nullptr || v_opacities == nullptr || n_vis < 0 || CN < 0 ||
         (n_vis > 0 && vis_ids == nullptr))
         return HGS_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
-    if ((e = cudaMemsetAsync(v_means2d, 0, (size_t)CN * 2 * sizeof(float), st)) != cudaSuccess) return (int)e;
-    if ((e = cudaMemsetAsync(v_opacities, 0, (size_t)CN * sizeof(float), st)) != cudaSuccess) return (int)e;
+    if (!outputs_zeroed) {
+        if ((e = cudaMemsetAsync(v_means2d, 0, (size_t)CN * 2 * sizeof(float), st)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemsetAsync(v_opacities, 0, (size_t)CN * sizeof(float), st)) != cudaSuccess) return (int)e;
+    }
     if (n_vis == 0) return 0;
     unpack_vpack_kernel<<<hgs_ceil_div(n_vis, 256), 256, 0, st>>>(vpack, vis_ids, n_vis, v_means2d, v_opacities);
     HGS_LAUNCH_CHECK();

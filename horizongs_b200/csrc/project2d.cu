@@ -181,7 +181,7 @@ HGS_API int hgs_project2d_bwd(const float* means, const float* quats, const floa
                               const int32_t* radii, const float* v_means2d, int ld_means2d, const float* v_depths,
                               int ld_depths, const float* v_ray_transforms, int ld_ray_transforms,
                               const float* v_normals, int ld_normals, const int32_t* vis_ids, long long n_vis,
-                              float* v_means, float* v_quats, float* v_scales, int accumulate_means, void* stream) {
+                              float* v_means, float* v_quats, float* v_scales, int flags, void* stream) {
     (void)width; (void)height;
     if (C <= 0 || N < 0 || n_vis < 0 || ld_means2d < 2 || ld_depths < 1 || ld_ray_transforms < 9 || ld_normals < 3)
         return HGS_ERR_INVALID_ARG;
@@ -189,10 +189,11 @@ HGS_API int hgs_project2d_bwd(const float* means, const float* quats, const floa
     cudaStream_t st = (cudaStream_t)stream;
     if (vis_ids != nullptr) {
         cudaError_t e;
-        if (!accumulate_means && (e = cudaMemsetAsync(v_means, 0, (size_t)N * 3 * sizeof(float), st)) != cudaSuccess)
+        const int accumulate_means = flags & 1, zeroed = flags & 2;   // see include/hgs_raster.h
+        if (!accumulate_means && !zeroed && (e = cudaMemsetAsync(v_means, 0, (size_t)N * 3 * sizeof(float), st)) != cudaSuccess)
             return (int)e;
-        if ((e = cudaMemsetAsync(v_quats, 0, (size_t)N * 4 * sizeof(float), st)) != cudaSuccess) return (int)e;
-        if ((e = cudaMemsetAsync(v_scales, 0, (size_t)N * 3 * sizeof(float), st)) != cudaSuccess) return (int)e;
+        if (!zeroed && (e = cudaMemsetAsync(v_quats, 0, (size_t)N * 4 * sizeof(float), st)) != cudaSuccess) return (int)e;
+        if (!zeroed && (e = cudaMemsetAsync(v_scales, 0, (size_t)N * 3 * sizeof(float), st)) != cudaSuccess) return (int)e;
         if (n_vis == 0) return 0;
         project2d_bwd_vis_kernel<<<hgs_ceil_div(n_vis, PB), PB, 0, st>>>(
             means, quats, scales, viewmats, Ks, C, N, near_plane, far_plane, vis_ids, n_vis, v_means2d, ld_means2d,
@@ -202,7 +203,7 @@ HGS_API int hgs_project2d_bwd(const float* means, const float* quats, const floa
     }
     project2d_bwd_kernel<<<hgs_ceil_div(N, PB), PB, 0, st>>>(
         means, quats, scales, viewmats, Ks, C, N, near_plane, far_plane, radii, v_means2d, ld_means2d, v_depths,
-        ld_depths, v_ray_transforms, ld_ray_transforms, v_normals, ld_normals, v_means, v_quats, v_scales, accumulate_means);
+        ld_depths, v_ray_transforms, ld_ray_transforms, v_normals, ld_normals, v_means, v_quats, v_scales, flags & 1);
     HGS_LAUNCH_CHECK();
     return 0;
 }

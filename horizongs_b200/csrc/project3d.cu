@@ -304,17 +304,18 @@ HGS_API int hgs_project3d_bwd(const float* means, const float* quats, const floa
                               float far_plane, const int32_t* radii, const float* v_means2d, int ld_means2d,
                               const float* v_depths, int ld_depths, const float* v_conics, int ld_conics,
                               const int32_t* vis_ids, long long n_vis, float* v_means, float* v_quats,
-                              float* v_scales, int accumulate_means, void* stream) {
+                              float* v_scales, int flags, void* stream) {
     if (C <= 0 || N < 0 || width <= 0 || height <= 0 || ld_means2d < 2 || ld_conics < 3 || ld_depths < 1 || n_vis < 0)
         return HGS_ERR_INVALID_ARG;
     if (N == 0) return 0;
     if (vis_ids != nullptr) {
         cudaStream_t st = (cudaStream_t)stream;
         cudaError_t e;
-        if (!accumulate_means && (e = cudaMemsetAsync(v_means, 0, (size_t)N * 3 * sizeof(float), st)) != cudaSuccess)
+        const int accumulate_means = flags & 1, zeroed = flags & 2;   // see include/hgs_raster.h
+        if (!accumulate_means && !zeroed && (e = cudaMemsetAsync(v_means, 0, (size_t)N * 3 * sizeof(float), st)) != cudaSuccess)
             return (int)e;
-        if ((e = cudaMemsetAsync(v_quats, 0, (size_t)N * 4 * sizeof(float), st)) != cudaSuccess) return (int)e;
-        if ((e = cudaMemsetAsync(v_scales, 0, (size_t)N * 3 * sizeof(float), st)) != cudaSuccess) return (int)e;
+        if (!zeroed && (e = cudaMemsetAsync(v_quats, 0, (size_t)N * 4 * sizeof(float), st)) != cudaSuccess) return (int)e;
+        if (!zeroed && (e = cudaMemsetAsync(v_scales, 0, (size_t)N * 3 * sizeof(float), st)) != cudaSuccess) return (int)e;
         if (n_vis == 0) return 0;
         project3d_bwd_vis_kernel<<<hgs_ceil_div(n_vis, PB), PB, 0, st>>>(
             means, quats, scales, viewmats, Ks, C, N, width, height, eps2d, near_plane, far_plane, vis_ids, n_vis,
@@ -324,7 +325,7 @@ HGS_API int hgs_project3d_bwd(const float* means, const float* quats, const floa
     }
     project3d_bwd_kernel<<<hgs_ceil_div(N, PB), PB, 0, (cudaStream_t)stream>>>(
         means, quats, scales, viewmats, Ks, C, N, width, height, eps2d, near_plane, far_plane, radii, v_means2d,
-        ld_means2d, v_depths, ld_depths, v_conics, ld_conics, v_means, v_quats, v_scales, accumulate_means);
+        ld_means2d, v_depths, ld_depths, v_conics, ld_conics, v_means, v_quats, v_scales, flags & 1);
     HGS_LAUNCH_CHECK();
     return 0;
 }

@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(SB) sh_bwd_fused_kernel(const float* __restric
 //   3. runs sh_grad_one per lane, leaves the coefficient-gradient row in the tile, writes the direction gradient,
 //   4. writes the 32 coefficient-gradient rows with coalesced stores.
 constexpr int SHW = 8;   // warps per CTA
-template <int DEG>
+template <int DEG, bool ZFILL>
 __global__ void __launch_bounds__(SHW * 32) sh_bwd_rounds_kernel(const float* __restrict__ means,
                                                                 const float* __restrict__ campos,
                                                                 const float* __restrict__ coeffs,
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(SHW * 32) sh_bwd_rounds_kernel(const float* __
         }
         x = means[n * 3] - campos[0]; y = means[n * 3 + 1] - campos[1]; z = means[n * 3 + 2] - campos[2];
     }
-    {
+    if (ZFILL) {
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (v_means != nullptr)
             for (long long e = lo * 3 + lane; e < hi * 3; e += 32) v_means[e] = 0.f;
@@ -373,7 +373,7 @@ HGS_API int hgs_sh_fwd(int degree, int K, const float* dirs, const float* means,
 HGS_API int hgs_sh_bwd(int degree, int K, const float* dirs, const float* means, const float* campos,
                        const float* coeffs, const int32_t* radii, const int32_t* vis_ids, long long n_vis,
                        const float* colors, const float* v_colors, int ld_v_colors, int C, int N, int post,
-                       float* v_coeffs, float* v_dirs, float* v_means, void* stream) {
+                       float* v_coeffs, float* v_dirs, float* v_means, int outputs_zeroed, void* stream) {
     if (degree < 0 || degree > 4 || K < (degree + 1) * (degree + 1) || C <= 0 || N < 0 || ld_v_colors < 3 || n_vis < 0)
         return HGS_ERR_INVALID_ARG;
     if (dirs == nullptr && (means == nullptr || campos == nullptr)) return HGS_ERR_INVALID_ARG;
@@ -381,15 +381,23 @@ HGS_API int hgs_sh_bwd(int degree, int K, const float* dirs, const float* means,
     if (N == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (vis_ids != nullptr && C == 1 && dirs == nullptr && v_dirs == nullptr && n_vis < (1ll << 31)) {
-        // rasterization path, one camera: dense-warp rounds over the visible work list (zero fill included)
+        // rasterization path, one camera: dense-warp rounds over the visible work list; the rows of the culled
+        // Gaussians are zeroed by memsets at copy-engine speed, the kernel only writes the visible rows
         const int n_rounds = (int)((n_vis + 31) / 32 < 1 ? 1 : (n_vis + 31) / 32);
         const int grid = hgs_ceil_div(n_rounds, SHW);
+        if (!outputs_zeroed) {
+            cudaError_t e = cudaMemsetAsync(v_coeffs, 0, (size_t)N * K * 3 * sizeof(float), st);
+            if (e != cudaSuccess) return (int)e;
+            if (v_means != nullptr && (e = cudaMemsetAsync(v_means, 0, (size_t)N * 3 * sizeof(float), st)) != cudaSuccess)
+                return (int)e;
+        }
 #define LAUNCH(DEG)                                                                                                \
     {                                                                                                              \
         const size_t smem = (size_t)SHW * 32 * ((((DEG) + 1) * ((DEG) + 1) * 3) | 1) * sizeof(float);              \
-        cudaFuncSetAttribute(sh_bwd_rounds_kernel<DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-        sh_bwd_rounds_kernel<DEG><<<grid, SHW * 32, smem, st>>>(means, campos, coeffs, vis_ids, (int)n_vis, colors, \
-                                                               v_colors, ld_v_colors, N, K, post, v_coeffs, v_means); \
+        cudaFuncSetAttribute(sh_bwd_rounds_kernel<DEG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        sh_bwd_rounds_kernel<DEG, false><<<grid, SHW * 32, smem, st>>>(means, campos, coeffs, vis_ids, (int)n_vis,     \
+                                                                      colors, v_colors, ld_v_colors, N, K, post,      \
+                                                                      v_coeffs, v_means);                            \
     }
         switch (degree) {
             case 0: LAUNCH(0) break;

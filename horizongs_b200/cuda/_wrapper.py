@@ -65,6 +65,41 @@ def current_deferred_sink():
     return _DEFER_SINK
 
 
+_SIDE_STREAMS = {}
+
+
+def _prezero_async(holder, shapes, dev):
+    """Start zero-filling the dense gradient tensors of a rasterization call's backward on a SECOND stream, so that
+    the ~1 GB of memsets (6 M Gaussians) runs in the shadow of the compute-bound blend backward instead of in front of
+    the SH / projection backward kernels.  holder["zeros"] = {name: tensor}, holder["zeros_event"] = completion."""
+    main = torch.cuda.current_stream(dev)
+    side = _SIDE_STREAMS.get(dev)
+    if side is None:
+        side = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    bufs = {k: torch.empty(shp, dtype=torch.float32, device=dev) for k, shp in shapes.items()}
+    side.wait_stream(main)              # the allocator may hand out memory whose last use is still queued on `main`
+    with torch.cuda.stream(side):
+        for t in bufs.values():
+            t.zero_()
+            t.record_stream(side)
+    holder["zeros"] = bufs
+    holder["zeros_event"] = side.record_event()
+
+
+def _take_zeros(holder, name, shape):
+    """the pre-zeroed tensor `name` of this call (after making the current stream wait for the fill), or None"""
+    if holder is None:
+        return None
+    bufs = holder.get("zeros")
+    if not bufs or name not in bufs:
+        return None
+    t = bufs.pop(name)
+    if tuple(t.shape) != tuple(shape):
+        return None
+    torch.cuda.current_stream(t.device).wait_event(holder["zeros_event"])
+    return t
+
+
 def _f32c(t: Optional[Tensor], name: str) -> Optional[Tensor]:
     if t is None:
         return None
@@ -145,19 +180,22 @@ class _Project3D(torch.autograd.Function):
         # instead of letting autograd sum two dense [N,3] tensors
         v_means = _take_sh_means_grad(ctx.holder, means)
         acc = v_means is not None
+        vis = None if ctx.holder is None else ctx.holder.get("vis_ids")
+        zq, zs = _take_zeros(ctx.holder, "v_quats", quats.shape), _take_zeros(ctx.holder, "v_scales", scales.shape)
+        zm = None if acc else _take_zeros(ctx.holder, "v_means", means.shape)
+        zeroed = vis is not None and zq is not None and zs is not None and (acc or zm is not None)
         if not acc:
-            v_means = torch.empty_like(means)
-        v_quats = torch.empty_like(quats)
-        v_scales = torch.empty_like(scales)
+            v_means = zm if zeroed else torch.empty_like(means)
+        v_quats = zq if zeroed else torch.empty_like(quats)
+        v_scales = zs if zeroed else torch.empty_like(scales)
         v_means2d, ld_m = _rows(means.new_zeros((C, N, 2)) if v_means2d is None else v_means2d, 2)
         v_conics, ld_c = _rows(means.new_zeros((C, N, 3)) if v_conics is None else v_conics, 3)
         v_depths, ld_d = _rows(None if v_depths is None else v_depths.unsqueeze(-1), 1)
-        vis = None if ctx.holder is None else ctx.holder.get("vis_ids")
         _mark("project3d_bwd", 0)
         check(L.hgs_project3d_bwd(ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), C, N, width, height,
                                   eps2d, near_plane, far_plane, ptr(radii), ptr(v_means2d), ld_m, ptr(v_depths), ld_d,
                                   ptr(v_conics), ld_c, ptr(vis), 0 if vis is None else vis.numel(), ptr(v_means),
-                                  ptr(v_quats), ptr(v_scales), int(acc), _stream()),
+                                  ptr(v_quats), ptr(v_scales), int(acc) | (2 if zeroed else 0), _stream()),
               "hgs_project3d_bwd")
         _mark("project3d_bwd", 1)
         return (v_means, v_quats, v_scales) + (None,) * 11
@@ -249,16 +287,19 @@ class _SphericalHarmonics(torch.autograd.Function):
             return (None,) * 11
         L = _lib.lib()
         v_colors, ld_vc = _rows(v_colors, 3)
-        v_coeffs = torch.empty_like(coeffs)
         need_dirs = dirs is not None and ctx.needs_input_grad[1]
         need_means = means is not None and ctx.needs_input_grad[2]
         v_dirs = torch.empty_like(dirs) if need_dirs else None
-        v_means = torch.empty_like(means) if need_means else None
         vis = ctx.vis_ids if ctx.holder is None else ctx.holder.get("vis_ids", ctx.vis_ids)
+        zc = _take_zeros(ctx.holder, "v_coeffs", coeffs.shape) if (vis is not None and C == 1 and dirs is None) else None
+        zm = _take_zeros(ctx.holder, "v_means", means.shape) if (zc is not None and need_means) else None
+        zeroed = zc is not None and (zm is not None or not need_means)
+        v_coeffs = zc if zeroed else torch.empty_like(coeffs)
+        v_means = (zm if zeroed else torch.empty_like(means)) if need_means else None
         _mark("sh_bwd", 0)
         check(L.hgs_sh_bwd(degree, K, ptr(dirs), ptr(means), ptr(campos), ptr(coeffs), ptr(radii), ptr(vis),
                            0 if vis is None else vis.numel(), ptr(colors), ptr(v_colors), ld_vc, C, N, post,
-                           ptr(v_coeffs), ptr(v_dirs), ptr(v_means), _stream()),
+                           ptr(v_coeffs), ptr(v_dirs), ptr(v_means), int(zeroed), _stream()),
               "hgs_sh_bwd")
         _mark("sh_bwd", 1)
         if v_means is not None and ctx.holder is not None and ctx.holder.get("park_means_grad") and \
@@ -431,10 +472,11 @@ class _Blend3D(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means2d, conics, colors, depths, opacities, backgrounds, width, height, tile_size,
                 isect_offsets, flatten_ids, absgrad, radii, normalize_depth, vis_ids=None, defer=None, records=None,
-                aux=None):
+                aux=None, prezero=None):
         L = _lib.lib()
         ctx.defer = defer
         ctx.vis_ids = vis_ids
+        ctx.prezero = prezero   # {"holder": dict shared with the projection / SH stages, "shapes": their dense gradients}
         ctx.aux = aux           # weak references to the per-Gaussian inputs (does anybody retain their gradient?)
         C, N = opacities.shape
         CH = colors.shape[-1]
@@ -476,11 +518,17 @@ class _Blend3D(torch.autograd.Function):
         L = _lib.lib()
         v_render_colors = v_render_colors.contiguous()
         v_render_alphas = v_render_alphas.contiguous()
-        tail = (None,) * 12
+        tail = (None,) * 13
         if ctx.fast:
             records, backgrounds, isect_offsets, flatten_ids, render_colors, render_alphas, last_ids = ctx.saved_tensors
             (C, N, _), has_depth = ctx.shapes
             vpack = _vpack_alloc(C, N, 12, ctx.vis_ids, ctx.aux, records.device)
+            pz = ctx.prezero
+            if pz is not None and ctx.vis_ids is not None and ctx.defer is None:
+                # dense zero fills of this backward pass: on a second stream, in the shadow of the blend backward
+                shapes = dict(pz["shapes"])
+                shapes.update(v_means2d=(C, N, 2), v_opacities=(C, N))
+                _prezero_async(pz["holder"], shapes, records.device)
             _mark("blend3d_bwd", 0)
             check(L.hgs_blend3d_bwd_packed(ptr(records), ptr(backgrounds), C, D, int(normalize_depth), width, height,
                                            tile_size, ptr(isect_offsets), ptr(flatten_ids), flatten_ids.numel(),
@@ -494,10 +542,13 @@ class _Blend3D(torch.autograd.Function):
             if ctx.vis_ids is not None and ctx.defer is None:
                 # autograd consumes these two as dense tensors (retain_grad clone, leaf accumulation): copy the visible
                 # rows into dense zero-filled tensors instead of handing out strided views of the 48-byte rows
-                v_means2d = torch.empty((C, N, 2), dtype=torch.float32, device=records.device)
-                v_opacities = torch.empty((C, N), dtype=torch.float32, device=records.device)
+                hold = None if ctx.prezero is None else ctx.prezero["holder"]
+                z2, zo = _take_zeros(hold, "v_means2d", (C, N, 2)), _take_zeros(hold, "v_opacities", (C, N))
+                zeroed = z2 is not None and zo is not None
+                v_means2d = z2 if zeroed else torch.empty((C, N, 2), dtype=torch.float32, device=records.device)
+                v_opacities = zo if zeroed else torch.empty((C, N), dtype=torch.float32, device=records.device)
                 check(L.hgs_blend3d_unpack(ptr(vpack), ptr(ctx.vis_ids), ctx.vis_ids.numel(), C * N, ptr(v_means2d),
-                                           ptr(v_opacities), _stream()), "hgs_blend3d_unpack")
+                                           ptr(v_opacities), int(zeroed), _stream()), "hgs_blend3d_unpack")
             v_colors = vpack[..., 8:8 + CH]
             v_depths = vpack[..., 8 + CH] if has_depth else None
             v_bg = None
@@ -560,7 +611,7 @@ def _vpack_alloc(C, N, width, vis_ids, aux, dev):
 
 def _blend3d(means2d, conics, colors, depths, opacities, backgrounds, width, height, tile_size, isect_offsets,
              flatten_ids, absgrad=False, radii=None, normalize_depth=False, vis_ids=None, defer=None, records=None,
-             aux=None):
+             aux=None, prezero=None):
     if tile_size not in _TILE_SIZES:
         raise NotImplementedError(f"tile_size {tile_size} is not supported (supported: {_TILE_SIZES})")
     D = colors.shape[-1] + (1 if depths is not None else 0)
@@ -570,7 +621,7 @@ def _blend3d(means2d, conics, colors, depths, opacities, backgrounds, width, hei
                           _f32c(depths, "depths"), _f32c(opacities, "opacities"), _f32c(backgrounds, "backgrounds"),
                           int(width), int(height), int(tile_size), isect_offsets.contiguous(),
                           flatten_ids.contiguous(), bool(absgrad), radii, bool(normalize_depth), vis_ids, defer, records,
-                          aux)
+                          aux, prezero)
 
 
 def rasterize_to_pixels(means2d: Tensor, conics: Tensor, colors: Tensor, opacities: Tensor, image_width: int,

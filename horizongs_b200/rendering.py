@@ -142,10 +142,22 @@ def rasterization(
     if defer is not None:
         defer["vis_ids"] = vis_ids
 
+    # dense gradients the backward of this call will have to zero-fill (done on a second stream, see W._prezero_async)
+    prezero = None
+    if C == 1 and torch.is_grad_enabled() and defer is None:
+        shapes = {}
+        if means.requires_grad:
+            shapes["v_means"] = tuple(means.shape)
+        if quats.requires_grad and scales.requires_grad and means.requires_grad:
+            shapes.update(v_quats=tuple(quats.shape), v_scales=tuple(scales.shape))
+        if sh_degree is not None and colors.requires_grad:
+            shapes["v_coeffs"] = tuple(colors.shape)
+        prezero = {"holder": holder, "shapes": shapes}
     render_colors, render_alphas = W._blend3d(means2d, conics, feats, depth_ch, opac, bgs, width, height, tile_size,
                                               isect_offsets, flatten_ids, absgrad, radii=radii,
                                               normalize_depth=fuse_norm, vis_ids=vis_ids, defer=defer, records=records,
-                                              aux=[weakref.ref(t) for t in (conics, feats, depth_ch) if t is not None])
+                                              aux=[weakref.ref(t) for t in (conics, feats, depth_ch) if t is not None],
+                                              prezero=prezero)
     if render_mode in ("ED", "RGB+ED") and not fuse_norm:
         render_colors = torch.cat(
             [render_colors[..., :-1], render_colors[..., -1:] / render_alphas.clamp(min=1e-10)], dim=-1)

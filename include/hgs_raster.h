@@ -53,14 +53,15 @@ int hgs_project3d_fwd(const float* means, const float* quats, const float* scale
  * passed without a copy;  out (overwritten, summed over cameras): v_means[N,3], v_quats[N,4], v_scales[N,3].
  * vis_ids (or NULL): work list of the n_vis visible flat indices c*N+n from hgs_isect_bin_prepare -- one thread per
  * visible pair instead of one per Gaussian (same results; with C > 1 the sums over cameras use atomics).
- * accumulate_means != 0: v_means already holds a gradient (the SH direction gradient of hgs_sh_bwd, zero in the rows of
- * culled Gaussians) and the projection gradient is ADDED to it instead of overwriting it. */
+ * flags bit 0: v_means already holds a gradient (the SH direction gradient of hgs_sh_bwd, zero in the rows of culled
+ * Gaussians) and the projection gradient is ADDED to it instead of overwriting it; bit 1 (work-list path): the
+ * caller has already zero-filled the outputs (e.g. on a second stream, while the blend backward runs). */
 int hgs_project3d_bwd(const float* means, const float* quats, const float* scales, const float* viewmats,
                       const float* Ks, int C, int N, int width, int height, float eps2d, float near_plane,
                       float far_plane, const int32_t* radii, const float* v_means2d, int ld_means2d,
                       const float* v_depths, int ld_depths, const float* v_conics, int ld_conics,
                       const int32_t* vis_ids, long long n_vis, float* v_means, float* v_quats, float* v_scales,
-                      int accumulate_means, void* stream);
+                      int flags, void* stream);
 
 /* ---- a4: fully_fused_projection_2dgs (render.py:171-186; inside rasterization_2dgs render.py:62) --
  * out: radii[C,N], means2d[C,N,2], depths[C,N], ray_transforms[C,N,3,3] (rows M0,M1,M2 of (K [R|t] H)),
@@ -76,7 +77,7 @@ int hgs_project2d_bwd(const float* means, const float* quats, const float* scale
                       const int32_t* radii, const float* v_means2d, int ld_means2d, const float* v_depths,
                       int ld_depths, const float* v_ray_transforms, int ld_ray_transforms, const float* v_normals,
                       int ld_normals, const int32_t* vis_ids, long long n_vis, float* v_means, float* v_quats,
-                      float* v_scales, int accumulate_means, void* stream);
+                      float* v_scales, int flags, void* stream);
 
 /* ---- a7: spherical_harmonics (inside rasterization* when sh_degree is not None) ------------------
  * Direction of Gaussian n for camera c is dirs[c,n,:] if dirs != NULL, else means[n,:] - campos[c,:]
@@ -94,7 +95,8 @@ int hgs_sh_fwd(int degree, int K, const float* dirs, const float* means, const f
 int hgs_sh_bwd(int degree, int K, const float* dirs, const float* means, const float* campos, const float* coeffs,
                const int32_t* radii, const int32_t* vis_ids, long long n_vis, const float* colors,
                const float* v_colors, int ld_v_colors, int C, int N, int post, float* v_coeffs, float* v_dirs,
-               float* v_means, void* stream);
+               float* v_means, int outputs_zeroed, void* stream);
+/* outputs_zeroed != 0 (one-camera work-list path only): v_coeffs / v_means were zero-filled by the caller. */
 
 /* ---- a8-a10: tile intersection, tile|depth key sort, per-tile ranges (integer, bit-exact) --------
  * key = cam << (32 + tile_bits) | tile_id << 32 | (int64)(int32 bits of depth), value = flat index;
@@ -189,7 +191,7 @@ int hgs_blend3d_bwd_packed(const void* records, const float* backgrounds, int C,
 /* Dense copies of two columns of vpack for the rows listed in vis_ids (the others are zero-filled): v_means2d[CN,2]
  * and v_opacities[CN] -- what autograd consumes as dense tensors (retain_grad of meta["means2d"], the opacity leaf). */
 int hgs_blend3d_unpack(const float* vpack, const int32_t* vis_ids, long long n_vis, long long CN, float* v_means2d,
-                       float* v_opacities, void* stream);
+                       float* v_opacities, int outputs_zeroed, void* stream);
 /* rows[ids[j]] of an [*, row_floats] float buffer (row_floats % 4 == 0, 16-byte aligned) := 0 for j < n_ids: zeroes the
  * accumulator rows of the visible Gaussians only, where every reader of the buffer goes through the same work list. */
 int hgs_zero_rows(float* rows, int row_floats, const int32_t* ids, long long n_ids, void* stream);
