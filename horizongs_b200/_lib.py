@@ -49,6 +49,8 @@ SIGNATURES = {
     "hgs_blend2d_pack": (_i, [_p] * 8 + [_ll, _ll, _i, _p, _p]),
     "hgs_blend2d_fwd_packed": (_i, [_p, _p] + [_i] * 6 + [_p, _p, _ll] + [_p] * 7 + [_p]),
     "hgs_blend2d_bwd_packed": (_i, [_p, _p] + [_i] * 6 + [_p, _p, _ll] + [_p] * 10 + [_p]),
+    "hgs_normals_post_fwd": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _p, _p, _p]),
+    "hgs_normals_post_bwd": (_i, [_p, _i, _p, _p, _i, _i, _i, _p, _p, _p, _p, _i, _p]),
     "hgs_densify_stats": (_i, [_p, _i, _p, _p, _ll, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "hgs_l1_loss_partials": (_i, []),
     "hgs_l1_loss_fwd": (_i, [_p, _p, _p, _ll, _i, _f, _f, _p, _p, _p]),

@@ -304,7 +304,7 @@ struct Bwd2Smem {
 // per-lane values: [0,1] v_xy (low-pass branch), [2..10] v_M (u,v,w), [11..13] v_normal, [14] v_opacity,
 // [15,16] densification gradient, [17..17+D) v_colour
 template <int D, bool NORM_DEPTH, bool DISTORT>
-__global__ void __launch_bounds__(BLK) blend2d_bwd_fast_kernel(
+__global__ void __launch_bounds__(BLK, 3) blend2d_bwd_fast_kernel(
     const SRec* __restrict__ recs, const float* __restrict__ backgrounds, int C, int W, int H, int tile_w, int tile_h,
     const int32_t* __restrict__ offsets, const int32_t* __restrict__ flatten_ids, int n_isects,
     const float* __restrict__ render_colors, const float* __restrict__ render_alphas,

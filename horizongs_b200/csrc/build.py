@@ -34,6 +34,7 @@ SOURCES = {
     "blend2d.cu": [],
     "blend2d_fast.cu": [],
     "densify.cu": [],
+    "normals.cu": [],
     "loss.cu": [],
     "decode.cu": [],
     "exchange.cu": [],

@@ -877,6 +877,59 @@ def rasterize_to_pixels_2dgs(means2d: Tensor, ray_transforms: Tensor, colors: Te
                     image_height, tile_size, isect_offsets, flatten_ids, distloss)
 
 
+# =====================================================================================
+# a13: 2DGS post-ops (normals to world frame, normals from depth)
+# =====================================================================================
+class _NormalsPost(torch.autograd.Function):
+    """(render_normals camera frame [C,H,W,3], depth_src [C,H,W,Dd] whose LAST channel is the z-depth map or None)
+    -> (render_normals world frame, normals_from_depth [C,H,W,3] or None)"""
+
+    @staticmethod
+    def forward(ctx, normals_cam, depth_src, viewmats, Ks, want_nfd):
+        L = _lib.lib()
+        C, H, Wd, _ = normals_cam.shape
+        ctx.set_materialize_grads(False)
+        normals_world = torch.empty_like(normals_cam)
+        nfd = torch.empty_like(normals_cam) if want_nfd else None
+        ld = depth_src.shape[-1] if depth_src is not None else 1
+        dptr = None if depth_src is None else _lib.C.c_void_p(depth_src.data_ptr() + 4 * (ld - 1))
+        _mark("normals_post_fwd", 0)
+        check(L.hgs_normals_post_fwd(ptr(normals_cam), dptr, ld, ptr(viewmats), ptr(Ks), C, H, Wd, ptr(normals_world),
+                                     ptr(nfd), _stream()), "hgs_normals_post_fwd")
+        _mark("normals_post_fwd", 1)
+        ctx.save_for_backward(depth_src, viewmats, Ks)
+        ctx.dims = (C, H, Wd, ld)
+        return normals_world, nfd
+
+    @staticmethod
+    def backward(ctx, v_normals_world, v_nfd):
+        depth_src, viewmats, Ks = ctx.saved_tensors
+        C, H, Wd, ld = ctx.dims
+        L = _lib.lib()
+        dev = viewmats.device
+        v_normals_world = None if v_normals_world is None else v_normals_world.contiguous()
+        v_nfd = None if v_nfd is None else v_nfd.contiguous()
+        v_normals_cam = torch.empty((C, H, Wd, 3), dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        v_src, vptr = None, None
+        if depth_src is not None and ctx.needs_input_grad[1] and v_nfd is not None:
+            v_src = torch.zeros_like(depth_src) if ld > 1 else torch.empty_like(depth_src)
+            vptr = _lib.C.c_void_p(v_src.data_ptr() + 4 * (ld - 1))
+        dptr = None if depth_src is None else _lib.C.c_void_p(depth_src.data_ptr() + 4 * (ld - 1))
+        _mark("normals_post_bwd", 0)
+        check(L.hgs_normals_post_bwd(dptr, ld, ptr(viewmats), ptr(Ks), C, H, Wd, ptr(v_normals_world), ptr(v_nfd),
+                                     ptr(v_normals_cam), vptr, ld, _stream()), "hgs_normals_post_bwd")
+        _mark("normals_post_bwd", 1)
+        return v_normals_cam, v_src, None, None, None
+
+
+def normals_post(render_normals: Tensor, depth_src: Optional[Tensor], viewmats: Tensor, Ks: Tensor, want_nfd: bool):
+    """gsplat.rasterization_2dgs' post-ops: render_normals to the world frame and (want_nfd) depth_to_normal of the
+    z-depth map in the last channel of depth_src [C,H,W,Dd]."""
+    return _NormalsPost.apply(_f32c(render_normals, "render_normals"),
+                              None if depth_src is None else _f32c(depth_src, "depth map"),
+                              _f32c(viewmats.detach(), "viewmats"), _f32c(Ks.detach(), "Ks"), bool(want_nfd))
+
+
 @torch.no_grad()
 def blend3d_pair_stats(means2d, conics, opacities, radii, width, height, tile_size, isect_offsets, flatten_ids):
     """(P_eval, P_blend) of a view -- measurement aid for bench.py's roofline figures (not on the product path)."""

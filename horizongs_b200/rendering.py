@@ -275,11 +275,13 @@ def rasterization_2dgs(
     if render_mode in ("ED", "RGB+ED") and not fuse_norm:
         render_colors = torch.cat(
             [render_colors[..., :-1], render_colors[..., -1:] / render_alphas.clamp(min=1e-10)], dim=-1)
-    c2w = torch.linalg.inv(viewmats)
+    # post-ops (a13): normals to the world frame + normals from the depth map, one kernel each way (csrc/normals.cu)
     if render_mode in ("RGB+D", "RGB+ED"):
-        depth_for_normal = render_colors[..., -1:] if depth_mode == "expected" else render_median
-        render_normals_from_depth = depth_to_normal(depth_for_normal, c2w, Ks).squeeze(0)
-    render_normals = torch.einsum("cij,chwj->chwi", c2w[:, :3, :3], render_normals)
+        depth_src = render_colors if depth_mode == "expected" else render_median
+        render_normals, render_normals_from_depth = W.normals_post(render_normals, depth_src, viewmats, Ks, True)
+        render_normals_from_depth = render_normals_from_depth.squeeze(0)
+    else:
+        render_normals, _ = W.normals_post(render_normals, None, viewmats, Ks, False)
 
     meta = {
         "camera_ids": None, "gaussian_ids": None, "radii": radii, "means2d": means2d_info, "depths": depths,

@@ -245,6 +245,20 @@ int hgs_blend2d_bwd_packed(const void* records, const float* backgrounds, int C,
                            const float* v_render_normals, const float* v_render_distort,
                            const float* v_render_median, float* vpack, void* stream);
 
+/* ---- a13: 2DGS post-ops of rasterization_2dgs (render.py:56-76; gsplat depth_to_normal + normal rotation) ---
+ * fwd: normals_world[C,H,W,3] = R_c2w normals_cam (both NULL to skip); normals_from_depth[C,H,W,3] (or NULL) from the
+ * z-depth map depth[(c*H*W + pixel) * ld_depth] (e.g. the last channel of render_colors: ld_depth = channels): back-
+ * projected pixel centres, central differences, normalised cross product, one-pixel zero border.  The camera-to-
+ * world transform is the closed form (R^T, -R^T t) of viewmats[C,4,4]; Ks[C,3,3].
+ * bwd: v_normals_cam[C,H,W,3] = R_c2w^T v_normals_world (NULL in: zeros); v_depth[(..) * ld_v_depth] = gradient of
+ * the depth map through normals_from_depth (v_normals_from_depth NULL: zeros).  Either output may be NULL. */
+int hgs_normals_post_fwd(const float* normals_cam, const float* depth, int ld_depth, const float* viewmats,
+                         const float* Ks, int C, int H, int W, float* normals_world, float* normals_from_depth,
+                         void* stream);
+int hgs_normals_post_bwd(const float* depth, int ld_depth, const float* viewmats, const float* Ks, int C, int H, int W,
+                         const float* v_normals_world, const float* v_normals_from_depth, float* v_normals_cam,
+                         float* v_depth, int ld_v_depth, void* stream);
+
 /* ---- f2 (next row of SURVEY.md section 8): densification statistics -------------------------------
  * One pass over the view-space gradient (scene/basic_model.py:96-144, the part fed by the rasterizer): for
  * Gaussians with radii > 0 in a view, grad_accum[n] += (mode_max ? max : sum) of ||v_means2d * (W/2, H/2)||,
