@@ -705,6 +705,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         fps = args.steps / (time.perf_counter() - t0)
 
+    fused_multicast = bool(fused is not None and fused.multicast)
     if peer is not None:
         peer.close()
     if fused is not None:
@@ -817,7 +818,10 @@ def run_ours(args):
                           if N * 38 * 4 > 126e6 else
                           "the view (and with it the set of visible Gaussians and every intermediate) changes every step; "
                           "parameters + gradients + intermediates of a step exceed L2"),
-                   "collective": exchange_name},
+                   "collective": exchange_name,
+                   "exchange_transport": (None if fused is None else
+                                          ("NVSwitch multicast: every record stored once with multimem.st, replicated by "
+                                           "the switch" if fused_multicast else "one unicast peer store per rank"))},
         "clocks": clk,
         "e2e": {"value": world * n_steps / (ms_e2e * 1e-3), "unit": "iters/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / n_steps},

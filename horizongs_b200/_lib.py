@@ -67,9 +67,9 @@ SIGNATURES = {
     "hgs_exchange_push": (_i, [_p, _p, _i, _ll, _p, _ll, _ll, _p, _i, _i, C.c_ulonglong, _p]),
     "hgs_exchange_reduce": (_i, [_p, _p, _i, _ll, _ll, _p, _i, _i, C.c_ulonglong, _p, _p]),
     "hgs_exchange_vjp_mailbox_bytes": (_sz, [_i, _ll, _ll]),
-    "hgs_exchange_vjp_push": (_i, [_i, _i] + [_p] * 9 + [_i, _i, _f, _f, _f, _ll, _p, _ll, _ll, _p, _i, _i,
+    "hgs_exchange_vjp_push": (_i, [_i, _i] + [_p] * 9 + [_i, _i, _f, _f, _f, _ll, _p, _ll, _ll, _p, _p, _i, _i,
                                                      C.c_ulonglong, _p]),
-    "hgs_exchange_vjp_push_2dgs": (_i, [_i, _i, _p, _i] + [_p] * 8 + [_i, _i, _f, _f, _ll, _p, _ll, _ll, _p, _i, _i,
+    "hgs_exchange_vjp_push_2dgs": (_i, [_i, _i, _p, _i] + [_p] * 8 + [_i, _i, _f, _f, _ll, _p, _ll, _ll, _p, _p, _i, _i,
                                                                   C.c_ulonglong, _p]),
     "hgs_exchange_vjp_reduce": (_i, [_i, _i, _p, _ll, _ll, _p, _i, _i, C.c_ulonglong] + [_p] * 8 + [_p]),
     "hgs_peer_alloc": (_i, [_sz, C.POINTER(C.c_void_p)]),

@@ -18,6 +18,7 @@ constexpr int EX_CHUNK = 64;           // records staged per TMA bulk store
 
 struct ExPeers {
     unsigned char* base[EX_MAX_W];
+    unsigned char* mc;      // NVLink multicast mapping of the mailboxes (a store lands in EVERY rank's mailbox), or NULL
     int world, rank;
 };
 // slot = [header 128 B][block entries: one per block of EX_IDS consecutive ids = {first record, 256-bit presence
@@ -50,6 +51,20 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(addr) : "memory");
     return v;
+}
+// stores through the NVSwitch multicast mapping: one store instruction, one NVLink transfer out, delivered to all ranks
+__device__ __forceinline__ void mc_st_v4(void* addr, float4 v) {
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void mc_st_f32(void* addr, float v) {
+    asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mc_st_u64(void* addr, unsigned long long v) {
+    asm volatile("multimem.st.weak.global.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void mc_st_release_sys_u64(void* addr, unsigned long long v) {
+    asm volatile("multimem.st.release.sys.global.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
@@ -96,6 +111,13 @@ __device__ __forceinline__ void write_block_entries(const ExPeers& P, const ExLa
         const uint4 e0 = make_uint4((unsigned)lo, bits[0], bits[1], bits[2]);
         const uint4 e1 = make_uint4(bits[3], bits[4], bits[5], bits[6]);
         const uint4 e2 = make_uint4(bits[7], 0u, 0u, 0u);
+        if (P.mc != nullptr) {
+            uint4* e = reinterpret_cast<uint4*>(P.mc + soff + L.ent_off) + (size_t)b * 3;
+            mc_st_v4(e, make_float4(__uint_as_float(e0.x), __uint_as_float(e0.y), __uint_as_float(e0.z), __uint_as_float(e0.w)));
+            mc_st_v4(e + 1, make_float4(__uint_as_float(e1.x), __uint_as_float(e1.y), __uint_as_float(e1.z), __uint_as_float(e1.w)));
+            mc_st_v4(e + 2, make_float4(__uint_as_float(e2.x), 0.f, 0.f, 0.f));
+            continue;
+        }
         for (int q = 0; q < P.world; ++q) {
             uint4* e = reinterpret_cast<uint4*>(P.base[q] + soff + L.ent_off) + (size_t)b * 3;
             e[0] = e0; e[1] = e1; e[2] = e2;
@@ -106,7 +128,7 @@ __device__ __forceinline__ void write_block_entries(const ExPeers& P, const ExLa
 // end of a push kernel: the threads that issued bulk stores complete them, every thread fences its stores
 // system-wide, and the last block to get here raises this rank's flag in every mailbox (release)
 __device__ __forceinline__ void publish_push(const ExPeers& P, unsigned long long flag_value) {
-    if (threadIdx.x < P.world) {
+    if (threadIdx.x < P.world && P.mc == nullptr) {
         bulk_wait_all();
         fence_proxy_async();
     }
@@ -118,8 +140,13 @@ __device__ __forceinline__ void publish_push(const ExPeers& P, unsigned long lon
         if (prev == gridDim.x - 1) {
             *counter = 0u;
             __threadfence_system();
-            for (int q = 0; q < P.world; ++q)
-                st_release_sys(reinterpret_cast<unsigned long long*>(P.base[q] + (size_t)P.rank * EX_FLAG_STRIDE), flag_value);
+            if (P.mc != nullptr) {
+                mc_st_release_sys_u64(P.mc + (size_t)P.rank * EX_FLAG_STRIDE, flag_value);
+            } else {
+                for (int q = 0; q < P.world; ++q)
+                    st_release_sys(reinterpret_cast<unsigned long long*>(P.base[q] + (size_t)P.rank * EX_FLAG_STRIDE),
+                                   flag_value);
+            }
         }
     }
 }
@@ -183,7 +210,8 @@ inline bool ex_bad_geometry(int world, int rank, long long n_ids, long long cap_
     return world < 1 || world > EX_MAX_W || rank < 0 || rank >= world || n_ids < 1 || n_ids >= (1ll << 31) ||
            cap_rows < 1 || cap_rows % 32 != 0 || cap_rows * 32 >= (1ll << 31);
 }
-inline int ex_fill_peers(ExPeers& P, void* const* mailboxes_host, int world, int rank) {
+inline int ex_fill_peers(ExPeers& P, void* const* mailboxes_host, int world, int rank, void* multicast = nullptr) {
+    P.mc = (unsigned char*)multicast;
     for (int q = 0; q < EX_MAX_W; ++q) P.base[q] = q < world ? (unsigned char*)mailboxes_host[q] : nullptr;
     for (int q = 0; q < world; ++q)
         if (P.base[q] == nullptr) return HGS_ERR_INVALID_ARG;

@@ -64,7 +64,16 @@ __global__ void __launch_bounds__(VJ_PUSH) vjp_push_kernel(
     write_block_entries(P, L, soff, ids, n_rows);
     if (blockIdx.x == 0 && threadIdx.x <= VJ_CAM) {
         const int t = threadIdx.x;
-        for (int q = 0; q < P.world; ++q) {
+        if (P.mc != nullptr) {
+            unsigned char* hdr = P.mc + soff;
+            if (t == 0) {
+                mc_st_u64(hdr, (unsigned long long)(long long)n_rows);
+            } else {
+                const int k = t - 1;
+                mc_st_f32(reinterpret_cast<float*>(hdr + 8) + k, k < 16 ? viewmat[k] : (k < 25 ? Kmat[k - 16] : campos[k - 25]));
+            }
+        }
+        for (int q = 0; q < (P.mc != nullptr ? 0 : P.world); ++q) {
             unsigned char* hdr = P.base[q] + soff;
             if (t == 0) {
                 *reinterpret_cast<long long*>(hdr) = n_rows;
@@ -85,8 +94,10 @@ __global__ void __launch_bounds__(VJ_PUSH) vjp_push_kernel(
         const int st = it & 1;
         const int r0 = chunk * VJ_PUSH;
         const int nr = min(VJ_PUSH, n_rows - r0);
-        if (threadIdx.x < P.world) bulk_wait_read<1>();   // stage `st` was last read by the stores of iteration it - 2
-        __syncthreads();
+        if (P.mc == nullptr) {
+            if (threadIdx.x < P.world) bulk_wait_read<1>();   // stage `st` was last read by the stores of iteration it - 2
+            __syncthreads();
+        }
         if (threadIdx.x < nr) {
             const long long n = ids[r0 + threadIdx.x];
             const float4 q0 = vpack[n * 3], q1 = vpack[n * 3 + 1];     // v_means2d, v_conics a b | c, v_opacity
@@ -112,12 +123,20 @@ __global__ void __launch_bounds__(VJ_PUSH) vjp_push_kernel(
                 proj3d_bwd_one(cam, f, s0, s1, s2, make_float2(q0.x, q0.y), q2.w, q0.z, 0.5f * q0.w, q1.x, g_mean, g_scale,
                                g_quat);
             const float gx = q0.x * (0.5f * Wf), gy = q0.y * (0.5f * Hf);
-            float4* rec = stage[st] + threadIdx.x * VJ_R4;
-            rec[0] = make_float4(g_mean[0], g_mean[1], g_mean[2], q1.y);
-            rec[1] = make_float4(g_quat[0], g_quat[1], g_quat[2], g_quat[3]);
-            rec[2] = make_float4(g_scale[0], g_scale[1], g_scale[2], sqrtf(gx * gx + gy * gy));
-            rec[3] = make_float4(q2.x, q2.y, q2.z, 0.f);
+            const float4 r0v = make_float4(g_mean[0], g_mean[1], g_mean[2], q1.y);
+            const float4 r1v = make_float4(g_quat[0], g_quat[1], g_quat[2], g_quat[3]);
+            const float4 r2v = make_float4(g_scale[0], g_scale[1], g_scale[2], sqrtf(gx * gx + gy * gy));
+            const float4 r3v = make_float4(q2.x, q2.y, q2.z, 0.f);
+            if (P.mc != nullptr) {
+                // one multicast store per 16 bytes: the switch replicates the record into every rank's mailbox
+                float4* dst = reinterpret_cast<float4*>(P.mc + soff + L.rows_off) + (size_t)(r0 + threadIdx.x) * VJ_R4;
+                mc_st_v4(dst, r0v); mc_st_v4(dst + 1, r1v); mc_st_v4(dst + 2, r2v); mc_st_v4(dst + 3, r3v);
+            } else {
+                float4* rec = stage[st] + threadIdx.x * VJ_R4;
+                rec[0] = r0v; rec[1] = r1v; rec[2] = r2v; rec[3] = r3v;
+            }
         }
+        if (P.mc != nullptr) continue;
         fence_proxy_async();
         __syncthreads();
         if (threadIdx.x < P.world) {
@@ -147,7 +166,16 @@ __global__ void __launch_bounds__(VJ_PUSH) vjp_push2d_kernel(
     write_block_entries(P, L, soff, ids, n_rows);
     if (blockIdx.x == 0 && threadIdx.x <= VJ_CAM) {
         const int t = threadIdx.x;
-        for (int q = 0; q < P.world; ++q) {
+        if (P.mc != nullptr) {
+            unsigned char* hdr = P.mc + soff;
+            if (t == 0) {
+                mc_st_u64(hdr, (unsigned long long)(long long)n_rows);
+            } else {
+                const int k = t - 1;
+                mc_st_f32(reinterpret_cast<float*>(hdr + 8) + k, k < 16 ? viewmat[k] : (k < 25 ? Kmat[k - 16] : campos[k - 25]));
+            }
+        }
+        for (int q = 0; q < (P.mc != nullptr ? 0 : P.world); ++q) {
             unsigned char* hdr = P.base[q] + soff;
             if (t == 0) {
                 *reinterpret_cast<long long*>(hdr) = n_rows;
@@ -168,8 +196,10 @@ __global__ void __launch_bounds__(VJ_PUSH) vjp_push2d_kernel(
         const int st = it & 1;
         const int r0 = chunk * VJ_PUSH;
         const int nr = min(VJ_PUSH, n_rows - r0);
-        if (threadIdx.x < P.world) bulk_wait_read<1>();
-        __syncthreads();
+        if (P.mc == nullptr) {
+            if (threadIdx.x < P.world) bulk_wait_read<1>();
+            __syncthreads();
+        }
         if (threadIdx.x < nr) {
             const long long n = ids[r0 + threadIdx.x];
             const float* row = vpack + n * VJ_ROW2D;
@@ -194,12 +224,19 @@ __global__ void __launch_bounds__(VJ_PUSH) vjp_push2d_kernel(
                 proj2d_bwd_one(cam, f, s0, s1, vpack, VJ_ROW2D, has_depth ? vpack + 19 : nullptr, VJ_ROW2D, vpack + 2, VJ_ROW2D,
                                vpack + 11, VJ_ROW2D, n, g_mean, g_scale, g_quat);
             const float gx = (row[0] + row[20]) * (0.5f * Wf), gy = (row[1] + row[21]) * (0.5f * Hf);
-            float4* rec = stage[st] + threadIdx.x * VJ_R4;
-            rec[0] = make_float4(g_mean[0], g_mean[1], g_mean[2], row[14]);
-            rec[1] = make_float4(g_quat[0], g_quat[1], g_quat[2], g_quat[3]);
-            rec[2] = make_float4(g_scale[0], g_scale[1], g_scale[2], sqrtf(gx * gx + gy * gy));
-            rec[3] = make_float4(v0, v1, v2, 0.f);
+            const float4 r0v = make_float4(g_mean[0], g_mean[1], g_mean[2], row[14]);
+            const float4 r1v = make_float4(g_quat[0], g_quat[1], g_quat[2], g_quat[3]);
+            const float4 r2v = make_float4(g_scale[0], g_scale[1], g_scale[2], sqrtf(gx * gx + gy * gy));
+            const float4 r3v = make_float4(v0, v1, v2, 0.f);
+            if (P.mc != nullptr) {
+                float4* dst = reinterpret_cast<float4*>(P.mc + soff + L.rows_off) + (size_t)(r0 + threadIdx.x) * VJ_R4;
+                mc_st_v4(dst, r0v); mc_st_v4(dst + 1, r1v); mc_st_v4(dst + 2, r2v); mc_st_v4(dst + 3, r3v);
+            } else {
+                float4* rec = stage[st] + threadIdx.x * VJ_R4;
+                rec[0] = r0v; rec[1] = r1v; rec[2] = r2v; rec[3] = r3v;
+            }
         }
+        if (P.mc != nullptr) continue;
         fence_proxy_async();
         __syncthreads();
         if (threadIdx.x < P.world) {
@@ -575,8 +612,8 @@ HGS_API int hgs_exchange_vjp_push(int sh_degree, int K, const float* vpack, cons
                                   const float* Kmat, const float* campos, const float* means, const float* quats,
                                   const float* scales, const float* coeffs, int width, int height, float eps2d,
                                   float near_plane, float far_plane, long long n_ids, const int32_t* ids,
-                                  long long n_rows, long long cap_rows, void* const* mailboxes_host, int world, int rank,
-                                  unsigned long long step, void* stream) {
+                                  long long n_rows, long long cap_rows, void* const* mailboxes_host, void* multicast_base,
+                                  int world, int rank, unsigned long long step, void* stream) {
     if (ex_bad_geometry(world, rank, n_ids, cap_rows) || n_rows < 0 || vpack == nullptr || viewmat == nullptr ||
         Kmat == nullptr || campos == nullptr || means == nullptr || quats == nullptr || scales == nullptr ||
         (reinterpret_cast<size_t>(vpack) & 15) || (reinterpret_cast<size_t>(quats) & 15) || sh_degree < -1 ||
@@ -587,7 +624,7 @@ HGS_API int hgs_exchange_vjp_push(int sh_degree, int K, const float* vpack, cons
     if (n_rows > 0 && ids == nullptr) return HGS_ERR_INVALID_ARG;
     if (n_rows > cap_rows) n_rows = -1;   // overflow: push no records and a negative row count (see exchange_wait_kernel)
     ExPeers P;
-    if (int e = ex_fill_peers(P, mailboxes_host, world, rank)) return e;
+    if (int e = ex_fill_peers(P, mailboxes_host, world, rank, multicast_base)) return e;
     const ExLayout L = make_layout(world, n_ids, cap_rows, VJ_ROW);
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL(DEG)                                                                                                       \
@@ -639,8 +676,8 @@ HGS_API int hgs_exchange_vjp_push_2dgs(int sh_degree, int K, const float* vpack2
                                        const float* viewmat, const float* Kmat, const float* campos, const float* means,
                                        const float* quats, const float* scales, const float* coeffs, int width, int height,
                                        float near_plane, float far_plane, long long n_ids, const int32_t* ids,
-                                       long long n_rows, long long cap_rows, void* const* mailboxes_host, int world,
-                                       int rank, unsigned long long step, void* stream) {
+                                       long long n_rows, long long cap_rows, void* const* mailboxes_host,
+                                       void* multicast_base, int world, int rank, unsigned long long step, void* stream) {
     if (ex_bad_geometry(world, rank, n_ids, cap_rows) || n_rows < 0 || vpack24 == nullptr || viewmat == nullptr ||
         Kmat == nullptr || campos == nullptr || means == nullptr || quats == nullptr || scales == nullptr ||
         (reinterpret_cast<size_t>(quats) & 15) || sh_degree < -1 || sh_degree > 4 || width <= 0 || height <= 0)
@@ -650,7 +687,7 @@ HGS_API int hgs_exchange_vjp_push_2dgs(int sh_degree, int K, const float* vpack2
     if (n_rows > 0 && ids == nullptr) return HGS_ERR_INVALID_ARG;
     if (n_rows > cap_rows) n_rows = -1;   // overflow: push no records and a negative row count (see exchange_wait_kernel)
     ExPeers P;
-    if (int e = ex_fill_peers(P, mailboxes_host, world, rank)) return e;
+    if (int e = ex_fill_peers(P, mailboxes_host, world, rank, multicast_base)) return e;
     const ExLayout L = make_layout(world, n_ids, cap_rows, VJ_ROW);
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL(DEG)                                                                                                       \

@@ -186,6 +186,66 @@ class _PeerMailbox:
         self._local = None
 
 
+class _SymmMailbox(_PeerMailbox):
+    """The same mailbox, allocated through torch's symmetric memory (CUDA VMM + handle exchange done by torch): gives
+    the peer pointers AND, on an NVSwitch fabric, a MULTICAST mapping of all ranks' mailboxes -- a store to
+    multicast_ptr + offset lands at `offset` of every rank's mailbox after crossing this GPU's NVLink once."""
+
+    def __init__(self, nbytes: int, group=None, device: Optional[torch.device] = None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        assert dist.is_available() and dist.is_initialized(), "peer-memory exchange needs an initialised process group"
+        self._C, self._lib, self._check = C, _lib.lib(), _lib.check
+        self.group = dist.group.WORLD if group is None else group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.nbytes = int(nbytes)
+        self._buf = symm_mem.empty((self.nbytes + 3) // 4, dtype=torch.float32, device=self.device)
+        self._buf.zero_()
+        self._hdl = symm_mem.rendezvous(self._buf, self.group)
+        self.ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+        self.ptrs_c = (C.c_void_p * self.world)(*self.ptrs)
+        self.multicast_ptr = int(self._hdl.multicast_ptr or 0)
+        self._local = C.c_void_p(self.ptrs[self.rank])
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._status_event = None
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=group)          # every mailbox is zeroed and mapped everywhere before the first push
+
+    def close(self) -> None:
+        if self._buf is None:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)     # nobody lets go while a peer may still push
+        self._hdl = None
+        self._buf = None
+        self._local = None
+
+
+def _make_mailbox(nbytes: int, group, device, want_multicast: bool):
+    """symmetric-memory mailbox with multicast when the fabric offers it (and HGS_EXCHANGE_NO_MULTICAST is unset), else
+    the CUDA-IPC mailbox.  The choice is collective: every rank takes the same path."""
+    import os
+    box = None
+    if want_multicast and not os.environ.get("HGS_EXCHANGE_NO_MULTICAST"):
+        try:
+            box = _SymmMailbox(nbytes, group, device)
+        except Exception:  # noqa: BLE001 -- symmetric memory unavailable on this build / fabric
+            box = None
+        ok = torch.tensor([1 if (box is not None and box.multicast_ptr) else 0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            if box is not None:
+                box.close()
+            box = None
+    if box is None:
+        box = _PeerMailbox(nbytes, group, device)
+        box.multicast_ptr = 0
+    return box
+
+
 class PeerGradientExchange:
     """Sparse SUM all-reduce of view-sharded gradients over NVLink peer memory (csrc/exchange.cu).
 
@@ -299,7 +359,15 @@ class FusedBackwardExchange:
         nbytes = L.hgs_exchange_vjp_mailbox_bytes(world, self.n_ids, self.cap_rows)
         if nbytes == 0:
             raise _lib.HgsError(f"unsupported exchange geometry: world {world}, N {self.n_ids}, cap {self.cap_rows}")
-        self.box = _PeerMailbox(nbytes, group, device)
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        # NVSwitch multicast (one multimem.st per record instead of world - 1 unicast copies) is available as an option
+        # (HGS_EXCHANGE_MULTICAST_MIN_RANKS=<n>) but OFF by default: every rank has to RECEIVE the other ranks' records
+        # either way, so the push is bound by NVLink ingress (7 x 50 MB at 8 ranks), and measured on 8 x B200 the
+        # multicast stores are slower (0.65 ms) than the per-peer TMA bulk stores (0.53 ms = 74 % of the ingress peak)
+        import os
+        mc_min = int(os.environ.get("HGS_EXCHANGE_MULTICAST_MIN_RANKS", "0"))
+        self.box = _make_mailbox(nbytes, group, dev, want_multicast=mc_min > 0 and world >= mc_min)
+        self.multicast = bool(self.box.multicast_ptr)
         self.world, self.rank = self.box.world, self.box.rank
         self.step = 0
         self.sink: dict = {}
@@ -335,19 +403,20 @@ class FusedBackwardExchange:
         from .cuda import _wrapper as W
         W._mark("exchange_vjp_push", 0)
         deg = -1 if sh_degree is None else int(sh_degree)
+        mc = C.c_void_p(self.box.multicast_ptr) if self.box.multicast_ptr else None
         dm, dq, ds, dc = means.detach(), quats.detach(), scales.detach(), colors.detach()
         if surfel:
             self._check(L.hgs_exchange_vjp_push_2dgs(deg, K, p(vpack), int(sk["has_depth"]), p(cf), p(sk["viewmats"]),
                                                      p(sk["Ks"]), p(sk["campos"]), p(dm), p(dq), p(ds), p(dc),
                                                      int(sk["width"]), int(sk["height"]), float(sk["near_plane"]),
                                                      float(sk["far_plane"]), N, p(ids) if n > 0 else None, n,
-                                                     self.cap_rows, self.box.ptrs_c, self.world, self.rank, self.step, st),
+                                                     self.cap_rows, self.box.ptrs_c, mc, self.world, self.rank, self.step, st),
                         "hgs_exchange_vjp_push_2dgs")
         else:
             self._check(L.hgs_exchange_vjp_push(deg, K, p(vpack), p(cf), p(sk["viewmats"]), p(sk["Ks"]), p(sk["campos"]),
                                                 p(dm), p(dq), p(ds), p(dc), int(sk["width"]), int(sk["height"]),
                                                 float(sk["eps2d"]), float(sk["near_plane"]), float(sk["far_plane"]), N,
-                                                p(ids) if n > 0 else None, n, self.cap_rows, self.box.ptrs_c, self.world,
+                                                p(ids) if n > 0 else None, n, self.cap_rows, self.box.ptrs_c, mc, self.world,
                                                 self.rank, self.step, st), "hgs_exchange_vjp_push")
         W._mark("exchange_vjp_push", 1)
         outs = [torch.empty_like(t) for t in (means, quats, scales, opacities, colors)]

@@ -368,7 +368,9 @@ int hgs_exchange_reduce(float* const* tensors_host, const int* widths_host, int 
  *            gradient (sh_degree >= 1: coeffs[N,K,3]; 0 or -1: none), SH clamp mask (colors_fwd[N,3] = the
  *            forward colours, or NULL), densification norm; the records and this rank's camera (DEVICE pointers
  *            viewmat[16], Kmat[9], campos[3]) go into slot (step & 1, rank) of every mailbox, then the rank's
- *            flag is raised (release).
+ *            flag is raised (release).  multicast_base (or NULL): an NVSwitch multicast mapping of the same
+ *            mailboxes (same offsets): every record, header and flag is then stored ONCE (multimem.st) and the
+ *            switch replicates it to all ranks, instead of one unicast copy per peer.
  *   reduce : waits for all flags, then for every Gaussian sums the records of the sources that listed it, in rank
  *            order, expanding the SH part with that source's direction, and OVERWRITES v_means[N,3], v_quats[N,4],
  *            v_scales[N,3], v_opacities[N], v_coeffs[N,K,3] (sh_degree -1: plain colours, K == 1) -- zeros for
@@ -379,7 +381,7 @@ int hgs_exchange_vjp_push(int sh_degree, int K, const float* vpack, const float*
                           const float* Kmat, const float* campos, const float* means, const float* quats,
                           const float* scales, const float* coeffs, int width, int height, float eps2d,
                           float near_plane, float far_plane, long long n_ids, const int32_t* ids, long long n_rows,
-                          long long cap_rows, void* const* mailboxes_host, int world, int rank,
+                          long long cap_rows, void* const* mailboxes_host, void* multicast_base, int world, int rank,
                           unsigned long long step, void* stream);
 /* the same push for rasterization_2dgs: vpack24[N,24] is the row layout of hgs_blend2d_bwd_packed (has_depth: the
  * depth channel was rendered, its gradient sits in column 19); the surfel projection VJP replaces the 3DGS one and
@@ -388,7 +390,7 @@ int hgs_exchange_vjp_push_2dgs(int sh_degree, int K, const float* vpack24, int h
                                const float* viewmat, const float* Kmat, const float* campos, const float* means,
                                const float* quats, const float* scales, const float* coeffs, int width, int height,
                                float near_plane, float far_plane, long long n_ids, const int32_t* ids, long long n_rows,
-                               long long cap_rows, void* const* mailboxes_host, int world, int rank,
+                               long long cap_rows, void* const* mailboxes_host, void* multicast_base, int world, int rank,
                                unsigned long long step, void* stream);
 int hgs_exchange_vjp_reduce(int sh_degree, int K, const float* means, long long n_ids, long long cap_rows,
                             const void* mailbox, int world, int rank, unsigned long long step, float* v_means,
