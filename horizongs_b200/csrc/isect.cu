@@ -21,14 +21,16 @@
 // Roofline: HBM for steps 1-3 (16 B per Gaussian + 8 B per pair), shuffle / issue for step 4.
 #include "hgs_common.cuh"
 #include "hgs_constants.cuh"
+#include "bin_common.cuh"
 #include "../../include/hgs_raster.h"
 
 namespace {
 
+using namespace hgs_bin;
+
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int SCAN_THREADS = 1024;
-constexpr int CP_TILE = 1024;  // elements per block in the compaction kernel
 
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 static int n_bits_of(long long n) {  // floor(log2(n)) + 1 for n >= 1
@@ -221,48 +223,7 @@ __global__ void isect_emit_kernel(const float* __restrict__ means2d, const int32
 // =============================================================================================
 // sorted path by binning (see the header comment)
 // =============================================================================================
-constexpr int ST = 2;                            // tiles per side of a super-tile (the binning / sorting unit)
-constexpr int ST2 = ST * ST;
-constexpr int SUB = 4;                           // sub-bins per super-tile (by flat index): spreads the atomics
-constexpr int PAD = 32;                          // u32 slots per atomic counter: one 128-byte line each (the L2 serialises
-                                                 // atomics per line, not per address)
-constexpr int BIG_AREA = 16;                     // Gaussians covering more tiles are spread over the whole CTA
-#define LB_AGG (1ull << 62)      // look-back flag: block aggregate published
-#define LB_PREFIX (2ull << 62)   // look-back flag: inclusive prefix published
-#define LB_MASK ((1ull << 62) - 1)
-#define KEY_INF (~0ull)
 constexpr int SORT_CHUNK = 2048;                 // keys one CTA sorts in registers (8 per thread)
-constexpr int ID_BITS = 28;                      // sort key = depth bits << 32 | flat index << 4 | tile mask
-static_assert(ST2 <= 4, "the tile mask of a key is 4 bits");
-
-// what the later kernels need to know about a visible Gaussian (written once, in work-list order)
-struct __align__(16) VisRec {
-    uint32_t g, depth_bits;
-    uint32_t xy0, xy1;       // tile box: x0 | y0 << 16,  x1 | y1 << 16
-};
-
-struct BinGeom {
-    int N, tile_w, tile_h, stw, sth;             // stw x sth super-tiles per camera
-    float tile_size, inv_tile_size;              // inv_tile_size > 0: tile_size is a power of two (x / ts == x * inv)
-};
-
-// tile box [x0, x1) x [y0, y1) of a visible Gaussian: hgs_tile_bbox's arithmetic (a power-of-two tile size
-// divides exactly by multiplication)
-__device__ __forceinline__ void tile_box(const BinGeom& G, const float* __restrict__ means2d,
-                                         const int32_t* __restrict__ radii, long long g, int& x0, int& y0, int& x1,
-                                         int& y1) {
-    const float2 m = reinterpret_cast<const float2*>(means2d)[g];
-    const float r = (float)radii[g];
-    if (G.inv_tile_size > 0.f) {
-        const float tr = r * G.inv_tile_size, tx = m.x * G.inv_tile_size, ty = m.y * G.inv_tile_size;
-        x0 = (int)fminf(fmaxf(floorf(tx - tr), 0.f), (float)G.tile_w);
-        y0 = (int)fminf(fmaxf(floorf(ty - tr), 0.f), (float)G.tile_h);
-        x1 = (int)fminf(fmaxf(ceilf(tx + tr), 0.f), (float)G.tile_w);
-        y1 = (int)fminf(fmaxf(ceilf(ty + tr), 0.f), (float)G.tile_h);
-    } else {
-        hgs_tile_bbox(m.x, m.y, r, G.tile_size, G.tile_w, G.tile_h, x0, y0, x1, y1);
-    }
-}
 
 // ---- phase 1a: ordered compaction of the Gaussians with tiles + super-tile histogram --------------------
 __global__ void __launch_bounds__(RS_THREADS) bin_count_kernel(
@@ -850,39 +811,6 @@ HGS_API int hgs_isect_emit(const float* means2d, const int32_t* radii, const flo
 // temp layout of the sorted path (zero-filled by phase 1 up to zero_bytes; shared by both phases):
 // look-back flags [ceil(CN / CP_TILE)] u64 | tile histogram [C*T] u32 | super-tile sub-bin histogram [S*SUB] u32 |
 // sub-bin cursors [S*SUB] u32 | ticket || sub-bin offsets [S*SUB] i32 | visible-Gaussian records [CN] x 16 B
-static BinGeom make_geom(int N, int tile_size, int tile_w, int tile_h) {
-    BinGeom G;
-    G.N = N; G.tile_w = tile_w; G.tile_h = tile_h;
-    G.stw = (tile_w + ST - 1) / ST;
-    G.sth = (tile_h + ST - 1) / ST;
-    G.tile_size = (float)tile_size;
-    G.inv_tile_size = (tile_size & (tile_size - 1)) == 0 ? 1.0f / (float)tile_size : 0.f;
-    return G;
-}
-struct BinTemp {
-    unsigned long long* flags;
-    uint32_t *tile_count, *super_count, *cursor, *ticket;
-    int32_t* soff;
-    VisRec* vrec;
-    size_t zero_bytes, bytes;
-};
-static BinTemp bin_temp(void* temp, long long CN, long long total_super, long long total_tiles) {
-    BinTemp T;
-    const size_t nblk = (size_t)hgs_ceil_div(CN > 0 ? CN : 1, CP_TILE);
-    const size_t S = (size_t)(total_super > 0 ? total_super : 1) * SUB, TT = (size_t)(total_tiles > 0 ? total_tiles : 1);
-    char* p = (char*)temp;
-    T.flags = (unsigned long long*)p; p += align_up(nblk * sizeof(unsigned long long));
-    T.tile_count = (uint32_t*)p; p += align_up(TT * sizeof(uint32_t));
-    T.super_count = (uint32_t*)p; p += align_up(S * PAD * sizeof(uint32_t));
-    T.cursor = (uint32_t*)p; p += align_up(S * PAD * sizeof(uint32_t));
-    T.ticket = (uint32_t*)p; p += 256;
-    T.zero_bytes = (size_t)(p - (char*)temp);
-    T.soff = (int32_t*)p; p += align_up(S * sizeof(int32_t));
-    T.vrec = (VisRec*)p; p += align_up((size_t)(CN > 0 ? CN : 1) * sizeof(VisRec));
-    T.bytes = (size_t)(p - (char*)temp);
-    return T;
-}
-
 HGS_API size_t hgs_isect_bin_temp_bytes(long long CN, int C, int tile_w, int tile_h) {
     const BinGeom G = make_geom(1, 16, tile_w > 0 ? tile_w : 1, tile_h > 0 ? tile_h : 1);
     return bin_temp(nullptr, CN, (long long)C * G.stw * G.sth, (long long)C * tile_w * tile_h).bytes;
@@ -917,6 +845,21 @@ HGS_API int hgs_isect_bin_prepare(const float* means2d, const int32_t* radii, co
                                                   T.super_count, visible_ids, T.vrec, counts_dev);
     HGS_LAUNCH_CHECK();
     hist_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(T.super_count, total_super * SUB, T.soff, counts_dev);
+    HGS_LAUNCH_CHECK();
+    return 0;
+}
+
+// second launch of phase 1 alone (after hgs_project3d_fwd_bin, which fuses the first one into the projection)
+HGS_API int hgs_isect_bin_scan(int C, int N, int tile_size, int tile_w, int tile_h, long long* counts_dev, void* temp,
+                               size_t temp_bytes, void* stream) {
+    if (C <= 0 || N < 0 || tile_size <= 0 || tile_w <= 0 || tile_h <= 0) return HGS_ERR_INVALID_ARG;
+    if (N == 0) return 0;
+    const long long CN = (long long)C * N;
+    const BinGeom G = make_geom(N, tile_size, tile_w, tile_h);
+    const int total_super = C * G.stw * G.sth;
+    const BinTemp T = bin_temp(temp, CN, total_super, (long long)C * tile_w * tile_h);
+    if (temp_bytes < T.bytes) return HGS_ERR_WORKSPACE;
+    hist_scan_kernel<<<1, SCAN_THREADS, 0, (cudaStream_t)stream>>>(T.super_count, total_super * SUB, T.soff, counts_dev);
     HGS_LAUNCH_CHECK();
     return 0;
 }

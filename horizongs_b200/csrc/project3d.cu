@@ -11,40 +11,60 @@
 #include "hgs_common.cuh"
 #include "hgs_constants.cuh"
 #include "project3d_math.cuh"
+#include "bin_common.cuh"
 
 namespace {
 
 constexpr int PB = 256;  // threads per block
-// Forward kernel in three phases so that the heavy math runs on densely populated warps even when only a
-// small, randomly scattered fraction of the Gaussians is on screen:
-//   1. every thread: camera-space centre of its Gaussian, near/far test, conservative off-screen test;
-//   2. the survivors of the block are compacted and the first n_pass threads do the covariance /
-//      Jacobian / conic / radius math, results go to shared memory;
-//   3. every thread writes its own output row (zeros for culled Gaussians), coalesced.
-__global__ void __launch_bounds__(PB) project3d_fwd_kernel(
+constexpr int CH = hgs_bin::CP_TILE;   // Gaussians per CTA of the forward kernel (4 per thread)
+constexpr int PER = CH / PB;
+
+// Forward kernel.  One CTA owns CH = 1024 consecutive Gaussians of one camera, so that the heavy math runs on
+// densely populated warps even when only a small, randomly scattered fraction of the Gaussians is on screen:
+//   1. every thread, 4 consecutive rows (16-byte loads / stores): camera-space centre, near/far test, conservative
+//      off-screen test; zeros are written to every output row; the survivors' row numbers are compacted, in order,
+//      into shared memory;
+//   2. the survivors, one per thread: quaternion load, covariance / Jacobian / conic / radius math, exact screen
+//      test, tile count; a visible Gaussian overwrites its output rows;
+//   3. (BIN) ordering, fused (what hgs_isect_bin_prepare's first kernel does from tiles_per_gauss): the visible
+//      Gaussians with tiles are compacted in ascending flat-index order across the CTAs (decoupled look-back;
+//      CTAs take their chunk by ticket so that every predecessor is running), their records {flat index, depth
+//      bits, tile box} are written in that order, and the super-tile histogram is updated.
+struct BinArgs {
+    hgs_bin::BinGeom G;
+    unsigned long long* flags;
+    uint32_t *ticket, *super_count;
+    int32_t* visible_ids;
+    hgs_bin::VisRec* vrec;
+    long long* counts_dev;
+};
+
+template <bool BIN>
+__global__ void __launch_bounds__(PB, 6) project3d_fwd_kernel(
     const float* __restrict__ means, const float* __restrict__ quats, const float* __restrict__ scales,
-    const float* __restrict__ viewmats, const float* __restrict__ Ks, int N, int W, int H, float eps2d,
+    const float* __restrict__ viewmats, const float* __restrict__ Ks, int N, int nblk_cam, int W, int H, float eps2d,
     float near_plane, float far_plane, float radius_clip, int tile_size, int tile_w, int tile_h,
     int32_t* __restrict__ radii, float* __restrict__ means2d, float* __restrict__ depths, float* __restrict__ conics,
-    float* __restrict__ compensations, int32_t* __restrict__ tiles_per_gauss) {
-    __shared__ float s_a[PB * 3];        // means in, conics out
-    __shared__ float s_b[PB * 3];        // scales
-    __shared__ float s_pc[PB * 3];       // camera-space centres of the survivors
-    __shared__ float s_out[PB * 4];      // m2x, m2y, depth, compensation
-    __shared__ int s_ri[PB * 2];         // radius, tile count
-    __shared__ int s_list[PB];
-    __shared__ int s_wcnt[PB / 32];
-    __shared__ float s_cam[26];          // viewmat (16), K (9), bound coefficient
-    const int c = blockIdx.y;
-    const long long base = (long long)blockIdx.x * PB;
-    const long long n = base + threadIdx.x;
+    float* __restrict__ compensations, int32_t* __restrict__ tiles_per_gauss, BinArgs B) {
+    __shared__ unsigned short s_list[CH];      // local rows of the phase-1 survivors, ascending
+    __shared__ int s_seg[PER * (PB / 32) + 1];
+    __shared__ float s_cam[26];                // viewmat (16), K (9), bound coefficient
+    __shared__ uint4 s_rec[BIN ? CH : 1];      // BIN: {flat index (~0: none), depth bits, box lo, box hi} per survivor
+    __shared__ uint32_t s_bid, s_nbig;
+    __shared__ unsigned long long s_excl, s_isect;
+    __shared__ unsigned short s_big[BIN ? CH : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    block_load_rows3<PB>(means, base, N, s_a);
-    block_load_rows3<PB>(scales, base, N, s_b);
-    // defaults: culled
-    s_ri[threadIdx.x * 2] = 0; s_ri[threadIdx.x * 2 + 1] = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) s_out[threadIdx.x * 4 + k] = 0.f;
+    if (BIN) {
+        if (threadIdx.x == 0) {
+            s_bid = atomicAdd(B.ticket, 1u);   // chunks are taken in start order (look-back needs the predecessors running)
+            s_nbig = 0;
+            s_isect = 0;
+        }
+        __syncthreads();
+    }
+    const uint32_t bid = BIN ? s_bid : (uint32_t)(blockIdx.y * nblk_cam + blockIdx.x);
+    const int c = (int)(bid / (uint32_t)nblk_cam);
+    const long long base = (long long)(bid - (uint32_t)c * nblk_cam) * CH;
     // camera: loaded once per block, the derived bound coefficient computed by one thread
     if (threadIdx.x < 16) s_cam[threadIdx.x] = viewmats[c * 16 + threadIdx.x];
     else if (threadIdx.x < 25) s_cam[threadIdx.x] = Ks[c * 9 + threadIdx.x - 16];
@@ -62,43 +82,117 @@ __global__ void __launch_bounds__(PB) project3d_fwd_kernel(
     const float jf_coeff = s_cam[25];
     const float (*R)[3] = cam.R;
 
-    // ---- phase 1
-    bool pass = false;
-    if (n < N) {
-        const float px = s_a[threadIdx.x * 3 + 0], py = s_a[threadIdx.x * 3 + 1], pz = s_a[threadIdx.x * 3 + 2];
-        const float s0 = s_b[threadIdx.x * 3 + 0], s1 = s_b[threadIdx.x * 3 + 1], s2 = s_b[threadIdx.x * 3 + 2];
-        const float zc = R[2][0] * px + R[2][1] * py + R[2][2] * pz + cam.t[2];
-        if (!(zc < near_plane || zc > far_plane)) {
-            const float xc = R[0][0] * px + R[0][1] * py + R[0][2] * pz + cam.t[0];
-            const float yc = R[1][0] * px + R[1][1] * py + R[1][2] * pz + cam.t[1];
-            pass = !proj3d_surely_offscreen(cam, jf_coeff, xc, yc, zc, fmaxf(fabsf(s0), fmaxf(fabsf(s1), fabsf(s2))),
-                                            (float)W, (float)H, eps2d);
-            if (pass) { s_pc[threadIdx.x * 3] = xc; s_pc[threadIdx.x * 3 + 1] = yc; s_pc[threadIdx.x * 3 + 2] = zc; }
+    // ---- phase 1: rows base + 4 * threadIdx.x + k (16-byte loads and stores when the rows are aligned)
+    bool pass[PER];
+    {
+        const long long n0 = base + (long long)threadIdx.x * PER;
+        const long long idx0 = (long long)c * N + n0;
+        const bool full = n0 + PER <= N;
+        const bool vec = full && (idx0 & 3) == 0;           // n0 is a multiple of 4; idx0 too unless C > 1 and N % 4 != 0
+        float m[PER * 3], sc[PER * 3];
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const float4 a = reinterpret_cast<const float4*>(means + n0 * 3)[j];
+                const float4 q = reinterpret_cast<const float4*>(scales + n0 * 3)[j];
+                m[4 * j] = a.x; m[4 * j + 1] = a.y; m[4 * j + 2] = a.z; m[4 * j + 3] = a.w;
+                sc[4 * j] = q.x; sc[4 * j + 1] = q.y; sc[4 * j + 2] = q.z; sc[4 * j + 3] = q.w;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < PER * 3; ++e) {
+                const bool in = n0 * 3 + e < (long long)N * 3;
+                m[e] = in ? means[n0 * 3 + e] : 0.f;
+                sc[e] = in ? scales[n0 * 3 + e] : 0.f;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            pass[k] = false;
+            if (n0 + k < N) {
+                const float px = m[3 * k], py = m[3 * k + 1], pz = m[3 * k + 2];
+                // zc decides the near / far cull: exactly the oracle's expression
+                const float zc = R[2][0] * px + R[2][1] * py + R[2][2] * pz + cam.t[2];
+                if (!(zc < near_plane || zc > far_plane)) {
+                    // the off-screen test is conservative (0.1 % + 1 px margin): fused arithmetic is fine here
+                    const float xc = __fmaf_rn(R[0][0], px, __fmaf_rn(R[0][1], py, __fmaf_rn(R[0][2], pz, cam.t[0])));
+                    const float yc = __fmaf_rn(R[1][0], px, __fmaf_rn(R[1][1], py, __fmaf_rn(R[1][2], pz, cam.t[1])));
+                    pass[k] = !proj3d_surely_offscreen(cam, jf_coeff, xc, yc, zc,
+                                                       fmaxf(fabsf(sc[3 * k]), fmaxf(fabsf(sc[3 * k + 1]), fabsf(sc[3 * k + 2]))),
+                                                       (float)W, (float)H, eps2d);
+                }
+            }
+        }
+        // defaults: culled
+        if (vec) {
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<int4*>(radii + idx0) = make_int4(0, 0, 0, 0);
+            reinterpret_cast<float4*>(means2d + idx0 * 2)[0] = z4;
+            reinterpret_cast<float4*>(means2d + idx0 * 2)[1] = z4;
+            *reinterpret_cast<float4*>(depths + idx0) = z4;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) reinterpret_cast<float4*>(conics + idx0 * 3)[j] = z4;
+            if (compensations != nullptr) *reinterpret_cast<float4*>(compensations + idx0) = z4;
+            if (tiles_per_gauss != nullptr) *reinterpret_cast<int4*>(tiles_per_gauss + idx0) = make_int4(0, 0, 0, 0);
+        } else {
+#pragma unroll
+            for (int k = 0; k < PER; ++k) {
+                if (n0 + k >= N) break;
+                const long long idx = idx0 + k;
+                radii[idx] = 0;
+                means2d[idx * 2] = 0.f; means2d[idx * 2 + 1] = 0.f;
+                depths[idx] = 0.f;
+                conics[idx * 3] = 0.f; conics[idx * 3 + 1] = 0.f; conics[idx * 3 + 2] = 0.f;
+                if (compensations != nullptr) compensations[idx] = 0.f;
+                if (tiles_per_gauss != nullptr) tiles_per_gauss[idx] = 0;
+            }
         }
     }
-    const unsigned bal = __ballot_sync(0xFFFFFFFFu, pass);
-    if (lane == 0) s_wcnt[warp] = __popc(bal);
-    __syncthreads();
-    int wbase = 0, n_pass = 0;
+    {
+        // ordered compaction of the survivors' local rows: exclusive scan of the per-thread counts over the CTA
+        int cnt = 0;
 #pragma unroll
-    for (int w = 0; w < PB / 32; ++w) {
-        if (w < warp) wbase += s_wcnt[w];
-        n_pass += s_wcnt[w];
+        for (int k = 0; k < PER; ++k) cnt += pass[k] ? 1 : 0;
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_seg[warp] = incl;
+        __syncthreads();
+        int wbase = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < PB / 32; ++w) {
+            const int x = s_seg[w];
+            if (w < warp) wbase += x;
+            total += x;
+        }
+        int pos = wbase + incl - cnt;
+#pragma unroll
+        for (int k = 0; k < PER; ++k)
+            if (pass[k]) s_list[pos++] = (unsigned short)(threadIdx.x * PER + k);
+        __syncthreads();
+        if (threadIdx.x == 0) s_seg[32] = total;
+        __syncthreads();
     }
-    if (pass) s_list[wbase + __popc(bal & ((1u << lane) - 1u))] = threadIdx.x;
-    __syncthreads();
+    const int n_pass = s_seg[32];
 
     // ---- phase 2: dense math on the survivors
-    float o_ca = 0.f, o_cb = 0.f, o_cc = 0.f;   // conics of the row this thread PROCESSED (written to s_a below)
-    int my_row = -1;
-    if (threadIdx.x < n_pass) {
-        const int r = s_list[threadIdx.x];
-        my_row = r;
-        const float4 qv = reinterpret_cast<const float4*>(quats)[base + r];
+    uint32_t n_vis_t = 0;       // BIN: visible Gaussians with tiles found by this thread
+    for (int i = threadIdx.x; i < n_pass; i += PB) {
+        const int r = s_list[i];
+        const long long n = base + r;
+        const long long idx = (long long)c * N + n;
+        const float4 qv = reinterpret_cast<const float4*>(quats)[n];
+        const float px = means[n * 3], py = means[n * 3 + 1], pz = means[n * 3 + 2];
         Proj3dFwd f;
-        f.xc = s_pc[r * 3]; f.yc = s_pc[r * 3 + 1]; f.zc = s_pc[r * 3 + 2];
-        proj3d_cov_and_project(cam, qv.x, qv.y, qv.z, qv.w, s_b[r * 3], s_b[r * 3 + 1], s_b[r * 3 + 2], (float)W,
+        f.zc = R[2][0] * px + R[2][1] * py + R[2][2] * pz + cam.t[2];
+        f.xc = R[0][0] * px + R[0][1] * py + R[0][2] * pz + cam.t[0];
+        f.yc = R[1][0] * px + R[1][1] * py + R[1][2] * pz + cam.t[1];
+        proj3d_cov_and_project(cam, qv.x, qv.y, qv.z, qv.w, scales[n * 3], scales[n * 3 + 1], scales[n * 3 + 2], (float)W,
                                (float)H, eps2d, f);
+        uint4 rec = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
         if (f.det > 0.f) {
             const float inv_det = 1.0f / f.det;
             const float b = 0.5f * (f.c00 + f.c11);
@@ -110,37 +204,105 @@ __global__ void __launch_bounds__(PB) project3d_fwd_kernel(
             if (vis) {
                 const int radius_i = (int)radius;
                 int ntiles = 0;
+                int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
                 if (tiles_per_gauss != nullptr && radius_i > 0) {
-                    int x0, y0, x1, y1;
                     hgs_tile_bbox(f.m2x, f.m2y, (float)radius_i, (float)tile_size, tile_w, tile_h, x0, y0, x1, y1);
                     ntiles = (y1 - y0) * (x1 - x0);
                 }
-                s_ri[r * 2] = radius_i; s_ri[r * 2 + 1] = ntiles;
-                s_out[r * 4] = f.m2x; s_out[r * 4 + 1] = f.m2y; s_out[r * 4 + 2] = f.zc;
-                s_out[r * 4 + 3] = sqrtf(fmaxf(f.det_orig / f.det, 0.f));
-                o_ca = f.c11 * inv_det;
-                o_cb = -f.c01 * inv_det;
-                o_cc = f.c00 * inv_det;
+                radii[idx] = radius_i;
+                reinterpret_cast<float2*>(means2d)[idx] = make_float2(f.m2x, f.m2y);
+                depths[idx] = f.zc;
+                conics[idx * 3] = f.c11 * inv_det;
+                conics[idx * 3 + 1] = -f.c01 * inv_det;
+                conics[idx * 3 + 2] = f.c00 * inv_det;
+                if (compensations != nullptr) compensations[idx] = sqrtf(fmaxf(f.det_orig / f.det, 0.f));
+                if (tiles_per_gauss != nullptr) tiles_per_gauss[idx] = ntiles;
+                if (BIN && ntiles > 0) {
+                    rec = make_uint4((uint32_t)idx, __float_as_uint(f.zc), (uint32_t)x0 | ((uint32_t)y0 << 16),
+                                     (uint32_t)x1 | ((uint32_t)y1 << 16));
+                    ++n_vis_t;
+                }
             }
         }
+        if (BIN) s_rec[i] = rec;
     }
-    __syncthreads();   // everyone is done reading means (s_a): reuse it for the conics
-    s_a[threadIdx.x * 3 + 0] = 0.f; s_a[threadIdx.x * 3 + 1] = 0.f; s_a[threadIdx.x * 3 + 2] = 0.f;
-    __syncthreads();
-    if (my_row >= 0) { s_a[my_row * 3 + 0] = o_ca; s_a[my_row * 3 + 1] = o_cb; s_a[my_row * 3 + 2] = o_cc; }
-    __syncthreads();
+    if (!BIN) return;
 
-    // ---- phase 3: coalesced rows
-    if (n < N) {
-        const long long idx = (long long)c * N + n;
-        radii[idx] = s_ri[threadIdx.x * 2];
-        reinterpret_cast<float2*>(means2d)[idx] = make_float2(s_out[threadIdx.x * 4], s_out[threadIdx.x * 4 + 1]);
-        depths[idx] = s_out[threadIdx.x * 4 + 2];
-        if (compensations != nullptr) compensations[idx] = s_out[threadIdx.x * 4 + 3];
-        if (tiles_per_gauss != nullptr) tiles_per_gauss[idx] = s_ri[threadIdx.x * 2 + 1];
+    // ---- phase 3: ordered compaction of the visible Gaussians, records, super-tile histogram
+    __syncthreads();
+    // position of survivor slot i among the CTA's visible ones: rounds of PB slots, (round, warp) segments in order
+    const int n_rounds = (n_pass + PB - 1) / PB;        // <= PER
+    for (int k = 0; k < PER; ++k) {
+        const int i = k * PB + threadIdx.x;
+        const bool v = k < n_rounds && i < n_pass && s_rec[i].x != 0xFFFFFFFFu;
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, v);
+        if (lane == 0) s_seg[k * (PB / 32) + warp] = __popc(bal);
     }
-    block_store_rows3<PB>(conics + (long long)c * N * 3, base, N, s_a);
+    __syncthreads();
+    if (warp == 0) {
+        const int v = s_seg[lane];
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        s_seg[lane] = incl - v;
+        if (lane == 31) {
+            s_seg[32] = incl;
+            volatile unsigned long long* vf = B.flags;      // publish the block total at once
+            vf[bid] = (bid == 0 ? LB_PREFIX : LB_AGG) | (unsigned long long)incl;
+        }
+    }
+    __syncthreads();
+    const uint32_t tot = (uint32_t)s_seg[32];
+    // histogram first (it does not need the prefix of the earlier blocks), tile total
+    unsigned long long isects = 0;
+    for (int k = 0; k < n_rounds; ++k) {
+        const int i = k * PB + threadIdx.x;
+        if (i >= n_pass) break;
+        const uint4 rec = s_rec[i];
+        if (rec.x == 0xFFFFFFFFu) continue;
+        const int x0 = (int)(rec.z & 0xFFFFu), y0 = (int)(rec.z >> 16), x1 = (int)(rec.w & 0xFFFFu), y1 = (int)(rec.w >> 16);
+        isects += (unsigned long long)((x1 - x0) * (y1 - y0));
+        if (hgs_bin::super_area(x0, y0, x1, y1) > hgs_bin::BIG_AREA) s_big[atomicAdd(&s_nbig, 1u)] = (unsigned short)i;
+        else hgs_bin::super_hist_add(B.G, B.super_count, rec.x, x0, y0, x1, y1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) isects += __shfl_xor_sync(0xFFFFFFFFu, isects, o);
+    if (lane == 0 && isects) atomicAdd(&s_isect, isects);
+    __syncthreads();
+    const uint32_t nbig = s_nbig;
+    for (uint32_t b = 0; b < nbig; ++b) {
+        const uint4 rec = s_rec[s_big[b]];
+        hgs_bin::super_hist_add_cta(B.G, B.super_count, rec.x, (int)(rec.z & 0xFFFFu), (int)(rec.z >> 16),
+                                    (int)(rec.w & 0xFFFFu), (int)(rec.w >> 16));
+    }
+    if (warp == 0) {
+        const unsigned long long excl = hgs_bin::lookback_exclusive(B.flags, bid, tot);
+        if (lane == 0) {
+            s_excl = excl;
+            if (bid == gridDim.x - 1) B.counts_dev[0] = (long long)(excl + tot);
+            if (s_isect) atomicAdd(reinterpret_cast<unsigned long long*>(B.counts_dev + 1), s_isect);
+        }
+    }
+    __syncthreads();
+    const long long out0 = (long long)s_excl;
+    for (int k = 0; k < n_rounds; ++k) {
+        const int i = k * PB + threadIdx.x;
+        const uint4 rec = i < n_pass ? s_rec[i] : make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+        const bool v = rec.x != 0xFFFFFFFFu;
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, v);
+        if (v) {
+            const long long p = out0 + s_seg[k * (PB / 32) + warp] + __popc(bal & ((1u << lane) - 1u));
+            B.visible_ids[p] = (int32_t)rec.x;
+            hgs_bin::VisRec r;
+            r.g = rec.x; r.depth_bits = rec.y; r.xy0 = rec.z; r.xy1 = rec.w;
+            B.vrec[p] = r;
+        }
+    }
 }
+static_assert(PER * (PB / 32) == 32, "one warp scans the (round, warp) segment counts");
 
 #define PROJ3D_BWD_LOAD_AND_RUN(IDX, N_, C_)                                                                         \
     {                                                                                                                \
@@ -290,11 +452,44 @@ HGS_API int hgs_project3d_fwd(const float* means, const float* quats, const floa
     if (C <= 0 || N < 0 || width <= 0 || height <= 0 || tile_size <= 0) return HGS_ERR_INVALID_ARG;
     if (N == 0) return 0;
     const int tile_w = (width + tile_size - 1) / tile_size, tile_h = (height + tile_size - 1) / tile_size;
-    dim3 grid(hgs_ceil_div(N, PB), C);
-    project3d_fwd_kernel<<<grid, PB, 0, (cudaStream_t)stream>>>(means, quats, scales, viewmats, Ks, N, width, height,
-                                                                  eps2d, near_plane, far_plane, radius_clip, tile_size,
-                                                                  tile_w, tile_h, radii, means2d, depths, conics,
-                                                                  compensations, tiles_per_gauss);
+    const int nblk_cam = hgs_ceil_div(N, CH);
+    dim3 grid(nblk_cam, C);
+    project3d_fwd_kernel<false><<<grid, PB, 0, (cudaStream_t)stream>>>(
+        means, quats, scales, viewmats, Ks, N, nblk_cam, width, height, eps2d, near_plane, far_plane, radius_clip, tile_size,
+        tile_w, tile_h, radii, means2d, depths, conics, compensations, tiles_per_gauss, BinArgs{});
+    HGS_LAUNCH_CHECK();
+    return 0;
+}
+
+// projection + first kernel of the ordering stage (hgs_isect_bin_prepare's compaction and histogram) in one launch;
+// temp as for hgs_isect_bin_prepare; the caller follows with hgs_isect_bin_scan.
+HGS_API int hgs_project3d_fwd_bin(const float* means, const float* quats, const float* scales, const float* viewmats,
+                                  const float* Ks, int C, int N, int width, int height, float eps2d, float near_plane,
+                                  float far_plane, float radius_clip, int tile_size, int32_t* radii, float* means2d,
+                                  float* depths, float* conics, float* compensations, int32_t* tiles_per_gauss,
+                                  int32_t* visible_ids, long long* counts_dev, void* temp, size_t temp_bytes,
+                                  void* stream) {
+    if (C <= 0 || N < 0 || width <= 0 || height <= 0 || tile_size <= 0 || tiles_per_gauss == nullptr ||
+        visible_ids == nullptr || counts_dev == nullptr)
+        return HGS_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int tile_w = (width + tile_size - 1) / tile_size, tile_h = (height + tile_size - 1) / tile_size;
+    const long long CN = (long long)C * N, tt = (long long)C * tile_w * tile_h;
+    if (CN >= (1ll << hgs_bin::ID_BITS) || tt >= (1ll << 29) || tile_w >= 65536 || tile_h >= 65536) return HGS_ERR_TOO_LARGE;
+    cudaError_t e = cudaMemsetAsync(counts_dev, 0, 3 * sizeof(long long), st);
+    if (e != cudaSuccess) return (int)e;
+    if (N == 0) return 0;
+    BinArgs B;
+    B.G = hgs_bin::make_geom(N, tile_size, tile_w, tile_h);
+    const hgs_bin::BinTemp T = hgs_bin::bin_temp(temp, CN, (long long)C * B.G.stw * B.G.sth, tt);
+    if (temp_bytes < T.bytes) return HGS_ERR_WORKSPACE;
+    if ((e = cudaMemsetAsync(temp, 0, T.zero_bytes, st)) != cudaSuccess) return (int)e;
+    B.flags = T.flags; B.ticket = T.ticket; B.super_count = T.super_count;
+    B.visible_ids = visible_ids; B.vrec = T.vrec; B.counts_dev = counts_dev;
+    const int nblk_cam = hgs_ceil_div(N, CH);
+    project3d_fwd_kernel<true><<<nblk_cam * C, PB, 0, st>>>(
+        means, quats, scales, viewmats, Ks, N, nblk_cam, width, height, eps2d, near_plane, far_plane, radius_clip, tile_size,
+        tile_w, tile_h, radii, means2d, depths, conics, compensations, tiles_per_gauss, B);
     HGS_LAUNCH_CHECK();
     return 0;
 }

@@ -154,10 +154,23 @@ class _Project3D(torch.autograd.Function):
         comps = torch.empty((C, N), dtype=torch.float32, device=dev) if calc_compensations else None
         tiles = torch.empty((C, N), dtype=torch.int32, device=dev) if tile_size > 0 else None
         _mark("project3d_fwd", 0)
-        check(L.hgs_project3d_fwd(ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), C, N, width, height,
-                                  eps2d, near_plane, far_plane, radius_clip, max(tile_size, 1), ptr(radii),
-                                  ptr(means2d), ptr(depths), ptr(conics), ptr(comps), ptr(tiles), _stream()),
-              "hgs_project3d_fwd")
+        if holder is not None and holder.get("fuse_bin") and tile_size > 0:
+            # projection + ordered compaction of the visible Gaussians + super-tile histogram in one launch
+            tw, th = -(-width // tile_size), -(-height // tile_size)
+            vis_ids = torch.empty(C * N, dtype=torch.int32, device=dev)
+            counts = torch.empty(3, dtype=torch.int64, device=dev)
+            tb = L.hgs_isect_bin_temp_bytes(C * N, C, tw, th)
+            temp = torch.empty(tb, dtype=torch.uint8, device=dev)
+            check(L.hgs_project3d_fwd_bin(ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), C, N, width, height,
+                                          eps2d, near_plane, far_plane, radius_clip, tile_size, ptr(radii), ptr(means2d),
+                                          ptr(depths), ptr(conics), ptr(comps), ptr(tiles), ptr(vis_ids), ptr(counts),
+                                          ptr(temp), tb, _stream()), "hgs_project3d_fwd_bin")
+            holder["bin"] = {"vis_full": vis_ids, "counts": counts, "temp": temp}
+        else:
+            check(L.hgs_project3d_fwd(ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), C, N, width, height,
+                                      eps2d, near_plane, far_plane, radius_clip, max(tile_size, 1), ptr(radii),
+                                      ptr(means2d), ptr(depths), ptr(conics), ptr(comps), ptr(tiles), _stream()),
+                  "hgs_project3d_fwd")
         _mark("project3d_fwd", 1)
         ctx.save_for_backward(means, quats, scales, viewmats, Ks, radii)
         ctx.cfg = (width, height, eps2d, near_plane, far_plane)
@@ -381,6 +394,23 @@ def _isect_prepare_async(means2d, radii, depths, tiles_per_gauss, C, N, tile_siz
     ev = torch.cuda.Event()
     ev.record()
     return {"vis_full": vis_ids, "counts": counts, "host": host, "event": ev, "temp": temp}
+
+
+def _isect_scan_async(prep, C, N, tile_size, tile_width, tile_height):
+    """phase 1 when its first launch ran fused in the projection (hgs_project3d_fwd_bin): the scan of the super-tile
+    histogram, then the asynchronous copy of the counts as in _isect_prepare_async"""
+    L = _lib.lib()
+    temp, counts = prep["temp"], prep["counts"]
+    _mark("isect_prepare", 0)
+    check(L.hgs_isect_bin_scan(C, N, tile_size, tile_width, tile_height, ptr(counts), ptr(temp), temp.numel(), _stream()),
+          "hgs_isect_bin_scan")
+    _mark("isect_prepare", 1)
+    host = _pinned_counts(counts.device)
+    host.copy_(counts, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    prep.update(host=host, event=ev)
+    return prep
 
 
 def _isect_finish(prep, means2d, radii, depths, C, N, tile_size, tile_width, tile_height):

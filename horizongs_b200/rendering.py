@@ -96,7 +96,7 @@ def rasterization(
     tile_width = math.ceil(width / float(tile_size))
     tile_height = math.ceil(height / float(tile_size))
 
-    holder: Dict = {"park_means_grad": sh_degree is not None}
+    holder: Dict = {"park_means_grad": sh_degree is not None, "fuse_bin": True}
     radii, means2d, depths, conics, comps, tiles_per_gauss = W._project3d(
         means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip,
         rasterize_mode == "antialiased", tile_size, holder)
@@ -108,7 +108,11 @@ def rasterization(
     # asynchronous, and the stages that only need the device-side count (SH colours, record packing) are enqueued
     # BEFORE the host waits for it, so the GPU is busy while the host reads the two numbers
     with torch.no_grad():
-        prep = W._isect_prepare_async(means2d, radii, depths, tiles_per_gauss, C, N, tile_size, tile_width, tile_height)
+        if "bin" in holder:         # the compaction / histogram ran inside the projection kernel
+            prep = W._isect_scan_async(holder.pop("bin"), C, N, tile_size, tile_width, tile_height)
+        else:
+            prep = W._isect_prepare_async(means2d, radii, depths, tiles_per_gauss, C, N, tile_size, tile_width,
+                                          tile_height)
     vis_full, n_vis_dev = prep["vis_full"], prep["counts"]
 
     # multi-GPU: the SH / projection backward is deferred and runs fused with the gradient exchange

@@ -129,6 +129,17 @@ int hgs_isect_emit(const float* means2d, const int32_t* radii, const float* dept
 int hgs_isect_bin_prepare(const float* means2d, const int32_t* radii, const float* depths,
                           const int32_t* tiles_per_gauss, int C, int N, int tile_size, int tile_w, int tile_h,
                           int32_t* visible_ids, long long* counts_dev, void* temp, size_t temp_bytes, void* stream);
+/* Phase 1 with its first launch fused into the projection: hgs_project3d_fwd_bin = hgs_project3d_fwd (tiles_per_gauss
+ * required) + the compaction / histogram of hgs_isect_bin_prepare in ONE kernel (the Gaussians' tile boxes and depths
+ * are still in registers there: no second pass over tiles_per_gauss, means2d, radii, depths); hgs_isect_bin_scan is
+ * the remaining scan launch.  Same outputs and temp as hgs_isect_bin_prepare. */
+int hgs_project3d_fwd_bin(const float* means, const float* quats, const float* scales, const float* viewmats,
+                          const float* Ks, int C, int N, int width, int height, float eps2d, float near_plane,
+                          float far_plane, float radius_clip, int tile_size, int32_t* radii, float* means2d, float* depths,
+                          float* conics, float* compensations, int32_t* tiles_per_gauss, int32_t* visible_ids,
+                          long long* counts_dev, void* temp, size_t temp_bytes, void* stream);
+int hgs_isect_bin_scan(int C, int N, int tile_size, int tile_w, int tile_h, long long* counts_dev, void* temp,
+                       size_t temp_bytes, void* stream);
 /* Phase 2 (counts read back by the caller to size the outputs; n_visible_bound >= counts_dev[0] sizes the grid,
  * the exact counts are read on the device): every visible Gaussian drops a key (depth bits << 32 | flat index << 4
  * | mask of the super-tile's tiles it touches; C*N < 2^28) into the ranges of the super-tiles it touches; one CTA per (camera, super-tile) sorts its range on the SM (bitonic network
