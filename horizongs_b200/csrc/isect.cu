@@ -447,28 +447,31 @@ __global__ void __launch_bounds__(RS_THREADS) bin_scatter_kernel(
 // Ascending bitonic network in its uniform-direction form (first stage of every merge pairs i with
 // i ^ (k - 1), the others i with i ^ j; every exchange puts the minimum at the lower index, so +inf padding at
 // the top never moves).  Blocked layout: thread t holds keys [t * IPT, (t + 1) * IPT).
-__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
+// The network is written once for two key types: the 64-bit keys, and 32-bit keys (see sort_small32).
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 shfl_xor_key(u64 v, int m) {
     const unsigned lo = __shfl_xor_sync(0xFFFFFFFFu, (unsigned)v, m);
     const unsigned hi = __shfl_xor_sync(0xFFFFFFFFu, (unsigned)(v >> 32), m);
-    return ((unsigned long long)hi << 32) | lo;
+    return ((u64)hi << 32) | lo;
 }
-__device__ __forceinline__ void cmp_exch(unsigned long long& a, unsigned long long& b) {
-    const bool sw = b < a;
-    const unsigned long long lo = sw ? b : a, hi = sw ? a : b;
+__device__ __forceinline__ uint32_t shfl_xor_key(uint32_t v, int m) { return __shfl_xor_sync(0xFFFFFFFFu, v, m); }
+template <typename K>
+__device__ __forceinline__ void cmp_exch(K& a, K& b) {
+    const K lo = a < b ? a : b, hi = a < b ? b : a;
     a = lo;
     b = hi;
 }
-__device__ __forceinline__ unsigned long long pick(bool lower, unsigned long long mine, unsigned long long other) {
-    const bool take = lower ? (other < mine) : (mine < other);
-    return take ? other : mine;
+template <typename K>
+__device__ __forceinline__ K pick(bool lower, K mine, K other) {
+    const K lo = mine < other ? mine : other, hi = mine < other ? other : mine;
+    return lower ? lo : hi;
 }
 
 // stages j = j_hi, j_hi / 2, ..., 1 (plain i ^ j exchanges); s_buf: RS_THREADS * IPT keys
 // `active`: the warp holds at least one real key (a warp of +inf padding never changes: it only takes part in the
 // shared-memory stages, where its partners read it)
-template <int IPT>
-__device__ __forceinline__ void merge_xor_stages(unsigned long long (&v)[IPT], int j_hi, unsigned long long* s_buf,
-                                                 bool active = true) {
+template <int IPT, typename K>
+__device__ __forceinline__ void merge_xor_stages(K (&v)[IPT], int j_hi, K* s_buf, bool active = true) {
     const int t = threadIdx.x;
     int j = j_hi;
     for (; j >= 32 * IPT; j >>= 1) {          // partner in another warp: through shared memory ([a][t] layout)
@@ -486,7 +489,7 @@ __device__ __forceinline__ void merge_xor_stages(unsigned long long (&v)[IPT], i
         const int m = j / IPT;
         const bool lower = (t & m) == 0;
 #pragma unroll
-        for (int a = 0; a < IPT; ++a) v[a] = pick(lower, v[a], shfl_xor_u64(v[a], m));
+        for (int a = 0; a < IPT; ++a) v[a] = pick(lower, v[a], shfl_xor_key(v[a], m));
     }
 #pragma unroll
     for (int jj = IPT / 2; jj > 0; jj >>= 1) {  // partner in this thread
@@ -500,9 +503,8 @@ __device__ __forceinline__ void merge_xor_stages(unsigned long long (&v)[IPT], i
 
 // full sort of the CTA's RS_THREADS * IPT keys; k_max = smallest power of two >= the number of real keys
 // (the +inf padding above it is already in place)
-template <int IPT>
-__device__ __forceinline__ void cta_sort(unsigned long long (&v)[IPT], int k_max, unsigned long long* s_buf,
-                                         bool active = true) {
+template <int IPT, typename K>
+__device__ __forceinline__ void cta_sort(K (&v)[IPT], int k_max, K* s_buf, bool active = true) {
     const int t = threadIdx.x;
 #pragma unroll
     for (int k = 2; k <= IPT; k <<= 1) {      // merges inside the thread
@@ -521,7 +523,7 @@ __device__ __forceinline__ void cta_sort(unsigned long long (&v)[IPT], int k_max
         // mirror stage: key (t, a) meets key (t ^ (k / IPT - 1), IPT - 1 - a)
         const int m = k / IPT - 1;
         const bool lower = (t & (k / IPT / 2)) == 0;
-        unsigned long long o[IPT];
+        K o[IPT];
         if (m >= 32) {
 #pragma unroll
             for (int a = 0; a < IPT; ++a) s_buf[a * RS_THREADS + t] = v[a];
@@ -533,11 +535,11 @@ __device__ __forceinline__ void cta_sort(unsigned long long (&v)[IPT], int k_max
             for (int a = 0; a < IPT; ++a) v[a] = pick(lower, v[a], o[a]);
         } else if (active) {
 #pragma unroll
-            for (int a = 0; a < IPT; ++a) o[a] = shfl_xor_u64(v[IPT - 1 - a], m);
+            for (int a = 0; a < IPT; ++a) o[a] = shfl_xor_key(v[IPT - 1 - a], m);
 #pragma unroll
             for (int a = 0; a < IPT; ++a) v[a] = pick(lower, v[a], o[a]);
         }
-        merge_xor_stages<IPT>(v, k >> 2, s_buf, active);
+        merge_xor_stages<IPT, K>(v, k >> 2, s_buf, active);
     }
 }
 
@@ -570,8 +572,82 @@ __device__ __forceinline__ void sort_small(const unsigned long long* bucket, int
     load_blocked<IPT>(v, bucket, n, s_buf);
     int k_max = 2;
     while (k_max < n) k_max <<= 1;
-    cta_sort<IPT>(v, k_max, s_buf, (threadIdx.x & ~31) * IPT < n);
+    cta_sort<IPT, u64>(v, k_max, s_buf, (threadIdx.x & ~31) * IPT < n);
     stage_blocked<IPT>(v, s_buf);
+}
+
+// The same with a 32-bit network (a third of the work per stage).  Within a super-tile the depth bits span a small
+// range, so the keys are first ordered by key32 = ((depth bits - min) >> s) << B | arrival index -- B = bits of the
+// padded length, s = whatever makes the depth part fit -- which is unique and sorts them by depth up to the dropped
+// bits; a few odd-even exchange passes on the full 64-bit keys then put neighbours that agree in the kept depth bits
+// (and exact depth ties, which the arrival index ordered arbitrarily) into (depth, flat index) order.  A pathological
+// range (more than MAX_FIX rounds needed) falls back to the 64-bit network.  The sorted keys end up in s_buf[0, n).
+constexpr int MAX_FIX = 24;
+template <int IPT>
+__device__ __forceinline__ void sort_small32(const u64* bucket, int n, u64* s_buf, uint32_t* s_k32, uint32_t* s_red) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    uint32_t dmin = 0xFFFFFFFFu, dmax = 0u;
+    for (int i = t; i < n; i += RS_THREADS) {
+        const u64 key = bucket[i];
+        s_buf[i] = key;
+        const uint32_t d = (uint32_t)(key >> 32);
+        dmin = min(dmin, d);
+        dmax = max(dmax, d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        dmin = min(dmin, __shfl_xor_sync(0xFFFFFFFFu, dmin, o));
+        dmax = max(dmax, __shfl_xor_sync(0xFFFFFFFFu, dmax, o));
+    }
+    if (lane == 0) { s_red[warp] = dmin; s_red[RS_WARPS + warp] = dmax; }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) { dmin = min(dmin, s_red[w]); dmax = max(dmax, s_red[RS_WARPS + w]); }
+    int k_max = 2;
+    while (k_max < n) k_max <<= 1;
+    const int B = 31 - __clz(k_max);                       // k_max = 2^B >= n: arrival indices fit in B bits
+    const int range_bits = 32 - __clz(dmax - dmin);         // 0 when all depths are equal
+    const int sh = max(0, range_bits - (32 - B));
+    uint32_t v[IPT];
+#pragma unroll
+    for (int a = 0; a < IPT; ++a) {
+        const int i = t * IPT + a;
+        v[a] = i < n ? ((((uint32_t)(s_buf[i] >> 32) - dmin) >> sh) << B) | (uint32_t)i : 0xFFFFFFFFu;
+    }
+    cta_sort<IPT, uint32_t>(v, k_max, s_k32, (t & ~31) * IPT < n);
+    // bring the 64-bit keys into that order (gather into registers, then store blocked)
+    u64 w64[IPT];
+#pragma unroll
+    for (int a = 0; a < IPT; ++a) w64[a] = t * IPT + a < n ? s_buf[v[a] & ((1u << B) - 1u)] : KEY_INF;
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < IPT; ++a)
+        if (t * IPT + a < n) s_buf[t * IPT + a] = w64[a];
+    __syncthreads();
+    // odd-even exchange passes on the full keys until nothing moves
+    int round = 0;
+    for (; round < MAX_FIX; ++round) {
+        bool moved = false;
+        for (int j = 2 * t; j + 1 < n; j += 2 * RS_THREADS) {
+            const u64 a = s_buf[j], b = s_buf[j + 1];
+            if (b < a) { s_buf[j] = b; s_buf[j + 1] = a; moved = true; }
+        }
+        __syncthreads();
+        for (int j = 2 * t + 1; j + 1 < n; j += 2 * RS_THREADS) {
+            const u64 a = s_buf[j], b = s_buf[j + 1];
+            if (b < a) { s_buf[j] = b; s_buf[j + 1] = a; moved = true; }
+        }
+        if (!__syncthreads_or(moved)) break;
+    }
+    if (round == MAX_FIX) {
+        // long runs of equal (kept) depth bits: finish with the 64-bit network
+        u64 k64[IPT];
+#pragma unroll
+        for (int a = 0; a < IPT; ++a) k64[a] = t * IPT + a < n ? s_buf[t * IPT + a] : KEY_INF;
+        __syncthreads();
+        cta_sort<IPT, u64>(k64, k_max, s_buf, (t & ~31) * IPT < n);
+        stage_blocked<IPT>(k64, s_buf);
+    }
 }
 
 // one global-memory exchange stage of the big merge: pairs (i, p) with bit `h` of i clear,
@@ -592,18 +668,17 @@ __device__ __forceinline__ void global_stage(unsigned long long* buf, int n, int
     __syncthreads();
 }
 
-// ranges longer than SORT_CHUNK: chunk sorts + merges whose wide strides go through (L2-resident) global
-// memory; sorted in place
-__device__ void sort_big(unsigned long long* bucket, int n, unsigned long long* s_buf) {
+// ranges longer than SORT_CHUNK: chunk sorts (32-bit network, as above) + merges whose wide strides go through
+// (L2-resident) global memory; sorted in place
+__device__ void sort_big(unsigned long long* bucket, int n, unsigned long long* s_buf, uint32_t* s_k32, uint32_t* s_red) {
     constexpr int IPT = SORT_CHUNK / RS_THREADS;
     const int n_chunks = (n + SORT_CHUNK - 1) / SORT_CHUNK;
     unsigned long long v[IPT];
     for (int c = 0; c < n_chunks; ++c) {
         unsigned long long* cb = bucket + (long long)c * SORT_CHUNK;
         const int cn = min(SORT_CHUNK, n - c * SORT_CHUNK);
-        load_blocked<IPT>(v, cb, cn, s_buf);
-        cta_sort<IPT>(v, SORT_CHUNK, s_buf);
-        stage_blocked<IPT>(v, s_buf);
+        sort_small32<IPT>(cb, cn, s_buf, s_k32, s_red);
+        __syncthreads();
         for (int i = threadIdx.x; i < cn; i += RS_THREADS) cb[i] = s_buf[i];
         __syncthreads();
     }
@@ -616,7 +691,7 @@ __device__ void sort_big(unsigned long long* bucket, int n, unsigned long long* 
             unsigned long long* cb = bucket + (long long)c * SORT_CHUNK;
             const int cn = min(SORT_CHUNK, n - c * SORT_CHUNK);
             load_blocked<IPT>(v, cb, cn, s_buf);
-            merge_xor_stages<IPT>(v, SORT_CHUNK >> 1, s_buf);
+            merge_xor_stages<IPT, u64>(v, SORT_CHUNK >> 1, s_buf);
             stage_blocked<IPT>(v, s_buf);
             for (int i = threadIdx.x; i < cn; i += RS_THREADS) cb[i] = s_buf[i];
             __syncthreads();
@@ -630,6 +705,8 @@ __global__ void __launch_bounds__(RS_THREADS) super_sort_kernel(
     BinGeom G, int total_super, const int32_t* __restrict__ soff, const long long* __restrict__ counts_dev,
     unsigned long long* bucket, uint32_t* __restrict__ tile_count) {
     __shared__ __align__(16) unsigned long long s_buf[SORT_CHUNK];
+    __shared__ uint32_t s_k32[SORT_CHUNK];
+    __shared__ uint32_t s_red[2 * RS_WARPS];
     __shared__ uint32_t s_cnt[ST2];
     const int s = blockIdx.x;
     const int n_super = G.stw * G.sth, n_tiles = G.tile_w * G.tile_h;
@@ -644,11 +721,11 @@ __global__ void __launch_bounds__(RS_THREADS) super_sort_kernel(
     if (n > 0) {
         unsigned long long* bk = bucket + begin;
         const bool big = n > SORT_CHUNK;
-        if (n <= RS_THREADS) sort_small<1>(bk, n, s_buf);
-        else if (n <= 2 * RS_THREADS) sort_small<2>(bk, n, s_buf);
-        else if (n <= 4 * RS_THREADS) sort_small<4>(bk, n, s_buf);
-        else if (!big) sort_small<8>(bk, n, s_buf);
-        else sort_big(bk, n, s_buf);
+        if (n <= RS_THREADS) sort_small32<1>(bk, n, s_buf, s_k32, s_red);
+        else if (n <= 2 * RS_THREADS) sort_small32<2>(bk, n, s_buf, s_k32, s_red);
+        else if (n <= 4 * RS_THREADS) sort_small32<4>(bk, n, s_buf, s_k32, s_red);
+        else if (!big) sort_small32<8>(bk, n, s_buf, s_k32, s_red);
+        else sort_big(bk, n, s_buf, s_k32, s_red);
         for (int i = threadIdx.x; i < n; i += RS_THREADS) {
             const unsigned long long key = big ? bk[i] : s_buf[i];
             if (!big) bk[i] = key;
