@@ -329,12 +329,12 @@ __global__ void __launch_bounds__(BLK) blend2d_bwd_kernel(
                     atomicAdd(vr + 3 + k, v_v[k]);
                     atomicAdd(vr + 6 + k, v_w[k]);
                 }
-                atomicAdd(v_means2d + g * 2 + 0, v_x);
-                atomicAdd(v_means2d + g * 2 + 1, v_y);
+                atomicAdd(v_means2d + (long long)g * 2 + 0, v_x);
+                atomicAdd(v_means2d + (long long)g * 2 + 1, v_y);
                 atomicAdd(v_opacities + g, v_o);
                 if (v_densify != nullptr) {
-                    atomicAdd(v_densify + g * 2 + 0, v_dx);
-                    atomicAdd(v_densify + g * 2 + 1, v_dy);
+                    atomicAdd(v_densify + (long long)g * 2 + 0, v_dx);
+                    atomicAdd(v_densify + (long long)g * 2 + 1, v_dy);
                 }
             }
         }

@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(BLK) blend3d_fwd_kernel(
             const int g = flatten_ids[idx];
             const float2 xy = reinterpret_cast<const float2*>(means2d)[g];
             s_xyo[tr] = make_float4(xy.x, xy.y, opacities[g], 0.f);
-            s_con[tr] = make_float4(conics[g * 3 + 0], conics[g * 3 + 1], conics[g * 3 + 2], 0.f);
+            s_con[tr] = make_float4(conics[(long long)g * 3 + 0], conics[(long long)g * 3 + 1], conics[(long long)g * 3 + 2], 0.f);
 #pragma unroll
             for (int k = 0; k < D; ++k)
                 s_col[tr * D + k] = (k < CH) ? colors[(long long)g * CH + k] : depths[g];
@@ -654,7 +654,7 @@ __global__ void __launch_bounds__(BLK) blend3d_bwd_kernel(
             s_id[tr] = g;
             const float2 xy = reinterpret_cast<const float2*>(means2d)[g];
             s_xyo[tr] = make_float4(xy.x, xy.y, opacities[g], 0.f);
-            s_con[tr] = make_float4(conics[g * 3 + 0], conics[g * 3 + 1], conics[g * 3 + 2], 0.f);
+            s_con[tr] = make_float4(conics[(long long)g * 3 + 0], conics[(long long)g * 3 + 1], conics[(long long)g * 3 + 2], 0.f);
 #pragma unroll
             for (int k = 0; k < D; ++k)
                 s_col[tr * D + k] = (k < CH) ? colors[(long long)g * CH + k] : depths[g];
@@ -718,14 +718,14 @@ __global__ void __launch_bounds__(BLK) blend3d_bwd_kernel(
                     if (k < CH) atomicAdd(v_colors + (long long)g * CH + k, v_col[k]);
                     else atomicAdd(v_depths + g, v_col[k]);
                 }
-                atomicAdd(v_conics + g * 3 + 0, v_con0);
-                atomicAdd(v_conics + g * 3 + 1, v_con1);
-                atomicAdd(v_conics + g * 3 + 2, v_con2);
-                atomicAdd(v_means2d + g * 2 + 0, v_x);
-                atomicAdd(v_means2d + g * 2 + 1, v_y);
+                atomicAdd(v_conics + (long long)g * 3 + 0, v_con0);
+                atomicAdd(v_conics + (long long)g * 3 + 1, v_con1);
+                atomicAdd(v_conics + (long long)g * 3 + 2, v_con2);
+                atomicAdd(v_means2d + (long long)g * 2 + 0, v_x);
+                atomicAdd(v_means2d + (long long)g * 2 + 1, v_y);
                 if (v_means2d_abs != nullptr) {
-                    atomicAdd(v_means2d_abs + g * 2 + 0, v_ax);
-                    atomicAdd(v_means2d_abs + g * 2 + 1, v_ay);
+                    atomicAdd(v_means2d_abs + (long long)g * 2 + 0, v_ax);
+                    atomicAdd(v_means2d_abs + (long long)g * 2 + 1, v_ay);
                 }
                 atomicAdd(v_opacities + g, v_o);
             }

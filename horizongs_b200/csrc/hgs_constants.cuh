@@ -1,5 +1,5 @@
 // Numeric constants of the rasterization path (CUDA side).
-// Mirror of oracle/constants.py; tests/test_constants.py checks the two agree.
+// Mirror of oracle/constants.py; tests/test_oracle_cpu.py::test_constants_agree_between_oracle_and_cuda_header checks the two agree.
 // Values restate the published gsplat ~v1.4 algorithm (PARITY UNPINNED).
 #pragma once
 

@@ -340,8 +340,8 @@ HGS_API int hgs_sh_fwd(int degree, int K, const float* dirs, const float* means,
     if (N == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (vis_ids != nullptr) {
-        cudaError_t e = cudaMemsetAsync(colors, 0, (size_t)C * N * 3 * sizeof(float), st);
-        if (e != cudaSuccess) return (int)e;
+        // work-list path: only the rows of the listed (visible) Gaussians are written -- every consumer of the colours
+        // inside the rasterization pipeline (record packing, SH backward, fused exchange) goes through the same list
         if (n_vis == 0) return 0;
         const int grid = hgs_ceil_div(n_vis, SB);
 #define LAUNCH(DEG) sh_fwd_vis_kernel<DEG><<<grid, SB, 0, st>>>(dirs, means, campos, coeffs, vis_ids, n_vis, n_vis_dev, N, K, post, colors);

@@ -82,15 +82,22 @@ class _AnchorDecode(torch.autograd.Function):
 
 def generate_neural_gaussians(anchor: Tensor, anchor_feat: Tensor, offset: Tensor, scaling: Tensor, cam_center: Tensor,
                               visible_mask: Tensor, mlp_opacity: nn.Sequential, mlp_cov: nn.Sequential,
-                              mlp_color: nn.Sequential) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+                              mlp_color: nn.Sequential, dist2level: str = "floor"
+                              ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     """-> (xyz [M,3], color [M,3], opacity [M,1], scaling [M,3], rot [M,4], mask [V*k] bool), the tensors
     scene/basic_model.py:297-371 returns (without the pass-through `offsets` / `active_sh_degree`).
 
     anchor [A,3], anchor_feat [A,32], offset [A,k,3], scaling [A,6] POST-activation (get_scaling = exp(_scaling),
     lod_model.py:182-183), cam_center [3], visible_mask [A] bool; the MLPs are the nn.Sequential modules of
-    scene/lod_model.py:67-84 (a trailing nn.Sigmoid on the colour MLP is honoured)."""
+    scene/lod_model.py:67-84 (a trailing nn.Sigmoid on the colour MLP is honoured).  dist2level: the model's level
+    mode; 'progressive' (which scales the opacities by _prog_ratio, lod_model.py:215-222) raises."""
     if not anchor.is_cuda:
         raise ValueError("generate_neural_gaussians runs on CUDA tensors only (no CPU fallback)")
+    if dist2level == "progressive":
+        # scene/lod_model.py:215-222 multiplies the opacities by the per-anchor _prog_ratio in that mode
+        # (smooth_complement); the fused decode implements smooth_complement == 1 (basic_model.py:43-44)
+        raise NotImplementedError("dist2level='progressive' (opacity x _prog_ratio, lod_model.py:215-222) is not "
+                                  "supported by the fused decode; use the PyTorch decode of the reference")
     A, k = anchor.shape[0], offset.shape[1]
     assert anchor_feat.shape == (A, 32), "feat_dim 32 (one lane per hidden unit)"
     assert offset.shape == (A, k, 3) and 1 <= k <= 16 and scaling.shape == (A, 6) and visible_mask.shape == (A,)

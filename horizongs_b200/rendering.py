@@ -91,6 +91,13 @@ def rasterization(
     if packed or sparse_grad or distributed or covars is not None or camera_model != "pinhole":
         raise NotImplementedError("packed / sparse_grad / distributed / covars / non-pinhole are not supported")
     assert rasterize_mode in ("classic", "antialiased"), rasterize_mode
+    if rasterize_mode == "antialiased" and torch.is_grad_enabled() and any(
+            t.requires_grad for t in (means, quats, scales)):
+        # gsplat back-propagates v_compensations into the covariance; that VJP is not implemented here, so training with
+        # it would silently drop a gradient term (the reference only uses 'classic', render.py:40-54)
+        raise NotImplementedError("rasterize_mode='antialiased' is forward-only here: the gradient of the opacity "
+                                  "compensation w.r.t. means / quats / scales is not implemented (use torch.no_grad(), "
+                                  "or rasterize_mode='classic' as the reference does)")
     C, N = _validate(means, quats, scales, opacities, colors, viewmats, Ks, render_mode, sh_degree, backgrounds)
     width, height = int(width), int(height)
     tile_width = math.ceil(width / float(tile_size))

@@ -83,7 +83,8 @@ int hgs_project2d_bwd(const float* means, const float* quats, const float* scale
  * Direction of Gaussian n for camera c is dirs[c,n,:] if dirs != NULL, else means[n,:] - campos[c,:]
  * (normalised inside).  coeffs[N,K,3] is shared by all cameras.  radii (or NULL) masks culled rows to 0.
  * post != 0 fuses gsplat's `clamp_min(colors + 0.5, 0)`.  out: colors[C,N,3].
- * vis_ids (or NULL) = work list of visible flat indices (then radii is not read).  n_vis_dev (or NULL): the length
+ * vis_ids (or NULL) = work list of visible flat indices (then radii is not read, and ONLY the listed rows of colors
+ * are written: the rows of culled Gaussians are left untouched).  n_vis_dev (or NULL): the length
  * of the work list as a DEVICE value (counts_dev[0] of hgs_isect_bin_prepare); n_vis is then only an upper bound, so the
  * call can be enqueued before the host has read the count. */
 int hgs_sh_fwd(int degree, int K, const float* dirs, const float* means, const float* campos, const float* coeffs,

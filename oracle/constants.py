@@ -1,7 +1,7 @@
 """Numeric constants of the rasterization path, one place for the oracle.
 
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  The CUDA side keeps the
-same values in horizongs_b200/csrc/hgs_constants.cuh; tests/test_constants.py
+same values in horizongs_b200/csrc/hgs_constants.cuh; tests/test_oracle_cpu.py (test_constants_agree_between_oracle_and_cuda_header)
 checks the two files agree, so a single edit re-aligns both once a real gsplat
 is available to compare against (SURVEY.md section 7 "hard parts").
 

@@ -71,3 +71,44 @@ def test_reader_rejects_what_it_does_not_support(tmp_path):
                   + np.array([1.5, -2.0], "<f4").tobytes())
     names, data, info = P.read_ply(str(p))
     assert names == ["x"] and data[:, 0].tolist() == [1.5, -2.0] and info == {}
+
+
+# ---- fixtures in the reference's plyfile layout (tests/golden/make_golden_ply.py, written without ply_io) --------------
+def _golden(name):
+    import os
+    return os.path.join(os.path.dirname(__file__), "golden", name)
+
+
+def test_reads_anchor_ply_in_the_reference_layout_and_rewrites_it_byte_for_byte(tmp_path):
+    """scene/lod_model.py:374-418 save_ply layout: values come back in the model's layout (load_ply, :420-465) and
+    save_anchors() reproduces the file exactly"""
+    import numpy as np
+    from horizongs_b200 import ply_io
+    G = np.load(_golden("reference_layout_ply.npz"))
+    got = ply_io.load_anchors(_golden("reference_layout_anchor.ply"))
+    assert np.array_equal(got["anchor"], G["anchor"]) and np.array_equal(got["offset"], G["offset"])
+    assert np.array_equal(got["anchor_feat"], G["feat"]) and np.array_equal(got["scaling"], G["scaling"])
+    assert np.array_equal(got["rotation"], G["rot"]) and np.array_equal(got["extra_level"], G["extra"][:, 0])
+    assert got["level"].dtype == np.int16 and np.array_equal(got["level"], G["level"][:, 0].astype(np.int16))
+    assert got["aerial_levels"] == 3 and got["street_levels"] == 8 and abs(got["standard_dist"] - 26.686) < 1e-6
+    out = str(tmp_path / "a.ply")
+    ply_io.save_anchors(out, got["anchor"], got["level"], got["extra_level"], got["offset"], got["anchor_feat"],
+                        got["scaling"], got["rotation"], got["standard_dist"], got["aerial_levels"], got["street_levels"])
+    assert open(out, "rb").read() == open(_golden("reference_layout_anchor.ply"), "rb").read()
+
+
+def test_reads_explicit_ply_in_the_reference_layout_and_rewrites_it_byte_for_byte(tmp_path):
+    """scene/lod_model.py:681-779 save_explicit layout (channel-major SH): colours come back as [N,K,3] (what
+    generate_explicit_gaussians feeds the rasterizer, basic_model.py:373-383), and the writer reproduces the file"""
+    import numpy as np
+    from horizongs_b200 import ply_io
+    G = np.load(_golden("reference_layout_ply.npz"))
+    got = ply_io.load_explicit_gaussians(_golden("reference_layout_explicit.ply"))
+    assert np.array_equal(got["xyz"], G["xyz"]) and np.array_equal(got["colors"], G["color"])
+    assert np.array_equal(got["opacity"], G["opacity"][:, 0]) and np.array_equal(got["scales"], G["scale"])
+    assert np.array_equal(got["rots"], G["rotation"]) and np.array_equal(got["level"], G["lvl"][:, 0].astype(np.int16))
+    out = str(tmp_path / "e.ply")
+    ply_io.save_explicit_gaussians(out, got["xyz"], got["level"], got["extra_level"], got["colors"], got["opacity"],
+                                   got["scales"], got["rots"], got["standard_dist"], got["aerial_levels"],
+                                   got["street_levels"])
+    assert open(out, "rb").read() == open(_golden("reference_layout_explicit.ply"), "rb").read()
