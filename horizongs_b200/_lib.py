@@ -60,9 +60,9 @@ SIGNATURES = {
     "hgs_ssim_partials": (_ll, [_i, _i, _i]),
     "hgs_ssim_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "hgs_ssim_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
-    "hgs_decode_count": (_i, [_p] * 5 + [_ll, _i, _i] + [_p] * 3 + [_p]),
-    "hgs_decode_fwd": (_i, [_p] * 7 + [_ll, _i, _i, _i] + [_p] * 8 + [_p]),
-    "hgs_decode_bwd": (_i, [_p] * 8 + [_ll, _i, _i, _i] + [_p] * 12 + [_p]),
+    "hgs_decode_count": (_i, [_p] * 5 + [_ll, _i, _i, _i, _i] + [_p] * 3 + [_p]),
+    "hgs_decode_fwd": (_i, [_p] * 7 + [_ll, _i, _i, _i, _i, _i] + [_p] * 8 + [_p]),
+    "hgs_decode_bwd": (_i, [_p] * 8 + [_ll, _i, _i, _i, _i, _i] + [_p] * 12 + [_p]),
     "hgs_anchor_filter": (_i, [_p, _p, _p, _p, _i, _p, _p, _f, _f, _f, _i, _i, _p, _p, _i, _i, _i, _f, _f, _f, _f, _p, _p]),
     "hgs_exchange_row_floats": (_i, [_p, _i]),
     "hgs_exchange_mailbox_bytes": (_sz, [_i, _ll, _ll, _i]),

@@ -22,10 +22,18 @@
 namespace {
 
 constexpr int DF = 32;                  // feat_dim = hidden width
-constexpr int DIN = DF + 3;             // MLP input: features + unit view direction
+constexpr int DINMAX = DF + 3;          // MLP input: features (+ unit view direction when view_dim == 3)
 constexpr int DKMAX = 16;               // max offsets per anchor
-constexpr int DTOTMAX = 11 * DKMAX;     // outputs: k opacity + 7k cov + 3k colour
+constexpr int DCMAX = 48;               // max colour floats per offset (3 = RGB, 3 (d + 1)^2 = SH of degree d <= 3)
 constexpr int DWARPS = 8;
+constexpr int DSMEM_MAX = 227 * 1024;
+
+// shape of one decode call: k offsets, cd colour floats per offset, vd = 0 | 3 view-direction inputs
+struct DShape {
+    int k, cd, vd;
+    __host__ __device__ int tot() const { return (8 + cd) * k; }     // outputs: k opacity + 7k cov + cd k colour
+    __host__ __device__ int din() const { return DF + vd; }
+};
 
 struct DecodeMlp {
     const float* W1[3];   // [F, F+3]   0 = opacity, 1 = cov, 2 = colour
@@ -48,11 +56,11 @@ struct SmemW {
     float* W2;
     float* b2;
 };
-__host__ __device__ inline int smem_w_floats(int tot) { return 3 * DF * DIN + 3 * DF + 2 * DF * tot + tot; }
-__device__ __forceinline__ SmemW carve(float* base, int tot) {
+__host__ __device__ inline int smem_w_floats(int tot, int din) { return 3 * DF * din + 3 * DF + 2 * DF * tot + tot; }
+__device__ __forceinline__ SmemW carve(float* base, int tot, int din) {
     SmemW s;
     s.W1 = base;
-    s.b1 = s.W1 + 3 * DF * DIN;
+    s.b1 = s.W1 + 3 * DF * din;
     s.W2T = s.b1 + 3 * DF;
     s.W2 = s.W2T + DF * tot;
     s.b2 = s.W2 + tot * DF;
@@ -62,8 +70,8 @@ __device__ __forceinline__ SmemW carve(float* base, int tot) {
 __device__ __forceinline__ int mlp_of(int o, int k) { return o < k ? 0 : (o < 8 * k ? 1 : 2); }
 __device__ __forceinline__ int first_of(int m, int k) { return m == 0 ? 0 : (m == 1 ? k : 8 * k); }
 
-__device__ void load_weights(const DecodeMlp& P, const SmemW& S, int k, bool need_w2_rowmajor) {
-    const int tot = 11 * k;
+__device__ void load_weights(const DecodeMlp& P, const SmemW& S, const DShape D, bool need_w2_rowmajor) {
+    const int tot = D.tot(), k = D.k, DIN = D.din();
     for (int i = threadIdx.x; i < 3 * DF * DIN; i += blockDim.x) S.W1[i] = P.W1[i / (DF * DIN)][i % (DF * DIN)];
     for (int i = threadIdx.x; i < 3 * DF; i += blockDim.x) S.b1[i] = P.b1[i / DF][i % DF];
     for (int i = threadIdx.x; i < tot * DF; i += blockDim.x) {
@@ -81,18 +89,18 @@ __device__ void load_weights(const DecodeMlp& P, const SmemW& S, int k, bool nee
 }
 
 // hidden layer of MLP m for this warp's anchor: lane j returns the pre-activation of hidden unit j
-__device__ __forceinline__ float hidden_pre(const SmemW& S, int m, float x_lane, float d0, float d1, float d2, int lane) {
-    const float* w = S.W1 + (m * DF + lane) * DIN;
+__device__ __forceinline__ float hidden_pre(const SmemW& S, int m, float x_lane, float d0, float d1, float d2, int lane,
+                                            int vd) {
+    const float* w = S.W1 + (m * DF + lane) * (DF + vd);
     float acc = S.b1[m * DF + lane];
 #pragma unroll
     for (int i = 0; i < DF; ++i) acc += w[i] * __shfl_sync(0xFFFFFFFFu, x_lane, i);
-    acc += w[DF] * d0 + w[DF + 1] * d1 + w[DF + 2] * d2;
+    if (vd == 3) acc += w[DF] * d0 + w[DF + 1] * d1 + w[DF + 2] * d2;
     return acc;
 }
 // outputs [o_begin, o_end) of the concatenated output vector -> s_out (pre-activation); s_h = [3][F] hidden activations
-__device__ __forceinline__ void outputs(const SmemW& S, const float* s_h, int k, int o_begin, int o_end, float* s_out,
-                                        int lane) {
-    const int tot = 11 * k;
+__device__ __forceinline__ void outputs(const SmemW& S, const float* s_h, int k, int tot, int o_begin, int o_end,
+                                        float* s_out, int lane) {
     for (int o = o_begin + lane; o < o_end; o += 32) {
         const float* h = s_h + mlp_of(o, k) * DF;
         float acc = S.b2[o];
@@ -122,22 +130,22 @@ __device__ __forceinline__ WarpAnchor load_anchor(const float* __restrict__ anch
 __global__ void __launch_bounds__(DWARPS * 32) decode_count_kernel(DecodeMlp P, const float* __restrict__ anchor,
                                                                   const float* __restrict__ feat,
                                                                   const float* __restrict__ cam,
-                                                                  const long long* __restrict__ vis, long long V, int k,
+                                                                  const long long* __restrict__ vis, long long V, DShape D,
                                                                   float* __restrict__ opac_all,
                                                                   int32_t* __restrict__ bits, int32_t* __restrict__ cnt) {
     extern __shared__ float sm[];
-    const int tot = 11 * k;
-    const SmemW S = carve(sm, tot);
-    load_weights(P, S, k, false);
-    float* s_h = sm + smem_w_floats(tot) + (threadIdx.x >> 5) * (3 * DF + DTOTMAX);
+    const int tot = D.tot(), k = D.k;
+    const SmemW S = carve(sm, tot, D.din());
+    load_weights(P, S, D, false);
+    float* s_h = sm + smem_w_floats(tot, D.din()) + (threadIdx.x >> 5) * (3 * DF + tot);
     float* s_out = s_h + 3 * DF;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (long long v = (long long)blockIdx.x * DWARPS + warp; v < V; v += (long long)gridDim.x * DWARPS) {
         const long long a = vis[v];
         const WarpAnchor w = load_anchor(anchor, feat, cam, a, lane);
-        s_h[lane] = fmaxf(hidden_pre(S, 0, w.x_lane, w.d0, w.d1, w.d2, lane), 0.f);
+        s_h[lane] = fmaxf(hidden_pre(S, 0, w.x_lane, w.d0, w.d1, w.d2, lane, D.vd), 0.f);
         __syncwarp();
-        outputs(S, s_h, k, 0, k, s_out, lane);
+        outputs(S, s_h, k, tot, 0, k, s_out, lane);
         __syncwarp();
         float op = 0.f;
         if (lane < k) {
@@ -153,15 +161,15 @@ __global__ void __launch_bounds__(DWARPS * 32) decode_count_kernel(DecodeMlp P, 
 // ---- forward ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(DWARPS * 32) decode_fwd_kernel(
     DecodeMlp P, const float* __restrict__ anchor, const float* __restrict__ feat, const float* __restrict__ offset,
-    const float* __restrict__ scaling, const float* __restrict__ cam, const long long* __restrict__ vis, long long V, int k,
-    int color_sigmoid, const float* __restrict__ opac_all, const int32_t* __restrict__ bits,
+    const float* __restrict__ scaling, const float* __restrict__ cam, const long long* __restrict__ vis, long long V,
+    DShape D, int color_sigmoid, const float* __restrict__ opac_all, const int32_t* __restrict__ bits,
     const long long* __restrict__ row0, float* __restrict__ xyz, float* __restrict__ color, float* __restrict__ opacity,
     float* __restrict__ scales, float* __restrict__ quats) {
     extern __shared__ float sm[];
-    const int tot = 11 * k;
-    const SmemW S = carve(sm, tot);
-    load_weights(P, S, k, false);
-    float* s_h = sm + smem_w_floats(tot) + (threadIdx.x >> 5) * (3 * DF + DTOTMAX);
+    const int tot = D.tot(), k = D.k, cd = D.cd;
+    const SmemW S = carve(sm, tot, D.din());
+    load_weights(P, S, D, false);
+    float* s_h = sm + smem_w_floats(tot, D.din()) + (threadIdx.x >> 5) * (3 * DF + tot);
     float* s_out = s_h + 3 * DF;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (long long v = (long long)blockIdx.x * DWARPS + warp; v < V; v += (long long)gridDim.x * DWARPS) {
@@ -169,25 +177,23 @@ __global__ void __launch_bounds__(DWARPS * 32) decode_fwd_kernel(
         if (m == 0u) continue;          // warp-uniform
         const long long a = vis[v];
         const WarpAnchor w = load_anchor(anchor, feat, cam, a, lane);
-        s_h[DF + lane] = fmaxf(hidden_pre(S, 1, w.x_lane, w.d0, w.d1, w.d2, lane), 0.f);
-        s_h[2 * DF + lane] = fmaxf(hidden_pre(S, 2, w.x_lane, w.d0, w.d1, w.d2, lane), 0.f);
+        s_h[DF + lane] = fmaxf(hidden_pre(S, 1, w.x_lane, w.d0, w.d1, w.d2, lane, D.vd), 0.f);
+        s_h[2 * DF + lane] = fmaxf(hidden_pre(S, 2, w.x_lane, w.d0, w.d1, w.d2, lane, D.vd), 0.f);
         __syncwarp();
-        outputs(S, s_h, k, k, tot, s_out, lane);
+        outputs(S, s_h, k, tot, k, tot, s_out, lane);
         __syncwarp();
         if (lane < k && ((m >> lane) & 1u)) {
             const long long r = row0[v] + __popc(m & ((1u << lane) - 1u));
             const float* sr = s_out + k + 7 * lane;
-            const float* co = s_out + 8 * k + 3 * lane;
+            const float* co = s_out + 8 * k + cd * lane;
             const float* gs = scaling + a * 6;
             const float* of = offset + (a * k + lane) * 3;
             xyz[r * 3] = w.ax + of[0] * gs[0];
             xyz[r * 3 + 1] = w.ay + of[1] * gs[1];
             xyz[r * 3 + 2] = w.az + of[2] * gs[2];
+            for (int c = 0; c < cd; ++c) color[r * cd + c] = color_sigmoid ? sigmoidf_(co[c]) : co[c];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                color[r * 3 + c] = color_sigmoid ? sigmoidf_(co[c]) : co[c];
-                scales[r * 3 + c] = gs[3 + c] * sigmoidf_(sr[c]);
-            }
+            for (int c = 0; c < 3; ++c) scales[r * 3 + c] = gs[3 + c] * sigmoidf_(sr[c]);
             const float n = fmaxf(sqrtf(sr[3] * sr[3] + sr[4] * sr[4] + sr[5] * sr[5] + sr[6] * sr[6]), 1e-12f);
             reinterpret_cast<float4*>(quats)[r] = make_float4(sr[3] / n, sr[4] / n, sr[5] / n, sr[6] / n);
             opacity[r] = opac_all[v * k + lane];
@@ -200,17 +206,17 @@ __global__ void __launch_bounds__(DWARPS * 32) decode_fwd_kernel(
 __global__ void __launch_bounds__(DWARPS * 32) decode_bwd_kernel(
     DecodeMlp P, DecodeMlpGrad G, const float* __restrict__ anchor, const float* __restrict__ feat,
     const float* __restrict__ offset, const float* __restrict__ scaling, const float* __restrict__ cam,
-    const long long* __restrict__ vis, long long V, int k, int color_sigmoid, const float* __restrict__ opac_all,
+    const long long* __restrict__ vis, long long V, DShape D, int color_sigmoid, const float* __restrict__ opac_all,
     const int32_t* __restrict__ bits, const long long* __restrict__ row0, const float* __restrict__ v_xyz,
     const float* __restrict__ v_color, const float* __restrict__ v_opacity, const float* __restrict__ v_scales,
     const float* __restrict__ v_quats, float* __restrict__ g_anchor, float* __restrict__ g_feat,
     float* __restrict__ g_offset, float* __restrict__ g_scaling) {
     extern __shared__ float sm[];
-    const int tot = 11 * k;
-    const SmemW S = carve(sm, tot);
-    load_weights(P, S, k, true);
-    // CTA-wide gradient accumulators: dW1[3][F][F+3] | db1[3][F] | dW2[TOT][F] | db2[TOT]
-    float* a_W1 = sm + smem_w_floats(tot);
+    const int tot = D.tot(), k = D.k, cd = D.cd, DIN = D.din();
+    const SmemW S = carve(sm, tot, DIN);
+    load_weights(P, S, D, true);
+    // CTA-wide gradient accumulators: dW1[3][F][F+vd] | db1[3][F] | dW2[TOT][F] | db2[TOT]
+    float* a_W1 = sm + smem_w_floats(tot, DIN);
     float* a_b1 = a_W1 + 3 * DF * DIN;
     float* a_W2 = a_b1 + 3 * DF;
     float* a_b2 = a_W2 + tot * DF;
@@ -218,11 +224,11 @@ __global__ void __launch_bounds__(DWARPS * 32) decode_bwd_kernel(
     for (int i = threadIdx.x; i < n_acc; i += blockDim.x) a_W1[i] = 0.f;
     __syncthreads();
     // per-warp scratch: h[3][F] | pre-mask [3][F] as floats | out[TOT] | gout[TOT] | x[F+3] | dpre[3][F]
-    float* s_h = a_W1 + n_acc + (threadIdx.x >> 5) * (3 * DF + 2 * DTOTMAX + DIN + 3 * DF + 8);
+    float* s_h = a_W1 + n_acc + (threadIdx.x >> 5) * (3 * DF + 2 * tot + DINMAX + 3 * DF + 8);
     float* s_out = s_h + 3 * DF;
-    float* s_gout = s_out + DTOTMAX;
-    float* s_x = s_gout + DTOTMAX;
-    float* s_dpre = s_x + DIN;
+    float* s_gout = s_out + tot;
+    float* s_x = s_gout + tot;
+    float* s_dpre = s_x + DINMAX;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (long long v = (long long)blockIdx.x * DWARPS + warp; v < V; v += (long long)gridDim.x * DWARPS) {
         const unsigned m = (unsigned)bits[v];
@@ -232,21 +238,21 @@ __global__ void __launch_bounds__(DWARPS * 32) decode_bwd_kernel(
         float pre[3];
 #pragma unroll
         for (int mm = 0; mm < 3; ++mm) {
-            pre[mm] = hidden_pre(S, mm, w.x_lane, w.d0, w.d1, w.d2, lane);
+            pre[mm] = hidden_pre(S, mm, w.x_lane, w.d0, w.d1, w.d2, lane, D.vd);
             s_h[mm * DF + lane] = fmaxf(pre[mm], 0.f);
         }
         s_x[lane] = w.x_lane;
         if (lane < 3) s_x[DF + lane] = lane == 0 ? w.d0 : (lane == 1 ? w.d1 : w.d2);
         for (int o = lane; o < tot; o += 32) s_gout[o] = 0.f;
         __syncwarp();
-        outputs(S, s_h, k, k, tot, s_out, lane);
+        outputs(S, s_h, k, tot, k, tot, s_out, lane);
         __syncwarp();
         // output gradients of the kept offsets, and the direct paths (anchor, offset, grid scaling)
         float ga0 = 0.f, ga1 = 0.f, ga2 = 0.f, gs[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (lane < k && ((m >> lane) & 1u)) {
             const long long r = row0[v] + __popc(m & ((1u << lane) - 1u));
             const float* sr = s_out + k + 7 * lane;
-            const float* co = s_out + 8 * k + 3 * lane;
+            const float* co = s_out + 8 * k + cd * lane;
             const float* gsc = scaling + a * 6;
             const float* of = offset + (a * k + lane) * 3;
             const float op = opac_all[v * k + lane];
@@ -261,12 +267,14 @@ __global__ void __launch_bounds__(DWARPS * 32) decode_bwd_kernel(
                 const float vs = v_scales[r * 3 + c];
                 gs[3 + c] = vs * sg;
                 s_gout[k + 7 * lane + c] = vs * gsc[3 + c] * sg * (1.0f - sg);
-                const float vc = v_color[r * 3 + c];
+            }
+            for (int c = 0; c < cd; ++c) {
+                const float vc = v_color[r * cd + c];
                 if (color_sigmoid) {
                     const float sc = sigmoidf_(co[c]);
-                    s_gout[8 * k + 3 * lane + c] = vc * sc * (1.0f - sc);
+                    s_gout[8 * k + cd * lane + c] = vc * sc * (1.0f - sc);
                 } else {
-                    s_gout[8 * k + 3 * lane + c] = vc;
+                    s_gout[8 * k + cd * lane + c] = vc;
                 }
             }
             // rot = q / max(|q|, eps): v_q -> (v - (v . qn) qn) / |q|
@@ -314,7 +322,6 @@ __global__ void __launch_bounds__(DWARPS * 32) decode_bwd_kernel(
             s_dpre[mm * DF + lane] = dp;
             if (dp != 0.f) {
                 float* dw = a_W1 + (mm * DF + lane) * DIN;
-#pragma unroll
                 for (int i = 0; i < DIN; ++i) atomicAdd(&dw[i], dp * s_x[i]);
                 atomicAdd(&a_b1[mm * DF + lane], dp);
             }
@@ -326,7 +333,7 @@ __global__ void __launch_bounds__(DWARPS * 32) decode_bwd_kernel(
             for (int j = 0; j < DF; ++j) {
                 const float dp = s_dpre[mm * DF + j];
                 dx += S.W1[(mm * DF + j) * DIN + lane] * dp;
-                if (lane < 3) dd += S.W1[(mm * DF + j) * DIN + DF + lane] * dp;
+                if (lane < D.vd) dd += S.W1[(mm * DF + j) * DIN + DF + lane] * dp;
             }
         }
         g_feat[a * DF + lane] = dx;
@@ -374,16 +381,24 @@ int decode_grid(long long V) {
 
 }  // namespace
 
+static bool bad_shape(int feat_dim, int k, int view_dim, int color_dim) {
+    return feat_dim != DF || k < 1 || k > DKMAX || (view_dim != 0 && view_dim != 3) || color_dim < 3 || color_dim > DCMAX ||
+           color_dim % 3 != 0;
+}
+
 HGS_API int hgs_decode_count(const float* const* mlp_host, const float* anchor, const float* feat, const float* cam_center,
-                             const long long* vis, long long V, int feat_dim, int k, float* opac_all, int32_t* bits,
-                             int32_t* cnt, void* stream) {
+                             const long long* vis, long long V, int feat_dim, int k, int view_dim, int color_dim,
+                             float* opac_all, int32_t* bits, int32_t* cnt, void* stream) {
     DecodeMlp P;
-    if (mlp_host == nullptr || fill_mlp(P, mlp_host) || feat_dim != DF || k < 1 || k > DKMAX || V < 0) return HGS_ERR_INVALID_ARG;
+    if (mlp_host == nullptr || fill_mlp(P, mlp_host) || bad_shape(feat_dim, k, view_dim, color_dim) || V < 0)
+        return HGS_ERR_INVALID_ARG;
     if (V == 0) return 0;
-    const int smem = (smem_w_floats(11 * k) + DWARPS * (3 * DF + DTOTMAX)) * (int)sizeof(float);
+    const DShape D{k, color_dim, view_dim};
+    const int smem = (smem_w_floats(D.tot(), D.din()) + DWARPS * (3 * DF + D.tot())) * (int)sizeof(float);
+    if (smem > DSMEM_MAX) return HGS_ERR_TOO_LARGE;
     cudaError_t e = cudaFuncSetAttribute(decode_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
-    decode_count_kernel<<<decode_grid(V), DWARPS * 32, smem, (cudaStream_t)stream>>>(P, anchor, feat, cam_center, vis, V, k,
+    decode_count_kernel<<<decode_grid(V), DWARPS * 32, smem, (cudaStream_t)stream>>>(P, anchor, feat, cam_center, vis, V, D,
                                                                                       opac_all, bits, cnt);
     HGS_LAUNCH_CHECK();
     return 0;
@@ -391,17 +406,21 @@ HGS_API int hgs_decode_count(const float* const* mlp_host, const float* anchor, 
 
 HGS_API int hgs_decode_fwd(const float* const* mlp_host, const float* anchor, const float* feat, const float* offset,
                            const float* scaling, const float* cam_center, const long long* vis, long long V, int feat_dim,
-                           int k, int color_sigmoid, const float* opac_all, const int32_t* bits, const long long* row0,
-                           float* xyz, float* color, float* opacity, float* scales, float* quats, void* stream) {
+                           int k, int view_dim, int color_dim, int color_sigmoid, const float* opac_all,
+                           const int32_t* bits, const long long* row0, float* xyz, float* color, float* opacity,
+                           float* scales, float* quats, void* stream) {
     DecodeMlp P;
-    if (mlp_host == nullptr || fill_mlp(P, mlp_host) || feat_dim != DF || k < 1 || k > DKMAX || V < 0) return HGS_ERR_INVALID_ARG;
+    if (mlp_host == nullptr || fill_mlp(P, mlp_host) || bad_shape(feat_dim, k, view_dim, color_dim) || V < 0)
+        return HGS_ERR_INVALID_ARG;
     if (V == 0) return 0;
     if (reinterpret_cast<size_t>(quats) & 15) return HGS_ERR_INVALID_ARG;
-    const int smem = (smem_w_floats(11 * k) + DWARPS * (3 * DF + DTOTMAX)) * (int)sizeof(float);
+    const DShape D{k, color_dim, view_dim};
+    const int smem = (smem_w_floats(D.tot(), D.din()) + DWARPS * (3 * DF + D.tot())) * (int)sizeof(float);
+    if (smem > DSMEM_MAX) return HGS_ERR_TOO_LARGE;
     cudaError_t e = cudaFuncSetAttribute(decode_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     decode_fwd_kernel<<<decode_grid(V), DWARPS * 32, smem, (cudaStream_t)stream>>>(
-        P, anchor, feat, offset, scaling, cam_center, vis, V, k, color_sigmoid, opac_all, bits, row0, xyz, color, opacity,
+        P, anchor, feat, offset, scaling, cam_center, vis, V, D, color_sigmoid, opac_all, bits, row0, xyz, color, opacity,
         scales, quats);
     HGS_LAUNCH_CHECK();
     return 0;
@@ -409,13 +428,13 @@ HGS_API int hgs_decode_fwd(const float* const* mlp_host, const float* anchor, co
 
 HGS_API int hgs_decode_bwd(const float* const* mlp_host, float* const* mlp_grad_host, const float* anchor, const float* feat,
                            const float* offset, const float* scaling, const float* cam_center, const long long* vis,
-                           long long V, int feat_dim, int k, int color_sigmoid, const float* opac_all, const int32_t* bits,
-                           const long long* row0, const float* v_xyz, const float* v_color, const float* v_opacity,
-                           const float* v_scales, const float* v_quats, float* g_anchor, float* g_feat, float* g_offset,
-                           float* g_scaling, void* stream) {
+                           long long V, int feat_dim, int k, int view_dim, int color_dim, int color_sigmoid,
+                           const float* opac_all, const int32_t* bits, const long long* row0, const float* v_xyz,
+                           const float* v_color, const float* v_opacity, const float* v_scales, const float* v_quats,
+                           float* g_anchor, float* g_feat, float* g_offset, float* g_scaling, void* stream) {
     DecodeMlp P;
-    if (mlp_host == nullptr || mlp_grad_host == nullptr || fill_mlp(P, mlp_host) || feat_dim != DF || k < 1 || k > DKMAX ||
-        V < 0)
+    if (mlp_host == nullptr || mlp_grad_host == nullptr || fill_mlp(P, mlp_host) ||
+        bad_shape(feat_dim, k, view_dim, color_dim) || V < 0)
         return HGS_ERR_INVALID_ARG;
     DecodeMlpGrad G;
     for (int m = 0; m < 3; ++m) {
@@ -425,13 +444,15 @@ HGS_API int hgs_decode_bwd(const float* const* mlp_host, float* const* mlp_grad_
     }
     if (V == 0) return 0;
     if (reinterpret_cast<size_t>(v_quats) & 15) return HGS_ERR_INVALID_ARG;
-    const int tot = 11 * k;
-    const int n_acc = 3 * DF * DIN + 3 * DF + tot * DF + tot;
-    const int smem = (smem_w_floats(tot) + n_acc + DWARPS * (3 * DF + 2 * DTOTMAX + DIN + 3 * DF + 8)) * (int)sizeof(float);
+    const DShape D{k, color_dim, view_dim};
+    const int tot = D.tot(), din = D.din();
+    const int n_acc = 3 * DF * din + 3 * DF + tot * DF + tot;
+    const int smem = (smem_w_floats(tot, din) + n_acc + DWARPS * (3 * DF + 2 * tot + DINMAX + 3 * DF + 8)) * (int)sizeof(float);
+    if (smem > DSMEM_MAX) return HGS_ERR_TOO_LARGE;
     cudaError_t e = cudaFuncSetAttribute(decode_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     decode_bwd_kernel<<<decode_grid(V), DWARPS * 32, smem, (cudaStream_t)stream>>>(
-        P, G, anchor, feat, offset, scaling, cam_center, vis, V, k, color_sigmoid, opac_all, bits, row0, v_xyz, v_color,
+        P, G, anchor, feat, offset, scaling, cam_center, vis, V, D, color_sigmoid, opac_all, bits, row0, v_xyz, v_color,
         v_opacity, v_scales, v_quats, g_anchor, g_feat, g_offset, g_scaling);
     HGS_LAUNCH_CHECK();
     return 0;

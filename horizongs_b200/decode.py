@@ -1,8 +1,9 @@
 """Fused anchor -> neural-Gaussian decode of the LOD model (csrc/decode.cu).
 
-``generate_neural_gaussians`` mirrors scene/basic_model.py:297-371 for the configuration Horizon-GS ships
-(view_dim 3, appearance_dim 0, colour_dim 3, feat_dim 32, n_offsets <= 16): three MLPs on cat(anchor_feat, unit view
-direction), the opacity > 0 mask, the compaction and the post-processing are three kernels (count / forward /
+``generate_neural_gaussians`` mirrors scene/basic_model.py:297-371 for the configurations Horizon-GS ships
+(feat_dim 32, appearance_dim 0, n_offsets <= 16; view_dim 3 with RGB colours, or view_dim 0 with SH colours of degree
+<= 3 -- color_attr 'RGB' / 'SH<d>', lod_model.py:58-61): three MLPs on cat(anchor_feat, unit view direction) (or on
+anchor_feat alone), the opacity > 0 mask, the compaction and the post-processing are three kernels (count / forward /
 backward) with the MLP weights in shared memory, and the kept Gaussians are written straight into the tensors
 ``rasterization()`` consumes.  Differentiable w.r.t. anchor, anchor_feat, offset, the (post-activation) grid scaling
 and all MLP parameters.  CUDA only (no fallback)."""
@@ -27,7 +28,7 @@ def _mlp_tensors(mlp: nn.Sequential):
 
 class _AnchorDecode(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, feat, offset, scaling, cam_center, vis, color_sigmoid, *mlp):
+    def forward(ctx, anchor, feat, offset, scaling, cam_center, vis, color_sigmoid, view_dim, color_dim, *mlp):
         L = _lib.lib()
         dev = anchor.device
         V, k, F = int(vis.numel()), int(offset.shape[1]), int(feat.shape[1])
@@ -37,36 +38,36 @@ class _AnchorDecode(torch.autograd.Function):
         opac_all = torch.empty((V, k), dtype=torch.float32, device=dev)
         bits = torch.empty(V, dtype=torch.int32, device=dev)
         cnt = torch.empty(V, dtype=torch.int32, device=dev)
-        check(L.hgs_decode_count(mp, ptr(anchor), ptr(feat), ptr(cam_center), ptr(vis), V, F, k, ptr(opac_all), ptr(bits),
-                                 ptr(cnt), st), "hgs_decode_count")
+        check(L.hgs_decode_count(mp, ptr(anchor), ptr(feat), ptr(cam_center), ptr(vis), V, F, k, view_dim, color_dim,
+                                 ptr(opac_all), ptr(bits), ptr(cnt), st), "hgs_decode_count")
         incl = torch.cumsum(cnt, 0, dtype=torch.int64)
         row0 = (incl - cnt).contiguous()
         M = int(incl[-1].item()) if V > 0 else 0            # the one host read (the reference's boolean gather has one too)
         xyz = torch.empty((M, 3), dtype=torch.float32, device=dev)
-        color = torch.empty((M, 3), dtype=torch.float32, device=dev)
+        color = torch.empty((M, color_dim), dtype=torch.float32, device=dev)
         opacity = torch.empty((M,), dtype=torch.float32, device=dev)
         scales = torch.empty((M, 3), dtype=torch.float32, device=dev)
         quats = torch.empty((M, 4), dtype=torch.float32, device=dev)
         check(L.hgs_decode_fwd(mp, ptr(anchor), ptr(feat), ptr(offset), ptr(scaling), ptr(cam_center), ptr(vis), V, F, k,
-                               int(color_sigmoid), ptr(opac_all), ptr(bits), ptr(row0), ptr(xyz), ptr(color), ptr(opacity),
+                               view_dim, color_dim, int(color_sigmoid), ptr(opac_all), ptr(bits), ptr(row0), ptr(xyz), ptr(color), ptr(opacity),
                                ptr(scales), ptr(quats), st), "hgs_decode_fwd")
         mask = ((bits[:, None] >> torch.arange(k, device=dev, dtype=torch.int32)[None]) & 1).bool().reshape(-1)
         ctx.save_for_backward(anchor, feat, offset, scaling, cam_center, vis, opac_all, bits, row0, *mlp)
-        ctx.cfg = (V, k, F, int(color_sigmoid))
+        ctx.cfg = (V, k, F, int(color_sigmoid), view_dim, color_dim)
         ctx.mark_non_differentiable(mask)
         return xyz, color, opacity, scales, quats, mask
 
     @staticmethod
     def backward(ctx, v_xyz, v_color, v_opacity, v_scales, v_quats, _v_mask):
         anchor, feat, offset, scaling, cam_center, vis, opac_all, bits, row0, *mlp = ctx.saved_tensors
-        V, k, F, color_sigmoid = ctx.cfg
+        V, k, F, color_sigmoid, view_dim, color_dim = ctx.cfg
         L = _lib.lib()
         dev = anchor.device
         rows = next((t.shape[0] for t in (v_xyz, v_color, v_opacity, v_scales, v_quats) if t is not None), 0)
 
         def dense(t, shape):
             return torch.zeros(shape, dtype=torch.float32, device=dev) if t is None else t.contiguous()
-        v_xyz, v_color = dense(v_xyz, (rows, 3)), dense(v_color, (rows, 3))
+        v_xyz, v_color = dense(v_xyz, (rows, 3)), dense(v_color, (rows, color_dim))
         v_opacity, v_scales, v_quats = dense(v_opacity, (rows,)), dense(v_scales, (rows, 3)), dense(v_quats, (rows, 4))
         g_anchor, g_feat = torch.zeros_like(anchor), torch.zeros_like(feat)
         g_offset, g_scaling = torch.zeros_like(offset), torch.zeros_like(scaling)
@@ -74,17 +75,17 @@ class _AnchorDecode(torch.autograd.Function):
         mp = (C.c_void_p * 12)(*[t.data_ptr() for t in mlp])
         gp = (C.c_void_p * 12)(*[t.data_ptr() for t in g_mlp])
         check(L.hgs_decode_bwd(mp, gp, ptr(anchor), ptr(feat), ptr(offset), ptr(scaling), ptr(cam_center), ptr(vis), V, F, k,
-                               color_sigmoid, ptr(opac_all), ptr(bits), ptr(row0), ptr(v_xyz), ptr(v_color), ptr(v_opacity),
+                               view_dim, color_dim, color_sigmoid, ptr(opac_all), ptr(bits), ptr(row0), ptr(v_xyz), ptr(v_color), ptr(v_opacity),
                                ptr(v_scales), ptr(v_quats), ptr(g_anchor), ptr(g_feat), ptr(g_offset), ptr(g_scaling),
                                torch.cuda.current_stream().cuda_stream), "hgs_decode_bwd")
-        return (g_anchor, g_feat, g_offset, g_scaling, None, None, None, *g_mlp)
+        return (g_anchor, g_feat, g_offset, g_scaling, None, None, None, None, None, *g_mlp)
 
 
 def generate_neural_gaussians(anchor: Tensor, anchor_feat: Tensor, offset: Tensor, scaling: Tensor, cam_center: Tensor,
                               visible_mask: Tensor, mlp_opacity: nn.Sequential, mlp_cov: nn.Sequential,
                               mlp_color: nn.Sequential, dist2level: str = "floor"
                               ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
-    """-> (xyz [M,3], color [M,3], opacity [M,1], scaling [M,3], rot [M,4], mask [V*k] bool), the tensors
+    """-> (xyz [M,3], color [M,3] (RGB) or [M,K,3] (SH), opacity [M,1], scaling [M,3], rot [M,4], mask [V*k] bool), the tensors
     scene/basic_model.py:297-371 returns (without the pass-through `offsets` / `active_sh_degree`).
 
     anchor [A,3], anchor_feat [A,32], offset [A,k,3], scaling [A,6] POST-activation (get_scaling = exp(_scaling),
@@ -105,13 +106,19 @@ def generate_neural_gaussians(anchor: Tensor, anchor_feat: Tensor, offset: Tenso
     if not isinstance(last(mlp_opacity), nn.Tanh):
         raise NotImplementedError("the opacity MLP must end in Tanh (scene/lod_model.py:67-72)")
     mlp = _mlp_tensors(mlp_opacity) + _mlp_tensors(mlp_cov) + _mlp_tensors(mlp_color)
-    if mlp[0].shape != (32, 35) or mlp[2].shape != (k, 32) or mlp[6].shape != (7 * k, 32) or mlp[10].shape != (3 * k, 32):
-        raise NotImplementedError("supported: view_dim 3, appearance_dim 0, colour_dim 3, feat_dim 32")
+    view_dim = mlp[0].shape[1] - 32
+    color_dim = mlp[10].shape[0] // k
+    if (view_dim not in (0, 3) or any(mlp[i].shape != (32, 32 + view_dim) for i in (0, 4, 8)) or mlp[2].shape != (k, 32)
+            or mlp[6].shape != (7 * k, 32) or mlp[10].shape != (color_dim * k, 32) or color_dim % 3 or not 3 <= color_dim <= 48):
+        raise NotImplementedError("supported: feat_dim 32, view_dim 3 or 0, appearance_dim 0, colour_dim 3 (RGB) or "
+                                  "3 (d + 1)^2 (SH degree d <= 3)")
     color_sigmoid = isinstance(last(mlp_color), nn.Sigmoid)
     vis = torch.nonzero(visible_mask).flatten().contiguous()                      # int64 work list (one host read)
     xyz, color, opacity, scales, quats, mask = _AnchorDecode.apply(
         anchor.contiguous(), anchor_feat.contiguous(), offset.contiguous(), scaling.contiguous(),
-        cam_center.detach().to(torch.float32).contiguous(), vis, color_sigmoid, *mlp)
+        cam_center.detach().to(torch.float32).contiguous(), vis, color_sigmoid, int(view_dim), int(color_dim), *mlp)
+    if color_dim != 3:
+        color = color.reshape(color.shape[0], color_dim // 3, 3)      # SH coefficients [M,K,3], basic_model.py:368-369
     return xyz, color, opacity[:, None], scales, quats, mask
 
 

@@ -304,26 +304,29 @@ int hgs_ssim_bwd(const float* render_colors, const float* gt, const float* dmaps
                  int W, int D, float* v_render_colors, void* stream);
 
 /* ---- f1 (next row of SURVEY.md section 8): fused anchor -> neural-Gaussian decode -------------------------------
- * scene/basic_model.py:297-371 generate_neural_gaussians for view_dim 3, appearance_dim 0, colour_dim 3,
- * feat_dim 32, n_offsets k <= 16: three MLPs Linear(35, 32) -> ReLU -> Linear(32, {k, 7k, 3k}) (scene/lod_model.py:
- * 67-84; Tanh on the opacity, optional Sigmoid on the colour) on cat(anchor_feat, unit(anchor - cam_center)).
- * mlp_host: HOST array of 12 device pointers {W1[32,35], b1[32], W2[out,32], b2[out]} x {opacity, cov, colour}.
+ * scene/basic_model.py:297-371 generate_neural_gaussians for view_dim 3 or 0, appearance_dim 0, feat_dim 32,
+ * n_offsets k <= 16, color_dim = 3 (color_attr 'RGB') or 3 (d + 1)^2 <= 48 (color_attr 'SH<d>', lod_model.py:58-61):
+ * three MLPs Linear(32 + view_dim, 32) -> ReLU -> Linear(32, {k, 7k, color_dim k}) (scene/lod_model.py:67-84; Tanh on
+ * the opacity, optional Sigmoid on the colour) on cat(anchor_feat, unit(anchor - cam_center)) -- or on anchor_feat
+ * alone when view_dim == 0 (basic_model.py:313-316).  HGS_ERR_TOO_LARGE when the weights do not fit shared memory.
+ * mlp_host: HOST array of 12 device pointers {W1[32,32+view_dim], b1[32], W2[out,32], b2[out]} x {opacity, cov, colour}.
  * vis[V] (int64): indices of the visible anchors.  count: opac_all[V,k] = tanh(opacity MLP), bits[V] = mask of the
  * offsets with opacity > 0, cnt[V] = their number.  fwd: row0[V] (int64) = exclusive scan of cnt; writes the kept
- * Gaussians at rows row0[v] + rank: xyz[M,3], color[M,3], opacity[M], scales[M,3], quats[M,4] (the rasterizer's
- * inputs).  bwd: gradients of those five tensors -> g_anchor[A,3], g_feat[A,32], g_offset[A,k,3], g_scaling[A,6]
+ * Gaussians at rows row0[v] + rank: xyz[M,3], color[M,color_dim], opacity[M], scales[M,3], quats[M,4] (the rasterizer's
+ * inputs; color is [M, color_dim]).  bwd: gradients of those five tensors -> g_anchor[A,3], g_feat[A,32], g_offset[A,k,3], g_scaling[A,6]
  * (rows of visible anchors with a kept offset are OVERWRITTEN; zero-fill first) and += into mlp_grad_host (12
  * device pointers, same shapes as mlp_host). */
 int hgs_decode_count(const float* const* mlp_host, const float* anchor, const float* feat, const float* cam_center,
-                     const long long* vis, long long V, int feat_dim, int k, float* opac_all, int32_t* bits,
-                     int32_t* cnt, void* stream);
+                     const long long* vis, long long V, int feat_dim, int k, int view_dim, int color_dim,
+                     float* opac_all, int32_t* bits, int32_t* cnt, void* stream);
 int hgs_decode_fwd(const float* const* mlp_host, const float* anchor, const float* feat, const float* offset,
                    const float* scaling, const float* cam_center, const long long* vis, long long V, int feat_dim,
-                   int k, int color_sigmoid, const float* opac_all, const int32_t* bits, const long long* row0,
+                   int k, int view_dim, int color_dim, int color_sigmoid, const float* opac_all, const int32_t* bits, const long long* row0,
                    float* xyz, float* color, float* opacity, float* scales, float* quats, void* stream);
 int hgs_decode_bwd(const float* const* mlp_host, float* const* mlp_grad_host, const float* anchor, const float* feat,
                    const float* offset, const float* scaling, const float* cam_center, const long long* vis,
-                   long long V, int feat_dim, int k, int color_sigmoid, const float* opac_all, const int32_t* bits,
+                   long long V, int feat_dim, int k, int view_dim, int color_dim, int color_sigmoid,
+                   const float* opac_all, const int32_t* bits,
                    const long long* row0, const float* v_xyz, const float* v_color, const float* v_opacity,
                    const float* v_scales, const float* v_quats, float* g_anchor, float* g_feat, float* g_offset,
                    float* g_scaling, void* stream);

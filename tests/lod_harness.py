@@ -13,8 +13,9 @@ import torch.nn as nn
 
 class TinyAnchorModel(nn.Module):
     def __init__(self, n_anchors=600, n_offsets=10, feat_dim=32, levels=3, extent=3.0, seed=0, voxel0=0.4,
-                 standard_dist=8.0):
+                 standard_dist=8.0, view_dim=3, color_dim=3):
         super().__init__()
+        self.view_dim, self.color_dim = view_dim, color_dim      # color_attr 'RGB' (3) or 'SH<d>' (3 (d+1)^2), lod_model.py:58-61
         g = torch.Generator().manual_seed(seed)
         self.n_offsets, self.levels = n_offsets, levels
         self.standard_dist, self.fork = standard_dist, 2
@@ -30,10 +31,11 @@ class TinyAnchorModel(nn.Module):
         rot[:, 0] = 1.0
         self.rotation = rot                                                   # identity wxyz (lod_model.py:269-270)
         torch.manual_seed(seed)
-        mlp = lambda out: nn.Sequential(nn.Linear(feat_dim + 3, feat_dim), nn.ReLU(True), nn.Linear(feat_dim, out))  # noqa: E731
+        mlp = lambda out: nn.Sequential(nn.Linear(feat_dim + view_dim, feat_dim), nn.ReLU(True), nn.Linear(feat_dim, out))  # noqa: E731
         self.mlp_opacity = nn.Sequential(mlp(n_offsets), nn.Tanh())
         self.mlp_cov = mlp(7 * n_offsets)
-        self.mlp_color = nn.Sequential(mlp(3 * n_offsets), nn.Sigmoid())
+        # scene/lod_model.py:80-84 has no activation on the colour MLP; the Sigmoid variant is kept for the RGB harness
+        self.mlp_color = nn.Sequential(mlp(3 * n_offsets), nn.Sigmoid()) if color_dim == 3 else mlp(color_dim * n_offsets)
 
     def anchor_mask(self, cam_center):
         """scene/lod_model.py:286-290 + basic_model.py:192-210: level <= int level of the view distance"""
@@ -50,18 +52,20 @@ class TinyAnchorModel(nn.Module):
         scaling = torch.exp(self.scaling[visible_mask])
         view = anchor - cam_center
         view = view / view.norm(dim=1, keepdim=True)
-        x = torch.cat([feat, view], 1)
-        k = self.n_offsets
+        x = torch.cat([feat, view], 1) if self.view_dim > 0 else feat                # basic_model.py:313-316
+        k, cd = self.n_offsets, self.color_dim
         opacity = self.mlp_opacity(x).reshape(-1, 1)
         mask = (opacity > 0).view(-1)
-        color = self.mlp_color(x).reshape(-1, 3)
+        color = self.mlp_color(x).reshape(-1, cd)
         scale_rot = self.mlp_cov(x).reshape(-1, 7)
         rep = torch.cat([scaling, anchor], -1).repeat_interleave(k, 0)
         allv = torch.cat([rep, color, scale_rot, offsets.reshape(-1, 3)], -1)[mask]
-        s_rep, a_rep, color, scale_rot, off = allv.split([6, 3, 3, 7, 3], -1)
+        s_rep, a_rep, color, scale_rot, off = allv.split([6, 3, cd, 7, 3], -1)
         scales = s_rep[:, 3:] * torch.sigmoid(scale_rot[:, :3])
         quats = torch.nn.functional.normalize(scale_rot[:, 3:7])
         xyz = a_rep + off * s_rep[:, :3]
+        if cd != 3:
+            color = color.reshape(color.shape[0], cd // 3, 3)                       # basic_model.py:368-369
         return xyz, color, opacity[mask], scales, quats
 
 
@@ -102,9 +106,12 @@ def render(model, viewmat, K, width, height, bg, backend, two_d=False, fused_dec
             model.mlp_opacity, model.mlp_cov, model.mlp_color)
     else:
         xyz, color, opacity, scaling, rot = model.decode(cam_center, visible)
+    # active_sh_degree: None for color_attr 'RGB', else the degree of the SH colours (basic_model.py:371; the harness
+    # uses the full degree)
+    sh_degree = None if model.color_dim == 3 else math.isqrt(model.color_dim // 3) - 1
     kw = dict(means=xyz, quats=rot, scales=scaling, opacities=opacity.squeeze(-1), colors=color,
               viewmats=viewmat[None], Ks=K[None], backgrounds=bg[None], width=int(width), height=int(height),
-              packed=False, sh_degree=None, render_mode="RGB+ED")
+              packed=False, sh_degree=sh_degree, render_mode="RGB+ED")
     if two_d:
         (rc, ra, rn, rnd, rd, rm), info = backend.rasterization_2dgs(**kw)
     else:

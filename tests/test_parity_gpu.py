@@ -426,8 +426,9 @@ def test_blend2d_stage(D, distloss):
 
 
 # ------------------------------------------------------------------------------------ configs[3]: LOD anchor model
-@pytest.mark.parametrize("two_d,fused", [(False, False), (True, False), (False, True)])
-def test_lod_anchor_model_render_through_adapter_control_flow(two_d, fused):
+@pytest.mark.parametrize("two_d,fused,sh", [(False, False, False), (True, False, False), (False, True, False),
+                                            (False, True, True), (True, False, True)])
+def test_lod_anchor_model_render_through_adapter_control_flow(two_d, fused, sh):
     """BASELINE.json configs[3] in miniature: anchor LOD mask -> prefilter (fully_fused_projection[_2dgs]) ->
     MLP decode in PyTorch -> rasterization[_2dgs], forward + backward to anchors / offsets / features / MLPs,
     CUDA operators against the oracle under the same adapter code (tests/lod_harness.py).  fused: the GPU side
@@ -440,7 +441,9 @@ def test_lod_anchor_model_render_through_adapter_control_flow(two_d, fused):
     V = scenes.look_at((0.0, -5.5, 3.0), (0.0, 0.0, 0.2))
     Km = scenes.intrinsics(Wd, H, 65.0)
     bg = torch.tensor([0.1, 0.2, 0.3])
-    ref_model = LH.TinyAnchorModel()
+    # sh: the other shipped model shape -- SH2 colours from the colour MLP, no view direction input
+    # (scene/basic_model.py:313-316,368-369; config/*: color_attr SH2, view_dim 0)
+    ref_model = LH.TinyAnchorModel(view_dim=0, color_dim=27) if sh else LH.TinyAnchorModel()
     gpu_model = copy.deepcopy(ref_model).cuda()
     w = _rand_like(torch.empty(3, H, Wd), 41)
     outs = []
@@ -514,17 +517,19 @@ def test_fused_l1_ssim_loss_matches_reference_golden(case):
 
 
 # ------------------------------------------------------------------------------------ f1: fused anchor decode
-@pytest.mark.parametrize("color_sigmoid", [True, False])
-def test_fused_anchor_decode_matches_pytorch_decode(color_sigmoid):
+@pytest.mark.parametrize("color_sigmoid,view_dim,color_dim", [(True, 3, 3), (False, 3, 3), (False, 0, 27), (False, 3, 12),
+                                                               (False, 0, 3)])
+def test_fused_anchor_decode_matches_pytorch_decode(color_sigmoid, view_dim, color_dim):
     """csrc/decode.cu against the PyTorch statement of scene/basic_model.py:297-371 (tests/lod_harness.py decode):
     same rows in the same order, and the same gradients w.r.t. anchors, offsets, features, scaling and all MLP
-    parameters."""
+    parameters -- for the shipped model shapes: view_dim 3 + RGB colours, and view_dim 0 + SH colours
+    (basic_model.py:313-316,368-369; 27 = SH2, 12 = SH1 coefficients x 3 channels per offset)."""
     import copy
     import torch.nn as nn
     from tests import lod_harness as LH
     from horizongs_b200 import decode as DEC
-    ref = LH.TinyAnchorModel(n_anchors=3000, seed=3)
-    if not color_sigmoid:
+    ref = LH.TinyAnchorModel(n_anchors=3000, seed=3, view_dim=view_dim, color_dim=color_dim)
+    if not color_sigmoid and color_dim == 3:
         ref.mlp_color = nn.Sequential(*list(ref.mlp_color)[:-1])          # scene/lod_model.py:80-84: no activation
     ref = ref.cuda()
     ref.level = ref.level.cuda()
