@@ -34,7 +34,8 @@ SIGNATURES = {
     "hgs_exclusive_scan_i32": (_i, [_p, _p, _p, _ll, _p, _sz, _p]),
     "hgs_isect_emit": (_i, [_p] * 4 + [_i] * 5 + [_p, _p, _p]),
     "hgs_isect_bin_prepare": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
-    "hgs_project3d_fwd_bin": (_i, [_p] * 5 + [_i] * 4 + [_f] * 4 + [_i] + [_p] * 9 + [_sz, _p]),
+    "hgs_project3d_fwd_bin": (_i, [_p] * 5 + [_i] * 4 + [_f] * 4 + [_i] + [_p] * 9 + [_sz] +
+                              [_i, _p, _i, _p, _p, _i, _p, _p] + [_p]),
     "hgs_isect_bin_scan": (_i, [_i, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "hgs_isect_bin_sorted": (_i, [_p, _i, _i, _ll, _ll, _ll, _i, _i, _i] + [_p] * 4 + [_sz, _p, _sz, _p]),
     "hgs_isect_offset_encode": (_i, [_p, _ll, _i, _i, _i, _p, _p]),

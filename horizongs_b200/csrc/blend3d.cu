@@ -33,21 +33,11 @@ constexpr int BLK = TS * TS;  // 256 threads
 // =====================================================================================================
 // packed per-Gaussian record
 // =====================================================================================================
-constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
-constexpr int REC_BYTES = 64;    // global record
 constexpr int SLOT_BYTES = 80;   // shared-memory slot (stride 80 B: lane-parallel float4 reads are conflict-free)
 constexpr int FB = 128;          // forward batch size (Gaussians staged per mbarrier phase)
 constexpr int FB_BWD = 96;       // backward batch size: 4 CTAs/SM fit in shared memory (50 KB each)
 constexpr float CULL_MARGIN = 0.02f;  // in log2 units; conservative (float error of the bound is ~1e-5)
-
-struct __align__(16) GRec {
-    float x, y, A, B;          // q0
-    float C, opac, p2min, _p;  // q1
-    float col[4];              // q2
-    float kx, ky, _p2, _p3;    // q3
-};
-static_assert(sizeof(GRec) == REC_BYTES, "record size");
 
 __global__ void pack3d_kernel(const float* __restrict__ means2d, const float* __restrict__ conics,
                               const float* __restrict__ colors, const float* __restrict__ depths,
@@ -63,20 +53,10 @@ __global__ void pack3d_kernel(const float* __restrict__ means2d, const float* __
     const float2 m = reinterpret_cast<const float2*>(means2d)[i];
     const float a = conics[i * 3 + 0], b = conics[i * 3 + 1], c = conics[i * 3 + 2];
     const float o = opacities[i];
-    GRec r;
-    r.x = m.x; r.y = m.y;
-    r.A = -0.5f * LOG2E * a;
-    r.B = -LOG2E * b;
-    r.C = -0.5f * LOG2E * c;
-    r.opac = o;
-    // contributes iff o * 2^p2 >= 1/255  <=>  p2 >= -log2(255 o); o <= 0 never contributes
-    r.p2min = (o > 0.f) ? -log2f(255.0f * o) : 1.0f;
-    r._p = 0.f;
+    float col[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) r.col[k] = (k < CH) ? colors[i * CH + k] : ((k == CH && depths != nullptr) ? depths[i] : 0.f);
-    r.kx = (r.C != 0.f) ? -r.B / (2.f * r.C) : 0.f;
-    r.ky = (r.A != 0.f) ? -r.B / (2.f * r.A) : 0.f;
-    r._p2 = 0.f; r._p3 = 0.f;
+    for (int k = 0; k < 4; ++k) col[k] = (k < CH) ? colors[i * CH + k] : ((k == CH && depths != nullptr) ? depths[i] : 0.f);
+    const GRec r = make_grec(m.x, m.y, a, b, c, o, col);
     float4* dst = reinterpret_cast<float4*>(recs + i);
     const float4* src = reinterpret_cast<const float4*>(&r);
 #pragma unroll

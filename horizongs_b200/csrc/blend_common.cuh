@@ -116,6 +116,37 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 
+// ---- packed per-Gaussian record of the fast 3DGS blend kernels -------------------------------------------
+// centre, conic pre-multiplied by -log2(e)/2 so that alpha = o * 2^(A dx^2 + B dx dy + C dy^2) is one MUFU.EX2,
+// opacity, cut-off exponent, colour (+ depth), edge-optimum slopes of the per-warp cull test.  Written by
+// hgs_blend3d_pack, or directly by the fused projection kernel (project3d.cu).
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr int REC_BYTES = 64;
+struct __align__(16) GRec {
+    float x, y, A, B;          // q0
+    float C, opac, p2min, _p;  // q1
+    float col[4];              // q2
+    float kx, ky, _p2, _p3;    // q3
+};
+static_assert(sizeof(GRec) == REC_BYTES, "record size");
+__device__ __forceinline__ GRec make_grec(float mx, float my, float a, float b, float c, float o, const float (&col)[4]) {
+    GRec r;
+    r.x = mx; r.y = my;
+    r.A = -0.5f * LOG2E * a;
+    r.B = -LOG2E * b;
+    r.C = -0.5f * LOG2E * c;
+    r.opac = o;
+    // contributes iff o * 2^p2 >= 1/255  <=>  p2 >= -log2(255 o); o <= 0 never contributes
+    r.p2min = (o > 0.f) ? -log2f(255.0f * o) : 1.0f;
+    r._p = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r.col[k] = col[k];
+    r.kx = (r.C != 0.f) ? -r.B / (2.f * r.C) : 0.f;
+    r.ky = (r.A != 0.f) ? -r.B / (2.f * r.A) : 0.f;
+    r._p2 = 0.f; r._p3 = 0.f;
+    return r;
+}
+
 // ---- tile / sub-tile geometry of the fast blend kernels ----------------------------------------------
 // One CTA of 256 threads per 16x16 tile; warp w owns the 8x4 pixel sub-tile ((w & 1) * 8, (w >> 1) * 4).
 struct TileGeom {

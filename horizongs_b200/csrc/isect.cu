@@ -402,10 +402,12 @@ __device__ __forceinline__ unsigned long long make_key(const VisRec& r, int sx, 
 
 __global__ void __launch_bounds__(RS_THREADS) bin_scatter_kernel(
     const VisRec* __restrict__ vrec, const long long* __restrict__ counts_dev, BinGeom G,
-    const int32_t* __restrict__ soff, uint32_t* __restrict__ cursor, unsigned long long* __restrict__ bucket) {
+    const int32_t* __restrict__ soff, uint32_t* __restrict__ cursor, unsigned long long* __restrict__ bucket,
+    long long cap_isects, long long cap_super) {
     __shared__ uint32_t s_nbig;
     __shared__ uint32_t s_big[RS_THREADS];
     const long long n_vis = counts_dev[0];
+    if (counts_dev[1] > cap_isects || counts_dev[2] > cap_super) return;   // outputs too small: the caller re-runs
     if ((long long)blockIdx.x * RS_THREADS >= n_vis) return;
     if (threadIdx.x == 0) s_nbig = 0;
     __syncthreads();
@@ -703,7 +705,8 @@ __device__ void sort_big(unsigned long long* bucket, int n, unsigned long long* 
 // the keys of each of its tiles (= the tile histogram) from the masks the keys carry.
 __global__ void __launch_bounds__(RS_THREADS) super_sort_kernel(
     BinGeom G, int total_super, const int32_t* __restrict__ soff, const long long* __restrict__ counts_dev,
-    unsigned long long* bucket, uint32_t* __restrict__ tile_count) {
+    unsigned long long* bucket, uint32_t* __restrict__ tile_count, long long cap_isects, long long cap_super) {
+    if (counts_dev[1] > cap_isects || counts_dev[2] > cap_super) return;
     __shared__ __align__(16) unsigned long long s_buf[SORT_CHUNK];
     __shared__ uint32_t s_k32[SORT_CHUNK];
     __shared__ uint32_t s_red[2 * RS_WARPS];
@@ -772,7 +775,9 @@ __device__ __forceinline__ long long block_sum_u32(const uint32_t* __restrict__ 
 __global__ void __launch_bounds__(RS_THREADS) super_expand_kernel(
     BinGeom G, int total_super, int tile_bits, const int32_t* __restrict__ soff, const long long* __restrict__ counts_dev,
     const unsigned long long* __restrict__ bucket, const uint32_t* __restrict__ tile_count,
-    int32_t* __restrict__ offsets, long long* __restrict__ isect_ids, int32_t* __restrict__ flatten_ids) {
+    int32_t* __restrict__ offsets, long long* __restrict__ isect_ids, int32_t* __restrict__ flatten_ids,
+    long long cap_isects, long long cap_super) {
+    if (counts_dev[1] > cap_isects || counts_dev[2] > cap_super) return;
     constexpr int CH = 1024;
     __shared__ __align__(16) unsigned long long s_key[CH];
     __shared__ long long s_red[RS_WARPS];
@@ -962,13 +967,19 @@ HGS_API int hgs_isect_bin_sorted(const long long* counts_dev, int C, int N,
     if (temp_bytes < T.bytes) return HGS_ERR_WORKSPACE;
     if (bucket_bytes < hgs_isect_bin_bucket_bytes(n_super_isects)) return HGS_ERR_WORKSPACE;
     unsigned long long* keys = (unsigned long long*)bucket;
-    bin_scatter_kernel<<<hgs_ceil_div(n_visible_bound, RS_THREADS), RS_THREADS, 0, st>>>(T.vrec, counts_dev, G, T.soff,
-                                                                                         T.cursor, keys);
+    // n_isects / n_super_isects are CAPACITIES of the outputs / the bucket (>= the exact counts when the caller has read
+    // them; a guess when it has not): every kernel returns at once when counts_dev says they do not fit, leaving temp
+    // untouched, and the caller -- who reads counts_dev afterwards -- calls again with larger buffers
+    const long long cap_super = (long long)(bucket_bytes / sizeof(unsigned long long));
+    bin_scatter_kernel<<<hgs_ceil_div(n_visible_bound, RS_THREADS), RS_THREADS, 0, st>>>(
+        T.vrec, counts_dev, G, T.soff, T.cursor, keys, n_isects, cap_super);
     HGS_LAUNCH_CHECK();
-    super_sort_kernel<<<total_super, RS_THREADS, 0, st>>>(G, total_super, T.soff, counts_dev, keys, T.tile_count);
+    super_sort_kernel<<<total_super, RS_THREADS, 0, st>>>(G, total_super, T.soff, counts_dev, keys, T.tile_count, n_isects,
+                                                          cap_super);
     HGS_LAUNCH_CHECK();
     super_expand_kernel<<<total_super, RS_THREADS, 0, st>>>(G, total_super, n_bits_of(n_tiles), T.soff, counts_dev, keys,
-                                                            T.tile_count, isect_offsets, isect_ids, flatten_ids);
+                                                            T.tile_count, isect_offsets, isect_ids, flatten_ids, n_isects,
+                                                            cap_super);
     HGS_LAUNCH_CHECK();
     return 0;
 }

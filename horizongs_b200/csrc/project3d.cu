@@ -12,6 +12,8 @@
 #include "hgs_constants.cuh"
 #include "project3d_math.cuh"
 #include "bin_common.cuh"
+#include "sh_math.cuh"
+#include "blend_common.cuh"
 
 namespace {
 
@@ -39,13 +41,27 @@ struct BinArgs {
     long long* counts_dev;
 };
 
-template <bool BIN>
+//   (SHADE) shading, fused (what hgs_sh_fwd + hgs_blend3d_pack do from the arrays this kernel writes): in phase 2 a
+//      visible Gaussian also evaluates its view-dependent colour (SHADE = SH degree 0..4; -1: colours given) and
+//      writes its 64-byte blend record -- centre, conic, depth are still in registers, so the five 64-byte-granule
+//      gathers of the pack kernel and the second read of the centre disappear.
+struct ShadeArgs {
+    const float* feats;       // SH coefficients [N,K,3] (SHADE >= 0) or colours [N,3] (SHADE == -1)
+    const float* opacities;   // [N]
+    const float* campos;      // [C,3]
+    int K, depth_channel;
+    float* colors;            // [C,N,3] out (SHADE >= 0): the clamped SH colour, visible rows only
+    hgs::GRec* recs;          // [C*N] out
+};
+constexpr int SHADE_NONE = -2, SHADE_RGB = -1;
+
+template <bool BIN, int SHADE>
 __global__ void __launch_bounds__(PB, 6) project3d_fwd_kernel(
     const float* __restrict__ means, const float* __restrict__ quats, const float* __restrict__ scales,
     const float* __restrict__ viewmats, const float* __restrict__ Ks, int N, int nblk_cam, int W, int H, float eps2d,
     float near_plane, float far_plane, float radius_clip, int tile_size, int tile_w, int tile_h,
     int32_t* __restrict__ radii, float* __restrict__ means2d, float* __restrict__ depths, float* __restrict__ conics,
-    float* __restrict__ compensations, int32_t* __restrict__ tiles_per_gauss, BinArgs B) {
+    float* __restrict__ compensations, int32_t* __restrict__ tiles_per_gauss, BinArgs B, ShadeArgs S) {
     __shared__ unsigned short s_list[CH];      // local rows of the phase-1 survivors, ascending
     __shared__ int s_seg[PER * (PB / 32) + 1];
     __shared__ float s_cam[26];                // viewmat (16), K (9), bound coefficient
@@ -217,6 +233,24 @@ __global__ void __launch_bounds__(PB, 6) project3d_fwd_kernel(
                 conics[idx * 3 + 2] = f.c00 * inv_det;
                 if (compensations != nullptr) compensations[idx] = sqrtf(fmaxf(f.det_orig / f.det, 0.f));
                 if (tiles_per_gauss != nullptr) tiles_per_gauss[idx] = ntiles;
+                if (SHADE != SHADE_NONE) {
+                    float col[4];
+                    if (SHADE == SHADE_RGB) {
+                        col[0] = S.feats[n * 3]; col[1] = S.feats[n * 3 + 1]; col[2] = S.feats[n * 3 + 2];
+                    } else {
+                        constexpr int DEG = SHADE < 0 ? 0 : SHADE;
+                        sh_eval_one<DEG>(px - S.campos[c * 3], py - S.campos[c * 3 + 1], pz - S.campos[c * 3 + 2],
+                                         S.feats + n * (long long)(S.K * 3), 1, col[0], col[1], col[2]);
+                        S.colors[idx * 3] = col[0]; S.colors[idx * 3 + 1] = col[1]; S.colors[idx * 3 + 2] = col[2];
+                    }
+                    col[3] = S.depth_channel ? f.zc : 0.f;
+                    const hgs::GRec gr = hgs::make_grec(f.m2x, f.m2y, f.c11 * inv_det, -f.c01 * inv_det, f.c00 * inv_det,
+                                              S.opacities[n], col);
+                    float4* dst = reinterpret_cast<float4*>(S.recs + idx);
+                    const float4* src = reinterpret_cast<const float4*>(&gr);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) dst[k] = src[k];
+                }
                 if (BIN && ntiles > 0) {
                     rec = make_uint4((uint32_t)idx, __float_as_uint(f.zc), (uint32_t)x0 | ((uint32_t)y0 << 16),
                                      (uint32_t)x1 | ((uint32_t)y1 << 16));
@@ -454,23 +488,31 @@ HGS_API int hgs_project3d_fwd(const float* means, const float* quats, const floa
     const int tile_w = (width + tile_size - 1) / tile_size, tile_h = (height + tile_size - 1) / tile_size;
     const int nblk_cam = hgs_ceil_div(N, CH);
     dim3 grid(nblk_cam, C);
-    project3d_fwd_kernel<false><<<grid, PB, 0, (cudaStream_t)stream>>>(
+    project3d_fwd_kernel<false, SHADE_NONE><<<grid, PB, 0, (cudaStream_t)stream>>>(
         means, quats, scales, viewmats, Ks, N, nblk_cam, width, height, eps2d, near_plane, far_plane, radius_clip, tile_size,
-        tile_w, tile_h, radii, means2d, depths, conics, compensations, tiles_per_gauss, BinArgs{});
+        tile_w, tile_h, radii, means2d, depths, conics, compensations, tiles_per_gauss, BinArgs{}, ShadeArgs{});
     HGS_LAUNCH_CHECK();
     return 0;
 }
 
 // projection + first kernel of the ordering stage (hgs_isect_bin_prepare's compaction and histogram) in one launch;
 // temp as for hgs_isect_bin_prepare; the caller follows with hgs_isect_bin_scan.
+// shade: -2 none; -1 colours [N,3] given in feats; 0..4 SH degree with coefficients feats [N,K,3], view direction
+// means - campos[c], colour = max(SH + 0.5, 0) written to colors_out [C,N,3] (visible rows only).  With shade != -2 the
+// 64-byte blend records of the visible Gaussians (hgs_blend3d_pack's, bit for bit) are written to records.
 HGS_API int hgs_project3d_fwd_bin(const float* means, const float* quats, const float* scales, const float* viewmats,
                                   const float* Ks, int C, int N, int width, int height, float eps2d, float near_plane,
                                   float far_plane, float radius_clip, int tile_size, int32_t* radii, float* means2d,
                                   float* depths, float* conics, float* compensations, int32_t* tiles_per_gauss,
                                   int32_t* visible_ids, long long* counts_dev, void* temp, size_t temp_bytes,
-                                  void* stream) {
+                                  int shade, const float* feats, int K, const float* opacities, const float* campos,
+                                  int depth_channel, float* colors_out, void* records, void* stream) {
     if (C <= 0 || N < 0 || width <= 0 || height <= 0 || tile_size <= 0 || tiles_per_gauss == nullptr ||
-        visible_ids == nullptr || counts_dev == nullptr)
+        visible_ids == nullptr || counts_dev == nullptr || shade < SHADE_NONE || shade > 4)
+        return HGS_ERR_INVALID_ARG;
+    if (shade != SHADE_NONE && (feats == nullptr || opacities == nullptr || records == nullptr ||
+                                (reinterpret_cast<size_t>(records) & 15) ||
+                                (shade >= 0 && (campos == nullptr || colors_out == nullptr || K < (shade + 1) * (shade + 1)))))
         return HGS_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int tile_w = (width + tile_size - 1) / tile_size, tile_h = (height + tile_size - 1) / tile_size;
@@ -487,9 +529,23 @@ HGS_API int hgs_project3d_fwd_bin(const float* means, const float* quats, const 
     B.flags = T.flags; B.ticket = T.ticket; B.super_count = T.super_count;
     B.visible_ids = visible_ids; B.vrec = T.vrec; B.counts_dev = counts_dev;
     const int nblk_cam = hgs_ceil_div(N, CH);
-    project3d_fwd_kernel<true><<<nblk_cam * C, PB, 0, st>>>(
-        means, quats, scales, viewmats, Ks, N, nblk_cam, width, height, eps2d, near_plane, far_plane, radius_clip, tile_size,
-        tile_w, tile_h, radii, means2d, depths, conics, compensations, tiles_per_gauss, B);
+    ShadeArgs S;
+    S.feats = feats; S.opacities = opacities; S.campos = campos; S.K = K; S.depth_channel = depth_channel;
+    S.colors = colors_out; S.recs = reinterpret_cast<hgs::GRec*>(records);
+#define LAUNCH(SH)                                                                                                    \
+    project3d_fwd_kernel<true, SH><<<nblk_cam * C, PB, 0, st>>>(                                                      \
+        means, quats, scales, viewmats, Ks, N, nblk_cam, width, height, eps2d, near_plane, far_plane, radius_clip,    \
+        tile_size, tile_w, tile_h, radii, means2d, depths, conics, compensations, tiles_per_gauss, B, S);
+    switch (shade) {
+        case SHADE_NONE: LAUNCH(SHADE_NONE) break;
+        case SHADE_RGB: LAUNCH(SHADE_RGB) break;
+        case 0: LAUNCH(0) break;
+        case 1: LAUNCH(1) break;
+        case 2: LAUNCH(2) break;
+        case 3: LAUNCH(3) break;
+        default: LAUNCH(4) break;
+    }
+#undef LAUNCH
     HGS_LAUNCH_CHECK();
     return 0;
 }

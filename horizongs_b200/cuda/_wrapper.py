@@ -161,10 +161,21 @@ class _Project3D(torch.autograd.Function):
             counts = torch.empty(3, dtype=torch.int64, device=dev)
             tb = L.hgs_isect_bin_temp_bytes(C * N, C, tw, th)
             temp = torch.empty(tb, dtype=torch.uint8, device=dev)
+            # shading fused as well (rendering.py decides): colour evaluation + the 64-byte blend records
+            sh = holder.get("shade") if comps is None else None
+            mode, feats, sh_k, opac, campos, colors_out, records = -2, None, 0, None, None, None, None
+            if sh is not None:
+                mode, feats, opac, campos = sh["mode"], sh["feats"], sh["opacities"], sh["campos"]
+                sh_k = feats.shape[1] if mode >= 0 else 0
+                records = torch.empty(L.hgs_blend3d_pack_bytes(C * N), dtype=torch.uint8, device=dev)
+                colors_out = torch.empty((C, N, 3), dtype=torch.float32, device=dev) if mode >= 0 else None
+                holder["shade_out"] = {"records": records, "colors": colors_out}
             check(L.hgs_project3d_fwd_bin(ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), C, N, width, height,
                                           eps2d, near_plane, far_plane, radius_clip, tile_size, ptr(radii), ptr(means2d),
                                           ptr(depths), ptr(conics), ptr(comps), ptr(tiles), ptr(vis_ids), ptr(counts),
-                                          ptr(temp), tb, _stream()), "hgs_project3d_fwd_bin")
+                                          ptr(temp), tb, mode, ptr(feats), sh_k, ptr(opac), ptr(campos),
+                                          int(bool(sh and sh["depth_channel"])), ptr(colors_out), ptr(records),
+                                          _stream()), "hgs_project3d_fwd_bin")
             holder["bin"] = {"vis_full": vis_ids, "counts": counts, "temp": temp}
         else:
             check(L.hgs_project3d_fwd(ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), C, N, width, height,
@@ -280,12 +291,18 @@ class _SphericalHarmonics(torch.autograd.Function):
         L = _lib.lib()
         N, K = coeffs.shape[0], coeffs.shape[1]
         C = dirs.shape[0] if dirs is not None else campos.shape[0]
-        colors = torch.empty((C, N, 3), dtype=torch.float32, device=coeffs.device)
-        _mark("sh_fwd", 0)
-        check(L.hgs_sh_fwd(degree, K, ptr(dirs), ptr(means), ptr(campos), ptr(coeffs), ptr(radii), ptr(vis_ids),
-                           0 if vis_ids is None else vis_ids.numel(), ptr(n_vis_dev), C, N, int(post), ptr(colors),
-                           _stream()), "hgs_sh_fwd")
-        _mark("sh_fwd", 1)
+        precomputed = None if holder is None else holder.pop("sh_precomputed", None)
+        if precomputed is not None:
+            # the projection kernel evaluated the colours of the visible rows (hgs_project3d_fwd_bin, shade >= 0);
+            # this node only carries the backward
+            colors = precomputed
+        else:
+            colors = torch.empty((C, N, 3), dtype=torch.float32, device=coeffs.device)
+            _mark("sh_fwd", 0)
+            check(L.hgs_sh_fwd(degree, K, ptr(dirs), ptr(means), ptr(campos), ptr(coeffs), ptr(radii), ptr(vis_ids),
+                               0 if vis_ids is None else vis_ids.numel(), ptr(n_vis_dev), C, N, int(post), ptr(colors),
+                               _stream()), "hgs_sh_fwd")
+            _mark("sh_fwd", 1)
         ctx.vis_ids = vis_ids
         ctx.save_for_backward(dirs, means, campos, coeffs, radii, colors if post else None)
         ctx.cfg = (degree, K, C, N, int(post))
@@ -413,27 +430,56 @@ def _isect_scan_async(prep, C, N, tile_size, tile_width, tile_height):
     return prep
 
 
+_ISECT_CAPS = {}            # (device, C, N, tile_width, tile_height) -> [capacity of I, capacity of super-tile keys]
+_CAP_SLACK = 1.5
+
+
 def _isect_finish(prep, means2d, radii, depths, C, N, tile_size, tile_width, tile_height):
-    """phase 2: the one host read (sizes the intersection arrays), then scatter into the tile ranges + per-tile sort."""
+    """phase 2: scatter into the super-tile ranges + per-super-tile sort + expansion into tile ranges, and the one host
+    read of (n_visible, n_isects, n_super) that sizes what the caller sees.
+
+    The first call of a (device, C, N, tile grid) reads the counts, then allocates exactly and launches.  Later calls
+    launch BEFORE the read, into buffers of 1.5 x the largest counts seen so far -- the device then has the whole
+    ordering stage queued while the host waits for the three numbers -- and return exact-length views.  If the counts
+    turn out larger than the guess the kernels did nothing (hgs_isect_bin_sorted's capacity rule) and the call is
+    repeated with exact sizes."""
     L = _lib.lib()
     dev = means2d.device
     st = _stream()
+    temp, counts = prep["temp"], prep["counts"]
+    key = (dev, C, N, tile_width, tile_height)
+    offsets = torch.empty((C, tile_height, tile_width), dtype=torch.int32, device=dev)
+
+    def launch(cap_i, cap_s):
+        ids = torch.empty(cap_i, dtype=torch.int64, device=dev)
+        flat = torch.empty(cap_i, dtype=torch.int32, device=dev)
+        bb = L.hgs_isect_bin_bucket_bytes(cap_s)
+        bucket = torch.empty(bb, dtype=torch.uint8, device=dev)
+        check(L.hgs_isect_bin_sorted(ptr(counts), C, N, C * N, cap_i, cap_s, tile_size, tile_width, tile_height,
+                                     ptr(offsets), ptr(ids), ptr(flat), ptr(temp), temp.numel(), ptr(bucket), bb, st),
+              "hgs_isect_bin_sorted")
+        return ids, flat
+
+    caps = _ISECT_CAPS.get(key)
+    ids = flat = None
+    if caps is not None:
+        _mark("isect_sorted", 0)
+        ids, flat = launch(caps[0], caps[1])
+        _mark("isect_sorted", 1)
     prep["event"].synchronize()
     n_visible, n_isects, n_super = prep["host"].tolist()
-    _mark("isect_sorted", 0)
     if n_isects >= 2 ** 31:
         raise _lib.HgsError(f"{n_isects} tile intersections exceed the 32-bit index range")
-    isect_ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
-    flatten_ids = torch.empty(n_isects, dtype=torch.int32, device=dev)
-    offsets = torch.empty((C, tile_height, tile_width), dtype=torch.int32, device=dev)
-    temp = prep["temp"]
-    bb = L.hgs_isect_bin_bucket_bytes(n_super)
-    bucket = torch.empty(bb, dtype=torch.uint8, device=dev)
-    check(L.hgs_isect_bin_sorted(ptr(prep["counts"]), C, N, n_visible, n_isects, n_super, tile_size, tile_width, tile_height, ptr(offsets),
-                                 ptr(isect_ids), ptr(flatten_ids), ptr(temp), temp.numel(), ptr(bucket), bb, st),
-          "hgs_isect_bin_sorted")
-    _mark("isect_sorted", 1)
-    return isect_ids, flatten_ids, offsets, prep["vis_full"][:n_visible]
+    if caps is None or n_isects > caps[0] or n_super > caps[1]:
+        _mark("isect_sorted", 0)
+        ids, flat = launch(n_isects, n_super)
+        _mark("isect_sorted", 1)
+    want = (int(n_isects * _CAP_SLACK) + 1, int(n_super * _CAP_SLACK) + 1)
+    if caps is None:
+        _ISECT_CAPS[key] = [want[0], want[1]]
+    else:
+        caps[0], caps[1] = max(caps[0], want[0]), max(caps[1], want[1])
+    return ids[:n_isects], flat[:n_isects], offsets, prep["vis_full"][:n_visible]
 
 
 def _isect_sorted_from_counts(means2d, radii, depths, tiles_per_gauss, C, N, tile_size, tile_width, tile_height):
@@ -627,11 +673,13 @@ def _pack3d(means2d, conics, colors, depths, opacities, radii, vis_ids, n_vis_de
 
 
 def _vpack_alloc(C, N, width, vis_ids, aux, dev):
-    """the packed gradient accumulator of a blend backward.  Every consumer of its rows (projection / SH backward,
-    the dense unpack, the fused exchange) goes through the work list of visible Gaussians, so only those rows are
-    zeroed (hgs_zero_rows) -- unless there is no work list, or somebody retains the gradient of one of the
-    per-Gaussian blend inputs and could look at the rows of culled Gaussians: then the whole buffer is zero-filled."""
-    dense = vis_ids is None or aux is None or any(r() is None or r().retains_grad for r in aux)
+    """the packed gradient accumulator of a blend backward.  When every consumer of its rows (projection / SH
+    backward, the dense unpack, the fused exchange) goes through the work list of visible Gaussians, only those rows
+    are zeroed (hgs_zero_rows).  The caller says so by passing `aux`, the weak references of the per-Gaussian blend
+    inputs that stay reachable (meta["conics"], meta["depths"]): aux is None when the colours are the caller's own
+    tensor (their gradient is a dense view of the rows), and a live input with retain_grad() could be inspected at
+    the rows of culled Gaussians -- in both cases the whole buffer is zero-filled."""
+    dense = vis_ids is None or aux is None or any(r() is not None and r().retains_grad for r in aux)
     if dense:
         return torch.zeros((C, N, width), dtype=torch.float32, device=dev)
     vpack = torch.empty((C, N, width), dtype=torch.float32, device=dev)

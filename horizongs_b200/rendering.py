@@ -51,14 +51,15 @@ def _validate(means, quats, scales, opacities, colors, viewmats, Ks, render_mode
 
 
 def _per_view_features(means, colors, viewmats, radii, sh_degree, C, vis_ids=None, defer=None, n_vis_dev=None,
-                       holder=None):
-    """-> [C,N,CH] colour features for blending (CH = 3 for SH)."""
+                       holder=None, campos=None):
+    """-> [C,N,CH] colour features for blending (CH = 3 for SH).  holder["sh_precomputed"]: the colours of the visible
+    rows, already evaluated by the projection kernel (the SH node then only carries the backward)."""
     if sh_degree is None:
         if colors.dim() == 2:
             return colors[None] if C == 1 else colors[None].expand(C, -1, -1)
         return colors
-    return W._sh_view_colors(sh_degree, means, _camera_positions(viewmats), colors, radii, vis_ids, defer, n_vis_dev,
-                             holder)
+    return W._sh_view_colors(sh_degree, means, _camera_positions(viewmats) if campos is None else campos, colors, radii,
+                             vis_ids, defer, n_vis_dev, holder)
 
 
 def _mode_features(feats, depths, backgrounds, render_mode):
@@ -104,6 +105,17 @@ def rasterization(
     tile_height = math.ceil(height / float(tile_size))
 
     holder: Dict = {"park_means_grad": sh_degree is not None, "fuse_bin": True}
+    # shading fused into the projection kernel: SH colours (or given [N,3] colours) + the blend records
+    campos = None
+    if (rasterize_mode == "classic" and not absgrad and render_mode in ("RGB", "RGB+D", "RGB+ED") and colors.is_cuda
+            and colors.dtype == torch.float32 and opacities.is_cuda and opacities.dtype == torch.float32
+            and ((sh_degree is not None and colors.dim() == 3 and 0 <= sh_degree <= 4)
+                 or (sh_degree is None and colors.dim() == 2 and colors.shape[-1] == 3))):
+        with torch.no_grad():
+            campos = _camera_positions(viewmats.detach()).contiguous() if sh_degree is not None else None
+            holder["shade"] = {"mode": -1 if sh_degree is None else int(sh_degree),
+                               "feats": colors.detach().contiguous(), "opacities": opacities.detach().contiguous(),
+                               "campos": campos, "depth_channel": render_mode != "RGB"}
     radii, means2d, depths, conics, comps, tiles_per_gauss = W._project3d(
         means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip,
         rasterize_mode == "antialiased", tile_size, holder)
@@ -136,12 +148,16 @@ def rasterization(
                      campos=_camera_positions(viewmats.detach()).contiguous(), width=width, height=height, eps2d=eps2d,
                      near_plane=near_plane, far_plane=far_plane, sh_degree=sh_degree, n=N)
 
-    feats = _per_view_features(means, colors, viewmats, radii, sh_degree, C, vis_full, defer, n_vis_dev, holder)
+    shaded = holder.pop("shade_out", None)
+    holder.pop("shade", None)
+    if shaded is not None and shaded["colors"] is not None:
+        holder["sh_precomputed"] = shaded["colors"]
+    feats = _per_view_features(means, colors, viewmats, radii, sh_degree, C, vis_full, defer, n_vis_dev, holder, campos)
     feats, depth_ch, bgs = _mode_features(feats, depths, backgrounds, render_mode)
     n_ch = feats.shape[-1] + (1 if depth_ch is not None else 0)
     fuse_norm = render_mode in ("ED", "RGB+ED") and n_ch <= 4 and not absgrad
-    records = None
-    if n_ch <= 4 and not absgrad:
+    records = None if shaded is None else shaded["records"]
+    if records is None and n_ch <= 4 and not absgrad:
         records = W._pack3d(W._f32c(means2d, "means2d"), W._f32c(conics, "conics"), W._f32c(feats, "colors"),
                             W._f32c(depth_ch, "depths"), W._f32c(opac, "opacities"), radii, vis_full, n_vis_dev)
 
@@ -167,7 +183,8 @@ def rasterization(
     render_colors, render_alphas = W._blend3d(means2d, conics, feats, depth_ch, opac, bgs, width, height, tile_size,
                                               isect_offsets, flatten_ids, absgrad, radii=radii,
                                               normalize_depth=fuse_norm, vis_ids=vis_ids, defer=defer, records=records,
-                                              aux=[weakref.ref(t) for t in (conics, feats, depth_ch) if t is not None],
+                                              aux=(None if sh_degree is None else
+                                                   [weakref.ref(t) for t in (conics, feats, depth_ch) if t is not None]),
                                               prezero=prezero)
     if render_mode in ("ED", "RGB+ED") and not fuse_norm:
         render_colors = torch.cat(

@@ -133,12 +133,20 @@ int hgs_isect_bin_prepare(const float* means2d, const int32_t* radii, const floa
 /* Phase 1 with its first launch fused into the projection: hgs_project3d_fwd_bin = hgs_project3d_fwd (tiles_per_gauss
  * required) + the compaction / histogram of hgs_isect_bin_prepare in ONE kernel (the Gaussians' tile boxes and depths
  * are still in registers there: no second pass over tiles_per_gauss, means2d, radii, depths); hgs_isect_bin_scan is
- * the remaining scan launch.  Same outputs and temp as hgs_isect_bin_prepare. */
+ * the remaining scan launch.  Same outputs and temp as hgs_isect_bin_prepare.
+ * Shading, optionally fused as well (shade != -2): a visible Gaussian evaluates its colour and writes its 64-byte
+ * blend record (what hgs_sh_fwd on the work list + hgs_blend3d_pack produce, bit for bit) while centre, conic and depth
+ * are in registers.  shade = -1: feats = colours [N,3]; shade = 0..4: feats = SH coefficients [N,K,3], direction
+ * means - campos[c], colors_out [C,N,3] receives max(SH + 0.5, 0) for the visible rows (other rows untouched).
+ * opacities [N]; depth_channel != 0 puts the camera depth in the record's fourth channel (RGB+D / RGB+ED);
+ * records: hgs_blend3d_pack_bytes(C*N) bytes, 16-byte aligned. */
 int hgs_project3d_fwd_bin(const float* means, const float* quats, const float* scales, const float* viewmats,
                           const float* Ks, int C, int N, int width, int height, float eps2d, float near_plane,
                           float far_plane, float radius_clip, int tile_size, int32_t* radii, float* means2d, float* depths,
                           float* conics, float* compensations, int32_t* tiles_per_gauss, int32_t* visible_ids,
-                          long long* counts_dev, void* temp, size_t temp_bytes, void* stream);
+                          long long* counts_dev, void* temp, size_t temp_bytes, int shade, const float* feats, int K,
+                          const float* opacities, const float* campos, int depth_channel, float* colors_out,
+                          void* records, void* stream);
 int hgs_isect_bin_scan(int C, int N, int tile_size, int tile_w, int tile_h, long long* counts_dev, void* temp,
                        size_t temp_bytes, void* stream);
 /* Phase 2 (counts read back by the caller to size the outputs; n_visible_bound >= counts_dev[0] sizes the grid,
@@ -148,7 +156,12 @@ int hgs_isect_bin_scan(int C, int N, int tile_size, int tile_w, int tile_h, long
  * each of its tiles; a last kernel sums those counts into the per-tile range starts and selects every tile's keys,
  * in order, from its super-tile's sorted range.
  * in: counts_dev, temp of phase 1 (it holds the tile boxes and depth bits of the visible Gaussians); bucket: hgs_isect_bin_bucket_bytes(counts[2]) bytes of scratch.
- * out: isect_ids[I] i64, flatten_ids[I] i32, isect_offsets[C*tile_h*tile_w] i32. */
+ * out: isect_ids[I] i64, flatten_ids[I] i32, isect_offsets[C*tile_h*tile_w] i32.
+ * n_isects and bucket_bytes / 8 are CAPACITIES (n_super_isects only sizes the check of bucket_bytes): a caller that has
+ * read counts_dev passes the exact counts; a caller that has not may pass a guess, enqueue the call without waiting,
+ * and compare counts_dev with its guess afterwards -- when I > n_isects or counts[2] > bucket_bytes / 8 every kernel of
+ * this call returns at once without touching temp or the outputs, and the call is simply repeated with larger buffers.
+ * n_visible_bound must be >= counts[0] (C*N always is). */
 int hgs_isect_bin_sorted(const long long* counts_dev, int C, int N, long long n_visible_bound, long long n_isects,
                          long long n_super_isects, int tile_size, int tile_w, int tile_h, int32_t* isect_offsets,
                          long long* isect_ids, int32_t* flatten_ids, void* temp, size_t temp_bytes, void* bucket,

@@ -153,6 +153,30 @@ def test_isect_deep_tiles_every_sort_class(n):
     assert torch.equal(cf.cpu(), flat), f"{int((cf.cpu() != flat).sum())} of {flat.numel()} values differ"
 
 
+def test_isect_capacity_guess_reruns_when_too_small():
+    """the sorted phase is enqueued into buffers sized from earlier calls before the host has read the counts
+    (cuda/_wrapper.py::_isect_finish): a guess that is too small must be detected and repeated, a generous one must
+    give the same arrays"""
+    from horizongs_b200.cuda import _wrapper as Wr
+    g = torch.Generator().manual_seed(5)
+    n = 5000
+    m2 = torch.rand(1, n, 2, generator=g) * torch.tensor([160.0, 96.0])
+    radii = torch.randint(0, 24, (1, n), generator=g, dtype=torch.int32)
+    depths = torch.rand(1, n, generator=g) + 0.5
+    tiles, ids, flat = O.isect_tiles(m2, radii, depths, 16, 10, 6)
+    off = O.isect_offset_encode(ids, 1, 10, 6)
+    key = (torch.device("cuda", torch.cuda.current_device()), 1, n, 10, 6)
+    for caps in (None, [1, 1], [ids.numel() - 1, 10 ** 7], [10 ** 7, 3], [ids.numel(), 10 ** 7], [10 ** 7, 10 ** 7]):
+        Wr._ISECT_CAPS.pop(key, None)
+        if caps is not None:
+            Wr._ISECT_CAPS[key] = list(caps)
+        ct, ci, cf, co = hgs.isect_tiles(m2.cuda(), radii.cuda(), depths.cuda(), 16, 10, 6, _with_offsets=True)
+        assert torch.equal(ct.cpu(), tiles) and torch.equal(co.cpu(), off), caps
+        assert torch.equal(ci.cpu(), ids) and torch.equal(cf.cpu(), flat), caps
+        assert Wr._ISECT_CAPS[key][0] >= ids.numel()
+    Wr._ISECT_CAPS.pop(key, None)
+
+
 def test_isect_empty():
     m2 = torch.zeros(1, 10, 2).cuda()
     radii = torch.zeros(1, 10, dtype=torch.int32).cuda()
