@@ -92,7 +92,7 @@ __device__ __forceinline__ const float4* slot_q(const unsigned char* stage, int 
 // fast forward
 // =====================================================================================================
 template <int D, bool NORM_DEPTH>
-__global__ void __launch_bounds__(BLK) blend3d_fwd_fast_kernel(
+__global__ void __launch_bounds__(BLK, 5) blend3d_fwd_fast_kernel(
     const GRec* __restrict__ recs, const float* __restrict__ backgrounds, int C, int W, int H, int tile_w, int tile_h,
     const int32_t* __restrict__ offsets, const int32_t* __restrict__ flatten_ids, int n_isects,
     float* __restrict__ render_colors, float* __restrict__ render_alphas, int32_t* __restrict__ last_ids) {
@@ -133,6 +133,11 @@ __global__ void __launch_bounds__(BLK) blend3d_fwd_fast_kernel(
     float pix[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) pix[k] = 0.f;
+    // a finished pixel (outside the image, or transmittance exhausted) is one whose alpha threshold can never be met:
+    // no separate flag to test in the inner loop
+    float amin = done ? 2.0f : HGS_ALPHA_MIN;
+    __shared__ unsigned short s_keep[BLK / 32][32];   // slots of the records that survive the warp's cull, in order
+    unsigned short* keep_list = s_keep[g.warp];
 
     for (int b = 0; b < nb; ++b) {
         const int st = b & 1;
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(BLK) blend3d_fwd_fast_kernel(
         const int batch_start = range_start + b * FB;
         const int batch_n = min(FB, range_end - batch_start);
         const unsigned char* stage = s_rec[st];
-        if (!__all_sync(0xFFFFFFFFu, done)) {
+        if (!__all_sync(0xFFFFFFFFu, amin > 1.f)) {
             for (int grp = 0; grp * 32 < batch_n; ++grp) {
                 const int t = grp * 32 + g.lane;
                 bool keep = false;
@@ -160,20 +165,22 @@ __global__ void __launch_bounds__(BLK) blend3d_fwd_fast_kernel(
                     const float4* q = slot_q(stage, t);
                     keep = cull_keep(q[0], q[1], q[3], g.X0, g.X1, g.Y0, g.Y1);
                 }
-                unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
-                while (m) {
-                    const int j = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int tt = grp * 32 + j;
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+                if (m == 0u) continue;
+                if (keep) keep_list[__popc(m & ((1u << g.lane) - 1u))] = (unsigned short)t;
+                __syncwarp();
+                const int n_keep = __popc(m);
+                for (int i = 0; i < n_keep; ++i) {
+                    const int tt = keep_list[i];
                     const float4* q = slot_q(stage, tt);
                     const float4 q0 = q[0], q1 = q[1];
                     const float dx = q0.x - g.px, dy = q0.y - g.py;
                     const float p2 = (q0.z * dx + q0.w * dy) * dx + (q1.x * dy) * dy;
                     const float alpha = fminf(HGS_ALPHA_MAX, q1.y * ex2_approx(p2));
-                    if (!done && p2 <= 0.f && alpha >= HGS_ALPHA_MIN) {
+                    if (p2 <= 0.f && alpha >= amin) {
                         const float next_T = T * (1.0f - alpha);
                         if (next_T <= HGS_T_EPS) {
-                            done = true;
+                            amin = 2.0f;
                         } else {
                             const float vis = alpha * T;
                             const float4 q2 = q[2];
@@ -186,10 +193,11 @@ __global__ void __launch_bounds__(BLK) blend3d_fwd_fast_kernel(
                         }
                     }
                 }
-                if (__all_sync(0xFFFFFFFFu, done)) break;
+                __syncwarp();
+                if (__all_sync(0xFFFFFFFFu, amin > 1.f)) break;
             }
         }
-        if (__syncthreads_count(done) >= BLK) {
+        if (__syncthreads_count(amin > 1.f) >= BLK) {
             if (b + 1 < nb) mbar_wait(&s_bar[st ^ 1], ((b + 1) >> 1) & 1);  // drain the in-flight prefetch
             break;
         }
@@ -286,6 +294,7 @@ struct BwdSmem {
     float acc[BLK / 32][FBB * ACC_STRIDE];
     int ids[2][FBB];
     unsigned wmask[BLK / 32][FBB / 32];
+    unsigned short keep[BLK / 32][32];   // slots that survive the warp's cull, in order
     int red[BLK / 32];
     uint64_t bar[2];
 };
@@ -403,12 +412,15 @@ __global__ void __launch_bounds__(BLK, 4) blend3d_bwd_fast_kernel(
                 const float4* q = slot_q(stage, t);
                 keep = cull_keep(q[0], q[1], q[3], g.X0, g.X1, g.Y0, g.Y1);
             }
-            unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
             unsigned written = 0u;
-            while (m) {
-                const int j = __ffs(m) - 1;
-                m &= m - 1;
-                const int tt = grp * 32 + j;
+            if (m != 0u) {
+                if (keep) S.keep[g.warp][__popc(m & ((1u << g.lane) - 1u))] = (unsigned short)t;
+                __syncwarp();
+            }
+            const int n_keep = __popc(m);
+            for (int i = 0; i < n_keep; ++i) {
+                const int tt = S.keep[g.warp][i];
                 const float4* q = slot_q(stage, tt);
                 const float4 q0 = q[0], q1 = q[1];
                 const float dx = q0.x - g.px, dy = q0.y - g.py;
@@ -450,8 +462,9 @@ __global__ void __launch_bounds__(BLK, 4) blend3d_bwd_fast_kernel(
                 }
                 const float r = halving_reduce<NV>(val, g.lane);
                 if (is_writer) S.acc[g.warp][tt * ACC_STRIDE + my_comp] = r;
-                written |= 1u << j;
+                written |= 1u << (tt & 31);
             }
+            __syncwarp();
             if (g.lane == 0) S.wmask[g.warp][grp] = written;
         }
         __syncthreads();
