@@ -477,6 +477,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    elif args.force_exchange:
+        # development aid: the fused backward + exchange kernels with ONE rank (their fixed costs; ncu can profile it)
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29571", rank=0, world_size=1, device_id=dev)
     L = _lib.lib()                                   # fails loudly if the CUDA library is missing
 
     wl = Workload(args.config, args.gaussians)
@@ -502,7 +505,7 @@ def run_ours(args):
     peer, fused, exchange, exchange_name = None, None, None, "none (1 GPU)"
     if world > 1 and wl.kind == "lod":
         raise SystemExit("configs[3] is a single-GPU bench line")
-    if world > 1 and args.exchange in ("peer", "fused"):
+    if (world > 1 or args.force_exchange) and args.exchange in ("peer", "fused"):
         try:
             if args.exchange == "fused":
                 fused = D.FusedBackwardExchange(N, cap_rows=N // 4, device=dev)
@@ -639,7 +642,9 @@ def run_ours(args):
 
     for s in range(args.warmup):
         step(s)
-    # ---- value: device-resident inputs, with per-stage CUDA events on the launching stream
+    # ---- value: device-resident inputs, timed WITHOUT instrumentation; the per-stage CUDA events (on the launching
+    # stream) come from a second pass over the same steps, so that their ~30 event records per step are not part of
+    # the reported time (ms_per_step_instrumented is that pass's own time)
     marks = []
 
     def hook(name, phase):
@@ -650,8 +655,9 @@ def run_ours(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    Wr.set_stage_hook(hook)
     ms_total, launches = timed(args.steps, args.warmup, e2e=False)
+    Wr.set_stage_hook(hook)
+    ms_instr, _ = timed(args.steps, args.warmup, e2e=False)
     Wr.set_stage_hook(None)
     stage_ms = {}
     opened = {}
@@ -842,6 +848,7 @@ def run_ours(args):
         "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline,
         "parity_check": parity, "exchange_parity": exchange_parity,
         "stage_ms": stage_avg, "stage_ms_sum": sum_stage, "outside_stage_ms": ms_total / n_steps - sum_stage,
+        "ms_per_step_instrumented": ms_instr / n_steps,
         "stage_ms_by_view": stage_by_view, "stage_ms_over_ranks": stage_ranks,
         "counts": ({"mean_n_visible": mean("n_visible"), "mean_I": mean("I"),
                     "mean_P_eval": mean("P_eval") if wl.kind == "3dgs" else None,
@@ -867,6 +874,8 @@ def main():
     ap.add_argument("--gaussians", type=int, default=None, help="override the Gaussian / anchor count of the config")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle legs (parity_check, cpu_baseline)")
     ap.add_argument("--parity-at-scale", action="store_true", help="N > 1: also run rank 0's oracle parity check")
+    ap.add_argument("--force-exchange", action="store_true",
+                    help="development aid: run the N > 1 exchange path with a single rank")
     ap.add_argument("--exchange", default="fused", choices=["fused", "peer", "nccl"],
                     help="N > 1: per-Gaussian backward fused with the exchange over NVLink peer memory (default), "
                          "sparse all-reduce of the parameter gradients over peer memory, or the dense NCCL all-reduce")

@@ -284,7 +284,7 @@ struct VjSmem {      // followed by unsigned bits[world][NW], int first[world][N
 static_assert(sizeof(VjSmem) % 16 == 0, "tile alignment");
 
 template <int DEG>
-__global__ void __launch_bounds__(VJ_WARPS * 32, 2) vjp_reduce_kernel(
+__global__ void __launch_bounds__(VJ_WARPS * 32, (DEG <= 2 ? 3 : 2)) vjp_reduce_kernel(
     ExLayout L, const unsigned char* mailbox, int parity, const int* __restrict__ status,
     const float* __restrict__ means, int K, float* __restrict__ v_means, float* __restrict__ v_quats,
     float* __restrict__ v_scales, float* __restrict__ v_opac, float* __restrict__ v_coeffs,
