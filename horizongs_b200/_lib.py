@@ -45,6 +45,7 @@ SIGNATURES = {
     "hgs_blend3d_pack": (_i, [_p] * 7 + [_ll, _p, _ll, _i, _p, _p]),
     "hgs_blend3d_fwd_packed": (_i, [_p, _p] + [_i] * 6 + [_p, _p, _ll] + [_p] * 3 + [_p]),
     "hgs_blend3d_bwd_packed": (_i, [_p, _p] + [_i] * 6 + [_p, _p, _ll] + [_p] * 6 + [_p]),
+    "hgs_gauss_bwd_fused": (_i, [_p, _i, _p, _ll, _i] + [_p] * 5 + [_i, _i, _f, _f, _f, _i, _i] + [_p] * 9 + [_p]),
     "hgs_blend3d_unpack": (_i, [_p, _p, _ll, _ll, _p, _p, _i, _p]),
     "hgs_zero_rows": (_i, [_p, _i, _p, _ll, _p]),
     "hgs_blend3d_stats": (_i, [_p, _i, _i, _i, _i, _p, _p, _ll, _p, _p]),

@@ -29,6 +29,7 @@ SOURCES = {
     "project3d.cu": ["-fmad=false"],
     "project2d.cu": ["-fmad=false"],
     "sh.cu": ["-fmad=false"],
+    "gauss_bwd.cu": ["-fmad=false"],
     "isect.cu": [],
     "blend3d.cu": [],
     "blend2d.cu": [],

@@ -11,6 +11,8 @@ from __future__ import annotations
 import math
 from typing import Optional, Tuple
 
+import os
+
 import torch
 from torch import Tensor
 
@@ -100,6 +102,19 @@ def _take_zeros(holder, name, shape):
     return t
 
 
+_FUSED_BWD = os.environ.get("HGS_FUSED_BWD", "1") != "0"     # development switch: 0 = three separate kernels
+FUSED_BWD_COUNTS = {"proj_direct": 0, "proj_delta": 0, "sh_direct": 0, "sh_delta": 0}   # how the nodes were served
+
+
+def _same_tensor(a, b) -> bool:
+    """is `a` the very gradient tensor `b` we handed to autograd (no other contribution was added to it)?"""
+    if a is b:
+        return True
+    if a is None or b is None:
+        return False
+    return a.data_ptr() == b.data_ptr() and a.shape == b.shape and a.stride() == b.stride() and a.dtype == b.dtype
+
+
 def _f32c(t: Optional[Tensor], name: str) -> Optional[Tensor]:
     if t is None:
         return None
@@ -185,6 +200,9 @@ class _Project3D(torch.autograd.Function):
         _mark("project3d_fwd", 1)
         ctx.save_for_backward(means, quats, scales, viewmats, Ks, radii)
         ctx.cfg = (width, height, eps2d, near_plane, far_plane)
+        if holder is not None and C == 1 and comps is None:
+            # what the fused per-Gaussian backward (hgs_gauss_bwd_fused, launched by the blend backward) needs
+            holder["proj_ctx"] = (means, quats, scales, viewmats, Ks, ctx.cfg)
         ctx.mark_non_differentiable(radii)
         if tiles is not None:
             ctx.mark_non_differentiable(tiles)
@@ -200,6 +218,34 @@ class _Project3D(torch.autograd.Function):
         width, height, eps2d, near_plane, far_plane = ctx.cfg
         L = _lib.lib()
         C, N = radii.shape
+        fb = None if ctx.holder is None else ctx.holder.get("fused_bwd")
+        if fb is not None:
+            # the blend backward already ran this node's kernel (fused with the SH backward) on the gradients it
+            # produced.  If autograd added nothing to them, that is the answer; otherwise the map is linear: add the
+            # backward of the difference.
+            ctx.holder["proj_bwd_done"] = True
+            extra = ctx.holder.pop("v_means_sh", None)
+            # pop: autograd accumulates a leaf gradient without a copy only if nobody else references the tensor
+            v_means, v_quats, v_scales = fb.pop("v_means"), fb.pop("v_quats"), fb.pop("v_scales")
+            direct = (_same_tensor(v_means2d, fb["v_means2d"]) and _same_tensor(v_conics, fb["v_conics"])
+                      and _same_tensor(v_depths, fb["v_depths"]))
+            FUSED_BWD_COUNTS["proj_direct" if direct else "proj_delta"] += 1
+            if not direct:
+                def diff(a, b, shape):
+                    a = torch.zeros(shape, dtype=torch.float32, device=means.device) if a is None else a
+                    return (a - b).contiguous() if b is not None else a.contiguous()
+                d_m2 = diff(v_means2d, fb["v_means2d"], (C, N, 2))
+                d_c = diff(v_conics, fb["v_conics"], (C, N, 3))
+                d_d = diff(v_depths, fb["v_depths"], (C, N))
+                g_m, g_q, g_s = torch.empty_like(means), torch.empty_like(quats), torch.empty_like(scales)
+                check(L.hgs_project3d_bwd(ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), C, N, width,
+                                          height, eps2d, near_plane, far_plane, ptr(radii), ptr(d_m2), 2, ptr(d_d), 1,
+                                          ptr(d_c), 3, None, 0, ptr(g_m), ptr(g_q), ptr(g_s), 0, _stream()),
+                      "hgs_project3d_bwd")
+                v_means, v_quats, v_scales = v_means + g_m, v_quats + g_q, v_scales + g_s
+            if extra is not None:
+                v_means = v_means + extra
+            return (v_means, v_quats, v_scales) + (None,) * 11
         # the SH stage ran its backward first and left its direction gradient for the means here: add to it
         # instead of letting autograd sum two dense [N,3] tensors
         v_means = _take_sh_means_grad(ctx.holder, means)
@@ -306,6 +352,10 @@ class _SphericalHarmonics(torch.autograd.Function):
         ctx.vis_ids = vis_ids
         ctx.save_for_backward(dirs, means, campos, coeffs, radii, colors if post else None)
         ctx.cfg = (degree, K, C, N, int(post))
+        if holder is not None and post and dirs is None and C == 1:
+            # colors.detach(): the output object itself gets this node as grad_fn -- holding it here would close a
+            # reference cycle (node -> ctx -> holder -> output -> node) and keep the whole step's tensors alive
+            holder["sh_ctx"] = (degree, K, coeffs, means, campos, colors.detach())
         return colors
 
     @staticmethod
@@ -316,6 +366,17 @@ class _SphericalHarmonics(torch.autograd.Function):
             ctx.defer["colors_fwd"] = colors      # the clamp mask of `post`; the gradient itself comes from vpack
             return (None,) * 11
         L = _lib.lib()
+        fb = None if ctx.holder is None else ctx.holder.get("fused_bwd")
+        delta_of = None
+        if fb is not None:
+            # computed by the blend backward's fused per-Gaussian kernel from the gradient it produced; the direction
+            # part of the mean gradient is already inside the projection node's result
+            if _same_tensor(v_colors, fb["v_colors"]):
+                FUSED_BWD_COUNTS["sh_direct"] += 1
+                return None, None, None, None, fb.pop("v_coeffs"), None, None, None, None, None, None
+            FUSED_BWD_COUNTS["sh_delta"] += 1
+            delta_of = {"v_coeffs": fb.pop("v_coeffs")}                       # something else was added: backward of the difference (linear map)
+            v_colors = (v_colors - fb["v_colors"]).contiguous()
         v_colors, ld_vc = _rows(v_colors, 3)
         need_dirs = dirs is not None and ctx.needs_input_grad[1]
         need_means = means is not None and ctx.needs_input_grad[2]
@@ -332,6 +393,8 @@ class _SphericalHarmonics(torch.autograd.Function):
                            ptr(v_coeffs), ptr(v_dirs), ptr(v_means), int(zeroed), _stream()),
               "hgs_sh_bwd")
         _mark("sh_bwd", 1)
+        if delta_of is not None:
+            v_coeffs = v_coeffs + delta_of["v_coeffs"]
         if v_means is not None and ctx.holder is not None and ctx.holder.get("park_means_grad") and \
                 not ctx.holder.get("proj_bwd_done"):
             # the projection backward of this call has not run yet: it will ADD its gradient into this tensor
@@ -615,18 +678,48 @@ class _Blend3D(torch.autograd.Function):
             if ctx.defer is not None:
                 ctx.defer["vpack"] = vpack
             v_means2d, v_conics, v_opacities = vpack[..., 0:2], vpack[..., 2:5], vpack[..., 5]
-            if ctx.vis_ids is not None and ctx.defer is None:
+            v_colors = vpack[..., 8:8 + CH]
+            v_depths = vpack[..., 8 + CH] if has_depth else None
+            hold = None if ctx.prezero is None else ctx.prezero["holder"]
+            fused = None
+            if (_FUSED_BWD and ctx.vis_ids is not None and ctx.defer is None and hold is not None and C == 1 and CH == 3
+                    and "sh_ctx" in hold and "proj_ctx" in hold
+                    and all(k in hold.get("zeros", {}) for k in ("v_means2d", "v_opacities", "v_coeffs", "v_means",
+                                                                 "v_quats", "v_scales"))):
+                # one pass over the visible Gaussians' rows does the dense unpack, the SH backward and the projection
+                # backward (hgs_gauss_bwd_fused); the SH / projection nodes then only hand out what is computed here
+                degree, K, coeffs, means, campos, colors_fwd = hold["sh_ctx"]
+                p_means, quats, scales, viewmats, Ks, (pw, ph, eps2d, near_plane, far_plane) = hold["proj_ctx"]
+                if p_means.data_ptr() == means.data_ptr():
+                    _mark("zeros_wait", 0)
+                    z = {k: _take_zeros(hold, k, shp) for k, shp in (
+                        ("v_means2d", (C, N, 2)), ("v_opacities", (C, N)), ("v_coeffs", coeffs.shape),
+                        ("v_means", means.shape), ("v_quats", quats.shape), ("v_scales", scales.shape))}
+                    _mark("zeros_wait", 1)
+                    if all(t is not None for t in z.values()):
+                        _mark("gauss_bwd", 0)
+                        check(L.hgs_gauss_bwd_fused(ptr(vpack), int(has_depth), ptr(ctx.vis_ids), ctx.vis_ids.numel(), N,
+                                                    ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), pw, ph,
+                                                    eps2d, near_plane, far_plane, degree, K, ptr(campos), ptr(coeffs),
+                                                    ptr(colors_fwd), ptr(z["v_means2d"]), ptr(z["v_opacities"]),
+                                                    ptr(z["v_coeffs"]), ptr(z["v_means"]), ptr(z["v_quats"]),
+                                                    ptr(z["v_scales"]), _stream()), "hgs_gauss_bwd_fused")
+                        _mark("gauss_bwd", 1)
+                        v_means2d, v_opacities = z["v_means2d"], z["v_opacities"]
+                        fused = dict(z, v_colors=v_colors, v_conics=v_conics, v_depths=v_depths)
+                        del fused["v_opacities"], z
+                        hold["fused_bwd"] = fused
+            if fused is None and ctx.vis_ids is not None and ctx.defer is None:
                 # autograd consumes these two as dense tensors (retain_grad clone, leaf accumulation): copy the visible
                 # rows into dense zero-filled tensors instead of handing out strided views of the 48-byte rows
-                hold = None if ctx.prezero is None else ctx.prezero["holder"]
+                _mark("zeros_wait", 0)
                 z2, zo = _take_zeros(hold, "v_means2d", (C, N, 2)), _take_zeros(hold, "v_opacities", (C, N))
+                _mark("zeros_wait", 1)
                 zeroed = z2 is not None and zo is not None
                 v_means2d = z2 if zeroed else torch.empty((C, N, 2), dtype=torch.float32, device=records.device)
                 v_opacities = zo if zeroed else torch.empty((C, N), dtype=torch.float32, device=records.device)
                 check(L.hgs_blend3d_unpack(ptr(vpack), ptr(ctx.vis_ids), ctx.vis_ids.numel(), C * N, ptr(v_means2d),
                                            ptr(v_opacities), int(zeroed), _stream()), "hgs_blend3d_unpack")
-            v_colors = vpack[..., 8:8 + CH]
-            v_depths = vpack[..., 8 + CH] if has_depth else None
             v_bg = None
             if backgrounds is not None and ctx.needs_input_grad[5]:
                 vrc = v_render_colors

@@ -170,6 +170,20 @@ int hgs_isect_bin_sorted(const long long* counts_dev, int C, int N, long long n_
 int hgs_isect_offset_encode(const long long* isect_ids, long long n_isects, int C, int tile_w, int tile_h,
                             int32_t* isect_offsets, void* stream);
 
+/* ---- backward of a3 + a7 of one rasterized view, fused (the three calls hgs_blend3d_unpack, hgs_sh_bwd and
+ * hgs_project3d_bwd over the same work list, bit for bit): one pass over the 48-byte rows of the packed gradient
+ * buffer vpack [N,12] that hgs_blend3d_bwd_packed accumulated (v_means2d 0..1 | v_conics 2..4 | v_opacity 5 |
+ * v_colors 8..10 | v_depth 11).  One camera; SH colours (degree 0..4, coefficients coeffs [N,K,3], campos [3],
+ * colors [N,3] = the clamped forward colours).  in: vis_ids[n_vis] ascending ids of the visible Gaussians.
+ * out (all zero-filled by the caller, rows of visible Gaussians written): v_means2d [N,2], v_opacities [N],
+ * v_coeffs [N,K,3], v_means [N,3] (projection part + SH view-direction part), v_quats [N,4], v_scales [N,3]. */
+int hgs_gauss_bwd_fused(const float* vpack, int has_depth, const int32_t* vis_ids, long long n_vis, int N,
+                        const float* means, const float* quats, const float* scales, const float* viewmat,
+                        const float* Kmat, int width, int height, float eps2d, float near_plane, float far_plane,
+                        int sh_degree, int K, const float* campos, const float* coeffs, const float* colors,
+                        float* v_means2d, float* v_opacities, float* v_coeffs, float* v_means, float* v_quats,
+                        float* v_scales, void* stream);
+
 /* ---- a11: rasterize_to_pixels (3DGS alpha blending) ----------------------------------------------
  * colors[C,N,CH]; if depths != NULL an extra channel CH (the camera-space depth) is blended after the
  * colours (render modes RGB+D / RGB+ED), so the output has D = CH + 1 channels, else D = CH.

@@ -220,7 +220,8 @@ def test_blend3d_forward_backward(C, D4, bg):
 
 
 # ------------------------------------------------------------------------------------ a5 full pipeline
-@pytest.mark.parametrize("mode,sh,C", [("RGB+ED", None, 1), ("RGB", 2, 1), ("RGB+ED", 2, 2), ("ED", None, 1)])
+@pytest.mark.parametrize("mode,sh,C", [("RGB+ED", None, 1), ("RGB", 2, 1), ("RGB+ED", 2, 1), ("RGB+ED", 3, 1),
+                                       ("RGB+ED", 2, 2), ("ED", None, 1)])
 def test_rasterization_pipeline(mode, sh, C):
     sc, V, Ks, Wd, H = small_scene(n=5000, C=C, sh_degree=sh, width=176, height=112, scale=0.1)
     bg = torch.tensor([[0.2, 0.4, 0.6]]).expand(C, -1).contiguous()
@@ -250,6 +251,44 @@ def test_rasterization_pipeline(mode, sh, C):
     # viewspace gradient for densification (scene/basic_model.py:131-134): pixel units, [C,N,2]
     assert cmeta["means2d"].grad is not None and cmeta["means2d"].grad.shape == (C, sc.n, 2)
     assert rel_err(cmeta["means2d"].grad.cpu(), meta["means2d"].grad) < GRAD_RTOL
+
+
+def test_rasterization_extra_loss_terms_on_meta_outputs():
+    """the per-Gaussian backward runs fused inside the blend backward (hgs_gauss_bwd_fused) on the gradients the blend
+    produced; loss terms that use meta["depths"] / meta["means2d"] / meta["conics"] directly add to those gradients
+    afterwards and must still arrive (backward of the difference, cuda/_wrapper.py::_Project3D.backward)"""
+    from horizongs_b200.cuda import _wrapper as Wr
+    sc, V, Ks, Wd, H = small_scene(n=4000, C=1, sh_degree=2, width=160, height=96, scale=0.1)
+    g = torch.Generator().manual_seed(3)
+    w_d, w_m, w_c = torch.rand(1, sc.n, generator=g), torch.rand(1, sc.n, 2, generator=g), torch.rand(1, sc.n, 3, generator=g)
+
+    def run(backend, dev, extra):
+        ins = [t.clone().to(dev).requires_grad_() for t in (sc.means, sc.quats, sc.scales, sc.opacities, sc.colors)]
+        rc, ra, meta = backend.rasterization(*ins, V.to(dev), Ks.to(dev), Wd, H, sh_degree=2, render_mode="RGB+ED")
+        loss = (rc * _rand_like(rc, 6).to(dev)).sum() + (ra * _rand_like(ra, 7).to(dev)).sum()
+        if extra:
+            loss = loss + (meta["depths"] * w_d.to(dev)).sum() + 1e-2 * (meta["means2d"] * w_m.to(dev)).sum() \
+                + 1e-3 * (meta["conics"] * w_c.to(dev)).sum()
+        loss.backward()
+        return [t.grad.cpu() for t in ins]
+
+    stages = []
+    Wr.set_stage_hook(lambda name, phase: stages.append(name))
+    try:
+        c0 = dict(Wr.FUSED_BWD_COUNTS)
+        got_plain = run(hgs, "cuda", False)
+        assert "gauss_bwd" in stages and "sh_bwd" not in stages and "project3d_bwd" not in stages, stages
+        c1 = dict(Wr.FUSED_BWD_COUNTS)
+        assert c1["proj_direct"] == c0["proj_direct"] + 1 and c1["sh_direct"] == c0["sh_direct"] + 1, (c0, c1)
+        got = run(hgs, "cuda", True)
+        c2 = dict(Wr.FUSED_BWD_COUNTS)
+        assert c2["proj_delta"] == c1["proj_delta"] + 1 and c2["sh_direct"] == c1["sh_direct"] + 1, (c1, c2)
+    finally:
+        Wr.set_stage_hook(None)
+    for extra, mine in ((False, got_plain), (True, got)):
+        ref = run(O, "cpu", extra)
+        for name, a, b in zip(("means", "quats", "scales", "opacities", "colors"), mine, ref):
+            assert rel_err(a, b) < GRAD_RTOL, (extra, name, rel_err(a, b))
 
 
 def test_rasterization_no_grad_and_determinism():
