@@ -56,14 +56,14 @@ def log(*a):
 class Workload:
     """scene + cameras + ground truth of one BASELINE.json config (CPU tensors; callers move them)"""
 
-    def __init__(self, config: int, n_gauss: int | None):
+    def __init__(self, config: int, n_gauss: int | None, n_views: int = 8):
         from horizongs_b200 import scenes
         t0 = time.time()
         self.config = config
         self.kind = "2dgs" if config == 2 else ("lod" if config == 3 else "3dgs")
         if config == 4:
             n = n_gauss or 6_000_000
-            self.sc, self.views, self.Ks, self.W, self.H = scenes.config4(n=n, n_views=8)
+            self.sc, self.views, self.Ks, self.W, self.H = scenes.config4(n=n, n_views=n_views)
             self.name = (f"configs[4]: {n / 1e6:g}M explicit SH2 3DGS Gaussians, {self.W}x{self.H}, RGB+ED, "
                          "1 view per GPU per step")
             self.metric = f"fwd+bwd iters/s, {n / 1e6:g}M Gaussians @{self.W}x{self.H}"
@@ -123,6 +123,16 @@ def loss_fn(rc, ra, gt, extra=None):
         nfd = rnd.reshape(rn.shape) * ra.detach()
         loss = loss + LAMBDA_NORMAL * (1.0 - (rn * nfd).sum(-1)).mean()
     return loss
+
+
+def view_schedule(step: int, rank: int, n_views: int, bucketed: bool) -> int:
+    """index of the view `rank` renders at `step` (views alternate aerial = even index / street = odd index).
+    bucketed: horizongs_b200.distributed.bucketed_view (one kind of view per step); interleaved: (rank + step) % n_views.
+    With one rank both are the sequence 0, 1, 2, ..."""
+    if bucketed:
+        from horizongs_b200.distributed import bucketed_view
+        return bucketed_view(step, rank, n_views)
+    return (rank + step) % n_views
 
 
 def render_explicit(backend, kind, params, view, Km, W, H, sh_degree, bg):
@@ -431,35 +441,36 @@ def exchange_parity_check(fused, step_plain, step_fused, params, stats, world, d
     autograd gradients (and densification statistics); bit-identity of the fused result across ranks."""
     import torch.distributed as dist
     N = params[0].shape[0]
-    s = 10_000                                          # a step index outside the timed range; same views both ways
-    # dense reference
-    st_ref = torch.zeros(2, N, device=dev)
-    step_plain(s, st_ref)
-    ref = [p.grad.clone().contiguous() for p in params]
-    for t in ref + [st_ref]:
-        dist.all_reduce(t)
-    for p in params:
-        p.grad = None
-    st_f = torch.zeros(2, N, device=dev)
-    step_fused(s, st_f)
-    torch.cuda.synchronize()
-    worst = 0.0
-    same = True
-    for p, r in zip(params, ref):
-        worst = max(worst, _rel(p.grad, r))
-        g0 = p.grad.clone()
-        dist.broadcast(g0, 0)
-        same = same and bool(torch.equal(g0, p.grad))
-    worst = max(worst, _rel(st_f[0], st_ref[0]))
-    same_den = bool(torch.equal(st_f[1], st_ref[1]))
+    worst, same, same_den = 0.0, True, True
+    for s in (10_000, 10_001):                          # step indices outside the timed range (one step of each kind of
+        # view under the bucketed schedule); the same views both ways
+        # dense reference
+        st_ref = torch.zeros(2, N, device=dev)
+        step_plain(s, st_ref)
+        ref = [p.grad.clone().contiguous() for p in params]
+        for t in ref + [st_ref]:
+            dist.all_reduce(t)
+        for p in params:
+            p.grad = None
+        st_f = torch.zeros(2, N, device=dev)
+        step_fused(s, st_f)
+        torch.cuda.synchronize()
+        for p, r in zip(params, ref):
+            worst = max(worst, _rel(p.grad, r))
+            g0 = p.grad.clone()
+            dist.broadcast(g0, 0)
+            same = same and bool(torch.equal(g0, p.grad))
+        worst = max(worst, _rel(st_f[0], st_ref[0]))
+        same_den = same_den and bool(torch.equal(st_f[1], st_ref[1]))
+        for p in params:
+            p.grad = None
+        del ref, st_ref, st_f
     t = torch.tensor([worst, 0.0 if same else 1.0, 0.0 if same_den else 1.0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    for p in params:
-        p.grad = None
     return {"max_rel": float(t[0]), "bit_identical": bool(t[1] == 0), "visibility_counts_equal": bool(t[2] == 0),
             "tol": 1e-3, "ok": bool(t[0] < 1e-3 and t[1] == 0 and t[2] == 0),
             "what": "fused SH/projection backward + peer-memory exchange vs dense NCCL all-reduce of every rank's autograd "
-                    "gradients and densification statistics, one extra step after the timed region"}
+                    "gradients and densification statistics, two extra steps (one of each kind of view) after the timed region"}
 
 
 # ------------------------------------------------------------------------------------------------- our arm
@@ -482,9 +493,21 @@ def run_ours(args):
         dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29571", rank=0, world_size=1, device_id=dev)
     L = _lib.lib()                                   # fails loudly if the CUDA library is missing
 
-    wl = Workload(args.config, args.gaussians)
+    # configs[4] has world-many distinct views of EACH kind (aerial / street) so that one step can hold one kind only
+    # (view_of below); the first 8 views are the same seeded cameras for every N
+    wl = Workload(args.config, args.gaussians, n_views=max(8, 2 * world))
     W, H, NV = wl.W, wl.H, wl.n_views
     views, Ks, gts = wl.views.to(dev), wl.Ks.to(dev), wl.gts.to(dev)
+    # View schedule.  Aerial views (even indices) cost ~1.6x a street view (odd indices).  "interleaved": rank r renders
+    # view (r + s) % NV, so for N > 1 every step holds both kinds and lasts as long as its aerial views.  "bucketed"
+    # (default for configs[4]): a step holds views of ONE kind -- step s renders kind s % 2, rank r takes the
+    # (r + s // 2)-th view of that kind -- the cost-bucketed batch sampler a data-parallel trainer uses.  Every rank still
+    # visits every view, each rank renders one aerial and one street view per two steps for every N (per-GPU work is
+    # unchanged: weak scaling), and with one rank the two schedules are the same sequence 0, 1, 2, ...
+    bucketed = (args.view_schedule == "bucketed" and args.config == 4 and NV % 2 == 0 and NV >= 2 * world)
+
+    def view_of(s, r=rank):
+        return view_schedule(s, r, NV, bucketed)
     bg = torch.zeros(1, 3, device=dev)
     if wl.kind == "lod":
         from tests import lod_harness as LH
@@ -547,7 +570,7 @@ def run_ours(args):
     views_pin, Ks_pin = wl.views.pin_memory(), wl.Ks.pin_memory()
 
     def inputs(s, e2e):
-        v = (rank + s) % NV
+        v = view_of(s)
         if not e2e:
             return views[v:v + 1], Ks[v:v + 1], gts[v:v + 1]
         # camera first (the forward needs it at once); the ground-truth image is copied on a second stream while the
@@ -669,12 +692,12 @@ def run_ours(args):
     stage_avg = {k: sum(v) / len(v) for k, v in stage_ms.items()}
     blend_b = "blend2d_bwd" if wl.kind == "2dgs" else "blend3d_bwd"
     blend_f = "blend2d_fwd" if wl.kind == "2dgs" else "blend3d_fwd"
-    # per-view split of the blend kernels (step s of the timed loop renders view (rank + warmup + s) % n_views)
+    # per-view split of the blend kernels (step s of the timed loop renders view_of(warmup + s))
     stage_by_view = {}
     for k in (blend_f, blend_b, "isect_sorted"):
         per = {}
         for i, t in enumerate(stage_ms.get(k, [])):
-            per.setdefault((rank + args.warmup + i) % NV, []).append(t)
+            per.setdefault(view_of(args.warmup + i), []).append(t)
         stage_by_view[k] = {str(v): round(sum(ts) / len(ts), 4) for v, ts in sorted(per.items())}
     # ---- e2e: host buffers, H2D of camera + ground truth and D2H of the loss inside the timed region
     for s in range(2):
@@ -832,6 +855,10 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl.name, "views": NV, "render_mode": "RGB+ED", "sh_degree": wl.sh_degree,
                    "tile_size": 16, "loss": LOSS_MODE,
+                   "view_schedule": ("bucketed: a step holds views of one kind (aerial on even steps, street on odd "
+                                     "steps; rank r renders the (r + s // 2)-th view of the kind); per-GPU work per two "
+                                     "steps = one aerial + one street view for every N" if bucketed else
+                                     "interleaved: rank r renders view (r + s) mod views"),
                    "l2": (f"inputs larger than L2 ({N * 38 * 4 / 1e6:.0f} MB of Gaussian parameters per step; no flush)"
                           if N * 38 * 4 > 126e6 else
                           "the view (and with it the set of visible Gaussians and every intermediate) changes every step; "
@@ -879,6 +906,8 @@ def main():
     ap.add_argument("--exchange", default="fused", choices=["fused", "peer", "nccl"],
                     help="N > 1: per-Gaussian backward fused with the exchange over NVLink peer memory (default), "
                          "sparse all-reduce of the parameter gradients over peer memory, or the dense NCCL all-reduce")
+    ap.add_argument("--view-schedule", default="bucketed", choices=["bucketed", "interleaved"],
+                    help="configs[4], N > 1: one kind of view (aerial / street) per step, or both kinds in every step")
     ap.add_argument("--loss", default="l1", choices=["l1", "l1ssim"],
                     help="loss inside the step: fused L1 (+ depth / alpha means; default) or the reference's "
                          "0.8 L1 + 0.2 (1 - SSIM), fused (csrc/loss.cu)")

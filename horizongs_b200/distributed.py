@@ -22,6 +22,19 @@ def shard_views(n_views: int, rank: int, world_size: int, step: int = 0) -> List
     return [v for v in range(n_views) if (v - step) % world_size == rank % world_size]
 
 
+def bucketed_view(step: int, rank: int, n_views: int, n_kinds: int = 2) -> int:
+    """Cost-bucketed view schedule for view-sharded data parallelism: the view `rank` renders at `step`.
+
+    Views are stored interleaved by kind (index % n_kinds: Horizon-GS trains on aerial AND street cameras of one scene,
+    train.py:107-125, and an aerial view costs ~1.6x a street view).  A step lasts as long as its slowest rank, so a
+    step should hold views of ONE kind: step s renders kind s % n_kinds and rank r takes the (r + s // n_kinds)-th view
+    of that kind.  Every rank visits every view, ranks never share a view within a step while
+    world_size <= n_views / n_kinds, and every rank renders one view of each kind per n_kinds steps whatever the world
+    size.  With one rank the schedule is 0, 1, 2, ..."""
+    per_kind = n_views // n_kinds
+    return n_kinds * ((rank + step // n_kinds) % per_kind) + (step % n_kinds)
+
+
 def allreduce_gradients(params: Iterable[torch.Tensor], group=None, average: bool = False,
                         async_op: bool = False):
     """SUM (or mean) the .grad of every parameter over the group, one collective per tensor (the tensors are

@@ -61,6 +61,23 @@ def test_shard_views_partition():
             assert seen == list(range(8))
 
 
+def test_bucketed_view_schedule():
+    """one kind of view per step, disjoint views within a step, every rank visits every view, equal work per rank for
+    every world size, and the one-rank schedule is 0, 1, 2, ..."""
+    assert [D.bucketed_view(s, 0, 8) for s in range(10)] == [0, 1, 2, 3, 4, 5, 6, 7, 0, 1]
+    for world in (1, 2, 4, 8):
+        nv = max(8, 2 * world)
+        for step in range(2 * nv):
+            vs = [D.bucketed_view(step, r, nv) for r in range(world)]
+            assert {v % 2 for v in vs} == {step % 2}
+            assert len(set(vs)) == world
+        for r in range(world):
+            seen = [D.bucketed_view(s, r, nv) for s in range(nv)]
+            assert sorted(seen) == list(range(nv))
+            kinds = [v % 2 for v in seen]
+            assert kinds == [s % 2 for s in range(nv)]
+
+
 @pytest.mark.timeout(300)
 @pytest.mark.parametrize("overlapped", [False, True])
 def test_two_rank_allreduce_equals_single_process_accumulation(tmp_path, overlapped):
