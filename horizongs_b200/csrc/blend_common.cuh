@@ -90,6 +90,58 @@ struct Halving<N, 0> {
     }
     static __device__ __forceinline__ int comp(const int (&id)[N], int) { return id[0]; }
 };
+// The same butterfly with the lane's side of every level given as a bit mask (all ones: the lane has bit M set):
+// "up ? a : b" becomes one three-input LOP3 on a mask register instead of a predicate that has to be rebuilt from
+// the lane id inside the loop (the blend kernels have no predicate registers to spare across their inner loop).
+__device__ __forceinline__ float mask_select(float a, float b, unsigned up_mask) {
+    return __int_as_float((__float_as_int(a) & up_mask) | (__float_as_int(b) & ~up_mask));
+}
+struct LaneMasks {
+    unsigned m16, m8, m4, m2;
+    __device__ __forceinline__ explicit LaneMasks(int lane)
+        : m16((lane & 16) ? ~0u : 0u), m8((lane & 8) ? ~0u : 0u), m4((lane & 4) ? ~0u : 0u), m2((lane & 2) ? ~0u : 0u) {
+        // opaque to the compiler, which would otherwise turn every mask back into "lane & M" predicates
+        asm volatile("" : "+r"(m16), "+r"(m8), "+r"(m4), "+r"(m2));
+    }
+    template <int M>
+    __device__ __forceinline__ unsigned get() const {
+        return M == 16 ? m16 : (M == 8 ? m8 : (M == 4 ? m4 : m2));
+    }
+};
+template <int N, int M>
+struct HalvingMasked {
+    static __device__ __forceinline__ float run(float (&v)[N], const LaneMasks& lm) {
+        constexpr int H = N / 2, R = N - 2 * H;
+        float nv[H + R];
+        const unsigned up = lm.get<M>();
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            const float keep = mask_select(v[2 * i + 1], v[2 * i], up);
+            const float send = mask_select(v[2 * i], v[2 * i + 1], up);
+            nv[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, M);
+        }
+        if (R) nv[H] = v[N - 1] + __shfl_xor_sync(0xFFFFFFFFu, v[N - 1], M);
+        return HalvingMasked<H + R, M / 2>::run(nv, lm);
+    }
+};
+template <int N>
+struct HalvingMasked<N, 0> {
+    static __device__ __forceinline__ float run(float (&v)[N], const LaneMasks&) {
+        static_assert(N == 1, "32 lanes reduce at most 32 components");
+        return v[0];
+    }
+};
+template <int M>
+struct HalvingMasked<1, M> {   // one component left: plain butterfly, no selection
+    static __device__ __forceinline__ float run(float (&v)[1], const LaneMasks& lm) {
+        float nv[1] = {v[0] + __shfl_xor_sync(0xFFFFFFFFu, v[0], M)};
+        return HalvingMasked<1, M / 2>::run(nv, lm);
+    }
+};
+template <>
+struct HalvingMasked<1, 0> {
+    static __device__ __forceinline__ float run(float (&v)[1], const LaneMasks&) { return v[0]; }
+};
 template <int N>
 __device__ __forceinline__ float halving_reduce(float (&v)[N], int lane) {
     return Halving<N, 16>::run(v, lane);
