@@ -528,17 +528,21 @@ def run_ours(args):
     peer, fused, exchange, exchange_name = None, None, None, "none (1 GPU)"
     if world > 1 and wl.kind == "lod":
         raise SystemExit("configs[3] is a single-GPU bench line")
+    # mailbox capacity = N rows per rank: a view can never overflow it (2 x world x N x 64 B = 6.1 GB of 180 GB at 8
+    # GPUs).  N // 4 was enough for views 0..7 (at most 1.02 M of 6 M visible) but not for view 11 of the 16-view set
+    # that 8 ranks use (1.68 M visible): the exchange reported the overflow on every rank, as designed.
+    cap_rows = N
     if (world > 1 or args.force_exchange) and args.exchange in ("peer", "fused"):
         try:
             if args.exchange == "fused":
-                fused = D.FusedBackwardExchange(N, cap_rows=N // 4, device=dev)
+                fused = D.FusedBackwardExchange(N, cap_rows=cap_rows, device=dev)
                 exchange_name = ("per-Gaussian backward fused with the exchange over NVLink peer memory (own kernels, "
                                  "csrc/exchange_vjp.cu): each rank runs the camera-specific SH / projection VJP of its own "
                                  "view and stores one 64-byte record per visible Gaussian into every peer's mailbox; every "
                                  "rank then expands the rank-one SH part, sums all views' records in rank order "
                                  "(bit-identical replicas) and updates the densification statistics")
             else:
-                peer = D.PeerGradientExchange((3, 4, 3, 1, 27, 1, 1), N, cap_rows=N // 4, device=dev)
+                peer = D.PeerGradientExchange((3, 4, 3, 1, 27, 1, 1), N, cap_rows=cap_rows, device=dev)
                 exchange_name = ("sparse all-reduce over NVLink peer memory (own kernels, csrc/exchange.cu): each rank "
                                  "stores the 40-float records (38 gradients + 2 densification statistics) of its visible "
                                  "Gaussians into every peer's mailbox, then merges all ranks' records in rank order")

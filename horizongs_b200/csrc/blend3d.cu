@@ -20,7 +20,6 @@
 //   * expected-depth normalisation (render modes ED / RGB+ED) is fused into the epilogue / prologue.
 // Roofline: FP32 FMA / MUFU.EX2 / shared-memory pipes (not HBM, no tensor cores: no dense contraction).
 // The plain kernels (one pixel per thread, gsplat-style staging) remain for 5..8 channels.
-#include <cstdlib>
 #include "blend_common.cuh"
 #include "../../include/hgs_raster.h"
 
@@ -92,7 +91,7 @@ __device__ __forceinline__ const float4* slot_q(const unsigned char* stage, int 
 // =====================================================================================================
 // fast forward
 // =====================================================================================================
-template <int D, bool NORM_DEPTH, int VARIANT>
+template <int D, bool NORM_DEPTH>
 __global__ void __launch_bounds__(BLK, 5) blend3d_fwd_fast_kernel(
     const GRec* __restrict__ recs, const float* __restrict__ backgrounds, int C, int W, int H, int tile_w, int tile_h,
     const int32_t* __restrict__ offsets, const int32_t* __restrict__ flatten_ids, int n_isects,
@@ -134,10 +133,10 @@ __global__ void __launch_bounds__(BLK, 5) blend3d_fwd_fast_kernel(
     float pix[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) pix[k] = 0.f;
-    // a finished pixel (outside the image, or transmittance exhausted) is one whose alpha threshold can never be met:
-    // no separate flag to test in the inner loop
-    float amin = done ? 2.0f : HGS_ALPHA_MIN;
-    float px = done ? __int_as_float(0x7fc00000) : g.px;   // VARIANT 1: NaN once the pixel is finished
+    // a finished pixel (outside the image, or transmittance exhausted) is one whose x coordinate is NaN: no separate
+    // flag to test in the inner loop
+    bool finished = done;
+    float px = done ? __int_as_float(0x7fc00000) : g.px;
     __shared__ unsigned short s_keep[BLK / 32][32];   // slots of the records that survive the warp's cull, in order
     unsigned short* keep_list = s_keep[g.warp];
 
@@ -159,7 +158,7 @@ __global__ void __launch_bounds__(BLK, 5) blend3d_fwd_fast_kernel(
         const int batch_start = range_start + b * FB;
         const int batch_n = min(FB, range_end - batch_start);
         const unsigned char* stage = s_rec[st];
-        if (!__all_sync(0xFFFFFFFFu, amin > 1.f)) {
+        if (!__all_sync(0xFFFFFFFFu, finished)) {
             for (int grp = 0; grp * 32 < batch_n; ++grp) {
                 const int t = grp * 32 + g.lane;
                 bool keep = false;
@@ -172,54 +171,25 @@ __global__ void __launch_bounds__(BLK, 5) blend3d_fwd_fast_kernel(
                 if (keep) keep_list[__popc(m & ((1u << g.lane) - 1u))] = (unsigned short)t;
                 __syncwarp();
                 const int n_keep = __popc(m);
-                if constexpr (VARIANT == 1) {
-                    // a finished pixel is one whose x coordinate is NaN: the exponent is NaN, "p2 <= 0" fails, and the
-                    // alpha threshold stays an immediate (no per-iteration copies of a loop-carried threshold)
-                    for (int i = 0; i < n_keep; ++i) {
-                        const int tt = keep_list[i];
-                        const float4* q = slot_q(stage, tt);
-                        const float4 q0 = q[0];
-                        const float2 q1 = *reinterpret_cast<const float2*>(q + 1);
-                        const float dx = q0.x - px, dy = q0.y - g.py;
-                        const float p2 = (q0.z * dx + q0.w * dy) * dx + (q1.x * dy) * dy;
-                        const float alpha = fminf(HGS_ALPHA_MAX, q1.y * ex2_approx(p2));
-                        if (p2 <= 0.f && alpha >= HGS_ALPHA_MIN) {
-                            const float next_T = T * (1.0f - alpha);
-                            // if (next_T <= T_EPS) px = NaN, as one predicated move
-                            asm("{\n\t.reg .pred ps;\n\t"
-                                "setp.le.f32 ps, %1, %2;\n\t"
-                                "@ps mov.b32 %0, 0x7fc00000;\n\t}"
-                                : "+f"(px)
-                                : "f"(next_T), "f"(HGS_T_EPS));
-                            if (!(next_T <= HGS_T_EPS)) {
-                                const float vis = alpha * T;
-                                const float4 q2 = q[2];
-                                pix[0] += q2.x * vis;
-                                if (D > 1) pix[1] += q2.y * vis;
-                                if (D > 2) pix[2] += q2.z * vis;
-                                if (D > 3) pix[3] += q2.w * vis;
-                                cur_idx = batch_start + tt;
-                                T = next_T;
-                            }
-                        }
-                    }
-                    amin = (px != px) ? 2.0f : HGS_ALPHA_MIN;
-                    __syncwarp();
-                    if (__all_sync(0xFFFFFFFFu, amin > 1.f)) break;
-                    continue;
-                }
+                // a finished pixel is one whose x coordinate is NaN: the exponent is NaN, "p2 <= 0" fails, and the
+                // alpha threshold stays an immediate (no per-iteration copies of a loop-carried threshold)
                 for (int i = 0; i < n_keep; ++i) {
                     const int tt = keep_list[i];
                     const float4* q = slot_q(stage, tt);
-                    const float4 q0 = q[0], q1 = q[1];
-                    const float dx = q0.x - g.px, dy = q0.y - g.py;
+                    const float4 q0 = q[0];
+                    const float2 q1 = *reinterpret_cast<const float2*>(q + 1);
+                    const float dx = q0.x - px, dy = q0.y - g.py;
                     const float p2 = (q0.z * dx + q0.w * dy) * dx + (q1.x * dy) * dy;
                     const float alpha = fminf(HGS_ALPHA_MAX, q1.y * ex2_approx(p2));
-                    if (p2 <= 0.f && alpha >= amin) {
+                    if (p2 <= 0.f && alpha >= HGS_ALPHA_MIN) {
                         const float next_T = T * (1.0f - alpha);
-                        if (next_T <= HGS_T_EPS) {
-                            amin = 2.0f;
-                        } else {
+                        // if (next_T <= T_EPS) px = NaN, as one predicated move
+                        asm("{\n\t.reg .pred ps;\n\t"
+                            "setp.le.f32 ps, %1, %2;\n\t"
+                            "@ps mov.b32 %0, 0x7fc00000;\n\t}"
+                            : "+f"(px)
+                            : "f"(next_T), "f"(HGS_T_EPS));
+                        if (!(next_T <= HGS_T_EPS)) {
                             const float vis = alpha * T;
                             const float4 q2 = q[2];
                             pix[0] += q2.x * vis;
@@ -231,11 +201,12 @@ __global__ void __launch_bounds__(BLK, 5) blend3d_fwd_fast_kernel(
                         }
                     }
                 }
+                finished = (px != px);
                 __syncwarp();
-                if (__all_sync(0xFFFFFFFFu, amin > 1.f)) break;
+                if (__all_sync(0xFFFFFFFFu, finished)) break;
             }
         }
-        if (__syncthreads_count(amin > 1.f) >= BLK) {
+        if (__syncthreads_count(finished) >= BLK) {
             if (b + 1 < nb) mbar_wait(&s_bar[st ^ 1], ((b + 1) >> 1) & 1);  // drain the in-flight prefetch
             break;
         }
@@ -323,7 +294,7 @@ __global__ void __launch_bounds__(BLK) blend3d_stats_kernel(const GRec* __restri
 // =====================================================================================================
 // fast backward
 // =====================================================================================================
-constexpr int ACC_STRIDE = 11;  // odd: conflict-free slot writes (10 lanes) and strided flush reads
+constexpr int ACC_STRIDE = SLOT_BYTES / 8;  // accumulator row of a slot: 10 floats at HALF the slot's byte offset
 constexpr int VP = 12;          // floats per row of the packed gradient buffer
 
 template <int D, int FBB>
@@ -337,7 +308,7 @@ struct BwdSmem {
     uint64_t bar[2];
 };
 
-template <int D, bool NORM_DEPTH, int FBB, int VARIANT>
+template <int D, bool NORM_DEPTH, int FBB>
 __global__ void __launch_bounds__(BLK, 4) blend3d_bwd_fast_kernel(
     const GRec* __restrict__ recs, const float* __restrict__ backgrounds, int C, int W, int H, int tile_w, int tile_h,
     const int32_t* __restrict__ offsets, const int32_t* __restrict__ flatten_ids, int n_isects,
@@ -403,22 +374,18 @@ __global__ void __launch_bounds__(BLK, 4) blend3d_bwd_fast_kernel(
     const int top = cta_bin_final;
     const int nb = (top - range_start + 1 + FBB - 1) / FBB;
 
+    // every lane ends the butterfly with the full sum of ONE component (halving_component) and stores it itself
     const int my_comp = halving_component<NV>(g.lane);
-    const bool is_writer = (g.lane == __ffs(__match_any_sync(0xFFFFFFFFu, my_comp)) - 1);
-    // VARIANT 1: colour-gradient pairs in the lane's keep / send order of the first butterfly level
-    const bool up16 = (g.lane & 16) != 0;
+    unsigned char* const acc_lane = reinterpret_cast<unsigned char*>(&S.acc[g.warp][my_comp]);
     const LaneMasks lm(g.lane);
-    constexpr int AS = VARIANT == 1 ? SLOT_BYTES / 8 : ACC_STRIDE;  // accumulator row stride in floats
-    static_assert(NV <= AS, "accumulator row too small");
+    // colour-gradient pairs in the lane's keep / send order of the first butterfly level
+    const bool up16 = (g.lane & 16) != 0;
     float vK[D / 2 + 1], vS[D / 2 + 1];
 #pragma unroll
     for (int k = 0; k < D / 2; ++k) {
         vK[k] = up16 ? v_c[2 * k + 1] : v_c[2 * k];
         vS[k] = up16 ? v_c[2 * k] : v_c[2 * k + 1];
     }
-    unsigned char* const acc_lane = reinterpret_cast<unsigned char*>(&S.acc[g.warp][my_comp]);
-    unsigned skip_mark = 0xFFFFu;
-    asm volatile("" : "+r"(skip_mark));  // stays in a register (else rebuilt inside the loop)
 
     int g_next = -1;
     if (tr < FBB) {
@@ -467,141 +434,85 @@ __global__ void __launch_bounds__(BLK, 4) blend3d_bwd_fast_kernel(
                 keep = cull_keep(q[0], q[1], q[3], g.X0, g.X1, g.Y0, g.Y1);
             }
             const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
-            if constexpr (VARIANT == 1) {
-                // lean loop: no divergent branch around the gradient math (lanes that do not blend select zeros);
-                // the first butterfly level is fed with values already in the lane's keep / send order (u, w = the
-                // lane's own / its partner's coordinate); lane-side selections are LOP3s on mask registers; the
-                // survivor list holds slot byte offsets (= 2 x the accumulator row offset), 0xFFFF once a survivor
-                // turned out to blend nowhere in the warp
-                int pos = 0;
-                if (m != 0u) {
-                    pos = __popc(m & ((1u << g.lane) - 1u));
-                    if (keep) S.keep[g.warp][pos] = (unsigned short)(t * SLOT_BYTES);
-                    __syncwarp();
-                }
-                unsigned short* const kl = S.keep[g.warp];
-                const int n_keep = __popc(m);
-                for (int i = 0; i < n_keep; ++i) {
-                    const int off = kl[i];
-                    const float4* q = reinterpret_cast<const float4*>(stage + off);
-                    const float4 q0 = q[0];
-                    const float2 q1 = *reinterpret_cast<const float2*>(q + 1);
-                    const float dx = q0.x - g.px, dy = q0.y - g.py;
-                    const float p2 = (q0.z * dx + q0.w * dy) * dx + (q1.x * dy) * dy;
-                    const float vis = ex2_approx(p2);
-                    const float opac = q1.y;
-                    const float av = opac * vis;
-                    const float alpha = fminf(HGS_ALPHA_MAX, av);
-                    const bool valid = (off >= off_min) && p2 <= 0.f && alpha >= HGS_ALPHA_MIN;
-                    if (!__any_sync(0xFFFFFFFFu, valid)) {
-                        kl[i] = (unsigned short)skip_mark;   // every lane stores the same value: no divergence inside the loop
-                        continue;
-                    }
-                    const float4 q2 = q[2];
-                    const float col[4] = {q2.x, q2.y, q2.z, q2.w};
-                    const float ra = rcp_approx(1.0f - alpha);  // 1 - alpha in [1e-3, 1]: 1-ulp reciprocal
-                    // if (valid) T *= ra, as ONE predicated multiply (the compiler prefers multiply + select)
-                    asm("{\n\t.reg .pred pv;\n\t"
-                        "setp.ne.b32 pv, %1, 0;\n\t"
-                        "@pv mul.f32 %0, %0, %2;\n\t}"
-                        : "+f"(T)
-                        : "r"((int)valid), "f"(ra));
-                    const float fac = (valid ? alpha : 0.f) * T;
-                    float cdot = 0.f;
-#pragma unroll
-                    for (int k = 0; k < D; ++k) cdot += col[k] * v_c[k];
-                    const float v_alpha = T * cdot + ra * (c0 - s_behind);
-                    s_behind += fac * cdot;
-                    // moments of v_sigma over the pixels; the flush turns them into v_means2d / v_conics
-                    float v_o;  // = (valid && av <= ALPHA_MAX) ? vis * v_alpha : 0, one compare chained on `valid`
-                    asm("{\n\t.reg .pred pv, pq;\n\t"
-                        "setp.ne.b32 pv, %1, 0;\n\t"
-                        "setp.le.and.f32 pq, %2, %3, pv;\n\t"
-                        "selp.f32 %0, %4, 0f00000000, pq;\n\t}"
-                        : "=f"(v_o)
-                        : "r"((int)valid), "f"(av), "f"(HGS_ALPHA_MAX), "f"(vis * v_alpha));
-                    const float v_sigma = -opac * v_o;
-                    const float u = mask_select(dy, dx, lm.m16), w = mask_select(dx, dy, lm.m16);
-                    constexpr int H = NV / 2, R = NV - 2 * H;
-                    float nv[H + R];
-                    const float k0 = v_sigma * u, s0 = v_sigma * w;           // components 0, 1: Mx, My
-                    const float k1 = k0 * u, s1 = s0 * w;                     // components 2, 3: Mxx, Myy
-                    const float mxy = k0 * w;
-                    const float k2 = mask_select(v_o, mxy, lm.m16);           // components 4, 5: Mxy, v_opacity
-                    const float s2 = mask_select(mxy, v_o, lm.m16);
-                    nv[0] = k0 + __shfl_xor_sync(0xFFFFFFFFu, s0, 16);
-                    nv[1] = k1 + __shfl_xor_sync(0xFFFFFFFFu, s1, 16);
-                    nv[2] = k2 + __shfl_xor_sync(0xFFFFFFFFu, s2, 16);
-#pragma unroll
-                    for (int k = 0; k < D / 2; ++k)                           // components 6 + 2k, 7 + 2k
-                        nv[3 + k] = fac * vK[k] + __shfl_xor_sync(0xFFFFFFFFu, fac * vS[k], 16);
-                    if (R) {
-                        const float last = fac * v_c[D - 1];
-                        nv[H] = last + __shfl_xor_sync(0xFFFFFFFFu, last, 16);
-                    }
-                    const float r = HalvingMasked<H + R, 8>::run(nv, lm);
-                    // every lane holds the full sum of ITS component (lanes sharing a component hold identical
-                    // bits: the last butterfly levels are commutative adds), so all 32 lanes store: no predicate
-                    *reinterpret_cast<float*>(acc_lane + (off >> 1)) = r;
-                }
-                __syncwarp();
-                const unsigned wm = __ballot_sync(0xFFFFFFFFu, keep && S.keep[g.warp][pos] != 0xFFFFu);
-                if (g.lane == 0) S.wmask[g.warp][grp] = wm;
-                continue;
-            }
-            unsigned written = 0u;
+            // lean loop: no divergent branch around the gradient math (lanes that do not blend select zeros);
+            // the first butterfly level is fed with values already in the lane's keep / send order (u, w = the
+            // lane's own / its partner's coordinate); lane-side selections are LOP3s on mask registers; the
+            // survivor list holds slot byte offsets (= 2 x the accumulator row offset), bit 15 set once a survivor
+            // turned out to blend nowhere in the warp
+            int pos = 0;
             if (m != 0u) {
-                if (keep) S.keep[g.warp][__popc(m & ((1u << g.lane) - 1u))] = (unsigned short)t;
+                pos = __popc(m & ((1u << g.lane) - 1u));
+                if (keep) S.keep[g.warp][pos] = (unsigned short)(t * SLOT_BYTES);
                 __syncwarp();
             }
+            unsigned short* const kl = S.keep[g.warp];
             const int n_keep = __popc(m);
             for (int i = 0; i < n_keep; ++i) {
-                const int tt = S.keep[g.warp][i];
-                const float4* q = slot_q(stage, tt);
-                const float4 q0 = q[0], q1 = q[1];
+                const int off = kl[i];
+                const float4* q = reinterpret_cast<const float4*>(stage + off);
+                const float4 q0 = q[0];
+                const float2 q1 = *reinterpret_cast<const float2*>(q + 1);
                 const float dx = q0.x - g.px, dy = q0.y - g.py;
                 const float p2 = (q0.z * dx + q0.w * dy) * dx + (q1.x * dy) * dy;
                 const float vis = ex2_approx(p2);
                 const float opac = q1.y;
-                const float alpha = fminf(HGS_ALPHA_MAX, opac * vis);
-                const bool valid = (batch_end - tt <= bin_final) && p2 <= 0.f && alpha >= HGS_ALPHA_MIN;
-                if (!__any_sync(0xFFFFFFFFu, valid)) continue;
-                float val[NV];
-#pragma unroll
-                for (int k = 0; k < NV; ++k) val[k] = 0.f;
-                if (valid) {
-                    const float4 q2 = q[2];
-                    const float col[4] = {q2.x, q2.y, q2.z, q2.w};
-                    const float ra = rcp_approx(1.0f - alpha);  // 1 - alpha in [1e-3, 1]: 1-ulp reciprocal
-                    T *= ra;
-                    const float fac = alpha * T;
-                    float cdot = 0.f;
-#pragma unroll
-                    for (int k = 0; k < D; ++k) {
-                        val[6 + k] = fac * v_c[k];
-                        cdot += col[k] * v_c[k];
-                    }
-                    const float v_alpha = T * cdot + ra * (c0 - s_behind);
-                    s_behind += fac * cdot;
-                    if (opac * vis <= HGS_ALPHA_MAX) {
-                        // moments of v_sigma over the pixels; the flush turns them into v_means2d / v_conics
-                        const float v_o = vis * v_alpha;
-                        const float v_sigma = -opac * v_o;
-                        const float mx = v_sigma * dx, my = v_sigma * dy;
-                        val[0] = mx;
-                        val[1] = my;
-                        val[2] = mx * dx;
-                        val[3] = mx * dy;
-                        val[4] = my * dy;
-                        val[5] = v_o;
-                    }
+                const float av = opac * vis;
+                const float alpha = fminf(HGS_ALPHA_MAX, av);
+                const bool valid = (off >= off_min) && p2 <= 0.f && alpha >= HGS_ALPHA_MIN;
+                if (!__any_sync(0xFFFFFFFFu, valid)) {
+                    kl[i] = (unsigned short)(off | 0x8000);   // every lane stores the same value: no divergence
+                    continue;
                 }
-                const float r = halving_reduce<NV>(val, g.lane);
-                if (is_writer) S.acc[g.warp][tt * ACC_STRIDE + my_comp] = r;
-                written |= 1u << (tt & 31);
+                const float4 q2 = q[2];
+                const float col[4] = {q2.x, q2.y, q2.z, q2.w};
+                const float ra = rcp_approx(1.0f - alpha);  // 1 - alpha in [1e-3, 1]: 1-ulp reciprocal
+                // if (valid) T *= ra, as ONE predicated multiply (the compiler prefers multiply + select)
+                asm("{\n\t.reg .pred pv;\n\t"
+                    "setp.ne.b32 pv, %1, 0;\n\t"
+                    "@pv mul.f32 %0, %0, %2;\n\t}"
+                    : "+f"(T)
+                    : "r"((int)valid), "f"(ra));
+                const float fac = (valid ? alpha : 0.f) * T;
+                float cdot = 0.f;
+#pragma unroll
+                for (int k = 0; k < D; ++k) cdot += col[k] * v_c[k];
+                const float v_alpha = T * cdot + ra * (c0 - s_behind);
+                s_behind += fac * cdot;
+                // moments of v_sigma over the pixels; the flush turns them into v_means2d / v_conics
+                float v_o;  // = (valid && av <= ALPHA_MAX) ? vis * v_alpha : 0, one compare chained on `valid`
+                asm("{\n\t.reg .pred pv, pq;\n\t"
+                    "setp.ne.b32 pv, %1, 0;\n\t"
+                    "setp.le.and.f32 pq, %2, %3, pv;\n\t"
+                    "selp.f32 %0, %4, 0f00000000, pq;\n\t}"
+                    : "=f"(v_o)
+                    : "r"((int)valid), "f"(av), "f"(HGS_ALPHA_MAX), "f"(vis * v_alpha));
+                const float v_sigma = -opac * v_o;
+                const float u = mask_select(dy, dx, lm.m16), w = mask_select(dx, dy, lm.m16);
+                constexpr int H = NV / 2, R = NV - 2 * H;
+                float nv[H + R];
+                const float k0 = v_sigma * u, s0 = v_sigma * w;           // components 0, 1: Mx, My
+                const float k1 = k0 * u, s1 = s0 * w;                     // components 2, 3: Mxx, Myy
+                const float mxy = k0 * w;
+                const float k2 = mask_select(v_o, mxy, lm.m16);           // components 4, 5: Mxy, v_opacity
+                const float s2 = mask_select(mxy, v_o, lm.m16);
+                nv[0] = k0 + __shfl_xor_sync(0xFFFFFFFFu, s0, 16);
+                nv[1] = k1 + __shfl_xor_sync(0xFFFFFFFFu, s1, 16);
+                nv[2] = k2 + __shfl_xor_sync(0xFFFFFFFFu, s2, 16);
+#pragma unroll
+                for (int k = 0; k < D / 2; ++k)                           // components 6 + 2k, 7 + 2k
+                    nv[3 + k] = fac * vK[k] + __shfl_xor_sync(0xFFFFFFFFu, fac * vS[k], 16);
+                if (R) {
+                    const float last = fac * v_c[D - 1];
+                    nv[H] = last + __shfl_xor_sync(0xFFFFFFFFu, last, 16);
+                }
+                const float r = HalvingMasked<H + R, 8>::run(nv, lm);
+                // every lane holds the full sum of ITS component (lanes sharing a component hold identical
+                // bits: the last butterfly levels are commutative adds), so all 32 lanes store: no predicate
+                *reinterpret_cast<float*>(acc_lane + (off >> 1)) = r;
             }
             __syncwarp();
-            if (g.lane == 0) S.wmask[g.warp][grp] = written;
+            const unsigned wm = __ballot_sync(0xFFFFFFFFu, keep && (S.keep[g.warp][pos] & 0x8000u) == 0u);
+            if (g.lane == 0) S.wmask[g.warp][grp] = wm;
         }
         __syncthreads();
         // flush: thread t sums the 8 warps' slots of Gaussian t and adds them to global memory
@@ -615,7 +526,7 @@ __global__ void __launch_bounds__(BLK, 4) blend3d_bwd_fast_kernel(
                 if ((S.wmask[w][tr >> 5] >> (tr & 31)) & 1u) {
                     any = true;
 #pragma unroll
-                    for (int k = 0; k < NV; ++k) sum[k] += S.acc[w][tr * AS + k];
+                    for (int k = 0; k < NV; ++k) sum[k] += S.acc[w][tr * ACC_STRIDE + k];
                 }
             }
             if (any) {
@@ -626,13 +537,10 @@ __global__ void __launch_bounds__(BLK, 4) blend3d_bwd_fast_kernel(
                 const float Mx = sum[0], My = sum[1];
                 sum[0] = -LN2 * (2.f * q0.z * Mx + q0.w * My);
                 sum[1] = -LN2 * (q0.w * Mx + 2.f * q1.x * My);
-                if (VARIANT == 1) {  // component order Mxx, Myy, Mxy
-                    const float myy = sum[3];
-                    sum[3] = sum[4];
-                    sum[4] = myy;
-                }
+                const float Myy = sum[3];  // component order Mxx, Myy, Mxy
                 sum[2] *= 0.5f;
-                sum[4] *= 0.5f;
+                sum[3] = sum[4];
+                sum[4] = 0.5f * Myy;
                 float* row = vpack + (long long)S.ids[st][tr] * VP;
                 red_add_v4(row, sum[0], sum[1], sum[2], sum[3]);
                 red_add_v2(row + 4, sum[4], sum[5]);
@@ -901,13 +809,9 @@ int launch_fwd_fast(const GRec* recs, const float* backgrounds, int C, int W, in
                     const int32_t* offsets, const int32_t* flatten_ids, int n_isects, float* render_colors,
                     float* render_alphas, int32_t* last_ids, cudaStream_t st) {
     dim3 grid(tile_w, tile_h, C);
-    static const int variant = [] {
-        const char* v = getenv("HGS_BLEND3D_FWD_VARIANT");
-        return (v != nullptr && v[0] == '0') ? 0 : 1;
-    }();
-    auto* kern = variant == 1 ? blend3d_fwd_fast_kernel<D, NORM, 1> : blend3d_fwd_fast_kernel<D, NORM, 0>;
-    kern<<<grid, BLK, 0, st>>>(recs, backgrounds, C, W, H, tile_w, tile_h, offsets, flatten_ids, n_isects, render_colors,
-                               render_alphas, last_ids);
+    blend3d_fwd_fast_kernel<D, NORM><<<grid, BLK, 0, st>>>(recs, backgrounds, C, W, H, tile_w, tile_h, offsets,
+                                                           flatten_ids, n_isects, render_colors, render_alphas,
+                                                           last_ids);
     HGS_LAUNCH_CHECK();
     return 0;
 }
@@ -919,11 +823,7 @@ int launch_bwd_fast(const GRec* recs, const float* backgrounds, int C, int W, in
                     const float* v_render_alphas, float* vpack, cudaStream_t st) {
     dim3 grid(tile_w, tile_h, C);
     const int smem = (int)sizeof(BwdSmem<D, FB_BWD>);
-    static const int variant = [] {
-        const char* v = getenv("HGS_BLEND3D_BWD_VARIANT");
-        return (v != nullptr && v[0] == '0') ? 0 : 1;
-    }();
-    auto* kern = variant == 1 ? blend3d_bwd_fast_kernel<D, NORM, FB_BWD, 1> : blend3d_bwd_fast_kernel<D, NORM, FB_BWD, 0>;
+    auto* kern = blend3d_bwd_fast_kernel<D, NORM, FB_BWD>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<grid, BLK, smem, st>>>(recs, backgrounds, C, W, H, tile_w, tile_h, offsets, flatten_ids, n_isects,

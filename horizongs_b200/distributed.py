@@ -354,7 +354,7 @@ class FusedBackwardExchange:
     everywhere, and sh_bwd + project3d_bwd + densify_stats + the all-reduce of a step collapse into one push and
     one reduce kernel.  One camera per rank and step.
 
-        ex = FusedBackwardExchange(N, cap_rows=N // 4)
+        ex = FusedBackwardExchange(N, cap_rows=N)   # N can never overflow; 2 x world x cap_rows x 64 B of HBM
         with ex.deferred():                       # backward stops after the blend backward
             rc, ra, meta = rasterization(means, quats, scales, opacities, colors, viewmat[None], K[None], W, H, ...)
             loss(rc, ra).backward()
