@@ -8,8 +8,10 @@ Default workload (config.workload): BASELINE.json configs[4] = the configuration
 explicit SH2 Gaussians, 1920x1080, render_mode RGB+ED, 8 seeded cameras (aerial / street alternating).  One "step"
 = one view per GPU: rasterization forward, an L1-style loss, backward to the 38 floats of every Gaussian, the
 densification statistics, and for N > 1 the gradient exchange (default: the per-Gaussian backward fused with the
-exchange over NVLink peer memory, csrc/exchange_vjp.cu; `--exchange nccl` = dense NCCL all-reduce).  Rank r renders
-view (r + step) mod 8, so every rank sees every view ("weak" scaling: per-GPU work fixed).
+exchange over NVLink peer memory, csrc/exchange_vjp.cu; `--exchange nccl` = dense NCCL all-reduce).  For N > 1 the
+views follow the cost-bucketed schedule (`--view-schedule bucketed`: a step holds views of one kind, every rank
+renders one aerial and one street view per two steps; `interleaved`: rank r renders view (r + step) mod 8); every
+rank sees every view either way ("weak" scaling: per-GPU work fixed).
 `--config 0..3` time the other named configurations (parity-test cases of the contract, measured for completeness):
 0 = 100k / 256x256 (the CPU-runnable case, full frame on both arms), 1 = 1M 3DGS 1080p aerial + street, 2 = 1M 2DGS
 surfels with the normal-consistency loss, 3 = LOD anchor model (500k anchors x 10) through the adapter control flow.
@@ -123,6 +125,14 @@ def loss_fn(rc, ra, gt, extra=None):
         nfd = rnd.reshape(rn.shape) * ra.detach()
         loss = loss + LAMBDA_NORMAL * (1.0 - (rn * nfd).sum(-1)).mean()
     return loss
+
+
+def exchange_cap_rows(n_gaussians: int) -> int:
+    """rows per rank of the peer-memory mailboxes (N > 1).  N rows: a view can never overflow them (2 x world x N x 64 B
+    = 6.1 GB of 180 GB at 8 GPUs and 6 M Gaussians).  N // 4 was enough for views 0..7 (at most 1.02 M of 6 M visible)
+    but not for view 11 of the 16-view set that 8 ranks use (1.68 M visible; tests/test_distributed_cpu.py counts them):
+    the exchange then reported HGS_EX_OVERFLOW on every rank, as designed."""
+    return int(n_gaussians)
 
 
 def view_schedule(step: int, rank: int, n_views: int, bucketed: bool) -> int:
@@ -528,10 +538,7 @@ def run_ours(args):
     peer, fused, exchange, exchange_name = None, None, None, "none (1 GPU)"
     if world > 1 and wl.kind == "lod":
         raise SystemExit("configs[3] is a single-GPU bench line")
-    # mailbox capacity = N rows per rank: a view can never overflow it (2 x world x N x 64 B = 6.1 GB of 180 GB at 8
-    # GPUs).  N // 4 was enough for views 0..7 (at most 1.02 M of 6 M visible) but not for view 11 of the 16-view set
-    # that 8 ranks use (1.68 M visible): the exchange reported the overflow on every rank, as designed.
-    cap_rows = N
+    cap_rows = exchange_cap_rows(N)
     if (world > 1 or args.force_exchange) and args.exchange in ("peer", "fused"):
         try:
             if args.exchange == "fused":

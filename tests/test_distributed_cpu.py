@@ -94,3 +94,25 @@ def test_two_rank_allreduce_equals_single_process_accumulation(tmp_path, overlap
         assert float((a - b).abs().max()) <= 1e-3 * float(b.abs().max()) + 1e-12
     assert torch.allclose(got["norm"], ref_norm, rtol=1e-4, atol=1e-7)
     assert torch.equal(got["vis"], ref_vis)
+
+
+def test_bench_mailboxes_hold_every_view_of_the_16_view_set():
+    """Regression guard for the 8-GPU bench: 8 ranks use a 16-view set of configs[4] whose view 11 (a street camera
+    inside the cloud) sees 1.68 M of the 6 M Gaussians -- more than the N // 4 rows bench.py used to give the peer-memory
+    mailboxes (views 0..7 need at most 1.02 M), which ended the one 8-GPU run of the bucketed schedule with the collective
+    HGS_EX_OVERFLOW error.  Visible counts come from the oracle's projection (radii > 0)."""
+    import bench
+    from horizongs_b200 import scenes
+    from oracle import gsplat_oracle as O
+    n = 6_000_000
+    sc, views, Ks, W, H = scenes.config4(n=n, n_views=16)
+    counts = []
+    with torch.no_grad():
+        for v in range(16):
+            radii = O.fully_fused_projection(sc.means, None, sc.quats, sc.scales, views[v:v + 1], Ks[v:v + 1], W, H)[0]
+            counts.append(int((radii > 0).sum()))
+    assert counts[:8] == [798985, 295666, 798538, 794317, 799036, 794879, 799390, 1016665], counts   # bench lines' counts
+    assert max(counts) == counts[11] == 1675448, counts
+    assert max(counts) > n // 4                      # the old capacity overflows ...
+    assert bench.exchange_cap_rows(n) >= max(counts)  # ... the current one cannot
+    assert bench.exchange_cap_rows(n) >= n
