@@ -130,8 +130,8 @@ def loss_fn(rc, ra, gt, extra=None):
 def exchange_cap_rows(n_gaussians: int) -> int:
     """rows per rank of the peer-memory mailboxes (N > 1).  N rows: a view can never overflow them (2 x world x N x 64 B
     = 6.1 GB of 180 GB at 8 GPUs and 6 M Gaussians).  N // 4 was enough for views 0..7 (at most 1.02 M of 6 M visible)
-    but not for view 11 of the 16-view set that 8 ranks use (1.68 M visible; tests/test_distributed_cpu.py counts them):
-    the exchange then reported HGS_EX_OVERFLOW on every rank, as designed."""
+    but not for view 11 of a 16-view set tried at 8 GPUs (1.68 M visible; tests/test_distributed_cpu.py counts them): the
+    exchange then reported HGS_EX_OVERFLOW on every rank, as designed."""
     return int(n_gaussians)
 
 
@@ -503,9 +503,8 @@ def run_ours(args):
         dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29571", rank=0, world_size=1, device_id=dev)
     L = _lib.lib()                                   # fails loudly if the CUDA library is missing
 
-    # configs[4] has world-many distinct views of EACH kind (aerial / street) so that one step can hold one kind only
-    # (view_of below); the first 8 views are the same seeded cameras for every N
-    wl = Workload(args.config, args.gaussians, n_views=max(8, 2 * world))
+    # configs[4]: the same 8 seeded cameras (4 aerial + 4 street) for every N -- BASELINE.json's "8-view batch"
+    wl = Workload(args.config, args.gaussians, n_views=8)
     W, H, NV = wl.W, wl.H, wl.n_views
     views, Ks, gts = wl.views.to(dev), wl.Ks.to(dev), wl.gts.to(dev)
     # View schedule.  Aerial views (even indices) cost ~1.6x a street view (odd indices).  "interleaved": rank r renders
@@ -513,7 +512,10 @@ def run_ours(args):
     # (default for configs[4]): a step holds views of ONE kind -- step s renders kind s % 2, rank r takes the
     # (r + s // 2)-th view of that kind -- the cost-bucketed batch sampler a data-parallel trainer uses.  Every rank still
     # visits every view, each rank renders one aerial and one street view per two steps for every N (per-GPU work is
-    # unchanged: weak scaling), and with one rank the two schedules are the same sequence 0, 1, 2, ...
+    # unchanged: weak scaling), and with one rank the two schedules are the same sequence 0, 1, 2, ...  It needs as many
+    # views of a kind as ranks: with 8 ranks a step IS the 8-view batch (4 aerial + 4 street, one view per rank, as
+    # BASELINE.json's configs[4] names it) and the schedule is the interleaved one.  (A 16-view set was tried for 8 ranks:
+    # its view 11 sees 1.68 M Gaussians and overflowed the N // 4 mailboxes of that time, see exchange_cap_rows.)
     bucketed = (args.view_schedule == "bucketed" and args.config == 4 and NV % 2 == 0 and NV >= 2 * world)
 
     def view_of(s, r=rank):
@@ -869,7 +871,8 @@ def run_ours(args):
                    "view_schedule": ("bucketed: a step holds views of one kind (aerial on even steps, street on odd "
                                      "steps; rank r renders the (r + s // 2)-th view of the kind); per-GPU work per two "
                                      "steps = one aerial + one street view for every N" if bucketed else
-                                     "interleaved: rank r renders view (r + s) mod views"),
+                                     "interleaved: rank r renders view (r + s) mod views (with 8 ranks every step is "
+                                     "the whole 8-view batch: 4 aerial + 4 street views, one per rank)"),
                    "l2": (f"inputs larger than L2 ({N * 38 * 4 / 1e6:.0f} MB of Gaussian parameters per step; no flush)"
                           if N * 38 * 4 > 126e6 else
                           "the view (and with it the set of visible Gaussians and every intermediate) changes every step; "
