@@ -273,3 +273,33 @@ def test_ctypes_signatures_match_the_header_prototypes():
             else:
                 assert t in (C.c_int, C.c_longlong, C.c_size_t, C.c_ulonglong), (name, p, t)
     assert seen == set(_lib.SIGNATURES), sorted(set(_lib.SIGNATURES) ^ seen)
+
+
+def test_committed_bench_line_carries_the_contract_keys():
+    """the final one-GPU bench line committed under profiles/ has every key of the bench contract, its roofline and
+    end-to-end blocks are self-consistent, and its parity block is green (guards bench.py's JSON line against silently
+    losing a key)"""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r02_bench_n1_final.json")
+    line = json.loads([x for x in open(path) if x.startswith("{")][-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in line, k
+    assert line["n_gpus"] == 1 and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert "workload" in line["config"] and "model" not in line["config"]
+    assert abs(line["value"] - 1000.0 / line["ms_per_step"]) < 1e-6 * line["value"]
+    e2e = line["e2e"]
+    assert e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0 and e2e["value"] < line["value"]
+    rf = line["roofline"]
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and 0.0 < rf["frac"] < 1.0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] > 0 and cb["sample"]
+    assert line["gpu_launches"] > 0
+    assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    pc = line["parity_check"]
+    assert pc["ok"] is True
+    for v in pc["per_view"].values():
+        assert all(v["integer_stages_bit_exact"].values())
+        assert v["image_max_err"] <= pc["tol"]["image_abs"]
+        assert max(v["grad_max_rel"].values()) <= pc["tol"]["grad_rel"]
