@@ -9,9 +9,10 @@ explicit SH2 Gaussians, 1920x1080, render_mode RGB+ED, 8 seeded cameras (aerial 
 = one view per GPU: rasterization forward, an L1-style loss, backward to the 38 floats of every Gaussian, the
 densification statistics, and for N > 1 the gradient exchange (default: the per-Gaussian backward fused with the
 exchange over NVLink peer memory, csrc/exchange_vjp.cu; `--exchange nccl` = dense NCCL all-reduce).  For N > 1 the
-views follow the cost-bucketed schedule (`--view-schedule bucketed`: a step holds views of one kind, every rank
-renders one aerial and one street view per two steps; `interleaved`: rank r renders view (r + step) mod 8); every
-rank sees every view either way ("weak" scaling: per-GPU work fixed).
+views follow the cost-bucketed schedule where it applies (2 and 4 GPUs; `--view-schedule bucketed`: a step holds views
+of one kind, every rank renders one aerial and one street view per two steps); with 8 GPUs a step is the whole 8-view
+batch, one view per rank (`interleaved`: rank r renders view (r + step) mod 8).  Every rank sees every view either way
+("weak" scaling: per-GPU work fixed).
 `--config 0..3` time the other named configurations (parity-test cases of the contract, measured for completeness):
 0 = 100k / 256x256 (the CPU-runnable case, full frame on both arms), 1 = 1M 3DGS 1080p aerial + street, 2 = 1M 2DGS
 surfels with the normal-consistency loss, 3 = LOD anchor model (500k anchors x 10) through the adapter control flow.
